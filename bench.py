@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the mc3d hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workload (BASELINE.json configs[1]): 8-camera COCO-17 confidence-weighted DLT triangulation of 10 M
+synthetic frames (1.7e8 joints), float storage.  A "step" is one pass of the triangulation kernel over the
+whole batch.  Metric: 3D joints triangulated per second (whole job, all ranks).
+
+  value      inputs resident in HBM, CUDA events on the launch stream, K steps, max over ranks
+  e2e        the same batch through the host-buffer C ABI (mc3d_triangulate_host_f32): pinned host
+             keypoints -> H2D -> kernel -> D2H -> pinned host result, every step
+  roofline   algorithmic bytes per launch (108 B/joint: 8 views x 3 floats in + 3 floats out, SURVEY.md
+             section 8d) / average launch time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the numpy oracle port (batched LAPACK SVD of A^T A, utils.py:19-34 generalised) on the
+             host cores, bounded sample; reported, not the target
+
+One JSON line on stdout (rank 0).  Multi-GPU: frames are sharded across ranks, no data-path collective
+(weak scaling: every rank triangulates its own 10 M frames).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+JOINTS = 17
+WORKLOADS = {
+    # name: (frames per GPU, views, io dtype)
+    'tri8_coco17_10Mframes_f32': (10_000_000, 8, 'f32'),
+    'tri8_coco17_10Mframes_f64': (10_000_000, 8, 'f64'),
+    'tri8_coco17_1Mframes_f32': (1_000_000, 8, 'f32'),
+}
+DEFAULT_WORKLOAD = 'tri8_coco17_10Mframes_f32'
+
+
+def make_triangulation_workload(n_joints, n_views, dtype, device, seed=0):
+    """Synthetic config-2 input generated on the device: ring rig of ``n_views`` cameras, X ~ N(centre, 400 mm),
+    pixels = projection + N(0, 1 px), w ~ U(0.2, 1).  Returns (kpts (n, V, 3) on ``device``, P (V,3,4) numpy)."""
+    import torch
+    from mc3d_b200 import synthetic as syn
+    cams = syn.ring_rig(n_views)
+    P = syn.projection_matrices(cams)
+    gen = torch.Generator(device=device).manual_seed(seed)
+    kp = torch.empty((n_joints, n_views, 3), dtype=dtype, device=device)
+    centre = torch.tensor(syn.SCENE_CENTRE, dtype=torch.float64, device=device)
+    Pt = torch.tensor(P, dtype=torch.float64, device=device)
+    chunk = 1 << 21
+    for lo in range(0, n_joints, chunk):
+        m = min(chunk, n_joints - lo)
+        X = centre + 400.0 * torch.randn((m, 3), dtype=torch.float64, device=device, generator=gen)
+        Xh = torch.cat([X, torch.ones((m, 1), dtype=torch.float64, device=device)], dim=1)
+        proj = torch.einsum('vij,nj->nvi', Pt, Xh)                     # (m, V, 3)
+        uv = proj[..., :2] / proj[..., 2:3] + torch.randn((m, n_views, 2), dtype=torch.float64, device=device,
+                                                          generator=gen)
+        w = 0.2 + 0.8 * torch.rand((m, n_views, 1), dtype=torch.float64, device=device, generator=gen)
+        kp[lo:lo + m] = torch.cat([uv, w], dim=2).to(dtype)
+    return kp, P
+
+
+# ---- clocks ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                clk, mx = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 - 0.1 <= ts <= t1 + 0.3:
+                sm.append(clk)
+                for nm, val in zip(names, parts[3:7]):
+                    if val.lower().startswith('active'):
+                        reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax, 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+# ---- CPU baseline (oracle port) ----------------------------------------------------------------------------
+def _cpu_worker(args):
+    n, n_views, seed, reps = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    from mc3d_b200 import synthetic as syn
+    from oracle import dlt as O
+    kp, P, _, _ = syn.multiview_points(n, n_views, seed=seed)
+    kp = kp.astype(np.float32).astype(np.float64)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.dlt_weighted(kp, P)
+    return n * reps, time.perf_counter() - t0
+
+
+def cpu_baseline_run(n_views, per_worker=100_000, reps=3, workers=None):
+    """Oracle port over all host cores (one process per core, frames split in blocks)."""
+    import multiprocessing as mp
+    workers = workers or (os.cpu_count() or 1)
+    ctx = mp.get_context('spawn')
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        # first map warms the workers (imports) and is not timed
+        pool.map(_cpu_worker, [(256, n_views, 1, 1)] * workers)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(per_worker, n_views, 100 + i, reps) for i in range(workers)])
+        wall = time.perf_counter() - t0
+    joints = sum(r[0] for r in res)
+    return joints / wall, workers, joints, wall
+
+
+def cpu_loop_rate(n_views, n=4000):
+    """The reference's own style: one scipy SVD per joint in a Python loop (utils.py:19-34), one core."""
+    from mc3d_b200 import synthetic as syn
+    from oracle import dlt as O
+    kp, P, _, _ = syn.multiview_points(n, n_views, seed=7)
+    t0 = time.perf_counter()
+    O.dlt_weighted_loop(kp, P)
+    return n / (time.perf_counter() - t0)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            with open(path) as fh:
+                return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def recorded_traffic(workload):
+    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(path):
+        try:
+            with open(path) as fh:
+                return json.load(fh).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+# ---- reference arm ------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    frames, n_views, io = WORKLOADS[args.workload]
+    per_worker = 50_000
+    rates = []
+    workers = os.cpu_count() or 1
+    total = 0
+    t_all = time.perf_counter()
+    for step in range(args.warmup + args.steps):
+        rate, workers, joints, wall = cpu_baseline_run(n_views, per_worker=per_worker, reps=1)
+        if step >= args.warmup:
+            rates.append((joints, wall))
+            total += joints
+    wall = sum(w for _, w in rates)
+    value = total / wall
+    line = {
+        'impl': 'reference', 'metric': 'joints_triangulated_per_sec', 'value': value, 'unit': 'joints/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(1, args.steps),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'views': n_views, 'joints_per_frame': JOINTS,
+                   'frames_per_gpu': frames, 'io_dtype': io,
+                   'note': 'CPU arm: numpy oracle port of the reference DLT (batched LAPACK SVD of A^T A) on a '
+                           f'bounded sample of {per_worker} joints per worker per step'},
+        'cpu_baseline': {'value': value, 'unit': 'joints/s', 'cores': workers, 'kind': 'port',
+                         'sample': f'{per_worker} joints x {workers} workers per step, {args.steps} steps'},
+        'e2e': {'value': value, 'unit': 'joints/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'wall_s': time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import mc3d_b200
+    from mc3d_b200 import _lib
+    from mc3d_b200.triangulation import triangulate_multiview
+
+    torch.cuda.set_device(local_rank)
+    device = f'cuda:{local_rank}'
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(device))
+    frames, n_views, io = WORKLOADS[args.workload]
+    tdtype = torch.float32 if io == 'f32' else torch.float64
+    esize = 4 if io == 'f32' else 8
+    n = frames * JOINTS
+    kp, P = make_triangulation_workload(n, n_views, tdtype, device, seed=1000 + rank)
+    out = torch.empty((n, 3), dtype=tdtype, device=device)
+    algo_bytes_per_joint = (3 * n_views + 3) * esize
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        triangulate_multiview(kp, P, out=out)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = mc3d_b200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = mc3d_b200.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * n * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+    achieved = algo_bytes_per_joint * n / (ms_per_step * 1e-3) / 1e9       # GB/s per GPU (per launch)
+
+    # ---- e2e: host buffers through the C ABI, every step --------------------------------------------------
+    e2e = None
+    try:
+        avail = _mem_available_bytes()
+        need = n * (3 * n_views + 3) * esize
+        local_world = int(os.environ.get('LOCAL_WORLD_SIZE', world))
+        n_e2e = n
+        while n_e2e > (1 << 20) and need * local_world * 2.5 > avail:
+            n_e2e //= 2
+            need = n_e2e * (3 * n_views + 3) * esize
+        h_kp = torch.empty((n_e2e, n_views, 3), dtype=tdtype, pin_memory=True)
+        h_out = torch.empty((n_e2e, 3), dtype=tdtype, pin_memory=True)
+        h_kp.copy_(kp[:n_e2e])
+        torch.cuda.synchronize()
+        kp_np, out_np = h_kp.numpy(), h_out.numpy()
+        e2e_steps = max(2, min(args.steps, 5))
+        triangulate_multiview(kp_np, P, out=out_np, device=local_rank)            # warm-up (allocates the ring)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            triangulate_multiview(kp_np, P, out=out_np, device=local_rank)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        check = bool(np.array_equal(out_np[:4096], out[:4096].cpu().numpy()))
+        e2e = {'value': world * n_e2e * e2e_steps / dt, 'unit': 'joints/s',
+               'h2d_bytes_per_step': int(n_e2e * 3 * n_views * esize), 'd2h_bytes_per_step': int(n_e2e * 3 * esize),
+               'steps': e2e_steps, 'joints_per_step_per_gpu': int(n_e2e), 'ms_per_step': 1e3 * dt / e2e_steps,
+               'matches_device_path': check,
+               'api': 'mc3d_triangulate_host_f32 (pinned host in/out, 3-deep H2D/kernel/D2H pipeline)'
+               if io == 'f32' else 'mc3d_triangulate_host_f64'}
+        del h_kp, h_out
+    except Exception as exc:            # report, do not hide
+        e2e = {'value': None, 'unit': 'joints/s', 'error': repr(exc)}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    line = {
+        'metric': 'joints_triangulated_per_sec', 'value': value, 'unit': 'joints/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'views': n_views, 'joints_per_frame': JOINTS, 'frames_per_gpu': frames,
+                   'joints_per_gpu': n, 'io_dtype': io, 'layout': '(N, V, 3) [x, y, w]', 'mode': 'weighted',
+                   'l2': f'inputs {n * 3 * n_views * esize / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)',
+                   'sharding': 'frames across ranks, no collective'},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': recorded_traffic(args.workload), 'peak_source': peak_src,
+                     'algorithmic_bytes_per_joint': algo_bytes_per_joint, 'kernel': 'mc3d::triangulate_kernel',
+                     'frac_of_nominal_8TBs': achieved / 8000.0},
+        'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        rate, workers, joints, wall = cpu_baseline_run(n_views)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'joints/s', 'cores': workers, 'kind': 'port',
+                                'sample': f'{joints} joints ({joints // workers} per worker x {workers} workers), '
+                                          f'{wall:.1f} s; numpy oracle: batched LAPACK SVD of A^T A',
+                                'reference_style_loop_joints_per_s_1core': cpu_loop_rate(n_views)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _mem_available_bytes():
+    try:
+        with open('/proc/meminfo') as fh:
+            for ln in fh:
+                if ln.startswith('MemAvailable:'):
+                    return int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    return 64 << 30
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', '29531', os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,159 @@
+// Library-level C ABI: errors, device info, launch counter, and the host-buffer pipelines.
+#include "mc3d_common.cuh"
+#include <atomic>
+#include <mutex>
+#include <string.h>
+
+namespace mc3d {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MC3D_ERR_NO_DEVICE : MC3D_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+template <typename T>
+int triangulate_device(const T *d_kpts, long long n, const mc3d_rig *rig, int layout, int mode, int flags, T *d_out,
+                       cudaStream_t stream);
+
+// ---- host-buffer pipeline ------------------------------------------------------------------------
+// Three in-flight chunks, one stream each: H2D(i+1) and D2H(i-1) overlap the kernel of chunk i
+// (PCIe is full duplex, the copy engines run beside the SMs).
+namespace {
+constexpr int NBUF = 3;
+struct HostPipe {
+    int device = -1;
+    cudaStream_t stream[NBUF] = {nullptr, nullptr, nullptr};
+    void *d_in[NBUF] = {nullptr, nullptr, nullptr};
+    void *d_out[NBUF] = {nullptr, nullptr, nullptr};
+    size_t in_bytes = 0, out_bytes = 0;
+};
+std::mutex g_pipe_mutex;
+HostPipe g_pipe;
+
+int ensure_pipe(int device, size_t in_bytes, size_t out_bytes) {
+    MC3D_CUDA_TRY(cudaSetDevice(device));
+    if (g_pipe.device != device) {
+        if (g_pipe.device >= 0) { set_error("host pipeline already bound to device %d", g_pipe.device); return MC3D_ERR_UNSUPPORTED; }
+        for (int b = 0; b < NBUF; ++b) MC3D_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.stream[b], cudaStreamNonBlocking));
+        g_pipe.device = device;
+    }
+    if (in_bytes > g_pipe.in_bytes) {
+        for (int b = 0; b < NBUF; ++b) {
+            if (g_pipe.d_in[b]) MC3D_CUDA_TRY(cudaFree(g_pipe.d_in[b]));
+            g_pipe.d_in[b] = nullptr;
+            MC3D_CUDA_TRY(cudaMalloc(&g_pipe.d_in[b], in_bytes));
+        }
+        g_pipe.in_bytes = in_bytes;
+    }
+    if (out_bytes > g_pipe.out_bytes) {
+        for (int b = 0; b < NBUF; ++b) {
+            if (g_pipe.d_out[b]) MC3D_CUDA_TRY(cudaFree(g_pipe.d_out[b]));
+            g_pipe.d_out[b] = nullptr;
+            MC3D_CUDA_TRY(cudaMalloc(&g_pipe.d_out[b], out_bytes));
+        }
+        g_pipe.out_bytes = out_bytes;
+    }
+    return MC3D_OK;
+}
+}  // namespace
+
+template <typename T>
+int triangulate_host(const T *h_kpts, long long n, const mc3d_rig *rig, int layout, int mode, int flags, T *h_out,
+                     int device) {
+    if (n < 0 || !rig) { set_error("bad arguments"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (n == 0) return MC3D_OK;
+    if (!h_kpts || !h_out) { set_error("NULL host pointer"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (rig->n_views < 2 || rig->n_views > MC3D_MAX_VIEWS) { set_error("n_views=%d out of range", rig->n_views); return MC3D_ERR_INVALID_ARGUMENT; }
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    const size_t row_bytes = (size_t)3 * rig->n_views * sizeof(T);
+    long long chunk = (long long)((64u << 20) / row_bytes) / 256 * 256;     // ~64 MiB of keypoints per chunk
+    if (chunk > n) chunk = (n + 255) / 256 * 256;
+    int st = ensure_pipe(device, (size_t)chunk * row_bytes, (size_t)chunk * 3 * sizeof(T));
+    if (st != MC3D_OK) return st;
+    int b = 0;
+    for (long long off = 0; off < n; off += chunk, b = (b + 1) % NBUF) {
+        const long long m = (n - off < chunk) ? (n - off) : chunk;
+        cudaStream_t s = g_pipe.stream[b];
+        MC3D_CUDA_TRY(cudaMemcpyAsync(g_pipe.d_in[b], h_kpts + off * 3 * rig->n_views, (size_t)m * row_bytes,
+                                      cudaMemcpyHostToDevice, s));
+        st = triangulate_device<T>((const T *)g_pipe.d_in[b], m, rig, layout, mode, flags, (T *)g_pipe.d_out[b], s);
+        if (st != MC3D_OK) return st;
+        MC3D_CUDA_TRY(cudaMemcpyAsync(h_out + off * 3, g_pipe.d_out[b], (size_t)m * 3 * sizeof(T),
+                                      cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < NBUF; ++i) MC3D_CUDA_TRY(cudaStreamSynchronize(g_pipe.stream[i]));
+    return MC3D_OK;
+}
+
+}  // namespace mc3d
+
+extern "C" {
+
+int mc3d_version(void) { return MC3D_VERSION; }
+
+const char *mc3d_last_error(void) { return mc3d::g_err; }
+
+const char *mc3d_status_string(int status) {
+    switch (status) {
+        case MC3D_OK: return "ok";
+        case MC3D_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case MC3D_ERR_MISALIGNED: return "misaligned pointer";
+        case MC3D_ERR_CUDA: return "CUDA error";
+        case MC3D_ERR_NO_DEVICE: return "no CUDA device";
+        case MC3D_ERR_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+int64_t mc3d_launch_count(void) { return mc3d::g_launches.load(); }
+
+int mc3d_device_info(char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor) {
+    int dev = 0;
+    MC3D_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    MC3D_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return MC3D_OK;
+}
+
+int mc3d_triangulate_host_f32(const float *h_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode, int flags,
+                              float *h_out, int device) {
+    return mc3d::triangulate_host<float>(h_kpts, n, rig, layout, mode, flags, h_out, device);
+}
+
+int mc3d_triangulate_host_f64(const double *h_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode, int flags,
+                              double *h_out, int device) {
+    return mc3d::triangulate_host<double>(h_kpts, n, rig, layout, mode, flags, h_out, device);
+}
+
+}  // extern "C"

@@ -1,0 +1,424 @@
+// Batched multi-view DLT triangulation for sm_100a.
+//
+// What it computes (per joint): the eigenvector h of the smallest eigenvalue of B = A^T A, where A
+// stacks, for each view v, the rows  w_v (y_v P_v[2] - P_v[1])  and  w_v (P_v[0] - x_v P_v[2])
+// (reference utils.py:21-28), and returns h[0:3] / h[3] (utils.py:34).  MODE_TOP2 first picks the two
+// highest-score views per joint and undistorts them (pose_estimation.py:35-52, utils.py:1314-1315).
+//
+// How: one thread per joint; a persistent CTA streams 256-joint tiles of the keypoint array through a
+// multi-stage shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier), accumulates the
+// 10 unique entries of B in registers (double), and finds the smallest eigenpair with a secular-equation
+// Newton / Rayleigh-quotient iteration on the (X,1) parametrisation:
+//      (M - lam I) X = -b,   lam <- lam + (c - lam + b.X) / (1 + X.X),      B = [[M, b], [b^T, c]]
+// (cubic convergence, 2 LDL^T solves for ordinary rigs).  Joints where that parametrisation breaks down
+// (pivot loss, no convergence, point at infinity) fall back to a cyclic 4x4 Jacobi eigensolver in
+// registers.  Results leave through a shared-memory tile and a TMA bulk store.
+#include "mc3d_common.cuh"
+#include <math.h>
+
+namespace mc3d {
+
+constexpr int TRI_TILE = 256;          // joints per tile == threads per CTA
+
+struct TriParams {
+    double P[MC3D_MAX_VIEWS][12];
+    double K[MC3D_MAX_VIEWS][9];
+    double dist[MC3D_MAX_VIEWS][5];
+    int n_views;
+    int undistort;
+    int flags;
+    int layout;
+};
+
+// ---- small dense helpers ----------------------------------------------------------------------
+
+// Solve (M) z = r for SPD 3x3 M (lower triangle m00 m10 m11 m20 m21 m22) by LDL^T.
+// Returns false when a pivot is not safely positive.  dmin = smallest pivot.
+__device__ __forceinline__ bool ldl3_solve(double m00, double m10, double m11, double m20, double m21, double m22,
+                                           double r0, double r1, double r2, double &z0, double &z1, double &z2,
+                                           double &dmin) {
+    const double tiny = 1e-13;
+    if (!(m00 > 0.0)) return false;
+    const double i0 = 1.0 / m00;
+    const double l10 = m10 * i0, l20 = m20 * i0;
+    const double d1 = fma(-l10, m10, m11);
+    if (!(d1 > tiny * m11)) return false;
+    const double i1 = 1.0 / d1;
+    const double t21 = fma(-l20, m10, m21);
+    const double l21 = t21 * i1;
+    const double d2 = fma(-l21, t21, fma(-l20, m20, m22));
+    if (!(d2 > tiny * m22)) return false;
+    const double i2 = 1.0 / d2;
+    const double y1 = fma(-l10, r0, r1);
+    const double y2 = fma(-l21, y1, fma(-l20, r0, r2));
+    z2 = y2 * i2;
+    z1 = fma(y1, i1, -l21 * z2);
+    z0 = fma(r0, i0, -fma(l10, z1, l20 * z2));
+    dmin = fmin(m00, fmin(d1, d2));
+    return true;
+}
+
+// Cyclic Jacobi on the symmetric 4x4 B (10 unique entries, order 00 10 11 20 21 22 30 31 32 33);
+// returns the eigenvector of the smallest eigenvalue de-homogenised.  Fallback path: kept out of line.
+__device__ __noinline__ void jacobi4_smallest(const double *Bsym, double &X0, double &X1, double &X2) {
+    double a[4][4], v[4][4];
+    a[0][0] = Bsym[0];
+    a[1][0] = a[0][1] = Bsym[1];
+    a[1][1] = Bsym[2];
+    a[2][0] = a[0][2] = Bsym[3];
+    a[2][1] = a[1][2] = Bsym[4];
+    a[2][2] = Bsym[5];
+    a[3][0] = a[0][3] = Bsym[6];
+    a[3][1] = a[1][3] = Bsym[7];
+    a[3][2] = a[2][3] = Bsym[8];
+    a[3][3] = Bsym[9];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        bool done = true;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = a[p][q];
+                // relative criterion suits graded positive semi-definite matrices
+                if (!(fabs(apq) > 1e-17 * sqrt(fabs(a[p][p] * a[q][q])) && apq != 0.0)) continue;
+                done = false;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+                const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                const double c = rsqrt(fma(t, t, 1.0));
+                const double s = t * c;
+                a[p][p] = fma(-t, apq, a[p][p]);
+                a[q][q] = fma(t, apq, a[q][q]);
+                a[p][q] = a[q][p] = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k != p && k != q) {
+                        const double akp = a[k][p], akq = a[k][q];
+                        a[k][p] = a[p][k] = fma(c, akp, -s * akq);
+                        a[k][q] = a[q][k] = fma(s, akp, c * akq);
+                    }
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = fma(c, vkp, -s * vkq);
+                    v[k][q] = fma(s, vkp, c * vkq);
+                }
+            }
+        }
+        if (done) break;
+    }
+    int best = 0;
+    double ev = a[0][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (a[i][i] < ev) { ev = a[i][i]; best = i; }
+    double h0 = v[0][0], h1 = v[1][0], h2 = v[2][0], h3 = v[3][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (best == i) { h0 = v[0][i]; h1 = v[1][i]; h2 = v[2][i]; h3 = v[3][i]; }
+    const double inv = 1.0 / h3;
+    X0 = h0 * inv;
+    X1 = h1 * inv;
+    X2 = h2 * inv;
+}
+
+// Smallest eigenpair of B via secular Newton; false -> caller should use Jacobi.
+__device__ __forceinline__ bool secular_newton(const double *B, double &X0, double &X1, double &X2) {
+    const double m00 = B[0], m10 = B[1], m11 = B[2], m20 = B[3], m21 = B[4], m22 = B[5];
+    const double b0 = B[6], b1 = B[7], b2 = B[8], c = B[9];
+    double lam = 0.0;
+#pragma unroll 1
+    for (int it = 0; it < 12; ++it) {
+        double z0, z1, z2, dmin;
+        if (!ldl3_solve(m00 - lam, m10, m11 - lam, m20, m21, m22 - lam, -b0, -b1, -b2, z0, z1, z2, dmin)) return false;
+        const double f = (c - lam) + fma(b0, z0, fma(b1, z1, b2 * z2));
+        const double dl = f / (1.0 + fma(z0, z0, fma(z1, z1, z2 * z2)));
+        X0 = z0; X1 = z1; X2 = z2;
+        if (!(fabs(dl) <= 1.0e300)) return false;            // NaN / inf
+        if (fabs(dl) <= 1e-13 * dmin) return true;            // X solved with lam accurate to |dl|
+        lam += dl;
+    }
+    return false;
+}
+
+// cv.undistortPoints(pt, K, dist, None, K): 5 fixed-point iterations then re-projection with K.
+__device__ __forceinline__ void undistort_px(double &u, double &v, const double *K, const double *d) {
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const double k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4];
+    const double x0 = (u - cx) / fx, y0 = (v - cy) / fy;
+    double x = x0, y = y0;
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = fma(x, x, y * y);
+        const double icdist = 1.0 / fma(fma(fma(k3, r2, k2), r2, k1), r2, 1.0);
+        if (icdist < 0.0) { x = x0; y = y0; break; }
+        const double dx = fma(2.0 * p1 * x, y, p2 * fma(2.0 * x, x, r2));
+        const double dy = fma(p1, fma(2.0 * y, y, r2), 2.0 * p2 * x * y);
+        x = (x0 - dx) * icdist;
+        y = (y0 - dy) * icdist;
+    }
+    const double ww = 1.0 / fma(K[6], x, fma(K[7], y, K[8]));
+    u = fma(K[0], x, fma(K[1], y, K[2])) * ww;
+    v = fma(K[3], x, fma(K[4], y, K[5])) * ww;
+}
+
+__device__ __forceinline__ void accumulate_view(double *B, double x, double y, double w, const double *p) {
+    const double wy = w * y, wx = w * x;
+    double a[4], c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a[k] = fma(wy, p[8 + k], -(w * p[4 + k]));
+        c[k] = fma(-wx, p[8 + k], w * p[k]);
+    }
+    B[0] = fma(a[0], a[0], fma(c[0], c[0], B[0]));
+    B[1] = fma(a[1], a[0], fma(c[1], c[0], B[1]));
+    B[2] = fma(a[1], a[1], fma(c[1], c[1], B[2]));
+    B[3] = fma(a[2], a[0], fma(c[2], c[0], B[3]));
+    B[4] = fma(a[2], a[1], fma(c[2], c[1], B[4]));
+    B[5] = fma(a[2], a[2], fma(c[2], c[2], B[5]));
+    B[6] = fma(a[3], a[0], fma(c[3], c[0], B[6]));
+    B[7] = fma(a[3], a[1], fma(c[3], c[1], B[7]));
+    B[8] = fma(a[3], a[2], fma(c[3], c[2], B[8]));
+    B[9] = fma(a[3], a[3], fma(c[3], c[3], B[9]));
+}
+
+// ---- kernel -----------------------------------------------------------------------------------
+// V > 0: number of views known at compile time (fully unrolled); V == 0: runtime prm.n_views.
+template <typename T, int V, int MODE>
+__global__ void __launch_bounds__(TRI_TILE, 2)
+triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n, int n_stages,
+                   const __grid_constant__ TriParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nv = (V > 0) ? V : prm.n_views;
+    const int row_elems = 3 * nv;
+    const uint32_t stage_bytes = (uint32_t)(TRI_TILE * row_elems * sizeof(T));
+    // layout: [n_stages][TILE*row] input ring | [2][TILE*3] output tiles | mbarriers | (TOP2) camera tables
+    T *ring = reinterpret_cast<T *>(smem_raw);
+    T *otile = reinterpret_cast<T *>(smem_raw + (size_t)n_stages * stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + 2 * TRI_TILE * 3 * sizeof(T));
+    double *cam = reinterpret_cast<double *>(full + 8);       // TOP2 only: [V][12+9+5]
+
+    const int tid = threadIdx.x;
+    const long long n_tiles = (n + TRI_TILE - 1) / TRI_TILE;
+    const long long first = blockIdx.x;
+    const long long stride = gridDim.x;
+    const long long my_tiles = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    if (MODE == MC3D_TRI_TOP2) {
+        for (int i = tid; i < nv * 26; i += TRI_TILE) {
+            const int v = i / 26, k = i % 26;
+            cam[i] = (k < 12) ? prm.P[v][k] : (k < 21 ? prm.K[v][k - 12] : prm.dist[v][k - 21]);
+        }
+    }
+    __syncthreads();
+
+    auto tile_is_full = [&](long long tile) { return (tile + 1) * TRI_TILE <= n; };
+    auto issue_load = [&](long long k) {   // thread 0 only
+        const long long tile = first + k * stride;
+        if (k < my_tiles && tile_is_full(tile)) {
+            const int s = (int)(k % n_stages);
+            mbar_arrive_expect_tx(&full[s], stage_bytes);
+            bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes,
+                     kpts + tile * TRI_TILE * (long long)row_elems, stage_bytes, &full[s]);
+        }
+    };
+    if (tid == 0)
+        for (int k = 0; k < n_stages - 1; ++k) issue_load(k);
+
+    for (long long k = 0; k < my_tiles; ++k) {
+        const long long tile = first + k * stride;
+        const int s = (int)(k % n_stages);
+        const uint32_t parity = (uint32_t)((k / n_stages) & 1);
+        const bool full_tile = tile_is_full(tile);
+        T *stage = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes);
+        if (tid == 0) {
+            issue_load(k + n_stages - 1);     // refills the stage consumed in iteration k-1
+            bulk_wait_read<1>();              // output tile (k&1) of iteration k-2 has left shared memory
+        }
+        const long long joint = tile * TRI_TILE + tid;
+        const bool active = joint < n;
+        if (full_tile) {
+            mbar_wait(&full[s], parity);
+        } else {                               // ragged last tile: plain cooperative copy
+            const long long base = tile * TRI_TILE * (long long)row_elems;
+            const long long cnt = (n - tile * TRI_TILE) * row_elems;
+            for (long long i = tid; i < cnt; i += TRI_TILE) stage[i] = kpts[base + i];
+            __syncthreads();
+        }
+
+        double B[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) B[i] = 0.0;
+        int n_used = 0;
+        bool finite_in = true;
+        if (active) {
+            const T *row = stage + (size_t)tid * row_elems;
+            const bool l3v = prm.layout == MC3D_LAYOUT_3V;
+            if (MODE == MC3D_TRI_WEIGHTED) {
+#pragma unroll
+                for (int v = 0; v < ((V > 0) ? V : MC3D_MAX_VIEWS); ++v) {
+                    if (V == 0 && v >= nv) break;
+                    double x = (double)(l3v ? row[v] : row[3 * v]);
+                    double y = (double)(l3v ? row[nv + v] : row[3 * v + 1]);
+                    const double w = (double)(l3v ? row[2 * nv + v] : row[3 * v + 2]);
+                    if (prm.undistort) undistort_px(x, y, prm.K[v], prm.dist[v]);
+                    finite_in = finite_in && (fabs(x) <= 1.0e300) && (fabs(y) <= 1.0e300) && (fabs(w) <= 1.0e300);
+                    n_used += (w != 0.0);
+                    accumulate_view(B, x, y, w, prm.P[v]);
+                }
+            } else {
+                // two highest scores; np.argsort(conf)[-2:] semantics: ties -> higher index, NaN sorts last
+                int i1 = -1, i0 = -1;
+                double k1 = 0.0, k0 = 0.0;
+                for (int v = 0; v < nv; ++v) {
+                    double sc = (double)(l3v ? row[2 * nv + v] : row[3 * v + 2]);
+                    if (sc != sc) sc = INFINITY;
+                    if (i1 < 0 || sc >= k1) { i0 = i1; k0 = k1; i1 = v; k1 = sc; }
+                    else if (i0 < 0 || sc >= k0) { i0 = v; k0 = sc; }
+                }
+                const int sel[2] = {i0, i1};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int v = sel[q];
+                    double x = (double)(l3v ? row[v] : row[3 * v]);
+                    double y = (double)(l3v ? row[nv + v] : row[3 * v + 1]);
+                    const double *cv = cam + v * 26;
+                    if (prm.undistort) undistort_px(x, y, cv + 12, cv + 21);
+                    finite_in = finite_in && (fabs(x) <= 1.0e300) && (fabs(y) <= 1.0e300);
+                    accumulate_view(B, x, y, 1.0, cv);
+                }
+                n_used = 2;
+            }
+        }
+        __syncthreads();                       // [A] every thread has consumed stage s
+
+        double X0 = NAN, X1 = NAN, X2 = NAN;
+        if (active && finite_in && n_used >= 2) {
+            bool ok = false;
+            if (!(prm.flags & MC3D_TRI_FLAG_JACOBI)) ok = secular_newton(B, X0, X1, X2);
+            if (!ok) jacobi4_smallest(B, X0, X1, X2);
+        }
+
+        T *ot = otile + (size_t)(k & 1) * TRI_TILE * 3;
+        if (full_tile) {
+            ot[tid * 3 + 0] = (T)X0;
+            ot[tid * 3 + 1] = (T)X1;
+            ot[tid * 3 + 2] = (T)X2;
+            fence_proxy_async_smem();
+            __syncthreads();                   // [B] tile complete and visible to the async proxy
+            if (tid == 0) {
+                bulk_s2g(out + tile * TRI_TILE * 3, ot, (uint32_t)(TRI_TILE * 3 * sizeof(T)));
+                bulk_commit();
+            }
+        } else {
+            if (active) {
+                out[joint * 3 + 0] = (T)X0;
+                out[joint * 3 + 1] = (T)X1;
+                out[joint * 3 + 2] = (T)X2;
+            }
+            if (tid == 0) bulk_commit();       // keep one group per iteration for wait_group accounting
+        }
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+
+// ---- host side --------------------------------------------------------------------------------
+static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode, int flags) {
+    if (!rig || !rig->P) { set_error("rig / rig->P is NULL"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (rig->n_views < 2 || rig->n_views > MC3D_MAX_VIEWS) {
+        set_error("n_views=%d outside [2, %d]", rig->n_views, MC3D_MAX_VIEWS);
+        return MC3D_ERR_INVALID_ARGUMENT;
+    }
+    if (layout != MC3D_LAYOUT_V3 && layout != MC3D_LAYOUT_3V) { set_error("bad layout %d", layout); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (mode != MC3D_TRI_WEIGHTED && mode != MC3D_TRI_TOP2) { set_error("bad mode %d", mode); return MC3D_ERR_INVALID_ARGUMENT; }
+    if ((rig->K == nullptr) != (rig->dist == nullptr)) {
+        set_error("rig->K and rig->dist must both be given or both be NULL");
+        return MC3D_ERR_INVALID_ARGUMENT;
+    }
+    memset(&prm, 0, sizeof(prm));
+    prm.n_views = rig->n_views;
+    prm.undistort = rig->K != nullptr;
+    prm.flags = flags;
+    prm.layout = layout;
+    for (int v = 0; v < rig->n_views; ++v) {
+        for (int k = 0; k < 12; ++k) prm.P[v][k] = rig->P[v * 12 + k];
+        if (rig->K) {
+            for (int k = 0; k < 9; ++k) prm.K[v][k] = rig->K[v * 9 + k];
+            for (int k = 0; k < 5; ++k) prm.dist[v][k] = rig->dist[v * 5 + k];
+        }
+    }
+    return MC3D_OK;
+}
+
+template <typename T, int V, int MODE>
+static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_out, cudaStream_t stream) {
+    const int nv = prm.n_views;
+    const size_t stage_bytes = (size_t)TRI_TILE * 3 * nv * sizeof(T);
+    int n_stages = stage_bytes <= 32 * 1024 ? 3 : 2;
+    const size_t smem = n_stages * stage_bytes + 2 * TRI_TILE * 3 * sizeof(T) + 8 * sizeof(uint64_t) +
+                        (MODE == MC3D_TRI_TOP2 ? (size_t)nv * 26 * sizeof(double) : 0);
+    auto kern = triangulate_kernel<T, V, MODE>;
+    static bool attr_done = false;     // per instantiation
+    if (!attr_done) {
+        MC3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    int per_sm = 0;
+    MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRI_TILE, smem));
+    if (per_sm < 1) { set_error("triangulate kernel does not fit: smem=%zu", smem); return MC3D_ERR_UNSUPPORTED; }
+    const long long n_tiles = (n + TRI_TILE - 1) / TRI_TILE;
+    long long grid = (long long)sm_count() * per_sm;      // persistent: a whole number of waves
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<(unsigned)grid, TRI_TILE, smem, stream>>>(d_kpts, d_out, n, n_stages, prm);
+    count_launch();
+    MC3D_CUDA_TRY(cudaGetLastError());
+    return MC3D_OK;
+}
+
+template <typename T>
+int triangulate_device(const T *d_kpts, long long n, const mc3d_rig *rig, int layout, int mode, int flags, T *d_out,
+                       cudaStream_t stream) {
+    TriParams prm;
+    int st = fill_params(prm, rig, layout, mode, flags);
+    if (st != MC3D_OK) return st;
+    if (n < 0) { set_error("n=%lld < 0", n); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (n == 0) return MC3D_OK;
+    if (!d_kpts || !d_out) { set_error("NULL device pointer"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (!aligned16(d_kpts) || !aligned16(d_out)) {
+        set_error("device pointers must be 16-byte aligned (kpts=%p out=%p)", (const void *)d_kpts, (void *)d_out);
+        return MC3D_ERR_MISALIGNED;
+    }
+    if (mode == MC3D_TRI_TOP2) return launch_one<T, 0, MC3D_TRI_TOP2>(d_kpts, n, prm, d_out, stream);
+    switch (prm.n_views) {
+        case 2: return launch_one<T, 2, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
+        case 3: return launch_one<T, 3, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
+        case 4: return launch_one<T, 4, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
+        case 8: return launch_one<T, 8, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
+        case 16: return launch_one<T, 16, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
+        default: return launch_one<T, 0, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
+    }
+}
+
+template int triangulate_device<float>(const float *, long long, const mc3d_rig *, int, int, int, float *, cudaStream_t);
+template int triangulate_device<double>(const double *, long long, const mc3d_rig *, int, int, int, double *, cudaStream_t);
+
+}  // namespace mc3d
+
+extern "C" {
+
+int mc3d_triangulate_f32(const float *d_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode, int flags,
+                         float *d_out, void *stream) {
+    return mc3d::triangulate_device<float>(d_kpts, n, rig, layout, mode, flags, d_out, (cudaStream_t)stream);
+}
+
+int mc3d_triangulate_f64(const double *d_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode, int flags,
+                         double *d_out, void *stream) {
+    return mc3d::triangulate_device<double>(d_kpts, n, rig, layout, mode, flags, d_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

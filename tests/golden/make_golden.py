@@ -1,0 +1,197 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in the build container.
+
+Usage (build container only; /root/reference does not exist on the GPU box):
+    python tests/golden/make_golden.py [--reference /root/reference]
+
+The reference is imported as-is with harmless ``sys.modules`` stubs for imports the
+hot path never touches (matplotlib -- pose_refinement.py:367 ``import
+matplotlib.pyplot`` -- and mmpose/tqdm -- mmpose_pose_estimation.py:5-8).  Inputs come
+from ``multi-camera_3d_pose_estimation_b200/synthetic.py`` with fixed seeds; only
+inputs, outputs and library versions are stored.  No reference source is copied.
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def import_reference(ref_dir):
+    for name in ['matplotlib', 'matplotlib.pyplot', 'matplotlib.animation', 'mmpose', 'mmpose.apis',
+                 'mmpose.structures', 'mmpose.utils', 'mmpose.evaluation', 'mmpose.evaluation.functional',
+                 'mmdet', 'mmdet.apis']:
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    sys.modules['mmpose.apis'].inference_topdown = None
+    sys.modules['mmpose.apis'].init_model = None
+    sys.modules['mmpose.structures'].merge_data_samples = None
+    sys.modules['mmpose.utils'].adapt_mmdet_pipeline = None
+    sys.modules['mmpose.evaluation.functional'].nms = None
+    sys.path.insert(0, ref_dir)
+    import utils as ref_utils
+    import pose_refinement as ref_refine
+    import mmpose_pose_estimation as ref_mm
+    import pose_estimation as ref_pe
+    return ref_utils, ref_refine, ref_mm, ref_pe
+
+
+def versions():
+    import cv2
+    import scipy
+    import torch
+    return np.array([f'numpy {np.__version__}', f'scipy {scipy.__version__}', f'cv2 {cv2.__version__}',
+                     f'torch {torch.__version__}'])
+
+
+def golden_dlt(ref_utils, syn, out):
+    import cv2 as cv
+    rng = np.random.default_rng(11)
+    cams = syn.stereo_rig(distortion=True)
+    X = syn.smooth_trajectory(8, 17, rng, centre=(0, 0, 3000.0))
+    kp = syn.keypoints_from_trajectory(X, cams, rng)               # (8,17,3,2)
+    P = syn.projection_matrices(cams)
+    pts = kp[:, :, :2, :].reshape(-1, 2, 2)                        # (N, xy, cam)
+    dlt = np.array([ref_utils.DLT(P[0], P[1], p[:, 0], p[:, 1]) for p in pts])
+    pair = np.ascontiguousarray(np.transpose(pts, (0, 2, 1)))      # (N, cam, xy)
+    c0, c1 = cams[0], cams[1]
+    tri = ref_utils.triangulate_points(pair.reshape(8, 17, 2, 2), c0[0], c0[3], c0[1], c0[2],
+                                       c1[0], c1[3], c1[1], c1[2])
+    und0 = cv.undistortPoints(pair[:, 0, :][:, None, :], c0[0], c0[3], None, c0[0])[:, 0, :]
+    und1 = cv.undistortPoints(pair[:, 1, :][:, None, :], c1[0], c1[3], None, c1[0])[:, 0, :]
+    np.savez(os.path.join(out, 'dlt_stereo.npz'), P=P, pts=pts, dlt=dlt, pair=pair, tri=tri,
+             und0=und0, und1=und1, versions=versions(),
+             **{f'cam{i}_{n}': np.asarray(cams[i][k]) for i in cams for k, n in enumerate(['K', 'R', 'T', 'dist'])})
+
+
+def golden_pose3d(ref_pe, syn, out):
+    rng = np.random.default_rng(12)
+    for n_cams, tag in [(2, 'c2'), (3, 'c3')]:
+        cams = syn.stereo_rig() if n_cams == 2 else syn.ring_rig(3, distortion=True)
+        centre = (0, 0, 3000.0)
+        X = syn.smooth_trajectory(6, 17, rng, centre=centre)
+        kp = syn.keypoints_from_trajectory(X, cams, rng)
+        cam_params = {i: [np.asarray(a) for a in cams[i]] for i in cams}
+        with contextlib.redirect_stdout(io.StringIO()):
+            p3d = ref_pe.get_pose_3D(cam_params, list(kp))
+            p3d_nod = ref_pe.get_pose_3D(cam_params, list(kp), ignore_nonlinear_distortions=True)
+            Rw = syn._look_at(np.array([100.0, 50.0, -500.0]))[0]
+            p3d_w = ref_pe.get_pose_3D(cam_params, list(kp), world_trans_rot=(Rw, np.zeros(3)))
+        np.savez(os.path.join(out, f'pose3d_{tag}.npz'), kpts=kp, p3d=p3d, p3d_nodist=p3d_nod, p3d_world=p3d_w,
+                 Rw=Rw, versions=versions(),
+                 **{f'cam{i}_{n}': np.asarray(cams[i][k]) for i in cams
+                    for k, n in enumerate(['K', 'R', 'T', 'dist'])})
+
+
+def golden_moments(ref_mm, syn, out):
+    import torch
+    hm, _ = syn.gaussian_blob_heatmaps(17, seed=13)
+    hm[5] = 0.004                       # below threshold everywhere -> six zeros (:191-193)
+    hm[6, :, :] = 0.0
+    hm[6, 10, 7] = 0.7                  # single pixel
+    moments_np = ref_mm.PoseEstimator.get_heatmap_means_cov(None, hm.copy())
+    moments_t = ref_mm.PoseEstimator.get_heatmap_means_cov(None, torch.tensor(hm.copy()))
+    means, stds = ref_mm.PoseEstimator.get_heatmap_means_stds(torch.tensor(np.where(hm < 0.01, 0, hm)))
+    np.savez(os.path.join(out, 'heatmap_moments.npz'), heatmaps=hm, moments=moments_np, moments_torch_in=moments_t,
+             means=np.array(means), stds=np.array(stds), versions=versions())
+
+
+def golden_refine(ref_refine, ref_utils, syn, out):
+    import torch
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    g, init, cams, _ = syn.refinement_inputs(48, n_cams=2, seed=14)
+    # a NaN joint in the initial trajectory exercises nan_mean masking (pose_refinement.py:221-229)
+    lengths = dict(syn.EXAMPLE_BODY_LENGTHS)
+    store = dict(gaussians=g, init=init, versions=versions(),
+                 **{f'cam{i}_{n}': np.asarray(cams[i][k]) for i in cams
+                    for k, n in enumerate(['K', 'R', 'T', 'dist'])})
+    # projection
+    for tag, dt in [('f32', torch.float32), ('f64', torch.float64)]:
+        for i in cams:
+            K, R, T, dist = cams[i]
+            pr = ref_refine.project_points_torch(init, K, R, T, dist, torch_dtype=dt)
+            store[f'proj_{tag}_cam{i}'] = pr.numpy()
+            pr = ref_refine.project_points_torch(init, K, R, T, dist, torch_dtype=dt, ignore_distortions=True)
+            store[f'proj_nodist_{tag}_cam{i}'] = pr.numpy()
+    # optimisation runs
+    runs = {
+        'readme': dict(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, patience=100, max_iter=60,
+                       time_interval=[0, 40]),
+        'defaults': dict(max_iter=25),
+        'stop': dict(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, patience=3, tolerance=1e-1, max_iter=200,
+                     time_interval=[0, 48]),
+        'nodist': dict(lr=0.005, lambda_smooth=0.5, lambda_body_length=0, max_iter=20, ignore_distortions=True,
+                       time_interval=[4, 44]),
+    }
+    for tag, dt in [('f32', torch.float32), ('f64', torch.float64)]:
+        for rname, kw in runs.items():
+            cam_params = {i: [np.asarray(a).copy() for a in cams[i]] for i in cams}
+            with contextlib.redirect_stdout(io.StringIO()):
+                opt = ref_refine.Optimized_3d_Pose_Estimation(g.copy(), init.copy(),
+                                                              decomposed_cam_params_initial=cam_params,
+                                                              body_lengths=lengths, torch_dtype=dt)
+                kwargs = ref_utils.prepare_kwargs(opt.sgd_optimize, kw)
+                opt.sgd_optimize(**kwargs)
+            key = f'run_{rname}_{tag}'
+            for cname, hist in opt.all_costs_total.items():
+                store[f'{key}_{cname}'] = np.array([float(h) for h in hist], dtype=np.float64)
+            store[f'{key}_best'] = opt.best_trajectory.numpy()
+            store[f'{key}_final'] = opt.trajectory.detach().numpy()
+    # NaN-masked variant: one joint-frame of the initial trajectory is NaN
+    init_nan = init.copy()
+    init_nan[7, 3, :] = np.nan
+    cam_params = {i: [np.asarray(a).copy() for a in cams[i]] for i in cams}
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt = ref_refine.Optimized_3d_Pose_Estimation(g.copy(), init_nan.copy(),
+                                                      decomposed_cam_params_initial=cam_params,
+                                                      body_lengths=lengths, torch_dtype=torch.float64)
+        # The reference masks non-finite entries in the FORWARD value (nan_mean) but autograd still
+        # propagates NaN into the gradient, the clip turns every gradient NaN, and iteration 1 dies
+        # with KeyError at pose_refinement.py:1053.  Only the iteration-0 costs are defined.
+        try:
+            opt.sgd_optimize(lr=0.01, lambda_smooth=1e-6, lambda_body_length=0, max_iter=5, time_interval=[0, 40])
+            store['run_nan_f64_raised'] = np.array('none')
+        except KeyError as e:
+            store['run_nan_f64_raised'] = np.array(f'KeyError {e}')
+    for cname, hist in opt.all_costs_total.items():
+        store[f'run_nan_f64_iter0_{cname}'] = np.array(float(hist[0]) if len(hist) else np.nan)
+    store['init_nan'] = init_nan
+    np.savez(os.path.join(out, 'refine_T48.npz'), **store)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--reference', default='/root/reference')
+    ap.add_argument('--only', nargs='*', default=None)
+    args = ap.parse_args()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        'mc3d_synthetic', os.path.join(ROOT, 'multi-camera_3d_pose_estimation_b200', 'synthetic.py'))
+    syn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(syn)
+    ref_utils, ref_refine, ref_mm, ref_pe = import_reference(args.reference)
+    todo = args.only or ['dlt', 'pose3d', 'moments', 'refine']
+    if 'dlt' in todo:
+        golden_dlt(ref_utils, syn, HERE)
+    if 'pose3d' in todo:
+        golden_pose3d(ref_pe, syn, HERE)
+    if 'moments' in todo:
+        golden_moments(ref_mm, syn, HERE)
+    if 'refine' in todo:
+        golden_refine(ref_refine, ref_utils, syn, HERE)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(HERE, f)), 'bytes')
+
+
+if __name__ == '__main__':
+    main()
