@@ -101,6 +101,31 @@ int mc3d_triangulate_host_f32(const float *h_kpts, int64_t n, const mc3d_rig *ri
 int mc3d_triangulate_host_f64(const double *h_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode,
                               int flags, double *h_out, int device);
 
+
+/* ---- 2. heatmap decode ----------------------------------------------------------------------
+ * d_heatmaps: n_maps x H x W floats.  Per map, in one pass over HBM:
+ *   d_kpt     [x, y, score]: flat argmax (first maximum), +-0.25 px towards the larger neighbour,
+ *             (-1,-1) when the maximum is <= 0 -- the mmpose MSRA decode behind
+ *             mmpose_pose_estimation.py:253-259 (third-party upstream; parity unpinned, see
+ *             oracle/decode.py); optional affine x*a0+a2, y*a1+a3 per `affine_group` maps.
+ *   d_moments [mean_x, mean_y, var_x, cov_xy, cov_xy, var_y] of the map with values < threshold
+ *             zeroed (0.01 upstream), six zeros for an all-zero map: get_heatmap_means_cov,
+ *             mmpose_pose_estimation.py:163-215.
+ * Either output may be NULL.  kpt_layout PLAIN writes d_kpt[map*3..]; NV3 / N3V read the map index
+ * as (t, view, joint) -- the reference's heatmap order (T, C, J), pose_estimation.py:110,190 -- and
+ * write the keypoint where the triangulation kernel expects it: (T*J, V, 3) or (T*J, 3, V). */
+typedef enum { MC3D_KPT_PLAIN = 0, MC3D_KPT_NV3 = 1, MC3D_KPT_N3V = 2 } mc3d_kpt_layout;
+enum {
+    MC3D_DECODE_FLAG_WRITE_BACK = 1,  /* also store the thresholded maps in place (upstream mutates its input) */
+    MC3D_DECODE_FLAG_GENERIC = 2      /* force the non-TMA kernel (test hook) */
+};
+int mc3d_decode_heatmaps_f32(const float *d_heatmaps, int64_t n_maps, int H, int W, float threshold, int flags,
+                             int kpt_layout, int views, int joints, const float *d_affine, int affine_group,
+                             float *d_kpt, double *d_moments, void *stream);
+/* Host-buffer variant (PLAIN layout, no affine): chunked H2D -> kernel -> D2H. */
+int mc3d_decode_heatmaps_host_f32(const float *h_heatmaps, int64_t n_maps, int H, int W, float threshold,
+                                  float *h_kpt, double *h_moments, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,9 @@ LAYOUT_3V = 1      # (N, 3, V)  -- the reference's kpts_2d (T, J, 3, C)
 TRI_WEIGHTED = 0
 TRI_TOP2 = 1
 TRI_FLAG_JACOBI = 1
+KPT_PLAIN, KPT_NV3, KPT_N3V = 0, 1, 2
+DECODE_FLAG_WRITE_BACK = 1
+DECODE_FLAG_GENERIC = 2
 
 
 class Mc3dError(RuntimeError):
@@ -51,6 +54,9 @@ SIGNATURES = {
     'mc3d_triangulate_f64': (_c_int, [_c_vp, _c_i64, ctypes.POINTER(Rig), _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     'mc3d_triangulate_host_f32': (_c_int, [_c_vp, _c_i64, ctypes.POINTER(Rig), _c_int, _c_int, _c_int, _c_vp, _c_int]),
     'mc3d_triangulate_host_f64': (_c_int, [_c_vp, _c_i64, ctypes.POINTER(Rig), _c_int, _c_int, _c_int, _c_vp, _c_int]),
+    'mc3d_decode_heatmaps_f32': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, ctypes.c_float, _c_int, _c_int, _c_int, _c_int,
+                                          _c_vp, _c_int, _c_vp, _c_vp, _c_vp]),
+    'mc3d_decode_heatmaps_host_f32': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, ctypes.c_float, _c_vp, _c_vp, _c_int]),
 }
 
 

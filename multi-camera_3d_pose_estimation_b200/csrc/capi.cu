@@ -38,6 +38,9 @@ int sm_count() {
 template <typename T>
 int triangulate_device(const T *d_kpts, long long n, const mc3d_rig *rig, int layout, int mode, int flags, T *d_out,
                        cudaStream_t stream);
+int decode_device(const float *d_hm, long long n_maps, int H, int W, float thr, int flags, int kpt_layout, int views,
+                  int joints, const float *d_affine, int affine_group, float *d_kpt, double *d_moments,
+                  cudaStream_t stream);
 
 // ---- host-buffer pipeline ------------------------------------------------------------------------
 // Three in-flight chunks, one stream each: H2D(i+1) and D2H(i-1) overlap the kernel of chunk i
@@ -109,9 +112,44 @@ int triangulate_host(const T *h_kpts, long long n, const mc3d_rig *rig, int layo
     return MC3D_OK;
 }
 
+int decode_host(const float *h_hm, long long n_maps, int H, int W, float thr, float *h_kpt, double *h_moments,
+                int device) {
+    if (n_maps < 0 || H <= 0 || W <= 0) { set_error("bad heatmap shape"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (n_maps == 0) return MC3D_OK;
+    if (!h_hm || (!h_kpt && !h_moments)) { set_error("NULL host pointer"); return MC3D_ERR_INVALID_ARGUMENT; }
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    const size_t map_bytes = (size_t)H * W * sizeof(float);
+    long long chunk = (long long)((64u << 20) / map_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_maps) chunk = n_maps;
+    const size_t kpt_bytes = ((size_t)chunk * 3 * sizeof(float) + 255) / 256 * 256;   // moments start 256-B aligned
+    int st = ensure_pipe(device, (size_t)chunk * map_bytes, kpt_bytes + (size_t)chunk * 6 * sizeof(double));
+    if (st != MC3D_OK) return st;
+    int b = 0;
+    for (long long off = 0; off < n_maps; off += chunk, b = (b + 1) % NBUF) {
+        const long long m = (n_maps - off < chunk) ? (n_maps - off) : chunk;
+        cudaStream_t s = g_pipe.stream[b];
+        float *d_kpt = (float *)g_pipe.d_out[b];
+        double *d_mom = (double *)((char *)g_pipe.d_out[b] + kpt_bytes);
+        MC3D_CUDA_TRY(cudaMemcpyAsync(g_pipe.d_in[b], h_hm + off * H * W, (size_t)m * map_bytes, cudaMemcpyHostToDevice, s));
+        st = decode_device((const float *)g_pipe.d_in[b], m, H, W, thr, 0, MC3D_KPT_PLAIN, 0, 0, nullptr, 0,
+                           h_kpt ? d_kpt : nullptr, h_moments ? d_mom : nullptr, s);
+        if (st != MC3D_OK) return st;
+        if (h_kpt) MC3D_CUDA_TRY(cudaMemcpyAsync(h_kpt + off * 3, d_kpt, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_moments) MC3D_CUDA_TRY(cudaMemcpyAsync(h_moments + off * 6, d_mom, (size_t)m * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < NBUF; ++i) MC3D_CUDA_TRY(cudaStreamSynchronize(g_pipe.stream[i]));
+    return MC3D_OK;
+}
+
 }  // namespace mc3d
 
 extern "C" {
+
+int mc3d_decode_heatmaps_host_f32(const float *h_heatmaps, int64_t n_maps, int H, int W, float threshold,
+                                  float *h_kpt, double *h_moments, int device) {
+    return mc3d::decode_host(h_heatmaps, n_maps, H, W, threshold, h_kpt, h_moments, device);
+}
 
 int mc3d_version(void) { return MC3D_VERSION; }
 

@@ -1,0 +1,307 @@
+// Heatmap -> (keypoint, score) + Gaussian moments, one pass over HBM, for sm_100a.
+//
+// Per heatmap (H x W floats):
+//   * argmax (first maximum), score = max, quarter-pixel shift towards the larger neighbour
+//     (the mmpose MSRA decode the reference gets from mmpose_pose_estimation.py:253-259);
+//   * values < thr -> 0, then sum / mean / central second moments of the normalised map:
+//     [mean_x, mean_y, var_x, cov_xy, cov_xy, var_y]   (reference mmpose_pose_estimation.py:163-215).
+//
+// One warp owns one heatmap at a time.  Each warp runs its own ring of shared-memory stages filled by
+// 1-D TMA bulk copies (a 64x48 map is one contiguous 12 KB copy) so several maps per warp are in flight
+// while the lanes make two passes over the resident map with conflict-free 128-bit shared loads and
+// warp-shuffle reductions.  HBM is read exactly once; 72 output bytes per map.
+#include "mc3d_common.cuh"
+#include <math.h>
+
+namespace mc3d {
+
+struct DecodeParams {
+    int H, W;
+    float thr;
+    int write_back;        // store the thresholded map back to global memory (reference quirk Q7)
+    int kpt_layout;        // MC3D_KPT_PLAIN / _NV3 / _N3V
+    int views, joints;     // for the transposing layouts: maps are ordered (T, C=views, J=joints)
+    int has_affine;
+    int affine_group;      // maps per affine entry
+};
+
+struct MapStats {
+    double s, mx, my, vx, vy, cxy;
+    float best;
+    int best_idx;
+};
+
+__device__ __forceinline__ void argmax_merge(float &bv, int &bi, float ov, int oi) {
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+}
+
+// Two passes over one resident map.  VEC4: W % 4 == 0 and src 16-byte aligned.
+template <bool VEC4>
+__device__ __forceinline__ MapStats map_stats(const float *src, float *wb, int H, int W, float thr, int lane) {
+    const int HW = H * W;
+    const float invW = 1.0f / (float)W;
+    float s = 0.f, sx = 0.f, sy = 0.f;
+    float best = -INFINITY;
+    int best_idx = 0x7fffffff;
+    if (VEC4) {
+        const float4 *src4 = reinterpret_cast<const float4 *>(src);
+        for (int i4 = lane; i4 < (HW >> 2); i4 += 32) {
+            const float4 v = src4[i4];
+            const int e = i4 << 2;
+            const int y = (int)(((float)e + 0.5f) * invW);
+            const int x = e - y * W;
+            if (v.x > best) { best = v.x; best_idx = e; }
+            if (v.y > best) { best = v.y; best_idx = e + 1; }
+            if (v.z > best) { best = v.z; best_idx = e + 2; }
+            if (v.w > best) { best = v.w; best_idx = e + 3; }
+            const float t0 = v.x < thr ? 0.f : v.x, t1 = v.y < thr ? 0.f : v.y;
+            const float t2 = v.z < thr ? 0.f : v.z, t3 = v.w < thr ? 0.f : v.w;
+            if (wb) reinterpret_cast<float4 *>(wb)[i4] = make_float4(t0, t1, t2, t3);
+            const float q = (t0 + t1) + (t2 + t3);
+            const float tx = fmaf(3.f, t3, fmaf(2.f, t2, t1));
+            s += q;
+            sx += fmaf((float)x, q, tx);
+            sy = fmaf((float)y, q, sy);
+        }
+    } else {
+        for (int e = lane; e < HW; e += 32) {
+            const float v = src[e];
+            const int y = (int)(((float)e + 0.5f) * invW);
+            const int x = e - y * W;
+            if (v > best) { best = v; best_idx = e; }
+            const float t = v < thr ? 0.f : v;
+            if (wb) wb[e] = t;
+            s += t;
+            sx = fmaf((float)x, t, sx);
+            sy = fmaf((float)y, t, sy);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+        argmax_merge(best, best_idx, ov, oi);
+    }
+    MapStats r;
+    r.best = best;
+    r.best_idx = best_idx;
+    r.s = warp_sum((double)s);
+    const double dsx = warp_sum((double)sx), dsy = warp_sum((double)sy);
+    r.mx = r.my = r.vx = r.vy = r.cxy = 0.0;
+    if (r.s == 0.0) return r;                           // all-zero map: six zeros (:191-193)
+    r.mx = dsx / r.s;
+    r.my = dsy / r.s;
+    const float fmx = (float)r.mx, fmy = (float)r.my;
+    // residual of the float means, applied analytically so the central moments are about the double means
+    float sxx = 0.f, syy = 0.f, sxy = 0.f, sdx = 0.f, sdy = 0.f;
+    if (VEC4) {
+        const float4 *src4 = reinterpret_cast<const float4 *>(src);
+        for (int i4 = lane; i4 < (HW >> 2); i4 += 32) {
+            const float4 v = src4[i4];
+            const int e = i4 << 2;
+            const int y = (int)(((float)e + 0.5f) * invW);
+            const int x = e - y * W;
+            const float t0 = v.x < thr ? 0.f : v.x, t1 = v.y < thr ? 0.f : v.y;
+            const float t2 = v.z < thr ? 0.f : v.z, t3 = v.w < thr ? 0.f : v.w;
+            const float dx0 = (float)x - fmx, dy = (float)y - fmy;
+            const float dx1 = dx0 + 1.f, dx2 = dx0 + 2.f, dx3 = dx0 + 3.f;
+            const float q = (t0 + t1) + (t2 + t3);
+            const float m1 = fmaf(dx0, t0, fmaf(dx1, t1, fmaf(dx2, t2, dx3 * t3)));
+            sxx += fmaf(dx0 * dx0, t0, fmaf(dx1 * dx1, t1, fmaf(dx2 * dx2, t2, dx3 * dx3 * t3)));
+            sdx += m1;
+            sxy = fmaf(dy, m1, sxy);
+            syy = fmaf(dy * dy, q, syy);
+            sdy = fmaf(dy, q, sdy);
+        }
+    } else {
+        for (int e = lane; e < HW; e += 32) {
+            const float v = src[e];
+            const int y = (int)(((float)e + 0.5f) * invW);
+            const int x = e - y * W;
+            const float t = v < thr ? 0.f : v;
+            const float dx = (float)x - fmx, dy = (float)y - fmy;
+            sxx = fmaf(dx * dx, t, sxx);
+            syy = fmaf(dy * dy, t, syy);
+            sxy = fmaf(dx * dy, t, sxy);
+            sdx = fmaf(dx, t, sdx);
+            sdy = fmaf(dy, t, sdy);
+        }
+    }
+    const double inv = 1.0 / r.s;
+    const double ex = warp_sum((double)sdx) * inv, ey = warp_sum((double)sdy) * inv;   // E[x - fmx], E[y - fmy]
+    r.vx = warp_sum((double)sxx) * inv - ex * ex;
+    r.vy = warp_sum((double)syy) * inv - ey * ey;
+    r.cxy = warp_sum((double)sxy) * inv - ex * ey;
+    return r;
+}
+
+__device__ __forceinline__ void write_outputs(const MapStats &r, const float *src, long long map, const DecodeParams &p,
+                                              const float *__restrict__ affine, float *__restrict__ kpt,
+                                              double *__restrict__ moments, int lane) {
+    if (moments && lane < 6) {
+        const double val = lane == 0 ? r.mx : lane == 1 ? r.my : lane == 2 ? r.vx : lane == 5 ? r.vy : r.cxy;
+        moments[map * 6 + lane] = val;
+    }
+    if (kpt && lane == 0) {
+        float kx = -1.f, ky = -1.f;
+        const float score = r.best;
+        if (score > 0.f) {                              // mmpose: maxima <= 0 are "not found" (-1, -1)
+            const int py = r.best_idx / p.W, px = r.best_idx - py * p.W;
+            kx = (float)px;
+            ky = (float)py;
+            if (px > 1 && px < p.W - 1 && py > 1 && py < p.H - 1) {
+                const float dx = src[py * p.W + px + 1] - src[py * p.W + px - 1];
+                const float dy = src[(py + 1) * p.W + px] - src[(py - 1) * p.W + px];
+                kx += dx > 0.f ? 0.25f : (dx < 0.f ? -0.25f : 0.f);
+                ky += dy > 0.f ? 0.25f : (dy < 0.f ? -0.25f : 0.f);
+            }
+            if (p.has_affine) {
+                const float *a = affine + (map / p.affine_group) * 4;
+                kx = fmaf(kx, a[0], a[2]);
+                ky = fmaf(ky, a[1], a[3]);
+            }
+        }
+        if (p.kpt_layout == MC3D_KPT_PLAIN) {
+            kpt[map * 3 + 0] = kx; kpt[map * 3 + 1] = ky; kpt[map * 3 + 2] = score;
+        } else {
+            const long long cj = (long long)p.views * p.joints;
+            const long long t = map / cj;
+            const int rem = (int)(map - t * cj);
+            const int c = rem / p.joints, j = rem - c * p.joints;
+            const long long tj = t * p.joints + j;
+            if (p.kpt_layout == MC3D_KPT_NV3) {
+                float *o = kpt + (tj * p.views + c) * 3;
+                o[0] = kx; o[1] = ky; o[2] = score;
+            } else {
+                float *o = kpt + tj * 3 * p.views + c;
+                o[0] = kx; o[p.views] = ky; o[2 * p.views] = score;
+            }
+        }
+    }
+}
+
+// TMA path: W % 4 == 0, map bytes % 16 == 0, base 16-byte aligned.
+__global__ void __launch_bounds__(256, 1)
+decode_tma_kernel(const float *__restrict__ hm, float *__restrict__ hm_wb, long long n_maps, int warps_per_cta,
+                  int n_stages, const float *__restrict__ affine, float *__restrict__ kpt,
+                  double *__restrict__ moments, const __grid_constant__ DecodeParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HW = p.H * p.W;
+    const uint32_t map_bytes = (uint32_t)HW * 4u;
+    float *ring = reinterpret_cast<float *>(smem_raw) + (size_t)warp * n_stages * HW;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)warps_per_cta * n_stages * map_bytes) + warp * 8;
+    if (lane == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const long long gwarp = (long long)blockIdx.x * warps_per_cta + warp;
+    const long long stride = (long long)gridDim.x * warps_per_cta;
+    const long long mine = gwarp < n_maps ? (n_maps - gwarp + stride - 1) / stride : 0;
+
+    auto issue = [&](long long k) {                      // lane 0
+        if (k < mine) {
+            const int s = (int)(k % n_stages);
+            mbar_arrive_expect_tx(&bars[s], map_bytes);
+            bulk_g2s(ring + (size_t)s * HW, hm + (gwarp + k * stride) * HW, map_bytes, &bars[s]);
+        }
+    };
+    if (lane == 0)
+        for (int k = 0; k < n_stages - 1; ++k) issue(k);
+    for (long long k = 0; k < mine; ++k) {
+        const long long map = gwarp + k * stride;
+        const int s = (int)(k % n_stages);
+        if (lane == 0) issue(k + n_stages - 1);          // the stage read in iteration k-1 (guarded by __syncwarp below)
+        mbar_wait(&bars[s], (uint32_t)((k / n_stages) & 1));
+        const float *src = ring + (size_t)s * HW;
+        const MapStats r = map_stats<true>(src, p.write_back ? hm_wb + map * HW : nullptr, p.H, p.W, p.thr, lane);
+        write_outputs(r, src, map, p, affine, kpt, moments, lane);
+        __syncwarp();
+    }
+}
+
+// Generic path (any W, any alignment): two passes straight from global memory (the second hits L1/L2).
+__global__ void __launch_bounds__(256)
+decode_generic_kernel(const float *__restrict__ hm, float *__restrict__ hm_wb, long long n_maps,
+                      const float *__restrict__ affine, float *__restrict__ kpt, double *__restrict__ moments,
+                      const __grid_constant__ DecodeParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int HW = p.H * p.W;
+    for (long long map = gwarp; map < n_maps; map += stride) {
+        const float *src = hm + map * HW;
+        const MapStats r = map_stats<false>(src, nullptr, p.H, p.W, p.thr, lane);
+        write_outputs(r, src, map, p, affine, kpt, moments, lane);
+        if (p.write_back) {                              // after the neighbour reads of write_outputs
+            __syncwarp();
+            for (int e = lane; e < HW; e += 32) {
+                const float v = src[e];
+                hm_wb[map * HW + e] = v < p.thr ? 0.f : v;
+            }
+        }
+    }
+}
+
+int decode_device(const float *d_hm, long long n_maps, int H, int W, float thr, int flags, int kpt_layout, int views,
+                  int joints, const float *d_affine, int affine_group, float *d_kpt, double *d_moments,
+                  cudaStream_t stream) {
+    if (n_maps < 0 || H <= 0 || W <= 0) { set_error("bad heatmap shape n=%lld H=%d W=%d", n_maps, H, W); return MC3D_ERR_INVALID_ARGUMENT; }
+    if ((long long)H * W > (1 << 22)) { set_error("heatmap %dx%d too large", H, W); return MC3D_ERR_UNSUPPORTED; }
+    if (kpt_layout != MC3D_KPT_PLAIN && kpt_layout != MC3D_KPT_NV3 && kpt_layout != MC3D_KPT_N3V) {
+        set_error("bad kpt_layout %d", kpt_layout);
+        return MC3D_ERR_INVALID_ARGUMENT;
+    }
+    if (kpt_layout != MC3D_KPT_PLAIN && (views <= 0 || joints <= 0 || n_maps % ((long long)views * joints) != 0)) {
+        set_error("transposing layouts need views, joints > 0 and n_maps %% (views*joints) == 0");
+        return MC3D_ERR_INVALID_ARGUMENT;
+    }
+    if (d_affine && affine_group <= 0) { set_error("affine_group must be > 0"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (n_maps == 0) return MC3D_OK;
+    if (!d_hm || (!d_kpt && !d_moments)) { set_error("NULL heatmap pointer or no output requested"); return MC3D_ERR_INVALID_ARGUMENT; }
+    DecodeParams p;
+    p.H = H; p.W = W; p.thr = thr;
+    p.write_back = (flags & MC3D_DECODE_FLAG_WRITE_BACK) ? 1 : 0;
+    p.kpt_layout = kpt_layout; p.views = views; p.joints = joints;
+    p.has_affine = d_affine != nullptr; p.affine_group = affine_group > 0 ? affine_group : 1;
+    float *wb = const_cast<float *>(d_hm);
+    const size_t map_bytes = (size_t)H * W * 4;
+    const bool tma_ok = (W % 4 == 0) && aligned16(d_hm) && map_bytes <= 96 * 1024 && !(flags & MC3D_DECODE_FLAG_GENERIC);
+    if (tma_ok) {
+        // choose warps x stages to keep as many bytes in flight as fit in ~200 KB of shared memory
+        int warps = 8, stages = 3;
+        const size_t budget = 200 * 1024;
+        while (warps > 1 && (size_t)warps * stages * map_bytes > budget) warps >>= 1;
+        while (stages > 2 && (size_t)warps * stages * map_bytes > budget) --stages;
+        while ((size_t)warps * (stages + 1) * map_bytes <= budget && stages < 4) ++stages;
+        const size_t smem = (size_t)warps * stages * map_bytes + (size_t)warps * 8 * sizeof(uint64_t);
+        static bool attr_done = false;
+        if (!attr_done) {
+            MC3D_CUDA_TRY(cudaFuncSetAttribute(decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done = true;
+        }
+        long long grid = sm_count();
+        const long long need = (n_maps + warps - 1) / warps;
+        if (grid > need) grid = need;
+        decode_tma_kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(d_hm, wb, n_maps, warps, stages, d_affine, d_kpt,
+                                                                       d_moments, p);
+    } else {
+        long long grid = (long long)sm_count() * 8;
+        const long long need = (n_maps + 7) / 8;
+        if (grid > need) grid = need;
+        decode_generic_kernel<<<(unsigned)grid, 256, 0, stream>>>(d_hm, wb, n_maps, d_affine, d_kpt, d_moments, p);
+    }
+    count_launch();
+    MC3D_CUDA_TRY(cudaGetLastError());
+    return MC3D_OK;
+}
+
+}  // namespace mc3d
+
+extern "C" int mc3d_decode_heatmaps_f32(const float *d_heatmaps, int64_t n_maps, int H, int W, float threshold,
+                                        int flags, int kpt_layout, int views, int joints, const float *d_affine,
+                                        int affine_group, float *d_kpt, double *d_moments, void *stream) {
+    return mc3d::decode_device(d_heatmaps, n_maps, H, W, threshold, flags, kpt_layout, views, joints, d_affine,
+                               affine_group, d_kpt, d_moments, (cudaStream_t)stream);
+}

@@ -185,8 +185,8 @@ __device__ __forceinline__ void accumulate_view(double *B, double x, double y, d
 
 // ---- kernel -----------------------------------------------------------------------------------
 // V > 0: number of views known at compile time (fully unrolled); V == 0: runtime prm.n_views.
-template <typename T, int V, int MODE>
-__global__ void __launch_bounds__(TRI_TILE, 2)
+template <typename T, int V, int MODE, bool UNDISTORT>
+__global__ void __launch_bounds__(TRI_TILE, (V > 0 && V <= 8) ? 3 : 2)
 triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n, int n_stages,
                    const __grid_constant__ TriParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -218,26 +218,26 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
     __syncthreads();
 
     auto tile_is_full = [&](long long tile) { return (tile + 1) * TRI_TILE <= n; };
-    auto issue_load = [&](long long k) {   // thread 0 only
+    auto issue_load = [&](long long k, int s) {   // thread 0 only; s = k % n_stages
         const long long tile = first + k * stride;
         if (k < my_tiles && tile_is_full(tile)) {
-            const int s = (int)(k % n_stages);
             mbar_arrive_expect_tx(&full[s], stage_bytes);
             bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes,
                      kpts + tile * TRI_TILE * (long long)row_elems, stage_bytes, &full[s]);
         }
     };
     if (tid == 0)
-        for (int k = 0; k < n_stages - 1; ++k) issue_load(k);
+        for (int k = 0; k < n_stages - 1; ++k) issue_load(k, k);
 
+    int s = 0;                     // stage of iteration k
+    int s_next = n_stages - 1;     // stage of iteration k + n_stages - 1
+    uint32_t parity = 0;
     for (long long k = 0; k < my_tiles; ++k) {
         const long long tile = first + k * stride;
-        const int s = (int)(k % n_stages);
-        const uint32_t parity = (uint32_t)((k / n_stages) & 1);
         const bool full_tile = tile_is_full(tile);
         T *stage = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes);
         if (tid == 0) {
-            issue_load(k + n_stages - 1);     // refills the stage consumed in iteration k-1
+            issue_load(k + n_stages - 1, s_next);   // refills the stage consumed in iteration k-1
             bulk_wait_read<1>();              // output tile (k&1) of iteration k-2 has left shared memory
         }
         const long long joint = tile * TRI_TILE + tid;
@@ -255,7 +255,6 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
 #pragma unroll
         for (int i = 0; i < 10; ++i) B[i] = 0.0;
         int n_used = 0;
-        bool finite_in = true;
         if (active) {
             const T *row = stage + (size_t)tid * row_elems;
             const bool l3v = prm.layout == MC3D_LAYOUT_3V;
@@ -266,8 +265,7 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
                     double x = (double)(l3v ? row[v] : row[3 * v]);
                     double y = (double)(l3v ? row[nv + v] : row[3 * v + 1]);
                     const double w = (double)(l3v ? row[2 * nv + v] : row[3 * v + 2]);
-                    if (prm.undistort) undistort_px(x, y, prm.K[v], prm.dist[v]);
-                    finite_in = finite_in && (fabs(x) <= 1.0e300) && (fabs(y) <= 1.0e300) && (fabs(w) <= 1.0e300);
+                    if (UNDISTORT) undistort_px(x, y, prm.K[v], prm.dist[v]);
                     n_used += (w != 0.0);
                     accumulate_view(B, x, y, w, prm.P[v]);
                 }
@@ -288,8 +286,7 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
                     double x = (double)(l3v ? row[v] : row[3 * v]);
                     double y = (double)(l3v ? row[nv + v] : row[3 * v + 1]);
                     const double *cv = cam + v * 26;
-                    if (prm.undistort) undistort_px(x, y, cv + 12, cv + 21);
-                    finite_in = finite_in && (fabs(x) <= 1.0e300) && (fabs(y) <= 1.0e300);
+                    if (UNDISTORT) undistort_px(x, y, cv + 12, cv + 21);
                     accumulate_view(B, x, y, 1.0, cv);
                 }
                 n_used = 2;
@@ -298,10 +295,17 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
         __syncthreads();                       // [A] every thread has consumed stage s
 
         double X0 = NAN, X1 = NAN, X2 = NAN;
+        // non-finite pixels or weights poison the (non-negative) diagonal of B
+        const bool finite_in = fabs((B[0] + B[2]) + (B[5] + B[9])) <= 1.0e300;
         if (active && finite_in && n_used >= 2) {
             bool ok = false;
             if (!(prm.flags & MC3D_TRI_FLAG_JACOBI)) ok = secular_newton(B, X0, X1, X2);
-            if (!ok) jacobi4_smallest(B, X0, X1, X2);
+            if (!ok) {                             // cold path: only here does B go to local memory
+                double Bl[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) Bl[i] = B[i];
+                jacobi4_smallest(Bl, X0, X1, X2);
+            }
         }
 
         T *ot = otile + (size_t)(k & 1) * TRI_TILE * 3;
@@ -323,6 +327,8 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
             }
             if (tid == 0) bulk_commit();       // keep one group per iteration for wait_group accounting
         }
+        if (++s == n_stages) { s = 0; parity ^= 1u; }
+        if (++s_next == n_stages) s_next = 0;
     }
     if (tid == 0) bulk_wait_all<0>();
 }
@@ -355,22 +361,30 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
     return MC3D_OK;
 }
 
-template <typename T, int V, int MODE>
+template <typename T, int V, int MODE, bool UNDISTORT>
 static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_out, cudaStream_t stream) {
     const int nv = prm.n_views;
     const size_t stage_bytes = (size_t)TRI_TILE * 3 * nv * sizeof(T);
-    int n_stages = stage_bytes <= 32 * 1024 ? 3 : 2;
-    const size_t smem = n_stages * stage_bytes + 2 * TRI_TILE * 3 * sizeof(T) + 8 * sizeof(uint64_t) +
-                        (MODE == MC3D_TRI_TOP2 ? (size_t)nv * 26 * sizeof(double) : 0);
-    auto kern = triangulate_kernel<T, V, MODE>;
+    auto kern = triangulate_kernel<T, V, MODE, UNDISTORT>;
     static bool attr_done = false;     // per instantiation
     if (!attr_done) {
         MC3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    int per_sm = 0;
-    MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRI_TILE, smem));
-    if (per_sm < 1) { set_error("triangulate kernel does not fit: smem=%zu", smem); return MC3D_ERR_UNSUPPORTED; }
+    // The kernel is bound by fp64 latency, not by bytes in flight: prefer more resident CTAs (warps) over a
+    // deeper ring; 2 stages already cover the HBM latency at this arithmetic intensity.
+    const size_t fixed = 2 * TRI_TILE * 3 * sizeof(T) + 8 * sizeof(uint64_t) +
+                         (MODE == MC3D_TRI_TOP2 ? (size_t)nv * 26 * sizeof(double) : 0);
+    int n_stages = 2, per_sm = 0;
+    size_t smem = 0;
+    for (int st = 4; st >= 2; --st) {
+        const size_t sm_bytes = st * stage_bytes + fixed;
+        if (sm_bytes > 227 * 1024) continue;
+        int occ = 0;
+        MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TRI_TILE, sm_bytes));
+        if (occ > per_sm) { per_sm = occ; n_stages = st; smem = sm_bytes; }
+    }
+    if (per_sm < 1) { set_error("triangulate kernel does not fit in shared memory (views=%d)", nv); return MC3D_ERR_UNSUPPORTED; }
     const long long n_tiles = (n + TRI_TILE - 1) / TRI_TILE;
     long long grid = (long long)sm_count() * per_sm;      // persistent: a whole number of waves
     if (grid > n_tiles) grid = n_tiles;
@@ -393,14 +407,18 @@ int triangulate_device(const T *d_kpts, long long n, const mc3d_rig *rig, int la
         set_error("device pointers must be 16-byte aligned (kpts=%p out=%p)", (const void *)d_kpts, (void *)d_out);
         return MC3D_ERR_MISALIGNED;
     }
-    if (mode == MC3D_TRI_TOP2) return launch_one<T, 0, MC3D_TRI_TOP2>(d_kpts, n, prm, d_out, stream);
-    switch (prm.n_views) {
-        case 2: return launch_one<T, 2, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
-        case 3: return launch_one<T, 3, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
-        case 4: return launch_one<T, 4, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
-        case 8: return launch_one<T, 8, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
-        case 16: return launch_one<T, 16, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
-        default: return launch_one<T, 0, MC3D_TRI_WEIGHTED>(d_kpts, n, prm, d_out, stream);
+    if (mode == MC3D_TRI_TOP2) {
+        if (prm.undistort) return launch_one<T, 0, MC3D_TRI_TOP2, true>(d_kpts, n, prm, d_out, stream);
+        return launch_one<T, 0, MC3D_TRI_TOP2, false>(d_kpts, n, prm, d_out, stream);
+    }
+    if (prm.undistort) return launch_one<T, 0, MC3D_TRI_WEIGHTED, true>(d_kpts, n, prm, d_out, stream);
+    switch (prm.n_views) {      // fully unrolled view loops for the common rigs
+        case 2: return launch_one<T, 2, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        case 3: return launch_one<T, 3, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        case 4: return launch_one<T, 4, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        case 8: return launch_one<T, 8, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        case 16: return launch_one<T, 16, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        default: return launch_one<T, 0, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
     }
 }
 
