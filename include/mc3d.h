@@ -126,6 +126,64 @@ int mc3d_decode_heatmaps_f32(const float *d_heatmaps, int64_t n_maps, int H, int
 int mc3d_decode_heatmaps_host_f32(const float *h_heatmaps, int64_t n_maps, int H, int W, float threshold,
                                   float *h_kpt, double *h_moments, int device);
 
+
+/* ---- 3. trajectory refinement -----------------------------------------------------------------
+ * One optimiser step of Optimized_3d_Pose_Estimation.sgd_optimize (pose_refinement.py:1006-1050) is three
+ * phases on the caller's stream:
+ *   phase 0  costs    : likelihood (:863-889, camera-0 Gaussians), smoothness (:836-845), bone length
+ *                       (:848-860) -> 7 global sums in ctrl, per-frame term_ok flags
+ *   phase 1  gradient : closed-form gradient (replaces total_cost.backward(), :1044) -> g, sum g^2 in ctrl
+ *   phase 2  step     : clip_grad_norm_(1.0) (:1047), Adam (:1050), running-mean early stopping (:1069-1089),
+ *                       best_trajectory snapshot (:1075), cost history (:1052-1054)
+ * All state is caller-owned device memory (state dtype = float or double per entry-point suffix):
+ *   x        (n_frames + 4, J, 3)  trajectory with TWO HALO FRAMES at each end (multi-GPU: neighbours' frames)
+ *   m, v, best, g  (n_frames, J, 3)  Adam moments, best snapshot, gradient scratch
+ *   mu0 (n_frames, J, 2), S (n_frames, J, 3)   from mc3d_refine_prepare_*: camera-0 means and the symmetric
+ *                                              inverse of (cov + 1e-6 I) as [s00, s01, s11] (:663-668)
+ *   term_ok  (n_frames + 4) bytes  validity of the smoothness term ending at each frame (halo-extended)
+ *   ctrl     doubles, >= 64 + 4 * hist_capacity, zero-filled except ctrl[32+3] = ctrl[48+3] = +inf:
+ *            [0..7]+16p   sums of the step with parity p: S_lik N_lik S_smooth N_smooth a.b b.b a.a gnorm^2
+ *            [32..39]+16p state entering a step of parity p: adam_step run_sum run_cnt best no_improve
+ *                         stopped iterations improved
+ *            [64+4s ..]   cost history of step s: total likelihood smoothness body_length
+ * A multi-GPU driver shards frames, exchanges the x / term_ok halos and all-reduces ctrl[0..6]+16p after
+ * phase 0 and ctrl[7]+16p after phase 1 (that is the whole exchange; every rank then takes the same decisions). */
+typedef struct {
+    int32_t n_joints, n_cams, n_bones, ignore_distortions;
+    int32_t patience, max_iter;
+    int64_t n_frames;        /* local frames (without halo) */
+    int64_t frame_offset;    /* global index of local frame 0 */
+    int64_t win_begin, win_end;   /* global frame window the costs are evaluated on (a batch, :786-796) */
+    int64_t hist_capacity;
+    double lr, beta1, beta2, eps, lambda_smooth, lambda_body, tolerance;
+    double aa;               /* ||a||^2 = window length x sum of squared target bone lengths (:857) */
+    double cams[MC3D_MAX_VIEWS][26];      /* per camera: K[9] R[9] T[3] dist[5] (pose_refinement.py:94) */
+    double bone_len[MC3D_MAX_BONES];
+    int32_t bone_start[MC3D_MAX_BONES], bone_end[MC3D_MAX_BONES];
+    int32_t adj_start[MC3D_MAX_JOINTS + 3];          /* CSR joint -> incident bones */
+    int32_t adj_bone[2 * MC3D_MAX_BONES], adj_sign[2 * MC3D_MAX_BONES];   /* sign +1: joint is the bone's end */
+    void *x, *m, *v, *best, *g, *mu0, *S;
+    uint8_t *term_ok;
+    double *ctrl;
+} mc3d_refine_problem;
+
+/* Pinhole + 5-coefficient Brown projection of n points (n,3) -> (n,2) for one camera given as
+ * cam26 = K[9] R[9] T[3] dist[5] (host doubles): project_points_torch, pose_refinement.py:94-179. */
+int mc3d_project_points_f32(const float *d_points, int64_t n, const double *cam26, int ignore_distortions, float *d_out, void *stream);
+int mc3d_project_points_f64(const double *d_points, int64_t n, const double *cam26, int ignore_distortions, double *d_out, void *stream);
+
+int mc3d_refine_prepare_f32(const float *d_gaussians, int64_t n_frames, int n_cams, int n_joints, int cam, double eps,
+                            float *d_mu0, float *d_S, void *stream);
+int mc3d_refine_prepare_f64(const double *d_gaussians, int64_t n_frames, int n_cams, int n_joints, int cam, double eps,
+                            double *d_mu0, double *d_S, void *stream);
+/* sizeof(mc3d_refine_problem), so that a binding can check its struct layout. */
+int mc3d_refine_problem_size(void);
+int mc3d_refine_phase_f32(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream);
+int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream);
+/* n_iters whole-window iterations (phases 0,1,2 each) on one GPU, replayed from a CUDA graph. */
+int mc3d_refine_run_f32(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
+int mc3d_refine_run_f64(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

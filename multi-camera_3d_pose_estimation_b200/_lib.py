@@ -30,9 +30,28 @@ class Rig(ctypes.Structure):
                 ('dist', ctypes.POINTER(ctypes.c_double))]
 
 
-class RefineCamera(ctypes.Structure):
-    _fields_ = [('K', ctypes.c_double * 9), ('R', ctypes.c_double * 9), ('T', ctypes.c_double * 3),
-                ('dist', ctypes.c_double * 5)]
+MAX_JOINTS = 133
+MAX_BONES = 64
+CT_ACC, CT_STATE, CT_HIST = 0, 32, 64          # control-block layout (include/mc3d.h)
+
+
+class RefineProblem(ctypes.Structure):
+    """mc3d_refine_problem (include/mc3d.h)."""
+    _fields_ = [('n_joints', ctypes.c_int32), ('n_cams', ctypes.c_int32), ('n_bones', ctypes.c_int32),
+                ('ignore_distortions', ctypes.c_int32), ('patience', ctypes.c_int32), ('max_iter', ctypes.c_int32),
+                ('n_frames', ctypes.c_int64), ('frame_offset', ctypes.c_int64), ('win_begin', ctypes.c_int64),
+                ('win_end', ctypes.c_int64), ('hist_capacity', ctypes.c_int64),
+                ('lr', ctypes.c_double), ('beta1', ctypes.c_double), ('beta2', ctypes.c_double),
+                ('eps', ctypes.c_double), ('lambda_smooth', ctypes.c_double), ('lambda_body', ctypes.c_double),
+                ('tolerance', ctypes.c_double), ('aa', ctypes.c_double),
+                ('cams', (ctypes.c_double * 26) * MAX_VIEWS),
+                ('bone_len', ctypes.c_double * MAX_BONES),
+                ('bone_start', ctypes.c_int32 * MAX_BONES), ('bone_end', ctypes.c_int32 * MAX_BONES),
+                ('adj_start', ctypes.c_int32 * (MAX_JOINTS + 3)),
+                ('adj_bone', ctypes.c_int32 * (2 * MAX_BONES)), ('adj_sign', ctypes.c_int32 * (2 * MAX_BONES)),
+                ('x', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p), ('best', ctypes.c_void_p),
+                ('g', ctypes.c_void_p), ('mu0', ctypes.c_void_p), ('S', ctypes.c_void_p),
+                ('term_ok', ctypes.c_void_p), ('ctrl', ctypes.c_void_p)]
 
 
 _lib = None
@@ -57,6 +76,15 @@ SIGNATURES = {
     'mc3d_decode_heatmaps_f32': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, ctypes.c_float, _c_int, _c_int, _c_int, _c_int,
                                           _c_vp, _c_int, _c_vp, _c_vp, _c_vp]),
     'mc3d_decode_heatmaps_host_f32': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, ctypes.c_float, _c_vp, _c_vp, _c_int]),
+    'mc3d_project_points_f32': (_c_int, [_c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp]),
+    'mc3d_project_points_f64': (_c_int, [_c_vp, _c_i64, _c_vp, _c_int, _c_vp, _c_vp]),
+    'mc3d_refine_prepare_f32': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp, _c_vp]),
+    'mc3d_refine_prepare_f64': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp, _c_vp]),
+    'mc3d_refine_problem_size': (_c_int, []),
+    'mc3d_refine_phase_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_int, _c_i64, _c_int, _c_vp]),
+    'mc3d_refine_phase_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_int, _c_i64, _c_int, _c_vp]),
+    'mc3d_refine_run_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_i64, _c_i64, _c_vp]),
+    'mc3d_refine_run_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_i64, _c_i64, _c_vp]),
 }
 
 
@@ -72,6 +100,8 @@ def lib():
             fn = getattr(handle, name)          # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
+        if handle.mc3d_refine_problem_size() != ctypes.sizeof(RefineProblem):
+            raise Mc3dError('mc3d_refine_problem layout mismatch between include/mc3d.h and _lib.py')
         _lib = handle
     return _lib
 

@@ -1,0 +1,561 @@
+// Trajectory refinement for sm_100a: the loss, its hand-derived gradient and the clipped Adam step that the
+// reference's Optimized_3d_Pose_Estimation.sgd_optimize iterates with torch autograd
+// (pose_refinement.py:836-889 costs, :1002-1091 loop).
+//
+// One optimiser step = three kernels over the frame-sharded state (no host round trip in between):
+//   A  costs   : per (frame, joint) reprojection Mahalanobis terms for every camera (camera-0 Gaussians, upstream
+//                quirk Q1), second-difference smoothness terms, bone lengths -> 7 global sums (finite-masked,
+//                nan_mean semantics) + per-frame finiteness flags
+//   B  gradient: closed-form gradient of the three terms (needs the global sums of A: counts, mu = a.b/b.b)
+//                -> g, and the global sum of g^2
+//   C  step    : clip_grad_norm_(1.0), Adam (torch.optim.Adam arithmetic), running-mean early-stopping
+//                bookkeeping, conditional best-trajectory snapshot, cost history
+// Global sums live in a small double control block (ping-pong by step parity) so that a multi-GPU driver can
+// all-reduce them between kernels; every thread re-derives the scalars it needs from that block, so there are no
+// single-thread "finalise" launches.  Blocks are persistent (grid = k x SM count) and stage their frames plus a
+// two-frame halo in shared memory; sums are reduced warp -> block -> one double atomic per block.
+#include "mc3d_common.cuh"
+#include <math.h>
+
+namespace mc3d {
+
+constexpr int RF_THREADS = 256;
+// control block layout (doubles)
+constexpr int CT_ACC = 0;        // + 16 * parity : S_lik N_lik S_s N_s ab bb aa_ok gnorm2
+constexpr int CT_STATE = 32;     // + 16 * parity : step run_sum run_cnt best no_improve stopped iters_done improved
+constexpr int CT_HIST = 64;      // + 4 * step    : total lik smooth body
+
+struct RefineDerived {
+    double inv_nlik, smooth_scale, mu, body_c;
+    double cost_lik, cost_s, cost_b, total;
+    bool stopped;
+};
+
+__device__ __forceinline__ RefineDerived derive(const mc3d_refine_problem &pb, const double *ctrl, int parity) {
+    const double *acc = ctrl + CT_ACC + 16 * parity;
+    const double *st = ctrl + CT_STATE + 16 * parity;
+    RefineDerived d;
+    d.stopped = st[5] != 0.0;
+    const double nl = acc[1], ns = acc[3];
+    d.inv_nlik = 1.0 / nl;
+    d.cost_lik = acc[0] / nl;
+    d.smooth_scale = 2.0 * pb.lambda_smooth / ns;
+    d.cost_s = pb.lambda_smooth > 0.0 ? pb.lambda_smooth * acc[2] / ns : 0.0;
+    d.mu = acc[4] / acc[5];
+    d.body_c = -2.0 * pb.lambda_body * d.mu / pb.aa;
+    d.cost_b = pb.lambda_body > 0.0 ? pb.lambda_body * (acc[6] - 2.0 * d.mu * acc[4] + d.mu * d.mu * acc[5]) / pb.aa : 0.0;
+    d.total = d.cost_lik + d.cost_s + d.cost_b;
+    return d;
+}
+
+// Reprojection term of one camera: returns 0.5 d^T S d, and (when GRAD) adds J^T S d * scale to g[3].
+template <bool GRAD>
+__device__ __forceinline__ double reproject_term(const double *cam, bool ignore_dist, double X, double Y, double Z,
+                                                 double mx, double my, double s00, double s01, double s11,
+                                                 double scale, double *g) {
+    const double *K = cam, *R = cam + 9, *T = cam + 18, *D = cam + 21;
+    const double xc = fma(R[0], X, fma(R[1], Y, fma(R[2], Z, T[0])));
+    const double yc = fma(R[3], X, fma(R[4], Y, fma(R[5], Z, T[1])));
+    const double zc = fma(R[6], X, fma(R[7], Y, fma(R[8], Z, T[2])));
+    const double iz = 1.0 / zc;
+    const double a = xc * iz, b = yc * iz;
+    double xd = a, yd = b, j00 = 1.0, j01 = 0.0, j11 = 1.0;
+    if (!ignore_dist) {
+        const double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3], k3 = D[4];
+        const double r2 = fma(a, a, b * b);
+        const double rad = fma(fma(fma(k3, r2, k2), r2, k1), r2, 1.0);
+        xd = fma(a, rad, fma(2.0 * p1 * a, b, p2 * fma(2.0 * a, a, r2)));
+        yd = fma(b, rad, fma(p1, fma(2.0 * b, b, r2), 2.0 * p2 * a * b));
+        if (GRAD) {
+            const double drad = fma(fma(3.0 * k3, r2, 2.0 * k2), r2, k1);
+            j00 = rad + 2.0 * a * a * drad + 2.0 * p1 * b + 6.0 * p2 * a;
+            j01 = 2.0 * a * b * drad + 2.0 * p1 * a + 2.0 * p2 * b;
+            j11 = rad + 2.0 * b * b * drad + 6.0 * p1 * b + 2.0 * p2 * a;
+        }
+    }
+    const double u = fma(K[0], xd, fma(K[1], yd, K[2]));
+    const double v = fma(K[3], xd, fma(K[4], yd, K[5]));
+    const double s = fma(K[6], xd, fma(K[7], yd, K[8]));
+    const double is = 1.0 / s;
+    const double px = u * is, py = v * is;
+    const double dx = px - mx, dy = py - my;
+    const double sdx = fma(s00, dx, s01 * dy), sdy = fma(s01, dx, s11 * dy);
+    const double q = 0.5 * fma(dx, sdx, dy * sdy);
+    if (GRAD && fabs(q) <= 1.0e300) {
+        // pixel -> distorted normalised
+        const double gxd = (sdx * (K[0] - px * K[6]) + sdy * (K[3] - py * K[6])) * is;
+        const double gyd = (sdx * (K[1] - px * K[7]) + sdy * (K[4] - py * K[7])) * is;
+        // distorted -> normalised
+        const double ga = fma(j00, gxd, j01 * gyd), gb = fma(j01, gxd, j11 * gyd);
+        // normalised -> camera frame
+        const double gxc = ga * iz, gyc = gb * iz, gzc = -(a * ga + b * gb) * iz;
+        // camera -> world (R^T)
+        g[0] = fma(scale, fma(R[0], gxc, fma(R[3], gyc, R[6] * gzc)), g[0]);
+        g[1] = fma(scale, fma(R[1], gxc, fma(R[4], gyc, R[7] * gzc)), g[1]);
+        g[2] = fma(scale, fma(R[2], gxc, fma(R[5], gyc, R[8] * gzc)), g[2]);
+    }
+    return q;
+}
+
+// Bone / adjacency tables are indexed per thread: keep them in shared memory (constant-bank reads with
+// lane-divergent addresses serialise).
+struct RefineTables {
+    double bone_len[MC3D_MAX_BONES];
+    int bone_start[MC3D_MAX_BONES], bone_end[MC3D_MAX_BONES];
+    int adj_start[MC3D_MAX_JOINTS + 3];
+    int adj_bone[2 * MC3D_MAX_BONES], adj_sign[2 * MC3D_MAX_BONES];
+};
+
+__device__ __forceinline__ void load_tables(RefineTables &tb, const mc3d_refine_problem &pb) {
+    for (int i = threadIdx.x; i < MC3D_MAX_BONES; i += blockDim.x) {
+        tb.bone_len[i] = pb.bone_len[i]; tb.bone_start[i] = pb.bone_start[i]; tb.bone_end[i] = pb.bone_end[i];
+    }
+    for (int i = threadIdx.x; i < 2 * MC3D_MAX_BONES; i += blockDim.x) { tb.adj_bone[i] = pb.adj_bone[i]; tb.adj_sign[i] = pb.adj_sign[i]; }
+    for (int i = threadIdx.x; i <= pb.n_joints; i += blockDim.x) tb.adj_start[i] = pb.adj_start[i];
+}
+
+template <int N>
+__device__ __forceinline__ void block_reduce_add(double (&vals)[N], double *smem_red, double *global_acc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) vals[i] = warp_sum(vals[i]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < N; ++i) smem_red[warp * N + i] = vals[i];
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += smem_red[w * N + threadIdx.x];
+        if (s != 0.0) atomicAdd(global_acc + threadIdx.x, s);
+    }
+    __syncthreads();
+}
+
+// Shared-memory staging of frames [t_lo - 2, t_lo + fpb + 2) of the (halo-extended) trajectory.
+template <typename T>
+__device__ __forceinline__ void stage_frames(const T *x_ext, double *xs, long long t_lo, int fpb, int J, long long n_local) {
+    // x_ext frame index = local frame + 2; local frames range [-2, n_local + 2)
+    const int count = (fpb + 4) * J * 3;
+    const long long base = t_lo * J * 3;            // (t_lo - 2 + 2) * J * 3
+    const long long limit = (n_local + 4) * (long long)J * 3;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const long long src = base + i;
+        xs[i] = (src < limit) ? (double)x_ext[src] : 0.0;
+    }
+}
+
+// ---- kernel A: costs ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
+    extern __shared__ __align__(16) double smem_d[];
+    __shared__ RefineTables tb;
+    double *ctrl = pb.ctrl;
+    if (ctrl[CT_STATE + 16 * parity + 5] != 0.0) return;          // stopped
+    load_tables(tb, pb);
+    const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones;
+    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;       // frames per tile (J <= 256)
+    double *xs = smem_d;                                           // (fpb + 4) * J * 3
+    double *d2 = xs + (fpb + 4) * J * 3;                           // fpb * J   per-joint smoothness contributions
+    double *red = d2 + fpb * J;                                    // 8 warps * 7
+    const T *x_ext = (const T *)pb.x;
+    const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
+    const long long nloc = pb.n_frames;
+    const long long n_tiles = (nloc + fpb - 1) / fpb;
+    const bool ign = pb.ignore_distortions != 0;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int tl = threadIdx.x / J, j = threadIdx.x - tl * J;
+    const bool lane_ok = tl < fpb;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long t_lo = tile * fpb;
+        __syncthreads();
+        stage_frames(x_ext, xs, t_lo, fpb, J, nloc);
+        __syncthreads();
+        const long long t = t_lo + tl;                             // local frame
+        const long long tg = t + pb.frame_offset;                  // global frame
+        const bool in_win = lane_ok && t < nloc && tg >= pb.win_begin && tg < pb.win_end;
+        if (lane_ok) d2[tl * J + j] = 0.0;
+        if (in_win) {
+            const double *xc = xs + ((tl + 2) * J + j) * 3;
+            const double X = xc[0], Y = xc[1], Z = xc[2];
+            const long long e = t * J + j;
+            const double mx = (double)mu0[e * 2], my = (double)mu0[e * 2 + 1];
+            const double s00 = (double)S[e * 3], s01 = (double)S[e * 3 + 1], s11 = (double)S[e * 3 + 2];
+            for (int c = 0; c < C; ++c) {
+                const double q = reproject_term<false>(pb.cams[c], ign, X, Y, Z, mx, my, s00, s01, s11, 0.0, nullptr);
+                if (fabs(q) <= 1.0e300) { acc[0] += q; acc[1] += 1.0; }
+            }
+            if (pb.lambda_smooth > 0.0 && tg - 2 >= pb.win_begin) {
+                const double *x1 = xc - J * 3, *x2 = xc - 2 * J * 3;
+                const double a0 = X - 2.0 * x1[0] + x2[0], a1 = Y - 2.0 * x1[1] + x2[1], a2 = Z - 2.0 * x1[2] + x2[2];
+                d2[tl * J + j] = a0 * a0 + a1 * a1 + a2 * a2;
+            }
+            if (pb.lambda_body > 0.0) {
+                const double *xf = xs + (tl + 2) * J * 3;
+                for (int k = j; k < NB; k += J) {
+                    const double *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
+                    const double v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
+                    const double b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                    if (fabs(b) <= 1.0e300) {
+                        const double a = tb.bone_len[k];
+                        acc[4] += a * b; acc[5] += b * b; acc[6] += a * a;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < fpb) {                                   // one thread per frame: frame-level smoothness term
+            const long long tt = t_lo + threadIdx.x, ttg = tt + pb.frame_offset;
+            if (tt < nloc && ttg >= pb.win_begin + 2 && ttg < pb.win_end && pb.lambda_smooth > 0.0) {
+                double sum = 0.0;
+                for (int jj = 0; jj < J; ++jj) sum += d2[threadIdx.x * J + jj];
+                const bool ok = fabs(sum) <= 1.0e300;
+                pb.term_ok[tt + 2] = ok ? 1 : 0;
+                if (ok) { acc[2] += sum; acc[3] += 1.0; }
+            } else if (tt < nloc) {
+                pb.term_ok[tt + 2] = 0;
+            }
+        }
+    }
+    block_reduce_add<7>(acc, red, ctrl + CT_ACC + 16 * parity);
+}
+
+// ---- kernel B: gradient ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
+    extern __shared__ __align__(16) double smem_d[];
+    __shared__ RefineTables tb;
+    double *ctrl = pb.ctrl;
+    const RefineDerived dv = derive(pb, ctrl, parity);
+    if (dv.stopped) return;
+    load_tables(tb, pb);
+    const int J = pb.n_joints, C = pb.n_cams;
+    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
+    double *xs = smem_d;
+    double *red = xs + (fpb + 4) * J * 3;
+    const T *x_ext = (const T *)pb.x;
+    const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
+    T *gout = (T *)pb.g;
+    const long long nloc = pb.n_frames;
+    const long long n_tiles = (nloc + fpb - 1) / fpb;
+    const bool ign = pb.ignore_distortions != 0;
+    double gn[1] = {0.0};
+    const int tl = threadIdx.x / J, j = threadIdx.x - tl * J;
+    const bool lane_ok = tl < fpb;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long t_lo = tile * fpb;
+        __syncthreads();
+        stage_frames(x_ext, xs, t_lo, fpb, J, nloc);
+        __syncthreads();
+        const long long t = t_lo + tl, tg = t + pb.frame_offset;
+        if (!(lane_ok && t < nloc)) continue;
+        const long long e = t * J + j;
+        double g[3] = {0.0, 0.0, 0.0};
+        const bool in_win = tg >= pb.win_begin && tg < pb.win_end;
+        const double *xc = xs + ((tl + 2) * J + j) * 3;
+        const double X = xc[0], Y = xc[1], Z = xc[2];
+        const bool self_ok = fabs(X) <= 1.0e300 && fabs(Y) <= 1.0e300 && fabs(Z) <= 1.0e300;
+        if (in_win && self_ok) {
+            const double mx = (double)mu0[e * 2], my = (double)mu0[e * 2 + 1];
+            const double s00 = (double)S[e * 3], s01 = (double)S[e * 3 + 1], s11 = (double)S[e * 3 + 2];
+            for (int c = 0; c < C; ++c)
+                reproject_term<true>(pb.cams[c], ign, X, Y, Z, mx, my, s00, s01, s11, dv.inv_nlik, g);
+            if (pb.lambda_smooth > 0.0) {
+                // d/dx_t of sum_s ||D_s||^2 = 2 (D_t - 2 D_{t+1} + D_{t+2}) over the valid terms s
+                const int JS = J * 3;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                if (pb.term_ok[t + 2]) {
+                    s0 += xc[0] - 2.0 * xc[-JS] + xc[-2 * JS]; s1 += xc[1] - 2.0 * xc[1 - JS] + xc[1 - 2 * JS];
+                    s2 += xc[2] - 2.0 * xc[2 - JS] + xc[2 - 2 * JS];
+                }
+                if (pb.term_ok[t + 3]) {
+                    s0 -= 2.0 * (xc[JS] - 2.0 * xc[0] + xc[-JS]); s1 -= 2.0 * (xc[1 + JS] - 2.0 * xc[1] + xc[1 - JS]);
+                    s2 -= 2.0 * (xc[2 + JS] - 2.0 * xc[2] + xc[2 - JS]);
+                }
+                if (pb.term_ok[t + 4]) {
+                    s0 += xc[2 * JS] - 2.0 * xc[JS] + xc[0]; s1 += xc[1 + 2 * JS] - 2.0 * xc[1 + JS] + xc[1];
+                    s2 += xc[2 + 2 * JS] - 2.0 * xc[2 + JS] + xc[2];
+                }
+                g[0] = fma(dv.smooth_scale, s0, g[0]); g[1] = fma(dv.smooth_scale, s1, g[1]); g[2] = fma(dv.smooth_scale, s2, g[2]);
+            }
+            if (pb.lambda_body > 0.0) {
+                const double *xf = xs + (tl + 2) * J * 3;
+                for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {
+                    const int k = tb.adj_bone[q];
+                    const double sign = (double)tb.adj_sign[q];
+                    const double *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
+                    const double v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
+                    const double b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                    if (fabs(b) <= 1.0e300 && b > 0.0) {
+                        const double coef = sign * dv.body_c * (tb.bone_len[k] - dv.mu * b) / b;
+                        g[0] = fma(coef, v0, g[0]); g[1] = fma(coef, v1, g[1]); g[2] = fma(coef, v2, g[2]);
+                    }
+                }
+            }
+        }
+        const T g0 = (T)g[0], g1 = (T)g[1], g2 = (T)g[2];
+        gout[e * 3 + 0] = g0; gout[e * 3 + 1] = g1; gout[e * 3 + 2] = g2;
+        gn[0] += (double)g0 * (double)g0 + (double)g1 * (double)g1 + (double)g2 * (double)g2;
+    }
+    __syncthreads();
+    block_reduce_add<1>(gn, red, ctrl + CT_ACC + 16 * parity + 7);
+}
+
+// ---- kernel C: clip + Adam + bookkeeping ------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, int end_of_iteration) {
+    double *ctrl = pb.ctrl;
+    const RefineDerived dv = derive(pb, ctrl, parity);
+    if (dv.stopped) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                 // carry the stopped state forward
+            for (int i = 0; i < 16; ++i) ctrl[CT_STATE + 16 * (parity ^ 1) + i] = ctrl[CT_STATE + 16 * parity + i];
+            for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
+        }
+        return;
+    }
+    const double *st = ctrl + CT_STATE + 16 * parity;
+    const double gnorm = sqrt(ctrl[CT_ACC + 16 * parity + 7]);
+    const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
+    const double step = st[0] + 1.0;
+    double run_sum = st[1] + dv.total, run_cnt = st[2] + 1.0;
+    double best = st[3], no_imp = st[4], iters = st[6];
+    bool improved = false, stop = false;
+    if (end_of_iteration) {
+        const double mean = run_sum / run_cnt;                     // running mean over costs AND earlier means (Q5)
+        run_sum += mean; run_cnt += 1.0;
+        improved = mean < best - pb.tolerance;
+        if (improved) { best = mean; no_imp = 0.0; } else { no_imp += 1.0; }
+        iters += 1.0;
+        stop = (no_imp >= (double)pb.patience) || (iters > (double)pb.max_iter);
+    }
+    const double bc1 = 1.0 - pow(pb.beta1, step), bc2 = 1.0 - pow(pb.beta2, step);
+    const T step_size = (T)(pb.lr / bc1);
+    const T inv_bc2_sqrt = (T)(1.0 / sqrt(bc2));
+    const T w1 = (T)(1.0 - pb.beta1), b2 = (T)pb.beta2, w2 = (T)(1.0 - pb.beta2), eps = (T)pb.eps, clipT = (T)clip;
+    const bool clip_nan = !(clip == clip);
+    T *x = (T *)pb.x + 2LL * pb.n_joints * 3;                       // skip the two halo frames
+    T *m = (T *)pb.m, *v = (T *)pb.v, *bestx = (T *)pb.best;
+    const T *g = (const T *)pb.g;
+    const long long per_frame = (long long)pb.n_joints * 3;
+    const long long n = pb.n_frames * per_frame;
+    const long long lo = (pb.win_begin - pb.frame_offset) * per_frame, hi = (pb.win_end - pb.frame_offset) * per_frame;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        T gi = (i >= lo && i < hi) ? g[i] : (T)0;
+        gi = clip_nan ? (T)NAN : gi * clipT;
+        T mi = m[i], vi = v[i], xi = x[i];
+        mi = mi + (gi - mi) * w1;                                  // exp_avg.lerp_(grad, 1 - beta1)
+        vi = vi * b2 + w2 * gi * gi;                               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const T denom = sqrt(vi) * inv_bc2_sqrt + eps;
+        xi = xi - step_size * (mi / denom);                        // param.addcdiv_(exp_avg, denom, value=-step_size)
+        m[i] = mi; v[i] = vi; x[i] = xi;
+        if (improved) bestx[i] = xi;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double *nx = ctrl + CT_STATE + 16 * (parity ^ 1);
+        nx[0] = step; nx[1] = run_sum; nx[2] = run_cnt; nx[3] = best; nx[4] = no_imp;
+        nx[5] = stop ? 1.0 : 0.0; nx[6] = iters; nx[7] = improved ? 1.0 : 0.0;
+        for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
+        const long long hs = (long long)(step - 1.0);
+        if (hs < pb.hist_capacity) {
+            double *h = ctrl + CT_HIST + 4 * hs;
+            h[0] = dv.total; h[1] = dv.cost_lik; h[2] = dv.cost_s; h[3] = dv.cost_b;
+        }
+    }
+}
+
+// ---- preparation: camera-0 means and inverse covariances (pose_refinement.py:663-668, :885) ----------------------
+template <typename T>
+__global__ void refine_prepare_kernel(const T *__restrict__ gauss, long long n_frames, int n_cams, int n_joints, int cam,
+                                      double eps, T *__restrict__ mu0, T *__restrict__ S) {
+    const long long n = n_frames * n_joints;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long t = e / n_joints;
+        const int j = (int)(e - t * n_joints);
+        const T *gp = gauss + ((t * n_cams + cam) * n_joints + j) * 6;
+        const T c00 = gp[2] + (T)eps, c01 = gp[3], c10 = gp[4], c11 = gp[5] + (T)eps;     // cov + eps I in the state dtype
+        const double det = (double)c00 * (double)c11 - (double)c01 * (double)c10;
+        const double i00 = (double)c11 / det, i11 = (double)c00 / det;
+        const double i01 = -0.5 * ((double)c01 + (double)c10) / det;                        // symmetric part: same d^T S d
+        mu0[e * 2] = gp[0]; mu0[e * 2 + 1] = gp[1];
+        S[e * 3] = (T)i00; S[e * 3 + 1] = (T)i01; S[e * 3 + 2] = (T)i11;
+    }
+}
+
+// ---- standalone projection (project_points_torch, pose_refinement.py:94-179) -----------------------------------
+struct CamParam { double c[26]; };
+
+template <typename T>
+__global__ void project_points_kernel(const T *__restrict__ pts, long long n, const __grid_constant__ CamParam cam,
+                                      int ignore_dist, T *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double X = (double)pts[i * 3], Y = (double)pts[i * 3 + 1], Z = (double)pts[i * 3 + 2];
+        const double *K = cam.c, *R = cam.c + 9, *Tt = cam.c + 18, *D = cam.c + 21;
+        const double xc = fma(R[0], X, fma(R[1], Y, fma(R[2], Z, Tt[0])));
+        const double yc = fma(R[3], X, fma(R[4], Y, fma(R[5], Z, Tt[1])));
+        const double zc = fma(R[6], X, fma(R[7], Y, fma(R[8], Z, Tt[2])));
+        const double a = xc / zc, b = yc / zc;
+        double xd = a, yd = b;
+        if (!ignore_dist) {
+            const double r2 = fma(a, a, b * b);
+            const double rad = fma(fma(fma(D[4], r2, D[1]), r2, D[0]), r2, 1.0);
+            xd = fma(a, rad, fma(2.0 * D[2] * a, b, D[3] * fma(2.0 * a, a, r2)));
+            yd = fma(b, rad, fma(D[2], fma(2.0 * b, b, r2), 2.0 * D[3] * a * b));
+        }
+        const double s = fma(K[6], xd, fma(K[7], yd, K[8]));
+        out[i * 2] = (T)(fma(K[0], xd, fma(K[1], yd, K[2])) / s);
+        out[i * 2 + 1] = (T)(fma(K[3], xd, fma(K[4], yd, K[5])) / s);
+    }
+}
+
+template <typename T>
+int project_points(const T *d_pts, long long n, const double *cam26, int ignore_dist, T *d_out, cudaStream_t stream) {
+    if (n < 0 || !cam26) { set_error("bad arguments"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (n == 0) return MC3D_OK;
+    if (!d_pts || !d_out) { set_error("NULL device pointer"); return MC3D_ERR_INVALID_ARGUMENT; }
+    CamParam cp;
+    for (int i = 0; i < 26; ++i) cp.c[i] = cam26[i];
+    long long grid = (n + 255) / 256;
+    if (grid > (long long)sm_count() * 8) grid = (long long)sm_count() * 8;
+    project_points_kernel<T><<<(unsigned)grid, 256, 0, stream>>>(d_pts, n, cp, ignore_dist, d_out);
+    count_launch();
+    MC3D_CUDA_TRY(cudaGetLastError());
+    return MC3D_OK;
+}
+
+static int validate(const mc3d_refine_problem *pb) {
+    if (!pb) { set_error("NULL problem"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (pb->n_joints < 1 || pb->n_joints > MC3D_MAX_JOINTS) { set_error("n_joints=%d outside [1, %d]", pb->n_joints, MC3D_MAX_JOINTS); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (pb->n_cams < 1 || pb->n_cams > MC3D_MAX_VIEWS) { set_error("n_cams=%d outside [1, %d]", pb->n_cams, MC3D_MAX_VIEWS); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (pb->n_bones < 0 || pb->n_bones > MC3D_MAX_BONES) { set_error("n_bones=%d outside [0, %d]", pb->n_bones, MC3D_MAX_BONES); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (pb->n_frames < 0) { set_error("n_frames < 0"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (!pb->x || !pb->m || !pb->v || !pb->best || !pb->g || !pb->mu0 || !pb->S || !pb->term_ok || !pb->ctrl) {
+        set_error("NULL device pointer in refine problem");
+        return MC3D_ERR_INVALID_ARGUMENT;
+    }
+    for (int k = 0; k < pb->n_bones; ++k)
+        if (pb->bone_start[k] < 0 || pb->bone_start[k] >= pb->n_joints || pb->bone_end[k] < 0 || pb->bone_end[k] >= pb->n_joints) {
+            set_error("bone %d references a joint outside [0, %d)", k, pb->n_joints);
+            return MC3D_ERR_INVALID_ARGUMENT;
+        }
+    return MC3D_OK;
+}
+
+template <typename T>
+int refine_phase(const mc3d_refine_problem *pb, int phase, long long step_index, int end_of_iteration, cudaStream_t stream) {
+    int st = validate(pb);
+    if (st != MC3D_OK) return st;
+    if (pb->n_frames == 0) return MC3D_OK;
+    const int parity = (int)(step_index & 1);
+    const int J = pb->n_joints;
+    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
+    const long long n_tiles = (pb->n_frames + fpb - 1) / fpb;
+    long long grid = (long long)sm_count() * 4;
+    if (grid > n_tiles) grid = n_tiles;
+    const size_t xs_bytes = (size_t)(fpb + 4) * J * 3 * sizeof(double);
+    if (phase == 0) {
+        const size_t smem = xs_bytes + (size_t)fpb * J * sizeof(double) + 8 * 7 * sizeof(double);
+        refine_costs_kernel<T><<<(unsigned)grid, RF_THREADS, smem, stream>>>(*pb, parity);
+    } else if (phase == 1) {
+        const size_t smem = xs_bytes + 8 * sizeof(double);
+        refine_grad_kernel<T><<<(unsigned)grid, RF_THREADS, smem, stream>>>(*pb, parity);
+    } else if (phase == 2) {
+        const long long n = (long long)pb->n_frames * J * 3;
+        long long g2 = (n + RF_THREADS * 4 - 1) / (RF_THREADS * 4);
+        if (g2 > (long long)sm_count() * 8) g2 = (long long)sm_count() * 8;
+        if (g2 < 1) g2 = 1;
+        refine_step_kernel<T><<<(unsigned)g2, RF_THREADS, 0, stream>>>(*pb, parity, end_of_iteration);
+    } else {
+        set_error("bad phase %d", phase);
+        return MC3D_ERR_INVALID_ARGUMENT;
+    }
+    count_launch();
+    MC3D_CUDA_TRY(cudaGetLastError());
+    return MC3D_OK;
+}
+
+// n whole-window iterations on one GPU.  Pairs of iterations (parity 0,1) are captured once into a CUDA graph and
+// replayed, so the per-iteration cost is three graph kernel nodes and no host work.
+template <typename T>
+int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_iters, cudaStream_t stream) {
+    int st = validate(pb);
+    if (st != MC3D_OK) return st;
+    long long done = 0;
+    auto one = [&](long long step) -> int {
+        for (int ph = 0; ph < 3; ++ph) {
+            int s2 = refine_phase<T>(pb, ph, step, 1, stream);
+            if (s2 != MC3D_OK) return s2;
+        }
+        return MC3D_OK;
+    };
+    if ((first_step & 1) && n_iters > 0) { st = one(first_step); if (st != MC3D_OK) return st; done = 1; }
+    const long long pairs = (n_iters - done) / 2;
+    if (pairs >= 4) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const int unroll = pairs >= 32 ? 8 : 1;                     // 2*unroll iterations per graph launch
+        MC3D_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        for (int u = 0; u < 2 * unroll && st == MC3D_OK; ++u) st = one(first_step + done + u);
+        cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+        if (st != MC3D_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+        MC3D_CUDA_TRY(ce);
+        MC3D_CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+        const long long launches = pairs / unroll;
+        for (long long i = 0; i < launches; ++i) MC3D_CUDA_TRY(cudaGraphLaunch(exec, stream));
+        count_launch((int)(launches * 2 * unroll * 3) - 2 * unroll * 3);   // capture counted one replay's worth already
+        done += launches * 2 * unroll;
+        MC3D_CUDA_TRY(cudaStreamSynchronize(stream));               // the exec must outlive its launches
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+    }
+    for (; done < n_iters; ++done) { st = one(first_step + done); if (st != MC3D_OK) return st; }
+    return MC3D_OK;
+}
+
+template <typename T>
+int refine_prepare(const T *d_gauss, long long n_frames, int n_cams, int n_joints, int cam, double eps, T *d_mu0, T *d_S,
+                   cudaStream_t stream) {
+    if (n_frames < 0 || n_cams < 1 || n_joints < 1 || cam < 0 || cam >= n_cams) { set_error("bad gaussians shape"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (n_frames == 0) return MC3D_OK;
+    if (!d_gauss || !d_mu0 || !d_S) { set_error("NULL device pointer"); return MC3D_ERR_INVALID_ARGUMENT; }
+    const long long n = n_frames * n_joints;
+    long long grid = (n + 255) / 256;
+    if (grid > (long long)sm_count() * 8) grid = (long long)sm_count() * 8;
+    refine_prepare_kernel<T><<<(unsigned)grid, 256, 0, stream>>>(d_gauss, n_frames, n_cams, n_joints, cam, eps, d_mu0, d_S);
+    count_launch();
+    MC3D_CUDA_TRY(cudaGetLastError());
+    return MC3D_OK;
+}
+
+}  // namespace mc3d
+
+extern "C" {
+int mc3d_refine_problem_size(void) { return (int)sizeof(mc3d_refine_problem); }
+int mc3d_project_points_f32(const float *d_points, int64_t n, const double *cam26, int ignore_distortions, float *d_out, void *stream) {
+    return mc3d::project_points<float>(d_points, n, cam26, ignore_distortions, d_out, (cudaStream_t)stream);
+}
+int mc3d_project_points_f64(const double *d_points, int64_t n, const double *cam26, int ignore_distortions, double *d_out, void *stream) {
+    return mc3d::project_points<double>(d_points, n, cam26, ignore_distortions, d_out, (cudaStream_t)stream);
+}
+int mc3d_refine_prepare_f32(const float *d_gauss, int64_t n_frames, int n_cams, int n_joints, int cam, double eps,
+                            float *d_mu0, float *d_S, void *stream) {
+    return mc3d::refine_prepare<float>(d_gauss, n_frames, n_cams, n_joints, cam, eps, d_mu0, d_S, (cudaStream_t)stream);
+}
+int mc3d_refine_prepare_f64(const double *d_gauss, int64_t n_frames, int n_cams, int n_joints, int cam, double eps,
+                            double *d_mu0, double *d_S, void *stream) {
+    return mc3d::refine_prepare<double>(d_gauss, n_frames, n_cams, n_joints, cam, eps, d_mu0, d_S, (cudaStream_t)stream);
+}
+int mc3d_refine_phase_f32(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream) {
+    return mc3d::refine_phase<float>(pb, phase, step_index, end_of_iteration, (cudaStream_t)stream);
+}
+int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream) {
+    return mc3d::refine_phase<double>(pb, phase, step_index, end_of_iteration, (cudaStream_t)stream);
+}
+int mc3d_refine_run_f32(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream) {
+    return mc3d::refine_run<float>(pb, first_step, n_iters, (cudaStream_t)stream);
+}
+int mc3d_refine_run_f64(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream) {
+    return mc3d::refine_run<double>(pb, first_step, n_iters, (cudaStream_t)stream);
+}
+}

@@ -1,0 +1,378 @@
+"""Drop-in for the hot-path part of the reference's ``pose_refinement`` module.
+
+``Optimized_3d_Pose_Estimation(...).sgd_optimize(**yaml['SGD'])`` keeps the reference's constructor and
+keyword names (pose_refinement.py:579, :894) and result attributes (``best_trajectory``, ``trajectory``,
+``all_costs_total``, ...), but every iteration runs as CUDA kernels (csrc/refine.cu) with the state resident on
+the GPU; under ``torchrun`` with several ranks the frames are sharded across the GPUs (refinement.py).
+
+Upstream behaviour that is reproduced on purpose: camera 0's Gaussians are
+used for every camera; Gaussian means are compared with image-pixel projections unscaled; the default
+``time_interval=[0, -1]`` drops the last frame; ``max_iter + 1`` iterations run; the early-stopping statistic is a
+running mean over a list that also holds its own earlier values.  ``per_camera_gaussians=True`` is NOT offered:
+the kernel keeps one Gaussian per (frame, joint) because that is what upstream evaluates.
+
+Out of scope (raise NotImplementedError): learning extrinsics (``extrinsic_optimization_IDs``,
+``optimize_trajectory=False``), ``use_NN``, ``randomize_params`` -- SURVEY.md section 8(f3).
+"""
+import argparse
+import math
+import os
+import pickle as pk
+from pathlib import Path
+
+import numpy as np
+import yaml
+
+from . import _lib
+from . import refinement as _ref
+from . import utils
+
+
+def _torch():
+    import torch
+    return torch
+
+
+# ---- module-level helpers of the reference -------------------------------------------------------------------------
+def project_points_torch(points, K, R, T, dist_coeffs, indicies=None, torch_dtype=None, ignore_distortions=False):
+    """Pinhole + Brown-distortion projection of a (Time, N, 3) trajectory to (Time, N, 2) pixels
+    (pose_refinement.py:94-179), on the GPU.  Returns a CPU torch tensor like upstream (inputs may be numpy arrays,
+    CPU or CUDA tensors; a CUDA input gives a CUDA result)."""
+    torch = _torch()
+    torch_dtype = torch_dtype or torch.float32
+    pts = torch.as_tensor(points)
+    if pts.dim() != 3 or pts.shape[2] != 3:
+        raise AssertionError('points must have shape (Time, N, 3)')
+    Kn, Tn = _ref._as_numpy(K), _ref._as_numpy(T)
+    dn = np.asarray(_ref._as_numpy(dist_coeffs), dtype=np.float64)
+    assert Kn.shape == (3, 3), 'K must have shape (3, 3)'
+    assert Tn.shape in ((3, 1), (3,)), 'T must have shape (3,) or (3, 1)'
+    assert dn.shape == (1, 5), 'dist_coeffs must have shape (1, 5)'
+    row = _ref.camera_rows({0: [Kn, R, Tn, dn]}, [0])[0]
+    # upstream rounds the camera to torch_dtype before projecting (:98-112)
+    row = np.asarray(torch.tensor(row, dtype=torch_dtype).to(torch.float64).numpy())
+    was_cuda = pts.is_cuda
+    dev = pts.device if was_cuda else torch.device('cuda', torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    if indicies is not None:
+        pts = pts[list(indicies)]
+    if not was_cuda and not torch.cuda.is_available():
+        raise _lib.Mc3dError('project_points_torch needs a CUDA device (no CPU fallback)')
+    p = pts.to(device=dev, dtype=torch_dtype).contiguous()
+    out = torch.empty(p.shape[:2] + (2,), dtype=torch_dtype, device=dev)
+    fn = _lib.lib().mc3d_project_points_f32 if torch_dtype == torch.float32 else _lib.lib().mc3d_project_points_f64
+    with torch.cuda.device(dev):
+        _lib.check(fn(p.data_ptr(), p.shape[0] * p.shape[1], row.ctypes.data, int(bool(ignore_distortions)),
+                      out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return out if was_cuda else out.cpu()
+
+
+def nan_mean(X):
+    """Mean over the finite entries of a list of tensors (pose_refinement.py:221-229).  Small helper kept for API
+    compatibility; the optimiser computes its masked means inside the kernels."""
+    torch = _torch()
+    stacked = torch.stack(X)
+    mask = ~(torch.isnan(stacked) | torch.isinf(stacked))
+    return torch.sum(stacked[mask]) / len(stacked[mask])
+
+
+def gaussian_likelihood(x, mean, cov_mat, eps=1e-6, torch_dtype=None):
+    """Log-likelihood of x under 2D Gaussians incl. the normalisation term (pose_refinement.py:182-218); API
+    helper in plain torch ops on the caller's tensors (the optimiser does not call it)."""
+    torch = _torch()
+    torch_dtype = torch_dtype or torch.float32
+    cov = cov_mat + eps * torch.eye(cov_mat.size(-1), device=cov_mat.device).expand_as(cov_mat)
+    cov_inv = torch.linalg.inv(cov).to(torch_dtype)
+    diff = x - mean
+    quad = -0.5 * torch.einsum('...i,...ij,...j->...', diff, cov_inv, diff)
+    norm = 0.5 * torch.log((2 * torch.pi) ** 2 * torch.det(cov) + eps)
+    return quad - norm
+
+
+# ---- the optimiser ----------------------------------------------------------------------------------------------------
+class Optimized_3d_Pose_Estimation:
+    """Maximum-likelihood trajectory refinement under smoothness and bone-length constraints.
+
+    Args (pose_refinement.py:579):
+      gaussians                      (Time, C, n_joints, 6) [mean_x, mean_y, var_x, cov, cov, var_y] per camera
+      initial_trajectory             (Time, n_joints, 3)
+      decomposed_cam_params_initial  dict id -> [K, R, T, dist]   (R/T None -> identity / zero)
+      body_lengths                   dict bone name -> target length (utils.POINT_INFO naming)
+      camera_IDs                     cameras in the likelihood (default: all)
+      torch_dtype                    torch.float32 (default) or torch.float64: dtype of the optimiser state
+      device                         extra: CUDA device (default: LOCAL_RANK under torchrun, else current)
+    """
+
+    def __init__(self, gaussians, initial_trajectory, decomposed_cam_params_initial=None, body_lengths=None,
+                 camera_IDs=None, R_initial=None, T_initial=None, N_sample_points=100, torch_dtype=None, device=None):
+        torch = _torch()
+        torch_dtype = torch_dtype or torch.float32
+        if decomposed_cam_params_initial is None:
+            raise TypeError("'NoneType' object is not iterable")                  # upstream iterates it unconditionally (:608)
+        for cid in decomposed_cam_params_initial:
+            if decomposed_cam_params_initial[cid][1] is None:
+                decomposed_cam_params_initial[cid][1] = torch.eye(3)
+            if decomposed_cam_params_initial[cid][2] is None:
+                decomposed_cam_params_initial[cid][2] = torch.zeros(3, 1)
+        self.gaussians = torch.as_tensor(gaussians).to(torch_dtype).clone()
+        self.decomposed_cam_params_initial = {
+            cid: [torch.as_tensor(np.asarray(_ref._as_numpy(cp)), dtype=torch_dtype) for cp in decomposed_cam_params_initial[cid]]
+            for cid in decomposed_cam_params_initial}
+        self.decomposed_cam_params = {cid: [cp.clone().detach() for cp in self.decomposed_cam_params_initial[cid]]
+                                      for cid in self.decomposed_cam_params_initial}
+        self.n_cams = self.gaussians.shape[1]
+        self.N_sample_points = N_sample_points
+        self.initial_trajectory = torch.as_tensor(initial_trajectory).to(torch_dtype).clone()
+        self.torch_dtype = torch_dtype
+        self.n_dims = self.initial_trajectory.shape[2]
+        if self.n_dims != 3:
+            raise NotImplementedError('only 3D trajectories are supported')
+        self.n_joints = self.gaussians.shape[2]
+        self.body_lengths = body_lengths
+        self.camera_IDs = camera_IDs if camera_IDs is not None else list(decomposed_cam_params_initial.keys())
+        self.camera_indices = [list(self.decomposed_cam_params.keys()).index(cid) for cid in self.camera_IDs]
+        self.device = device
+        self.best_trajectory = None
+        self.best_decomposed_cam_params = None
+        self.trajectory = None
+        self.all_costs_total = None
+
+    def _pick_device(self):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.Mc3dError('sgd_optimize needs a CUDA device (no CPU fallback)')
+        if self.device is not None:
+            return torch.device(self.device)
+        if 'LOCAL_RANK' in os.environ and torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.device('cuda', int(os.environ['LOCAL_RANK']))
+        return torch.device('cuda', torch.cuda.current_device())
+
+    def create_batch_indices(self):
+        """Half-overlapping windows of ``batch_size`` frames (pose_refinement.py:786-796)."""
+        step = self.batch_size // 2
+        return [list(range(s, s + self.batch_size)) for s in range(0, self.Time - self.batch_size + 1, step)]
+
+    def sgd_optimize(self, extrinsic_optimization_IDs=[], optimize_trajectory=True, lr=0.001, betas=(0.9, 0.999),
+                     lambda_smooth=1.0, lambda_body_length=1.0, patience=100, tolerance=1e-5, max_iter=1000,
+                     print_frequency=100, batch_size=None, N_sample_points=100, GT_camera_IDs=None,
+                     ignore_distortions=False, reset_camera_params=False, print_compute_times=False,
+                     time_interval=[0, -1], randomize_params=False, use_NN=False):
+        torch = _torch()
+        if len(extrinsic_optimization_IDs) or not optimize_trajectory:
+            raise NotImplementedError('learning camera extrinsics is outside the accelerated path (SURVEY.md 8(f3))')
+        if use_NN or randomize_params:
+            raise NotImplementedError('use_NN / randomize_params are outside the accelerated path (SURVEY.md 8(f3))')
+        if self.body_lengths is None:
+            raise AttributeError("'NoneType' object has no attribute 'values'")   # create_body_length_vect, :770
+
+        t0, t1 = time_interval[0], time_interval[1]
+        gaussians_subset = self.gaussians[t0:t1]
+        self.Time = len(gaussians_subset)
+        if batch_size is None:
+            batch_size = self.Time
+        self.Time = int(np.floor(self.Time / batch_size) * batch_size)
+        self.gaussians_subset = gaussians_subset[:self.Time]
+        if reset_camera_params:
+            self.decomposed_cam_params = {cid: [cp.clone().detach() for cp in self.decomposed_cam_params_initial[cid]]
+                                          for cid in self.decomposed_cam_params_initial}
+        self.n_cams = len(self.camera_IDs)
+        self.GT_camera_IDs = GT_camera_IDs
+        self.ignore_distortions = ignore_distortions
+        self.extrinsic_optimization_IDs = extrinsic_optimization_IDs
+        self.batch_size = batch_size
+        self.lambda_smooth, self.lambda_body_length = lambda_smooth, lambda_body_length
+        trajectory0 = self.initial_trajectory[t0:t1].clone().detach()
+        windows = [(b[0], b[-1] + 1) for b in self.create_batch_indices()]
+        if not windows:
+            raise ValueError('time_interval / batch_size leave no frames to optimise')
+
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1
+        if dist_on and len(windows) > 1:
+            raise NotImplementedError('batch_size windows are sequential Adam steps and do not shard; run them on one GPU')
+        comm = _ref.DistComm() if dist_on else _ref.LocalComm()
+        device = self._pick_device()
+        n_iters_max = int(max_iter) + 1 if math.isfinite(max_iter) else 2 ** 31 - 2      # `iteration <= max_iter` (Q4)
+        hist_cap = min(n_iters_max * len(windows), 4_000_000)
+        cam_rows = _ref.camera_rows(self.decomposed_cam_params, self.camera_IDs)
+        cam_rows = torch.tensor(cam_rows, dtype=self.torch_dtype).to(torch.float64).numpy()   # cameras live in torch_dtype upstream
+
+        engine = _ref.RefineEngine(trajectory0, self.gaussians_subset, cam_rows, self.body_lengths,
+                                   torch_dtype=self.torch_dtype, device=device, lr=lr, betas=betas,
+                                   lambda_smooth=lambda_smooth, lambda_body_length=lambda_body_length,
+                                   patience=patience, tolerance=tolerance, max_iter=max_iter,
+                                   ignore_distortions=ignore_distortions, window=windows[0],
+                                   n_window_frames=batch_size, hist_capacity=hist_cap, comm=comm)
+        self._engine = engine
+        names = ['total_cost', 'likelihood_cost'] + (['smoothness_cost'] if lambda_smooth > 0 else []) + \
+                (['body_length_cost'] if lambda_body_length > 0 else [])
+        col = {'total_cost': 0, 'likelihood_cost': 1, 'smoothness_cost': 2, 'body_length_cost': 3}
+        chunk = max(1, int(print_frequency)) if print_frequency and math.isfinite(print_frequency) else 100
+        chunk = min(chunk, 1000)
+        iters_done, printed = 0, 0
+        stopped_early = False
+        with torch.cuda.device(device):
+            while iters_done < n_iters_max:
+                n = min(chunk, n_iters_max - iters_done)
+                if len(windows) == 1:
+                    engine.run(n)
+                else:
+                    for _ in range(n):
+                        for wi, (wb, we) in enumerate(windows):
+                            engine.set_window(wb, we)
+                            engine.one_step(end_of_iteration=(wi == len(windows) - 1))
+                st = engine.state()
+                iters_done = st['iterations']
+                hist = engine.history(st['adam_step'])
+                means = _running_means(hist[:, 0], len(windows))
+                if print_frequency and math.isfinite(print_frequency):
+                    while printed < iters_done:
+                        if printed % int(print_frequency) == 0 and not (st['stopped'] and printed == iters_done - 1 and
+                                                                        st['no_improve'] >= patience):
+                            cur = {nm: _running_means(hist[:, col[nm]], len(windows))[printed] for nm in names}
+                            print(f'Iteration {printed}: ' + ', '.join(f'{k}: {v:.2e}' for k, v in cur.items()))
+                        printed += 1
+                if st['stopped'] or np.isnan(means[-1] if len(means) else 0.0):
+                    stopped_early = st['no_improve'] >= patience
+                    break
+        st = engine.state()
+        hist = engine.history(st['adam_step'])
+        if stopped_early:
+            cur = {nm: _running_means(hist[:, col[nm]], len(windows))[-1] for nm in names}
+            print(f"Early stopping at iteration {st['iterations'] - 1}. " + ', '.join(f'{k}: {v:.2e}' for k, v in cur.items()))
+
+        # results, in the reference's containers
+        self.trajectory = engine.trajectory().cpu()
+        improved_once = math.isfinite(st['best'])
+        self.best_trajectory = engine.best_trajectory().cpu() if improved_once else None
+        self.best_decomposed_cam_params = {k: [p.clone().detach() for p in self.decomposed_cam_params[k]]
+                                           for k in self.decomposed_cam_params} if improved_once else None
+        self.all_costs_total = {}
+        for nm in names:
+            self.all_costs_total[nm] = _interleave_history(hist[:, col[nm]], len(windows), self.torch_dtype)
+        self.iterations = st['iterations']
+        return self
+
+
+def _running_means(costs, steps_per_iter):
+    """The reference's per-iteration statistic (pose_refinement.py:1069-1071): after each iteration the mean of the
+    list holding every step cost so far AND every earlier mean is appended to that same list (quirk Q5)."""
+    means, s, n = [], 0.0, 0
+    for i in range(len(costs) // steps_per_iter):
+        for c in costs[i * steps_per_iter:(i + 1) * steps_per_iter]:
+            s += float(c)
+            n += 1
+        mean = s / n
+        means.append(mean)
+        s += mean
+        n += 1
+    return means
+
+
+def _interleave_history(costs, steps_per_iter, torch_dtype):
+    """[cost..., running mean, cost..., running mean, ...] with upstream's element types: 0-d tensors for the step
+    costs, numpy scalars for the means."""
+    torch = _torch()
+    np_dtype = np.float32 if torch_dtype == torch.float32 else np.float64
+    out = []
+    means = _running_means(costs, steps_per_iter)
+    for i, mean in enumerate(means):
+        for c in costs[i * steps_per_iter:(i + 1) * steps_per_iter]:
+            out.append(torch.tensor(float(c), dtype=torch_dtype))
+        out.append(np_dtype(mean))
+    return out
+
+
+# ---- command line (pose_refinement.py:1099-1256) ------------------------------------------------------------------------
+def main(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--run_path', type=str)
+    parser.add_argument('--refinement_types', nargs='+', default=['linear_interpolation'])
+    parser.add_argument('--recording_log', type=str)
+    parser.add_argument('--heatmaps_2d', type=str)
+    parser.add_argument('--kpts_2d', type=str)
+    parser.add_argument('--kpts_3d', type=str)
+    parser.add_argument('--model', type=str)
+    parser.add_argument('--save_path', type=str)
+    parser.add_argument('--extrinsic_params_dir', type=str)
+    parser.add_argument('--intrinsic_params_dir', type=str)
+    parser.add_argument('--refinement_params_yaml', type=str)
+    parser.add_argument('--body_part_lengths_yaml', type=str)
+    parser.add_argument('--body_part_lengths_individual_name_yaml', default='my_lengths', type=str)
+    parser.add_argument('--ignore_body_lengths', action='store_true')
+    parser.add_argument('--interpolate_before_SGD', action='store_true')
+    args = parser.parse_args(argv)
+    torch = _torch()
+
+    if args.run_path is None:
+        args.run_path = os.getcwd()
+    if args.save_path is None:
+        args.save_path = args.run_path
+    if args.extrinsic_params_dir is None:
+        args.extrinsic_params_dir = Path(args.run_path).parent.parent / 'extrinsic_camera_parameters'
+    if args.intrinsic_params_dir is None:
+        args.intrinsic_params_dir = os.path.join(os.getcwd(), 'intrinsic_camera_parameters')
+
+    log = {}
+    if args.recording_log is not None:
+        with open(args.recording_log) as fh:
+            log = yaml.safe_load(fh)
+    elif os.path.exists(os.path.join(args.run_path, 'recording_log.yaml')):
+        with open(os.path.join(args.run_path, 'recording_log.yaml')) as fh:
+            log = yaml.safe_load(fh)
+    args.recording_log = log
+    for name, value in vars(args).items():          # unset flags come from the recording log (:1142-1144)
+        if value is None and name in log:
+            setattr(args, name, log[name])
+
+    kpts_3d = utils.load_if_exists(args.kpts_3d)
+    utils.load_if_exists(args.kpts_2d) if args.kpts_2d else None
+    heatmaps = utils.load_if_exists(args.heatmaps_2d) if args.heatmaps_2d else None
+    refinement_types = set(args.refinement_types)
+    params = utils.load_config(args.refinement_params_yaml)
+
+    kpts_3d_interpolation = None
+    if 'linear_interpolation' in refinement_types or args.interpolate_before_SGD:
+        from .interpolation import linear_interpolation
+        kwargs = utils.prepare_kwargs(linear_interpolation, params.get('linear_interpolation'))
+        kpts_3d_interpolation = linear_interpolation(kpts_3d, **kwargs)
+    if 'linear_interpolation' in refinement_types:
+        out = os.path.join(args.save_path, 'kpts_3d_linear_interpolation.npy')
+        print(f'saving linear interpolation at {out}')
+        np.save(out, kpts_3d_interpolation)
+        refinement_types.remove('linear_interpolation')
+
+    if 'SGD' in refinement_types:
+        with open(os.path.join(args.extrinsic_params_dir, 'camera_names.pkl'), 'rb') as fh:
+            cameras, _origin_camera = pk.load(fh)
+        decomposed = {}
+        for i in cameras.keys():
+            _, decomposed[i] = utils.get_params_from_name(cameras[i], intrinsic_params_dir=args.intrinsic_params_dir,
+                                                          extrinsic_params_dir=args.extrinsic_params_dir)
+        my_lengths = None
+        if not args.ignore_body_lengths:
+            if args.body_part_lengths_yaml is None and os.path.exists('./body_part_lengths.yaml'):
+                args.body_part_lengths_yaml = './body_part_lengths.yaml'
+            if args.body_part_lengths_yaml is not None:
+                with open(args.body_part_lengths_yaml) as fh:
+                    my_lengths = yaml.safe_load(fh)[args.body_part_lengths_individual_name_yaml]
+        if args.interpolate_before_SGD:
+            kpts_3d = kpts_3d_interpolation
+        opt = Optimized_3d_Pose_Estimation(torch.tensor(heatmaps), kpts_3d, decomposed_cam_params_initial=decomposed,
+                                           body_lengths=my_lengths)
+        kwargs = utils.prepare_kwargs(opt.sgd_optimize, params.get('SGD'))
+        opt.sgd_optimize(**kwargs)
+        if my_lengths is not None:
+            for title, traj in (("mean and standardized error of initial trajectory's body part lengths", opt.initial_trajectory),
+                                ("mean and standardized error of the estimated trajectory's' body part lengths", opt.best_trajectory)):
+                print(title)
+                lengths = utils.get_body_part_lengths(traj)
+                for bp in my_lengths:
+                    print('; '.join([bp, str(torch.mean(lengths[bp])), str(torch.std(lengths[bp]))]))
+        out = os.path.join(args.save_path, 'kpts_3d_SGD.npy')
+        print(f'saving SGD at {out}')
+        np.save(out, np.array(opt.best_trajectory))
+        refinement_types.remove('SGD')
+
+
+if __name__ == '__main__':
+    main()

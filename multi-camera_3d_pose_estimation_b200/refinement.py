@@ -1,0 +1,311 @@
+"""Device-side engine of the trajectory refinement (host side of csrc/refine.cu).
+
+``RefineEngine`` owns the frame-sharded state of one rank (trajectory with a two-frame halo, Adam moments,
+best snapshot, gradient scratch, camera-0 means / inverse covariances, the double control block) and drives
+the three phases of an optimiser step.  With ``world_size > 1`` (``torch.distributed`` initialised, one
+process per GPU) frames are sharded contiguously and the ONLY traffic per step is
+
+    after phase 2 (previous step):  x halo   -- 2 frames to each neighbour             (point-to-point)
+    after phase 0:                  all-reduce of 7 doubles + 2 term_ok halo bytes to the left neighbour
+    after phase 1:                  all-reduce of 1 double (sum g^2)
+
+so every rank takes identical clip / Adam / early-stopping decisions with no further communication
+(SURVEY.md section 8e).  The collectives are injected (``comm``) so the same driver runs over NCCL on GPUs and
+over gloo on CPU tensors in the tests.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from . import utils as _utils
+
+
+def frame_shard(n_frames, rank, world):
+    """Contiguous, balanced [begin, end) of ``n_frames`` for ``rank`` of ``world`` (first ranks get the remainder)."""
+    base, rem = divmod(n_frames, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def bone_tables(body_lengths, n_joints, connectivity_type='coco'):
+    """yaml bones -> (start[], end[], length[]) in yaml key order, plus the joint->bones CSR adjacency.
+    Bone names are ``<start>_<end>`` from utils.POINT_INFO (utils.py:1175-1181); an unknown name raises
+    KeyError exactly like upstream's ``BPL[bl]`` lookup (pose_refinement.py:851)."""
+    bones = _utils.CONNECTIVITY_DICT[connectivity_type]
+    names = _utils.generate_connectivity_names(bones, _utils.POINT_INFO[connectivity_type])
+    by_name = {names[i]: bones[i] for i in range(len(bones))}
+    start, end, length = [], [], []
+    for key, val in body_lengths.items():
+        s, e = by_name[key]
+        if max(s, e) >= n_joints:
+            raise IndexError(f'bone {key} needs joint {max(s, e)} but the trajectory has {n_joints} joints')
+        start.append(s)
+        end.append(e)
+        length.append(float(val))
+    if len(start) > _lib.MAX_BONES:
+        raise ValueError(f'at most {_lib.MAX_BONES} bones are supported')
+    adj = [[] for _ in range(n_joints)]
+    for k, (s, e) in enumerate(zip(start, end)):
+        adj[e].append((k, +1))
+        adj[s].append((k, -1))
+    adj_start, adj_bone, adj_sign = [0], [], []
+    for j in range(n_joints):
+        for k, sg in adj[j]:
+            adj_bone.append(k)
+            adj_sign.append(sg)
+        adj_start.append(len(adj_bone))
+    return start, end, length, adj_start, adj_bone, adj_sign
+
+
+def camera_rows(cam_params, camera_ids):
+    """[K9 R9 T3 dist5] rows (float64) for the likelihood cameras.  R may be a rotation matrix or an axis-angle
+    vector (utils.rotation_conversion, pose_refinement.py:114)."""
+    rows = []
+    for cid in camera_ids:
+        K, R, T, dist = cam_params[cid]
+        R = np.asarray(_as_numpy(R), dtype=np.float64)
+        if R.shape != (3, 3):
+            R = np.asarray(_utils.rotation_conversion(R.reshape(3), to_vector=False), dtype=np.float64)
+        d = np.zeros(5)
+        dd = np.asarray(_as_numpy(dist), dtype=np.float64).reshape(-1)
+        d[:min(5, dd.size)] = dd[:5]
+        rows.append(np.concatenate([np.asarray(_as_numpy(K), dtype=np.float64).reshape(9), R.reshape(9),
+                                    np.asarray(_as_numpy(T), dtype=np.float64).reshape(3), d]))
+    return np.stack(rows)
+
+
+def _as_numpy(a):
+    return a.detach().cpu().numpy() if hasattr(a, 'detach') else np.asarray(a)
+
+
+class LocalComm:
+    """Single-process stand-in for the collectives."""
+    rank, world = 0, 1
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def exchange_halo(self, x_ext, n_local):
+        pass
+
+    def exchange_term_ok(self, term_ok, n_local):
+        pass
+
+    def all_gather_frames(self, local, total_frames):
+        return local
+
+
+class DistComm:
+    """torch.distributed collectives for the frame-sharded refinement (NCCL on GPUs, gloo on CPU tensors)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def _sendrecv(self, ops):
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def exchange_halo(self, x_ext, n_local):
+        """x_ext (n_local + 4, J, 3): send my first / last two frames, receive the neighbours' into the halo."""
+        P2P = self.dist.P2POp
+        ops = []
+        if self.rank > 0:
+            ops.append(P2P(self.dist.isend, x_ext[2:4].contiguous(), self.rank - 1, self.group))
+            ops.append(P2P(self.dist.irecv, x_ext[0:2], self.rank - 1, self.group))
+        if self.rank < self.world - 1:
+            ops.append(P2P(self.dist.isend, x_ext[n_local:n_local + 2].contiguous(), self.rank + 1, self.group))
+            ops.append(P2P(self.dist.irecv, x_ext[n_local + 2:n_local + 4], self.rank + 1, self.group))
+        self._sendrecv(ops)
+
+    def exchange_term_ok(self, term_ok, n_local):
+        """The smoothness terms ending at my first two frames are needed by the left neighbour's gradient."""
+        P2P = self.dist.P2POp
+        ops = []
+        if self.rank > 0:
+            ops.append(P2P(self.dist.isend, term_ok[2:4].contiguous(), self.rank - 1, self.group))
+        if self.rank < self.world - 1:
+            ops.append(P2P(self.dist.irecv, term_ok[n_local + 2:n_local + 4], self.rank + 1, self.group))
+        self._sendrecv(ops)
+
+    def all_gather_frames(self, local, total_frames):
+        import torch
+        sizes = [frame_shard(total_frames, r, self.world) for r in range(self.world)]
+        longest = max(e - b for b, e in sizes)
+        pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        self.dist.all_gather(out, pad, group=self.group)
+        return torch.cat([o[:e - b] for o, (b, e) in zip(out, sizes)], dim=0)
+
+
+class CudaPhases:
+    """The three phases on the GPU through the C ABI (mc3d_refine_phase_* / mc3d_refine_run_*)."""
+
+    def __init__(self, dtype_tag):
+        lib = _lib.lib()
+        self.phase_fn = getattr(lib, f'mc3d_refine_phase_{dtype_tag}')
+        self.run_fn = getattr(lib, f'mc3d_refine_run_{dtype_tag}')
+
+    def phase(self, problem, phase, step, end_of_iteration, stream):
+        _lib.check(self.phase_fn(ctypes.byref(problem), phase, step, int(end_of_iteration), stream))
+
+    def run(self, problem, first_step, n_iters, stream):
+        _lib.check(self.run_fn(ctypes.byref(problem), first_step, n_iters, stream))
+
+
+class RefineEngine:
+    """Frame-sharded optimiser state of one rank plus the step driver."""
+
+    def __init__(self, trajectory, gaussians, cam_rows, body_lengths, *, torch_dtype, device, lr, betas,
+                 lambda_smooth, lambda_body_length, patience, tolerance, max_iter, ignore_distortions,
+                 window, n_window_frames, hist_capacity, comm=None, phases=None, gaussian_camera=0, adam_eps=1e-8):
+        import torch
+        self.torch = torch
+        self.comm = comm or LocalComm()
+        self.dtype = torch_dtype
+        self.tag = 'f32' if torch_dtype == torch.float32 else 'f64'
+        if torch_dtype not in (torch.float32, torch.float64):
+            raise TypeError('torch_dtype must be float32 or float64')
+        self.device = torch.device(device)
+        self.total_frames = int(trajectory.shape[0])
+        self.J = int(trajectory.shape[1])
+        if self.J > _lib.MAX_JOINTS:
+            raise ValueError(f'at most {_lib.MAX_JOINTS} joints are supported')
+        self.begin, self.end = frame_shard(self.total_frames, self.comm.rank, self.comm.world)
+        n = self.n_local = self.end - self.begin
+        dev, dt = self.device, torch_dtype
+
+        traj = torch.as_tensor(trajectory).to(dt)
+        self.x_ext = torch.zeros((n + 4, self.J, 3), dtype=dt, device=dev)
+        self.x_ext[2:n + 2] = traj[self.begin:self.end].to(dev)
+        self.m = torch.zeros((n, self.J, 3), dtype=dt, device=dev)
+        self.v = torch.zeros_like(self.m)
+        self.best = torch.zeros_like(self.m)
+        self.g = torch.zeros_like(self.m)
+        self.term_ok = torch.zeros((n + 4,), dtype=torch.uint8, device=dev)
+        self.mu0 = torch.zeros((n, self.J, 2), dtype=dt, device=dev)
+        self.S = torch.zeros((n, self.J, 3), dtype=dt, device=dev)
+        self.hist_capacity = int(hist_capacity)
+        self.ctrl = torch.zeros((_lib.CT_HIST + 4 * self.hist_capacity,), dtype=torch.float64, device=dev)
+        self.ctrl[_lib.CT_STATE + 3] = math.inf
+        self.ctrl[_lib.CT_STATE + 16 + 3] = math.inf
+
+        # camera-0 means and inverse covariances for my frames (frames beyond the gaussians stay zero: never in a window)
+        g_all = torch.as_tensor(gaussians).to(dt)
+        n_g = max(0, min(self.end, int(g_all.shape[0])) - self.begin)
+        self.n_cams_in_gaussians = int(g_all.shape[1])
+        if n_g > 0:
+            g_loc = g_all[self.begin:self.begin + n_g].to(dev).contiguous()
+            if dev.type == 'cuda':
+                fn = getattr(_lib.lib(), f'mc3d_refine_prepare_{self.tag}')
+                with torch.cuda.device(dev):
+                    _lib.check(fn(g_loc.data_ptr(), n_g, int(g_loc.shape[1]), self.J, int(gaussian_camera), 1e-6,
+                                  self.mu0.data_ptr(), self.S.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                    torch.cuda.current_stream().synchronize()           # g_loc may be freed after this
+            else:
+                self._prepare_host(g_loc, n_g, gaussian_camera)
+
+        start, end_, length, adj_start, adj_bone, adj_sign = bone_tables(body_lengths, self.J)
+        pb = self.problem = _lib.RefineProblem()
+        pb.n_joints, pb.n_cams, pb.n_bones = self.J, int(cam_rows.shape[0]), len(start)
+        if pb.n_cams > _lib.MAX_VIEWS:
+            raise ValueError(f'at most {_lib.MAX_VIEWS} cameras are supported')
+        pb.ignore_distortions = int(bool(ignore_distortions))
+        pb.patience = int(min(patience, 2 ** 31 - 1)) if math.isfinite(patience) else 2 ** 31 - 1
+        pb.max_iter = int(min(max_iter, 2 ** 31 - 2)) if math.isfinite(max_iter) else 2 ** 31 - 2
+        pb.n_frames, pb.frame_offset = n, self.begin
+        pb.win_begin, pb.win_end = int(window[0]), int(window[1])
+        pb.hist_capacity = self.hist_capacity
+        pb.lr, pb.beta1, pb.beta2, pb.eps = float(lr), float(betas[0]), float(betas[1]), float(adam_eps)
+        pb.lambda_smooth, pb.lambda_body = float(lambda_smooth), float(lambda_body_length)
+        pb.tolerance = float(tolerance)
+        pb.aa = float(n_window_frames) * float(sum(a * a for a in length))
+        for c in range(pb.n_cams):
+            for i in range(26):
+                pb.cams[c][i] = float(cam_rows[c, i])
+        for k in range(len(start)):
+            pb.bone_start[k], pb.bone_end[k], pb.bone_len[k] = start[k], end_[k], length[k]
+        for i, a in enumerate(adj_start):
+            pb.adj_start[i] = a
+        for i, (b, sg) in enumerate(zip(adj_bone, adj_sign)):
+            pb.adj_bone[i], pb.adj_sign[i] = b, sg
+        for name in ('m', 'v', 'best', 'g', 'mu0', 'S', 'term_ok', 'ctrl'):
+            setattr(pb, name, getattr(self, name).data_ptr())
+        pb.x = self.x_ext.data_ptr()
+        self.phases = phases or CudaPhases(self.tag)
+        self.step = 0
+        if self.comm.world > 1:
+            self.comm.exchange_halo(self.x_ext, n)
+
+    def _prepare_host(self, g_loc, n_g, cam):
+        # CPU tensors exist only for the gloo tests of the sharding logic (tests inject their own phases).
+        torch = self.torch
+        gp = g_loc[:, cam]
+        c00, c01, c10, c11 = gp[..., 2] + 1e-6, gp[..., 3], gp[..., 4], gp[..., 5] + 1e-6
+        det = c00.double() * c11.double() - c01.double() * c10.double()
+        self.mu0[:n_g] = gp[..., :2]
+        self.S[:n_g] = torch.stack([c11.double() / det, -0.5 * (c01.double() + c10.double()) / det,
+                                    c00.double() / det], dim=-1).to(self.dtype)
+
+    # ---- stepping ------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return self.torch.cuda.current_stream().cuda_stream if self.device.type == 'cuda' else None
+
+    def set_window(self, begin, end):
+        self.problem.win_begin, self.problem.win_end = int(begin), int(end)
+
+    def one_step(self, end_of_iteration=True):
+        """Phases 0, 1, 2 with the inter-rank exchanges in between."""
+        p = self.step & 1
+        acc = self.ctrl[_lib.CT_ACC + 16 * p:_lib.CT_ACC + 16 * p + 8]
+        st = self._stream()
+        self.phases.phase(self.problem, 0, self.step, end_of_iteration, st)
+        if self.comm.world > 1:
+            self.comm.all_reduce_sum(acc[0:7])
+            self.comm.exchange_term_ok(self.term_ok, self.n_local)
+        self.phases.phase(self.problem, 1, self.step, end_of_iteration, st)
+        if self.comm.world > 1:
+            self.comm.all_reduce_sum(acc[7:8])
+        self.phases.phase(self.problem, 2, self.step, end_of_iteration, st)
+        if self.comm.world > 1:
+            self.comm.exchange_halo(self.x_ext, self.n_local)
+        self.step += 1
+
+    def run(self, n_iters):
+        """``n_iters`` whole-window iterations.  One rank: a single C call replaying a CUDA graph."""
+        if self.comm.world == 1 and hasattr(self.phases, 'run') and self.device.type == 'cuda':
+            with self.torch.cuda.device(self.device):
+                self.phases.run(self.problem, self.step, int(n_iters), self._stream())
+            self.step += int(n_iters)
+        else:
+            for _ in range(int(n_iters)):
+                self.one_step(True)
+
+    # ---- read-back ---------------------------------------------------------------------------------------------------
+    def state(self):
+        """State entering the next step: dict(adam_step, best, no_improve, stopped, iterations, improved)."""
+        s = self.ctrl[_lib.CT_STATE + 16 * (self.step & 1):_lib.CT_STATE + 16 * (self.step & 1) + 8].cpu().numpy()
+        return dict(adam_step=int(s[0]), run_sum=float(s[1]), run_cnt=int(s[2]), best=float(s[3]), no_improve=int(s[4]),
+                    stopped=bool(s[5]), iterations=int(s[6]), improved=bool(s[7]))
+
+    def history(self, n_steps):
+        """(n_steps, 4) float64 [total, likelihood, smoothness, body_length] per optimiser step."""
+        n_steps = min(int(n_steps), self.hist_capacity)
+        return self.ctrl[_lib.CT_HIST:_lib.CT_HIST + 4 * n_steps].cpu().numpy().reshape(n_steps, 4)
+
+    def trajectory(self):
+        return self.comm.all_gather_frames(self.x_ext[2:self.n_local + 2], self.total_frames)
+
+    def best_trajectory(self):
+        return self.comm.all_gather_frames(self.best, self.total_frames)

@@ -1,0 +1,235 @@
+"""GPU parity: csrc/refine.cu through the drop-in class against runs of the unmodified reference
+(tests/golden/refine_T48.npz) and against the oracle.
+
+Tolerance (BASELINE.json north_star): the loss history at equal iterations within 1e-4 relative.  The float64
+path is held to 1e-9; trajectories to 1e-6 mm (float64) / 5e-2 mm (float32 state, the reference's own float32
+autograd noise over tens of Adam steps).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import cams_from_golden, load_golden
+from oracle import refine as R
+from test_oracle_refine import RUNS
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def pr():
+    import __graft_entry__ as g
+    g.build()
+    import mc3d_b200.pose_refinement as m
+    return m
+
+
+def _cam_params(g, n):
+    return {i: [np.asarray(a).copy() for a in cams_from_golden(g, n)[i]] for i in range(n)}
+
+
+def _history(opt):
+    return {k: np.array([float(v) for v in vals]) for k, vals in opt.all_costs_total.items()}
+
+
+def test_project_points_torch_matches_reference(pr):
+    import torch
+    g = load_golden('refine_T48.npz')
+    cams = cams_from_golden(g, 2)
+    for i in range(2):
+        K, Rm, T, dist = cams[i]
+        for tag, dt, tol in (('f64', torch.float64, 1e-9), ('f32', torch.float32, 1e-3)):
+            out = pr.project_points_torch(g['init'], K, Rm, T, dist, torch_dtype=dt)
+            assert isinstance(out, torch.Tensor) and out.dtype == dt and tuple(out.shape) == (48, 17, 2) and not out.is_cuda
+            assert np.abs(out.numpy() - g[f'proj_{tag}_cam{i}']).max() < tol
+            out = pr.project_points_torch(torch.tensor(g['init']), torch.tensor(K), torch.tensor(Rm), torch.tensor(T),
+                                          torch.tensor(dist), torch_dtype=dt, ignore_distortions=True)
+            assert np.abs(out.numpy() - g[f'proj_nodist_{tag}_cam{i}']).max() < tol
+        sub = pr.project_points_torch(g['init'], K, Rm, T, dist, indicies=[3, 4, 9], torch_dtype=torch.float64)
+        assert np.abs(sub.numpy() - g[f'proj_f64_cam{i}'][[3, 4, 9]]).max() < 1e-9
+
+
+@pytest.mark.parametrize('run', sorted(RUNS))
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+def test_sgd_optimize_matches_reference_runs(pr, syn, run, tag, capsys):
+    import torch
+    g = load_golden('refine_T48.npz')
+    dt = torch.float64 if tag == 'f64' else torch.float32
+    opt = pr.Optimized_3d_Pose_Estimation(g['gaussians'].copy(), g['init'].copy(),
+                                          decomposed_cam_params_initial=_cam_params(g, 2),
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+    import mc3d_b200.utils as u
+    opt.sgd_optimize(**u.prepare_kwargs(opt.sgd_optimize, RUNS[run]))
+    key = f'run_{run}_{tag}'
+    hist = _history(opt)
+    rtol = 1e-9 if tag == 'f64' else LOSS_RTOL
+    assert set(hist) == {k[len(key) + 1:] for k in g.files if k.startswith(key) and k.endswith('_cost')}
+    for name, h in hist.items():
+        ref = g[f'{key}_{name}']
+        assert len(h) == len(ref), (name, len(h), len(ref))           # same iteration count incl. early stopping
+        assert np.max(np.abs(h - ref) / np.abs(ref)) < rtol, name
+    atol = 1e-6 if tag == 'f64' else 5e-2
+    assert isinstance(opt.best_trajectory, torch.Tensor) and not opt.best_trajectory.is_cuda
+    assert np.abs(np.array(opt.best_trajectory) - g[f'{key}_best']).max() < atol
+    assert np.abs(opt.trajectory.numpy() - g[f'{key}_final']).max() < atol
+    # element types of the history follow upstream: tensors for step costs, numpy scalars for running means
+    tc = opt.all_costs_total['total_cost']
+    assert isinstance(tc[0], torch.Tensor) and isinstance(tc[1], np.floating)
+    out = capsys.readouterr().out
+    assert 'Iteration 0: total_cost:' in out
+    if run == 'stop':
+        assert 'Early stopping at iteration' in out
+
+
+def test_gradient_kernel_matches_oracle(pr, syn):
+    import torch
+    from mc3d_b200 import refinement as rf
+    gs, init, cams, _ = syn.refinement_inputs(64, n_cams=3, seed=21)
+    init[5, 2] = np.nan                                                 # a frozen joint: masked everywhere
+    rows = rf.camera_rows(cams, list(cams))
+    eng = rf.RefineEngine(init, gs, rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=torch.float64, device='cuda:0', lr=0.01,
+                          betas=(0.9, 0.999), lambda_smooth=0.4, lambda_body_length=1.2, patience=10, tolerance=1e-5,
+                          max_iter=5, ignore_distortions=False, window=(0, 64), n_window_frames=64, hist_capacity=16)
+    eng.phases.phase(eng.problem, 0, 0, True, None)
+    eng.phases.phase(eng.problem, 1, 0, True, None)
+    torch.cuda.synchronize()
+    acc = eng.ctrl[:8].cpu().numpy()
+    Sinv = R.cov_inverse(gs)
+    bones = R.bone_table(syn.EXAMPLE_BODY_LENGTHS)
+    cl, gl, nl = R.likelihood(init, gs[:, 0, :, :2], Sinv, list(cams.values()))
+    cs, gsm, ns = R.smoothness(init, 0.4)
+    cb, gb, mu = R.body_length(init, bones, 1.2)
+    assert np.isclose(acc[0] / acc[1], cl, rtol=1e-12) and acc[1] == nl
+    assert np.isclose(0.4 * acc[2] / acc[3], cs, rtol=1e-12) and acc[3] == ns
+    assert np.isclose(acc[4] / acc[5], mu, rtol=1e-12)
+    ref = gl + gsm + gb
+    ref[5, 2] = 0.0                                                      # the NaN joint itself gets no gradient
+    got = eng.g.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - np.nan_to_num(ref)).max() < 1e-12 * max(1.0, np.abs(np.nan_to_num(ref)).max())
+    assert np.isclose(acc[7], (got ** 2).sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize('case', ['batch', 'three_cams_f32', 'subset_of_cameras'])
+def test_sgd_optimize_matches_oracle(pr, syn, case):
+    import torch
+    n_cams = 3 if case != 'batch' else 2
+    gs, init, cams, _ = syn.refinement_inputs(90, n_cams=n_cams, seed=22)
+    kw = dict(lr=0.01, lambda_smooth=1e-3, lambda_body_length=1.0, max_iter=12, time_interval=[3, 83], patience=50)
+    dt, np_dt, rtol = torch.float64, np.float64, 1e-9
+    cam_ids = None
+    if case == 'batch':
+        kw['batch_size'] = 32                                            # windows [0,32) [16,48) [32,64): 3 Adam steps / iteration
+    if case == 'three_cams_f32':
+        dt, np_dt, rtol = torch.float32, np.float32, LOSS_RTOL
+    if case == 'subset_of_cameras':
+        cam_ids = [0, 2]
+    opt = pr.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(), decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), camera_IDs=cam_ids, torch_dtype=dt)
+    opt.sgd_optimize(print_frequency=5, **kw)
+    use = list(cams.values()) if cam_ids is None else [cams[i] for i in cam_ids]
+    ref = R.sgd_optimize(gs, init, use, syn.EXAMPLE_BODY_LENGTHS, dtype=np_dt, **kw)
+    hist = _history(opt)
+    for name, h in ref['history'].items():
+        assert len(hist[name]) == len(h)
+        assert np.max(np.abs(hist[name] - np.array(h)) / np.abs(h)) < rtol, name
+    assert np.abs(opt.trajectory.numpy() - ref['final']).max() < (1e-6 if dt == torch.float64 else 5e-2)
+    assert tuple(opt.trajectory.shape) == (80, 17, 3)
+
+
+def test_nan_joint_is_masked_not_fatal(pr, syn):
+    """Upstream masks non-finite terms in the forward value only and then dies (KeyError) at iteration 1; here the
+    same masked objective is optimised with the NaN joint frozen.  Iteration-0 costs equal upstream's."""
+    import torch
+    g = load_golden('refine_T48.npz')
+    opt = pr.Optimized_3d_Pose_Estimation(g['gaussians'].copy(), g['init_nan'].copy(),
+                                          decomposed_cam_params_initial=_cam_params(g, 2),
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=torch.float64)
+    opt.sgd_optimize(lr=0.01, lambda_smooth=1e-6, lambda_body_length=0, max_iter=5, time_interval=[0, 40], print_frequency=np.inf)
+    hist = _history(opt)
+    for name in ('total_cost', 'likelihood_cost', 'smoothness_cost'):
+        assert np.isclose(hist[name][0], float(g[f'run_nan_f64_iter0_{name}']), rtol=1e-10)
+    assert len(hist['total_cost']) == 12 and np.isfinite(hist['total_cost']).all()
+    final = opt.trajectory.numpy()
+    assert np.isnan(final[7, 3]).all() and np.isfinite(np.delete(final.reshape(40, -1), [9, 10, 11], axis=1)).all()
+
+
+def test_unsupported_modes_and_errors(pr, syn):
+    gs, init, cams, _ = syn.refinement_inputs(8, seed=1)
+    mk = lambda **k: pr.Optimized_3d_Pose_Estimation(gs, init, decomposed_cam_params_initial={i: list(cams[i]) for i in cams}, **k)
+    with pytest.raises(NotImplementedError):
+        mk(body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS)).sgd_optimize(extrinsic_optimization_IDs=[1])
+    with pytest.raises(NotImplementedError):
+        mk(body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS)).sgd_optimize(use_NN=True)
+    with pytest.raises(AttributeError):
+        mk(body_lengths=None).sgd_optimize(max_iter=1)                   # upstream: create_body_length_vect on None
+    with pytest.raises(KeyError):
+        mk(body_lengths={'left_elbow_nose': 3.0}).sgd_optimize(max_iter=1)
+
+
+def test_cli_round_trip(pr, syn, tmp_path):
+    """`pose_refinement.py --refinement_types SGD` on a recording directory (pose_refinement.py:1099-1256)."""
+    import pickle
+    import yaml
+    gs, init, cams, _ = syn.refinement_inputs(30, seed=23)
+    root = tmp_path / 'session'
+    run = root / 'recordings' / '0'
+    ext = root / 'extrinsic_camera_parameters'
+    intr = tmp_path / 'intrinsic_camera_parameters'
+    for d in (run, ext, intr):
+        d.mkdir(parents=True)
+    names = {0: 'camA', 1: 'camB'}
+    for i, nm in names.items():
+        K, Rm, T, dist = cams[i]
+        with open(intr / f'{nm}.dat', 'w') as fh:
+            fh.write('intrinsic:\n' + '\n'.join(' '.join(repr(float(v)) for v in row) for row in K) + '\ndistortion:\n' +
+                     ' '.join(repr(float(v)) for v in dist.ravel()) + '\n')
+        with open(ext / f'rot_trans_{nm}.dat', 'w') as fh:
+            fh.write('R:\n' + '\n'.join(' '.join(repr(float(v)) for v in row) for row in Rm) + '\nT:\n' +
+                     '\n'.join(repr(float(v)) for v in T.ravel()) + '\n')
+    with open(ext / 'camera_names.pkl', 'wb') as fh:
+        pickle.dump((names, 'camA'), fh)
+    np.save(run / 'kpts_3d.npy', init)
+    np.save(run / 'heatmaps_2d.npy', gs)
+    np.save(run / 'kpts_2d.npy', np.zeros((30, 17, 3, 2)))
+    with open(run / 'recording_log.yaml', 'w') as fh:
+        yaml.safe_dump({'kpts_3d': str(run / 'kpts_3d.npy'), 'heatmaps_2d': str(run / 'heatmaps_2d.npy'),
+                        'kpts_2d': str(run / 'kpts_2d.npy'), 'recording_paths': [], 'estimator_model': 'x',
+                        'detector_model': 'y'}, fh)
+    with open(tmp_path / 'params.yaml', 'w') as fh:
+        yaml.safe_dump({'SGD': {'max_iter': 15, 'lr': 0.01, 'lambda_smooth': 1e-6, 'lambda_body_length': 1,
+                                'patience': 100, 'time_interval': [0, 30]}}, fh)
+    with open(tmp_path / 'lengths.yaml', 'w') as fh:
+        yaml.safe_dump({'my_lengths': dict(syn.EXAMPLE_BODY_LENGTHS)}, fh, sort_keys=False)
+    pr.main(['--run_path', str(run), '--refinement_types', 'SGD', '--intrinsic_params_dir', str(intr),
+             '--refinement_params_yaml', str(tmp_path / 'params.yaml'), '--body_part_lengths_yaml', str(tmp_path / 'lengths.yaml')])
+    saved = np.load(run / 'kpts_3d_SGD.npy')
+    ref = R.sgd_optimize(gs, init, list(cams.values()), syn.EXAMPLE_BODY_LENGTHS, dtype=np.float32, lr=0.01,
+                         lambda_smooth=1e-6, lambda_body_length=1, max_iter=15, time_interval=[0, 30])
+    assert saved.shape == (30, 17, 3) and np.abs(saved - ref['best']).max() < 5e-2
+
+
+def test_long_run_at_scale_is_consistent_with_oracle_statistics(pr, syn):
+    """Config-4 shape at reduced length (T=4000): the kernel's cost after 200 iterations equals the oracle's cost
+    function evaluated on the kernel's own trajectory (size-independent property)."""
+    import torch
+    gs, init, cams, _ = syn.refinement_inputs(4000, seed=24)
+    opt = pr.Optimized_3d_Pose_Estimation(gs, init, decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=torch.float64)
+    opt.sgd_optimize(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, max_iter=199, time_interval=[0, 4000],
+                     print_frequency=np.inf, patience=1000)
+    hist = _history(opt)
+    assert len(hist['total_cost']) == 400
+    assert hist['total_cost'][-2] < hist['total_cost'][0]
+    # re-evaluate with the oracle at the state BEFORE the last step: run one fewer iteration and compare the next cost
+    opt2 = pr.Optimized_3d_Pose_Estimation(gs, init, decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                           body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=torch.float64)
+    opt2.sgd_optimize(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, max_iter=198, time_interval=[0, 4000],
+                      print_frequency=np.inf, patience=1000)
+    x = opt2.trajectory.numpy()
+    costs, _ = R.total_cost_and_grad(x, gs[:, 0, :, :2], R.cov_inverse(gs), list(cams.values()),
+                                     R.bone_table(syn.EXAMPLE_BODY_LENGTHS), 1e-6, 1.0)
+    assert np.isclose(hist['total_cost'][-2], costs['total_cost'], rtol=1e-9)
