@@ -482,34 +482,39 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
     int st = validate(pb);
     if (st != MC3D_OK) return st;
     long long done = 0;
-    auto one = [&](long long step) -> int {
+    auto one = [&](long long step, cudaStream_t s) -> int {
         for (int ph = 0; ph < 3; ++ph) {
-            int s2 = refine_phase<T>(pb, ph, step, 1, stream);
+            int s2 = refine_phase<T>(pb, ph, step, 1, s);
             if (s2 != MC3D_OK) return s2;
         }
         return MC3D_OK;
     };
-    if ((first_step & 1) && n_iters > 0) { st = one(first_step); if (st != MC3D_OK) return st; done = 1; }
+    if ((first_step & 1) && n_iters > 0) { st = one(first_step, stream); if (st != MC3D_OK) return st; done = 1; }
     const long long pairs = (n_iters - done) / 2;
     if (pairs >= 4) {
+        // The legacy default stream cannot be captured: record on a private stream, replay on the caller's.
+        static thread_local cudaStream_t cap_stream = nullptr;
+        if (!cap_stream) MC3D_CUDA_TRY(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         const int unroll = pairs >= 32 ? 8 : 1;                     // 2*unroll iterations per graph launch
-        MC3D_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        for (int u = 0; u < 2 * unroll && st == MC3D_OK; ++u) st = one(first_step + done + u);
-        cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+        MC3D_CUDA_TRY(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+        const long long before = mc3d_launch_count();
+        for (int u = 0; u < 2 * unroll && st == MC3D_OK; ++u) st = one(first_step + done + u, cap_stream);
+        cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+        count_launch((int)(before - mc3d_launch_count()));          // recording is not launching
         if (st != MC3D_OK) { if (graph) cudaGraphDestroy(graph); return st; }
         MC3D_CUDA_TRY(ce);
         MC3D_CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
         const long long launches = pairs / unroll;
         for (long long i = 0; i < launches; ++i) MC3D_CUDA_TRY(cudaGraphLaunch(exec, stream));
-        count_launch((int)(launches * 2 * unroll * 3) - 2 * unroll * 3);   // capture counted one replay's worth already
+        count_launch((int)(launches * 2 * unroll * 3));
         done += launches * 2 * unroll;
         MC3D_CUDA_TRY(cudaStreamSynchronize(stream));               // the exec must outlive its launches
         cudaGraphExecDestroy(exec);
         cudaGraphDestroy(graph);
     }
-    for (; done < n_iters; ++done) { st = one(first_step + done); if (st != MC3D_OK) return st; }
+    for (; done < n_iters; ++done) { st = one(first_step + done, stream); if (st != MC3D_OK) return st; }
     return MC3D_OK;
 }
 

@@ -127,7 +127,7 @@ def golden_refine(ref_refine, ref_utils, syn, out):
         'readme': dict(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, patience=100, max_iter=60,
                        time_interval=[0, 40]),
         'defaults': dict(max_iter=25),
-        'stop': dict(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, patience=3, tolerance=1e-1, max_iter=200,
+        'stop': dict(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, patience=3, tolerance=0.7, max_iter=200,
                      time_interval=[0, 48]),
         'nodist': dict(lr=0.005, lambda_smooth=0.5, lambda_body_length=0, max_iter=20, ignore_distortions=True,
                        time_interval=[4, 44]),
