@@ -335,6 +335,12 @@ def run_ours(args, rank, local_rank, world):
                      'frac_of_nominal_8TBs': achieved / 8000.0},
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }
+    if world == 1 and not args.no_refine:
+        try:
+            line['refine'] = {'T100k_f32': refine_benchmark(100_000, 400, 'f32', device),
+                              'T400_f32': refine_benchmark(400, 2000, 'f32', device)}
+        except Exception as exc:
+            line['refine'] = {'error': repr(exc)}
     if world == 1 and not args.no_cpu:
         rate, workers, joints, wall = cpu_baseline_run(n_views)
         line['cpu_baseline'] = {'value': rate, 'unit': 'joints/s', 'cores': workers, 'kind': 'port',
@@ -345,6 +351,39 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0):
+    """Config 4 shape: refinement iterations per second on `n_frames` frames x 17 joints x 2 cameras
+    (lambda_smooth=1e-6, lambda_body_length=1, lr=0.01).  Returns a dict for the JSON line."""
+    import torch
+    from mc3d_b200 import refinement as rf
+    from mc3d_b200 import synthetic as syn
+    gs, init, cams, _ = syn.refinement_inputs(n_frames, n_cams=2, seed=seed)
+    dt = torch.float32 if dtype_name == 'f32' else torch.float64
+    rows = rf.camera_rows(cams, list(cams))
+    comm = rf.DistComm() if world > 1 else rf.LocalComm()
+    eng = rf.RefineEngine(init, gs, rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=dt, device=device, lr=0.01,
+                          betas=(0.9, 0.999), lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
+                          max_iter=10 ** 9, ignore_distortions=False, window=(0, n_frames), n_window_frames=n_frames,
+                          hist_capacity=iters * 2 + 64, comm=comm)
+    warm = 32 if world == 1 else 8
+    eng.run(warm)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    eng.run(iters)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    hist = eng.history(warm + iters)
+    esize = 4 if dtype_name == 'f32' else 8
+    # per joint-frame and iteration: A reads x, mu0, S (8 scalars); B reads the same and writes g (11); C reads g, x, m, v
+    # and writes x, m, v (+ best when improved) (21..24)
+    algo = n_frames * 17 * (8 + 11 + 21) * esize
+    return {'frames': n_frames, 'iters': iters, 'dtype': dtype_name, 'iters_per_s': iters / (ms * 1e-3), 'us_per_iter': 1e3 * ms / iters,
+            'algorithmic_bytes_per_iter': algo, 'achieved_GBs': algo / (ms * 1e-3 / iters) / 1e9,
+            'cost_first': float(hist[0, 0]), 'cost_last': float(hist[-1, 0]), 'kernels_per_iter': 3}
 
 
 def _mem_available_bytes():
@@ -366,6 +405,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-refine', action='store_true', help='skip the refinement iters/sec extra')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

@@ -1,0 +1,41 @@
+"""GPU, >= 2 devices: frame-sharded paths under torchrun (skipped on a single-GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.timeout(900)
+def test_sharded_refinement_equals_single_gpu():
+    if _n_gpus() < 2:
+        pytest.skip('needs two GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29541', os.path.join(ROOT, 'tests', 'mgpu_refine_check.py')]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'ok=True' in r.stdout
+
+
+@pytest.mark.timeout(900)
+def test_sharded_triangulation_bench_line():
+    if _n_gpus() < 2:
+        pytest.skip('needs two GPUs')
+    import json
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29542', os.path.join(ROOT, 'bench.py'), '--gpus', '2', '--steps', '3', '--warmup', '3',
+           '--workload', 'tri8_coco17_1Mframes_f32']
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('{')][-1])
+    assert line['n_gpus'] == 2 and line['scaling'] == 'weak' and line['value'] > 1e10
+    assert line['e2e']['matches_device_path']
