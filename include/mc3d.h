@@ -60,7 +60,8 @@ typedef enum {
 } mc3d_tri_mode;
 
 enum {
-    MC3D_TRI_FLAG_JACOBI = 1   /* solve every joint with the 4x4 Jacobi eigensolver (test hook) */
+    MC3D_TRI_FLAG_JACOBI = 1,  /* solve every joint with the 4x4 Jacobi eigensolver (test hook) */
+    MC3D_TRI_FLAG_FP64 = 2     /* float storage: use the all-double solver instead of the mixed-precision one */
 };
 
 /* Per-rig camera description for triangulation (host memory, double).
@@ -87,7 +88,8 @@ int mc3d_device_info(char *name, int name_len, int *sm_count, int *cc_major, int
 /* ---- 1. triangulation ---------------------------------------------------------------------
  * d_kpts: n joints x 3V scalars in `layout`; d_out: n x 3 (X,Y,Z).
  * Replaces: the per-(frame,joint) loop of pose_estimation.py:27-54 and utils.py:19-34.
- * f32: float storage, double arithmetic inside (error = one output rounding).
+ * f32: float storage; A^T A is accumulated in float and the solution is polished with residuals evaluated in
+ *      double, so the error is one output rounding (MC3D_TRI_FLAG_FP64 selects all-double arithmetic).
  * Degenerate joints (fewer than two views with non-zero weight, non-finite input) give NaN. */
 int mc3d_triangulate_f32(const float *d_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode,
                          int flags, float *d_out, void *stream);

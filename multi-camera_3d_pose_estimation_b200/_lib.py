@@ -14,6 +14,7 @@ LAYOUT_3V = 1      # (N, 3, V)  -- the reference's kpts_2d (T, J, 3, C)
 TRI_WEIGHTED = 0
 TRI_TOP2 = 1
 TRI_FLAG_JACOBI = 1
+TRI_FLAG_FP64 = 2
 KPT_PLAIN, KPT_NV3, KPT_N3V = 0, 1, 2
 DECODE_FLAG_WRITE_BACK = 1
 DECODE_FLAG_GENERIC = 2

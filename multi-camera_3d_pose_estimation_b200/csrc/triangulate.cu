@@ -15,6 +15,7 @@
 // registers.  Results leave through a shared-memory tile and a TMA bulk store.
 #include "mc3d_common.cuh"
 #include <math.h>
+#include <type_traits>
 
 namespace mc3d {
 
@@ -28,6 +29,13 @@ struct TriParams {
     int undistort;
     int flags;
     int layout;
+    // mixed-precision path (float storage): rows re-centred on each view's principal point
+    //   a = (y - cy) P2 - P1',  c = P0' - (x - cx) P2,   P0' = P0 - cx P2,  P1' = P1 - cy P2   (same rows, smaller numbers)
+    float2 p2[MC3D_MAX_VIEWS][4];     // (P2_k, P2_k)
+    float2 p10[MC3D_MAX_VIEWS][4];    // (-P1'_k, P0'_k)
+    float2 cxy[MC3D_MAX_VIEWS];       // (cx, cy) as floats
+    double cxyd[MC3D_MAX_VIEWS][2];   // the same values as doubles
+    double Pc[MC3D_MAX_VIEWS][12];    // P0', P1', P2 in double
 };
 
 // ---- small dense helpers ----------------------------------------------------------------------
@@ -183,9 +191,127 @@ __device__ __forceinline__ void accumulate_view(double *B, double x, double y, d
     B[9] = fma(a[3], a[3], fma(c[3], c[3], B[9]));
 }
 
+// ---- mixed-precision solver (float storage) ---------------------------------------------------------------------
+// float LDL^T solve of a 3x3 SPD system; approximate reciprocals are fine: this solve only preconditions the
+// iteration below, whose fixed point is set by residuals evaluated in double.
+__device__ __forceinline__ bool ldl3_solve_f(float m00, float m10, float m11, float m20, float m21, float m22,
+                                             float r0, float r1, float r2, float &z0, float &z1, float &z2) {
+    if (!(m00 > 0.f)) return false;
+    const float i0 = __fdividef(1.f, m00);
+    const float l10 = m10 * i0, l20 = m20 * i0;
+    const float d1 = fmaf(-l10, m10, m11);
+    if (!(d1 > 1e-6f * m11)) return false;
+    const float i1 = __fdividef(1.f, d1);
+    const float t21 = fmaf(-l20, m10, m21);
+    const float l21 = t21 * i1;
+    const float d2 = fmaf(-l21, t21, fmaf(-l20, m20, m22));
+    if (!(d2 > 1e-6f * m22)) return false;
+    const float i2 = __fdividef(1.f, d2);
+    const float y1 = fmaf(-l10, r0, r1);
+    const float y2 = fmaf(-l21, y1, fmaf(-l20, r0, r2));
+    z2 = y2 * i2;
+    z1 = fmaf(y1, i1, -l21 * z2);
+    z0 = fmaf(r0, i0, -fmaf(l10, z1, l20 * z2));
+    return true;
+}
+
+// Smallest eigenpair of B = A^T A without ever forming B in double:
+//   1. M~, b~ (the blocks of B) accumulated in float with packed FFMA2 -- the two rows of a view ride in one
+//      float2 -- and a float LDL^T solve give X0 (error ~1e-6 relative);
+//   2. Newton on the eigen-equations  F(X) = A_m^T A (X,1) - lam X = 0,  lam = |A (X,1)|^2 / (1 + |X|^2),
+//      with the residual A (X,1) evaluated in DOUBLE from the double projection rows (the cancellation
+//      y (P2.X) - P1.X happens in double) and the correction solved with the float factorisation of M~ - lam I.
+//      Each step contracts the error by ~cond(M) * 1e-6, so one or two steps reach double-class accuracy.
+// Returns false when the float factorisation breaks down or the iteration stalls (caller falls back to the
+// all-double path).  Degenerate / non-finite joints return true with NaN.
+template <int V>
+__device__ __forceinline__ bool solve_mixed(const TriParams &prm, const float *row, bool l3v, double &X0, double &X1,
+                                            double &X2) {
+    float2 aM[6], ab[3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) aM[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ab[i] = make_float2(0.f, 0.f);
+    int n_used = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const float x = l3v ? row[v] : row[3 * v];
+        const float y = l3v ? row[V + v] : row[3 * v + 1];
+        const float w = l3v ? row[2 * V + v] : row[3 * v + 2];
+        n_used += (w != 0.f);
+        const float xc = x - prm.cxy[v].x, yc = y - prm.cxy[v].y;
+        const float2 sv = make_float2(w * yc, -(w * xc));
+        const float2 ww = make_float2(w, w);
+        float2 ac[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ac[k] = __ffma2_rn(sv, prm.p2[v][k], __fmul2_rn(ww, prm.p10[v][k]));
+        aM[0] = __ffma2_rn(ac[0], ac[0], aM[0]);
+        aM[1] = __ffma2_rn(ac[1], ac[0], aM[1]);
+        aM[2] = __ffma2_rn(ac[1], ac[1], aM[2]);
+        aM[3] = __ffma2_rn(ac[2], ac[0], aM[3]);
+        aM[4] = __ffma2_rn(ac[2], ac[1], aM[4]);
+        aM[5] = __ffma2_rn(ac[2], ac[2], aM[5]);
+        ab[0] = __ffma2_rn(ac[3], ac[0], ab[0]);
+        ab[1] = __ffma2_rn(ac[3], ac[1], ab[1]);
+        ab[2] = __ffma2_rn(ac[3], ac[2], ab[2]);
+    }
+    const float m00 = aM[0].x + aM[0].y, m10 = aM[1].x + aM[1].y, m11 = aM[2].x + aM[2].y;
+    const float m20 = aM[3].x + aM[3].y, m21 = aM[4].x + aM[4].y, m22 = aM[5].x + aM[5].y;
+    const float b0 = ab[0].x + ab[0].y, b1 = ab[1].x + ab[1].y, b2 = ab[2].x + ab[2].y;
+    X0 = X1 = X2 = NAN;
+    if (n_used < 2 || !(fabsf(m00 + m11 + m22) <= 3.0e38f) || !(fabsf(b0) + fabsf(b1) + fabsf(b2) <= 3.0e38f)) return true;
+    float z0, z1, z2;
+    if (!ldl3_solve_f(m00, m10, m11, m20, m21, m22, -b0, -b1, -b2, z0, z1, z2)) return false;
+    double Xd0 = (double)z0, Xd1 = (double)z1, Xd2 = (double)z2;
+#pragma unroll 1
+    for (int it = 0; it < 6; ++it) {
+        float2 gp[3];
+        float gq[3], rr = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { gp[k] = make_float2(0.f, 0.f); gq[k] = 0.f; }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const double *Pc = prm.Pc[v];
+            const double d0 = fma(Pc[0], Xd0, fma(Pc[1], Xd1, fma(Pc[2], Xd2, Pc[3])));
+            const double d1 = fma(Pc[4], Xd0, fma(Pc[5], Xd1, fma(Pc[6], Xd2, Pc[7])));
+            const double d2 = fma(Pc[8], Xd0, fma(Pc[9], Xd1, fma(Pc[10], Xd2, Pc[11])));
+            // inputs are re-read from the shared-memory row (still resident) rather than held in registers
+            const float x = l3v ? row[v] : row[3 * v];
+            const float y = l3v ? row[V + v] : row[3 * v + 1];
+            const float w = l3v ? row[2 * V + v] : row[3 * v + 2];
+            const double xcd = (double)x - prm.cxyd[v][0], ycd = (double)y - prm.cxyd[v][1];
+            const float r1 = (float)fma(ycd, d2, -d1);           // y (P2.X) - P1.X   : the cancellation is in double
+            const float r2 = (float)fma(-xcd, d2, d0);           // P0.X - x (P2.X)
+            const float w2 = w * w;
+            const float2 t = __fmul2_rn(make_float2(w2, w2), make_float2(r1, r2));
+            const float xc = x - prm.cxy[v].x, yc = y - prm.cxy[v].y;
+            const float t3 = fmaf(t.x, yc, -(t.y * xc));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                gp[k] = __ffma2_rn(t, prm.p10[v][k], gp[k]);     // (-t1 P1'_k, t2 P0'_k)
+                gq[k] = fmaf(t3, prm.p2[v][k].x, gq[k]);
+            }
+            rr = fmaf(t.x, r1, fmaf(t.y, r2, rr));
+        }
+        const float xf0 = (float)Xd0, xf1 = (float)Xd1, xf2 = (float)Xd2;
+        const float nx = fmaf(xf0, xf0, fmaf(xf1, xf1, xf2 * xf2));
+        const float lam = __fdividef(rr, 1.f + nx);
+        const float f0 = (gp[0].x + gp[0].y + gq[0]) - lam * xf0;
+        const float f1 = (gp[1].x + gp[1].y + gq[1]) - lam * xf1;
+        const float f2 = (gp[2].x + gp[2].y + gq[2]) - lam * xf2;
+        float e0, e1, e2;
+        if (!ldl3_solve_f(m00 - lam, m10, m11 - lam, m20, m21, m22 - lam, -f0, -f1, -f2, e0, e1, e2)) return false;
+        Xd0 += (double)e0; Xd1 += (double)e1; Xd2 += (double)e2;
+        const float ne = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
+        if (!(ne <= 3.0e38f)) return false;
+        if (ne <= 1e-8f * nx) { X0 = Xd0; X1 = Xd1; X2 = Xd2; return true; }   // |dX| <= 1e-4 |X|: next error ~1e-10 |X|
+    }
+    return false;
+}
+
 // ---- kernel -----------------------------------------------------------------------------------
 // V > 0: number of views known at compile time (fully unrolled); V == 0: runtime prm.n_views.
-template <typename T, int V, int MODE, bool UNDISTORT>
+template <typename T, int V, int MODE, bool UNDISTORT, bool MIXED>
 __global__ void __launch_bounds__(TRI_TILE, (V > 0 && V <= 8) ? 3 : 2)
 triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n, int n_stages,
                    const __grid_constant__ TriParams prm) {
@@ -251,11 +377,18 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
             __syncthreads();
         }
 
+        double X0 = NAN, X1 = NAN, X2 = NAN;
+        bool solved = false;
+        if (MIXED && active) {
+            if constexpr (MIXED)
+                solved = solve_mixed<V>(prm, reinterpret_cast<const float *>(stage) + (size_t)tid * row_elems,
+                                        prm.layout == MC3D_LAYOUT_3V, X0, X1, X2);
+        }
         double B[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) B[i] = 0.0;
         int n_used = 0;
-        if (active) {
+        if (active && !solved) {
             const T *row = stage + (size_t)tid * row_elems;
             const bool l3v = prm.layout == MC3D_LAYOUT_3V;
             if (MODE == MC3D_TRI_WEIGHTED) {
@@ -294,10 +427,9 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
         }
         __syncthreads();                       // [A] every thread has consumed stage s
 
-        double X0 = NAN, X1 = NAN, X2 = NAN;
         // non-finite pixels or weights poison the (non-negative) diagonal of B
         const bool finite_in = fabs((B[0] + B[2]) + (B[5] + B[9])) <= 1.0e300;
-        if (active && finite_in && n_used >= 2) {
+        if (active && !solved && finite_in && n_used >= 2) {
             bool ok = false;
             if (!(prm.flags & MC3D_TRI_FLAG_JACOBI)) ok = secular_newton(B, X0, X1, X2);
             if (!ok) {                             // cold path: only here does B go to local memory
@@ -358,14 +490,30 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
             for (int k = 0; k < 5; ++k) prm.dist[v][k] = rig->dist[v * 5 + k];
         }
     }
+    for (int v = 0; v < rig->n_views; ++v) {
+        const double *P0 = prm.P[v], *P1 = prm.P[v] + 4, *P2 = prm.P[v] + 8;
+        const double n2 = P2[0] * P2[0] + P2[1] * P2[1] + P2[2] * P2[2];
+        // principal point of the view: any value keeps the rows identical, this one keeps their entries small
+        const float cx = n2 > 0 ? (float)((P0[0] * P2[0] + P0[1] * P2[1] + P0[2] * P2[2]) / n2) : 0.f;
+        const float cy = n2 > 0 ? (float)((P1[0] * P2[0] + P1[1] * P2[1] + P1[2] * P2[2]) / n2) : 0.f;
+        prm.cxy[v] = make_float2(cx, cy);
+        prm.cxyd[v][0] = (double)cx;
+        prm.cxyd[v][1] = (double)cy;
+        for (int k = 0; k < 4; ++k) {
+            const double p0c = P0[k] - (double)cx * P2[k], p1c = P1[k] - (double)cy * P2[k];
+            prm.Pc[v][k] = p0c; prm.Pc[v][4 + k] = p1c; prm.Pc[v][8 + k] = P2[k];
+            prm.p2[v][k] = make_float2((float)P2[k], (float)P2[k]);
+            prm.p10[v][k] = make_float2((float)-p1c, (float)p0c);
+        }
+    }
     return MC3D_OK;
 }
 
-template <typename T, int V, int MODE, bool UNDISTORT>
+template <typename T, int V, int MODE, bool UNDISTORT, bool MIXED>
 static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_out, cudaStream_t stream) {
     const int nv = prm.n_views;
     const size_t stage_bytes = (size_t)TRI_TILE * 3 * nv * sizeof(T);
-    auto kern = triangulate_kernel<T, V, MODE, UNDISTORT>;
+    auto kern = triangulate_kernel<T, V, MODE, UNDISTORT, MIXED>;
     static bool attr_done = false;     // per instantiation
     if (!attr_done) {
         MC3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -408,18 +556,26 @@ int triangulate_device(const T *d_kpts, long long n, const mc3d_rig *rig, int la
         return MC3D_ERR_MISALIGNED;
     }
     if (mode == MC3D_TRI_TOP2) {
-        if (prm.undistort) return launch_one<T, 0, MC3D_TRI_TOP2, true>(d_kpts, n, prm, d_out, stream);
-        return launch_one<T, 0, MC3D_TRI_TOP2, false>(d_kpts, n, prm, d_out, stream);
+        if (prm.undistort) return launch_one<T, 0, MC3D_TRI_TOP2, true, false>(d_kpts, n, prm, d_out, stream);
+        return launch_one<T, 0, MC3D_TRI_TOP2, false, false>(d_kpts, n, prm, d_out, stream);
     }
-    if (prm.undistort) return launch_one<T, 0, MC3D_TRI_WEIGHTED, true>(d_kpts, n, prm, d_out, stream);
+    if (prm.undistort) return launch_one<T, 0, MC3D_TRI_WEIGHTED, true, false>(d_kpts, n, prm, d_out, stream);
+    // float storage, common rigs: mixed-precision solver (float accumulation + double residuals)
+    constexpr bool F = std::is_same<T, float>::value;
+    const bool mixed = F && !(flags & (MC3D_TRI_FLAG_JACOBI | MC3D_TRI_FLAG_FP64));
+#define MC3D_TRI_CASE(NV)                                                                                   \
+    case NV:                                                                                                \
+        if (mixed) return launch_one<T, NV, MC3D_TRI_WEIGHTED, false, F>(d_kpts, n, prm, d_out, stream);    \
+        return launch_one<T, NV, MC3D_TRI_WEIGHTED, false, false>(d_kpts, n, prm, d_out, stream);
     switch (prm.n_views) {      // fully unrolled view loops for the common rigs
-        case 2: return launch_one<T, 2, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
-        case 3: return launch_one<T, 3, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
-        case 4: return launch_one<T, 4, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
-        case 8: return launch_one<T, 8, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
-        case 16: return launch_one<T, 16, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
-        default: return launch_one<T, 0, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        MC3D_TRI_CASE(2)
+        MC3D_TRI_CASE(3)
+        MC3D_TRI_CASE(4)
+        MC3D_TRI_CASE(8)
+        MC3D_TRI_CASE(16)
+        default: return launch_one<T, 0, MC3D_TRI_WEIGHTED, false, false>(d_kpts, n, prm, d_out, stream);
     }
+#undef MC3D_TRI_CASE
 }
 
 template int triangulate_device<float>(const float *, long long, const mc3d_rig *, int, int, int, float *, cudaStream_t);

@@ -141,11 +141,51 @@ def test_weighted_fp32(tri, syn, n_views):
     assert np.array_equal(got.cpu().numpy(), ref.astype(np.float32)) or err.max() < 5e-4
 
 
+def test_fp32_mixed_solver_agrees_with_all_double_solver(tri, syn):
+    """float storage: the mixed-precision solver (float A^T A + double residual Newton) against the all-double
+    solver on the same inputs -- both are one output rounding away from the exact minimiser."""
+    from mc3d_b200 import _lib
+    for n_views in (2, 3, 4, 8, 16):
+        kp, P, _, _ = syn.multiview_points(30000, n_views, seed=60 + n_views)
+        if n_views == 2:
+            cams = syn.stereo_rig(distortion=False)
+            P = syn.projection_matrices(cams)
+            rng = np.random.default_rng(3)
+            X = syn.SCENE_CENTRE + rng.normal(0, 400, size=(30000, 3))
+            for c in range(2):
+                kp[:, c, :2] = syn.project(X, cams[c], distort=False) + rng.normal(0, 1, size=(30000, 2))
+        kp32 = _cuda(kp.astype(np.float32))
+        a = tri(kp32, P).cpu().numpy().astype(np.float64)
+        b = tri(kp32, P, flags=_lib.TRI_FLAG_FP64).cpu().numpy().astype(np.float64)
+        assert np.linalg.norm(a - b, axis=1).max() < 5e-4            # at most one float ulp per coordinate at ~3 m
+        assert np.mean(np.all(a == b, axis=1)) > 0.95
+        ref = O.dlt_weighted_polished(kp.astype(np.float32).astype(np.float64), P)
+        assert np.linalg.norm(a - ref, axis=1).max() < FP32_ATOL_MM
+
+
+def test_fp32_points_near_world_origin(tri, syn):
+    rng = np.random.default_rng(34)
+    cams = syn.ring_rig(8, centre=(0.0, 0.0, 0.0))
+    P = syn.projection_matrices(cams)
+    X = rng.normal(0, 30.0, size=(20000, 3))
+    kp = np.empty((20000, 8, 3))
+    for c in range(8):
+        kp[:, c, :2] = syn.project(X, cams[c], distort=False) + rng.normal(0, 1, size=(20000, 2))
+    kp[:, :, 2] = rng.uniform(0.2, 1, size=(20000, 8))
+    kp32 = kp.astype(np.float32)
+    got = tri(_cuda(kp32), P).cpu().numpy().astype(np.float64)
+    pol = O.dlt_weighted_polished(kp32.astype(np.float64), P, iters=8)
+    assert np.linalg.norm(got - pol, axis=1).max() < FP32_ATOL_MM
+
+
 def test_layouts_agree_bitwise(tri, syn):
     kp, P, _, _ = syn.multiview_points(3000, 8, seed=31)
     a = tri(_cuda(kp), P, layout='nv3')
     b = tri(_cuda(np.ascontiguousarray(np.transpose(kp, (0, 2, 1)))), P, layout='n3v')
     assert bool((a == b).all())
+    a32 = tri(_cuda(kp.astype(np.float32)), P, layout='nv3')
+    b32 = tri(_cuda(np.ascontiguousarray(np.transpose(kp, (0, 2, 1))).astype(np.float32)), P, layout='n3v')
+    assert bool((a32 == b32).all())
     kp4 = kp.reshape(30, 100, 8, 3)                         # leading dims are kept
     assert tuple(tri(_cuda(kp4), P).shape) == (30, 100, 3)
 
