@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libmc3d.so')
+LIB_PATH = os.environ.get('MC3D_LIB') or os.path.join(HERE, 'libmc3d.so')     # MC3D_LIB: tuning builds only
 
 MAX_VIEWS = 16
 LAYOUT_V3 = 0      # (N, V, 3)

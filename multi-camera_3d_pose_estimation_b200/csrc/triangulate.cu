@@ -215,103 +215,332 @@ __device__ __forceinline__ bool ldl3_solve_f(float m00, float m10, float m11, fl
     return true;
 }
 
-// Smallest eigenpair of B = A^T A without ever forming B in double:
+// All-double solve of one joint straight from its shared-memory row (cold path of the mixed kernel).
+__device__ __noinline__ void solve_double_from_row(const TriParams &prm, const float *row, int nv, bool l3v, double &X0,
+                                                   double &X1, double &X2) {
+    double B[10];
+    for (int i = 0; i < 10; ++i) B[i] = 0.0;
+    int n_used = 0;
+    for (int v = 0; v < nv; ++v) {
+        const double x = (double)(l3v ? row[v] : row[3 * v]);
+        const double y = (double)(l3v ? row[nv + v] : row[3 * v + 1]);
+        const double w = (double)(l3v ? row[2 * nv + v] : row[3 * v + 2]);
+        n_used += (w != 0.0);
+        accumulate_view(B, x, y, w, prm.P[v]);
+    }
+    X0 = X1 = X2 = NAN;
+    if (!(fabs((B[0] + B[2]) + (B[5] + B[9])) <= 1.0e300) || n_used < 2) return;
+    if (!secular_newton(B, X0, X1, X2)) jacobi4_smallest(B, X0, X1, X2);
+}
+
+// x, y, w of views [vg, vg + G) of one joint from its shared-memory row; 128-bit loads when the row allows it.
+template <int V, int LAYOUT, int G>
+__device__ __forceinline__ void load_group(const float *row, int vg, float (&gx)[G], float (&gy)[G], float (&gw)[G]) {
+    if constexpr (G == 4 && V % 4 == 0) {
+        if constexpr (LAYOUT == MC3D_LAYOUT_3V) {
+            const float4 a = *reinterpret_cast<const float4 *>(row + vg);
+            const float4 b = *reinterpret_cast<const float4 *>(row + V + vg);
+            const float4 c = *reinterpret_cast<const float4 *>(row + 2 * V + vg);
+            gx[0] = a.x; gx[1] = a.y; gx[2] = a.z; gx[3] = a.w;
+            gy[0] = b.x; gy[1] = b.y; gy[2] = b.z; gy[3] = b.w;
+            gw[0] = c.x; gw[1] = c.y; gw[2] = c.z; gw[3] = c.w;
+        } else {
+            const float4 a = *reinterpret_cast<const float4 *>(row + 3 * vg);
+            const float4 b = *reinterpret_cast<const float4 *>(row + 3 * vg + 4);
+            const float4 c = *reinterpret_cast<const float4 *>(row + 3 * vg + 8);
+            gx[0] = a.x; gy[0] = a.y; gw[0] = a.z;
+            gx[1] = a.w; gy[1] = b.x; gw[1] = b.y;
+            gx[2] = b.z; gy[2] = b.w; gw[2] = c.x;
+            gx[3] = c.y; gy[3] = c.z; gw[3] = c.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int v = vg + i;
+            gx[i] = LAYOUT == MC3D_LAYOUT_3V ? row[v] : row[3 * v];
+            gy[i] = LAYOUT == MC3D_LAYOUT_3V ? row[V + v] : row[3 * v + 1];
+            gw[i] = LAYOUT == MC3D_LAYOUT_3V ? row[2 * V + v] : row[3 * v + 2];
+        }
+    }
+}
+
+// Smallest eigenpair of B = A^T A without ever forming B in double, NJ joints per thread in lock-step (the
+// per-view camera constants are fetched once and used NJ times; the joints give independent instruction streams):
 //   1. M~, b~ (the blocks of B) accumulated in float with packed FFMA2 -- the two rows of a view ride in one
 //      float2 -- and a float LDL^T solve give X0 (error ~1e-6 relative);
 //   2. Newton on the eigen-equations  F(X) = A_m^T A (X,1) - lam X = 0,  lam = |A (X,1)|^2 / (1 + |X|^2),
 //      with the residual A (X,1) evaluated in DOUBLE from the double projection rows (the cancellation
 //      y (P2.X) - P1.X happens in double) and the correction solved with the float factorisation of M~ - lam I.
 //      Each step contracts the error by ~cond(M) * 1e-6, so one or two steps reach double-class accuracy.
-// Returns false when the float factorisation breaks down or the iteration stalls (caller falls back to the
-// all-double path).  Degenerate / non-finite joints return true with NaN.
-template <int V>
-__device__ __forceinline__ bool solve_mixed(const TriParams &prm, const float *row, bool l3v, double &X0, double &X1,
-                                            double &X2) {
-    float2 aM[6], ab[3];
+// state[j]: 0 = solved (X valid, NaN for degenerate / non-finite joints), 1 = needs the all-double fallback.
+template <int V, int LAYOUT, int NJ>
+__device__ __forceinline__ void solve_mixed(const TriParams &prm, const float *const (&rows)[NJ], const bool (&act)[NJ],
+                                            double (&X)[NJ][3], int (&state)[NJ]) {
+    float2 aM[NJ][6], ab[NJ][3];
+    int n_used[NJ];
+    float m[NJ][6], b[NJ][3];
+    constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
 #pragma unroll
-    for (int i = 0; i < 6; ++i) aM[i] = make_float2(0.f, 0.f);
+    for (int j = 0; j < NJ; ++j) {
+        n_used[j] = 0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) ab[i] = make_float2(0.f, 0.f);
-    int n_used = 0;
+        for (int i = 0; i < 6; ++i) aM[j][i] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        const float x = l3v ? row[v] : row[3 * v];
-        const float y = l3v ? row[V + v] : row[3 * v + 1];
-        const float w = l3v ? row[2 * V + v] : row[3 * v + 2];
-        n_used += (w != 0.f);
-        const float xc = x - prm.cxy[v].x, yc = y - prm.cxy[v].y;
-        const float2 sv = make_float2(w * yc, -(w * xc));
-        const float2 ww = make_float2(w, w);
-        float2 ac[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ac[k] = __ffma2_rn(sv, prm.p2[v][k], __fmul2_rn(ww, prm.p10[v][k]));
-        aM[0] = __ffma2_rn(ac[0], ac[0], aM[0]);
-        aM[1] = __ffma2_rn(ac[1], ac[0], aM[1]);
-        aM[2] = __ffma2_rn(ac[1], ac[1], aM[2]);
-        aM[3] = __ffma2_rn(ac[2], ac[0], aM[3]);
-        aM[4] = __ffma2_rn(ac[2], ac[1], aM[4]);
-        aM[5] = __ffma2_rn(ac[2], ac[2], aM[5]);
-        ab[0] = __ffma2_rn(ac[3], ac[0], ab[0]);
-        ab[1] = __ffma2_rn(ac[3], ac[1], ab[1]);
-        ab[2] = __ffma2_rn(ac[3], ac[2], ab[2]);
+        for (int i = 0; i < 3; ++i) ab[j][i] = make_float2(0.f, 0.f);
     }
-    const float m00 = aM[0].x + aM[0].y, m10 = aM[1].x + aM[1].y, m11 = aM[2].x + aM[2].y;
-    const float m20 = aM[3].x + aM[3].y, m21 = aM[4].x + aM[4].y, m22 = aM[5].x + aM[5].y;
-    const float b0 = ab[0].x + ab[0].y, b1 = ab[1].x + ab[1].y, b2 = ab[2].x + ab[2].y;
-    X0 = X1 = X2 = NAN;
-    if (n_used < 2 || !(fabsf(m00 + m11 + m22) <= 3.0e38f) || !(fabsf(b0) + fabsf(b1) + fabsf(b2) <= 3.0e38f)) return true;
-    float z0, z1, z2;
-    if (!ldl3_solve_f(m00, m10, m11, m20, m21, m22, -b0, -b1, -b2, z0, z1, z2)) return false;
-    double Xd0 = (double)z0, Xd1 = (double)z1, Xd2 = (double)z2;
+#pragma unroll
+    for (int vg = 0; vg < V; vg += G) {
+        float gx[NJ][G], gy[NJ][G], gw[NJ][G];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) load_group<V, LAYOUT, G>(rows[j], vg, gx[j], gy[j], gw[j]);
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            const int v = vg + i;
+            const float2 cxy = prm.cxy[v];
+            float2 p2[4], p10[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { p2[k] = prm.p2[v][k]; p10[k] = prm.p10[v][k]; }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const float w = gw[j][i];
+                n_used[j] += (w != 0.f);
+                const float xc = gx[j][i] - cxy.x, yc = gy[j][i] - cxy.y;
+                const float2 sv = make_float2(w * yc, -(w * xc));
+                const float2 ww = make_float2(w, w);
+                float2 ac[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ac[k] = __ffma2_rn(sv, p2[k], __fmul2_rn(ww, p10[k]));
+                aM[j][0] = __ffma2_rn(ac[0], ac[0], aM[j][0]);
+                aM[j][1] = __ffma2_rn(ac[1], ac[0], aM[j][1]);
+                aM[j][2] = __ffma2_rn(ac[1], ac[1], aM[j][2]);
+                aM[j][3] = __ffma2_rn(ac[2], ac[0], aM[j][3]);
+                aM[j][4] = __ffma2_rn(ac[2], ac[1], aM[j][4]);
+                aM[j][5] = __ffma2_rn(ac[2], ac[2], aM[j][5]);
+                ab[j][0] = __ffma2_rn(ac[3], ac[0], ab[j][0]);
+                ab[j][1] = __ffma2_rn(ac[3], ac[1], ab[j][1]);
+                ab[j][2] = __ffma2_rn(ac[3], ac[2], ab[j][2]);
+            }
+        }
+    }
+    double Xd[NJ][3];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) m[j][i] = aM[j][i].x + aM[j][i].y;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) b[j][i] = ab[j][i].x + ab[j][i].y;
+        X[j][0] = X[j][1] = X[j][2] = NAN;
+        Xd[j][0] = Xd[j][1] = Xd[j][2] = 0.0;
+        state[j] = 0;
+        if (!act[j]) { state[j] = 0; continue; }
+        const bool fin = (fabsf(m[j][0] + m[j][2] + m[j][5]) <= 3.0e38f) && (fabsf(b[j][0]) + fabsf(b[j][1]) + fabsf(b[j][2]) <= 3.0e38f);
+        if (n_used[j] < 2 || !fin) continue;                    // degenerate: NaN, done
+        float z0, z1, z2;
+        if (!ldl3_solve_f(m[j][0], m[j][1], m[j][2], m[j][3], m[j][4], m[j][5], -b[j][0], -b[j][1], -b[j][2], z0, z1, z2)) {
+            state[j] = 1;
+            continue;
+        }
+        Xd[j][0] = (double)z0; Xd[j][1] = (double)z1; Xd[j][2] = (double)z2;
+        state[j] = 2;                                            // iterating
+    }
 #pragma unroll 1
     for (int it = 0; it < 6; ++it) {
-        float2 gp[3];
-        float gq[3], rr = 0.f;
+        bool any = false;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { gp[k] = make_float2(0.f, 0.f); gq[k] = 0.f; }
+        for (int j = 0; j < NJ; ++j) any = any || (state[j] == 2);
+        if (!any) break;
+        float2 gp[NJ][3];
+        float gq[NJ][3], rr[NJ];
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const double *Pc = prm.Pc[v];
-            const double d0 = fma(Pc[0], Xd0, fma(Pc[1], Xd1, fma(Pc[2], Xd2, Pc[3])));
-            const double d1 = fma(Pc[4], Xd0, fma(Pc[5], Xd1, fma(Pc[6], Xd2, Pc[7])));
-            const double d2 = fma(Pc[8], Xd0, fma(Pc[9], Xd1, fma(Pc[10], Xd2, Pc[11])));
-            // inputs are re-read from the shared-memory row (still resident) rather than held in registers
-            const float x = l3v ? row[v] : row[3 * v];
-            const float y = l3v ? row[V + v] : row[3 * v + 1];
-            const float w = l3v ? row[2 * V + v] : row[3 * v + 2];
-            const double xcd = (double)x - prm.cxyd[v][0], ycd = (double)y - prm.cxyd[v][1];
-            const float r1 = (float)fma(ycd, d2, -d1);           // y (P2.X) - P1.X   : the cancellation is in double
-            const float r2 = (float)fma(-xcd, d2, d0);           // P0.X - x (P2.X)
-            const float w2 = w * w;
-            const float2 t = __fmul2_rn(make_float2(w2, w2), make_float2(r1, r2));
-            const float xc = x - prm.cxy[v].x, yc = y - prm.cxy[v].y;
-            const float t3 = fmaf(t.x, yc, -(t.y * xc));
+        for (int j = 0; j < NJ; ++j) {
+            rr[j] = 0.f;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                gp[k] = __ffma2_rn(t, prm.p10[v][k], gp[k]);     // (-t1 P1'_k, t2 P0'_k)
-                gq[k] = fmaf(t3, prm.p2[v][k].x, gq[k]);
-            }
-            rr = fmaf(t.x, r1, fmaf(t.y, r2, rr));
+            for (int k = 0; k < 3; ++k) { gp[j][k] = make_float2(0.f, 0.f); gq[j][k] = 0.f; }
         }
-        const float xf0 = (float)Xd0, xf1 = (float)Xd1, xf2 = (float)Xd2;
-        const float nx = fmaf(xf0, xf0, fmaf(xf1, xf1, xf2 * xf2));
-        const float lam = __fdividef(rr, 1.f + nx);
-        const float f0 = (gp[0].x + gp[0].y + gq[0]) - lam * xf0;
-        const float f1 = (gp[1].x + gp[1].y + gq[1]) - lam * xf1;
-        const float f2 = (gp[2].x + gp[2].y + gq[2]) - lam * xf2;
-        float e0, e1, e2;
-        if (!ldl3_solve_f(m00 - lam, m10, m11 - lam, m20, m21, m22 - lam, -f0, -f1, -f2, e0, e1, e2)) return false;
-        Xd0 += (double)e0; Xd1 += (double)e1; Xd2 += (double)e2;
-        const float ne = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
-        if (!(ne <= 3.0e38f)) return false;
-        if (ne <= 1e-8f * nx) { X0 = Xd0; X1 = Xd1; X2 = Xd2; return true; }   // |dX| <= 1e-4 |X|: next error ~1e-10 |X|
+#pragma unroll
+        for (int vg = 0; vg < V; vg += G) {
+            float gx[NJ][G], gy[NJ][G], gw[NJ][G];              // re-read: cheaper than holding 3V registers per joint
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) load_group<V, LAYOUT, G>(rows[j], vg, gx[j], gy[j], gw[j]);
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const int v = vg + i;
+                double Pc[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) Pc[k] = prm.Pc[v][k];
+                const double cxd = prm.cxyd[v][0], cyd = prm.cxyd[v][1];
+                const float2 cxy = prm.cxy[v];
+                float2 p10[3];
+                float p2x[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { p10[k] = prm.p10[v][k]; p2x[k] = prm.p2[v][k].x; }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const double d0 = fma(Pc[0], Xd[j][0], fma(Pc[1], Xd[j][1], fma(Pc[2], Xd[j][2], Pc[3])));
+                    const double d1 = fma(Pc[4], Xd[j][0], fma(Pc[5], Xd[j][1], fma(Pc[6], Xd[j][2], Pc[7])));
+                    const double d2 = fma(Pc[8], Xd[j][0], fma(Pc[9], Xd[j][1], fma(Pc[10], Xd[j][2], Pc[11])));
+                    const float x = gx[j][i], y = gy[j][i], w = gw[j][i];
+                    const double xcd = (double)x - cxd, ycd = (double)y - cyd;
+                    const float r1 = (float)fma(ycd, d2, -d1);   // y (P2.X) - P1.X : the cancellation is in double
+                    const float r2 = (float)fma(-xcd, d2, d0);   // P0.X - x (P2.X)
+                    const float w2 = w * w;
+                    const float2 t = __fmul2_rn(make_float2(w2, w2), make_float2(r1, r2));
+                    const float xc = x - cxy.x, yc = y - cxy.y;
+                    const float t3 = fmaf(t.x, yc, -(t.y * xc));
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        gp[j][k] = __ffma2_rn(t, p10[k], gp[j][k]);   // (-t1 P1'_k, t2 P0'_k)
+                        gq[j][k] = fmaf(t3, p2x[k], gq[j][k]);
+                    }
+                    rr[j] = fmaf(t.x, r1, fmaf(t.y, r2, rr[j]));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            if (state[j] != 2) continue;
+            const float xf0 = (float)Xd[j][0], xf1 = (float)Xd[j][1], xf2 = (float)Xd[j][2];
+            const float nx = fmaf(xf0, xf0, fmaf(xf1, xf1, xf2 * xf2));
+            const float lam = __fdividef(rr[j], 1.f + nx);
+            const float f0 = (gp[j][0].x + gp[j][0].y + gq[j][0]) - lam * xf0;
+            const float f1 = (gp[j][1].x + gp[j][1].y + gq[j][1]) - lam * xf1;
+            const float f2 = (gp[j][2].x + gp[j][2].y + gq[j][2]) - lam * xf2;
+            float e0, e1, e2;
+            if (!ldl3_solve_f(m[j][0] - lam, m[j][1], m[j][2] - lam, m[j][3], m[j][4], m[j][5] - lam, -f0, -f1, -f2, e0, e1, e2)) {
+                state[j] = 1;
+                continue;
+            }
+            Xd[j][0] += (double)e0; Xd[j][1] += (double)e1; Xd[j][2] += (double)e2;
+            const float ne = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
+            if (!(ne <= 3.0e38f)) { state[j] = 1; continue; }
+            if (ne <= 1e-8f * nx) {                              // |dX| <= 1e-4 |X|: the next error is ~1e-10 |X|
+                X[j][0] = Xd[j][0]; X[j][1] = Xd[j][1]; X[j][2] = Xd[j][2];
+                state[j] = 0;
+            }
+        }
     }
-    return false;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+        if (state[j] == 2) state[j] = 1;                         // did not converge in 6 steps
+}
+
+#ifndef MC3D_TRI_NJ
+#define MC3D_TRI_NJ 2
+#endif
+#ifndef MC3D_TRI_MTHREADS
+#define MC3D_TRI_MTHREADS 128
+#endif
+#ifndef MC3D_TRI_MBLOCKS
+#define MC3D_TRI_MBLOCKS 3
+#endif
+constexpr int TRI_NJ = MC3D_TRI_NJ;             // joints per thread in the mixed kernel
+constexpr int TRI_MTHREADS = MC3D_TRI_MTHREADS; // threads per CTA of the mixed kernel
+constexpr int TRI_MTILE = TRI_MTHREADS * TRI_NJ;    // joints per tile
+
+// Mixed-precision kernel (float storage, weighted mode, V in {2,3,4,8,16}, no undistortion).  Same TMA ring as the
+// generic kernel; 128 threads x 2 joints per thread (thread t owns joints t and t + 128 of a 256-joint tile) at
+// 3 CTAs per SM measured fastest on B200 of the (joints/thread, threads, CTAs/SM) variants tried -- it is the one
+// whose register budget (168) avoids spilling the per-joint accumulators (profiles/README.md).
+template <int V, int LAYOUT>
+__global__ void __launch_bounds__(TRI_MTHREADS, MC3D_TRI_MBLOCKS)
+triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out, long long n, int n_stages,
+                         const __grid_constant__ TriParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int row_elems = 3 * V;
+    constexpr uint32_t stage_bytes = (uint32_t)(TRI_MTILE * row_elems * sizeof(float));
+    float *ring = reinterpret_cast<float *>(smem_raw);
+    float *otile = reinterpret_cast<float *>(smem_raw + (size_t)n_stages * stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + 2 * TRI_MTILE * 3 * sizeof(float));
+    const int tid = threadIdx.x;
+    const long long n_tiles = (n + TRI_MTILE - 1) / TRI_MTILE;
+    const long long first = blockIdx.x, stride = gridDim.x;
+    const long long my_tiles = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto tile_is_full = [&](long long tile) { return (tile + 1) * TRI_MTILE <= n; };
+    auto issue_load = [&](long long k, int s) {
+        const long long tile = first + k * stride;
+        if (k < my_tiles && tile_is_full(tile)) {
+            mbar_arrive_expect_tx(&full[s], stage_bytes);
+            bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes,
+                     kpts + tile * TRI_MTILE * (long long)row_elems, stage_bytes, &full[s]);
+        }
+    };
+    if (tid == 0)
+        for (int k = 0; k < n_stages - 1; ++k) issue_load(k, k);
+    int s = 0, s_next = n_stages - 1;
+    uint32_t parity = 0;
+    for (long long k = 0; k < my_tiles; ++k) {
+        const long long tile = first + k * stride;
+        const bool full_tile = tile_is_full(tile);
+        float *stage = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes);
+        if (tid == 0) {
+            issue_load(k + n_stages - 1, s_next);
+            bulk_wait_read<1>();
+        }
+        if (full_tile) {
+            mbar_wait(&full[s], parity);
+        } else {
+            const long long base = tile * TRI_MTILE * (long long)row_elems;
+            const long long cnt = (n - tile * TRI_MTILE) * row_elems;
+            for (long long i = tid; i < cnt; i += TRI_MTHREADS) stage[i] = kpts[base + i];
+            __syncthreads();
+        }
+        const float *rows[TRI_NJ];
+        bool act[TRI_NJ];
+        double X[TRI_NJ][3];
+        int state[TRI_NJ];
+#pragma unroll
+        for (int j = 0; j < TRI_NJ; ++j) {
+            const int slot = tid + j * TRI_MTHREADS;
+            act[j] = tile * TRI_MTILE + slot < n;
+            rows[j] = stage + (size_t)(act[j] ? slot : tid) * row_elems;      // inactive slots read a valid row
+        }
+        solve_mixed<V, LAYOUT, TRI_NJ>(prm, rows, act, X, state);
+#pragma unroll
+        for (int j = 0; j < TRI_NJ; ++j)
+            if (act[j] && state[j] == 1)
+                solve_double_from_row(prm, rows[j], V, LAYOUT == MC3D_LAYOUT_3V, X[j][0], X[j][1], X[j][2]);
+        __syncthreads();                       // [A] every thread has consumed stage s
+        float *ot = otile + (size_t)(k & 1) * TRI_MTILE * 3;
+        if (full_tile) {
+#pragma unroll
+            for (int j = 0; j < TRI_NJ; ++j) {
+                const int slot = tid + j * TRI_MTHREADS;
+                ot[slot * 3 + 0] = (float)X[j][0];
+                ot[slot * 3 + 1] = (float)X[j][1];
+                ot[slot * 3 + 2] = (float)X[j][2];
+            }
+            fence_proxy_async_smem();
+            __syncthreads();                   // [B]
+            if (tid == 0) {
+                bulk_s2g(out + tile * TRI_MTILE * 3, ot, (uint32_t)(TRI_MTILE * 3 * sizeof(float)));
+                bulk_commit();
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TRI_NJ; ++j) {
+                const long long joint = tile * TRI_MTILE + tid + j * TRI_MTHREADS;
+                if (act[j]) {
+                    out[joint * 3 + 0] = (float)X[j][0];
+                    out[joint * 3 + 1] = (float)X[j][1];
+                    out[joint * 3 + 2] = (float)X[j][2];
+                }
+            }
+            if (tid == 0) bulk_commit();
+        }
+        if (++s == n_stages) { s = 0; parity ^= 1u; }
+        if (++s_next == n_stages) s_next = 0;
+    }
+    if (tid == 0) bulk_wait_all<0>();
 }
 
 // ---- kernel -----------------------------------------------------------------------------------
 // V > 0: number of views known at compile time (fully unrolled); V == 0: runtime prm.n_views.
-template <typename T, int V, int MODE, bool UNDISTORT, bool MIXED>
+template <typename T, int V, int MODE, bool UNDISTORT>
 __global__ void __launch_bounds__(TRI_TILE, (V > 0 && V <= 8) ? 3 : 2)
 triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n, int n_stages,
                    const __grid_constant__ TriParams prm) {
@@ -378,12 +607,7 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
         }
 
         double X0 = NAN, X1 = NAN, X2 = NAN;
-        bool solved = false;
-        if (MIXED && active) {
-            if constexpr (MIXED)
-                solved = solve_mixed<V>(prm, reinterpret_cast<const float *>(stage) + (size_t)tid * row_elems,
-                                        prm.layout == MC3D_LAYOUT_3V, X0, X1, X2);
-        }
+        const bool solved = false;
         double B[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) B[i] = 0.0;
@@ -509,11 +733,11 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
     return MC3D_OK;
 }
 
-template <typename T, int V, int MODE, bool UNDISTORT, bool MIXED>
+template <typename T, int V, int MODE, bool UNDISTORT>
 static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_out, cudaStream_t stream) {
     const int nv = prm.n_views;
     const size_t stage_bytes = (size_t)TRI_TILE * 3 * nv * sizeof(T);
-    auto kern = triangulate_kernel<T, V, MODE, UNDISTORT, MIXED>;
+    auto kern = triangulate_kernel<T, V, MODE, UNDISTORT>;
     static bool attr_done = false;     // per instantiation
     if (!attr_done) {
         MC3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -542,6 +766,41 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
     return MC3D_OK;
 }
 
+template <int V, int LAYOUT>
+static int launch_mixed(const float *d_kpts, long long n, const TriParams &prm, float *d_out, cudaStream_t stream) {
+    const size_t stage_bytes = (size_t)TRI_MTILE * 3 * V * sizeof(float);
+    auto kern = triangulate_mixed_kernel<V, LAYOUT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MC3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    const size_t fixed = 2 * TRI_MTILE * 3 * sizeof(float) + 8 * sizeof(uint64_t);
+    int n_stages = 2, per_sm = 0;
+    size_t smem = 0;
+    for (int st = 3; st >= 2; --st) {
+        const size_t sm_bytes = st * stage_bytes + fixed;
+        if (sm_bytes > 227 * 1024) continue;
+        int occ = 0;
+        MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TRI_MTHREADS, sm_bytes));
+        if (occ > per_sm) { per_sm = occ; n_stages = st; smem = sm_bytes; }
+    }
+    if (per_sm < 1) { set_error("mixed triangulate kernel does not fit in shared memory"); return MC3D_ERR_UNSUPPORTED; }
+    const long long n_tiles = (n + TRI_MTILE - 1) / TRI_MTILE;
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<(unsigned)grid, TRI_MTHREADS, smem, stream>>>(d_kpts, d_out, n, n_stages, prm);
+    count_launch();
+    MC3D_CUDA_TRY(cudaGetLastError());
+    return MC3D_OK;
+}
+
+template <int V>
+static int launch_mixed_layout(const float *d_kpts, long long n, const TriParams &prm, float *d_out, cudaStream_t stream) {
+    if (prm.layout == MC3D_LAYOUT_3V) return launch_mixed<V, MC3D_LAYOUT_3V>(d_kpts, n, prm, d_out, stream);
+    return launch_mixed<V, MC3D_LAYOUT_V3>(d_kpts, n, prm, d_out, stream);
+}
+
 template <typename T>
 int triangulate_device(const T *d_kpts, long long n, const mc3d_rig *rig, int layout, int mode, int flags, T *d_out,
                        cudaStream_t stream) {
@@ -556,26 +815,31 @@ int triangulate_device(const T *d_kpts, long long n, const mc3d_rig *rig, int la
         return MC3D_ERR_MISALIGNED;
     }
     if (mode == MC3D_TRI_TOP2) {
-        if (prm.undistort) return launch_one<T, 0, MC3D_TRI_TOP2, true, false>(d_kpts, n, prm, d_out, stream);
-        return launch_one<T, 0, MC3D_TRI_TOP2, false, false>(d_kpts, n, prm, d_out, stream);
+        if (prm.undistort) return launch_one<T, 0, MC3D_TRI_TOP2, true>(d_kpts, n, prm, d_out, stream);
+        return launch_one<T, 0, MC3D_TRI_TOP2, false>(d_kpts, n, prm, d_out, stream);
     }
-    if (prm.undistort) return launch_one<T, 0, MC3D_TRI_WEIGHTED, true, false>(d_kpts, n, prm, d_out, stream);
-    // float storage, common rigs: mixed-precision solver (float accumulation + double residuals)
-    constexpr bool F = std::is_same<T, float>::value;
-    const bool mixed = F && !(flags & (MC3D_TRI_FLAG_JACOBI | MC3D_TRI_FLAG_FP64));
-#define MC3D_TRI_CASE(NV)                                                                                   \
-    case NV:                                                                                                \
-        if (mixed) return launch_one<T, NV, MC3D_TRI_WEIGHTED, false, F>(d_kpts, n, prm, d_out, stream);    \
-        return launch_one<T, NV, MC3D_TRI_WEIGHTED, false, false>(d_kpts, n, prm, d_out, stream);
+    if (prm.undistort) return launch_one<T, 0, MC3D_TRI_WEIGHTED, true>(d_kpts, n, prm, d_out, stream);
+    // float storage, common rigs: mixed-precision kernel (float accumulation + double residuals)
+    if constexpr (std::is_same<T, float>::value) {
+        if (!(flags & (MC3D_TRI_FLAG_JACOBI | MC3D_TRI_FLAG_FP64))) {
+            switch (prm.n_views) {
+                case 2: return launch_mixed_layout<2>(d_kpts, n, prm, d_out, stream);
+                case 3: return launch_mixed_layout<3>(d_kpts, n, prm, d_out, stream);
+                case 4: return launch_mixed_layout<4>(d_kpts, n, prm, d_out, stream);
+                case 8: return launch_mixed_layout<8>(d_kpts, n, prm, d_out, stream);
+                case 16: return launch_mixed_layout<16>(d_kpts, n, prm, d_out, stream);
+                default: break;
+            }
+        }
+    }
     switch (prm.n_views) {      // fully unrolled view loops for the common rigs
-        MC3D_TRI_CASE(2)
-        MC3D_TRI_CASE(3)
-        MC3D_TRI_CASE(4)
-        MC3D_TRI_CASE(8)
-        MC3D_TRI_CASE(16)
-        default: return launch_one<T, 0, MC3D_TRI_WEIGHTED, false, false>(d_kpts, n, prm, d_out, stream);
+        case 2: return launch_one<T, 2, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        case 3: return launch_one<T, 3, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        case 4: return launch_one<T, 4, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        case 8: return launch_one<T, 8, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        case 16: return launch_one<T, 16, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
+        default: return launch_one<T, 0, MC3D_TRI_WEIGHTED, false>(d_kpts, n, prm, d_out, stream);
     }
-#undef MC3D_TRI_CASE
 }
 
 template int triangulate_device<float>(const float *, long long, const mc3d_rig *, int, int, int, float *, cudaStream_t);

@@ -37,8 +37,11 @@ def main():
     dev = 'cuda:0'
     n = 17_000_000
     out = {}
+    only = sys.argv[1] if len(sys.argv) > 1 else ''
     for io, dt, es in (('f32', torch.float32, 4), ('f64', torch.float64, 8)):
         for V in (8, 16):
+            if only and only != f'tri_{io}_V{V}':
+                continue
             nn = n if V == 8 else n // 2
             kp, P = make_triangulation_workload(nn, V, dt, dev, seed=1)
             res = torch.empty((nn, 3), dtype=dt, device=dev)
@@ -46,6 +49,10 @@ def main():
             gbs = nn * (3 * V + 3) * es / ms / 1e6
             out[f'triangulate_{io}_V{V}'] = (ms, nn / ms * 1e3, gbs)
             del kp, res
+    if only:
+        for k, (ms, rate, gbs) in out.items():
+            print(f'{k:28s} {ms:9.4f} ms  {rate:14.4g} units/s  {gbs:8.1f} GB/s algorithmic')
+        return
     hm = torch.rand((200_000, 64, 48), device=dev) * 0.05
     hm[:, 30:34, 20:24] += 0.8
     ms = timed(lambda: decode_heatmaps(hm))
