@@ -341,6 +341,13 @@ def run_ours(args, rank, local_rank, world):
                               'T400_f32': refine_benchmark(400, 2000, 'f32', device)}
         except Exception as exc:
             line['refine'] = {'error': repr(exc)}
+    if world == 1 and not args.no_extras:
+        del kp, out
+        torch.cuda.empty_cache()
+        try:
+            line['other_configs'] = extra_measurements(device, peak)
+        except Exception as exc:
+            line['other_configs'] = {'error': repr(exc)}
     if world == 1 and not args.no_cpu:
         rate, workers, joints, wall = cpu_baseline_run(n_views)
         line['cpu_baseline'] = {'value': rate, 'unit': 'joints/s', 'cores': workers, 'kind': 'port',
@@ -386,6 +393,82 @@ def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0):
             'cost_first': float(hist[0, 0]), 'cost_last': float(hist[-1, 0]), 'kernels_per_iter': 3}
 
 
+def _time_launches(fn, reps):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def extra_measurements(device, peak):
+    """The other BASELINE.json configs, measured briefly on one GPU (inputs resident, CUDA events):
+    config 2 in float64, config 5 (COCO-WholeBody 133 joints x 16 views, point-count sweep) and config 3
+    (heatmap decode 17x64x48 x 4 views feeding the triangulation)."""
+    import torch
+    from mc3d_b200.decode import decode_heatmaps
+    from mc3d_b200.triangulation import triangulate_multiview
+    out = {}
+    # config 2, float64 storage
+    n = 4_000_000 * JOINTS
+    kp, P = make_triangulation_workload(n, 8, torch.float64, device, seed=5)
+    res = torch.empty((n, 3), dtype=torch.float64, device=device)
+    ms = _time_launches(lambda: triangulate_multiview(kp, P, out=res), 5)
+    gbs = n * 216 / ms / 1e6
+    out['tri8_coco17_f64'] = {'joints': n, 'joints_per_s': n / ms * 1e3, 'GBs': gbs, 'roofline_frac': gbs / peak,
+                              'algorithmic_bytes_per_joint': 216}
+    del kp, res
+    # config 5: 16 views, WholeBody; points = frames x 133
+    sweep = {}
+    for npts in (1_000_000, 10_000_000, 100_000_000):
+        for io, dt, es in (('f32', torch.float32, 4), ('f64', torch.float64, 8)):
+            if npts * 51 * es > 45e9:
+                continue
+            kp, P = make_triangulation_workload(npts, 16, dt, device, seed=6)
+            res = torch.empty((npts, 3), dtype=dt, device=device)
+            ms = _time_launches(lambda: triangulate_multiview(kp, P, out=res), 3)
+            gbs = npts * 51 * es / ms / 1e6
+            sweep[f'{npts:.0e}_{io}'] = {'points_per_s': npts / ms * 1e3, 'GBs': gbs, 'roofline_frac': gbs / peak}
+            del kp, res
+    out['tri16_wholebody133'] = {'algorithmic_bytes_per_point': {'f32': 204, 'f64': 408}, 'sweep': sweep,
+                                 'note': '1e9 points = 204 GB in float32: sharded over >= 2 GPUs (frames across ranks)'}
+    # config 3: decode (17 x 64 x 48 per view, 4 views) + triangulation; 16 384 frames resident, re-used as a stream
+    T_, C = 16_384, 4
+    hm = torch.rand((T_, C, JOINTS, 64, 48), device=device) * 0.02
+    cy = torch.randint(8, 56, (T_, C, JOINTS), device=device)
+    cx = torch.randint(8, 40, (T_, C, JOINTS), device=device)
+    ti, ci, ji = torch.meshgrid(torch.arange(T_, device=device), torch.arange(C, device=device),
+                                torch.arange(JOINTS, device=device), indexing='ij')
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            hm[ti, ci, ji, cy + dy, cx + dx] += 0.9 if (dx == 0 and dy == 0) else 0.4
+    from mc3d_b200 import synthetic as syn
+    P4 = syn.projection_matrices(syn.ring_rig(4))
+    aff = torch.tensor([[1280 / 48.0, 720 / 64.0, 0.0, 0.0]], dtype=torch.float32, device=device).repeat(T_ * C, 1)
+    res = torch.empty((T_, JOINTS, 3), dtype=torch.float32, device=device)
+
+    def step():
+        kpts, _ = decode_heatmaps(hm, want_moments=False, kpt_layout='nv3', affine=aff, affine_group=JOINTS)
+        triangulate_multiview(kpts, P4, out=res)
+
+    ms = _time_launches(step, 5)
+    in_bytes = hm.numel() * 4
+    both = _time_launches(lambda: decode_heatmaps(hm, kpt_layout='nv3', affine=aff, affine_group=JOINTS), 5)
+    out['decode_tri4_coco17'] = {'frames_resident': T_, 'frames_per_s': T_ / ms * 1e3, 'joints_per_s': T_ * JOINTS / ms * 1e3,
+                                 'GBs': in_bytes / ms / 1e6, 'roofline_frac': in_bytes / ms / 1e6 / peak,
+                                 'algorithmic_bytes_per_frame': 835_584 + 204,
+                                 'decode_kpts_plus_moments_GBs': in_bytes / both / 1e6,
+                                 'time_for_1M_frames_s': 1e6 / (T_ / ms * 1e3),
+                                 'note': '1 M frames = 835.6 GB of heatmaps: streamed through HBM in 16 384-frame chunks; '
+                                         'the resident chunk (13.7 GB >> L2) is re-used for timing'}
+    return out
+
+
 def _mem_available_bytes():
     try:
         with open('/proc/meminfo') as fh:
@@ -406,6 +489,7 @@ def main():
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-refine', action='store_true', help='skip the refinement iters/sec extra')
+    ap.add_argument('--no-extras', action='store_true', help='skip the other BASELINE configs (f64, 16-view WholeBody, decode+triangulate)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

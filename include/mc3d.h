@@ -186,6 +186,16 @@ int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step
 int mc3d_refine_run_f32(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
 int mc3d_refine_run_f64(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
 
+
+/* ---- 4. linear interpolation (pose_refinement.py:15-84) ---------------------------------------------------
+ * d_points / d_out: (n_frames, scalars_per_frame) doubles, scalars_per_frame = joints x dims.  Per scalar and frame:
+ * window of k//2 frames each side, outliers outside mean +- k_std*std and (optionally) median +- median_std*MAD are
+ * dropped, the rest is fitted by a least-squares line evaluated at the frame (or averaged); fewer than two survivors
+ * give 0 as upstream.  k <= 64. */
+int mc3d_linear_interpolation_f64(const double *d_points, int64_t n_frames, int64_t scalars_per_frame, int k, double k_std,
+                                  double median_std, int use_rolling_average, int filter_distance_from_median,
+                                  double *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

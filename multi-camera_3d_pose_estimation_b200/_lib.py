@@ -86,6 +86,7 @@ SIGNATURES = {
     'mc3d_refine_phase_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_int, _c_i64, _c_int, _c_vp]),
     'mc3d_refine_run_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_i64, _c_i64, _c_vp]),
     'mc3d_refine_run_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_i64, _c_i64, _c_vp]),
+    'mc3d_linear_interpolation_f64': (_c_int, [_c_vp, _c_i64, _c_i64, _c_int, _c_dbl, _c_dbl, _c_int, _c_int, _c_vp, _c_vp]),
 }
 
 

@@ -168,6 +168,22 @@ def golden_refine(ref_refine, ref_utils, syn, out):
     np.savez(os.path.join(out, 'refine_T48.npz'), **store)
 
 
+def golden_interp(ref_refine, syn, out):
+    rng = np.random.default_rng(15)
+    X = syn.smooth_trajectory(60, 17, rng, centre=(0, 0, 3000.0))
+    X += rng.normal(0, 2.0, size=X.shape)
+    spikes = rng.random(X.shape) < 0.04
+    X[spikes] += rng.normal(0, 150.0, size=int(spikes.sum()))
+    X[10:13, 2, :] = X[9, 2, :]                      # a constant stretch: std = mad = 0
+    store = dict(points=X, versions=versions())
+    store['default'] = ref_refine.linear_interpolation(X)
+    store['k9'] = ref_refine.linear_interpolation(X, k=9, k_std=1.5, median_std=3)
+    store['rolling'] = ref_refine.linear_interpolation(X, k=7, use_rolling_average=True)
+    store['nomedian'] = ref_refine.linear_interpolation(X, k=4, filter_distance_from_median=False)
+    store['two_dim'] = ref_refine.linear_interpolation(X[:, :, 0])
+    np.savez(os.path.join(out, 'interp.npz'), **store)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reference', default='/root/reference')
@@ -179,7 +195,7 @@ def main():
     syn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(syn)
     ref_utils, ref_refine, ref_mm, ref_pe = import_reference(args.reference)
-    todo = args.only or ['dlt', 'pose3d', 'moments', 'refine']
+    todo = args.only or ['dlt', 'pose3d', 'moments', 'refine', 'interp']
     if 'dlt' in todo:
         golden_dlt(ref_utils, syn, HERE)
     if 'pose3d' in todo:
@@ -188,6 +204,8 @@ def main():
         golden_moments(ref_mm, syn, HERE)
     if 'refine' in todo:
         golden_refine(ref_refine, ref_utils, syn, HERE)
+    if 'interp' in todo:
+        golden_interp(ref_refine, syn, HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)), 'bytes')
