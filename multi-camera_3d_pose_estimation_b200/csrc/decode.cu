@@ -270,10 +270,11 @@ int decode_device(const float *d_hm, long long n_maps, int H, int W, float thr, 
     const bool tma_ok = (W % 4 == 0) && aligned16(d_hm) && map_bytes <= 96 * 1024 && !(flags & MC3D_DECODE_FLAG_GENERIC);
     if (tma_ok) {
         // choose warps x stages to keep as many bytes in flight as fit in ~200 KB of shared memory
-        int warps = 8, stages = 3;
-        const size_t budget = 200 * 1024;
+        // The two passes are issue-bound, not latency-bound: warps (instruction streams) matter more than ring depth.
+        // Two stages per warp already overlap the next map's copy with the current map's arithmetic.
+        int warps = 8, stages = 2;
+        const size_t budget = 216 * 1024;
         while (warps > 1 && (size_t)warps * stages * map_bytes > budget) warps >>= 1;
-        while (stages > 2 && (size_t)warps * stages * map_bytes > budget) --stages;
         while ((size_t)warps * (stages + 1) * map_bytes <= budget && stages < 4) ++stages;
         const size_t smem = (size_t)warps * stages * map_bytes + (size_t)warps * 8 * sizeof(uint64_t);
         static bool attr_done = false;

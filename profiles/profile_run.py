@@ -49,6 +49,13 @@ def main():
             gbs = nn * (3 * V + 3) * es / ms / 1e6
             out[f'triangulate_{io}_V{V}'] = (ms, nn / ms * 1e3, gbs)
             del kp, res
+    if only == 'decode':
+        hm = torch.rand((200_000, 64, 48), device=dev) * 0.05
+        hm[:, 30:34, 20:24] += 0.8
+        ms = timed(lambda: decode_heatmaps(hm))
+        out['decode_64x48'] = (ms, hm.shape[0] / ms * 1e3, hm.numel() * 4 / ms / 1e6)
+        ms = timed(lambda: decode_heatmaps(hm, want_moments=False))
+        out['decode_64x48_kpts_only'] = (ms, hm.shape[0] / ms * 1e3, hm.numel() * 4 / ms / 1e6)
     if only:
         for k, (ms, rate, gbs) in out.items():
             print(f'{k:28s} {ms:9.4f} ms  {rate:14.4g} units/s  {gbs:8.1f} GB/s algorithmic')
