@@ -18,6 +18,7 @@ TRI_FLAG_FP64 = 2
 KPT_PLAIN, KPT_NV3, KPT_N3V = 0, 1, 2
 DECODE_FLAG_WRITE_BACK = 1
 DECODE_FLAG_GENERIC = 2
+DECODE_FLAG_TMA = 4
 
 
 class Mc3dError(RuntimeError):

@@ -180,6 +180,129 @@ __device__ __forceinline__ void write_outputs(const MapStats &r, const float *sr
     }
 }
 
+
+// ---- register-resident kernel for 64 x 48 maps (the reference's heatmap size, BASELINE config 3) ----------------
+// One warp per map; every lane pulls its 24 float4 (element e = 4 lane + 128 k, k = 0..23) with streaming 128-bit
+// loads straight into registers -- 12 KB in flight per warp, 16 warps per SM -- and both passes run from registers:
+// no shared memory, no re-read.  With W = 48 the lane's column quad repeats with period 3 in k and its row is
+// 8 (k / 3) + const, so coordinates cost one add per float4.
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+#ifndef MC3D_DEC_BLOCKS
+#define MC3D_DEC_BLOCKS 4
+#endif
+// MOMENTS = false (keypoints only, e.g. decode -> triangulate): the thresholding, both moment passes and six of the
+// eight warp reductions disappear and the kernel is a pure streaming max.
+template <bool MOMENTS>
+__global__ void __launch_bounds__(128, MOMENTS ? MC3D_DEC_BLOCKS : 4)
+decode_reg6448_kernel(const float *__restrict__ hm, float *__restrict__ hm_wb, long long n_maps,
+                      const float *__restrict__ affine, float *__restrict__ kpt, double *__restrict__ moments,
+                      const __grid_constant__ DecodeParams p) {
+    constexpr int W = 48, HW = 64 * 48, NK = HW / 128;          // 24 float4 per lane
+    const int lane = threadIdx.x & 31;
+    const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
+    // lane constants: k = 3 j + r  ->  x0 = X[r], y = 8 j + Y[r]
+    float Xr[3], Yr[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int u = 4 * lane + 32 * r;
+        Xr[r] = (float)(u % W);
+        Yr[r] = (float)(2 * r + u / W);
+    }
+    const float thr = p.thr;
+    for (long long map = gwarp; map < n_maps; map += stride) {
+        const float4 *src = reinterpret_cast<const float4 *>(hm + map * HW) + lane;
+        float4 v[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) v[k] = ldg_stream(src + 32 * k);
+        // pass 1: argmax on the raw values, threshold in place, zeroth and first moments
+        float best = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
+        int bk = 0;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const float m4 = fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w));
+            if (m4 > best) { best = m4; bk = k; }
+            if (!MOMENTS) continue;
+            v[k].x = v[k].x < thr ? 0.f : v[k].x;
+            v[k].y = v[k].y < thr ? 0.f : v[k].y;
+            v[k].z = v[k].z < thr ? 0.f : v[k].z;
+            v[k].w = v[k].w < thr ? 0.f : v[k].w;
+            const float q = (v[k].x + v[k].y) + (v[k].z + v[k].w);
+            const float tx = fmaf(3.f, v[k].w, fmaf(2.f, v[k].z, v[k].y));
+            const float yk = Yr[k % 3] + (float)(8 * (k / 3));
+            s += q;
+            sx += fmaf(Xr[k % 3], q, tx);
+            sy = fmaf(yk, q, sy);
+        }
+        // NaN anywhere: fmaxf drops it from the argmax (as the smem kernel's `>` does) but the sums carry it
+        int best_idx = 4 * lane + 128 * bk;                  // base of the float4 holding this lane's maximum
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+            argmax_merge(best, best_idx, ov, oi);
+        }
+        MapStats r;
+        r.best = best;
+        r.best_idx = best_idx;
+        r.s = r.mx = r.my = r.vx = r.vy = r.cxy = 0.0;
+        double dsx = 0.0, dsy = 0.0;
+        if (MOMENTS) {
+            r.s = warp_sum((double)s);
+            dsx = warp_sum((double)sx);
+            dsy = warp_sum((double)sy);
+        }
+        if (MOMENTS && r.s != 0.0) {
+            r.mx = dsx / r.s;
+            r.my = dsy / r.s;
+            const float fmx = (float)r.mx, fmy = (float)r.my;
+            float dX[3], dY[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { dX[q] = Xr[q] - fmx; dY[q] = Yr[q] - fmy; }
+            float sxx = 0.f, syy = 0.f, sxy = 0.f, sdx = 0.f, sdy = 0.f;
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                const float dx0 = dX[k % 3], dy = dY[k % 3] + (float)(8 * (k / 3));
+                const float dx1 = dx0 + 1.f, dx2 = dx0 + 2.f, dx3 = dx0 + 3.f;
+                const float p0 = dx0 * v[k].x, p1 = dx1 * v[k].y, p2 = dx2 * v[k].z, p3 = dx3 * v[k].w;
+                const float m1 = (p0 + p1) + (p2 + p3);
+                const float q = (v[k].x + v[k].y) + (v[k].z + v[k].w);
+                sxx += fmaf(p0, dx0, fmaf(p1, dx1, fmaf(p2, dx2, p3 * dx3)));
+                sdx += m1;
+                sxy = fmaf(dy, m1, sxy);
+                const float dq = dy * q;
+                syy = fmaf(dy, dq, syy);
+                sdy += dq;
+            }
+            const double inv = 1.0 / r.s;
+            const double ex = warp_sum((double)sdx) * inv, ey = warp_sum((double)sdy) * inv;
+            r.vx = warp_sum((double)sxx) * inv - ex * ex;
+            r.vy = warp_sum((double)syy) * inv - ey * ey;
+            r.cxy = warp_sum((double)sxy) * inv - ex * ey;
+        }
+        // resolve the element inside the winning float4 (first maximum); raw values are still in memory
+        if (kpt && lane == 0 && best > -INFINITY) {
+            const float *raw = hm + map * HW;
+            int e = r.best_idx;
+            while (e < r.best_idx + 3 && !(raw[e] == best)) ++e;
+            r.best_idx = e;
+        }
+        write_outputs(r, hm + map * HW, map, p, affine, kpt, moments, lane);    // reads the raw neighbours of the maximum
+        if (MOMENTS && p.write_back) {                       // upstream's in-place thresholding, after the raw reads
+            __syncwarp();
+            float4 *dst = reinterpret_cast<float4 *>(hm_wb + map * HW) + lane;
+#pragma unroll
+            for (int k = 0; k < NK; ++k) dst[32 * k] = v[k];
+        }
+    }
+}
+
 // TMA path: W % 4 == 0, map bytes % 16 == 0, base 16-byte aligned.
 __global__ void __launch_bounds__(256, 1)
 decode_tma_kernel(const float *__restrict__ hm, float *__restrict__ hm_wb, long long n_maps, int warps_per_cta,
@@ -268,7 +391,16 @@ int decode_device(const float *d_hm, long long n_maps, int H, int W, float thr, 
     float *wb = const_cast<float *>(d_hm);
     const size_t map_bytes = (size_t)H * W * 4;
     const bool tma_ok = (W % 4 == 0) && aligned16(d_hm) && map_bytes <= 96 * 1024 && !(flags & MC3D_DECODE_FLAG_GENERIC);
-    if (tma_ok) {
+    const bool reg_ok = H == 64 && W == 48 && aligned16(d_hm) && !(flags & (MC3D_DECODE_FLAG_GENERIC | MC3D_DECODE_FLAG_TMA));
+    if (reg_ok) {
+        long long grid = (long long)sm_count() * 4;
+        const long long need = (n_maps + 3) / 4;
+        if (grid > need) grid = need;
+        if (d_moments || p.write_back)
+            decode_reg6448_kernel<true><<<(unsigned)grid, 128, 0, stream>>>(d_hm, wb, n_maps, d_affine, d_kpt, d_moments, p);
+        else
+            decode_reg6448_kernel<false><<<(unsigned)grid, 128, 0, stream>>>(d_hm, wb, n_maps, d_affine, d_kpt, nullptr, p);
+    } else if (tma_ok) {
         // choose warps x stages to keep as many bytes in flight as fit in ~200 KB of shared memory
         // The two passes are issue-bound, not latency-bound: warps (instruction streams) matter more than ring depth.
         // Two stages per warp already overlap the next map's copy with the current map's arithmetic.

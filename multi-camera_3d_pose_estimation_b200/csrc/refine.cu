@@ -48,47 +48,62 @@ __device__ __forceinline__ RefineDerived derive(const mc3d_refine_problem &pb, c
     return d;
 }
 
+// Arithmetic type of the per-element maths: the state dtype (float state -> float arithmetic, as upstream's torch
+// float32 run; double state -> double).  Global sums are always accumulated in double.
+template <typename C> struct Lim;
+template <> struct Lim<float> { static __device__ __forceinline__ float big() { return 3.0e38f; } };
+template <> struct Lim<double> { static __device__ __forceinline__ double big() { return 1.0e300; } };
+template <typename C> __device__ __forceinline__ bool finite_c(C v) { return fabs(v) <= Lim<C>::big(); }
+__device__ __forceinline__ float rcp_c(float v) { return 1.0f / v; }
+__device__ __forceinline__ double rcp_c(double v) { return 1.0 / v; }
+
 // Reprojection term of one camera: returns 0.5 d^T S d, and (when GRAD) adds J^T S d * scale to g[3].
-template <bool GRAD>
-__device__ __forceinline__ double reproject_term(const double *cam, bool ignore_dist, double X, double Y, double Z,
-                                                 double mx, double my, double s00, double s01, double s11,
-                                                 double scale, double *g) {
-    const double *K = cam, *R = cam + 9, *T = cam + 18, *D = cam + 21;
-    const double xc = fma(R[0], X, fma(R[1], Y, fma(R[2], Z, T[0])));
-    const double yc = fma(R[3], X, fma(R[4], Y, fma(R[5], Z, T[1])));
-    const double zc = fma(R[6], X, fma(R[7], Y, fma(R[8], Z, T[2])));
-    const double iz = 1.0 / zc;
-    const double a = xc * iz, b = yc * iz;
-    double xd = a, yd = b, j00 = 1.0, j01 = 0.0, j11 = 1.0;
+template <bool GRAD, typename C>
+__device__ __forceinline__ C reproject_term(const double *cam, bool ignore_dist, C X, C Y, C Z, C mx, C my, C s00, C s01,
+                                            C s11, C scale, C *g) {
+    C K[9], R[9], T[3], D[5];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { K[i] = (C)cam[i]; R[i] = (C)cam[9 + i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) T[i] = (C)cam[18 + i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) D[i] = (C)cam[21 + i];
+    const C one = (C)1, two = (C)2;
+    const C xc = fma(R[0], X, fma(R[1], Y, fma(R[2], Z, T[0])));
+    const C yc = fma(R[3], X, fma(R[4], Y, fma(R[5], Z, T[1])));
+    const C zc = fma(R[6], X, fma(R[7], Y, fma(R[8], Z, T[2])));
+    const C iz = rcp_c(zc);
+    const C a = xc * iz, b = yc * iz;
+    C xd = a, yd = b, j00 = one, j01 = (C)0, j11 = one;
     if (!ignore_dist) {
-        const double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3], k3 = D[4];
-        const double r2 = fma(a, a, b * b);
-        const double rad = fma(fma(fma(k3, r2, k2), r2, k1), r2, 1.0);
-        xd = fma(a, rad, fma(2.0 * p1 * a, b, p2 * fma(2.0 * a, a, r2)));
-        yd = fma(b, rad, fma(p1, fma(2.0 * b, b, r2), 2.0 * p2 * a * b));
+        const C k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3], k3 = D[4];
+        const C r2 = fma(a, a, b * b);
+        const C rad = fma(fma(fma(k3, r2, k2), r2, k1), r2, one);
+        xd = fma(a, rad, fma(two * p1 * a, b, p2 * fma(two * a, a, r2)));
+        yd = fma(b, rad, fma(p1, fma(two * b, b, r2), two * p2 * a * b));
         if (GRAD) {
-            const double drad = fma(fma(3.0 * k3, r2, 2.0 * k2), r2, k1);
-            j00 = rad + 2.0 * a * a * drad + 2.0 * p1 * b + 6.0 * p2 * a;
-            j01 = 2.0 * a * b * drad + 2.0 * p1 * a + 2.0 * p2 * b;
-            j11 = rad + 2.0 * b * b * drad + 6.0 * p1 * b + 2.0 * p2 * a;
+            const C drad = fma(fma((C)3 * k3, r2, two * k2), r2, k1);
+            j00 = rad + two * a * a * drad + two * p1 * b + (C)6 * p2 * a;
+            j01 = two * a * b * drad + two * p1 * a + two * p2 * b;
+            j11 = rad + two * b * b * drad + (C)6 * p1 * b + two * p2 * a;
         }
     }
-    const double u = fma(K[0], xd, fma(K[1], yd, K[2]));
-    const double v = fma(K[3], xd, fma(K[4], yd, K[5]));
-    const double s = fma(K[6], xd, fma(K[7], yd, K[8]));
-    const double is = 1.0 / s;
-    const double px = u * is, py = v * is;
-    const double dx = px - mx, dy = py - my;
-    const double sdx = fma(s00, dx, s01 * dy), sdy = fma(s01, dx, s11 * dy);
-    const double q = 0.5 * fma(dx, sdx, dy * sdy);
-    if (GRAD && fabs(q) <= 1.0e300) {
+    const C u = fma(K[0], xd, fma(K[1], yd, K[2]));
+    const C v = fma(K[3], xd, fma(K[4], yd, K[5]));
+    const C sden = fma(K[6], xd, fma(K[7], yd, K[8]));
+    const C is = rcp_c(sden);
+    const C px = u * is, py = v * is;
+    const C dx = px - mx, dy = py - my;
+    const C sdx = fma(s00, dx, s01 * dy), sdy = fma(s01, dx, s11 * dy);
+    const C q = (C)0.5 * fma(dx, sdx, dy * sdy);
+    if (GRAD && finite_c(q)) {
         // pixel -> distorted normalised
-        const double gxd = (sdx * (K[0] - px * K[6]) + sdy * (K[3] - py * K[6])) * is;
-        const double gyd = (sdx * (K[1] - px * K[7]) + sdy * (K[4] - py * K[7])) * is;
+        const C gxd = (sdx * (K[0] - px * K[6]) + sdy * (K[3] - py * K[6])) * is;
+        const C gyd = (sdx * (K[1] - px * K[7]) + sdy * (K[4] - py * K[7])) * is;
         // distorted -> normalised
-        const double ga = fma(j00, gxd, j01 * gyd), gb = fma(j01, gxd, j11 * gyd);
+        const C ga = fma(j00, gxd, j01 * gyd), gb = fma(j01, gxd, j11 * gyd);
         // normalised -> camera frame
-        const double gxc = ga * iz, gyc = gb * iz, gzc = -(a * ga + b * gb) * iz;
+        const C gxc = ga * iz, gyc = gb * iz, gzc = -(a * ga + b * gb) * iz;
         // camera -> world (R^T)
         g[0] = fma(scale, fma(R[0], gxc, fma(R[3], gyc, R[6] * gzc)), g[0]);
         g[1] = fma(scale, fma(R[1], gxc, fma(R[4], gyc, R[7] * gzc)), g[1]);
@@ -133,18 +148,19 @@ __device__ __forceinline__ void block_reduce_add(double (&vals)[N], double *smem
 
 // Shared-memory staging of frames [t_lo - 2, t_lo + fpb + 2) of the (halo-extended) trajectory.
 template <typename T>
-__device__ __forceinline__ void stage_frames(const T *x_ext, double *xs, long long t_lo, int fpb, int J, long long n_local) {
+__device__ __forceinline__ void stage_frames(const T *x_ext, T *xs, long long t_lo, int fpb, int J, long long n_local) {
     // x_ext frame index = local frame + 2; local frames range [-2, n_local + 2)
     const int count = (fpb + 4) * J * 3;
     const long long base = t_lo * J * 3;            // (t_lo - 2 + 2) * J * 3
     const long long limit = (n_local + 4) * (long long)J * 3;
     for (int i = threadIdx.x; i < count; i += blockDim.x) {
         const long long src = base + i;
-        xs[i] = (src < limit) ? (double)x_ext[src] : 0.0;
+        xs[i] = (src < limit) ? x_ext[src] : (T)0;
     }
 }
 
 // ---- kernel A: costs ------------------------------------------------------------------------------------------
+// Dynamic shared memory: [8 warps x 7 doubles reduction scratch | staged frames (fpb + 4) x J x 3 of T | d2 fpb x J of T]
 template <typename T>
 __global__ void __launch_bounds__(RF_THREADS)
 refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
@@ -154,15 +170,16 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
     if (ctrl[CT_STATE + 16 * parity + 5] != 0.0) return;          // stopped
     load_tables(tb, pb);
     const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones;
-    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;       // frames per tile (J <= 256)
-    double *xs = smem_d;                                           // (fpb + 4) * J * 3
-    double *d2 = xs + (fpb + 4) * J * 3;                           // fpb * J   per-joint smoothness contributions
-    double *red = d2 + fpb * J;                                    // 8 warps * 7
+    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;       // frames per tile
+    double *red = smem_d;                                          // 8 warps * 7
+    T *xs = reinterpret_cast<T *>(smem_d + 8 * 7);                 // (fpb + 4) * J * 3
+    T *d2 = xs + (fpb + 4) * J * 3;                                // fpb * J   per-joint smoothness contributions
     const T *x_ext = (const T *)pb.x;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
     const long long nloc = pb.n_frames;
     const long long n_tiles = (nloc + fpb - 1) / fpb;
     const bool ign = pb.ignore_distortions != 0;
+    const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     const int tl = threadIdx.x / J, j = threadIdx.x - tl * J;
     const bool lane_ok = tl < fpb;
@@ -174,31 +191,31 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
         const long long t = t_lo + tl;                             // local frame
         const long long tg = t + pb.frame_offset;                  // global frame
         const bool in_win = lane_ok && t < nloc && tg >= pb.win_begin && tg < pb.win_end;
-        if (lane_ok) d2[tl * J + j] = 0.0;
+        if (lane_ok) d2[tl * J + j] = (T)0;
         if (in_win) {
-            const double *xc = xs + ((tl + 2) * J + j) * 3;
-            const double X = xc[0], Y = xc[1], Z = xc[2];
+            const T *xc = xs + ((tl + 2) * J + j) * 3;
+            const T X = xc[0], Y = xc[1], Z = xc[2];
             const long long e = t * J + j;
-            const double mx = (double)mu0[e * 2], my = (double)mu0[e * 2 + 1];
-            const double s00 = (double)S[e * 3], s01 = (double)S[e * 3 + 1], s11 = (double)S[e * 3 + 2];
+            const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
+            const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
             for (int c = 0; c < C; ++c) {
-                const double q = reproject_term<false>(pb.cams[c], ign, X, Y, Z, mx, my, s00, s01, s11, 0.0, nullptr);
-                if (fabs(q) <= 1.0e300) { acc[0] += q; acc[1] += 1.0; }
+                const T q = reproject_term<false, T>(pb.cams[c], ign, X, Y, Z, mx, my, s00, s01, s11, (T)0, nullptr);
+                if (finite_c(q)) { acc[0] += (double)q; acc[1] += 1.0; }
             }
-            if (pb.lambda_smooth > 0.0 && tg - 2 >= pb.win_begin) {
-                const double *x1 = xc - J * 3, *x2 = xc - 2 * J * 3;
-                const double a0 = X - 2.0 * x1[0] + x2[0], a1 = Y - 2.0 * x1[1] + x2[1], a2 = Z - 2.0 * x1[2] + x2[2];
+            if (do_smooth && tg - 2 >= pb.win_begin) {
+                const T *x1 = xc - J * 3, *x2 = xc - 2 * J * 3;
+                const T a0 = X - (T)2 * x1[0] + x2[0], a1 = Y - (T)2 * x1[1] + x2[1], a2 = Z - (T)2 * x1[2] + x2[2];
                 d2[tl * J + j] = a0 * a0 + a1 * a1 + a2 * a2;
             }
-            if (pb.lambda_body > 0.0) {
-                const double *xf = xs + (tl + 2) * J * 3;
+            if (do_body) {
+                const T *xf = xs + (tl + 2) * J * 3;
                 for (int k = j; k < NB; k += J) {
-                    const double *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
-                    const double v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
-                    const double b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-                    if (fabs(b) <= 1.0e300) {
-                        const double a = tb.bone_len[k];
-                        acc[4] += a * b; acc[5] += b * b; acc[6] += a * a;
+                    const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
+                    const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
+                    const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                    if (finite_c(b)) {
+                        const double a = tb.bone_len[k], bd = (double)b;
+                        acc[4] += a * bd; acc[5] += bd * bd; acc[6] += a * a;
                     }
                 }
             }
@@ -206,9 +223,9 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
         __syncthreads();
         if (threadIdx.x < fpb) {                                   // one thread per frame: frame-level smoothness term
             const long long tt = t_lo + threadIdx.x, ttg = tt + pb.frame_offset;
-            if (tt < nloc && ttg >= pb.win_begin + 2 && ttg < pb.win_end && pb.lambda_smooth > 0.0) {
+            if (tt < nloc && ttg >= pb.win_begin + 2 && ttg < pb.win_end && do_smooth) {
                 double sum = 0.0;
-                for (int jj = 0; jj < J; ++jj) sum += d2[threadIdx.x * J + jj];
+                for (int jj = 0; jj < J; ++jj) sum += (double)d2[threadIdx.x * J + jj];
                 const bool ok = fabs(sum) <= 1.0e300;
                 pb.term_ok[tt + 2] = ok ? 1 : 0;
                 if (ok) { acc[2] += sum; acc[3] += 1.0; }
@@ -232,14 +249,16 @@ refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
     load_tables(tb, pb);
     const int J = pb.n_joints, C = pb.n_cams;
     const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
-    double *xs = smem_d;
-    double *red = xs + (fpb + 4) * J * 3;
+    double *red = smem_d;                                          // 8 warps
+    T *xs = reinterpret_cast<T *>(smem_d + 8);
     const T *x_ext = (const T *)pb.x;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
     T *gout = (T *)pb.g;
     const long long nloc = pb.n_frames;
     const long long n_tiles = (nloc + fpb - 1) / fpb;
     const bool ign = pb.ignore_distortions != 0;
+    const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
+    const T inv_nlik = (T)dv.inv_nlik, smooth_scale = (T)dv.smooth_scale, mu = (T)dv.mu, body_c = (T)dv.body_c;
     double gn[1] = {0.0};
     const int tl = threadIdx.x / J, j = threadIdx.x - tl * J;
     const bool lane_ok = tl < fpb;
@@ -251,52 +270,52 @@ refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
         const long long t = t_lo + tl, tg = t + pb.frame_offset;
         if (!(lane_ok && t < nloc)) continue;
         const long long e = t * J + j;
-        double g[3] = {0.0, 0.0, 0.0};
+        T g[3] = {(T)0, (T)0, (T)0};
         const bool in_win = tg >= pb.win_begin && tg < pb.win_end;
-        const double *xc = xs + ((tl + 2) * J + j) * 3;
-        const double X = xc[0], Y = xc[1], Z = xc[2];
-        const bool self_ok = fabs(X) <= 1.0e300 && fabs(Y) <= 1.0e300 && fabs(Z) <= 1.0e300;
+        const T *xc = xs + ((tl + 2) * J + j) * 3;
+        const T X = xc[0], Y = xc[1], Z = xc[2];
+        const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
         if (in_win && self_ok) {
-            const double mx = (double)mu0[e * 2], my = (double)mu0[e * 2 + 1];
-            const double s00 = (double)S[e * 3], s01 = (double)S[e * 3 + 1], s11 = (double)S[e * 3 + 2];
+            const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
+            const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
             for (int c = 0; c < C; ++c)
-                reproject_term<true>(pb.cams[c], ign, X, Y, Z, mx, my, s00, s01, s11, dv.inv_nlik, g);
-            if (pb.lambda_smooth > 0.0) {
+                reproject_term<true, T>(pb.cams[c], ign, X, Y, Z, mx, my, s00, s01, s11, inv_nlik, g);
+            if (do_smooth) {
                 // d/dx_t of sum_s ||D_s||^2 = 2 (D_t - 2 D_{t+1} + D_{t+2}) over the valid terms s
                 const int JS = J * 3;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                const T two = (T)2;
+                T s0 = (T)0, s1 = (T)0, s2 = (T)0;
                 if (pb.term_ok[t + 2]) {
-                    s0 += xc[0] - 2.0 * xc[-JS] + xc[-2 * JS]; s1 += xc[1] - 2.0 * xc[1 - JS] + xc[1 - 2 * JS];
-                    s2 += xc[2] - 2.0 * xc[2 - JS] + xc[2 - 2 * JS];
+                    s0 += xc[0] - two * xc[-JS] + xc[-2 * JS]; s1 += xc[1] - two * xc[1 - JS] + xc[1 - 2 * JS];
+                    s2 += xc[2] - two * xc[2 - JS] + xc[2 - 2 * JS];
                 }
                 if (pb.term_ok[t + 3]) {
-                    s0 -= 2.0 * (xc[JS] - 2.0 * xc[0] + xc[-JS]); s1 -= 2.0 * (xc[1 + JS] - 2.0 * xc[1] + xc[1 - JS]);
-                    s2 -= 2.0 * (xc[2 + JS] - 2.0 * xc[2] + xc[2 - JS]);
+                    s0 -= two * (xc[JS] - two * xc[0] + xc[-JS]); s1 -= two * (xc[1 + JS] - two * xc[1] + xc[1 - JS]);
+                    s2 -= two * (xc[2 + JS] - two * xc[2] + xc[2 - JS]);
                 }
                 if (pb.term_ok[t + 4]) {
-                    s0 += xc[2 * JS] - 2.0 * xc[JS] + xc[0]; s1 += xc[1 + 2 * JS] - 2.0 * xc[1 + JS] + xc[1];
-                    s2 += xc[2 + 2 * JS] - 2.0 * xc[2 + JS] + xc[2];
+                    s0 += xc[2 * JS] - two * xc[JS] + xc[0]; s1 += xc[1 + 2 * JS] - two * xc[1 + JS] + xc[1];
+                    s2 += xc[2 + 2 * JS] - two * xc[2 + JS] + xc[2];
                 }
-                g[0] = fma(dv.smooth_scale, s0, g[0]); g[1] = fma(dv.smooth_scale, s1, g[1]); g[2] = fma(dv.smooth_scale, s2, g[2]);
+                g[0] = fma(smooth_scale, s0, g[0]); g[1] = fma(smooth_scale, s1, g[1]); g[2] = fma(smooth_scale, s2, g[2]);
             }
-            if (pb.lambda_body > 0.0) {
-                const double *xf = xs + (tl + 2) * J * 3;
+            if (do_body) {
+                const T *xf = xs + (tl + 2) * J * 3;
                 for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {
                     const int k = tb.adj_bone[q];
-                    const double sign = (double)tb.adj_sign[q];
-                    const double *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
-                    const double v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
-                    const double b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-                    if (fabs(b) <= 1.0e300 && b > 0.0) {
-                        const double coef = sign * dv.body_c * (tb.bone_len[k] - dv.mu * b) / b;
+                    const T sign = (T)tb.adj_sign[q];
+                    const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
+                    const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
+                    const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                    if (finite_c(b) && b > (T)0) {
+                        const T coef = sign * body_c * ((T)tb.bone_len[k] - mu * b) / b;
                         g[0] = fma(coef, v0, g[0]); g[1] = fma(coef, v1, g[1]); g[2] = fma(coef, v2, g[2]);
                     }
                 }
             }
         }
-        const T g0 = (T)g[0], g1 = (T)g[1], g2 = (T)g[2];
-        gout[e * 3 + 0] = g0; gout[e * 3 + 1] = g1; gout[e * 3 + 2] = g2;
-        gn[0] += (double)g0 * (double)g0 + (double)g1 * (double)g1 + (double)g2 * (double)g2;
+        gout[e * 3 + 0] = g[0]; gout[e * 3 + 1] = g[1]; gout[e * 3 + 2] = g[2];
+        gn[0] += (double)g[0] * (double)g[0] + (double)g[1] * (double)g[1] + (double)g[2] * (double)g[2];
     }
     __syncthreads();
     block_reduce_add<1>(gn, red, ctrl + CT_ACC + 16 * parity + 7);
@@ -453,9 +472,9 @@ int refine_phase(const mc3d_refine_problem *pb, int phase, long long step_index,
     const long long n_tiles = (pb->n_frames + fpb - 1) / fpb;
     long long grid = (long long)sm_count() * 4;
     if (grid > n_tiles) grid = n_tiles;
-    const size_t xs_bytes = (size_t)(fpb + 4) * J * 3 * sizeof(double);
+    const size_t xs_bytes = (size_t)(fpb + 4) * J * 3 * sizeof(T);
     if (phase == 0) {
-        const size_t smem = xs_bytes + (size_t)fpb * J * sizeof(double) + 8 * 7 * sizeof(double);
+        const size_t smem = xs_bytes + (size_t)fpb * J * sizeof(T) + 8 * 7 * sizeof(double);
         refine_costs_kernel<T><<<(unsigned)grid, RF_THREADS, smem, stream>>>(*pb, parity);
     } else if (phase == 1) {
         const size_t smem = xs_bytes + 8 * sizeof(double);

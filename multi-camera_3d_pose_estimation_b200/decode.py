@@ -9,7 +9,7 @@ _KPT_LAYOUTS = {'plain': _lib.KPT_PLAIN, 'nv3': _lib.KPT_NV3, 'n3v': _lib.KPT_N3
 
 
 def decode_heatmaps(heatmaps, threshold=0.01, want_kpts=True, want_moments=True, write_back=False,
-                    kpt_layout='plain', affine=None, affine_group=None, generic=False, device=0):
+                    kpt_layout='plain', affine=None, affine_group=None, generic=False, device=0, force_tma=False):
     """heatmaps (..., H, W) float32 -> (kpts (..., 3) float32 [x, y, score] | None,
                                          moments (..., 6) float64 | None).
 
@@ -66,7 +66,8 @@ def decode_heatmaps(heatmaps, threshold=0.01, want_kpts=True, want_moments=True,
         if affine.shape[0] * group < n:
             raise ValueError('affine table too short for the number of heatmaps')
         aff_ptr = affine.data_ptr()
-    flags = (_lib.DECODE_FLAG_WRITE_BACK if write_back else 0) | (_lib.DECODE_FLAG_GENERIC if generic else 0)
+    flags = (_lib.DECODE_FLAG_WRITE_BACK if write_back else 0) | (_lib.DECODE_FLAG_GENERIC if generic else 0) | \
+        (_lib.DECODE_FLAG_TMA if force_tma else 0)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.mc3d_decode_heatmaps_f32(heatmaps.data_ptr(), n, H, W, float(threshold), flags,

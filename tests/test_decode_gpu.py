@@ -67,7 +67,7 @@ def test_means_stds_match_reference_golden():
 
 
 @pytest.mark.parametrize('shape', [(64, 48), (96, 72), (32, 32), (17, 23), (128, 96), (5, 4)])
-@pytest.mark.parametrize('generic', [False, True])
+@pytest.mark.parametrize('generic', [False, True, 'tma'])
 def test_decode_vs_oracle(dec, syn, shape, generic):
     H, W = shape
     hm, _ = syn.gaussian_blob_heatmaps(300, H=H, W=W, seed=H * W) if min(H, W) > 16 else \
@@ -75,7 +75,7 @@ def test_decode_vs_oracle(dec, syn, shape, generic):
     hm[3] = 0.0
     hm[4] = -1.0                                                   # maximum <= 0 -> (-1, -1)
     hm[7, 0, 0] = 5.0                                              # maximum on the border: no sub-pixel shift
-    kp, mom = dec(_cuda(hm), generic=generic)
+    kp, mom = dec(_cuda(hm), generic=(generic is True), force_tma=(generic == 'tma'))
     kp, mom = kp.cpu().numpy(), mom.cpu().numpy()
     ref_kp, ref_sc = D.argmax_decode(hm)
     assert np.array_equal(kp[:, :2], ref_kp)
@@ -118,6 +118,20 @@ def test_transposed_layouts_feed_triangulation(dec, syn):
     assert tuple(nv3.shape) == (T_, J, C, 3) and tuple(n3v.shape) == (T_, J, 3, C)
     assert np.allclose(nv3.cpu().numpy(), expect, rtol=1e-6, atol=1e-5)
     assert np.array_equal(np.transpose(n3v.cpu().numpy(), (0, 1, 3, 2)), nv3.cpu().numpy())
+
+
+def test_write_back_on_device_keeps_subpixel_decode(dec, syn):
+    """In-place thresholding (upstream quirk Q7) must not disturb the raw-neighbour read of the quarter-pixel shift."""
+    hm, _ = syn.gaussian_blob_heatmaps(500, seed=8, noise=0.02)
+    for kw in ({}, {'force_tma': True}, {'generic': True}):
+        t = _cuda(hm.copy())
+        kp, mom = dec(t, write_back=True, **kw)
+        ref_kp, ref_sc = D.argmax_decode(hm)
+        assert np.array_equal(kp.cpu().numpy()[:, :2], ref_kp) and np.array_equal(kp.cpu().numpy()[:, 2], ref_sc)
+        expect = hm.copy()
+        expect[expect < 0.01] = 0
+        assert np.array_equal(t.cpu().numpy(), expect)
+        assert np.abs(mom.cpu().numpy() - D.heatmap_means_cov_f64(hm)).max() < MOMENT_ATOL
 
 
 def test_nan_map_gives_nan_moments_only_there(dec, syn):
