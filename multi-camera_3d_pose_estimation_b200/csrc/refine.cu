@@ -58,16 +58,11 @@ __device__ __forceinline__ float rcp_c(float v) { return 1.0f / v; }
 __device__ __forceinline__ double rcp_c(double v) { return 1.0 / v; }
 
 // Reprojection term of one camera: returns 0.5 d^T S d, and (when GRAD) adds J^T S d * scale to g[3].
+// cam: K[9] R[9] T[3] dist[5] already in the arithmetic type (shared memory, broadcast reads).
 template <bool GRAD, typename C>
-__device__ __forceinline__ C reproject_term(const double *cam, bool ignore_dist, C X, C Y, C Z, C mx, C my, C s00, C s01,
+__device__ __forceinline__ C reproject_term(const C *cam, bool ignore_dist, C X, C Y, C Z, C mx, C my, C s00, C s01,
                                             C s11, C scale, C *g) {
-    C K[9], R[9], T[3], D[5];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { K[i] = (C)cam[i]; R[i] = (C)cam[9 + i]; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) T[i] = (C)cam[18 + i];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) D[i] = (C)cam[21 + i];
+    const C *K = cam, *R = cam + 9, *T = cam + 18, *D = cam + 21;
     const C one = (C)1, two = (C)2;
     const C xc = fma(R[0], X, fma(R[1], Y, fma(R[2], Z, T[0])));
     const C yc = fma(R[3], X, fma(R[4], Y, fma(R[5], Z, T[1])));
@@ -166,9 +161,11 @@ __global__ void __launch_bounds__(RF_THREADS)
 refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
     extern __shared__ __align__(16) double smem_d[];
     __shared__ RefineTables tb;
+    __shared__ T camf[MC3D_MAX_VIEWS * 26];
     double *ctrl = pb.ctrl;
     if (ctrl[CT_STATE + 16 * parity + 5] != 0.0) return;          // stopped
     load_tables(tb, pb);
+    for (int i = threadIdx.x; i < pb.n_cams * 26; i += blockDim.x) camf[i] = (T)pb.cams[i / 26][i % 26];
     const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones;
     const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;       // frames per tile
     double *red = smem_d;                                          // 8 warps * 7
@@ -199,7 +196,7 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
             const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
             const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
             for (int c = 0; c < C; ++c) {
-                const T q = reproject_term<false, T>(pb.cams[c], ign, X, Y, Z, mx, my, s00, s01, s11, (T)0, nullptr);
+                const T q = reproject_term<false, T>(camf + c * 26, ign, X, Y, Z, mx, my, s00, s01, s11, (T)0, nullptr);
                 if (finite_c(q)) { acc[0] += (double)q; acc[1] += 1.0; }
             }
             if (do_smooth && tg - 2 >= pb.win_begin) {
@@ -243,10 +240,12 @@ __global__ void __launch_bounds__(RF_THREADS)
 refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
     extern __shared__ __align__(16) double smem_d[];
     __shared__ RefineTables tb;
+    __shared__ T camf[MC3D_MAX_VIEWS * 26];
     double *ctrl = pb.ctrl;
     const RefineDerived dv = derive(pb, ctrl, parity);
     if (dv.stopped) return;
     load_tables(tb, pb);
+    for (int i = threadIdx.x; i < pb.n_cams * 26; i += blockDim.x) camf[i] = (T)pb.cams[i / 26][i % 26];
     const int J = pb.n_joints, C = pb.n_cams;
     const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
     double *red = smem_d;                                          // 8 warps
@@ -279,7 +278,7 @@ refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
             const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
             const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
             for (int c = 0; c < C; ++c)
-                reproject_term<true, T>(pb.cams[c], ign, X, Y, Z, mx, my, s00, s01, s11, inv_nlik, g);
+                reproject_term<true, T>(camf + c * 26, ign, X, Y, Z, mx, my, s00, s01, s11, inv_nlik, g);
             if (do_smooth) {
                 // d/dx_t of sum_s ||D_s||^2 = 2 (D_t - 2 D_{t+1} + D_{t+2}) over the valid terms s
                 const int JS = J * 3;

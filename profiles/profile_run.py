@@ -56,6 +56,15 @@ def main():
         out['decode_64x48'] = (ms, hm.shape[0] / ms * 1e3, hm.numel() * 4 / ms / 1e6)
         ms = timed(lambda: decode_heatmaps(hm, want_moments=False))
         out['decode_64x48_kpts_only'] = (ms, hm.shape[0] / ms * 1e3, hm.numel() * 4 / ms / 1e6)
+    if only == 'refine':
+        gs, init, cams, _ = syn.refinement_inputs(100_000, n_cams=2, seed=0)
+        rows = rf.camera_rows(cams, list(cams))
+        eng = rf.RefineEngine(init, gs, rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=torch.float32, device=dev, lr=0.01,
+                              betas=(0.9, 0.999), lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
+                              max_iter=10 ** 9, ignore_distortions=False, window=(0, 100_000), n_window_frames=100_000,
+                              hist_capacity=64)
+        ms = timed(lambda: eng.one_step(True), reps=4)
+        out['refine_step_f32_T100k'] = (ms, 1e3 / ms, 100_000 * 17 * 160 / ms / 1e6)
     if only:
         for k, (ms, rate, gbs) in out.items():
             print(f'{k:28s} {ms:9.4f} ms  {rate:14.4g} units/s  {gbs:8.1f} GB/s algorithmic')

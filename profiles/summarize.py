@@ -45,15 +45,18 @@ def main():
                 print(f'stall {h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", "")} = {v:.2f} warps per issue')
     src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
-    start = None
-    for i, r in enumerate(rows):
-        if 'Source' in r and 'Instructions Executed' in r:
-            hdr2, start = r, i + 1
-            break
-    if start is not None:
+    sections, cur = [], None
+    for r in rows:
+        if 'Source' in r and 'Instructions Executed' in r:      # one header row per profiled kernel
+            cur = {'hdr': r, 'rows': []}
+            sections.append(cur)
+        elif cur is not None:
+            cur['rows'].append(r)
+    if which < len(sections):
+        hdr2, body = sections[which]['hdr'], sections[which]['rows']
         si, ei = hdr2.index('Source'), hdr2.index('Instructions Executed')
         cnt, tot = collections.Counter(), 0
-        for r in rows[start:]:
+        for r in body:
             if len(r) <= max(si, ei):
                 continue
             try:
@@ -65,7 +68,7 @@ def main():
             cnt[op] += n
             tot += n
         per = units / 32.0
-        print(f'warp instructions executed (first kernel in the report): {tot}  = {tot / per:.1f} per unit (thread-level)')
+        print(f'warp instructions executed: {tot}  = {tot / per:.1f} per unit (thread-level)')
         print('opcode mix per unit: ' + ' '.join(f'{op}:{n / per:.1f}' for op, n in cnt.most_common(24)))
         sass = ' '.join(cnt)
         print('TMA / Blackwell evidence in executed SASS: ' + ', '.join(op for op in ('UBLKCP', 'SYNCS', 'FFMA2', 'FMUL2', 'UTMALDG') if op in cnt))
