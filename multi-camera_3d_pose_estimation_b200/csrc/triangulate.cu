@@ -194,25 +194,29 @@ __device__ __forceinline__ void accumulate_view(double *B, double x, double y, d
 // ---- mixed-precision solver (float storage) ---------------------------------------------------------------------
 // float LDL^T solve of a 3x3 SPD system; approximate reciprocals are fine: this solve only preconditions the
 // iteration below, whose fixed point is set by residuals evaluated in double.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ bool ldl3_solve_f(float m00, float m10, float m11, float m20, float m21, float m22,
                                              float r0, float r1, float r2, float &z0, float &z1, float &z2) {
-    if (!(m00 > 0.f)) return false;
-    const float i0 = __fdividef(1.f, m00);
+    // branch-free: bad pivots produce inf / NaN that the caller discards through the returned flag
+    const float i0 = rcp_fast(m00);
     const float l10 = m10 * i0, l20 = m20 * i0;
     const float d1 = fmaf(-l10, m10, m11);
-    if (!(d1 > 1e-6f * m11)) return false;
-    const float i1 = __fdividef(1.f, d1);
+    const float i1 = rcp_fast(d1);
     const float t21 = fmaf(-l20, m10, m21);
     const float l21 = t21 * i1;
     const float d2 = fmaf(-l21, t21, fmaf(-l20, m20, m22));
-    if (!(d2 > 1e-6f * m22)) return false;
-    const float i2 = __fdividef(1.f, d2);
+    const float i2 = rcp_fast(d2);
     const float y1 = fmaf(-l10, r0, r1);
     const float y2 = fmaf(-l21, y1, fmaf(-l20, r0, r2));
     z2 = y2 * i2;
     z1 = fmaf(y1, i1, -l21 * z2);
     z0 = fmaf(r0, i0, -fmaf(l10, z1, l20 * z2));
-    return true;
+    return (m00 > 0.f) & (d1 > 1e-6f * m11) & (d2 > 1e-6f * m22);
 }
 
 // All-double solve of one joint straight from its shared-memory row (cold path of the mixed kernel).
@@ -277,18 +281,20 @@ template <int V, int LAYOUT, int NJ>
 __device__ __forceinline__ void solve_mixed(const TriParams &prm, const float *const (&rows)[NJ], const bool (&act)[NJ],
                                             double (&X)[NJ][3], int (&state)[NJ]) {
     float2 aM[NJ][6], ab[NJ][3];
-    int n_used[NJ];
     float m[NJ][6], b[NJ][3];
     constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
+#ifndef MC3D_TRI_UNR_LIMIT
+#define MC3D_TRI_UNR_LIMIT 4
+#endif
+    constexpr int UNR = (V > MC3D_TRI_UNR_LIMIT) ? 1 : (V / G);   // full unrolling of 8+ views hoists loads into spills
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        n_used[j] = 0;
 #pragma unroll
         for (int i = 0; i < 6; ++i) aM[j][i] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 3; ++i) ab[j][i] = make_float2(0.f, 0.f);
     }
-#pragma unroll
+#pragma unroll UNR
     for (int vg = 0; vg < V; vg += G) {
         float gx[NJ][G], gy[NJ][G], gw[NJ][G];
 #pragma unroll
@@ -303,7 +309,6 @@ __device__ __forceinline__ void solve_mixed(const TriParams &prm, const float *c
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const float w = gw[j][i];
-                n_used[j] += (w != 0.f);
                 const float xc = gx[j][i] - cxy.x, yc = gy[j][i] - cxy.y;
                 const float2 sv = make_float2(w * yc, -(w * xc));
                 const float2 ww = make_float2(w, w);
@@ -333,8 +338,9 @@ __device__ __forceinline__ void solve_mixed(const TriParams &prm, const float *c
         Xd[j][0] = Xd[j][1] = Xd[j][2] = 0.0;
         state[j] = 0;
         if (!act[j]) { state[j] = 0; continue; }
-        const bool fin = (fabsf(m[j][0] + m[j][2] + m[j][5]) <= 3.0e38f) && (fabsf(b[j][0]) + fabsf(b[j][1]) + fabsf(b[j][2]) <= 3.0e38f);
-        if (n_used[j] < 2 || !fin) continue;                    // degenerate: NaN, done
+        // Non-finite input or fewer than two usable views make the float factorisation fail (NaN compares false,
+        // a rank-deficient M~ has a pivot at rounding level): those joints take the all-double path, which
+        // classifies them (NaN output) exactly like the double-storage kernel.
         float z0, z1, z2;
         if (!ldl3_solve_f(m[j][0], m[j][1], m[j][2], m[j][3], m[j][4], m[j][5], -b[j][0], -b[j][1], -b[j][2], z0, z1, z2)) {
             state[j] = 1;
@@ -357,7 +363,7 @@ __device__ __forceinline__ void solve_mixed(const TriParams &prm, const float *c
 #pragma unroll
             for (int k = 0; k < 3; ++k) { gp[j][k] = make_float2(0.f, 0.f); gq[j][k] = 0.f; }
         }
-#pragma unroll
+#pragma unroll UNR
         for (int vg = 0; vg < V; vg += G) {
             float gx[NJ][G], gy[NJ][G], gw[NJ][G];              // re-read: cheaper than holding 3V registers per joint
 #pragma unroll
@@ -401,7 +407,7 @@ __device__ __forceinline__ void solve_mixed(const TriParams &prm, const float *c
             if (state[j] != 2) continue;
             const float xf0 = (float)Xd[j][0], xf1 = (float)Xd[j][1], xf2 = (float)Xd[j][2];
             const float nx = fmaf(xf0, xf0, fmaf(xf1, xf1, xf2 * xf2));
-            const float lam = __fdividef(rr[j], 1.f + nx);
+            const float lam = rr[j] * rcp_fast(1.f + nx);
             const float f0 = (gp[j][0].x + gp[j][0].y + gq[j][0]) - lam * xf0;
             const float f1 = (gp[j][1].x + gp[j][1].y + gq[j][1]) - lam * xf1;
             const float f2 = (gp[j][2].x + gp[j][2].y + gq[j][2]) - lam * xf2;
@@ -431,16 +437,16 @@ __device__ __forceinline__ void solve_mixed(const TriParams &prm, const float *c
 #define MC3D_TRI_MTHREADS 128
 #endif
 #ifndef MC3D_TRI_MBLOCKS
-#define MC3D_TRI_MBLOCKS 3
+#define MC3D_TRI_MBLOCKS 4
 #endif
 constexpr int TRI_NJ = MC3D_TRI_NJ;             // joints per thread in the mixed kernel
 constexpr int TRI_MTHREADS = MC3D_TRI_MTHREADS; // threads per CTA of the mixed kernel
 constexpr int TRI_MTILE = TRI_MTHREADS * TRI_NJ;    // joints per tile
 
 // Mixed-precision kernel (float storage, weighted mode, V in {2,3,4,8,16}, no undistortion).  Same TMA ring as the
-// generic kernel; 128 threads x 2 joints per thread (thread t owns joints t and t + 128 of a 256-joint tile) at
-// 3 CTAs per SM measured fastest on B200 of the (joints/thread, threads, CTAs/SM) variants tried -- it is the one
-// whose register budget (168) avoids spilling the per-joint accumulators (profiles/README.md).
+// generic kernel; 128 threads x 2 joints per thread (thread t owns joints t and t + 128 of a 256-joint tile), view
+// loops unrolled four views at a time, 4 CTAs per SM (112 registers, no spills): the fastest on B200 of the
+// (joints/thread, threads, CTAs/SM, unroll) variants timed (profiles/README.md).
 template <int V, int LAYOUT>
 __global__ void __launch_bounds__(TRI_MTHREADS, MC3D_TRI_MBLOCKS)
 triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out, long long n, int n_stages,
@@ -502,8 +508,11 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
         solve_mixed<V, LAYOUT, TRI_NJ>(prm, rows, act, X, state);
 #pragma unroll
         for (int j = 0; j < TRI_NJ; ++j)
-            if (act[j] && state[j] == 1)
-                solve_double_from_row(prm, rows[j], V, LAYOUT == MC3D_LAYOUT_3V, X[j][0], X[j][1], X[j][2]);
+            if (act[j] && state[j] == 1) {
+                double f0, f1, f2;                   // separate scalars: X[][] must not have its address taken
+                solve_double_from_row(prm, rows[j], V, LAYOUT == MC3D_LAYOUT_3V, f0, f1, f2);
+                X[j][0] = f0; X[j][1] = f1; X[j][2] = f2;
+            }
         __syncthreads();                       // [A] every thread has consumed stage s
         float *ot = otile + (size_t)(k & 1) * TRI_MTILE * 3;
         if (full_tile) {
