@@ -20,6 +20,13 @@
 namespace mc3d {
 
 constexpr int RF_THREADS = 256;
+#ifndef MC3D_RF_ITEMS
+#define MC3D_RF_ITEMS 1
+#endif
+#ifndef MC3D_RF_GRID
+#define MC3D_RF_GRID 4
+#endif
+constexpr int RF_ITEMS = MC3D_RF_ITEMS;   // (frame, joint) items per thread and tile; 1 measured fastest (2, 4 starve the grid of tiles)
 // control block layout (doubles)
 constexpr int CT_ACC = 0;        // + 16 * parity : S_lik N_lik S_s N_s ab bb aa_ok gnorm2
 constexpr int CT_STATE = 32;     // + 16 * parity : step run_sum run_cnt best no_improve stopped iters_done improved
@@ -155,7 +162,8 @@ __device__ __forceinline__ void stage_frames(const T *x_ext, T *xs, long long t_
 }
 
 // ---- kernel A: costs ------------------------------------------------------------------------------------------
-// Dynamic shared memory: [8 warps x 7 doubles reduction scratch | staged frames (fpb + 4) x J x 3 of T | d2 fpb x J of T]
+// Dynamic shared memory: [8 warps x 7 doubles reduction scratch | staged frames (F + 4) x J x 3 of T | d2 F x J of T],
+// F = RF_ITEMS * (256 / J) frames per tile; thread (tl, j) owns frames tl, tl + fpb, ... of the tile.
 template <typename T>
 __global__ void __launch_bounds__(RF_THREADS)
 refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
@@ -167,30 +175,34 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
     load_tables(tb, pb);
     for (int i = threadIdx.x; i < pb.n_cams * 26; i += blockDim.x) camf[i] = (T)pb.cams[i / 26][i % 26];
     const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones;
-    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;       // frames per tile
+    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
+    const int F = fpb * RF_ITEMS;                                  // frames per tile
     double *red = smem_d;                                          // 8 warps * 7
-    T *xs = reinterpret_cast<T *>(smem_d + 8 * 7);                 // (fpb + 4) * J * 3
-    T *d2 = xs + (fpb + 4) * J * 3;                                // fpb * J   per-joint smoothness contributions
+    T *xs = reinterpret_cast<T *>(smem_d + 8 * 7);                 // (F + 4) * J * 3
+    T *d2 = xs + (F + 4) * J * 3;                                  // F * J   per-joint smoothness contributions
     const T *x_ext = (const T *)pb.x;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
     const long long nloc = pb.n_frames;
-    const long long n_tiles = (nloc + fpb - 1) / fpb;
+    const long long n_tiles = (nloc + F - 1) / F;
     const bool ign = pb.ignore_distortions != 0;
     const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     const int tl = threadIdx.x / J, j = threadIdx.x - tl * J;
     const bool lane_ok = tl < fpb;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long t_lo = tile * fpb;
+        const long long t_lo = tile * F;
         __syncthreads();
-        stage_frames(x_ext, xs, t_lo, fpb, J, nloc);
+        stage_frames(x_ext, xs, t_lo, F, J, nloc);
         __syncthreads();
-        const long long t = t_lo + tl;                             // local frame
-        const long long tg = t + pb.frame_offset;                  // global frame
-        const bool in_win = lane_ok && t < nloc && tg >= pb.win_begin && tg < pb.win_end;
-        if (lane_ok) d2[tl * J + j] = (T)0;
-        if (in_win) {
-            const T *xc = xs + ((tl + 2) * J + j) * 3;
+#pragma unroll
+        for (int it = 0; it < RF_ITEMS; ++it) {
+            const int fl = tl + it * fpb;                          // frame within the tile
+            const long long t = t_lo + fl;                         // local frame
+            const long long tg = t + pb.frame_offset;              // global frame
+            const bool in_win = lane_ok && t < nloc && tg >= pb.win_begin && tg < pb.win_end;
+            if (lane_ok) d2[fl * J + j] = (T)0;
+            if (!in_win) continue;
+            const T *xc = xs + ((fl + 2) * J + j) * 3;
             const T X = xc[0], Y = xc[1], Z = xc[2];
             const long long e = t * J + j;
             const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
@@ -202,10 +214,10 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
             if (do_smooth && tg - 2 >= pb.win_begin) {
                 const T *x1 = xc - J * 3, *x2 = xc - 2 * J * 3;
                 const T a0 = X - (T)2 * x1[0] + x2[0], a1 = Y - (T)2 * x1[1] + x2[1], a2 = Z - (T)2 * x1[2] + x2[2];
-                d2[tl * J + j] = a0 * a0 + a1 * a1 + a2 * a2;
+                d2[fl * J + j] = a0 * a0 + a1 * a1 + a2 * a2;
             }
             if (do_body) {
-                const T *xf = xs + (tl + 2) * J * 3;
+                const T *xf = xs + (fl + 2) * J * 3;
                 for (int k = j; k < NB; k += J) {
                     const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
                     const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
@@ -218,11 +230,11 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
             }
         }
         __syncthreads();
-        if (threadIdx.x < fpb) {                                   // one thread per frame: frame-level smoothness term
-            const long long tt = t_lo + threadIdx.x, ttg = tt + pb.frame_offset;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {        // one thread per frame: frame-level smoothness term
+            const long long tt = t_lo + f, ttg = tt + pb.frame_offset;
             if (tt < nloc && ttg >= pb.win_begin + 2 && ttg < pb.win_end && do_smooth) {
                 double sum = 0.0;
-                for (int jj = 0; jj < J; ++jj) sum += (double)d2[threadIdx.x * J + jj];
+                for (int jj = 0; jj < J; ++jj) sum += (double)d2[f * J + jj];
                 const bool ok = fabs(sum) <= 1.0e300;
                 pb.term_ok[tt + 2] = ok ? 1 : 0;
                 if (ok) { acc[2] += sum; acc[3] += 1.0; }
@@ -248,13 +260,14 @@ refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
     for (int i = threadIdx.x; i < pb.n_cams * 26; i += blockDim.x) camf[i] = (T)pb.cams[i / 26][i % 26];
     const int J = pb.n_joints, C = pb.n_cams;
     const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
+    const int F = fpb * RF_ITEMS;
     double *red = smem_d;                                          // 8 warps
     T *xs = reinterpret_cast<T *>(smem_d + 8);
     const T *x_ext = (const T *)pb.x;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
     T *gout = (T *)pb.g;
     const long long nloc = pb.n_frames;
-    const long long n_tiles = (nloc + fpb - 1) / fpb;
+    const long long n_tiles = (nloc + F - 1) / F;
     const bool ign = pb.ignore_distortions != 0;
     const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
     const T inv_nlik = (T)dv.inv_nlik, smooth_scale = (T)dv.smooth_scale, mu = (T)dv.mu, body_c = (T)dv.body_c;
@@ -262,59 +275,63 @@ refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
     const int tl = threadIdx.x / J, j = threadIdx.x - tl * J;
     const bool lane_ok = tl < fpb;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long t_lo = tile * fpb;
+        const long long t_lo = tile * F;
         __syncthreads();
-        stage_frames(x_ext, xs, t_lo, fpb, J, nloc);
+        stage_frames(x_ext, xs, t_lo, F, J, nloc);
         __syncthreads();
-        const long long t = t_lo + tl, tg = t + pb.frame_offset;
-        if (!(lane_ok && t < nloc)) continue;
-        const long long e = t * J + j;
-        T g[3] = {(T)0, (T)0, (T)0};
-        const bool in_win = tg >= pb.win_begin && tg < pb.win_end;
-        const T *xc = xs + ((tl + 2) * J + j) * 3;
-        const T X = xc[0], Y = xc[1], Z = xc[2];
-        const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
-        if (in_win && self_ok) {
-            const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
-            const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
-            for (int c = 0; c < C; ++c)
-                reproject_term<true, T>(camf + c * 26, ign, X, Y, Z, mx, my, s00, s01, s11, inv_nlik, g);
-            if (do_smooth) {
-                // d/dx_t of sum_s ||D_s||^2 = 2 (D_t - 2 D_{t+1} + D_{t+2}) over the valid terms s
-                const int JS = J * 3;
-                const T two = (T)2;
-                T s0 = (T)0, s1 = (T)0, s2 = (T)0;
-                if (pb.term_ok[t + 2]) {
-                    s0 += xc[0] - two * xc[-JS] + xc[-2 * JS]; s1 += xc[1] - two * xc[1 - JS] + xc[1 - 2 * JS];
-                    s2 += xc[2] - two * xc[2 - JS] + xc[2 - 2 * JS];
+#pragma unroll
+        for (int it = 0; it < RF_ITEMS; ++it) {
+            const int fl = tl + it * fpb;
+            const long long t = t_lo + fl, tg = t + pb.frame_offset;
+            if (!(lane_ok && t < nloc)) continue;
+            const long long e = t * J + j;
+            T g[3] = {(T)0, (T)0, (T)0};
+            const bool in_win = tg >= pb.win_begin && tg < pb.win_end;
+            const T *xc = xs + ((fl + 2) * J + j) * 3;
+            const T X = xc[0], Y = xc[1], Z = xc[2];
+            const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
+            if (in_win && self_ok) {
+                const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
+                const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
+                for (int c = 0; c < C; ++c)
+                    reproject_term<true, T>(camf + c * 26, ign, X, Y, Z, mx, my, s00, s01, s11, inv_nlik, g);
+                if (do_smooth) {
+                    // d/dx_t of sum_s ||D_s||^2 = 2 (D_t - 2 D_{t+1} + D_{t+2}) over the valid terms s
+                    const int JS = J * 3;
+                    const T two = (T)2;
+                    T s0 = (T)0, s1 = (T)0, s2 = (T)0;
+                    if (pb.term_ok[t + 2]) {
+                        s0 += xc[0] - two * xc[-JS] + xc[-2 * JS]; s1 += xc[1] - two * xc[1 - JS] + xc[1 - 2 * JS];
+                        s2 += xc[2] - two * xc[2 - JS] + xc[2 - 2 * JS];
+                    }
+                    if (pb.term_ok[t + 3]) {
+                        s0 -= two * (xc[JS] - two * xc[0] + xc[-JS]); s1 -= two * (xc[1 + JS] - two * xc[1] + xc[1 - JS]);
+                        s2 -= two * (xc[2 + JS] - two * xc[2] + xc[2 - JS]);
+                    }
+                    if (pb.term_ok[t + 4]) {
+                        s0 += xc[2 * JS] - two * xc[JS] + xc[0]; s1 += xc[1 + 2 * JS] - two * xc[1 + JS] + xc[1];
+                        s2 += xc[2 + 2 * JS] - two * xc[2 + JS] + xc[2];
+                    }
+                    g[0] = fma(smooth_scale, s0, g[0]); g[1] = fma(smooth_scale, s1, g[1]); g[2] = fma(smooth_scale, s2, g[2]);
                 }
-                if (pb.term_ok[t + 3]) {
-                    s0 -= two * (xc[JS] - two * xc[0] + xc[-JS]); s1 -= two * (xc[1 + JS] - two * xc[1] + xc[1 - JS]);
-                    s2 -= two * (xc[2 + JS] - two * xc[2] + xc[2 - JS]);
-                }
-                if (pb.term_ok[t + 4]) {
-                    s0 += xc[2 * JS] - two * xc[JS] + xc[0]; s1 += xc[1 + 2 * JS] - two * xc[1 + JS] + xc[1];
-                    s2 += xc[2 + 2 * JS] - two * xc[2 + JS] + xc[2];
-                }
-                g[0] = fma(smooth_scale, s0, g[0]); g[1] = fma(smooth_scale, s1, g[1]); g[2] = fma(smooth_scale, s2, g[2]);
-            }
-            if (do_body) {
-                const T *xf = xs + (tl + 2) * J * 3;
-                for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {
-                    const int k = tb.adj_bone[q];
-                    const T sign = (T)tb.adj_sign[q];
-                    const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
-                    const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
-                    const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-                    if (finite_c(b) && b > (T)0) {
-                        const T coef = sign * body_c * ((T)tb.bone_len[k] - mu * b) / b;
-                        g[0] = fma(coef, v0, g[0]); g[1] = fma(coef, v1, g[1]); g[2] = fma(coef, v2, g[2]);
+                if (do_body) {
+                    const T *xf = xs + (fl + 2) * J * 3;
+                    for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {
+                        const int k = tb.adj_bone[q];
+                        const T sign = (T)tb.adj_sign[q];
+                        const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
+                        const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
+                        const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                        if (finite_c(b) && b > (T)0) {
+                            const T coef = sign * body_c * ((T)tb.bone_len[k] - mu * b) / b;
+                            g[0] = fma(coef, v0, g[0]); g[1] = fma(coef, v1, g[1]); g[2] = fma(coef, v2, g[2]);
+                        }
                     }
                 }
             }
+            gout[e * 3 + 0] = g[0]; gout[e * 3 + 1] = g[1]; gout[e * 3 + 2] = g[2];
+            gn[0] += (double)g[0] * (double)g[0] + (double)g[1] * (double)g[1] + (double)g[2] * (double)g[2];
         }
-        gout[e * 3 + 0] = g[0]; gout[e * 3 + 1] = g[1]; gout[e * 3 + 2] = g[2];
-        gn[0] += (double)g[0] * (double)g[0] + (double)g[1] * (double)g[1] + (double)g[2] * (double)g[2];
     }
     __syncthreads();
     block_reduce_add<1>(gn, red, ctrl + CT_ACC + 16 * parity + 7);
@@ -348,9 +365,14 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
         iters += 1.0;
         stop = (no_imp >= (double)pb.patience) || (iters > (double)pb.max_iter);
     }
-    const double bc1 = 1.0 - pow(pb.beta1, step), bc2 = 1.0 - pow(pb.beta2, step);
-    const T step_size = (T)(pb.lr / bc1);
-    const T inv_bc2_sqrt = (T)(1.0 / sqrt(bc2));
+    __shared__ double bias[2];
+    if (threadIdx.x == 0) {                                        // two double pow() per block, not per thread
+        bias[0] = 1.0 - pow(pb.beta1, step);
+        bias[1] = 1.0 - pow(pb.beta2, step);
+    }
+    __syncthreads();
+    const T step_size = (T)(pb.lr / bias[0]);
+    const T inv_bc2_sqrt = (T)(1.0 / sqrt(bias[1]));
     const T w1 = (T)(1.0 - pb.beta1), b2 = (T)pb.beta2, w2 = (T)(1.0 - pb.beta2), eps = (T)pb.eps, clipT = (T)clip;
     const bool clip_nan = !(clip == clip);
     T *x = (T *)pb.x + 2LL * pb.n_joints * 3;                       // skip the two halo frames
@@ -359,14 +381,34 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
     const long long per_frame = (long long)pb.n_joints * 3;
     const long long n = pb.n_frames * per_frame;
     const long long lo = (pb.win_begin - pb.frame_offset) * per_frame, hi = (pb.win_end - pb.frame_offset) * per_frame;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        T gi = (i >= lo && i < hi) ? g[i] : (T)0;
+    auto adam = [&](T gi, T &mi, T &vi, T &xi) {
         gi = clip_nan ? (T)NAN : gi * clipT;
-        T mi = m[i], vi = v[i], xi = x[i];
         mi = mi + (gi - mi) * w1;                                  // exp_avg.lerp_(grad, 1 - beta1)
         vi = vi * b2 + w2 * gi * gi;                               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
         const T denom = sqrt(vi) * inv_bc2_sqrt + eps;
         xi = xi - step_size * (mi / denom);                        // param.addcdiv_(exp_avg, denom, value=-step_size)
+    };
+    // two scalars per access: the halo offset of x (2 J 3 scalars) is always 8-byte (float) / 16-byte (double) aligned
+    struct alignas(2 * sizeof(T)) Vec2 { T a, b; };
+    const long long n2 = n >> 1;
+    const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    for (long long i2 = tid0; i2 < n2; i2 += nthr) {
+        const long long i = i2 << 1;
+        Vec2 gv = reinterpret_cast<const Vec2 *>(g)[i2];
+        Vec2 mv = reinterpret_cast<Vec2 *>(m)[i2], vv = reinterpret_cast<Vec2 *>(v)[i2], xv = reinterpret_cast<Vec2 *>(x)[i2];
+        if (!(i >= lo && i < hi)) gv.a = (T)0;
+        if (!(i + 1 >= lo && i + 1 < hi)) gv.b = (T)0;
+        adam(gv.a, mv.a, vv.a, xv.a);
+        adam(gv.b, mv.b, vv.b, xv.b);
+        reinterpret_cast<Vec2 *>(m)[i2] = mv;
+        reinterpret_cast<Vec2 *>(v)[i2] = vv;
+        reinterpret_cast<Vec2 *>(x)[i2] = xv;
+        if (improved) reinterpret_cast<Vec2 *>(bestx)[i2] = xv;
+    }
+    if ((n & 1) && tid0 == 0) {                                    // odd tail
+        const long long i = n - 1;
+        T gi = (i >= lo && i < hi) ? g[i] : (T)0, mi = m[i], vi = v[i], xi = x[i];
+        adam(gi, mi, vi, xi);
         m[i] = mi; v[i] = vi; x[i] = xi;
         if (improved) bestx[i] = xi;
     }
@@ -468,12 +510,13 @@ int refine_phase(const mc3d_refine_problem *pb, int phase, long long step_index,
     const int parity = (int)(step_index & 1);
     const int J = pb->n_joints;
     const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
-    const long long n_tiles = (pb->n_frames + fpb - 1) / fpb;
-    long long grid = (long long)sm_count() * 4;
+    const int F = fpb * RF_ITEMS;
+    const long long n_tiles = (pb->n_frames + F - 1) / F;
+    long long grid = (long long)sm_count() * MC3D_RF_GRID;
     if (grid > n_tiles) grid = n_tiles;
-    const size_t xs_bytes = (size_t)(fpb + 4) * J * 3 * sizeof(T);
+    const size_t xs_bytes = (size_t)(F + 4) * J * 3 * sizeof(T);
     if (phase == 0) {
-        const size_t smem = xs_bytes + (size_t)fpb * J * sizeof(T) + 8 * 7 * sizeof(double);
+        const size_t smem = xs_bytes + (size_t)F * J * sizeof(T) + 8 * 7 * sizeof(double);
         refine_costs_kernel<T><<<(unsigned)grid, RF_THREADS, smem, stream>>>(*pb, parity);
     } else if (phase == 1) {
         const size_t smem = xs_bytes + 8 * sizeof(double);
