@@ -320,6 +320,16 @@ def run_ours(args, rank, local_rank, world):
     except Exception as exc:            # report, do not hide
         e2e = {'value': None, 'unit': 'joints/s', 'error': repr(exc)}
 
+    refine_mgpu = None
+    if world > 1 and not args.no_refine:
+        # config 4 sharded over the ranks: 100 000 frames in total, halos + 2 scalar all-reduces per step over NCCL
+        del kp, out
+        torch.cuda.empty_cache()
+        try:
+            refine_mgpu = refine_benchmark(100_000, 400, 'f32', device, world=world)
+        except Exception as exc:
+            refine_mgpu = {'error': repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -341,6 +351,8 @@ def run_ours(args, rank, local_rank, world):
                      'frac_of_nominal_8TBs': achieved / 8000.0},
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }
+    if refine_mgpu is not None:
+        line['refine'] = {f'T100k_f32_sharded_over_{world}_gpus': refine_mgpu}
     if world == 1 and not args.no_refine:
         try:
             line['refine'] = {'T100k_f32': refine_benchmark(100_000, 400, 'f32', device),
@@ -380,15 +392,23 @@ def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0):
                           betas=(0.9, 0.999), lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
                           max_iter=10 ** 9, ignore_distortions=False, window=(0, n_frames), n_window_frames=n_frames,
                           hist_capacity=iters * 2 + 64, comm=comm)
-    warm = 32 if world == 1 else 8
-    eng.run(warm)
+    warm = 32
+    eng.run(warm)                                  # several ranks: also captures the 2-step CUDA graph
     torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     eng.run(iters)
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    graphed = getattr(eng, '_graph', None) is not None
+    eng.release_graph()
     hist = eng.history(warm + iters)
     esize = 4 if dtype_name == 'f32' else 8
     # per joint-frame and iteration: A reads x, mu0, S (8 scalars); B reads the same and writes g (11); C reads g, x, m, v
@@ -396,7 +416,8 @@ def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0):
     algo = n_frames * 17 * (8 + 11 + 21) * esize
     return {'frames': n_frames, 'iters': iters, 'dtype': dtype_name, 'iters_per_s': iters / (ms * 1e-3), 'us_per_iter': 1e3 * ms / iters,
             'algorithmic_bytes_per_iter': algo, 'achieved_GBs': algo / (ms * 1e-3 / iters) / 1e9,
-            'cost_first': float(hist[0, 0]), 'cost_last': float(hist[-1, 0]), 'kernels_per_iter': 3}
+            'cost_first': float(hist[0, 0]), 'cost_last': float(hist[-1, 0]), 'kernels_per_iter': 3, 'world': world,
+            'collectives_per_iter': 0 if world == 1 else 4, 'multi_rank_cuda_graph': graphed}
 
 
 def _time_launches(fn, reps):

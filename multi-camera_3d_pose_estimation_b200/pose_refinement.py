@@ -234,6 +234,7 @@ class Optimized_3d_Pose_Estimation:
                 if st['stopped'] or np.isnan(means[-1] if len(means) else 0.0):
                     stopped_early = st['no_improve'] >= patience
                     break
+        engine.release_graph()
         st = engine.state()
         hist = engine.history(st['adam_step'])
         if stopped_early:

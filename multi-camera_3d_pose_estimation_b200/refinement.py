@@ -15,6 +15,7 @@ over gloo on CPU tensors in the tests.
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 
@@ -92,6 +93,52 @@ class LocalComm:
 
     def exchange_term_ok(self, term_ok, n_local):
         pass
+
+    def all_gather_frames(self, local, total_frames):
+        return local
+
+
+class DistComm:
+    """torch.distributed collectives for the frame-sharded refinement (NCCL on GPUs, gloo on CPU tensors)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    # The halo traffic is a few hundred bytes per rank, so it rides on all_gather (a plain collective that CUDA
+    # graphs capture reliably) instead of point-to-point sends: every rank contributes its two first and two last
+    # frames and picks its neighbours' out of the gathered block.
+    def exchange_halo(self, x_ext, n_local):
+        """x_ext (n_local + 4, J, 3): fill the two halo frames at each end with the neighbours' boundary frames."""
+        torch = self._torch()
+        mine = torch.cat([x_ext[2:4], x_ext[n_local:n_local + 2]], dim=0).contiguous()        # (4, J, 3)
+        out = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        if self.rank > 0:
+            x_ext[0:2] = out[self.rank - 1, 2:4]
+        if self.rank < self.world - 1:
+            x_ext[n_local + 2:n_local + 4] = out[self.rank + 1, 0:2]
+
+    def exchange_term_ok(self, term_ok, n_local):
+        """The smoothness terms ending at my first two frames are needed by the left neighbour's gradient."""
+        torch = self._torch()
+        mine = term_ok[2:4].contiguous()
+        out = torch.empty((self.world, 2), dtype=mine.dtype, device=mine.device)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        if self.rank < self.world - 1:
+            term_ok[n_local + 2:n_local + 4] = out[self.rank + 1]
+
+    @staticmethod
+    def _torch():
+        import torch
+        return torch
 
     def all_gather_frames(self, local, total_frames):
         return local
@@ -245,6 +292,8 @@ class RefineEngine:
         pb.x = self.x_ext.data_ptr()
         self.phases = phases or CudaPhases(self.tag)
         self.step = 0
+        self.use_graph = os.environ.get('MC3D_REFINE_GRAPH', '1') != '0'      # multi-rank CUDA-graph replay
+        self._graph = None
         if self.comm.world > 1:
             self.comm.exchange_halo(self.x_ext, n)
 
@@ -283,14 +332,58 @@ class RefineEngine:
         self.step += 1
 
     def run(self, n_iters):
-        """``n_iters`` whole-window iterations.  One rank: a single C call replaying a CUDA graph."""
+        """``n_iters`` whole-window iterations.
+
+        One rank: a single C call replaying a CUDA graph of the three kernels.  Several ranks (NCCL): two
+        consecutive steps -- kernels, the two all-reduces and the halo exchanges -- are captured once into a CUDA
+        graph and replayed, so the per-step cost is GPU-side latency only (no Python / NCCL launch overhead)."""
+        n_iters = int(n_iters)
         if self.comm.world == 1 and hasattr(self.phases, 'run') and self.device.type == 'cuda':
             with self.torch.cuda.device(self.device):
-                self.phases.run(self.problem, self.step, int(n_iters), self._stream())
-            self.step += int(n_iters)
-        else:
-            for _ in range(int(n_iters)):
-                self.one_step(True)
+                self.phases.run(self.problem, self.step, n_iters, self._stream())
+            self.step += n_iters
+            return
+        done = 0
+        if self.comm.world > 1 and self.device.type == 'cuda' and self.use_graph and n_iters >= 8:
+            torch = self.torch
+            with torch.cuda.device(self.device):
+                while done < 2 or (self.step & 1):              # eager warm-up (NCCL channels), even parity for the graph
+                    self.one_step(True)
+                    done += 1
+                if self._graph is None:
+                    first = self.step
+                    ok = 1.0
+                    graph = None
+                    try:
+                        torch.cuda.synchronize()
+                        graph = torch.cuda.CUDAGraph()
+                        # thread-local: the NCCL watchdog thread must not invalidate the capture
+                        with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                            self.one_step(True)
+                            self.one_step(True)
+                    except Exception:                            # capture unsupported here
+                        ok = 0.0
+                    self.step = first                           # capturing did not execute anything
+                    torch.cuda.synchronize()
+                    flag = torch.tensor([ok], dtype=torch.float64, device=self.device)
+                    self.comm.dist.all_reduce(flag, op=self.comm.dist.ReduceOp.MIN, group=self.comm.group)
+                    if flag.item() == 1.0:                      # every rank captured: replay; otherwise all stay eager
+                        self._graph = graph
+                    else:
+                        self.use_graph = False
+                if self._graph is not None:
+                    for _ in range((n_iters - done) // 2):
+                        self._graph.replay()
+                        self.step += 2
+                        done += 2
+        for _ in range(n_iters - done):
+            self.one_step(True)
+
+    def release_graph(self):
+        """Drop the captured multi-rank graph (it holds NCCL kernels: release it before the process group goes away)."""
+        if self._graph is not None:
+            self.torch.cuda.synchronize()
+            self._graph = None
 
     # ---- read-back ---------------------------------------------------------------------------------------------------
     def state(self):

@@ -41,19 +41,30 @@ def main():
     ok = ok and bool(np.isnan(sharded.trajectory.numpy()[1500, 7]).all())
     # iterations per second of the sharded path (NCCL collectives between phases)
     eng = sharded._engine
+    eng.use_graph = True
     torch.cuda.synchronize()
     dist.barrier()
     import time
+    eng.run(20)                                  # captures the 2-step graph
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    eng.run(200)
+    torch.cuda.synchronize()
+    dist.barrier()
+    rate = 200 / (time.perf_counter() - t0)
+    eng.use_graph = False
     t0 = time.perf_counter()
     eng.run(50)
     torch.cuda.synchronize()
     dist.barrier()
-    rate = 50 / (time.perf_counter() - t0)
+    rate_eager = 50 / (time.perf_counter() - t0)
+    eng.release_graph()
     flag = torch.tensor([1.0 if ok else 0.0], device=f'cuda:{local}')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f'MGPU_REFINE world={dist.get_world_size()} ok={bool(flag.item())} dtraj={dtraj:.2e} dbest={dbest:.2e} '
-              f'hist_rel={np.max(np.abs(h1 - h2) / np.abs(h1)):.2e} sharded_iters_per_s={rate:.0f}')
+              f'hist_rel={np.max(np.abs(h1 - h2) / np.abs(h1)):.2e} sharded_iters_per_s={rate:.0f} (graph={eng._graph is not None}) eager={rate_eager:.0f}')
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 
