@@ -134,7 +134,7 @@ int mc3d_decode_heatmaps_host_f32(const float *h_heatmaps, int64_t n_maps, int H
  * One optimiser step of Optimized_3d_Pose_Estimation.sgd_optimize (pose_refinement.py:1006-1050) is three
  * phases on the caller's stream:
  *   phase 0  costs    : likelihood (:863-889, camera-0 Gaussians), smoothness (:836-845), bone length
- *                       (:848-860) -> 7 global sums in ctrl, per-frame term_ok flags
+ *                       (:848-860) -> 7 global sums in ctrl
  *   phase 1  gradient : closed-form gradient (replaces total_cost.backward(), :1044) -> g, sum g^2 in ctrl
  *   phase 2  step     : clip_grad_norm_(1.0) (:1047), Adam (:1050), running-mean early stopping (:1069-1089),
  *                       best_trajectory snapshot (:1075), cost history (:1052-1054)
@@ -143,14 +143,15 @@ int mc3d_decode_heatmaps_host_f32(const float *h_heatmaps, int64_t n_maps, int H
  *   m, v, best, g  (n_frames, J, 3)  Adam moments, best snapshot, gradient scratch
  *   mu0 (n_frames, J, 2), S (n_frames, J, 3)   from mc3d_refine_prepare_*: camera-0 means and the symmetric
  *                                              inverse of (cov + 1e-6 I) as [s00, s01, s11] (:663-668)
- *   term_ok  (n_frames + 4) bytes  validity of the smoothness term ending at each frame (halo-extended)
+ *   term_ok  (n_frames + 4) bytes  validity of the smoothness term ending at each frame (halo-extended); written
+ *                                  once per run by mc3d_refine_flags_* after the x halo is in place
  *   ctrl     doubles, >= 64 + 4 * hist_capacity, zero-filled except ctrl[32+3] = ctrl[48+3] = +inf:
  *            [0..7]+16p   sums of the step with parity p: S_lik N_lik S_smooth N_smooth a.b b.b a.a gnorm^2
  *            [32..39]+16p state entering a step of parity p: adam_step run_sum run_cnt best no_improve
  *                         stopped iterations improved
  *            [64+4s ..]   cost history of step s: total likelihood smoothness body_length
- * A multi-GPU driver shards frames, exchanges the x / term_ok halos and all-reduces ctrl[0..6]+16p after
- * phase 0 and ctrl[7]+16p after phase 1 (that is the whole exchange; every rank then takes the same decisions). */
+ * A multi-GPU driver shards frames, exchanges the x halo after phase 2 and all-reduces ctrl[0..6]+16p after phase 0
+ * and ctrl[7]+16p after phase 1 (that is the whole exchange; every rank then takes the same decisions). */
 typedef struct {
     int32_t n_joints, n_cams, n_bones, ignore_distortions;
     int32_t patience, max_iter;
@@ -158,6 +159,7 @@ typedef struct {
     int64_t frame_offset;    /* global index of local frame 0 */
     int64_t win_begin, win_end;   /* global frame window the costs are evaluated on (a batch, :786-796) */
     int64_t hist_capacity;
+    int64_t total_frames;    /* frames of the whole (unsharded) trajectory */
     double lr, beta1, beta2, eps, lambda_smooth, lambda_body, tolerance;
     double aa;               /* ||a||^2 = window length x sum of squared target bone lengths (:857) */
     double cams[MC3D_MAX_VIEWS][26];      /* per camera: K[9] R[9] T[3] dist[5] (pose_refinement.py:94) */
@@ -179,6 +181,9 @@ int mc3d_refine_prepare_f32(const float *d_gaussians, int64_t n_frames, int n_ca
                             float *d_mu0, float *d_S, void *stream);
 int mc3d_refine_prepare_f64(const double *d_gaussians, int64_t n_frames, int n_cams, int n_joints, int cam, double eps,
                             double *d_mu0, double *d_S, void *stream);
+/* term_ok[s + 2] = frames s, s-1, s-2 all finite and inside the trajectory, for local s in [0, n_frames + 2). */
+int mc3d_refine_flags_f32(const mc3d_refine_problem *pb, void *stream);
+int mc3d_refine_flags_f64(const mc3d_refine_problem *pb, void *stream);
 /* sizeof(mc3d_refine_problem), so that a binding can check its struct layout. */
 int mc3d_refine_problem_size(void);
 int mc3d_refine_phase_f32(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream);

@@ -42,7 +42,7 @@ class RefineProblem(ctypes.Structure):
     _fields_ = [('n_joints', ctypes.c_int32), ('n_cams', ctypes.c_int32), ('n_bones', ctypes.c_int32),
                 ('ignore_distortions', ctypes.c_int32), ('patience', ctypes.c_int32), ('max_iter', ctypes.c_int32),
                 ('n_frames', ctypes.c_int64), ('frame_offset', ctypes.c_int64), ('win_begin', ctypes.c_int64),
-                ('win_end', ctypes.c_int64), ('hist_capacity', ctypes.c_int64),
+                ('win_end', ctypes.c_int64), ('hist_capacity', ctypes.c_int64), ('total_frames', ctypes.c_int64),
                 ('lr', ctypes.c_double), ('beta1', ctypes.c_double), ('beta2', ctypes.c_double),
                 ('eps', ctypes.c_double), ('lambda_smooth', ctypes.c_double), ('lambda_body', ctypes.c_double),
                 ('tolerance', ctypes.c_double), ('aa', ctypes.c_double),
@@ -83,6 +83,8 @@ SIGNATURES = {
     'mc3d_refine_prepare_f32': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp, _c_vp]),
     'mc3d_refine_prepare_f64': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp, _c_vp]),
     'mc3d_refine_problem_size': (_c_int, []),
+    'mc3d_refine_flags_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_vp]),
+    'mc3d_refine_flags_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_vp]),
     'mc3d_refine_phase_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_int, _c_i64, _c_int, _c_vp]),
     'mc3d_refine_phase_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_int, _c_i64, _c_int, _c_vp]),
     'mc3d_refine_run_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_i64, _c_i64, _c_vp]),

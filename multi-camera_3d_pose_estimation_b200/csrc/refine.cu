@@ -5,28 +5,26 @@
 // One optimiser step = three kernels over the frame-sharded state (no host round trip in between):
 //   A  costs   : per (frame, joint) reprojection Mahalanobis terms for every camera (camera-0 Gaussians, upstream
 //                quirk Q1), second-difference smoothness terms, bone lengths -> 7 global sums (finite-masked,
-//                nan_mean semantics) + per-frame finiteness flags
+//                nan_mean semantics)
 //   B  gradient: closed-form gradient of the three terms (needs the global sums of A: counts, mu = a.b/b.b)
 //                -> g, and the global sum of g^2
 //   C  step    : clip_grad_norm_(1.0), Adam (torch.optim.Adam arithmetic), running-mean early-stopping
 //                bookkeeping, conditional best-trajectory snapshot, cost history
 // Global sums live in a small double control block (ping-pong by step parity) so that a multi-GPU driver can
 // all-reduce them between kernels; every thread re-derives the scalars it needs from that block, so there are no
-// single-thread "finalise" launches.  Blocks are persistent (grid = k x SM count) and stage their frames plus a
-// two-frame halo in shared memory; sums are reduced warp -> block -> one double atomic per block.
+// single-thread "finalise" launches.  A and B are grid-stride loops with one (frame, joint) item per thread
+// iteration and no barriers: temporal neighbours and bone end points come from global memory through L1, the
+// cameras sit in shared memory (128-bit loads), sums are reduced thread -> warp -> block -> one double atomic per
+// block.  The arithmetic type is the state dtype (float state -> float maths, as upstream's float32 run).
 #include "mc3d_common.cuh"
 #include <math.h>
 
 namespace mc3d {
 
 constexpr int RF_THREADS = 256;
-#ifndef MC3D_RF_ITEMS
-#define MC3D_RF_ITEMS 1
-#endif
 #ifndef MC3D_RF_GRID
-#define MC3D_RF_GRID 4
+#define MC3D_RF_GRID 8
 #endif
-constexpr int RF_ITEMS = MC3D_RF_ITEMS;   // (frame, joint) items per thread and tile; 1 measured fastest (2, 4 starve the grid of tiles)
 // control block layout (doubles)
 constexpr int CT_ACC = 0;        // + 16 * parity : S_lik N_lik S_s N_s ab bb aa_ok gnorm2
 constexpr int CT_STATE = 32;     // + 16 * parity : step run_sum run_cnt best no_improve stopped iters_done improved
@@ -65,10 +63,25 @@ __device__ __forceinline__ float rcp_c(float v) { return 1.0f / v; }
 __device__ __forceinline__ double rcp_c(double v) { return 1.0 / v; }
 
 // Reprojection term of one camera: returns 0.5 d^T S d, and (when GRAD) adds J^T S d * scale to g[3].
-// cam: K[9] R[9] T[3] dist[5] already in the arithmetic type (shared memory, broadcast reads).
+constexpr int CAM_STRIDE = 28;      // K[9] R[9] T[3] dist[5] + 2 pad: a whole number of 16-byte shared-memory loads
+
+// One camera from shared memory into registers with 128-bit loads (28 scalars = 7 / 14 loads for float / double).
+template <typename C>
+__device__ __forceinline__ void load_camera(const C *cam_smem, C (&cam)[CAM_STRIDE]) {
+    constexpr int PER = 16 / sizeof(C);
+    struct alignas(16) V { C v[PER]; };
+#pragma unroll
+    for (int i = 0; i < CAM_STRIDE / PER; ++i) {
+        const V q = reinterpret_cast<const V *>(cam_smem)[i];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) cam[i * PER + k] = q.v[k];
+    }
+}
+
+// cam: K[9] R[9] T[3] dist[5] in the arithmetic type, in registers.
 template <bool GRAD, typename C>
-__device__ __forceinline__ C reproject_term(const C *cam, bool ignore_dist, C X, C Y, C Z, C mx, C my, C s00, C s01,
-                                            C s11, C scale, C *g) {
+__device__ __forceinline__ C reproject_term(const C (&cam)[CAM_STRIDE], bool ignore_dist, C X, C Y, C Z, C mx, C my, C s00,
+                                            C s01, C s11, C scale, C *g) {
     const C *K = cam, *R = cam + 9, *T = cam + 18, *D = cam + 21;
     const C one = (C)1, two = (C)2;
     const C xc = fma(R[0], X, fma(R[1], Y, fma(R[2], Z, T[0])));
@@ -148,101 +161,109 @@ __device__ __forceinline__ void block_reduce_add(double (&vals)[N], double *smem
     __syncthreads();
 }
 
-// Shared-memory staging of frames [t_lo - 2, t_lo + fpb + 2) of the (halo-extended) trajectory.
+// ---- smoothness-term validity flags --------------------------------------------------------------------------------
+// term_ok[s + 2] = 1 when frames s, s-1, s-2 are entirely finite, for local s in [0, n + 2) (the two extra entries are
+// the terms owned by the right neighbour, which the gradient of the last two local frames needs; their frames are in
+// the halo).  upstream drops a whole frame's term when it is non-finite (nan_mean, pose_refinement.py:845).  A joint
+// that starts non-finite stays frozen (its gradient is masked) and a finite one only becomes non-finite if the
+// optimisation has already diverged, so the flags are computed once per run, not once per step.
 template <typename T>
-__device__ __forceinline__ void stage_frames(const T *x_ext, T *xs, long long t_lo, int fpb, int J, long long n_local) {
-    // x_ext frame index = local frame + 2; local frames range [-2, n_local + 2)
-    const int count = (fpb + 4) * J * 3;
-    const long long base = t_lo * J * 3;            // (t_lo - 2 + 2) * J * 3
-    const long long limit = (n_local + 4) * (long long)J * 3;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const long long src = base + i;
-        xs[i] = (src < limit) ? x_ext[src] : (T)0;
+__global__ void refine_flags_kernel(const __grid_constant__ mc3d_refine_problem pb) {
+    const long long n = pb.n_frames;
+    const int per = pb.n_joints * 3;
+    const T *x_ext = (const T *)pb.x;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n + 2; s += (long long)gridDim.x * blockDim.x) {
+        bool ok = true;
+        const long long g0 = s + pb.frame_offset;                  // global index of the term's last frame
+        if (g0 - 2 < 0 || g0 >= pb.total_frames) ok = false;       // frames outside the trajectory
+        for (int f = 0; f < 3 && ok; ++f) {
+            const T *fr = x_ext + (s + 2 - f) * per;               // ext index = local + 2
+            for (int i = 0; i < per; ++i) ok = ok && finite_c(fr[i]);
+        }
+        pb.term_ok[s + 2] = ok ? 1 : 0;
     }
 }
 
 // ---- kernel A: costs ------------------------------------------------------------------------------------------
-// Dynamic shared memory: [8 warps x 7 doubles reduction scratch | staged frames (F + 4) x J x 3 of T | d2 F x J of T],
-// F = RF_ITEMS * (256 / J) frames per tile; thread (tl, j) owns frames tl, tl + fpb, ... of the tile.
+// One thread per (frame, joint) item, grid-stride, no shared-memory staging and no block barriers in the loop:
+// temporal neighbours and bone end points are read straight from global memory (each x element is read by the five
+// items around it and by its bones, all within a few hundred bytes, so they hit L1).  Per-thread partial sums are
+// float (a thread sees a few dozen items) and are widened to double for the warp / block / grid reduction.
+struct ItemCursor {                 // (frame, joint) of a grid-stride loop without a division per item
+    long long t, e;
+    int j;
+    long long de, dt;
+    int dj;
+    __device__ __forceinline__ ItemCursor(int J) {
+        e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        de = (long long)gridDim.x * blockDim.x;
+        t = e / J; j = (int)(e - t * J);
+        dt = de / J; dj = (int)(de - dt * J);
+    }
+    __device__ __forceinline__ void next(int J) {
+        e += de; t += dt; j += dj;
+        if (j >= J) { j -= J; ++t; }
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(RF_THREADS)
 refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
-    extern __shared__ __align__(16) double smem_d[];
+    __shared__ double red[8 * 7];
     __shared__ RefineTables tb;
-    __shared__ T camf[MC3D_MAX_VIEWS * 26];
+    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
     double *ctrl = pb.ctrl;
     if (ctrl[CT_STATE + 16 * parity + 5] != 0.0) return;          // stopped
     load_tables(tb, pb);
-    for (int i = threadIdx.x; i < pb.n_cams * 26; i += blockDim.x) camf[i] = (T)pb.cams[i / 26][i % 26];
-    const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones;
-    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
-    const int F = fpb * RF_ITEMS;                                  // frames per tile
-    double *red = smem_d;                                          // 8 warps * 7
-    T *xs = reinterpret_cast<T *>(smem_d + 8 * 7);                 // (F + 4) * J * 3
-    T *d2 = xs + (F + 4) * J * 3;                                  // F * J   per-joint smoothness contributions
-    const T *x_ext = (const T *)pb.x;
+    for (int i = threadIdx.x; i < pb.n_cams * CAM_STRIDE; i += blockDim.x)
+        camf[i] = (i % CAM_STRIDE) < 26 ? (T)pb.cams[i / CAM_STRIDE][i % CAM_STRIDE] : (T)0;
+    __syncthreads();
+    const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones, JS = J * 3;
+    const T *x = (const T *)pb.x + 2LL * JS;                       // local frame 0 (halo frames sit before / after)
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
-    const long long nloc = pb.n_frames;
-    const long long n_tiles = (nloc + F - 1) / F;
+    const long long n_items = pb.n_frames * J;
     const bool ign = pb.ignore_distortions != 0;
     const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
-    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    const int tl = threadIdx.x / J, j = threadIdx.x - tl * J;
-    const bool lane_ok = tl < fpb;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long t_lo = tile * F;
-        __syncthreads();
-        stage_frames(x_ext, xs, t_lo, F, J, nloc);
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < RF_ITEMS; ++it) {
-            const int fl = tl + it * fpb;                          // frame within the tile
-            const long long t = t_lo + fl;                         // local frame
-            const long long tg = t + pb.frame_offset;              // global frame
-            const bool in_win = lane_ok && t < nloc && tg >= pb.win_begin && tg < pb.win_end;
-            if (lane_ok) d2[fl * J + j] = (T)0;
-            if (!in_win) continue;
-            const T *xc = xs + ((fl + 2) * J + j) * 3;
-            const T X = xc[0], Y = xc[1], Z = xc[2];
-            const long long e = t * J + j;
-            const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
-            const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
-            for (int c = 0; c < C; ++c) {
-                const T q = reproject_term<false, T>(camf + c * 26, ign, X, Y, Z, mx, my, s00, s01, s11, (T)0, nullptr);
-                if (finite_c(q)) { acc[0] += (double)q; acc[1] += 1.0; }
-            }
-            if (do_smooth && tg - 2 >= pb.win_begin) {
-                const T *x1 = xc - J * 3, *x2 = xc - 2 * J * 3;
-                const T a0 = X - (T)2 * x1[0] + x2[0], a1 = Y - (T)2 * x1[1] + x2[1], a2 = Z - (T)2 * x1[2] + x2[2];
-                d2[fl * J + j] = a0 * a0 + a1 * a1 + a2 * a2;
-            }
-            if (do_body) {
-                const T *xf = xs + (fl + 2) * J * 3;
-                for (int k = j; k < NB; k += J) {
-                    const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
-                    const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
-                    const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-                    if (finite_c(b)) {
-                        const double a = tb.bone_len[k], bd = (double)b;
-                        acc[4] += a * bd; acc[5] += bd * bd; acc[6] += a * a;
-                    }
+    const long long lo = pb.win_begin - pb.frame_offset, hi = pb.win_end - pb.frame_offset;   // window in local frames
+    T accf[7] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
+    for (ItemCursor it(J); it.e < n_items; it.next(J)) {
+        const long long t = it.t, e = it.e;
+        const int j = it.j;
+        if (t < lo || t >= hi) continue;
+        const T *xc = x + e * 3;
+        const T X = xc[0], Y = xc[1], Z = xc[2];
+        const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
+        const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
+        for (int c = 0; c < C; ++c) {
+            T cam[CAM_STRIDE];
+            load_camera(camf + c * CAM_STRIDE, cam);
+            const T q = reproject_term<false, T>(cam, ign, X, Y, Z, mx, my, s00, s01, s11, (T)0, nullptr);
+            const bool ok = finite_c(q);
+            accf[0] += ok ? q : (T)0;
+            accf[1] += ok ? (T)1 : (T)0;
+        }
+        if (do_smooth && t - 2 >= lo && pb.term_ok[t + 2]) {
+            const T *x1 = xc - JS, *x2 = xc - 2 * JS;
+            const T a0 = X - (T)2 * x1[0] + x2[0], a1 = Y - (T)2 * x1[1] + x2[1], a2 = Z - (T)2 * x1[2] + x2[2];
+            accf[2] += a0 * a0 + a1 * a1 + a2 * a2;
+            accf[3] += j == 0 ? (T)1 : (T)0;
+        }
+        if (do_body) {
+            const T *xf = x + t * JS;
+            for (int k = j; k < NB; k += J) {
+                const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
+                const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
+                const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                if (finite_c(b)) {
+                    const T a = (T)tb.bone_len[k];
+                    accf[4] += a * b; accf[5] += b * b; accf[6] += a * a;
                 }
             }
         }
-        __syncthreads();
-        for (int f = threadIdx.x; f < F; f += blockDim.x) {        // one thread per frame: frame-level smoothness term
-            const long long tt = t_lo + f, ttg = tt + pb.frame_offset;
-            if (tt < nloc && ttg >= pb.win_begin + 2 && ttg < pb.win_end && do_smooth) {
-                double sum = 0.0;
-                for (int jj = 0; jj < J; ++jj) sum += (double)d2[f * J + jj];
-                const bool ok = fabs(sum) <= 1.0e300;
-                pb.term_ok[tt + 2] = ok ? 1 : 0;
-                if (ok) { acc[2] += sum; acc[3] += 1.0; }
-            } else if (tt < nloc) {
-                pb.term_ok[tt + 2] = 0;
-            }
-        }
     }
+    double acc[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) acc[i] = (double)accf[i];
     block_reduce_add<7>(acc, red, ctrl + CT_ACC + 16 * parity);
 }
 
@@ -250,90 +271,81 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
 template <typename T>
 __global__ void __launch_bounds__(RF_THREADS)
 refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
-    extern __shared__ __align__(16) double smem_d[];
+    __shared__ double red[8];
     __shared__ RefineTables tb;
-    __shared__ T camf[MC3D_MAX_VIEWS * 26];
+    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
     double *ctrl = pb.ctrl;
     const RefineDerived dv = derive(pb, ctrl, parity);
     if (dv.stopped) return;
     load_tables(tb, pb);
-    for (int i = threadIdx.x; i < pb.n_cams * 26; i += blockDim.x) camf[i] = (T)pb.cams[i / 26][i % 26];
-    const int J = pb.n_joints, C = pb.n_cams;
-    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
-    const int F = fpb * RF_ITEMS;
-    double *red = smem_d;                                          // 8 warps
-    T *xs = reinterpret_cast<T *>(smem_d + 8);
-    const T *x_ext = (const T *)pb.x;
+    for (int i = threadIdx.x; i < pb.n_cams * CAM_STRIDE; i += blockDim.x)
+        camf[i] = (i % CAM_STRIDE) < 26 ? (T)pb.cams[i / CAM_STRIDE][i % CAM_STRIDE] : (T)0;
+    __syncthreads();
+    const int J = pb.n_joints, C = pb.n_cams, JS = J * 3;
+    const T *x = (const T *)pb.x + 2LL * JS;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
     T *gout = (T *)pb.g;
-    const long long nloc = pb.n_frames;
-    const long long n_tiles = (nloc + F - 1) / F;
+    const long long n_items = pb.n_frames * J;
     const bool ign = pb.ignore_distortions != 0;
     const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
+    const long long lo = pb.win_begin - pb.frame_offset, hi = pb.win_end - pb.frame_offset;
     const T inv_nlik = (T)dv.inv_nlik, smooth_scale = (T)dv.smooth_scale, mu = (T)dv.mu, body_c = (T)dv.body_c;
-    double gn[1] = {0.0};
-    const int tl = threadIdx.x / J, j = threadIdx.x - tl * J;
-    const bool lane_ok = tl < fpb;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long t_lo = tile * F;
-        __syncthreads();
-        stage_frames(x_ext, xs, t_lo, F, J, nloc);
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < RF_ITEMS; ++it) {
-            const int fl = tl + it * fpb;
-            const long long t = t_lo + fl, tg = t + pb.frame_offset;
-            if (!(lane_ok && t < nloc)) continue;
-            const long long e = t * J + j;
-            T g[3] = {(T)0, (T)0, (T)0};
-            const bool in_win = tg >= pb.win_begin && tg < pb.win_end;
-            const T *xc = xs + ((fl + 2) * J + j) * 3;
-            const T X = xc[0], Y = xc[1], Z = xc[2];
-            const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
-            if (in_win && self_ok) {
-                const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
-                const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
-                for (int c = 0; c < C; ++c)
-                    reproject_term<true, T>(camf + c * 26, ign, X, Y, Z, mx, my, s00, s01, s11, inv_nlik, g);
-                if (do_smooth) {
-                    // d/dx_t of sum_s ||D_s||^2 = 2 (D_t - 2 D_{t+1} + D_{t+2}) over the valid terms s
-                    const int JS = J * 3;
-                    const T two = (T)2;
-                    T s0 = (T)0, s1 = (T)0, s2 = (T)0;
-                    if (pb.term_ok[t + 2]) {
-                        s0 += xc[0] - two * xc[-JS] + xc[-2 * JS]; s1 += xc[1] - two * xc[1 - JS] + xc[1 - 2 * JS];
-                        s2 += xc[2] - two * xc[2 - JS] + xc[2 - 2 * JS];
-                    }
-                    if (pb.term_ok[t + 3]) {
-                        s0 -= two * (xc[JS] - two * xc[0] + xc[-JS]); s1 -= two * (xc[1 + JS] - two * xc[1] + xc[1 - JS]);
-                        s2 -= two * (xc[2 + JS] - two * xc[2] + xc[2 - JS]);
-                    }
-                    if (pb.term_ok[t + 4]) {
-                        s0 += xc[2 * JS] - two * xc[JS] + xc[0]; s1 += xc[1 + 2 * JS] - two * xc[1 + JS] + xc[1];
-                        s2 += xc[2 + 2 * JS] - two * xc[2 + JS] + xc[2];
-                    }
-                    g[0] = fma(smooth_scale, s0, g[0]); g[1] = fma(smooth_scale, s1, g[1]); g[2] = fma(smooth_scale, s2, g[2]);
+    T gnf = (T)0;
+    for (ItemCursor it(J); it.e < n_items; it.next(J)) {
+        const long long t = it.t, e = it.e;
+        const int j = it.j;
+        T g[3] = {(T)0, (T)0, (T)0};
+        const T *xc = x + e * 3;
+        const T X = xc[0], Y = xc[1], Z = xc[2];
+        const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
+        if (t >= lo && t < hi && self_ok) {
+            const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
+            const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
+            for (int c = 0; c < C; ++c) {
+                T cam[CAM_STRIDE];
+                load_camera(camf + c * CAM_STRIDE, cam);
+                reproject_term<true, T>(cam, ign, X, Y, Z, mx, my, s00, s01, s11, inv_nlik, g);
+            }
+            if (do_smooth) {
+                // d/dx_t of sum_s ||D_s||^2 = 2 (D_t - 2 D_{t+1} + D_{t+2}) over the valid terms s (s - 2 >= lo, s < hi)
+                const T two = (T)2;
+                const bool k0 = t - 2 >= lo && pb.term_ok[t + 2];
+                const bool k1 = t - 1 >= lo && t + 1 < hi && pb.term_ok[t + 3];
+                const bool k2 = t + 2 < hi && pb.term_ok[t + 4];
+                T s0 = (T)0, s1 = (T)0, s2 = (T)0;
+                if (k0) {
+                    s0 += xc[0] - two * xc[-JS] + xc[-2 * JS]; s1 += xc[1] - two * xc[1 - JS] + xc[1 - 2 * JS];
+                    s2 += xc[2] - two * xc[2 - JS] + xc[2 - 2 * JS];
                 }
-                if (do_body) {
-                    const T *xf = xs + (fl + 2) * J * 3;
-                    for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {
-                        const int k = tb.adj_bone[q];
-                        const T sign = (T)tb.adj_sign[q];
-                        const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
-                        const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
-                        const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-                        if (finite_c(b) && b > (T)0) {
-                            const T coef = sign * body_c * ((T)tb.bone_len[k] - mu * b) / b;
-                            g[0] = fma(coef, v0, g[0]); g[1] = fma(coef, v1, g[1]); g[2] = fma(coef, v2, g[2]);
-                        }
+                if (k1) {
+                    s0 -= two * (xc[JS] - two * xc[0] + xc[-JS]); s1 -= two * (xc[1 + JS] - two * xc[1] + xc[1 - JS]);
+                    s2 -= two * (xc[2 + JS] - two * xc[2] + xc[2 - JS]);
+                }
+                if (k2) {
+                    s0 += xc[2 * JS] - two * xc[JS] + xc[0]; s1 += xc[1 + 2 * JS] - two * xc[1 + JS] + xc[1];
+                    s2 += xc[2 + 2 * JS] - two * xc[2 + JS] + xc[2];
+                }
+                g[0] = fma(smooth_scale, s0, g[0]); g[1] = fma(smooth_scale, s1, g[1]); g[2] = fma(smooth_scale, s2, g[2]);
+            }
+            if (do_body) {
+                const T *xf = x + t * JS;
+                for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {
+                    const int k = tb.adj_bone[q];
+                    const T sign = (T)tb.adj_sign[q];
+                    const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
+                    const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
+                    const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                    if (finite_c(b) && b > (T)0) {
+                        const T coef = sign * body_c * ((T)tb.bone_len[k] - mu * b) / b;
+                        g[0] = fma(coef, v0, g[0]); g[1] = fma(coef, v1, g[1]); g[2] = fma(coef, v2, g[2]);
                     }
                 }
             }
-            gout[e * 3 + 0] = g[0]; gout[e * 3 + 1] = g[1]; gout[e * 3 + 2] = g[2];
-            gn[0] += (double)g[0] * (double)g[0] + (double)g[1] * (double)g[1] + (double)g[2] * (double)g[2];
         }
+        gout[e * 3 + 0] = g[0]; gout[e * 3 + 1] = g[1]; gout[e * 3 + 2] = g[2];
+        gnf += g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
     }
-    __syncthreads();
+    double gn[1] = {(double)gnf};
     block_reduce_add<1>(gn, red, ctrl + CT_ACC + 16 * parity + 7);
 }
 
@@ -509,18 +521,13 @@ int refine_phase(const mc3d_refine_problem *pb, int phase, long long step_index,
     if (pb->n_frames == 0) return MC3D_OK;
     const int parity = (int)(step_index & 1);
     const int J = pb->n_joints;
-    const int fpb = RF_THREADS / J > 0 ? RF_THREADS / J : 1;
-    const int F = fpb * RF_ITEMS;
-    const long long n_tiles = (pb->n_frames + F - 1) / F;
-    long long grid = (long long)sm_count() * MC3D_RF_GRID;
-    if (grid > n_tiles) grid = n_tiles;
-    const size_t xs_bytes = (size_t)(F + 4) * J * 3 * sizeof(T);
+    const long long n_items = (long long)pb->n_frames * J;
+    long long grid = (n_items + RF_THREADS - 1) / RF_THREADS;
+    if (grid > (long long)sm_count() * MC3D_RF_GRID) grid = (long long)sm_count() * MC3D_RF_GRID;
     if (phase == 0) {
-        const size_t smem = xs_bytes + (size_t)F * J * sizeof(T) + 8 * 7 * sizeof(double);
-        refine_costs_kernel<T><<<(unsigned)grid, RF_THREADS, smem, stream>>>(*pb, parity);
+        refine_costs_kernel<T><<<(unsigned)grid, RF_THREADS, 0, stream>>>(*pb, parity);
     } else if (phase == 1) {
-        const size_t smem = xs_bytes + 8 * sizeof(double);
-        refine_grad_kernel<T><<<(unsigned)grid, RF_THREADS, smem, stream>>>(*pb, parity);
+        refine_grad_kernel<T><<<(unsigned)grid, RF_THREADS, 0, stream>>>(*pb, parity);
     } else if (phase == 2) {
         const long long n = (long long)pb->n_frames * J * 3;
         long long g2 = (n + RF_THREADS * 4 - 1) / (RF_THREADS * 4);
@@ -580,6 +587,18 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
 }
 
 template <typename T>
+int refine_flags(const mc3d_refine_problem *pb, cudaStream_t stream) {
+    int st = validate(pb);
+    if (st != MC3D_OK) return st;
+    long long grid = (pb->n_frames + 2 + 127) / 128;
+    if (grid > (long long)sm_count() * 8) grid = (long long)sm_count() * 8;
+    refine_flags_kernel<T><<<(unsigned)grid, 128, 0, stream>>>(*pb);
+    count_launch();
+    MC3D_CUDA_TRY(cudaGetLastError());
+    return MC3D_OK;
+}
+
+template <typename T>
 int refine_prepare(const T *d_gauss, long long n_frames, int n_cams, int n_joints, int cam, double eps, T *d_mu0, T *d_S,
                    cudaStream_t stream) {
     if (n_frames < 0 || n_cams < 1 || n_joints < 1 || cam < 0 || cam >= n_cams) { set_error("bad gaussians shape"); return MC3D_ERR_INVALID_ARGUMENT; }
@@ -612,6 +631,8 @@ int mc3d_refine_prepare_f64(const double *d_gauss, int64_t n_frames, int n_cams,
                             double *d_mu0, double *d_S, void *stream) {
     return mc3d::refine_prepare<double>(d_gauss, n_frames, n_cams, n_joints, cam, eps, d_mu0, d_S, (cudaStream_t)stream);
 }
+int mc3d_refine_flags_f32(const mc3d_refine_problem *pb, void *stream) { return mc3d::refine_flags<float>(pb, (cudaStream_t)stream); }
+int mc3d_refine_flags_f64(const mc3d_refine_problem *pb, void *stream) { return mc3d::refine_flags<double>(pb, (cudaStream_t)stream); }
 int mc3d_refine_phase_f32(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream) {
     return mc3d::refine_phase<float>(pb, phase, step_index, end_of_iteration, (cudaStream_t)stream);
 }

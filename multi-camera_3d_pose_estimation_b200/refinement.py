@@ -5,8 +5,8 @@ best snapshot, gradient scratch, camera-0 means / inverse covariances, the doubl
 the three phases of an optimiser step.  With ``world_size > 1`` (``torch.distributed`` initialised, one
 process per GPU) frames are sharded contiguously and the ONLY traffic per step is
 
-    after phase 2 (previous step):  x halo   -- 2 frames to each neighbour             (point-to-point)
-    after phase 0:                  all-reduce of 7 doubles + 2 term_ok halo bytes to the left neighbour
+    after phase 2 (previous step):  x halo   -- 2 frames to each neighbour (all_gather of the boundary frames)
+    after phase 0:                  all-reduce of 7 doubles (cost sums and counts)
     after phase 1:                  all-reduce of 1 double (sum g^2)
 
 so every rank takes identical clip / Adam / early-stopping decisions with no further communication
@@ -91,9 +91,6 @@ class LocalComm:
     def exchange_halo(self, x_ext, n_local):
         pass
 
-    def exchange_term_ok(self, term_ok, n_local):
-        pass
-
     def all_gather_frames(self, local, total_frames):
         return local
 
@@ -125,15 +122,6 @@ class DistComm:
             x_ext[0:2] = out[self.rank - 1, 2:4]
         if self.rank < self.world - 1:
             x_ext[n_local + 2:n_local + 4] = out[self.rank + 1, 0:2]
-
-    def exchange_term_ok(self, term_ok, n_local):
-        """The smoothness terms ending at my first two frames are needed by the left neighbour's gradient."""
-        torch = self._torch()
-        mine = term_ok[2:4].contiguous()
-        out = torch.empty((self.world, 2), dtype=mine.dtype, device=mine.device)
-        self.dist.all_gather_into_tensor(out, mine, group=self.group)
-        if self.rank < self.world - 1:
-            term_ok[n_local + 2:n_local + 4] = out[self.rank + 1]
 
     @staticmethod
     def _torch():
@@ -203,9 +191,13 @@ class CudaPhases:
         lib = _lib.lib()
         self.phase_fn = getattr(lib, f'mc3d_refine_phase_{dtype_tag}')
         self.run_fn = getattr(lib, f'mc3d_refine_run_{dtype_tag}')
+        self.flags_fn = getattr(lib, f'mc3d_refine_flags_{dtype_tag}')
 
     def phase(self, problem, phase, step, end_of_iteration, stream):
         _lib.check(self.phase_fn(ctypes.byref(problem), phase, step, int(end_of_iteration), stream))
+
+    def flags(self, problem, stream):
+        _lib.check(self.flags_fn(ctypes.byref(problem), stream))
 
     def run(self, problem, first_step, n_iters, stream):
         _lib.check(self.run_fn(ctypes.byref(problem), first_step, n_iters, stream))
@@ -274,6 +266,7 @@ class RefineEngine:
         pb.n_frames, pb.frame_offset = n, self.begin
         pb.win_begin, pb.win_end = int(window[0]), int(window[1])
         pb.hist_capacity = self.hist_capacity
+        pb.total_frames = self.total_frames
         pb.lr, pb.beta1, pb.beta2, pb.eps = float(lr), float(betas[0]), float(betas[1]), float(adam_eps)
         pb.lambda_smooth, pb.lambda_body = float(lambda_smooth), float(lambda_body_length)
         pb.tolerance = float(tolerance)
@@ -296,6 +289,9 @@ class RefineEngine:
         self._graph = None
         if self.comm.world > 1:
             self.comm.exchange_halo(self.x_ext, n)
+        if getattr(self.phases, 'engine', 0) is None:         # test phases operate on this engine's tensors
+            self.phases.engine = self
+        self.phases.flags(self.problem, self._stream())       # smoothness-term validity, once per run
 
     def _prepare_host(self, g_loc, n_g, cam):
         # CPU tensors exist only for the gloo tests of the sharding logic (tests inject their own phases).
@@ -322,7 +318,6 @@ class RefineEngine:
         self.phases.phase(self.problem, 0, self.step, end_of_iteration, st)
         if self.comm.world > 1:
             self.comm.all_reduce_sum(acc[0:7])
-            self.comm.exchange_term_ok(self.term_ok, self.n_local)
         self.phases.phase(self.problem, 1, self.step, end_of_iteration, st)
         if self.comm.world > 1:
             self.comm.all_reduce_sum(acc[7:8])

@@ -20,6 +20,21 @@ class NumpyPhases:
         return (e.x_ext.numpy(), e.m.numpy(), e.v.numpy(), e.best.numpy(), e.g.numpy(), e.mu0.numpy(), e.S.numpy(),
                 e.term_ok.numpy(), e.ctrl.numpy())
 
+    def flags(self, pb, stream):
+        """mc3d_refine_flags_*: static validity of the smoothness term ending at local frame s, s in [0, n + 2)."""
+        x_ext, term_ok = self.engine_views()
+        n, off, total = int(pb.n_frames), int(pb.frame_offset), int(pb.total_frames)
+        term_ok[:] = 0
+        for s_ in range(n + 2):
+            g0 = s_ + off
+            if g0 - 2 < 0 or g0 >= total:
+                continue
+            term_ok[s_ + 2] = int(np.isfinite(x_ext[s_:s_ + 3]).all())      # ext frames s, s+1, s+2 = local s-2 .. s
+
+    def engine_views(self):
+        e = self.engine
+        return e.x_ext.numpy(), e.term_ok.numpy()
+
     def _derive(self, pb, ctrl, p):
         acc = ctrl[CT_ACC + 16 * p:CT_ACC + 16 * p + 8]
         with np.errstate(divide='ignore', invalid='ignore'):
@@ -56,16 +71,12 @@ class NumpyPhases:
                 ok = np.isfinite(q)
                 acc[0] += q[ok].sum()
                 acc[1] += ok.sum()
-            term_ok[2:n + 2] = 0
             if pb.lambda_smooth > 0:
                 for t in idx:
-                    if glob[t] - 2 >= wb:
+                    if glob[t] - 2 >= wb and term_ok[t + 2]:
                         D = xe[t + 2] - 2 * xe[t + 1] + xe[t]
-                        val = (D * D).sum()
-                        if np.isfinite(val):
-                            acc[2] += val
-                            acc[3] += 1
-                            term_ok[t + 2] = 1
+                        acc[2] += (D * D).sum()
+                        acc[3] += 1
             if pb.lambda_body > 0:
                 for s, e, a in self.bones:
                     b = np.linalg.norm(x[idx, e] - x[idx, s], axis=1)
@@ -90,7 +101,7 @@ class NumpyPhases:
                 sc = 2 * pb.lambda_smooth / dv['n_s']
                 for t in idx:
                     for k, coef in ((0, 1.0), (1, -2.0), (2, 1.0)):
-                        if term_ok[t + 2 + k]:
+                        if term_ok[t + 2 + k] and glob[t] + k - 2 >= wb and glob[t] + k < we:
                             tt = t + k                       # term ending at local frame tt
                             D = xe[tt + 2] - 2 * xe[tt + 1] + xe[tt]
                             gg[t] += sc * coef * D
