@@ -71,6 +71,41 @@ def triangulate_points(kpts_2d, cmtx1, dist1, R1, T1, cmtx2, dist2, R2, T2):
     return X.reshape(lead + [3])
 
 
+# ---- reprojection (utils.py:438-458, 558-567) ---------------------------------------------------------------------
+def project_points(points_3d, K, R, T, dist_coeffs=None):
+    """Project (N,3) or (Time,N,3) points to pixels with intrinsics K, extrinsics R (3,3), T and optional Brown
+    distortion (k1,k2,p1,p2,k3) -- the cv.projectPoints wrapper of reference utils.py:438-458.  float64 in and out;
+    runs on the GPU (csrc/refine.cu projection kernel)."""
+    import torch
+    from . import _lib
+    pts = np.asarray(points_3d, dtype=np.float64)
+    shape = pts.shape
+    flat = np.ascontiguousarray(pts.reshape(-1, 3))
+    d = np.zeros(5)
+    if dist_coeffs is not None:
+        dd = np.asarray(dist_coeffs, dtype=np.float64).reshape(-1)
+        d[:min(5, dd.size)] = dd[:5]
+    row = np.ascontiguousarray(np.concatenate([np.asarray(K, dtype=np.float64).reshape(9), np.asarray(R, dtype=np.float64).reshape(9),
+                                               np.asarray(T, dtype=np.float64).reshape(3), d]))
+    if not torch.cuda.is_available():
+        raise _lib.Mc3dError('project_points needs a CUDA device (no CPU fallback)')
+    dev = torch.device('cuda', torch.cuda.current_device())
+    p = torch.as_tensor(flat).to(dev)
+    out = torch.empty((flat.shape[0], 2), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().mc3d_project_points_f64(p.data_ptr(), flat.shape[0], row.ctypes.data, 0, out.data_ptr(),
+                                                      torch.cuda.current_stream().cuda_stream))
+    res = out.cpu().numpy()
+    return res.reshape(shape[:2] + (2,)) if len(shape) == 3 else res.reshape(-1, 2)
+
+
+def compute_2d_coordinates(P, point_3d):
+    """Undistorted projection of one 3D point with a 3x4 projection matrix (utils.py:558-567); host arithmetic on
+    four numbers, kept for the plotting callers."""
+    uv = np.asarray(P, dtype=np.float64) @ np.array([point_3d[0], point_3d[1], point_3d[2], 1.0])
+    return np.array([uv[0], uv[1]]) / uv[2]
+
+
 # ---- camera parameter files (formats of utils.py:750-793) -----------------------------------------
 def read_camera_parameters(camera_name, params_dir=''):
     """`<name>.dat`: a header line, 3 rows of the intrinsic matrix, a header line, one row of

@@ -67,7 +67,11 @@ def golden_dlt(ref_utils, syn, out):
                                        c1[0], c1[3], c1[1], c1[2])
     und0 = cv.undistortPoints(pair[:, 0, :][:, None, :], c0[0], c0[3], None, c0[0])[:, 0, :]
     und1 = cv.undistortPoints(pair[:, 1, :][:, None, :], c1[0], c1[3], None, c1[0])[:, 0, :]
-    np.savez(os.path.join(out, 'dlt_stereo.npz'), P=P, pts=pts, dlt=dlt, pair=pair, tri=tri,
+    proj_pts = X[:3]
+    proj = {f'proj_cam{i}': ref_utils.project_points(proj_pts, cams[i][0], cams[i][1], cams[i][2], cams[i][3]) for i in cams}
+    proj['proj_flat_nodist'] = ref_utils.project_points(proj_pts.reshape(-1, 3), c1[0], c1[1], c1[2])
+    proj['uv_c2d'] = ref_utils.compute_2d_coordinates(P[1], X[0, 0])
+    np.savez(os.path.join(out, 'dlt_stereo.npz'), P=P, pts=pts, dlt=dlt, pair=pair, tri=tri, proj_pts=proj_pts, **proj,
              und0=und0, und1=und1, versions=versions(),
              **{f'cam{i}_{n}': np.asarray(cams[i][k]) for i in cams for k, n in enumerate(['K', 'R', 'T', 'dist'])})
 

@@ -336,3 +336,17 @@ def test_full_size_sample_check(tri, syn):
     assert err.max() < FP32_ATOL_MM
     # determinism: a second launch gives the same bits
     assert bool((tri(kp, P) == out).all())
+
+
+def test_project_points_matches_reference_golden():
+    """utils.project_points (the cv.projectPoints wrapper, utils.py:438-458) and compute_2d_coordinates (:558-567)."""
+    import mc3d_b200.utils as u
+    g = load_golden('dlt_stereo.npz')
+    c = cams_from_golden(g, 2)
+    for i in range(2):
+        got = u.project_points(g['proj_pts'], c[i][0], c[i][1], c[i][2], c[i][3])
+        assert got.shape == g[f'proj_cam{i}'].shape == (3, 17, 2)
+        assert np.abs(got - g[f'proj_cam{i}']).max() < 1e-9
+    flat = u.project_points(g['proj_pts'].reshape(-1, 3), c[1][0], c[1][1], c[1][2])
+    assert flat.shape == (51, 2) and np.abs(flat - g['proj_flat_nodist']).max() < 1e-9
+    assert np.abs(u.compute_2d_coordinates(g['P'][1], g['proj_pts'][0, 0]) - g['uv_c2d']).max() < 1e-9
