@@ -15,6 +15,8 @@
 // registers.  Results leave through a shared-memory tile and a TMA bulk store.
 #include "mc3d_common.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 
 namespace mc3d {
@@ -36,6 +38,7 @@ struct TriParams {
     float2 cxy[MC3D_MAX_VIEWS];       // (cx, cy) as floats
     double cxyd[MC3D_MAX_VIEWS][2];   // the same values as doubles
     double Pc[MC3D_MAX_VIEWS][12];    // P0', P1', P2 in double
+    float rig2;                       // mean squared distance of the camera centres from the world origin
 };
 
 // ---- small dense helpers ----------------------------------------------------------------------
@@ -192,31 +195,12 @@ __device__ __forceinline__ void accumulate_view(double *B, double x, double y, d
 }
 
 // ---- mixed-precision solver (float storage) ---------------------------------------------------------------------
-// float LDL^T solve of a 3x3 SPD system; approximate reciprocals are fine: this solve only preconditions the
-// iteration below, whose fixed point is set by residuals evaluated in double.
+// float LDL^T of a 3x3 SPD system (ldl3_factor_f / ldl3_apply_f below); approximate reciprocals are fine: the solve
+// only preconditions an iteration whose fixed point is set by residuals evaluated in double.
 __device__ __forceinline__ float rcp_fast(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
-}
-
-__device__ __forceinline__ bool ldl3_solve_f(float m00, float m10, float m11, float m20, float m21, float m22,
-                                             float r0, float r1, float r2, float &z0, float &z1, float &z2) {
-    // branch-free: bad pivots produce inf / NaN that the caller discards through the returned flag
-    const float i0 = rcp_fast(m00);
-    const float l10 = m10 * i0, l20 = m20 * i0;
-    const float d1 = fmaf(-l10, m10, m11);
-    const float i1 = rcp_fast(d1);
-    const float t21 = fmaf(-l20, m10, m21);
-    const float l21 = t21 * i1;
-    const float d2 = fmaf(-l21, t21, fmaf(-l20, m20, m22));
-    const float i2 = rcp_fast(d2);
-    const float y1 = fmaf(-l10, r0, r1);
-    const float y2 = fmaf(-l21, y1, fmaf(-l20, r0, r2));
-    z2 = y2 * i2;
-    z1 = fmaf(y1, i1, -l21 * z2);
-    z0 = fmaf(r0, i0, -fmaf(l10, z1, l20 * z2));
-    return (m00 > 0.f) & (d1 > 1e-6f * m11) & (d2 > 1e-6f * m22);
 }
 
 // All-double solve of one joint straight from its shared-memory row (cold path of the mixed kernel).
@@ -268,158 +252,250 @@ __device__ __forceinline__ void load_group(const float *row, int vg, float (&gx)
     }
 }
 
-// Smallest eigenpair of B = A^T A without ever forming B in double, NJ joints per thread in lock-step (the
-// per-view camera constants are fetched once and used NJ times; the joints give independent instruction streams):
-//   1. M~, b~ (the blocks of B) accumulated in float with packed FFMA2 -- the two rows of a view ride in one
-//      float2 -- and a float LDL^T solve give X0 (error ~1e-6 relative);
-//   2. Newton on the eigen-equations  F(X) = A_m^T A (X,1) - lam X = 0,  lam = |A (X,1)|^2 / (1 + |X|^2),
-//      with the residual A (X,1) evaluated in DOUBLE from the double projection rows (the cancellation
-//      y (P2.X) - P1.X happens in double) and the correction solved with the float factorisation of M~ - lam I.
-//      Each step contracts the error by ~cond(M) * 1e-6, so one or two steps reach double-class accuracy.
-// state[j]: 0 = solved (X valid, NaN for degenerate / non-finite joints), 1 = needs the all-double fallback.
-template <int V, int LAYOUT, int NJ>
-__device__ __forceinline__ void solve_mixed(const TriParams &prm, const float *const (&rows)[NJ], const bool (&act)[NJ],
-                                            double (&X)[NJ][3], int (&state)[NJ]) {
-    float2 aM[NJ][6], ab[NJ][3];
-    float m[NJ][6], b[NJ][3];
-    constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
+// ---- merged-pass mixed-precision solver (float storage) -----------------------------------------------------------
+// The two-pass solver above touches every view twice (float normal equations, then double residuals).  This one
+// touches the full view set once:
+//   E. a float DLT over a fixed subset of (at most) three well-spread views gives a starting point Xp that is a few
+//      millimetres from the minimiser (the subset's own noise);
+//   M. ONE pass over all V views accumulates, per view, the float normal matrix M~ = sum w^2 (a a^T + c c^T) and the
+//      gradient g = A_m^T A (Xp,1) with the residual A (Xp,1) evaluated in DOUBLE (the cancellation
+//      y (P2.X) - P1.X needs it) and rounded to float;
+//   S. the correction solves the eigen-equations to first order in lam/M:
+//         e1 = -M~^-1 g,   lam = (|r|^2 + g.e1) / (1 + |Xp + e1|^2),   e = e1 + lam M~^-1 (Xp + e1)
+//      (exact fixed point (M - lam) X = -b; the neglected term is (lam/mu_min)^2 |X|, checked per joint).
+// The float solve is accurate to ~3e-7 |e|, so a correction of up to a few centimetres lands within 1e-5 mm;
+// larger corrections take another pass from the updated point, and whatever cannot be handled (failed pivots,
+// non-finite input, lam not small, no convergence) goes to the all-double solver.
+struct __align__(16) CamC {
+    double Pc[12];       // P0', P1', P2 (rows re-centred on the principal point)
+    double cxd, cyd;
+    float2 p10[4];       // (-P1'_k, P0'_k)
+    float4 p2;           // P2_k
+    float cx, cy, pad0, pad1;
+};
+static_assert(sizeof(CamC) == 176, "CamC layout");
+
+struct Ldl3f {
+    float i0, l10, l20, i1, l21, i2;
+};
+
+__device__ __forceinline__ bool ldl3_factor_f(float m00, float m10, float m11, float m20, float m21, float m22, Ldl3f &f) {
+    f.i0 = rcp_fast(m00);
+    f.l10 = m10 * f.i0;
+    f.l20 = m20 * f.i0;
+    const float d1 = fmaf(-f.l10, m10, m11);
+    f.i1 = rcp_fast(d1);
+    const float t21 = fmaf(-f.l20, m10, m21);
+    f.l21 = t21 * f.i1;
+    const float d2 = fmaf(-f.l21, t21, fmaf(-f.l20, m20, m22));
+    f.i2 = rcp_fast(d2);
+    return (m00 > 0.f) & (d1 > 1e-6f * m11) & (d2 > 1e-6f * m22);
+}
+
+__device__ __forceinline__ void ldl3_apply_f(const Ldl3f &f, float r0, float r1, float r2, float &z0, float &z1, float &z2) {
+    const float y1 = fmaf(-f.l10, r0, r1);
+    const float y2 = fmaf(-f.l21, y1, fmaf(-f.l20, r0, r2));
+    z2 = y2 * f.i2;
+    z1 = fmaf(y1, f.i1, -f.l21 * z2);
+    z0 = fmaf(r0, f.i0, -fmaf(f.l10, z1, f.l20 * z2));
+}
+
+// views of the starting-point subset: (i * V) / NE for i < NE, NE = min(V, 3)
+__host__ __device__ constexpr int est_count(int V) { return V < 3 ? V : 3; }
+__host__ __device__ constexpr bool is_est_view(int V, int v) {
+    for (int i = 0; i < est_count(V); ++i)
+        if ((i * V) / est_count(V) == v) return true;
+    return false;
+}
+__host__ __device__ constexpr bool group_has_est_view(int V, int vg, int G) {
+    for (int i = 0; i < G; ++i)
+        if (is_est_view(V, vg + i)) return true;
+    return false;
+}
+
+// weighted float rows of one view, packed (a_k, c_k), k < NK
+template <int NK>
+__device__ __forceinline__ void float_rows(float x, float y, float w, float cx, float cy, const float (&p2)[4],
+                                           const float2 (&p10)[4], float2 (&ac)[NK]) {
+    const float xc = x - cx, yc = y - cy;
+    const float2 sv = make_float2(w * yc, -(w * xc));
+    const float2 ww = make_float2(w, w);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) ac[k] = __ffma2_rn(sv, make_float2(p2[k], p2[k]), __fmul2_rn(ww, p10[k]));
+}
+
 #ifndef MC3D_TRI_UNR_LIMIT
-#define MC3D_TRI_UNR_LIMIT 4
+#define MC3D_TRI_UNR_LIMIT 4            // full unrolling of 8+ views hoists loads into spills
 #endif
-    constexpr int UNR = (V > MC3D_TRI_UNR_LIMIT) ? 1 : (V / G);   // full unrolling of 8+ views hoists loads into spills
+#ifndef MC3D_TRI_ACCEPT
+#define MC3D_TRI_ACCEPT 1.0e-3f      // accept a correction with |e|^2 <= this * (|X|^2 + rig scale^2): |e| <~ 3 % of the range
+#endif
+
+template <int V, int LAYOUT, int NJ>
+__device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float rig2, const float *const (&rows)[NJ],
+                                             const bool (&act)[NJ], double (&X)[NJ][3], int (&state)[NJ]) {
+    constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
+    double Xd[NJ][3];
+    // ---- E: starting point from the subset ---------------------------------------------------------------
+    {
+        float2 aM[NJ][6], ab[NJ][3];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
+        for (int j = 0; j < NJ; ++j) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) aM[j][i] = make_float2(0.f, 0.f);
+            for (int i = 0; i < 6; ++i) aM[j][i] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) ab[j][i] = make_float2(0.f, 0.f);
-    }
-#pragma unroll UNR
-    for (int vg = 0; vg < V; vg += G) {
-        float gx[NJ][G], gy[NJ][G], gw[NJ][G];
+            for (int i = 0; i < 3; ++i) ab[j][i] = make_float2(0.f, 0.f);
+        }
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) load_group<V, LAYOUT, G>(rows[j], vg, gx[j], gy[j], gw[j]);
+        for (int vg = 0; vg < V; vg += G) {
+            if (!group_has_est_view(V, vg, G)) continue;
+            float gx[NJ][G], gy[NJ][G], gw[NJ][G];
 #pragma unroll
-        for (int i = 0; i < G; ++i) {
-            const int v = vg + i;
-            const float2 cxy = prm.cxy[v];
-            float2 p2[4], p10[4];
+            for (int j = 0; j < NJ; ++j) load_group<V, LAYOUT, G>(rows[j], vg, gx[j], gy[j], gw[j]);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { p2[k] = prm.p2[v][k]; p10[k] = prm.p10[v][k]; }
+            for (int i = 0; i < G; ++i) {
+                const int v = vg + i;
+                if (!is_est_view(V, v)) continue;
+                const CamC &c = cam[v];
+                const float4 p2v = c.p2;
+                const float p2[4] = {p2v.x, p2v.y, p2v.z, p2v.w};
+                float2 p10[4];
+                {
+                    const float4 a = *reinterpret_cast<const float4 *>(&c.p10[0]);
+                    const float4 b = *reinterpret_cast<const float4 *>(&c.p10[2]);
+                    p10[0] = make_float2(a.x, a.y); p10[1] = make_float2(a.z, a.w);
+                    p10[2] = make_float2(b.x, b.y); p10[3] = make_float2(b.z, b.w);
+                }
+                const float2 cxy = *reinterpret_cast<const float2 *>(&c.cx);
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const float w = gw[j][i];
-                const float xc = gx[j][i] - cxy.x, yc = gy[j][i] - cxy.y;
-                const float2 sv = make_float2(w * yc, -(w * xc));
-                const float2 ww = make_float2(w, w);
-                float2 ac[4];
+                for (int j = 0; j < NJ; ++j) {
+                    float2 ac[4];
+#ifdef MC3D_TRI_EST_WEIGHTED
+                    float_rows<4>(gx[j][i], gy[j][i], gw[j][i], cxy.x, cxy.y, p2, p10, ac);
+#else
+                    // unweighted rows: the starting point only has to be close (a zero-weight view with a wild
+                    // pixel costs one extra pass, not accuracy)
+                    const float2 yx = make_float2(gy[j][i] - cxy.y, cxy.x - gx[j][i]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ac[k] = __ffma2_rn(sv, p2[k], __fmul2_rn(ww, p10[k]));
-                aM[j][0] = __ffma2_rn(ac[0], ac[0], aM[j][0]);
-                aM[j][1] = __ffma2_rn(ac[1], ac[0], aM[j][1]);
-                aM[j][2] = __ffma2_rn(ac[1], ac[1], aM[j][2]);
-                aM[j][3] = __ffma2_rn(ac[2], ac[0], aM[j][3]);
-                aM[j][4] = __ffma2_rn(ac[2], ac[1], aM[j][4]);
-                aM[j][5] = __ffma2_rn(ac[2], ac[2], aM[j][5]);
-                ab[j][0] = __ffma2_rn(ac[3], ac[0], ab[j][0]);
-                ab[j][1] = __ffma2_rn(ac[3], ac[1], ab[j][1]);
-                ab[j][2] = __ffma2_rn(ac[3], ac[2], ab[j][2]);
+                    for (int k = 0; k < 4; ++k) ac[k] = __ffma2_rn(yx, make_float2(p2[k], p2[k]), p10[k]);
+#endif
+                    aM[j][0] = __ffma2_rn(ac[0], ac[0], aM[j][0]);
+                    aM[j][1] = __ffma2_rn(ac[1], ac[0], aM[j][1]);
+                    aM[j][2] = __ffma2_rn(ac[1], ac[1], aM[j][2]);
+                    aM[j][3] = __ffma2_rn(ac[2], ac[0], aM[j][3]);
+                    aM[j][4] = __ffma2_rn(ac[2], ac[1], aM[j][4]);
+                    aM[j][5] = __ffma2_rn(ac[2], ac[2], aM[j][5]);
+                    ab[j][0] = __ffma2_rn(ac[3], ac[0], ab[j][0]);
+                    ab[j][1] = __ffma2_rn(ac[3], ac[1], ab[j][1]);
+                    ab[j][2] = __ffma2_rn(ac[3], ac[2], ab[j][2]);
+                }
             }
         }
-    }
-    double Xd[NJ][3];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) m[j][i] = aM[j][i].x + aM[j][i].y;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) b[j][i] = ab[j][i].x + ab[j][i].y;
-        X[j][0] = X[j][1] = X[j][2] = NAN;
-        Xd[j][0] = Xd[j][1] = Xd[j][2] = 0.0;
-        state[j] = 0;
-        if (!act[j]) { state[j] = 0; continue; }
-        // Non-finite input or fewer than two usable views make the float factorisation fail (NaN compares false,
-        // a rank-deficient M~ has a pivot at rounding level): those joints take the all-double path, which
-        // classifies them (NaN output) exactly like the double-storage kernel.
-        float z0, z1, z2;
-        if (!ldl3_solve_f(m[j][0], m[j][1], m[j][2], m[j][3], m[j][4], m[j][5], -b[j][0], -b[j][1], -b[j][2], z0, z1, z2)) {
-            state[j] = 1;
-            continue;
+        for (int j = 0; j < NJ; ++j) {
+            X[j][0] = X[j][1] = X[j][2] = NAN;
+            Xd[j][0] = Xd[j][1] = Xd[j][2] = 0.0;
+            state[j] = 0;
+            if (!act[j]) continue;
+            Ldl3f f;
+            const bool ok = ldl3_factor_f(aM[j][0].x + aM[j][0].y, aM[j][1].x + aM[j][1].y, aM[j][2].x + aM[j][2].y,
+                                          aM[j][3].x + aM[j][3].y, aM[j][4].x + aM[j][4].y, aM[j][5].x + aM[j][5].y, f);
+            float z0, z1, z2;
+            ldl3_apply_f(f, -(ab[j][0].x + ab[j][0].y), -(ab[j][1].x + ab[j][1].y), -(ab[j][2].x + ab[j][2].y), z0, z1, z2);
+            const float nz = fmaf(z0, z0, fmaf(z1, z1, z2 * z2));
+            if (!ok || !(nz <= 3.0e38f)) { state[j] = 1; continue; }   // subset degenerate / non-finite: all-double path
+            Xd[j][0] = (double)z0; Xd[j][1] = (double)z1; Xd[j][2] = (double)z2;
+            state[j] = 2;
         }
-        Xd[j][0] = (double)z0; Xd[j][1] = (double)z1; Xd[j][2] = (double)z2;
-        state[j] = 2;                                            // iterating
     }
+    // ---- M + S: merged pass from Xp, repeated only when the correction was large ---------------------------------
+    constexpr int UNR = (V > MC3D_TRI_UNR_LIMIT) ? 1 : (V / G);
 #pragma unroll 1
     for (int it = 0; it < 6; ++it) {
         bool any = false;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) any = any || (state[j] == 2);
         if (!any) break;
-        float2 gp[NJ][3];
-        float gq[NJ][3], rr[NJ];
+        float2 aM[NJ][6], ag[NJ][3], arr[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            rr[j] = 0.f;
+            arr[j] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { gp[j][k] = make_float2(0.f, 0.f); gq[j][k] = 0.f; }
+            for (int i = 0; i < 6; ++i) aM[j][i] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) ag[j][i] = make_float2(0.f, 0.f);
         }
 #pragma unroll UNR
         for (int vg = 0; vg < V; vg += G) {
-            float gx[NJ][G], gy[NJ][G], gw[NJ][G];              // re-read: cheaper than holding 3V registers per joint
+            float gx[NJ][G], gy[NJ][G], gw[NJ][G];
 #pragma unroll
             for (int j = 0; j < NJ; ++j) load_group<V, LAYOUT, G>(rows[j], vg, gx[j], gy[j], gw[j]);
 #pragma unroll
             for (int i = 0; i < G; ++i) {
-                const int v = vg + i;
+                const CamC &c = cam[vg + i];
                 double Pc[12];
 #pragma unroll
-                for (int k = 0; k < 12; ++k) Pc[k] = prm.Pc[v][k];
-                const double cxd = prm.cxyd[v][0], cyd = prm.cxyd[v][1];
-                const float2 cxy = prm.cxy[v];
-                float2 p10[3];
-                float p2x[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { p10[k] = prm.p10[v][k]; p2x[k] = prm.p2[v][k].x; }
+                for (int k = 0; k < 6; ++k) {
+                    const double2 t = *reinterpret_cast<const double2 *>(&c.Pc[2 * k]);
+                    Pc[2 * k] = t.x; Pc[2 * k + 1] = t.y;
+                }
+                const double2 cxyd = *reinterpret_cast<const double2 *>(&c.cxd);
+                const float4 p2v = c.p2;
+                const float p2[4] = {p2v.x, p2v.y, p2v.z, p2v.w};
+                float2 p10[4];
+                {
+                    const float4 a = *reinterpret_cast<const float4 *>(&c.p10[0]);
+                    const float2 b = c.p10[2];
+                    p10[0] = make_float2(a.x, a.y); p10[1] = make_float2(a.z, a.w); p10[2] = b;
+                    p10[3] = make_float2(0.f, 0.f);
+                }
+                const float2 cxy = *reinterpret_cast<const float2 *>(&c.cx);
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
+                    const float x = gx[j][i], y = gy[j][i], w = gw[j][i];
+                    float2 ac[3];
+                    float_rows<3>(x, y, w, cxy.x, cxy.y, p2, p10, ac);
+                    aM[j][0] = __ffma2_rn(ac[0], ac[0], aM[j][0]);
+                    aM[j][1] = __ffma2_rn(ac[1], ac[0], aM[j][1]);
+                    aM[j][2] = __ffma2_rn(ac[1], ac[1], aM[j][2]);
+                    aM[j][3] = __ffma2_rn(ac[2], ac[0], aM[j][3]);
+                    aM[j][4] = __ffma2_rn(ac[2], ac[1], aM[j][4]);
+                    aM[j][5] = __ffma2_rn(ac[2], ac[2], aM[j][5]);
                     const double d0 = fma(Pc[0], Xd[j][0], fma(Pc[1], Xd[j][1], fma(Pc[2], Xd[j][2], Pc[3])));
                     const double d1 = fma(Pc[4], Xd[j][0], fma(Pc[5], Xd[j][1], fma(Pc[6], Xd[j][2], Pc[7])));
                     const double d2 = fma(Pc[8], Xd[j][0], fma(Pc[9], Xd[j][1], fma(Pc[10], Xd[j][2], Pc[11])));
-                    const float x = gx[j][i], y = gy[j][i], w = gw[j][i];
-                    const double xcd = (double)x - cxd, ycd = (double)y - cyd;
+                    const double xcd = (double)x - cxyd.x, ycd = (double)y - cxyd.y;
                     const float r1 = (float)fma(ycd, d2, -d1);   // y (P2.X) - P1.X : the cancellation is in double
                     const float r2 = (float)fma(-xcd, d2, d0);   // P0.X - x (P2.X)
-                    const float w2 = w * w;
-                    const float2 t = __fmul2_rn(make_float2(w2, w2), make_float2(r1, r2));
-                    const float xc = x - cxy.x, yc = y - cxy.y;
-                    const float t3 = fmaf(t.x, yc, -(t.y * xc));
+                    const float2 t = __fmul2_rn(make_float2(w, w), make_float2(r1, r2));
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        gp[j][k] = __ffma2_rn(t, p10[k], gp[j][k]);   // (-t1 P1'_k, t2 P0'_k)
-                        gq[j][k] = fmaf(t3, p2x[k], gq[j][k]);
-                    }
-                    rr[j] = fmaf(t.x, r1, fmaf(t.y, r2, rr[j]));
+                    for (int k = 0; k < 3; ++k) ag[j][k] = __ffma2_rn(t, ac[k], ag[j][k]);
+                    arr[j] = __ffma2_rn(t, t, arr[j]);
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             if (state[j] != 2) continue;
-            const float xf0 = (float)Xd[j][0], xf1 = (float)Xd[j][1], xf2 = (float)Xd[j][2];
-            const float nx = fmaf(xf0, xf0, fmaf(xf1, xf1, xf2 * xf2));
-            const float lam = rr[j] * rcp_fast(1.f + nx);
-            const float f0 = (gp[j][0].x + gp[j][0].y + gq[j][0]) - lam * xf0;
-            const float f1 = (gp[j][1].x + gp[j][1].y + gq[j][1]) - lam * xf1;
-            const float f2 = (gp[j][2].x + gp[j][2].y + gq[j][2]) - lam * xf2;
+            Ldl3f f;
+            const bool ok = ldl3_factor_f(aM[j][0].x + aM[j][0].y, aM[j][1].x + aM[j][1].y, aM[j][2].x + aM[j][2].y,
+                                          aM[j][3].x + aM[j][3].y, aM[j][4].x + aM[j][4].y, aM[j][5].x + aM[j][5].y, f);
+            const float g0 = ag[j][0].x + ag[j][0].y, g1 = ag[j][1].x + ag[j][1].y, g2 = ag[j][2].x + ag[j][2].y;
             float e0, e1, e2;
-            if (!ldl3_solve_f(m[j][0] - lam, m[j][1], m[j][2] - lam, m[j][3], m[j][4], m[j][5] - lam, -f0, -f1, -f2, e0, e1, e2)) {
-                state[j] = 1;
-                continue;
-            }
-            Xd[j][0] += (double)e0; Xd[j][1] += (double)e1; Xd[j][2] += (double)e2;
+            ldl3_apply_f(f, -g0, -g1, -g2, e0, e1, e2);
+            const float rr = (arr[j].x + arr[j].y) + fmaf(g0, e0, fmaf(g1, e1, g2 * e2));
+            const float x0 = (float)Xd[j][0] + e0, x1 = (float)Xd[j][1] + e1, x2 = (float)Xd[j][2] + e2;
+            const float nx = fmaf(x0, x0, fmaf(x1, x1, x2 * x2));
+            const float lam = rr * rcp_fast(1.f + nx);
+            float h0, h1, h2;
+            ldl3_apply_f(f, lam * x0, lam * x1, lam * x2, h0, h1, h2);
+            e0 += h0; e1 += h1; e2 += h2;
             const float ne = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
-            if (!(ne <= 3.0e38f)) { state[j] = 1; continue; }
-            if (ne <= 1e-8f * nx) {                              // |dX| <= 1e-4 |X|: the next error is ~1e-10 |X|
+            // first-order treatment of lam needs lam << smallest pivot of M~
+            const float imax = fmaxf(f.i0, fmaxf(f.i1, f.i2));
+            if (!ok || !(ne <= 3.0e38f) || !(fabsf(lam) * imax <= 3.0e-5f)) { state[j] = 1; continue; }
+            Xd[j][0] += (double)e0; Xd[j][1] += (double)e1; Xd[j][2] += (double)e2;
+            if (ne <= MC3D_TRI_ACCEPT * (nx + rig2)) {
                 X[j][0] = Xd[j][0]; X[j][1] = Xd[j][1]; X[j][2] = Xd[j][2];
                 state[j] = 0;
             }
@@ -427,7 +503,7 @@ __device__ __forceinline__ void solve_mixed(const TriParams &prm, const float *c
     }
 #pragma unroll
     for (int j = 0; j < NJ; ++j)
-        if (state[j] == 2) state[j] = 1;                         // did not converge in 6 steps
+        if (state[j] == 2) state[j] = 1;                         // did not converge in 6 passes
 }
 
 #ifndef MC3D_TRI_NJ
@@ -445,10 +521,11 @@ constexpr int TRI_MTILE = TRI_MTHREADS * TRI_NJ;    // joints per tile
 
 // Mixed-precision kernel (float storage, weighted mode, V in {2,3,4,8,16}, no undistortion).  Same TMA ring as the
 // generic kernel; 128 threads x 2 joints per thread (thread t owns joints t and t + 128 of a 256-joint tile), view
-// loops unrolled four views at a time, 4 CTAs per SM (112 registers, no spills): the fastest on B200 of the
-// (joints/thread, threads, CTAs/SM, unroll) variants timed (profiles/README.md).
+// loops unrolled four views at a time, camera constants in shared memory (128-bit broadcast loads), 4 CTAs per SM
+// (3 for 16 views): the fastest on B200 of the (joints/thread, threads, CTAs/SM, unroll) variants timed
+// (profiles/README.md).
 template <int V, int LAYOUT>
-__global__ void __launch_bounds__(TRI_MTHREADS, MC3D_TRI_MBLOCKS)
+__global__ void __launch_bounds__(TRI_MTHREADS, (V >= 16) ? MC3D_TRI_MBLOCKS - 1 : MC3D_TRI_MBLOCKS)
 triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out, long long n, int n_stages,
                          const __grid_constant__ TriParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -457,6 +534,7 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     float *ring = reinterpret_cast<float *>(smem_raw);
     float *otile = reinterpret_cast<float *>(smem_raw + (size_t)n_stages * stage_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + 2 * TRI_MTILE * 3 * sizeof(float));
+    CamC *cam = reinterpret_cast<CamC *>(full + 8);          // per-view constants, read with 128-bit loads
     const int tid = threadIdx.x;
     const long long n_tiles = (n + TRI_MTILE - 1) / TRI_MTILE;
     const long long first = blockIdx.x, stride = gridDim.x;
@@ -464,6 +542,20 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
+    }
+    if (tid < V) {
+        CamC c;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) c.Pc[k] = prm.Pc[tid][k];
+        c.cxd = prm.cxyd[tid][0];
+        c.cyd = prm.cxyd[tid][1];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c.p10[k] = prm.p10[tid][k];
+        c.p2 = make_float4(prm.p2[tid][0].x, prm.p2[tid][1].x, prm.p2[tid][2].x, prm.p2[tid][3].x);
+        c.cx = prm.cxy[tid].x;
+        c.cy = prm.cxy[tid].y;
+        c.pad0 = c.pad1 = 0.f;
+        cam[tid] = c;
     }
     __syncthreads();
     auto tile_is_full = [&](long long tile) { return (tile + 1) * TRI_MTILE <= n; };
@@ -505,7 +597,7 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
             act[j] = tile * TRI_MTILE + slot < n;
             rows[j] = stage + (size_t)(act[j] ? slot : tid) * row_elems;      // inactive slots read a valid row
         }
-        solve_mixed<V, LAYOUT, TRI_NJ>(prm, rows, act, X, state);
+        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state);
 #pragma unroll
         for (int j = 0; j < TRI_NJ; ++j)
             if (act[j] && state[j] == 1) {
@@ -546,6 +638,7 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     }
     if (tid == 0) bulk_wait_all<0>();
 }
+
 
 // ---- kernel -----------------------------------------------------------------------------------
 // V > 0: number of views known at compile time (fully unrolled); V == 0: runtime prm.n_views.
@@ -739,6 +832,21 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
             prm.p10[v][k] = make_float2((float)-p1c, (float)p0c);
         }
     }
+    double acc = 0.0;
+    int cnt = 0;
+    for (int v = 0; v < rig->n_views; ++v) {                 // camera centre C: P (C,1) = 0
+        const double *p = prm.P[v];
+        const double a = p[0], b = p[1], c = p[2], d = p[4], e = p[5], f = p[6], g = p[8], h = p[9], i = p[10];
+        const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+        if (!(fabs(det) > 0.0)) continue;
+        const double r0 = -p[3], r1 = -p[7], r2 = -p[11];
+        const double c0 = (r0 * (e * i - f * h) - b * (r1 * i - f * r2) + c * (r1 * h - e * r2)) / det;
+        const double c1 = (a * (r1 * i - f * r2) - r0 * (d * i - f * g) + c * (d * r2 - r1 * g)) / det;
+        const double c2 = (a * (e * r2 - r1 * h) - b * (d * r2 - r1 * g) + r0 * (d * h - e * g)) / det;
+        const double n2 = c0 * c0 + c1 * c1 + c2 * c2;
+        if (n2 <= 1.0e300) { acc += n2; ++cnt; }
+    }
+    prm.rig2 = cnt ? (float)fmin(acc / cnt, 1.0e30) : 0.f;
     return MC3D_OK;
 }
 
@@ -784,7 +892,7 @@ static int launch_mixed(const float *d_kpts, long long n, const TriParams &prm, 
         MC3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    const size_t fixed = 2 * TRI_MTILE * 3 * sizeof(float) + 8 * sizeof(uint64_t);
+    const size_t fixed = 2 * TRI_MTILE * 3 * sizeof(float) + 8 * sizeof(uint64_t) + V * sizeof(CamC);
     int n_stages = 2, per_sm = 0;
     size_t smem = 0;
     for (int st = 3; st >= 2; --st) {

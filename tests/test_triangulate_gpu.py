@@ -163,6 +163,26 @@ def test_fp32_mixed_solver_agrees_with_all_double_solver(tri, syn):
         assert np.linalg.norm(a - ref, axis=1).max() < FP32_ATOL_MM
 
 
+def test_fp32_starting_subset_views_missing_or_wild(tri, syn):
+    """The float kernel starts from a DLT over views {0, V/3, 2V/3} (triangulate.cu solve_merged).  Zero-weight
+    views there (with wild pixels), outliers that put the start far from the answer, and a subset reduced to one
+    usable view must all end at the same minimiser as the float64 oracle."""
+    kp, P, _, _ = syn.multiview_points(20000, 8, seed=77)
+    rng = np.random.default_rng(5)
+    kp[0:4000, 0, 2] = 0.0                                   # view 0 unused, pixel left as is
+    kp[4000:8000, 2, 2] = 0.0
+    kp[4000:8000, 2, :2] = rng.uniform(-5000, 5000, size=(4000, 2))      # unused view with a wild pixel
+    kp[8000:12000, 5, :2] += rng.normal(0, 60.0, size=(4000, 2))           # gross outlier in a starting view (weighted in)
+    kp[12000:16000, [0, 2], 2] = 0.0                         # only one starting view usable -> 2 unknown-rank start
+    kp[16000:18000, [0, 2, 5], 2] = 0.0                      # no starting view usable
+    kp32 = kp.astype(np.float32)
+    got = tri(_cuda(kp32), P).cpu().numpy().astype(np.float64)
+    ref = O.dlt_weighted_polished(kp32.astype(np.float64), P)
+    err = np.linalg.norm(got - ref, axis=1)
+    assert np.isfinite(got).all()
+    assert err.max() < FP32_ATOL_MM, (err.max(), int(err.argmax()))
+
+
 def test_fp32_points_near_world_origin(tri, syn):
     rng = np.random.default_rng(34)
     cams = syn.ring_rig(8, centre=(0.0, 0.0, 0.0))
