@@ -36,6 +36,8 @@ extern "C" {
 #define MC3D_MAX_VIEWS 16         /* cameras per rig handled by one launch */
 #define MC3D_MAX_JOINTS 133       /* COCO-WholeBody */
 #define MC3D_MAX_BONES 64
+#define MC3D_MAX_PEERS 16         /* ranks of one NVLink domain in the in-kernel refinement exchange */
+#define MC3D_IPC_HANDLE_BYTES 64
 
 typedef enum {
     MC3D_OK = 0,
@@ -150,8 +152,17 @@ int mc3d_decode_heatmaps_host_f32(const float *h_heatmaps, int64_t n_maps, int H
  *            [32..39]+16p state entering a step of parity p: adam_step run_sum run_cnt best no_improve
  *                         stopped iterations improved
  *            [64+4s ..]   cost history of step s: total likelihood smoothness body_length
- * A multi-GPU driver shards frames, exchanges the x halo after phase 2 and all-reduces ctrl[0..6]+16p after phase 0
- * and ctrl[7]+16p after phase 1 (that is the whole exchange; every rank then takes the same decisions). */
+ * Multi-GPU (frames sharded contiguously, one process per GPU), two ways:
+ *   host-driven: the driver exchanges the x halo after phase 2 and all-reduces ctrl[0..6]+16p after phase 0 and
+ *                ctrl[7]+16p after phase 1 with any collective library (that is the whole exchange; every rank then
+ *                takes the same decisions);
+ *   in-kernel  : `xchg` holds every rank's exchange block (mc3d_peer_alloc / mc3d_peer_open, NVLink peer memory) and
+ *                the kernels do the exchange themselves: the last block of phase 0 / 1 stores this rank's partial
+ *                sums into every peer's block followed by a sequence flag, phases 1 / 2 spin on their own block's
+ *                flags and add the partial sums in rank order (bitwise identical on every rank), and phase 2 stores
+ *                its boundary frames straight into the neighbours' halo frames.  No NCCL call, no host round trip,
+ *                and the whole step sequence can be replayed from one CUDA graph on every rank.
+ *                In this mode `x` must live inside the exchange allocation at byte MC3D_XCHG_X_OFFSET. */
 typedef struct {
     int32_t n_joints, n_cams, n_bones, ignore_distortions;
     int32_t patience, max_iter;
@@ -170,7 +181,23 @@ typedef struct {
     void *x, *m, *v, *best, *g, *mu0, *S;
     uint8_t *term_ok;
     double *ctrl;
+    /* in-kernel exchange (all zero / NULL = off) */
+    int32_t rank, world;
+    int64_t n_frames_left;   /* local frame count of rank - 1 (locates its right halo) */
+    int64_t spin_timeout_ns; /* a wait on a peer gives up after this long and sets mc3d_refine_xchg.error */
+    void *xchg[MC3D_MAX_PEERS];   /* exchange blocks of all ranks as mapped in this process; xchg[rank] is local */
 } mc3d_refine_problem;
+
+/* Exchange block at the start of each rank's peer allocation (zero-filled by mc3d_peer_alloc). */
+#define MC3D_XCHG_X_OFFSET 4096
+typedef struct {
+    double sums[2][MC3D_MAX_PEERS][8];      /* [step parity][source rank]: S_lik N_lik S_s N_s a.b b.b a.a | gnorm^2 */
+    int64_t seq_costs[2][MC3D_MAX_PEERS];   /* adam step + 1 of the cost sums stored in that slot */
+    int64_t seq_grad[2][MC3D_MAX_PEERS];    /* the same for gnorm^2 */
+    int64_t halo_seq[2];                    /* adam step count the left / right halo frames belong to */
+    int64_t ticket[4];                      /* block tickets of phases 0, 1, 2 (local) */
+    int64_t error;                          /* != 0: a wait timed out (results are invalid) */
+} mc3d_refine_xchg;
 
 /* Pinhole + 5-coefficient Brown projection of n points (n,3) -> (n,2) for one camera given as
  * cam26 = K[9] R[9] T[3] dist[5] (host doubles): project_points_torch, pose_refinement.py:94-179. */
@@ -191,6 +218,14 @@ int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step
 /* n_iters whole-window iterations (phases 0,1,2 each) on one GPU, replayed from a CUDA graph. */
 int mc3d_refine_run_f32(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
 int mc3d_refine_run_f64(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
+
+/* Peer memory for the in-kernel exchange: a zero-filled device allocation on the current device plus its CUDA IPC
+ * handle (MC3D_IPC_HANDLE_BYTES bytes) for the other ranks of the node; mc3d_peer_open maps another rank's
+ * allocation into this process with peer access enabled (NVLink / NVSwitch on an HGX B200 board). */
+int mc3d_peer_alloc(int64_t bytes, void **d_ptr, unsigned char *handle);
+int mc3d_peer_open(const unsigned char *handle, void **d_ptr);
+int mc3d_peer_close(void *d_ptr);
+int mc3d_peer_free(void *d_ptr);
 
 
 /* ---- 4. linear interpolation (pose_refinement.py:15-84) ---------------------------------------------------

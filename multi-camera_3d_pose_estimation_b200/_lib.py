@@ -34,6 +34,9 @@ class Rig(ctypes.Structure):
 
 MAX_JOINTS = 133
 MAX_BONES = 64
+MAX_PEERS = 16
+IPC_HANDLE_BYTES = 64
+XCHG_X_OFFSET = 4096
 CT_ACC, CT_STATE, CT_HIST = 0, 32, 64          # control-block layout (include/mc3d.h)
 
 
@@ -53,7 +56,16 @@ class RefineProblem(ctypes.Structure):
                 ('adj_bone', ctypes.c_int32 * (2 * MAX_BONES)), ('adj_sign', ctypes.c_int32 * (2 * MAX_BONES)),
                 ('x', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p), ('best', ctypes.c_void_p),
                 ('g', ctypes.c_void_p), ('mu0', ctypes.c_void_p), ('S', ctypes.c_void_p),
-                ('term_ok', ctypes.c_void_p), ('ctrl', ctypes.c_void_p)]
+                ('term_ok', ctypes.c_void_p), ('ctrl', ctypes.c_void_p),
+                ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('n_frames_left', ctypes.c_int64),
+                ('spin_timeout_ns', ctypes.c_int64), ('xchg', ctypes.c_void_p * MAX_PEERS)]
+
+
+class RefineXchg(ctypes.Structure):
+    """mc3d_refine_xchg (include/mc3d.h): head of a rank's peer allocation."""
+    _fields_ = [('sums', ((ctypes.c_double * 8) * MAX_PEERS) * 2),
+                ('seq_costs', (ctypes.c_int64 * MAX_PEERS) * 2), ('seq_grad', (ctypes.c_int64 * MAX_PEERS) * 2),
+                ('halo_seq', ctypes.c_int64 * 2), ('ticket', ctypes.c_int64 * 4), ('error', ctypes.c_int64)]
 
 
 _lib = None
@@ -89,6 +101,10 @@ SIGNATURES = {
     'mc3d_refine_phase_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_int, _c_i64, _c_int, _c_vp]),
     'mc3d_refine_run_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_i64, _c_i64, _c_vp]),
     'mc3d_refine_run_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_i64, _c_i64, _c_vp]),
+    'mc3d_peer_alloc': (_c_int, [_c_i64, ctypes.POINTER(_c_vp), _c_vp]),
+    'mc3d_peer_open': (_c_int, [_c_vp, ctypes.POINTER(_c_vp)]),
+    'mc3d_peer_close': (_c_int, [_c_vp]),
+    'mc3d_peer_free': (_c_int, [_c_vp]),
     'mc3d_linear_interpolation_f64': (_c_int, [_c_vp, _c_i64, _c_i64, _c_int, _c_dbl, _c_dbl, _c_int, _c_int, _c_vp, _c_vp]),
 }
 

@@ -194,4 +194,43 @@ int mc3d_triangulate_host_f64(const double *h_kpts, int64_t n, const mc3d_rig *r
     return mc3d::triangulate_host<double>(h_kpts, n, rig, layout, mode, flags, h_out, device);
 }
 
+// ---- peer memory (in-kernel refinement exchange) ------------------------------------------------------------
+int mc3d_peer_alloc(int64_t bytes, void **d_ptr, unsigned char *handle) {
+    if (bytes <= 0 || !d_ptr || !handle) { mc3d::set_error("mc3d_peer_alloc: bad arguments"); return MC3D_ERR_INVALID_ARGUMENT; }
+    static_assert(sizeof(cudaIpcMemHandle_t) <= MC3D_IPC_HANDLE_BYTES, "IPC handle size");
+    void *p = nullptr;
+    MC3D_CUDA_TRY(cudaMalloc(&p, (size_t)bytes));
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(p); return mc3d::cuda_fail(e, "mc3d_peer_alloc"); }
+    memset(handle, 0, MC3D_IPC_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    *d_ptr = p;
+    return MC3D_OK;
+}
+
+int mc3d_peer_open(const unsigned char *handle, void **d_ptr) {
+    if (!handle || !d_ptr) { mc3d::set_error("mc3d_peer_open: bad arguments"); return MC3D_ERR_INVALID_ARGUMENT; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    MC3D_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = p;
+    return MC3D_OK;
+}
+
+int mc3d_peer_close(void *d_ptr) {
+    if (!d_ptr) return MC3D_OK;
+    MC3D_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return MC3D_OK;
+}
+
+int mc3d_peer_free(void *d_ptr) {
+    if (!d_ptr) return MC3D_OK;
+    MC3D_CUDA_TRY(cudaFree(d_ptr));
+    return MC3D_OK;
+}
+
 }  // extern "C"

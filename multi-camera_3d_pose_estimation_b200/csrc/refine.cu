@@ -36,9 +36,7 @@ struct RefineDerived {
     bool stopped;
 };
 
-__device__ __forceinline__ RefineDerived derive(const mc3d_refine_problem &pb, const double *ctrl, int parity) {
-    const double *acc = ctrl + CT_ACC + 16 * parity;
-    const double *st = ctrl + CT_STATE + 16 * parity;
+__device__ __forceinline__ RefineDerived derive(const mc3d_refine_problem &pb, const double *acc, const double *st) {
     RefineDerived d;
     d.stopped = st[5] != 0.0;
     const double nl = acc[1], ns = acc[3];
@@ -51,6 +49,88 @@ __device__ __forceinline__ RefineDerived derive(const mc3d_refine_problem &pb, c
     d.cost_b = pb.lambda_body > 0.0 ? pb.lambda_body * (acc[6] - 2.0 * d.mu * acc[4] + d.mu * d.mu * acc[5]) / pb.aa : 0.0;
     d.total = d.cost_lik + d.cost_s + d.cost_b;
     return d;
+}
+
+// ---- in-kernel exchange over peer memory (include/mc3d.h: mc3d_refine_xchg) ---------------------------------------
+// Push model: a rank stores its contribution into every peer's block and then a sequence flag (release, system
+// scope); consumers spin on flags in their OWN memory (acquire, system scope).  Flags carry the Adam step count, so
+// nothing is ever reset and a replayed CUDA graph needs no per-step argument.
+__device__ __forceinline__ bool xchg_on(const mc3d_refine_problem &pb) { return pb.xchg[pb.rank] != nullptr; }
+__device__ __forceinline__ mc3d_refine_xchg *xchg_of(const mc3d_refine_problem &pb, int r) {
+    return reinterpret_cast<mc3d_refine_xchg *>(pb.xchg[r]);
+}
+__device__ __forceinline__ long long ld_acquire_sys(const int64_t *p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int64_t *p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait until *flag >= target.  A peer that never arrives must not hang the GPU: give up after the timeout, mark the
+// local block as failed (the host checks it after the run) and carry on with whatever is there.
+__device__ __noinline__ void xchg_wait(const mc3d_refine_problem &pb, const int64_t *flag, long long target) {
+    if (ld_acquire_sys(flag) >= target) return;
+    const unsigned long long t0 = globaltimer_ns();
+    const unsigned long long limit = pb.spin_timeout_ns > 0 ? (unsigned long long)pb.spin_timeout_ns : 10000000000ULL;
+    while (ld_acquire_sys(flag) < target) {
+        __nanosleep(40);
+        if (globaltimer_ns() - t0 > limit) {
+            xchg_of(pb, pb.rank)->error = 1;
+            __threadfence_system();
+            return;
+        }
+    }
+}
+
+// Last block of a phase: store N partial sums (acc[0..N)) into slot sums[parity][rank][OFF..] of EVERY rank, then the
+// flag.  `ticket` counts finished blocks and is reset by the last one for the next launch.
+template <int N, int OFF>
+__device__ __forceinline__ void xchg_publish(const mc3d_refine_problem &pb, int parity, const double *acc, int ticket_idx,
+                                             bool grad_flag, long long seq) {
+    __shared__ int is_last;
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&mine->ticket[ticket_idx]), 1ULL);
+        is_last = old == (unsigned long long)gridDim.x - 1ULL;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    if (threadIdx.x == 0) mine->ticket[ticket_idx] = 0;
+    __threadfence();
+    if (threadIdx.x < N) {
+        const double v = __ldcg(acc + threadIdx.x);
+        for (int r = 0; r < pb.world; ++r) xchg_of(pb, r)->sums[parity][pb.rank][OFF + threadIdx.x] = v;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int r = 0; r < pb.world; ++r) {
+            mc3d_refine_xchg *xr = xchg_of(pb, r);
+            st_release_sys(grad_flag ? &xr->seq_grad[parity][pb.rank] : &xr->seq_costs[parity][pb.rank], seq);
+        }
+}
+
+// Totals over ranks of sums[parity][*][0..N) into tot[] (shared), added in rank order on every rank.
+template <int N>
+__device__ __forceinline__ void xchg_gather(const mc3d_refine_problem &pb, int parity, bool grad_flag, long long seq, double *tot) {
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    if (threadIdx.x == 0)
+        for (int r = 0; r < pb.world; ++r)
+            xchg_wait(pb, grad_flag ? &mine->seq_grad[parity][r] : &mine->seq_costs[parity][r], seq);
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double s = 0.0;
+        for (int r = 0; r < pb.world; ++r) s += __ldcg(&mine->sums[parity][r][threadIdx.x]);
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
 }
 
 // Arithmetic type of the per-element maths: the state dtype (float state -> float arithmetic, as upstream's torch
@@ -214,6 +294,13 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
     __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
     double *ctrl = pb.ctrl;
     if (ctrl[CT_STATE + 16 * parity + 5] != 0.0) return;          // stopped
+    const bool xchg = xchg_on(pb);
+    const long long adam_step = (long long)ctrl[CT_STATE + 16 * parity];
+    if (xchg && threadIdx.x == 0) {                                // the neighbours' boundary frames of this step are in my halo
+        mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+        if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], adam_step);
+        if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], adam_step);
+    }
     load_tables(tb, pb);
     for (int i = threadIdx.x; i < pb.n_cams * CAM_STRIDE; i += blockDim.x)
         camf[i] = (i % CAM_STRIDE) < 26 ? (T)pb.cams[i / CAM_STRIDE][i % CAM_STRIDE] : (T)0;
@@ -265,6 +352,7 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
 #pragma unroll
     for (int i = 0; i < 7; ++i) acc[i] = (double)accf[i];
     block_reduce_add<7>(acc, red, ctrl + CT_ACC + 16 * parity);
+    if (xchg) xchg_publish<7, 0>(pb, parity, ctrl + CT_ACC + 16 * parity, 0, false, adam_step + 1);
 }
 
 // ---- kernel B: gradient ---------------------------------------------------------------------------------------
@@ -274,9 +362,14 @@ refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
     __shared__ double red[8];
     __shared__ RefineTables tb;
     __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
+    __shared__ double tot[8];
     double *ctrl = pb.ctrl;
-    const RefineDerived dv = derive(pb, ctrl, parity);
-    if (dv.stopped) return;
+    const double *state = ctrl + CT_STATE + 16 * parity;
+    if (state[5] != 0.0) return;                                   // stopped
+    const bool xchg = xchg_on(pb);
+    const long long adam_step = (long long)state[0];
+    if (xchg) xchg_gather<7>(pb, parity, false, adam_step + 1, tot);
+    const RefineDerived dv = derive(pb, xchg ? tot : ctrl + CT_ACC + 16 * parity, state);
     load_tables(tb, pb);
     for (int i = threadIdx.x; i < pb.n_cams * CAM_STRIDE; i += blockDim.x)
         camf[i] = (i % CAM_STRIDE) < 26 ? (T)pb.cams[i / CAM_STRIDE][i % CAM_STRIDE] : (T)0;
@@ -347,23 +440,29 @@ refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
     }
     double gn[1] = {(double)gnf};
     block_reduce_add<1>(gn, red, ctrl + CT_ACC + 16 * parity + 7);
+    if (xchg) xchg_publish<1, 7>(pb, parity, ctrl + CT_ACC + 16 * parity + 7, 1, true, adam_step + 1);
 }
 
 // ---- kernel C: clip + Adam + bookkeeping ------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(RF_THREADS)
 refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, int end_of_iteration) {
+    __shared__ double tot[8];
     double *ctrl = pb.ctrl;
-    const RefineDerived dv = derive(pb, ctrl, parity);
-    if (dv.stopped) {
+    const double *st = ctrl + CT_STATE + 16 * parity;
+    if (st[5] != 0.0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {                 // carry the stopped state forward
             for (int i = 0; i < 16; ++i) ctrl[CT_STATE + 16 * (parity ^ 1) + i] = ctrl[CT_STATE + 16 * parity + i];
             for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
         }
         return;
     }
-    const double *st = ctrl + CT_STATE + 16 * parity;
-    const double gnorm = sqrt(ctrl[CT_ACC + 16 * parity + 7]);
+    const bool xchg = xchg_on(pb);
+    const long long adam_step = (long long)st[0];
+    if (xchg) xchg_gather<8>(pb, parity, true, adam_step + 1, tot);     // every rank has finished its gradient pass
+    const double *acc = xchg ? tot : ctrl + CT_ACC + 16 * parity;
+    const RefineDerived dv = derive(pb, acc, st);
+    const double gnorm = sqrt(acc[7]);
     const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
     const double step = st[0] + 1.0;
     double run_sum = st[1] + dv.total, run_cnt = st[2] + 1.0;
@@ -404,6 +503,18 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
     struct alignas(2 * sizeof(T)) Vec2 { T a, b; };
     const long long n2 = n >> 1;
     const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    // in-kernel exchange: my first / last two frames are the neighbours' halo frames -- store them there directly
+    const long long halo_n = 2 * per_frame;
+    T *left_halo = nullptr, *right_halo = nullptr;
+    if (xchg && pb.rank > 0)                   // right halo of rank - 1: its frames n_left + 2, n_left + 3
+        left_halo = reinterpret_cast<T *>(reinterpret_cast<char *>(pb.xchg[pb.rank - 1]) + MC3D_XCHG_X_OFFSET) + (pb.n_frames_left + 2) * per_frame;
+    if (xchg && pb.rank < pb.world - 1)        // left halo of rank + 1: its frames 0, 1
+        right_halo = reinterpret_cast<T *>(reinterpret_cast<char *>(pb.xchg[pb.rank + 1]) + MC3D_XCHG_X_OFFSET);
+    bool pushed = false;
+    auto push = [&](long long i, T xi) {
+        if (left_halo && i < halo_n) { left_halo[i] = xi; pushed = true; }
+        if (right_halo && i >= n - halo_n) { right_halo[i - (n - halo_n)] = xi; pushed = true; }
+    };
     for (long long i2 = tid0; i2 < n2; i2 += nthr) {
         const long long i = i2 << 1;
         Vec2 gv = reinterpret_cast<const Vec2 *>(g)[i2];
@@ -416,6 +527,7 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
         reinterpret_cast<Vec2 *>(v)[i2] = vv;
         reinterpret_cast<Vec2 *>(x)[i2] = xv;
         if (improved) reinterpret_cast<Vec2 *>(bestx)[i2] = xv;
+        if (xchg) { push(i, xv.a); push(i + 1, xv.b); }
     }
     if ((n & 1) && tid0 == 0) {                                    // odd tail
         const long long i = n - 1;
@@ -423,6 +535,24 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
         adam(gi, mi, vi, xi);
         m[i] = mi; v[i] = vi; x[i] = xi;
         if (improved) bestx[i] = xi;
+        if (xchg) push(i, xi);
+    }
+    if (xchg && pb.world > 1) {                                    // flag the halos once every block's stores are out
+        __shared__ int is_last;
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&mine->ticket[2]), 1ULL);
+            is_last = old == (unsigned long long)gridDim.x - 1ULL;
+            if (is_last) {
+                mine->ticket[2] = 0;
+                __threadfence_system();
+                if (pb.rank > 0) st_release_sys(&xchg_of(pb, pb.rank - 1)->halo_seq[1], adam_step + 1);
+                if (pb.rank < pb.world - 1) st_release_sys(&xchg_of(pb, pb.rank + 1)->halo_seq[0], adam_step + 1);
+            }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         double *nx = ctrl + CT_STATE + 16 * (parity ^ 1);
@@ -505,6 +635,22 @@ static int validate(const mc3d_refine_problem *pb) {
     if (!pb->x || !pb->m || !pb->v || !pb->best || !pb->g || !pb->mu0 || !pb->S || !pb->term_ok || !pb->ctrl) {
         set_error("NULL device pointer in refine problem");
         return MC3D_ERR_INVALID_ARGUMENT;
+    }
+    if (pb->xchg[0] || pb->world != 0 || pb->rank != 0) {
+        if (pb->world < 1 || pb->world > MC3D_MAX_PEERS || pb->rank < 0 || pb->rank >= pb->world) {
+            set_error("in-kernel exchange: rank %d / world %d outside [0, %d]", pb->rank, pb->world, MC3D_MAX_PEERS);
+            return MC3D_ERR_INVALID_ARGUMENT;
+        }
+        for (int r = 0; r < pb->world; ++r)
+            if (!pb->xchg[r]) { set_error("in-kernel exchange: xchg[%d] is NULL", r); return MC3D_ERR_INVALID_ARGUMENT; }
+        if ((char *)pb->x != (char *)pb->xchg[pb->rank] + MC3D_XCHG_X_OFFSET) {
+            set_error("in-kernel exchange: x must sit at byte %d of this rank's exchange allocation", MC3D_XCHG_X_OFFSET);
+            return MC3D_ERR_INVALID_ARGUMENT;
+        }
+        if (pb->world > 1 && (pb->n_frames < 2 || (pb->rank > 0 && pb->n_frames_left < 2))) {
+            set_error("in-kernel exchange: every rank needs at least two frames");
+            return MC3D_ERR_INVALID_ARGUMENT;
+        }
     }
     for (int k = 0; k < pb->n_bones; ++k)
         if (pb->bone_start[k] < 0 || pb->bone_start[k] >= pb->n_joints || pb->bone_end[k] < 0 || pb->bone_end[k] >= pb->n_joints) {

@@ -245,6 +245,7 @@ class Optimized_3d_Pose_Estimation:
         self.trajectory = engine.trajectory().cpu()
         improved_once = math.isfinite(st['best'])
         self.best_trajectory = engine.best_trajectory().cpu() if improved_once else None
+        engine.close()                       # sharded runs: unmap the peers' exchange blocks (collective)
         self.best_decomposed_cam_params = {k: [p.clone().detach() for p in self.decomposed_cam_params[k]]
                                            for k in self.decomposed_cam_params} if improved_once else None
         self.all_costs_total = {}

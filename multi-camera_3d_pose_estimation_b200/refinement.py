@@ -10,8 +10,13 @@ process per GPU) frames are sharded contiguously and the ONLY traffic per step i
     after phase 1:                  all-reduce of 1 double (sum g^2)
 
 so every rank takes identical clip / Adam / early-stopping decisions with no further communication
-(SURVEY.md section 8e).  The collectives are injected (``comm``) so the same driver runs over NCCL on GPUs and
-over gloo on CPU tensors in the tests.
+(SURVEY.md section 8e).  On GPUs that exchange happens INSIDE the kernels over NVLink peer memory (``PeerExchange``,
+csrc/refine.cu ``xchg_*``): every rank maps every other rank's exchange block through CUDA IPC, partial sums and
+boundary frames are stored straight into the peers' memory followed by a sequence flag, and consumers spin on flags in
+their own memory -- no NCCL call and no host work per step, so any number of steps replays from one CUDA graph.
+``torch.distributed`` is only used once, to hand the IPC handles round and for the initial halo.  The host-driven
+variant (collectives injected through ``comm``) remains for CPU tensors -- the gloo tests of the sharding logic -- and
+as ``MC3D_REFINE_PEER=0``.
 """
 import ctypes
 import math
@@ -85,6 +90,12 @@ class LocalComm:
     """Single-process stand-in for the collectives."""
     rank, world = 0, 1
 
+    def all_gather_object(self, obj):
+        return [obj]
+
+    def barrier(self):
+        pass
+
     def all_reduce_sum(self, t):
         return t
 
@@ -109,6 +120,14 @@ class DistComm:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def all_gather_object(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
     # The halo traffic is a few hundred bytes per rank, so it rides on all_gather (a plain collective that CUDA
     # graphs capture reliably) instead of point-to-point sends: every rank contributes its two first and two last
     # frames and picks its neighbours' out of the gathered block.
@@ -116,8 +135,9 @@ class DistComm:
         """x_ext (n_local + 4, J, 3): fill the two halo frames at each end with the neighbours' boundary frames."""
         torch = self._torch()
         mine = torch.cat([x_ext[2:4], x_ext[n_local:n_local + 2]], dim=0).contiguous()        # (4, J, 3)
-        out = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        flat = torch.empty((self.world * 4,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        self.dist.all_gather_into_tensor(flat, mine, group=self.group)
+        out = flat.view((self.world, 4) + tuple(mine.shape[1:]))
         if self.rank > 0:
             x_ext[0:2] = out[self.rank - 1, 2:4]
         if self.rank < self.world - 1:
@@ -129,51 +149,6 @@ class DistComm:
         return torch
 
     def all_gather_frames(self, local, total_frames):
-        return local
-
-
-class DistComm:
-    """torch.distributed collectives for the frame-sharded refinement (NCCL on GPUs, gloo on CPU tensors)."""
-
-    def __init__(self, group=None):
-        import torch.distributed as dist
-        self.dist = dist
-        self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
-
-    def all_reduce_sum(self, t):
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
-        return t
-
-    def _sendrecv(self, ops):
-        if ops:
-            for req in self.dist.batch_isend_irecv(ops):
-                req.wait()
-
-    def exchange_halo(self, x_ext, n_local):
-        """x_ext (n_local + 4, J, 3): send my first / last two frames, receive the neighbours' into the halo."""
-        P2P = self.dist.P2POp
-        ops = []
-        if self.rank > 0:
-            ops.append(P2P(self.dist.isend, x_ext[2:4].contiguous(), self.rank - 1, self.group))
-            ops.append(P2P(self.dist.irecv, x_ext[0:2], self.rank - 1, self.group))
-        if self.rank < self.world - 1:
-            ops.append(P2P(self.dist.isend, x_ext[n_local:n_local + 2].contiguous(), self.rank + 1, self.group))
-            ops.append(P2P(self.dist.irecv, x_ext[n_local + 2:n_local + 4], self.rank + 1, self.group))
-        self._sendrecv(ops)
-
-    def exchange_term_ok(self, term_ok, n_local):
-        """The smoothness terms ending at my first two frames are needed by the left neighbour's gradient."""
-        P2P = self.dist.P2POp
-        ops = []
-        if self.rank > 0:
-            ops.append(P2P(self.dist.isend, term_ok[2:4].contiguous(), self.rank - 1, self.group))
-        if self.rank < self.world - 1:
-            ops.append(P2P(self.dist.irecv, term_ok[n_local + 2:n_local + 4], self.rank + 1, self.group))
-        self._sendrecv(ops)
-
-    def all_gather_frames(self, local, total_frames):
         import torch
         sizes = [frame_shard(total_frames, r, self.world) for r in range(self.world)]
         longest = max(e - b for b, e in sizes)
@@ -182,6 +157,71 @@ class DistComm:
         out = [torch.empty_like(pad) for _ in range(self.world)]
         self.dist.all_gather(out, pad, group=self.group)
         return torch.cat([o[:e - b] for o, (b, e) in zip(out, sizes)], dim=0)
+
+
+class _DeviceBytes:
+    """Library-owned device memory exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {'shape': (int(nbytes),), 'typestr': '|u1', 'data': (int(ptr), False), 'version': 2}
+
+
+class PeerExchange:
+    """One rank's exchange allocation (mc3d_refine_xchg header + the halo-extended trajectory) and the peers' mappings.
+
+    Layout and protocol: include/mc3d.h (``mc3d_refine_xchg``), csrc/refine.cu (``xchg_publish`` / ``xchg_gather``)."""
+
+    def __init__(self, comm, device, x_bytes):
+        import torch
+        self.torch, self.comm, self.device = torch, comm, device
+        self.lib = _lib.lib()
+        self.nbytes = (_lib.XCHG_X_OFFSET + int(x_bytes) + 255) // 256 * 256
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.mc3d_peer_alloc(self.nbytes, ctypes.byref(ptr), handle))
+            self.local_ptr = ptr.value
+            self.bytes_view = torch.as_tensor(_DeviceBytes(self.local_ptr, self.nbytes), device=device)
+            self.ptrs = [None] * comm.world
+            self.ptrs[comm.rank] = self.local_ptr
+            self._opened = []
+            if comm.world > 1:
+                if comm.world > _lib.MAX_PEERS:
+                    raise ValueError(f'at most {_lib.MAX_PEERS} ranks are supported by the in-kernel exchange')
+                handles = comm.all_gather_object(bytes(handle))
+                for r, h in enumerate(handles):
+                    if r == comm.rank:
+                        continue
+                    p = ctypes.c_void_p()
+                    hb = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                    _lib.check(self.lib.mc3d_peer_open(hb, ctypes.byref(p)))
+                    self.ptrs[r] = p.value
+                    self._opened.append(p.value)
+
+    def x_view(self, shape, dtype):
+        """The trajectory tensor living at byte XCHG_X_OFFSET of the local allocation."""
+        n = int(np.prod(shape)) * self.torch.empty((), dtype=dtype).element_size()
+        return self.bytes_view[_lib.XCHG_X_OFFSET:_lib.XCHG_X_OFFSET + n].view(dtype).view(*shape)
+
+    def error(self):
+        """True when a wait on a peer timed out in some kernel of this rank."""
+        head = self.bytes_view[:ctypes.sizeof(_lib.RefineXchg)].cpu().numpy().tobytes()
+        return _lib.RefineXchg.from_buffer_copy(head).error != 0
+
+    def close(self):
+        """Collective: nobody unmaps or frees while a peer may still store into the block."""
+        if self.local_ptr is None:
+            return
+        with self.torch.cuda.device(self.device):
+            self.torch.cuda.synchronize()
+            self.comm.barrier()
+            for p in self._opened:
+                self.lib.mc3d_peer_close(p)
+            self._opened = []
+            self.comm.barrier()
+            self.bytes_view = None
+            self.lib.mc3d_peer_free(self.local_ptr)
+            self.local_ptr = None
 
 
 class CudaPhases:
@@ -226,7 +266,19 @@ class RefineEngine:
         dev, dt = self.device, torch_dtype
 
         traj = torch.as_tensor(trajectory).to(dt)
-        self.x_ext = torch.zeros((n + 4, self.J, 3), dtype=dt, device=dev)
+        # GPUs: the kernels exchange sums and halo frames themselves over peer memory, and the trajectory lives in
+        # the exchange allocation.  MC3D_REFINE_PEER=1 forces that path on one GPU (tests), =0 the host-driven one.
+        mode = os.environ.get('MC3D_REFINE_PEER', '')
+        self.peer = None
+        if dev.type == 'cuda' and phases is None and mode != '0' and (self.comm.world > 1 or mode == '1'):
+            if self.comm.world > 1 and min(frame_shard(self.total_frames, r, self.comm.world)[1] -
+                                           frame_shard(self.total_frames, r, self.comm.world)[0]
+                                           for r in range(self.comm.world)) < 2:
+                raise ValueError('the frame-sharded refinement needs at least two frames per rank')
+            self.peer = PeerExchange(self.comm, dev, (n + 4) * self.J * 3 * torch.empty((), dtype=dt).element_size())
+            self.x_ext = self.peer.x_view((n + 4, self.J, 3), dt)
+        else:
+            self.x_ext = torch.zeros((n + 4, self.J, 3), dtype=dt, device=dev)
         self.x_ext[2:n + 2] = traj[self.begin:self.end].to(dev)
         self.m = torch.zeros((n, self.J, 3), dtype=dt, device=dev)
         self.v = torch.zeros_like(self.m)
@@ -283,6 +335,14 @@ class RefineEngine:
         for name in ('m', 'v', 'best', 'g', 'mu0', 'S', 'term_ok', 'ctrl'):
             setattr(pb, name, getattr(self, name).data_ptr())
         pb.x = self.x_ext.data_ptr()
+        if self.peer is not None:
+            pb.rank, pb.world = self.comm.rank, self.comm.world
+            if self.comm.rank > 0:
+                lb, le = frame_shard(self.total_frames, self.comm.rank - 1, self.comm.world)
+                pb.n_frames_left = le - lb
+            pb.spin_timeout_ns = int(float(os.environ.get('MC3D_REFINE_SPIN_TIMEOUT_S', '10')) * 1e9)
+            for r, p in enumerate(self.peer.ptrs):
+                pb.xchg[r] = p
         self.phases = phases or CudaPhases(self.tag)
         self.step = 0
         self.use_graph = os.environ.get('MC3D_REFINE_GRAPH', '1') != '0'      # multi-rank CUDA-graph replay
@@ -315,25 +375,26 @@ class RefineEngine:
         p = self.step & 1
         acc = self.ctrl[_lib.CT_ACC + 16 * p:_lib.CT_ACC + 16 * p + 8]
         st = self._stream()
+        host_exchange = self.comm.world > 1 and self.peer is None
         self.phases.phase(self.problem, 0, self.step, end_of_iteration, st)
-        if self.comm.world > 1:
+        if host_exchange:
             self.comm.all_reduce_sum(acc[0:7])
         self.phases.phase(self.problem, 1, self.step, end_of_iteration, st)
-        if self.comm.world > 1:
+        if host_exchange:
             self.comm.all_reduce_sum(acc[7:8])
         self.phases.phase(self.problem, 2, self.step, end_of_iteration, st)
-        if self.comm.world > 1:
+        if host_exchange:
             self.comm.exchange_halo(self.x_ext, self.n_local)
         self.step += 1
 
     def run(self, n_iters):
         """``n_iters`` whole-window iterations.
 
-        One rank: a single C call replaying a CUDA graph of the three kernels.  Several ranks (NCCL): two
-        consecutive steps -- kernels, the two all-reduces and the halo exchanges -- are captured once into a CUDA
-        graph and replayed, so the per-step cost is GPU-side latency only (no Python / NCCL launch overhead)."""
+        One rank, or several ranks with the in-kernel exchange: a single C call replaying a CUDA graph of the three
+        kernels (the ranks meet inside the kernels).  Host-driven exchange over NCCL: two consecutive steps --
+        kernels, the two all-reduces and the halo exchanges -- are captured once into a CUDA graph and replayed."""
         n_iters = int(n_iters)
-        if self.comm.world == 1 and hasattr(self.phases, 'run') and self.device.type == 'cuda':
+        if (self.comm.world == 1 or self.peer is not None) and hasattr(self.phases, 'run') and self.device.type == 'cuda':
             with self.torch.cuda.device(self.device):
                 self.phases.run(self.problem, self.step, n_iters, self._stream())
             self.step += n_iters
@@ -380,6 +441,22 @@ class RefineEngine:
             self.torch.cuda.synchronize()
             self._graph = None
 
+    def close(self):
+        """Collective when sharded: release the graph and the peer mappings.  The trajectory tensors read back before
+        this call stay valid only if they were copied (``trajectory()`` / ``best_trajectory()`` return copies)."""
+        self.release_graph()
+        if self.peer is not None:
+            if self.peer.error():
+                self.peer.close()
+                self.peer = None
+                raise _lib.Mc3dError('a wait on a peer rank timed out inside a refinement kernel (results are invalid)')
+            self.x_ext = self.x_ext.clone()
+            self.problem.x = self.x_ext.data_ptr()
+            for r in range(_lib.MAX_PEERS):
+                self.problem.xchg[r] = None
+            self.peer.close()
+            self.peer = None
+
     # ---- read-back ---------------------------------------------------------------------------------------------------
     def state(self):
         """State entering the next step: dict(adam_step, best, no_improve, stopped, iterations, improved)."""
@@ -393,7 +470,7 @@ class RefineEngine:
         return self.ctrl[_lib.CT_HIST:_lib.CT_HIST + 4 * n_steps].cpu().numpy().reshape(n_steps, 4)
 
     def trajectory(self):
-        return self.comm.all_gather_frames(self.x_ext[2:self.n_local + 2], self.total_frames)
+        return self.comm.all_gather_frames(self.x_ext[2:self.n_local + 2].clone(), self.total_frames)
 
     def best_trajectory(self):
         return self.comm.all_gather_frames(self.best, self.total_frames)

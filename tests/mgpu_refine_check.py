@@ -39,32 +39,46 @@ def main():
     dbest = np.nanmax(np.abs(single.best_trajectory.numpy() - sharded.best_trajectory.numpy()))
     ok = ok and dtraj < 1e-9 and dbest < 1e-9 and tuple(sharded.trajectory.shape) == (n_frames, 17, 3)
     ok = ok and bool(np.isnan(sharded.trajectory.numpy()[1500, 7]).all())
-    # iterations per second of the sharded path (NCCL collectives between phases)
-    eng = sharded._engine
-    eng.use_graph = True
-    torch.cuda.synchronize()
-    dist.barrier()
+    ok = ok and sharded._engine.peer is None                 # sgd_optimize closed the exchange
+    # iterations per second of the sharded path: in-kernel exchange over NVLink peer memory against the host-driven
+    # NCCL exchange (CUDA graph and eager)
     import time
-    eng.run(20)                                  # captures the 2-step graph
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    eng.run(200)
-    torch.cuda.synchronize()
-    dist.barrier()
-    rate = 200 / (time.perf_counter() - t0)
+    rows = rf.camera_rows(cams, list(cams))
+
+    def engine():
+        return rf.RefineEngine(init, gs, rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=torch.float32, device=f'cuda:{local}', lr=0.01,
+                               betas=(0.9, 0.999), lambda_smooth=1e-3, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
+                               max_iter=10 ** 9, ignore_distortions=False, window=(0, n_frames), n_window_frames=n_frames,
+                               hist_capacity=64, comm=rf.DistComm())
+
+    def rate_of(eng, n):
+        eng.run(20)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        eng.run(n)
+        torch.cuda.synchronize()
+        dist.barrier()
+        return n / (time.perf_counter() - t0)
+
+    eng = engine()
+    peer_on = eng.peer is not None
+    rate_peer = rate_of(eng, 400)
+    eng.close()
+    os.environ['MC3D_REFINE_PEER'] = '0'
+    eng = engine()
+    rate = rate_of(eng, 200)
+    graph_on = eng._graph is not None
     eng.use_graph = False
-    t0 = time.perf_counter()
-    eng.run(50)
-    torch.cuda.synchronize()
-    dist.barrier()
-    rate_eager = 50 / (time.perf_counter() - t0)
-    eng.release_graph()
+    rate_eager = rate_of(eng, 50)
+    eng.close()
+    del os.environ['MC3D_REFINE_PEER']
     flag = torch.tensor([1.0 if ok else 0.0], device=f'cuda:{local}')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f'MGPU_REFINE world={dist.get_world_size()} ok={bool(flag.item())} dtraj={dtraj:.2e} dbest={dbest:.2e} '
-              f'hist_rel={np.max(np.abs(h1 - h2) / np.abs(h1)):.2e} sharded_iters_per_s={rate:.0f} (graph={eng._graph is not None}) eager={rate_eager:.0f}')
+              f'hist_rel={np.max(np.abs(h1 - h2) / np.abs(h1)):.2e} peer_exchange={peer_on} iters_per_s: in-kernel={rate_peer:.0f} '
+              f'nccl_graph={rate:.0f} (graph={graph_on}) nccl_eager={rate_eager:.0f}')
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 

@@ -84,6 +84,46 @@ def test_sgd_optimize_matches_reference_runs(pr, syn, run, tag, capsys):
         assert 'Early stopping at iteration' in out
 
 
+@pytest.mark.parametrize('dt_name', ['f64', 'f32'])
+def test_in_kernel_exchange_path_on_one_gpu(pr, syn, dt_name, monkeypatch):
+    """MC3D_REFINE_PEER=1 runs the NVLink peer-memory protocol (tickets, sequence flags, rank-ordered sums, csrc/refine.cu
+    xchg_*) with this GPU as its own only peer: the cost history and trajectories must equal the plain path."""
+    import torch
+    dt = torch.float64 if dt_name == 'f64' else torch.float32
+    gs, init, cams, _ = syn.refinement_inputs(120, n_cams=2, seed=23)
+    init[40, 3] = np.nan
+    kw = dict(lr=0.01, lambda_smooth=1e-3, lambda_body_length=1.0, max_iter=60, time_interval=[0, 120], patience=10 ** 6,
+              print_frequency=np.inf)
+
+    def run():
+        opt = pr.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(), decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                              body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+        opt.sgd_optimize(**kw)
+        return opt
+
+    plain = run()
+    assert plain._engine.peer is None
+    monkeypatch.setenv('MC3D_REFINE_PEER', '1')
+    from mc3d_b200 import refinement as rf
+    made = []
+    orig = rf.PeerExchange.__init__
+
+    def spy(self, *a, **k):
+        made.append(1)
+        orig(self, *a, **k)
+    monkeypatch.setattr(rf.PeerExchange, '__init__', spy)
+    peer = run()
+    assert made, 'the in-kernel exchange path was not taken'
+    h1 = np.array([float(v) for v in plain.all_costs_total['total_cost']])
+    h2 = np.array([float(v) for v in peer.all_costs_total['total_cost']])
+    # not bitwise: the block partial sums are added with double atomics in arrival order on either path
+    rtol, atol = (1e-11, 1e-9) if dt_name == 'f64' else (1e-6, 1e-3)
+    assert len(h1) == len(h2) == 122 and np.allclose(h1, h2, rtol=rtol, atol=0)
+    assert np.allclose(plain.trajectory.numpy(), peer.trajectory.numpy(), rtol=0, atol=atol, equal_nan=True)
+    assert np.allclose(plain.best_trajectory.numpy(), peer.best_trajectory.numpy(), rtol=0, atol=atol, equal_nan=True)
+    assert np.isnan(peer.trajectory.numpy()[40, 3]).all()
+
+
 def test_gradient_kernel_matches_oracle(pr, syn):
     import torch
     from mc3d_b200 import refinement as rf
