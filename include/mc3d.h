@@ -196,6 +196,7 @@ typedef struct {
     int64_t seq_grad[2][MC3D_MAX_PEERS];    /* the same for gnorm^2 */
     int64_t halo_seq[2];                    /* adam step count the left / right halo frames belong to */
     int64_t ticket[4];                      /* block tickets of phases 0, 1, 2 (local) */
+    int64_t gen[4];                         /* persistent kernel: grid-barrier generation of phases 0, 1, 2 (local) */
     int64_t error;                          /* != 0: a wait timed out (results are invalid) */
 } mc3d_refine_xchg;
 
@@ -215,7 +216,11 @@ int mc3d_refine_flags_f64(const mc3d_refine_problem *pb, void *stream);
 int mc3d_refine_problem_size(void);
 int mc3d_refine_phase_f32(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream);
 int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream);
-/* n_iters whole-window iterations (phases 0,1,2 each) on one GPU, replayed from a CUDA graph. */
+/* n_iters whole-window iterations (phases 0,1,2 each), replayed from a CUDA graph of the three kernels.  With the
+ * in-kernel exchange (xchg set, any world size) the iterations run instead inside ONE persistent cooperative kernel:
+ * the three phases are separated by grid barriers (the last block to arrive does the cross-rank exchange), the
+ * cameras and bone tables stay in shared memory, and there is no launch boundary per phase (MC3D_REFINE_FUSED=0 in
+ * the environment selects the graph of three kernels).  Every rank must call it with the same arguments. */
 int mc3d_refine_run_f32(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
 int mc3d_refine_run_f64(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
 

@@ -65,7 +65,8 @@ class RefineXchg(ctypes.Structure):
     """mc3d_refine_xchg (include/mc3d.h): head of a rank's peer allocation."""
     _fields_ = [('sums', ((ctypes.c_double * 8) * MAX_PEERS) * 2),
                 ('seq_costs', (ctypes.c_int64 * MAX_PEERS) * 2), ('seq_grad', (ctypes.c_int64 * MAX_PEERS) * 2),
-                ('halo_seq', ctypes.c_int64 * 2), ('ticket', ctypes.c_int64 * 4), ('error', ctypes.c_int64)]
+                ('halo_seq', ctypes.c_int64 * 2), ('ticket', ctypes.c_int64 * 4), ('gen', ctypes.c_int64 * 4),
+                ('error', ctypes.c_int64)]
 
 
 _lib = None

@@ -18,6 +18,8 @@
 // block.  The arithmetic type is the state dtype (float state -> float maths, as upstream's float32 run).
 #include "mc3d_common.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <type_traits>
 
 namespace mc3d {
 
@@ -59,27 +61,31 @@ __device__ __forceinline__ bool xchg_on(const mc3d_refine_problem &pb) { return 
 __device__ __forceinline__ mc3d_refine_xchg *xchg_of(const mc3d_refine_problem &pb, int r) {
     return reinterpret_cast<mc3d_refine_xchg *>(pb.xchg[r]);
 }
-__device__ __forceinline__ long long ld_acquire_sys(const int64_t *p) {
+__device__ __forceinline__ long long ld_relaxed_sys(const int64_t *p) {
     long long v;
-    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(int64_t *p, long long v) {
-    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(int64_t *p, long long v) {
+    asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// one rank only: nothing leaves this GPU, device scope is enough
+__device__ __forceinline__ void fence_xchg(const mc3d_refine_problem &pb) { if (pb.world > 1) fence_sys(); else fence_gpu(); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// Wait until *flag >= target.  A peer that never arrives must not hang the GPU: give up after the timeout, mark the
-// local block as failed (the host checks it after the run) and carry on with whatever is there.
+// Wait until *flag >= target with relaxed polls; the caller fences ONCE after its last wait (acquire pattern).
+// A peer that never arrives must not hang the GPU: give up after the timeout, mark the local block as failed (the
+// host checks it after the run) and carry on with whatever is there.
 __device__ __noinline__ void xchg_wait(const mc3d_refine_problem &pb, const int64_t *flag, long long target) {
-    if (ld_acquire_sys(flag) >= target) return;
+    if (ld_relaxed_sys(flag) >= target) return;
     const unsigned long long t0 = globaltimer_ns();
     const unsigned long long limit = pb.spin_timeout_ns > 0 ? (unsigned long long)pb.spin_timeout_ns : 10000000000ULL;
-    while (ld_acquire_sys(flag) < target) {
-        __nanosleep(40);
+    while (ld_relaxed_sys(flag) < target) {
         if (globaltimer_ns() - t0 > limit) {
             xchg_of(pb, pb.rank)->error = 1;
             __threadfence_system();
@@ -107,23 +113,26 @@ __device__ __forceinline__ void xchg_publish(const mc3d_refine_problem &pb, int 
     if (threadIdx.x < N) {
         const double v = __ldcg(acc + threadIdx.x);
         for (int r = 0; r < pb.world; ++r) xchg_of(pb, r)->sums[parity][pb.rank][OFF + threadIdx.x] = v;
-        __threadfence_system();
     }
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
+        fence_xchg(pb);                                            // release: the sums before the flags
         for (int r = 0; r < pb.world; ++r) {
             mc3d_refine_xchg *xr = xchg_of(pb, r);
-            st_release_sys(grad_flag ? &xr->seq_grad[parity][pb.rank] : &xr->seq_costs[parity][pb.rank], seq);
+            st_relaxed_sys(grad_flag ? &xr->seq_grad[parity][pb.rank] : &xr->seq_costs[parity][pb.rank], seq);
         }
+    }
 }
 
 // Totals over ranks of sums[parity][*][0..N) into tot[] (shared), added in rank order on every rank.
 template <int N>
 __device__ __forceinline__ void xchg_gather(const mc3d_refine_problem &pb, int parity, bool grad_flag, long long seq, double *tot) {
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         for (int r = 0; r < pb.world; ++r)
             xchg_wait(pb, grad_flag ? &mine->seq_grad[parity][r] : &mine->seq_costs[parity][r], seq);
+        fence_xchg(pb);                                            // acquire: the flags before the sums
+    }
     __syncthreads();
     if (threadIdx.x < N) {
         double s = 0.0;
@@ -286,25 +295,9 @@ struct ItemCursor {                 // (frame, joint) of a grid-stride loop with
     }
 };
 
+// The grid-stride cost loop of one rank: acc[0..7) = this thread's partial sums (widened to double).
 template <typename T>
-__global__ void __launch_bounds__(RF_THREADS)
-refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
-    __shared__ double red[8 * 7];
-    __shared__ RefineTables tb;
-    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
-    double *ctrl = pb.ctrl;
-    if (ctrl[CT_STATE + 16 * parity + 5] != 0.0) return;          // stopped
-    const bool xchg = xchg_on(pb);
-    const long long adam_step = (long long)ctrl[CT_STATE + 16 * parity];
-    if (xchg && threadIdx.x == 0) {                                // the neighbours' boundary frames of this step are in my halo
-        mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
-        if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], adam_step);
-        if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], adam_step);
-    }
-    load_tables(tb, pb);
-    for (int i = threadIdx.x; i < pb.n_cams * CAM_STRIDE; i += blockDim.x)
-        camf[i] = (i % CAM_STRIDE) < 26 ? (T)pb.cams[i / CAM_STRIDE][i % CAM_STRIDE] : (T)0;
-    __syncthreads();
+__device__ __forceinline__ void costs_loop(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, double (&acc)[7]) {
     const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones, JS = J * 3;
     const T *x = (const T *)pb.x + 2LL * JS;                       // local frame 0 (halo frames sit before / after)
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
@@ -348,32 +341,45 @@ refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
             }
         }
     }
-    double acc[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) acc[i] = (double)accf[i];
+}
+
+template <typename T>
+__device__ __forceinline__ void load_cameras_and_tables(const mc3d_refine_problem &pb, RefineTables &tb, T *camf) {
+    load_tables(tb, pb);
+    for (int i = threadIdx.x; i < pb.n_cams * CAM_STRIDE; i += blockDim.x)
+        camf[i] = (i % CAM_STRIDE) < 26 ? (T)pb.cams[i / CAM_STRIDE][i % CAM_STRIDE] : (T)0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_costs_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
+    __shared__ double red[8 * 7];
+    __shared__ RefineTables tb;
+    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
+    double *ctrl = pb.ctrl;
+    if (ctrl[CT_STATE + 16 * parity + 5] != 0.0) return;          // stopped
+    const bool xchg = xchg_on(pb);
+    const long long adam_step = (long long)ctrl[CT_STATE + 16 * parity];
+    if (xchg && threadIdx.x == 0) {                                // the neighbours' boundary frames of this step are in my halo
+        mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+        if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], adam_step);
+        if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], adam_step);
+        fence_xchg(pb);
+    }
+    load_cameras_and_tables(pb, tb, camf);
+    __syncthreads();
+    double acc[7];
+    costs_loop<T>(pb, tb, camf, acc);
     block_reduce_add<7>(acc, red, ctrl + CT_ACC + 16 * parity);
     if (xchg) xchg_publish<7, 0>(pb, parity, ctrl + CT_ACC + 16 * parity, 0, false, adam_step + 1);
 }
 
 // ---- kernel B: gradient ---------------------------------------------------------------------------------------
+// The grid-stride gradient loop of one rank: writes g, returns this thread's partial sum of g^2.
 template <typename T>
-__global__ void __launch_bounds__(RF_THREADS)
-refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
-    __shared__ double red[8];
-    __shared__ RefineTables tb;
-    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
-    __shared__ double tot[8];
-    double *ctrl = pb.ctrl;
-    const double *state = ctrl + CT_STATE + 16 * parity;
-    if (state[5] != 0.0) return;                                   // stopped
-    const bool xchg = xchg_on(pb);
-    const long long adam_step = (long long)state[0];
-    if (xchg) xchg_gather<7>(pb, parity, false, adam_step + 1, tot);
-    const RefineDerived dv = derive(pb, xchg ? tot : ctrl + CT_ACC + 16 * parity, state);
-    load_tables(tb, pb);
-    for (int i = threadIdx.x; i < pb.n_cams * CAM_STRIDE; i += blockDim.x)
-        camf[i] = (i % CAM_STRIDE) < 26 ? (T)pb.cams[i / CAM_STRIDE][i % CAM_STRIDE] : (T)0;
-    __syncthreads();
+__device__ __forceinline__ double grad_loop(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, const RefineDerived &dv) {
     const int J = pb.n_joints, C = pb.n_cams, JS = J * 3;
     const T *x = (const T *)pb.x + 2LL * JS;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
@@ -438,30 +444,38 @@ refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
         gout[e * 3 + 0] = g[0]; gout[e * 3 + 1] = g[1]; gout[e * 3 + 2] = g[2];
         gnf += g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
     }
-    double gn[1] = {(double)gnf};
+    return (double)gnf;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
+    __shared__ double red[8];
+    __shared__ RefineTables tb;
+    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
+    __shared__ double tot[8];
+    double *ctrl = pb.ctrl;
+    const double *state = ctrl + CT_STATE + 16 * parity;
+    if (state[5] != 0.0) return;                                   // stopped
+    const bool xchg = xchg_on(pb);
+    const long long adam_step = (long long)state[0];
+    if (xchg) xchg_gather<7>(pb, parity, false, adam_step + 1, tot);
+    const RefineDerived dv = derive(pb, xchg ? tot : ctrl + CT_ACC + 16 * parity, state);
+    load_cameras_and_tables(pb, tb, camf);
+    __syncthreads();
+    double gn[1] = {grad_loop<T>(pb, tb, camf, dv)};
     block_reduce_add<1>(gn, red, ctrl + CT_ACC + 16 * parity + 7);
     if (xchg) xchg_publish<1, 7>(pb, parity, ctrl + CT_ACC + 16 * parity + 7, 1, true, adam_step + 1);
 }
 
 // ---- kernel C: clip + Adam + bookkeeping ------------------------------------------------------------------------
+// Clip + Adam over this rank's elements, boundary frames stored into the neighbours' halos (in-kernel exchange), and
+// the bookkeeping for the next step (block 0).  acc: the 8 global sums of this step; st: state entering it.
+// Returns true when this thread stored into a peer's memory.
 template <typename T>
-__global__ void __launch_bounds__(RF_THREADS)
-refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, int end_of_iteration) {
-    __shared__ double tot[8];
+__device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int parity, int end_of_iteration, const double *acc,
+                                          const double *st, const RefineDerived &dv, bool xchg, double *bias, bool both_parities) {
     double *ctrl = pb.ctrl;
-    const double *st = ctrl + CT_STATE + 16 * parity;
-    if (st[5] != 0.0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) {                 // carry the stopped state forward
-            for (int i = 0; i < 16; ++i) ctrl[CT_STATE + 16 * (parity ^ 1) + i] = ctrl[CT_STATE + 16 * parity + i];
-            for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
-        }
-        return;
-    }
-    const bool xchg = xchg_on(pb);
-    const long long adam_step = (long long)st[0];
-    if (xchg) xchg_gather<8>(pb, parity, true, adam_step + 1, tot);     // every rank has finished its gradient pass
-    const double *acc = xchg ? tot : ctrl + CT_ACC + 16 * parity;
-    const RefineDerived dv = derive(pb, acc, st);
     const double gnorm = sqrt(acc[7]);
     const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
     const double step = st[0] + 1.0;
@@ -476,7 +490,6 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
         iters += 1.0;
         stop = (no_imp >= (double)pb.patience) || (iters > (double)pb.max_iter);
     }
-    __shared__ double bias[2];
     if (threadIdx.x == 0) {                                        // two double pow() per block, not per thread
         bias[0] = 1.0 - pow(pb.beta1, step);
         bias[1] = 1.0 - pow(pb.beta2, step);
@@ -537,6 +550,48 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
         if (improved) bestx[i] = xi;
         if (xchg) push(i, xi);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double *nx = ctrl + CT_STATE + 16 * (parity ^ 1);
+        nx[0] = step; nx[1] = run_sum; nx[2] = run_cnt; nx[3] = best; nx[4] = no_imp;
+        nx[5] = stop ? 1.0 : 0.0; nx[6] = iters; nx[7] = improved ? 1.0 : 0.0;
+        if (both_parities && stop)                                 // a persistent kernel leaves its loop here: the stopped
+            for (int i = 0; i < 8; ++i) ctrl[CT_STATE + 16 * parity + i] = nx[i];      // state must be found at either parity
+        for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
+        const long long hs = (long long)(step - 1.0);
+        if (hs < pb.hist_capacity) {
+            double *h = ctrl + CT_HIST + 4 * hs;
+            h[0] = dv.total; h[1] = dv.cost_lik; h[2] = dv.cost_s; h[3] = dv.cost_b;
+        }
+    }
+    return pushed;
+}
+
+// Flag the neighbours' halos once every block's stores are out (ticket 2); returns true in the last block.
+__device__ __forceinline__ void halo_flags(const mc3d_refine_problem &pb, long long seq) {
+    if (pb.rank > 0) st_relaxed_sys(&xchg_of(pb, pb.rank - 1)->halo_seq[1], seq);      // after the caller's system fence
+    if (pb.rank < pb.world - 1) st_relaxed_sys(&xchg_of(pb, pb.rank + 1)->halo_seq[0], seq);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, int end_of_iteration) {
+    __shared__ double tot[8];
+    __shared__ double bias[2];
+    double *ctrl = pb.ctrl;
+    const double *st = ctrl + CT_STATE + 16 * parity;
+    if (st[5] != 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                 // carry the stopped state forward
+            for (int i = 0; i < 16; ++i) ctrl[CT_STATE + 16 * (parity ^ 1) + i] = ctrl[CT_STATE + 16 * parity + i];
+            for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
+        }
+        return;
+    }
+    const bool xchg = xchg_on(pb);
+    const long long adam_step = (long long)st[0];
+    if (xchg) xchg_gather<8>(pb, parity, true, adam_step + 1, tot);     // every rank has finished its gradient pass
+    const double *acc = xchg ? tot : ctrl + CT_ACC + 16 * parity;
+    const RefineDerived dv = derive(pb, acc, st);
+    const bool pushed = step_loop<T>(pb, parity, end_of_iteration, acc, st, dv, xchg, bias, false);
     if (xchg && pb.world > 1) {                                    // flag the halos once every block's stores are out
         __shared__ int is_last;
         if (pushed) __threadfence_system();
@@ -548,22 +603,121 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
             is_last = old == (unsigned long long)gridDim.x - 1ULL;
             if (is_last) {
                 mine->ticket[2] = 0;
-                __threadfence_system();
-                if (pb.rank > 0) st_release_sys(&xchg_of(pb, pb.rank - 1)->halo_seq[1], adam_step + 1);
-                if (pb.rank < pb.world - 1) st_release_sys(&xchg_of(pb, pb.rank + 1)->halo_seq[0], adam_step + 1);
+                fence_sys();
+                halo_flags(pb, adam_step + 1);
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double *nx = ctrl + CT_STATE + 16 * (parity ^ 1);
-        nx[0] = step; nx[1] = run_sum; nx[2] = run_cnt; nx[3] = best; nx[4] = no_imp;
-        nx[5] = stop ? 1.0 : 0.0; nx[6] = iters; nx[7] = improved ? 1.0 : 0.0;
-        for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
-        const long long hs = (long long)(step - 1.0);
-        if (hs < pb.hist_capacity) {
-            double *h = ctrl + CT_HIST + 4 * hs;
-            h[0] = dv.total; h[1] = dv.cost_lik; h[2] = dv.cost_s; h[3] = dv.cost_b;
+}
+
+// ---- persistent kernel: n iterations of A -> B -> C with grid barriers instead of launch boundaries -------------------
+// Grid barrier + cross-rank exchange in one: every block takes a ticket; the last one publishes this rank's partial
+// sums to all peers, waits for theirs, and releases the local generation flag the other blocks spin on.  After the
+// barrier every block adds the per-rank partial sums itself (in rank order -> identical on every block and rank).
+// N sums starting at acc (local, filled by the blocks' atomics) go to slot OFF; NTOT totals come back in tot[].
+// Sum barriers: the last block publishes, and EVERY block polls the per-rank flags in its own exchange block (the
+// local rank's flag doubles as the grid barrier).  HALO barrier (closes phase C): the last block flags the
+// neighbours' halos and releases the local generation the other blocks poll.
+template <int N, int OFF, int NTOT, bool HALO>
+__device__ __forceinline__ void grid_exchange(const mc3d_refine_problem &pb, int parity, const double *acc, int idx, bool grad_flag,
+                                              long long seq, double *tot, bool pushed) {
+    __shared__ int is_last;
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    if (HALO && pushed) fence_sys();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fence_gpu();
+        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&mine->ticket[idx]), 1ULL);
+        is_last = old == (unsigned long long)gridDim.x - 1ULL;
+    }
+    __syncthreads();
+    if (is_last) {
+        if (threadIdx.x == 0) { mine->ticket[idx] = 0; fence_gpu(); }
+        if (!HALO) {
+            __syncthreads();
+            if (threadIdx.x < N) {
+                const double v = __ldcg(acc + threadIdx.x);
+                for (int r = 0; r < pb.world; ++r) xchg_of(pb, r)->sums[parity][pb.rank][OFF + threadIdx.x] = v;
+            }
+            __syncthreads();
         }
+        if (threadIdx.x == 0) {
+            fence_xchg(pb);
+            if (HALO) {
+                halo_flags(pb, seq);
+                st_relaxed_sys(&mine->gen[idx], seq);
+            } else {
+                for (int r = 0; r < pb.world; ++r) {
+                    mc3d_refine_xchg *xr = xchg_of(pb, r);
+                    st_relaxed_sys(grad_flag ? &xr->seq_grad[parity][pb.rank] : &xr->seq_costs[parity][pb.rank], seq);
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (HALO) {
+            xchg_wait(pb, &mine->gen[idx], seq);
+            fence_gpu();
+        } else {
+            for (int r = 0; r < pb.world; ++r)
+                xchg_wait(pb, grad_flag ? &mine->seq_grad[parity][r] : &mine->seq_costs[parity][r], seq);
+            fence_xchg(pb);
+        }
+    }
+    __syncthreads();
+    if (NTOT > 0) {
+        if (threadIdx.x < NTOT) {
+            double s = 0.0;
+            for (int r = 0; r < pb.world; ++r) s += __ldcg(&mine->sums[parity][r][threadIdx.x]);
+            tot[threadIdx.x] = s;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_fused_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_parity, long long n_iters) {
+    __shared__ double red[8 * 7];
+    __shared__ RefineTables tb;
+    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
+    __shared__ double tot[8];
+    __shared__ double bias[2];
+    double *ctrl = pb.ctrl;
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    load_cameras_and_tables(pb, tb, camf);
+    __syncthreads();
+    int parity = first_parity & 1;
+    for (long long it = 0; it < n_iters; ++it, parity ^= 1) {
+        double st[8];                                              // state entering this step (written before the last barrier)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st[i] = __ldcg(ctrl + CT_STATE + 16 * parity + i);
+        if (st[5] != 0.0) break;                                   // stopped: identical decision in every block and rank
+        const long long seq = (long long)st[0] + 1;
+        if (pb.world > 1) {
+            if (threadIdx.x == 0) {                                // the neighbours' boundary frames of this step are in my halo
+                if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], seq - 1);
+                if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], seq - 1);
+                fence_sys();
+            }
+            __syncthreads();
+        }
+        double *acc = ctrl + CT_ACC + 16 * parity;
+        {   // A: costs
+            double a7[7];
+            costs_loop<T>(pb, tb, camf, a7);
+            block_reduce_add<7>(a7, red, acc);
+        }
+        grid_exchange<7, 0, 7, false>(pb, parity, acc, 0, false, seq, tot, false);
+        const RefineDerived dv = derive(pb, tot, st);
+        {   // B: gradient
+            double gn[1] = {grad_loop<T>(pb, tb, camf, dv)};
+            block_reduce_add<1>(gn, red, acc + 7);
+        }
+        grid_exchange<1, 7, 8, false>(pb, parity, acc + 7, 1, true, seq, tot, false);
+        // C: clipped Adam, boundary frames into the neighbours' halos, bookkeeping
+        const bool pushed = step_loop<T>(pb, parity, 1, tot, st, dv, true, bias, true);
+        grid_exchange<0, 0, 0, true>(pb, parity, nullptr, 2, false, seq, tot, pushed);
     }
 }
 
@@ -689,6 +843,27 @@ int refine_phase(const mc3d_refine_problem *pb, int phase, long long step_index,
     return MC3D_OK;
 }
 
+// n whole-window iterations inside one persistent cooperative kernel (needs the exchange block for its barriers).
+template <typename T>
+int refine_run_fused(const mc3d_refine_problem *pb, long long first_step, long long n_iters, cudaStream_t stream) {
+    auto kern = refine_fused_kernel<T>;
+    int per_sm = 0;
+    MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RF_THREADS, 0));
+    if (per_sm < 1) { set_error("persistent refinement kernel does not fit on an SM"); return MC3D_ERR_UNSUPPORTED; }
+    if (per_sm > MC3D_RF_GRID) per_sm = MC3D_RF_GRID;
+    const long long n_items = (long long)pb->n_frames * pb->n_joints;
+    long long grid = (n_items + RF_THREADS - 1) / RF_THREADS;
+    if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;      // all blocks co-resident
+    if (grid < 1) grid = 1;
+    mc3d_refine_problem prob = *pb;
+    int parity = (int)(first_step & 1);
+    long long iters = n_iters;
+    void *args[] = {(void *)&prob, (void *)&parity, (void *)&iters};
+    MC3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(RF_THREADS), args, 0, stream));
+    count_launch();
+    return MC3D_OK;
+}
+
 // n whole-window iterations on one GPU.  Pairs of iterations (parity 0,1) are captured once into a CUDA graph and
 // replayed, so the per-iteration cost is three graph kernel nodes and no host work.
 template <typename T>
@@ -696,6 +871,16 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
     int st = validate(pb);
     if (st != MC3D_OK) return st;
     long long done = 0;
+    if (pb->xchg[0] && n_iters > 0 && pb->n_frames > 0) {
+        // The persistent kernel wins while a phase is latency-bound (few items per thread: no launch boundaries,
+        // cheaper barriers); for big shards the three separate kernels run at higher occupancy and win.  Measured
+        // crossover on B200 (float state): between 12 500 and 100 000 frames x 17 joints per GPU.
+        const char *env = getenv("MC3D_REFINE_FUSED");              // read per call: tests switch it; 1 forces, 0 forbids
+        const int fused_env = env ? atoi(env) : -1;
+        const long long n_items = (long long)pb->n_frames * pb->n_joints;
+        const bool small = n_items <= 8LL * sm_count() * 2 * RF_THREADS;
+        if (fused_env == 1 || (fused_env != 0 && small)) return refine_run_fused<T>(pb, first_step, n_iters, stream);
+    }
     auto one = [&](long long step, cudaStream_t s) -> int {
         for (int ph = 0; ph < 3; ++ph) {
             int s2 = refine_phase<T>(pb, ph, step, 1, s);

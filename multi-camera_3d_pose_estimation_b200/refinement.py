@@ -267,10 +267,11 @@ class RefineEngine:
 
         traj = torch.as_tensor(trajectory).to(dt)
         # GPUs: the kernels exchange sums and halo frames themselves over peer memory, and the trajectory lives in
-        # the exchange allocation.  MC3D_REFINE_PEER=1 forces that path on one GPU (tests), =0 the host-driven one.
+        # the exchange allocation (one GPU: the block only serves the persistent kernel's grid barriers).
+        # MC3D_REFINE_PEER=0 selects the host-driven exchange / the plain three-kernel graph instead.
         mode = os.environ.get('MC3D_REFINE_PEER', '')
         self.peer = None
-        if dev.type == 'cuda' and phases is None and mode != '0' and (self.comm.world > 1 or mode == '1'):
+        if dev.type == 'cuda' and phases is None and mode != '0':
             if self.comm.world > 1 and min(frame_shard(self.total_frames, r, self.comm.world)[1] -
                                            frame_shard(self.total_frames, r, self.comm.world)[0]
                                            for r in range(self.comm.world)) < 2:

@@ -85,25 +85,16 @@ def test_sgd_optimize_matches_reference_runs(pr, syn, run, tag, capsys):
 
 
 @pytest.mark.parametrize('dt_name', ['f64', 'f32'])
-def test_in_kernel_exchange_path_on_one_gpu(pr, syn, dt_name, monkeypatch):
-    """MC3D_REFINE_PEER=1 runs the NVLink peer-memory protocol (tickets, sequence flags, rank-ordered sums, csrc/refine.cu
-    xchg_*) with this GPU as its own only peer: the cost history and trajectories must equal the plain path."""
+def test_exchange_and_persistent_kernel_paths_on_one_gpu(pr, syn, dt_name, monkeypatch):
+    """Three ways to run the same optimisation on one GPU must agree: the plain graph of three kernels
+    (MC3D_REFINE_PEER=0), the three kernels with the NVLink peer-memory protocol (tickets, sequence flags, rank-ordered
+    sums; this GPU is its own only peer; MC3D_REFINE_FUSED=0), and the persistent cooperative kernel (default)."""
     import torch
     dt = torch.float64 if dt_name == 'f64' else torch.float32
     gs, init, cams, _ = syn.refinement_inputs(120, n_cams=2, seed=23)
     init[40, 3] = np.nan
     kw = dict(lr=0.01, lambda_smooth=1e-3, lambda_body_length=1.0, max_iter=60, time_interval=[0, 120], patience=10 ** 6,
               print_frequency=np.inf)
-
-    def run():
-        opt = pr.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(), decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
-                                              body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
-        opt.sgd_optimize(**kw)
-        return opt
-
-    plain = run()
-    assert plain._engine.peer is None
-    monkeypatch.setenv('MC3D_REFINE_PEER', '1')
     from mc3d_b200 import refinement as rf
     made = []
     orig = rf.PeerExchange.__init__
@@ -112,16 +103,50 @@ def test_in_kernel_exchange_path_on_one_gpu(pr, syn, dt_name, monkeypatch):
         made.append(1)
         orig(self, *a, **k)
     monkeypatch.setattr(rf.PeerExchange, '__init__', spy)
-    peer = run()
-    assert made, 'the in-kernel exchange path was not taken'
+
+    def run(peer, fused):
+        monkeypatch.setenv('MC3D_REFINE_PEER', peer)
+        monkeypatch.setenv('MC3D_REFINE_FUSED', fused)
+        opt = pr.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(), decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                              body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+        opt.sgd_optimize(**kw)
+        return opt
+
+    plain = run('0', '1')
+    assert not made
+    runs = {'exchange': run('1', '0'), 'persistent': run('1', '1')}
+    assert len(made) == 2, 'the in-kernel exchange path was not taken'
     h1 = np.array([float(v) for v in plain.all_costs_total['total_cost']])
-    h2 = np.array([float(v) for v in peer.all_costs_total['total_cost']])
-    # not bitwise: the block partial sums are added with double atomics in arrival order on either path
+    # not bitwise: the block partial sums are added with double atomics in arrival order on every path
     rtol, atol = (1e-11, 1e-9) if dt_name == 'f64' else (1e-6, 1e-3)
-    assert len(h1) == len(h2) == 122 and np.allclose(h1, h2, rtol=rtol, atol=0)
-    assert np.allclose(plain.trajectory.numpy(), peer.trajectory.numpy(), rtol=0, atol=atol, equal_nan=True)
-    assert np.allclose(plain.best_trajectory.numpy(), peer.best_trajectory.numpy(), rtol=0, atol=atol, equal_nan=True)
-    assert np.isnan(peer.trajectory.numpy()[40, 3]).all()
+    for name, other in runs.items():
+        h2 = np.array([float(v) for v in other.all_costs_total['total_cost']])
+        assert len(h1) == len(h2) == 122 and np.allclose(h1, h2, rtol=rtol, atol=0), name
+        assert np.allclose(plain.trajectory.numpy(), other.trajectory.numpy(), rtol=0, atol=atol, equal_nan=True), name
+        assert np.allclose(plain.best_trajectory.numpy(), other.best_trajectory.numpy(), rtol=0, atol=atol, equal_nan=True), name
+        assert np.isnan(other.trajectory.numpy()[40, 3]).all()
+        assert other.iterations == plain.iterations == 61
+
+
+def test_persistent_kernel_early_stop_matches_three_kernel_graph(pr, syn, monkeypatch):
+    """Early stopping inside the persistent kernel (it leaves its loop; the state is stored at both parities)."""
+    import torch
+    gs, init, cams, _ = syn.refinement_inputs(60, n_cams=2, seed=24)
+    kw = dict(lr=0.01, lambda_smooth=1e-3, lambda_body_length=1.0, max_iter=500, time_interval=[0, 60], patience=7,
+              tolerance=1e3, print_frequency=np.inf)
+
+    def run(peer):
+        monkeypatch.setenv('MC3D_REFINE_PEER', peer)
+        opt = pr.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(), decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                              body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=torch.float64)
+        opt.sgd_optimize(**kw)
+        return opt
+    a, b = run('0'), run('1')
+    assert a.iterations == b.iterations and a.iterations < 400
+    ha = np.array([float(v) for v in a.all_costs_total['total_cost']])
+    hb = np.array([float(v) for v in b.all_costs_total['total_cost']])
+    assert len(ha) == len(hb) and np.allclose(ha, hb, rtol=1e-11)
+    assert np.allclose(a.best_trajectory.numpy(), b.best_trajectory.numpy(), atol=1e-9)
 
 
 def test_gradient_kernel_matches_oracle(pr, syn):
