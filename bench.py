@@ -411,6 +411,7 @@ def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0):
     exchange = 'none (one rank)' if world == 1 else ('in-kernel stores + sequence flags over NVLink peer memory (CUDA IPC), no NCCL'
                                                      if eng.peer is not None else 'NCCL all_reduce x2 + all_gather halo')
     hist = eng.history(warm + iters)
+    plan = eng.plan()
     eng.close()
     esize = 4 if dtype_name == 'f32' else 8
     # per joint-frame and iteration: A reads x, mu0, S (8 scalars); B reads the same and writes g (11); C reads g, x, m, v
@@ -418,7 +419,7 @@ def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0):
     algo = n_frames * 17 * (8 + 11 + 21) * esize
     return {'frames': n_frames, 'iters': iters, 'dtype': dtype_name, 'iters_per_s': iters / (ms * 1e-3), 'us_per_iter': 1e3 * ms / iters,
             'algorithmic_bytes_per_iter': algo, 'achieved_GBs': algo / (ms * 1e-3 / iters) / 1e9,
-            'cost_first': float(hist[0, 0]), 'cost_last': float(hist[-1, 0]), 'kernels_per_iter': 3, 'world': world,
+            'cost_first': float(hist[0, 0]), 'cost_last': float(hist[-1, 0]), 'step': plan, 'world': world,
             'exchange': exchange, 'nccl_collectives_per_iter': 3 if exchange.startswith('NCCL') else 0,
             'multi_rank_cuda_graph': graphed}
 

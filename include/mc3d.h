@@ -182,6 +182,8 @@ typedef struct {
     uint8_t *term_ok;
     double *ctrl;
     /* in-kernel exchange (all zero / NULL = off) */
+    void *gc;                /* 4 gradient components of the two-phase step, each n_frames*J*3 scalars at a stride rounded
+                              * up to a multiple of 4 scalars (16-byte aligned starts); NULL selects the three phases */
     int32_t rank, world;
     int64_t n_frames_left;   /* local frame count of rank - 1 (locates its right halo) */
     int64_t spin_timeout_ns; /* a wait on a peer gives up after this long and sets mc3d_refine_xchg.error */
@@ -189,7 +191,8 @@ typedef struct {
 } mc3d_refine_problem;
 
 /* Exchange block at the start of each rank's peer allocation (zero-filled by mc3d_peer_alloc). */
-#define MC3D_XCHG_X_OFFSET 4096
+#define MC3D_XCHG_X_OFFSET 16384
+#define MC3D_REFINE_SUMS2 17     /* sums of the two-phase step: 7 cost sums + 10 gradient-component dot products */
 typedef struct {
     double sums[2][MC3D_MAX_PEERS][8];      /* [step parity][source rank]: S_lik N_lik S_s N_s a.b b.b a.a | gnorm^2 */
     int64_t seq_costs[2][MC3D_MAX_PEERS];   /* adam step + 1 of the cost sums stored in that slot */
@@ -198,6 +201,10 @@ typedef struct {
     int64_t ticket[4];                      /* block tickets of phases 0, 1, 2 (local) */
     int64_t gen[4];                         /* persistent kernel: grid-barrier generation of phases 0, 1, 2 (local) */
     int64_t error;                          /* != 0: a wait timed out (results are invalid) */
+    /* two-phase step (mc3d_refine_run_*): one exchange of MC3D_REFINE_SUMS2 sums per step */
+    double acc2[2][24];                     /* [parity]: this rank's sums (atomic targets of its blocks) */
+    double sums2[2][MC3D_MAX_PEERS][24];    /* [parity][source rank] */
+    int64_t seq2[2][MC3D_MAX_PEERS];
 } mc3d_refine_xchg;
 
 /* Pinhole + 5-coefficient Brown projection of n points (n,3) -> (n,2) for one camera given as
@@ -216,11 +223,24 @@ int mc3d_refine_flags_f64(const mc3d_refine_problem *pb, void *stream);
 int mc3d_refine_problem_size(void);
 int mc3d_refine_phase_f32(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream);
 int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream);
-/* n_iters whole-window iterations (phases 0,1,2 each), replayed from a CUDA graph of the three kernels.  With the
+/* n_iters whole-window iterations.
+ * Two-phase step (needs `gc` and the exchange block `xchg`; any world size): the gradient does not wait for the
+ * global sums.  It is linear in three scalars that depend on them,
+ *     g = alpha g1 + sigma gs + beta (G2 - mu G3),   alpha = 1/N_lik, sigma = 2 lambda_s/N_s, beta = -2 lambda_b mu/(a.a),
+ * so ONE pass computes the costs, the four component vectors (g1 likelihood, gs smoothness, G2' = G2 - mu_prev G3 and
+ * G3 bone length; mu_prev = last step's mu keeps the cancelling pair small) and their 10 mutual dot products.  After
+ * ONE reduction of 17 sums every thread knows alpha, sigma, beta, mu and |g|^2 (a quadratic form in them), and the
+ * second pass combines the components, clips and applies Adam.  Per step: two passes, one cross-rank exchange of 17
+ * doubles and the halo stores (the three-phase step needs three passes and two exchanges).
+ * ctrl[32 + 16p + 8] carries mu_prev.  Small shards run all iterations inside one persistent cooperative kernel
+ * (two grid barriers per step), big ones replay a CUDA graph of the two kernels.
+ * Without `gc`: phases 0,1,2 replayed from a CUDA graph of the three kernels.  With the
  * in-kernel exchange (xchg set, any world size) the iterations run instead inside ONE persistent cooperative kernel:
  * the three phases are separated by grid barriers (the last block to arrive does the cross-rank exchange), the
  * cameras and bone tables stay in shared memory, and there is no launch boundary per phase (MC3D_REFINE_FUSED=0 in
  * the environment selects the graph of three kernels).  Every rank must call it with the same arguments. */
+/* Text describing what mc3d_refine_run_* launches for this problem on the current device (static string). */
+const char *mc3d_refine_plan(const mc3d_refine_problem *pb);
 int mc3d_refine_run_f32(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
 int mc3d_refine_run_f64(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
 

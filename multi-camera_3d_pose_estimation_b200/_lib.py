@@ -36,7 +36,7 @@ MAX_JOINTS = 133
 MAX_BONES = 64
 MAX_PEERS = 16
 IPC_HANDLE_BYTES = 64
-XCHG_X_OFFSET = 4096
+XCHG_X_OFFSET = 16384
 CT_ACC, CT_STATE, CT_HIST = 0, 32, 64          # control-block layout (include/mc3d.h)
 
 
@@ -56,7 +56,7 @@ class RefineProblem(ctypes.Structure):
                 ('adj_bone', ctypes.c_int32 * (2 * MAX_BONES)), ('adj_sign', ctypes.c_int32 * (2 * MAX_BONES)),
                 ('x', ctypes.c_void_p), ('m', ctypes.c_void_p), ('v', ctypes.c_void_p), ('best', ctypes.c_void_p),
                 ('g', ctypes.c_void_p), ('mu0', ctypes.c_void_p), ('S', ctypes.c_void_p),
-                ('term_ok', ctypes.c_void_p), ('ctrl', ctypes.c_void_p),
+                ('term_ok', ctypes.c_void_p), ('ctrl', ctypes.c_void_p), ('gc', ctypes.c_void_p),
                 ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('n_frames_left', ctypes.c_int64),
                 ('spin_timeout_ns', ctypes.c_int64), ('xchg', ctypes.c_void_p * MAX_PEERS)]
 
@@ -66,7 +66,9 @@ class RefineXchg(ctypes.Structure):
     _fields_ = [('sums', ((ctypes.c_double * 8) * MAX_PEERS) * 2),
                 ('seq_costs', (ctypes.c_int64 * MAX_PEERS) * 2), ('seq_grad', (ctypes.c_int64 * MAX_PEERS) * 2),
                 ('halo_seq', ctypes.c_int64 * 2), ('ticket', ctypes.c_int64 * 4), ('gen', ctypes.c_int64 * 4),
-                ('error', ctypes.c_int64)]
+                ('error', ctypes.c_int64),
+                ('acc2', (ctypes.c_double * 24) * 2), ('sums2', ((ctypes.c_double * 24) * MAX_PEERS) * 2),
+                ('seq2', (ctypes.c_int64 * MAX_PEERS) * 2)]
 
 
 _lib = None
@@ -96,6 +98,7 @@ SIGNATURES = {
     'mc3d_refine_prepare_f32': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp, _c_vp]),
     'mc3d_refine_prepare_f64': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp, _c_vp]),
     'mc3d_refine_problem_size': (_c_int, []),
+    'mc3d_refine_plan': (ctypes.c_char_p, [ctypes.POINTER(RefineProblem)]),
     'mc3d_refine_flags_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_vp]),
     'mc3d_refine_flags_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_vp]),
     'mc3d_refine_phase_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_int, _c_i64, _c_int, _c_vp]),

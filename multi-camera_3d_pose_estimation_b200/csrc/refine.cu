@@ -27,6 +27,9 @@ constexpr int RF_THREADS = 256;
 #ifndef MC3D_RF_GRID
 #define MC3D_RF_GRID 8
 #endif
+#ifndef MC3D_RF_SMALL
+#define MC3D_RF_SMALL 17         // items per thread of a full persistent grid (2 CTAs/SM) up to which a shard counts as small (~76k frames x 17 joints)
+#endif
 // control block layout (doubles)
 constexpr int CT_ACC = 0;        // + 16 * parity : S_lik N_lik S_s N_s ab bb aa_ok gnorm2
 constexpr int CT_STATE = 32;     // + 16 * parity : step run_sum run_cnt best no_improve stopped iters_done improved
@@ -472,11 +475,26 @@ refine_grad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
 // Clip + Adam over this rank's elements, boundary frames stored into the neighbours' halos (in-kernel exchange), and
 // the bookkeeping for the next step (block 0).  acc: the 8 global sums of this step; st: state entering it.
 // Returns true when this thread stored into a peer's memory.
+// Elements between the four gradient components in `gc`: n_frames x J x 3 rounded up to a multiple of 4, so that each
+// component starts 16-byte aligned (pairs of scalars are read with one access).
+__host__ __device__ __forceinline__ long long gc_stride(const mc3d_refine_problem &pb) {
+    return ((long long)pb.n_frames * pb.n_joints * 3 + 3) / 4 * 4;
+}
+
+// Two-phase step: the gradient is combined here from its four stored components with the scalars of this step.
 template <typename T>
-__device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int parity, int end_of_iteration, const double *acc,
-                                          const double *st, const RefineDerived &dv, bool xchg, double *bias, bool both_parities) {
+struct GradMix {
+    bool on;
+    T alpha, sigma, beta, gamma;           // g = alpha g1 + sigma gs + beta G2' + gamma G3
+    double mu;                             // this step's a.b / b.b (next step's mu_prev)
+};
+
+template <typename T>
+__device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int parity, int end_of_iteration, double gnorm2,
+                                          const double *st, const RefineDerived &dv, bool xchg, double *bias, bool both_parities,
+                                          const GradMix<T> mix) {
     double *ctrl = pb.ctrl;
-    const double gnorm = sqrt(acc[7]);
+    const double gnorm = sqrt(gnorm2);
     const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
     const double step = st[0] + 1.0;
     double run_sum = st[1] + dv.total, run_cnt = st[2] + 1.0;
@@ -502,6 +520,8 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
     T *x = (T *)pb.x + 2LL * pb.n_joints * 3;                       // skip the two halo frames
     T *m = (T *)pb.m, *v = (T *)pb.v, *bestx = (T *)pb.best;
     const T *g = (const T *)pb.g;
+    const long long n3 = gc_stride(pb);                             // elements per gradient component
+    const T *c1 = (const T *)pb.gc, *cs = c1 + n3, *c2 = cs + n3, *c3 = c2 + n3;
     const long long per_frame = (long long)pb.n_joints * 3;
     const long long n = pb.n_frames * per_frame;
     const long long lo = (pb.win_begin - pb.frame_offset) * per_frame, hi = (pb.win_end - pb.frame_offset) * per_frame;
@@ -530,7 +550,15 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
     };
     for (long long i2 = tid0; i2 < n2; i2 += nthr) {
         const long long i = i2 << 1;
-        Vec2 gv = reinterpret_cast<const Vec2 *>(g)[i2];
+        Vec2 gv;
+        if (mix.on) {
+            const Vec2 a1 = reinterpret_cast<const Vec2 *>(c1)[i2], as = reinterpret_cast<const Vec2 *>(cs)[i2];
+            const Vec2 a2 = reinterpret_cast<const Vec2 *>(c2)[i2], a3 = reinterpret_cast<const Vec2 *>(c3)[i2];
+            gv.a = fma(mix.alpha, a1.a, fma(mix.sigma, as.a, fma(mix.beta, a2.a, mix.gamma * a3.a)));
+            gv.b = fma(mix.alpha, a1.b, fma(mix.sigma, as.b, fma(mix.beta, a2.b, mix.gamma * a3.b)));
+        } else {
+            gv = reinterpret_cast<const Vec2 *>(g)[i2];
+        }
         Vec2 mv = reinterpret_cast<Vec2 *>(m)[i2], vv = reinterpret_cast<Vec2 *>(v)[i2], xv = reinterpret_cast<Vec2 *>(x)[i2];
         if (!(i >= lo && i < hi)) gv.a = (T)0;
         if (!(i + 1 >= lo && i + 1 < hi)) gv.b = (T)0;
@@ -544,7 +572,9 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
     }
     if ((n & 1) && tid0 == 0) {                                    // odd tail
         const long long i = n - 1;
-        T gi = (i >= lo && i < hi) ? g[i] : (T)0, mi = m[i], vi = v[i], xi = x[i];
+        T gi = mix.on ? fma(mix.alpha, c1[i], fma(mix.sigma, cs[i], fma(mix.beta, c2[i], mix.gamma * c3[i]))) : g[i];
+        if (!(i >= lo && i < hi)) gi = (T)0;
+        T mi = m[i], vi = v[i], xi = x[i];
         adam(gi, mi, vi, xi);
         m[i] = mi; v[i] = vi; x[i] = xi;
         if (improved) bestx[i] = xi;
@@ -554,8 +584,9 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         double *nx = ctrl + CT_STATE + 16 * (parity ^ 1);
         nx[0] = step; nx[1] = run_sum; nx[2] = run_cnt; nx[3] = best; nx[4] = no_imp;
         nx[5] = stop ? 1.0 : 0.0; nx[6] = iters; nx[7] = improved ? 1.0 : 0.0;
+        nx[8] = mix.on ? mix.mu : 0.0;
         if (both_parities && stop)                                 // a persistent kernel leaves its loop here: the stopped
-            for (int i = 0; i < 8; ++i) ctrl[CT_STATE + 16 * parity + i] = nx[i];      // state must be found at either parity
+            for (int i = 0; i < 9; ++i) ctrl[CT_STATE + 16 * parity + i] = nx[i];      // state must be found at either parity
         for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
         const long long hs = (long long)(step - 1.0);
         if (hs < pb.hist_capacity) {
@@ -591,7 +622,7 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
     if (xchg) xchg_gather<8>(pb, parity, true, adam_step + 1, tot);     // every rank has finished its gradient pass
     const double *acc = xchg ? tot : ctrl + CT_ACC + 16 * parity;
     const RefineDerived dv = derive(pb, acc, st);
-    const bool pushed = step_loop<T>(pb, parity, end_of_iteration, acc, st, dv, xchg, bias, false);
+    const bool pushed = step_loop<T>(pb, parity, end_of_iteration, acc[7], st, dv, xchg, bias, false, GradMix<T>{false, 0, 0, 0, 0, 0.0});
     if (xchg && pb.world > 1) {                                    // flag the halos once every block's stores are out
         __shared__ int is_last;
         if (pushed) __threadfence_system();
@@ -716,7 +747,267 @@ refine_fused_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_pa
         }
         grid_exchange<1, 7, 8, false>(pb, parity, acc + 7, 1, true, seq, tot, false);
         // C: clipped Adam, boundary frames into the neighbours' halos, bookkeeping
-        const bool pushed = step_loop<T>(pb, parity, 1, tot, st, dv, true, bias, true);
+        const bool pushed = step_loop<T>(pb, parity, 1, tot[7], st, dv, true, bias, true, GradMix<T>{false, 0, 0, 0, 0, 0.0});
+        grid_exchange<0, 0, 0, true>(pb, parity, nullptr, 2, false, seq, tot, pushed);
+    }
+}
+
+// ==== two-phase step ================================================================================================
+// Pass 1 (costs + gradient components).  The gradient is linear in three scalars that need the global sums,
+//     g = alpha g1 + sigma gs + beta (G2 - mu G3),
+// so this pass stores g1, gs, G2' = G2 - mu_prev G3 and G3 (mu_prev = last step's mu: G2' is the small, already
+// cancelled combination, and the coefficient of G3 becomes the tiny beta (mu_prev - mu)) together with the 10 dot
+// products that give |g|^2 as a quadratic form.  sums: [0..7) as in pass A, [7..17) = 11 1s 12 13 ss s2 s3 22 23 33.
+constexpr int NS2 = MC3D_REFINE_SUMS2;
+
+template <typename T>
+__device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, T mu_prev,
+                                              double (&acc)[NS2]) {
+    const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones, JS = J * 3;
+    const T *x = (const T *)pb.x + 2LL * JS;
+    const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
+    const long long n_items = pb.n_frames * J, n3 = gc_stride(pb);
+    T *o1 = (T *)pb.gc, *os = o1 + n3, *o2 = os + n3, *o3 = o2 + n3;
+    const bool ign = pb.ignore_distortions != 0;
+    const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
+    const long long lo = pb.win_begin - pb.frame_offset, hi = pb.win_end - pb.frame_offset;
+    T a[NS2];
+#pragma unroll
+    for (int i = 0; i < NS2; ++i) a[i] = (T)0;
+    for (ItemCursor it(J); it.e < n_items; it.next(J)) {
+        const long long t = it.t, e = it.e;
+        const int j = it.j;
+        T g1[3] = {(T)0, (T)0, (T)0}, gs[3] = {(T)0, (T)0, (T)0}, g2[3] = {(T)0, (T)0, (T)0}, g3[3] = {(T)0, (T)0, (T)0};
+        if (t >= lo && t < hi) {
+            const T *xc = x + e * 3;
+            const T X = xc[0], Y = xc[1], Z = xc[2];
+            const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
+            const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
+            const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
+            for (int c = 0; c < C; ++c) {
+                T cam[CAM_STRIDE];
+                load_camera(camf + c * CAM_STRIDE, cam);
+                const T q = reproject_term<true, T>(cam, ign, X, Y, Z, mx, my, s00, s01, s11, (T)1, g1);   // adds only when finite
+                const bool ok = finite_c(q);
+                a[0] += ok ? q : (T)0;
+                a[1] += ok ? (T)1 : (T)0;
+            }
+            if (do_smooth) {
+                const T two = (T)2;
+                const bool k0 = t - 2 >= lo && pb.term_ok[t + 2];
+                if (k0) {                                           // the cost term ending at this frame
+                    const T d0 = X - two * xc[-JS] + xc[-2 * JS], d1 = Y - two * xc[1 - JS] + xc[1 - 2 * JS],
+                            d2 = Z - two * xc[2 - JS] + xc[2 - 2 * JS];
+                    a[2] += d0 * d0 + d1 * d1 + d2 * d2;
+                    a[3] += j == 0 ? (T)1 : (T)0;
+                    gs[0] += d0; gs[1] += d1; gs[2] += d2;
+                }
+                if (self_ok) {
+                    const bool k1 = t - 1 >= lo && t + 1 < hi && pb.term_ok[t + 3];
+                    const bool k2 = t + 2 < hi && pb.term_ok[t + 4];
+                    if (k1) {
+                        gs[0] -= two * (xc[JS] - two * xc[0] + xc[-JS]); gs[1] -= two * (xc[1 + JS] - two * xc[1] + xc[1 - JS]);
+                        gs[2] -= two * (xc[2 + JS] - two * xc[2] + xc[2 - JS]);
+                    }
+                    if (k2) {
+                        gs[0] += xc[2 * JS] - two * xc[JS] + xc[0]; gs[1] += xc[1 + 2 * JS] - two * xc[1 + JS] + xc[1];
+                        gs[2] += xc[2 + 2 * JS] - two * xc[2 + JS] + xc[2];
+                    }
+                } else {
+                    gs[0] = gs[1] = gs[2] = (T)0;                   // a non-finite joint is frozen
+                }
+            }
+            if (do_body) {
+                const T *xf = x + t * JS;
+                for (int k = j; k < NB; k += J) {                   // cost: every bone of the frame once
+                    const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
+                    const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
+                    const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                    if (finite_c(b)) {
+                        const T al = (T)tb.bone_len[k];
+                        a[4] += al * b; a[5] += b * b; a[6] += al * al;
+                    }
+                }
+                if (self_ok)
+                    for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {   // gradient: the bones at this joint
+                        const int k = tb.adj_bone[q];
+                        const T sign = (T)tb.adj_sign[q];
+                        const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
+                        const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
+                        const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                        if (finite_c(b) && b > (T)0) {
+                            const T c2 = sign * ((T)tb.bone_len[k] - mu_prev * b) / b;     // G2 - mu_prev G3
+                            g2[0] = fma(c2, v0, g2[0]); g2[1] = fma(c2, v1, g2[1]); g2[2] = fma(c2, v2, g2[2]);
+                            g3[0] = fma(sign, v0, g3[0]); g3[1] = fma(sign, v1, g3[1]); g3[2] = fma(sign, v2, g3[2]);
+                        }
+                    }
+            }
+            if (!self_ok) g1[0] = g1[1] = g1[2] = (T)0;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            o1[e * 3 + k] = g1[k]; os[e * 3 + k] = gs[k]; o2[e * 3 + k] = g2[k]; o3[e * 3 + k] = g3[k];
+            a[7] = fma(g1[k], g1[k], a[7]);   a[8] = fma(g1[k], gs[k], a[8]);   a[9] = fma(g1[k], g2[k], a[9]);
+            a[10] = fma(g1[k], g3[k], a[10]); a[11] = fma(gs[k], gs[k], a[11]); a[12] = fma(gs[k], g2[k], a[12]);
+            a[13] = fma(gs[k], g3[k], a[13]); a[14] = fma(g2[k], g2[k], a[14]); a[15] = fma(g2[k], g3[k], a[15]);
+            a[16] = fma(g3[k], g3[k], a[16]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NS2; ++i) acc[i] = (double)a[i];
+}
+
+// Scalars of the step from the 17 totals: the usual derived costs, the mix coefficients and |g|^2.
+template <typename T>
+__device__ __forceinline__ GradMix<T> mix_of(const mc3d_refine_problem &pb, const double *tot, const RefineDerived &dv, double mu_prev,
+                                             double &gnorm2) {
+    const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
+    const double al = dv.inv_nlik, si = do_smooth ? dv.smooth_scale : 0.0;
+    const double be = do_body ? dv.body_c : 0.0, ga = do_body ? dv.body_c * (mu_prev - dv.mu) : 0.0;
+    // rounded to the state type first: |g|^2 is the norm of the gradient that is actually applied
+    GradMix<T> m{true, (T)al, (T)si, (T)be, (T)ga, do_body ? dv.mu : 0.0};
+    const double A = (double)m.alpha, S = (double)m.sigma, B = (double)m.beta, G = (double)m.gamma;
+    gnorm2 = A * A * tot[7] + S * S * tot[11] + B * B * tot[14] + G * G * tot[16] +
+             2.0 * (A * S * tot[8] + A * B * tot[9] + A * G * tot[10] + S * B * tot[12] + S * G * tot[13] + B * G * tot[15]);
+    if (gnorm2 < 0.0) gnorm2 = 0.0;
+    return m;
+}
+
+// Grid barrier + exchange of the two-phase step (see grid_exchange): NS2 sums, flags seq2.  FUSED: called by every block
+// of the persistent kernel (the local flag doubles as the grid barrier); otherwise only the publish half runs, in the
+// last block of pass 1, and pass 2 gathers.
+__device__ __forceinline__ void publish2(const mc3d_refine_problem &pb, int parity, long long seq) {   // last block only
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    if (threadIdx.x < NS2) {
+        const double v = __ldcg(&mine->acc2[parity][threadIdx.x]);
+        for (int r = 0; r < pb.world; ++r) xchg_of(pb, r)->sums2[parity][pb.rank][threadIdx.x] = v;
+        mine->acc2[parity][threadIdx.x] = 0.0;                     // ready for the step after next
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fence_xchg(pb);
+        for (int r = 0; r < pb.world; ++r) st_relaxed_sys(&xchg_of(pb, r)->seq2[parity][pb.rank], seq);
+    }
+}
+
+__device__ __forceinline__ void gather2(const mc3d_refine_problem &pb, int parity, long long seq, double *tot) {
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < pb.world; ++r) xchg_wait(pb, &mine->seq2[parity][r], seq);
+        fence_xchg(pb);
+    }
+    __syncthreads();
+    if (threadIdx.x < NS2) {
+        double s = 0.0;
+        for (int r = 0; r < pb.world; ++r) s += __ldcg(&mine->sums2[parity][r][threadIdx.x]);
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool take_ticket(mc3d_refine_xchg *mine, int idx) {      // true in the last block
+    __shared__ int is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fence_gpu();
+        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&mine->ticket[idx]), 1ULL);
+        is_last = old == (unsigned long long)gridDim.x - 1ULL;
+        if (is_last) { mine->ticket[idx] = 0; fence_gpu(); }
+    }
+    __syncthreads();
+    return is_last != 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_costgrad_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
+    __shared__ double red[8 * NS2];
+    __shared__ RefineTables tb;
+    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
+    const double *st = pb.ctrl + CT_STATE + 16 * parity;
+    if (st[5] != 0.0) return;                                      // stopped
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    const long long adam_step = (long long)st[0];
+    if (pb.world > 1 && threadIdx.x == 0) {                        // the neighbours' boundary frames of this step are in my halo
+        if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], adam_step);
+        if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], adam_step);
+        fence_sys();
+    }
+    load_cameras_and_tables(pb, tb, camf);
+    __syncthreads();
+    double acc[NS2];
+    costgrad_loop<T>(pb, tb, camf, (T)st[8], acc);
+    block_reduce_add<NS2>(acc, red, mine->acc2[parity]);
+    if (take_ticket(mine, 0)) publish2(pb, parity, adam_step + 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_step2_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) {
+    __shared__ double tot[24];
+    __shared__ double bias[2];
+    double *ctrl = pb.ctrl;
+    const double *st = ctrl + CT_STATE + 16 * parity;
+    if (st[5] != 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0)                   // carry the stopped state forward
+            for (int i = 0; i < 16; ++i) ctrl[CT_STATE + 16 * (parity ^ 1) + i] = ctrl[CT_STATE + 16 * parity + i];
+        return;
+    }
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    const long long adam_step = (long long)st[0];
+    gather2(pb, parity, adam_step + 1, tot);                       // every rank has finished pass 1
+    const RefineDerived dv = derive(pb, tot, st);
+    double gnorm2;
+    const GradMix<T> mix = mix_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);   // mu_prev as pass 1 used it
+    const bool pushed = step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, false, mix);
+    if (pb.world > 1) {                                            // flag the halos once every block's stores are out
+        if (pushed) fence_sys();
+        if (take_ticket(mine, 2) && threadIdx.x == 0) {
+            fence_sys();
+            halo_flags(pb, adam_step + 1);
+        }
+    }
+}
+
+// All iterations inside one persistent cooperative kernel: two grid barriers per step.
+template <typename T>
+__global__ void __launch_bounds__(RF_THREADS)
+refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_parity, long long n_iters) {
+    __shared__ double red[8 * NS2];
+    __shared__ RefineTables tb;
+    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
+    __shared__ double tot[24];
+    __shared__ double bias[2];
+    double *ctrl = pb.ctrl;
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    load_cameras_and_tables(pb, tb, camf);
+    __syncthreads();
+    int parity = first_parity & 1;
+    for (long long it = 0; it < n_iters; ++it, parity ^= 1) {
+        double st[9];                                              // state entering this step (written before the last barrier)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) st[i] = __ldcg(ctrl + CT_STATE + 16 * parity + i);
+        if (st[5] != 0.0) break;                                   // stopped: identical decision in every block and rank
+        const long long seq = (long long)st[0] + 1;
+        if (pb.world > 1) {
+            if (threadIdx.x == 0) {
+                if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], seq - 1);
+                if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], seq - 1);
+                fence_sys();
+            }
+            __syncthreads();
+        }
+        {   // pass 1
+            double acc[NS2];
+            costgrad_loop<T>(pb, tb, camf, (T)st[8], acc);
+            block_reduce_add<NS2>(acc, red, mine->acc2[parity]);
+        }
+        if (take_ticket(mine, 0)) publish2(pb, parity, seq);
+        gather2(pb, parity, seq, tot);                             // grid barrier + cross-rank sums in one
+        const RefineDerived dv = derive(pb, tot, st);
+        double gnorm2;
+        const GradMix<T> mix = mix_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);   // mu_prev as pass 1 used it
+        const bool pushed = step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, true, mix);
         grid_exchange<0, 0, 0, true>(pb, parity, nullptr, 2, false, seq, tot, pushed);
     }
 }
@@ -843,6 +1134,70 @@ int refine_phase(const mc3d_refine_problem *pb, int phase, long long step_index,
     return MC3D_OK;
 }
 
+// Two-phase step: persistent kernel for small shards, otherwise a CUDA graph of (costgrad, step2) pairs.
+template <typename T>
+int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, long long n_iters, cudaStream_t stream) {
+    const long long n_items = (long long)pb->n_frames * pb->n_joints;
+    const char *env = getenv("MC3D_REFINE_FUSED");                  // 1 forces the persistent kernel, 0 forbids it
+    const int fused_env = env ? atoi(env) : -1;
+    const bool small = n_items <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
+    mc3d_refine_problem prob = *pb;
+    if (fused_env == 1 || (fused_env != 0 && small)) {
+        auto kern = refine_fused2_kernel<T>;
+        int per_sm = 0;
+        MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RF_THREADS, 0));
+        if (per_sm < 1) { set_error("persistent refinement kernel does not fit on an SM"); return MC3D_ERR_UNSUPPORTED; }
+        if (per_sm > MC3D_RF_GRID) per_sm = MC3D_RF_GRID;
+        long long grid = (n_items + RF_THREADS - 1) / RF_THREADS;
+        if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;      // all blocks co-resident
+        if (grid < 1) grid = 1;
+        int parity = (int)(first_step & 1);
+        long long iters = n_iters;
+        void *args[] = {(void *)&prob, (void *)&parity, (void *)&iters};
+        MC3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(RF_THREADS), args, 0, stream));
+        count_launch();
+        return MC3D_OK;
+    }
+    long long grid1 = (n_items + RF_THREADS - 1) / RF_THREADS;
+    if (grid1 > (long long)sm_count() * MC3D_RF_GRID) grid1 = (long long)sm_count() * MC3D_RF_GRID;
+    long long grid2 = (n_items * 3 + RF_THREADS * 4 - 1) / (RF_THREADS * 4);
+    if (grid2 > (long long)sm_count() * 8) grid2 = (long long)sm_count() * 8;
+    if (grid2 < 1) grid2 = 1;
+    auto one = [&](long long step, cudaStream_t s) -> int {
+        const int parity = (int)(step & 1);
+        refine_costgrad_kernel<T><<<(unsigned)grid1, RF_THREADS, 0, s>>>(prob, parity);
+        refine_step2_kernel<T><<<(unsigned)grid2, RF_THREADS, 0, s>>>(prob, parity);
+        MC3D_CUDA_TRY(cudaGetLastError());
+        return MC3D_OK;
+    };
+    long long done = 0;
+    int st = MC3D_OK;
+    if ((first_step & 1) && n_iters > 0) { st = one(first_step, stream); if (st != MC3D_OK) return st; count_launch(2); done = 1; }
+    const long long pairs = (n_iters - done) / 2;
+    if (pairs >= 4) {
+        static thread_local cudaStream_t cap_stream = nullptr;
+        if (!cap_stream) MC3D_CUDA_TRY(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const int unroll = pairs >= 32 ? 8 : 1;
+        MC3D_CUDA_TRY(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+        for (int u = 0; u < 2 * unroll && st == MC3D_OK; ++u) st = one(first_step + done + u, cap_stream);
+        cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+        if (st != MC3D_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+        MC3D_CUDA_TRY(ce);
+        MC3D_CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+        const long long launches = pairs / unroll;
+        for (long long i = 0; i < launches; ++i) MC3D_CUDA_TRY(cudaGraphLaunch(exec, stream));
+        count_launch((int)(launches * 2 * unroll * 2));
+        done += launches * 2 * unroll;
+        MC3D_CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+    }
+    for (; done < n_iters; ++done) { st = one(first_step + done, stream); if (st != MC3D_OK) return st; count_launch(2); }
+    return MC3D_OK;
+}
+
 // n whole-window iterations inside one persistent cooperative kernel (needs the exchange block for its barriers).
 template <typename T>
 int refine_run_fused(const mc3d_refine_problem *pb, long long first_step, long long n_iters, cudaStream_t stream) {
@@ -871,6 +1226,17 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
     int st = validate(pb);
     if (st != MC3D_OK) return st;
     long long done = 0;
+    if (pb->gc && pb->xchg[0] && n_iters > 0 && pb->n_frames > 0) {
+        // Measured on B200 (float state, us per step at 400 / 12 500 / 100 000 frames x 17 joints on one GPU):
+        //   two-phase persistent 14.6 / 28 / 144, three-phase persistent 18 / 32 / 144, graph of three kernels
+        //   17 / 40 / 134, graph of two kernels 17 / 43 / 164.  The two-phase step moves 25 % more bytes (four gradient
+        //   components instead of one), so it wins while a step is latency-bound and loses once it is bandwidth-bound.
+        const char *env2 = getenv("MC3D_REFINE_TWO_PHASE");          // 1 forces the two-phase step, 0 forbids it
+        const int two_env = env2 ? atoi(env2) : -1;
+        const long long n_items2 = (long long)pb->n_frames * pb->n_joints;
+        const bool small2 = n_items2 <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
+        if (two_env == 1 || (two_env != 0 && small2)) return refine_run_two_phase<T>(pb, first_step, n_iters, stream);
+    }
     if (pb->xchg[0] && n_iters > 0 && pb->n_frames > 0) {
         // The persistent kernel wins while a phase is latency-bound (few items per thread: no launch boundaries,
         // cheaper barriers); for big shards the three separate kernels run at higher occupancy and win.  Measured
@@ -878,7 +1244,7 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
         const char *env = getenv("MC3D_REFINE_FUSED");              // read per call: tests switch it; 1 forces, 0 forbids
         const int fused_env = env ? atoi(env) : -1;
         const long long n_items = (long long)pb->n_frames * pb->n_joints;
-        const bool small = n_items <= 8LL * sm_count() * 2 * RF_THREADS;
+        const bool small = n_items <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
         if (fused_env == 1 || (fused_env != 0 && small)) return refine_run_fused<T>(pb, first_step, n_iters, stream);
     }
     auto one = [&](long long step, cudaStream_t s) -> int {
@@ -917,6 +1283,23 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
     return MC3D_OK;
 }
 
+// What refine_run would launch for this problem (same decisions, no launch).
+static const char *refine_plan(const mc3d_refine_problem *pb) {
+    if (!pb) return "invalid";
+    const long long n_items = (long long)pb->n_frames * pb->n_joints;
+    const bool small = n_items <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
+    const char *e2 = getenv("MC3D_REFINE_TWO_PHASE"), *ef = getenv("MC3D_REFINE_FUSED");
+    const int two_env = e2 ? atoi(e2) : -1, fused_env = ef ? atoi(ef) : -1;
+    const bool fused = fused_env == 1 || (fused_env != 0 && small);
+    if (pb->gc && pb->xchg[0] && (two_env == 1 || (two_env != 0 && small)))
+        return fused ? "two-phase step, persistent cooperative kernel (2 grid barriers, 1 exchange of 17 sums + halo stores per step)"
+                     : "two-phase step, CUDA graph of 2 kernels per step (1 exchange of 17 sums + halo stores per step)";
+    if (pb->xchg[0])
+        return fused ? "three-phase step, persistent cooperative kernel (3 grid barriers, 2 exchanges + halo stores per step)"
+                     : "three-phase step, CUDA graph of 3 kernels per step with the in-kernel exchange (2 exchanges + halo stores per step)";
+    return "three-phase step, CUDA graph of 3 kernels per step (one rank, or host-driven exchange)";
+}
+
 template <typename T>
 int refine_flags(const mc3d_refine_problem *pb, cudaStream_t stream) {
     int st = validate(pb);
@@ -948,6 +1331,7 @@ int refine_prepare(const T *d_gauss, long long n_frames, int n_cams, int n_joint
 
 extern "C" {
 int mc3d_refine_problem_size(void) { return (int)sizeof(mc3d_refine_problem); }
+const char *mc3d_refine_plan(const mc3d_refine_problem *pb) { return mc3d::refine_plan(pb); }
 int mc3d_project_points_f32(const float *d_points, int64_t n, const double *cam26, int ignore_distortions, float *d_out, void *stream) {
     return mc3d::project_points<float>(d_points, n, cam26, ignore_distortions, d_out, (cudaStream_t)stream);
 }

@@ -285,6 +285,9 @@ class RefineEngine:
         self.v = torch.zeros_like(self.m)
         self.best = torch.zeros_like(self.m)
         self.g = torch.zeros_like(self.m)
+        # two-phase step (csrc/refine.cu costgrad_loop): likelihood, smoothness and the two bone-length components
+        # (four components at a stride of n*J*3 rounded up to a multiple of 4 scalars)
+        self.gc = torch.zeros((4 * ((n * self.J * 3 + 3) // 4 * 4),), dtype=dt, device=dev) if self.peer is not None else None
         self.term_ok = torch.zeros((n + 4,), dtype=torch.uint8, device=dev)
         self.mu0 = torch.zeros((n, self.J, 2), dtype=dt, device=dev)
         self.S = torch.zeros((n, self.J, 3), dtype=dt, device=dev)
@@ -337,6 +340,7 @@ class RefineEngine:
             setattr(pb, name, getattr(self, name).data_ptr())
         pb.x = self.x_ext.data_ptr()
         if self.peer is not None:
+            pb.gc = self.gc.data_ptr()
             pb.rank, pb.world = self.comm.rank, self.comm.world
             if self.comm.rank > 0:
                 lb, le = frame_shard(self.total_frames, self.comm.rank - 1, self.comm.world)
@@ -435,6 +439,15 @@ class RefineEngine:
                         done += 2
         for _ in range(n_iters - done):
             self.one_step(True)
+
+    def plan(self):
+        """What ``run`` launches for this engine (text from the library)."""
+        if self.device.type != 'cuda' or not hasattr(self.phases, 'run_fn'):
+            return 'host-driven phases'
+        if self.comm.world > 1 and self.peer is None:
+            return 'three-phase step, host-driven exchange over torch.distributed (NCCL), 2-step CUDA graph'
+        with self.torch.cuda.device(self.device):
+            return _lib.lib().mc3d_refine_plan(ctypes.byref(self.problem)).decode()
 
     def release_graph(self):
         """Drop the captured multi-rank graph (it holds NCCL kernels: release it before the process group goes away)."""
