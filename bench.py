@@ -137,7 +137,7 @@ def _cpu_worker(args):
     return n * reps, time.perf_counter() - t0
 
 
-def cpu_baseline_run(n_views, per_worker=100_000, reps=3, workers=None):
+def cpu_baseline_run(n_views, per_worker=100_000, reps=16, workers=None):
     """Oracle port over all host cores (one process per core, frames split in blocks)."""
     import multiprocessing as mp
     workers = workers or (os.cpu_count() or 1)
@@ -194,7 +194,7 @@ def run_reference(args, rank, world):
         return
     import multiprocessing as mp
     frames, n_views, io = WORKLOADS[args.workload]
-    per_worker = 50_000
+    per_worker = 200_000
     workers = os.cpu_count() or 1
     t_all = time.perf_counter()
     total, wall = 0, 0.0
@@ -340,14 +340,17 @@ def run_ours(args, rank, local_rank, world):
     line = {
         'metric': 'joints_triangulated_per_sec', 'value': value, 'unit': 'joints/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32+f64' if io == 'f32' else 'f64',     # f32 storage: float normal equations, double residuals
+        'data': 'synthetic',
         'config': {'workload': args.workload, 'views': n_views, 'joints_per_frame': JOINTS, 'frames_per_gpu': frames,
                    'joints_per_gpu': n, 'io_dtype': io, 'layout': '(N, V, 3) [x, y, w]', 'mode': 'weighted',
                    'l2': f'inputs {n * 3 * n_views * esize / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)',
                    'sharding': 'frames across ranks, no collective'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': recorded_traffic(args.workload), 'peak_source': peak_src,
-                     'algorithmic_bytes_per_joint': algo_bytes_per_joint, 'kernel': 'mc3d::triangulate_kernel',
+                     'algorithmic_bytes_per_joint': algo_bytes_per_joint,
+                     'kernel': f'mc3d::triangulate_mixed_kernel<{n_views}, layout>' if io == 'f32' else f'mc3d::triangulate_kernel<double, {n_views}, weighted>',
                      'frac_of_nominal_8TBs': achieved / 8000.0},
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }
@@ -357,6 +360,9 @@ def run_ours(args, rank, local_rank, world):
         try:
             line['refine'] = {'T100k_f32': refine_benchmark(100_000, 400, 'f32', device),
                               'T400_f32': refine_benchmark(400, 2000, 'f32', device)}
+            # the per-GPU shard sizes of config 4 at 2 / 4 / 8 GPUs, on one GPU (no exchange partner)
+            for nf in (50_000, 25_000, 12_500):
+                line['refine'][f'T{nf}_f32'] = refine_benchmark(nf, 400, 'f32', device)
         except Exception as exc:
             line['refine'] = {'error': repr(exc)}
     if world == 1 and not args.no_extras:

@@ -1247,6 +1247,13 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
         const bool small = n_items <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
         if (fused_env == 1 || (fused_env != 0 && small)) return refine_run_fused<T>(pb, first_step, n_iters, stream);
     }
+    // One rank, big shard: the exchange protocol (tickets, fences, flags) would only cost time -- run the plain kernels.
+    mc3d_refine_problem plain = *pb;
+    if (pb->world <= 1) {
+        plain.world = plain.rank = 0;
+        for (int r = 0; r < MC3D_MAX_PEERS; ++r) plain.xchg[r] = nullptr;
+        pb = &plain;
+    }
     auto one = [&](long long step, cudaStream_t s) -> int {
         for (int ph = 0; ph < 3; ++ph) {
             int s2 = refine_phase<T>(pb, ph, step, 1, s);
@@ -1294,9 +1301,10 @@ static const char *refine_plan(const mc3d_refine_problem *pb) {
     if (pb->gc && pb->xchg[0] && (two_env == 1 || (two_env != 0 && small)))
         return fused ? "two-phase step, persistent cooperative kernel (2 grid barriers, 1 exchange of 17 sums + halo stores per step)"
                      : "two-phase step, CUDA graph of 2 kernels per step (1 exchange of 17 sums + halo stores per step)";
-    if (pb->xchg[0])
-        return fused ? "three-phase step, persistent cooperative kernel (3 grid barriers, 2 exchanges + halo stores per step)"
-                     : "three-phase step, CUDA graph of 3 kernels per step with the in-kernel exchange (2 exchanges + halo stores per step)";
+    if (pb->xchg[0] && fused)
+        return "three-phase step, persistent cooperative kernel (3 grid barriers, 2 exchanges + halo stores per step)";
+    if (pb->xchg[0] && pb->world > 1)
+        return "three-phase step, CUDA graph of 3 kernels per step with the in-kernel exchange (2 exchanges + halo stores per step)";
     return "three-phase step, CUDA graph of 3 kernels per step (one rank, or host-driven exchange)";
 }
 

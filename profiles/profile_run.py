@@ -1,7 +1,7 @@
 """Short fixed sequence of every hot-path kernel, for ncu (launch list and --set full captures).
 
     python profiles/profile_run.py            # plain run, prints CUDA-event times per kernel
-    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'triangulate_kernel|decode_|refine_' ... python profiles/profile_run.py
+    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'triangulate_|decode_|refine_' ... python profiles/profile_run.py
 """
 import os
 import sys
@@ -63,8 +63,15 @@ def main():
                               betas=(0.9, 0.999), lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
                               max_iter=10 ** 9, ignore_distortions=False, window=(0, 100_000), n_window_frames=100_000,
                               hist_capacity=64)
-        ms = timed(lambda: eng.one_step(True), reps=4)
+        ms = timed(lambda: eng.run(16), reps=4) / 16
         out['refine_step_f32_T100k'] = (ms, 1e3 / ms, 100_000 * 17 * 160 / ms / 1e6)
+        eng.close()
+        eng = rf.RefineEngine(init[:12500], gs[:12500], rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=torch.float32, device=dev, lr=0.01,
+                              betas=(0.9, 0.999), lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
+                              max_iter=10 ** 9, ignore_distortions=False, window=(0, 12_500), n_window_frames=12_500, hist_capacity=64)
+        ms = timed(lambda: eng.run(16), reps=4) / 16           # one persistent launch = 16 steps
+        out['refine_step_f32_T12500'] = (ms, 1e3 / ms, 12_500 * 17 * 200 / ms / 1e6)
+        eng.close()
     if only:
         for k, (ms, rate, gbs) in out.items():
             print(f'{k:28s} {ms:9.4f} ms  {rate:14.4g} units/s  {gbs:8.1f} GB/s algorithmic')
@@ -80,11 +87,15 @@ def main():
         eng = rf.RefineEngine(init, gs, rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=dt, device=dev, lr=0.01, betas=(0.9, 0.999),
                               lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5, max_iter=10 ** 9,
                               ignore_distortions=False, window=(0, 100_000), n_window_frames=100_000, hist_capacity=64)
-        for ph, name in enumerate(('costs', 'grad', 'step')):
-            # phases are idempotent enough for timing when run out of order on the same step index
-            pass
-        ms = timed(lambda: eng.one_step(True), reps=4)
+        ms = timed(lambda: eng.run(16), reps=4) / 16
         out[f'refine_step_{io}_T100k'] = (ms, 1e3 / ms, 0.0)
+        eng.close()
+        eng = rf.RefineEngine(init[:12500], gs[:12500], rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=dt, device=dev, lr=0.01,
+                              betas=(0.9, 0.999), lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
+                              max_iter=10 ** 9, ignore_distortions=False, window=(0, 12_500), n_window_frames=12_500, hist_capacity=64)
+        ms = timed(lambda: eng.run(16), reps=4) / 16           # one persistent launch = 16 steps
+        out[f'refine_step_{io}_T12500'] = (ms, 1e3 / ms, 0.0)
+        eng.close()
     for k, (ms, rate, gbs) in out.items():
         print(f'{k:28s} {ms:9.4f} ms  {rate:14.4g} units/s  {gbs:8.1f} GB/s algorithmic')
 
