@@ -253,6 +253,32 @@ int mc3d_peer_close(void *d_ptr);
 int mc3d_peer_free(void *d_ptr);
 
 
+/* ---- 3b. one camera's extrinsics from sampled points ---------------------------------------------------------
+ * The optimize_trajectory=False / extrinsic_optimization_IDs=[id] branch of sgd_optimize (pose_refinement.py:915-1091,
+ * cost :800-831): N samples per (frame, joint) -- drawn from the two ground-truth cameras' Gaussians (:684-706) and
+ * triangulated (mc3d_triangulate_*) -- are projected with the learnt camera and scored with 0.5 d^T S d against one
+ * Gaussian per (frame, joint); the mean over the finite samples is minimised over the 9 entries of R and the 3 of T
+ * with clip_grad_norm_(1.0) + Adam and the same running-mean early stopping as the trajectory optimiser.
+ *   samples3d (T, J, N, 3), mean (T, J, 2), S (T, J, 3) [s00 s01 s11]: device, state dtype
+ *   params   48 device doubles: R[9] T[3] | Adam m[12] | v[12] | best R, T[12]
+ *   ctrl     device doubles >= 64 + 2 * hist_capacity, zero-filled except ctrl[32+3] = ctrl[48+3] = +inf:
+ *            [0..13]+16p sums (cost, count, dR[9], dT[3]); [32..39]+16p state as in mc3d_refine_problem;
+ *            [64+2s..] history of step s: sample cost, total cost (= sample cost + const_cost)            */
+typedef struct {
+    int64_t n_frames;
+    int32_t n_joints, n_samples, ignore_distortions, patience, max_iter, reserved;
+    int64_t hist_capacity;
+    double lr, beta1, beta2, eps, tolerance;
+    double const_cost;       /* smoothness + bone-length cost of the fixed trajectory (:984-986) */
+    double K[9], dist[5];    /* intrinsics of the learnt camera */
+    const void *samples3d, *mean, *S;
+    double *params, *ctrl;
+} mc3d_extrinsic_problem;
+int mc3d_extrinsic_problem_size(void);
+int mc3d_extrinsic_run_f32(const mc3d_extrinsic_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
+int mc3d_extrinsic_run_f64(const mc3d_extrinsic_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
+
+
 /* ---- 4. linear interpolation (pose_refinement.py:15-84) ---------------------------------------------------
  * d_points / d_out: (n_frames, scalars_per_frame) doubles, scalars_per_frame = joints x dims.  Per scalar and frame:
  * window of k//2 frames each side, outliers outside mean +- k_std*std and (optionally) median +- median_std*MAD are

@@ -71,6 +71,18 @@ class RefineXchg(ctypes.Structure):
                 ('seq2', (ctypes.c_int64 * MAX_PEERS) * 2)]
 
 
+class ExtrinsicProblem(ctypes.Structure):
+    """mc3d_extrinsic_problem (include/mc3d.h)."""
+    _fields_ = [('n_frames', ctypes.c_int64), ('n_joints', ctypes.c_int32), ('n_samples', ctypes.c_int32),
+                ('ignore_distortions', ctypes.c_int32), ('patience', ctypes.c_int32), ('max_iter', ctypes.c_int32),
+                ('reserved', ctypes.c_int32), ('hist_capacity', ctypes.c_int64),
+                ('lr', ctypes.c_double), ('beta1', ctypes.c_double), ('beta2', ctypes.c_double), ('eps', ctypes.c_double),
+                ('tolerance', ctypes.c_double), ('const_cost', ctypes.c_double),
+                ('K', ctypes.c_double * 9), ('dist', ctypes.c_double * 5),
+                ('samples3d', ctypes.c_void_p), ('mean', ctypes.c_void_p), ('S', ctypes.c_void_p),
+                ('params', ctypes.c_void_p), ('ctrl', ctypes.c_void_p)]
+
+
 _lib = None
 
 _c_i64 = ctypes.c_int64
@@ -105,6 +117,9 @@ SIGNATURES = {
     'mc3d_refine_phase_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_int, _c_i64, _c_int, _c_vp]),
     'mc3d_refine_run_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_i64, _c_i64, _c_vp]),
     'mc3d_refine_run_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_i64, _c_i64, _c_vp]),
+    'mc3d_extrinsic_problem_size': (_c_int, []),
+    'mc3d_extrinsic_run_f32': (_c_int, [ctypes.POINTER(ExtrinsicProblem), _c_i64, _c_i64, _c_vp]),
+    'mc3d_extrinsic_run_f64': (_c_int, [ctypes.POINTER(ExtrinsicProblem), _c_i64, _c_i64, _c_vp]),
     'mc3d_peer_alloc': (_c_int, [_c_i64, ctypes.POINTER(_c_vp), _c_vp]),
     'mc3d_peer_open': (_c_int, [_c_vp, ctypes.POINTER(_c_vp)]),
     'mc3d_peer_close': (_c_int, [_c_vp]),
@@ -127,6 +142,8 @@ def lib():
             fn.argtypes = args
         if handle.mc3d_refine_problem_size() != ctypes.sizeof(RefineProblem):
             raise Mc3dError('mc3d_refine_problem layout mismatch between include/mc3d.h and _lib.py')
+        if handle.mc3d_extrinsic_problem_size() != ctypes.sizeof(ExtrinsicProblem):
+            raise Mc3dError('mc3d_extrinsic_problem layout mismatch between include/mc3d.h and _lib.py')
         _lib = handle
     return _lib
 

@@ -11,13 +11,20 @@ used for every camera; Gaussian means are compared with image-pixel projections 
 running mean over a list that also holds its own earlier values.  ``per_camera_gaussians=True`` is NOT offered:
 the kernel keeps one Gaussian per (frame, joint) because that is what upstream evaluates.
 
-Out of scope (raise NotImplementedError): learning extrinsics (``extrinsic_optimization_IDs``,
-``optimize_trajectory=False``), ``use_NN``, ``randomize_params`` -- SURVEY.md section 8(f3).
+``sgd_optimize(extrinsic_optimization_IDs=[id], optimize_trajectory=False, GT_camera_IDs=[a, b])`` learns one
+camera's extrinsics from points sampled from the two ground-truth cameras' Gaussians (pose_refinement.py:684-706,
+:800-831, :915-1091; csrc/extrinsic.cu) -- SURVEY.md section 8(f3).
+
+Out of scope (raise NotImplementedError): learning cameras and trajectory jointly (``extrinsic_optimization_IDs`` with
+``optimize_trajectory=True``), ``use_NN``, ``randomize_params``, and the superseded ``ExtrinsicParameterRefinement`` /
+``Trajectory_Optimization`` classes.
 """
 import argparse
+import ctypes
 import math
 import os
 import pickle as pk
+import random
 from pathlib import Path
 
 import numpy as np
@@ -157,10 +164,17 @@ class Optimized_3d_Pose_Estimation:
                      ignore_distortions=False, reset_camera_params=False, print_compute_times=False,
                      time_interval=[0, -1], randomize_params=False, use_NN=False):
         torch = _torch()
-        if len(extrinsic_optimization_IDs) or not optimize_trajectory:
-            raise NotImplementedError('learning camera extrinsics is outside the accelerated path (SURVEY.md 8(f3))')
         if use_NN or randomize_params:
             raise NotImplementedError('use_NN / randomize_params are outside the accelerated path (SURVEY.md 8(f3))')
+        if extrinsic_optimization_IDs is not None and optimize_trajectory is False:
+            return self._learn_extrinsics_from_samples(extrinsic_optimization_IDs, GT_camera_IDs, lr=lr, betas=betas,
+                                                       lambda_smooth=lambda_smooth, lambda_body_length=lambda_body_length,
+                                                       patience=patience, tolerance=tolerance, max_iter=max_iter,
+                                                       print_frequency=print_frequency, batch_size=batch_size,
+                                                       ignore_distortions=ignore_distortions,
+                                                       reset_camera_params=reset_camera_params, time_interval=time_interval)
+        if extrinsic_optimization_IDs is not None and len(extrinsic_optimization_IDs):
+            raise NotImplementedError('learning cameras and trajectory jointly is outside the accelerated path (SURVEY.md 8(f3))')
         if self.body_lengths is None:
             raise AttributeError("'NoneType' object has no attribute 'values'")   # create_body_length_vect, :770
 
@@ -251,6 +265,193 @@ class Optimized_3d_Pose_Estimation:
         self.all_costs_total = {}
         for nm in names:
             self.all_costs_total[nm] = _interleave_history(hist[:, col[nm]], len(windows), self.torch_dtype)
+        self.iterations = st['iterations']
+        return self
+
+
+    # ---- one camera's extrinsics from sampled points (pose_refinement.py:684-706, :800-831, :915-1091) -----------------
+    def sample_gaussians(self, N=None):
+        """N pixel samples per (frame, GT camera, joint) from the 2D Gaussians, (Time, n_joints, N, 2, 2); the same
+        numpy call in the same order as upstream (pose_refinement.py:684-706), so a seeded ``np.random`` gives the
+        same draws."""
+        if N is None:
+            N = self.N_sample_points
+        g = self.gaussians_subset
+        means = g[:, self.GT_camera_IDs, :, :2]
+        covs = g[:, self.GT_camera_IDs, :, 2:].reshape(self.Time, 2, self.n_joints, 2, 2)
+        samples = np.empty((self.Time, 2, self.n_joints, N, 2))
+        for t in range(self.Time):
+            for cam in range(2):
+                for point in range(self.n_joints):
+                    samples[t, cam, point] = np.random.multivariate_normal(means[t, cam, point].numpy(), covs[t, cam, point].numpy(), N)
+        self.samples = np.transpose(samples, (0, 2, 3, 1, 4))
+        return self.samples
+
+    def _fixed_trajectory_costs(self, trajectory, device, lambda_smooth, lambda_body_length):
+        """Smoothness / bone-length cost of a trajectory that is not being optimised (constants of the total,
+        pose_refinement.py:984-986), from one launch of the cost kernel."""
+        torch = _torch()
+        cam_rows = _ref.camera_rows(self.decomposed_cam_params, self.camera_IDs[:1])
+        cam_rows = torch.tensor(cam_rows, dtype=self.torch_dtype).to(torch.float64).numpy()
+        eng = _ref.RefineEngine(trajectory, self.gaussians_subset, cam_rows, self.body_lengths, torch_dtype=self.torch_dtype,
+                                device=device, lr=0.0, betas=(0.9, 0.999), lambda_smooth=lambda_smooth,
+                                lambda_body_length=lambda_body_length, patience=1, tolerance=0.0, max_iter=1,
+                                ignore_distortions=True, window=(0, self.Time), n_window_frames=self.Time, hist_capacity=4,
+                                comm=_ref.LocalComm(), use_exchange=False)
+        with torch.cuda.device(device):
+            eng.phases.phase(eng.problem, 0, 0, True, torch.cuda.current_stream().cuda_stream)
+            acc = eng.ctrl[:8].cpu().numpy()
+        out = {}
+        if lambda_smooth > 0:
+            out['smoothness_cost'] = lambda_smooth * acc[2] / acc[3] if acc[3] else float('nan')
+        if lambda_body_length > 0:
+            mu = acc[4] / acc[5]
+            out['body_length_cost'] = lambda_body_length * (acc[6] - 2.0 * mu * acc[4] + mu * mu * acc[5]) / eng.problem.aa
+        return out
+
+    def _learn_extrinsics_from_samples(self, extrinsic_optimization_IDs, GT_camera_IDs, *, lr, betas, lambda_smooth,
+                                       lambda_body_length, patience, tolerance, max_iter, print_frequency, batch_size,
+                                       ignore_distortions, reset_camera_params, time_interval):
+        torch = _torch()
+        if batch_size is not None:
+            raise NotImplementedError('batch_size windows are not supported when learning extrinsics from samples')
+        if self.body_lengths is None:
+            raise AttributeError("'NoneType' object has no attribute 'values'")   # create_body_length_vect, :770
+        t0, t1 = time_interval[0], time_interval[1]
+        self.gaussians_subset = self.gaussians[t0:t1]
+        self.Time = len(self.gaussians_subset)
+        if reset_camera_params:
+            self.decomposed_cam_params = {cid: [cp.clone().detach() for cp in self.decomposed_cam_params_initial[cid]]
+                                          for cid in self.decomposed_cam_params_initial}
+        self.n_cams = len(self.camera_IDs)
+        self.GT_camera_IDs = GT_camera_IDs
+        self.ignore_distortions = ignore_distortions
+        self.learning_extrinsics_from_samples = True
+        self.extrinsic_optimization_IDs = extrinsic_optimization_IDs
+        if self.GT_camera_IDs is None:
+            raise TypeError("'NoneType' object is not iterable")                 # upstream's default expression, :920
+        assert len(self.extrinsic_optimization_IDs) == 1
+        assert len(self.GT_camera_IDs) == 2
+        assert min([idx in self.decomposed_cam_params.keys() for idx in self.GT_camera_IDs])
+        ID = self.extrinsic_optimization_IDs[0]
+        assert ID in self.decomposed_cam_params
+        # upstream converts only the INITIAL copy to axis-angle (:934); the live 3x3 matrix is what gets optimised
+        self.decomposed_cam_params_initial[ID][1] = utils.rotation_conversion(self.decomposed_cam_params_initial[ID][1], to_vector=True)
+        Rl, Tl = self.decomposed_cam_params[ID][1], self.decomposed_cam_params[ID][2]
+        if tuple(Rl.shape) != (3, 3):
+            Rl = self.decomposed_cam_params[ID][1] = utils.rotation_conversion(Rl.reshape(3), to_vector=False).to(self.torch_dtype)
+        Rl[Rl == 0] = random.random() / 10 ** 6                                  # :937-938, one draw per tensor
+        Tl[Tl == 0] = random.random() / 10 ** 6
+        self.trajectory = self.initial_trajectory[t0:t1].clone().detach()
+        self.batch_size = self.Time
+        self.lambda_smooth, self.lambda_body_length = lambda_smooth, lambda_body_length
+        device = self._pick_device()
+
+        names = ['total_cost'] + (['smoothness_cost'] if lambda_smooth > 0 else []) + \
+                (['body_length_cost'] if lambda_body_length > 0 else []) + ['extrinsic_param_sample_cost']
+        consts = self._fixed_trajectory_costs(self.trajectory, device, lambda_smooth, lambda_body_length) \
+            if (lambda_smooth > 0 or lambda_body_length > 0) else {}
+
+        self.samples = self.sample_gaussians()
+        cm1, R1, T1, d1 = self.decomposed_cam_params[self.GT_camera_IDs[0]]
+        cm2, R2, T2, d2 = self.decomposed_cam_params[self.GT_camera_IDs[1]]
+        self.samples_3d = torch.from_numpy(utils.triangulate_points(self.samples, cm1, d1, R1, T1, cm2, d2, R2, T2)).to(self.torch_dtype)
+
+        dt, tag = self.torch_dtype, ('f32' if self.torch_dtype == torch.float32 else 'f64')
+        lib = _lib.lib()
+        n_iters_max = int(max_iter) + 1 if math.isfinite(max_iter) else 2 ** 31 - 2
+        hist_cap = min(n_iters_max, 4_000_000)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream().cuda_stream
+            g_dev = self.gaussians_subset.to(device).contiguous()
+            T_, C_, J_ = int(g_dev.shape[0]), int(g_dev.shape[1]), int(g_dev.shape[2])
+            mean = torch.empty((T_, J_, 2), dtype=dt, device=device)
+            S = torch.empty((T_, J_, 3), dtype=dt, device=device)
+            scratch_mu = torch.empty_like(mean)
+            scratch_S = torch.empty_like(S)
+            prep = getattr(lib, f'mc3d_refine_prepare_{tag}')
+            # means of camera INDEX 2 (hard-coded upstream, :803); inverse covariances of camera 0 (quirk Q1, :663-668)
+            _lib.check(prep(g_dev.data_ptr(), T_, C_, J_, 2, 1e-6, mean.data_ptr(), scratch_S.data_ptr(), stream))
+            _lib.check(prep(g_dev.data_ptr(), T_, C_, J_, 0, 1e-6, scratch_mu.data_ptr(), S.data_ptr(), stream))
+            s3 = self.samples_3d.to(device).contiguous()
+            params = torch.zeros(48, dtype=torch.float64, device=device)
+            params[:9] = Rl.detach().to(torch.float64).reshape(9).to(device)
+            params[9:12] = Tl.detach().to(torch.float64).reshape(3).to(device)
+            params[36:48] = params[:12]
+            ctrl = torch.zeros(64 + 2 * hist_cap, dtype=torch.float64, device=device)
+            ctrl[32 + 3] = math.inf
+            ctrl[48 + 3] = math.inf
+            pb = _lib.ExtrinsicProblem()
+            pb.n_frames, pb.n_joints, pb.n_samples = T_, J_, int(self.samples_3d.shape[2])
+            pb.ignore_distortions = int(bool(ignore_distortions))
+            pb.patience = int(min(patience, 2 ** 31 - 1)) if math.isfinite(patience) else 2 ** 31 - 1
+            pb.max_iter = int(min(max_iter, 2 ** 31 - 2)) if math.isfinite(max_iter) else 2 ** 31 - 2
+            pb.hist_capacity = hist_cap
+            pb.lr, pb.beta1, pb.beta2, pb.eps, pb.tolerance = float(lr), float(betas[0]), float(betas[1]), 1e-8, float(tolerance)
+            pb.const_cost = float(sum(consts.values()))
+            Kl = torch.as_tensor(self.decomposed_cam_params[ID][0]).to(torch.float64).reshape(9)
+            Dl = torch.zeros(5, dtype=torch.float64)
+            dd = torch.as_tensor(self.decomposed_cam_params[ID][3]).to(torch.float64).reshape(-1)
+            Dl[:min(5, dd.numel())] = dd[:5]
+            for i in range(9):
+                pb.K[i] = float(Kl[i])
+            for i in range(5):
+                pb.dist[i] = float(Dl[i])
+            pb.samples3d, pb.mean, pb.S = s3.data_ptr(), mean.data_ptr(), S.data_ptr()
+            pb.params, pb.ctrl = params.data_ptr(), ctrl.data_ptr()
+            run = getattr(lib, f'mc3d_extrinsic_run_{tag}')
+
+            def state(step):
+                st = ctrl[32 + 16 * (step & 1):32 + 16 * (step & 1) + 8].cpu().numpy()
+                return dict(adam_step=int(st[0]), best=float(st[3]), no_improve=int(st[4]), stopped=bool(st[5]), iterations=int(st[6]))
+
+            chunk = max(1, int(print_frequency)) if print_frequency and math.isfinite(print_frequency) else 100
+            chunk = min(chunk, 1000)
+            step, printed, stopped_early = 0, 0, False
+            st = state(0)
+
+            def series(hist):
+                cols = {'extrinsic_param_sample_cost': hist[:, 0], 'total_cost': hist[:, 1]}
+                for k, v in consts.items():
+                    cols[k] = np.full(len(hist), v)
+                return cols
+
+            while st['iterations'] < n_iters_max:
+                n = min(chunk, n_iters_max - st['iterations'])
+                _lib.check(run(ctypes.byref(pb), step, n, stream))
+                step += n
+                st = state(step)
+                hist = ctrl[64:64 + 2 * st['adam_step']].cpu().numpy().reshape(-1, 2)
+                cols = series(hist)
+                if print_frequency and math.isfinite(print_frequency):
+                    while printed < st['iterations']:
+                        if printed % int(print_frequency) == 0 and not (st['stopped'] and printed == st['iterations'] - 1 and
+                                                                        st['no_improve'] >= patience):
+                            cur = {nm: _running_means(cols[nm], 1)[printed] for nm in names}
+                            print(f'Iteration {printed}: ' + ', '.join(f'{k}: {v:.2e}' for k, v in cur.items()))
+                        printed += 1
+                if st['stopped']:
+                    stopped_early = st['no_improve'] >= patience
+                    break
+            hist = ctrl[64:64 + 2 * st['adam_step']].cpu().numpy().reshape(-1, 2)
+            cols = series(hist)
+            if stopped_early:
+                cur = {nm: _running_means(cols[nm], 1)[-1] for nm in names}
+                print(f"Early stopping at iteration {st['iterations'] - 1}. " + ', '.join(f'{k}: {v:.2e}' for k, v in cur.items()))
+            p_host = params.cpu()
+        self._extrinsic_launch_plan = 'csrc/extrinsic.cu: 2 kernels per iteration, CUDA graph'
+        self.decomposed_cam_params[ID][1] = p_host[:9].reshape(3, 3).to(dt)
+        self.decomposed_cam_params[ID][2] = p_host[9:12].reshape(3, 1).to(dt)
+        improved_once = math.isfinite(st['best'])
+        self.best_trajectory = self.trajectory.clone().detach() if improved_once else None
+        if improved_once:
+            self.best_decomposed_cam_params = {k: [q.clone().detach() for q in self.decomposed_cam_params[k]]
+                                               for k in self.decomposed_cam_params}
+            self.best_decomposed_cam_params[ID][1] = p_host[36:45].reshape(3, 3).to(dt)
+            self.best_decomposed_cam_params[ID][2] = p_host[45:48].reshape(3, 1).to(dt)
+        else:
+            self.best_decomposed_cam_params = None
+        self.all_costs_total = {nm: _interleave_history(cols[nm], 1, dt) for nm in names}
         self.iterations = st['iterations']
         return self
 

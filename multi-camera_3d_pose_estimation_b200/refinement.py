@@ -248,7 +248,8 @@ class RefineEngine:
 
     def __init__(self, trajectory, gaussians, cam_rows, body_lengths, *, torch_dtype, device, lr, betas,
                  lambda_smooth, lambda_body_length, patience, tolerance, max_iter, ignore_distortions,
-                 window, n_window_frames, hist_capacity, comm=None, phases=None, gaussian_camera=0, adam_eps=1e-8):
+                 window, n_window_frames, hist_capacity, comm=None, phases=None, gaussian_camera=0, adam_eps=1e-8,
+                 use_exchange=None):
         import torch
         self.torch = torch
         self.comm = comm or LocalComm()
@@ -271,7 +272,7 @@ class RefineEngine:
         # MC3D_REFINE_PEER=0 selects the host-driven exchange / the plain three-kernel graph instead.
         mode = os.environ.get('MC3D_REFINE_PEER', '')
         self.peer = None
-        if dev.type == 'cuda' and phases is None and mode != '0':
+        if dev.type == 'cuda' and phases is None and mode != '0' and use_exchange is not False:
             if self.comm.world > 1 and min(frame_shard(self.total_frames, r, self.comm.world)[1] -
                                            frame_shard(self.total_frames, r, self.comm.world)[0]
                                            for r in range(self.comm.world)) < 2:

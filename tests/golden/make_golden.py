@@ -188,6 +188,46 @@ def golden_interp(ref_refine, syn, out):
     np.savez(os.path.join(out, 'interp.npz'), **store)
 
 
+def golden_extrinsic(ref_refine, syn, out):
+    """Learning camera 2's extrinsics from samples (pose_refinement.py:684-706, :800-831, :915-1091): four runs of the
+    unmodified reference with numpy / random / torch seeded -- float64 and float32, with and without the constant
+    smoothness / bone-length terms -- storing the samples it drew, the cost histories and the learnt R, T."""
+    import random
+    import torch
+    gs, init, cams, _ = syn.refinement_inputs(12, n_cams=3, seed=5)
+    cams = {k: [np.array(c, dtype=np.float64) for c in v] for k, v in cams.items()}
+    cams[2][2] = cams[2][2] + np.array([[15.0], [-10.0], [20.0]])          # camera 2 starts 27 mm off
+    store = dict(gaussians=gs, initial=init, versions=versions())
+    for cid, cam in cams.items():
+        for nm, arr in zip(('K', 'R', 'T', 'dist'), cam):
+            store[f'cam{cid}_{nm}'] = np.asarray(arr)
+    runs = {'plain': dict(lambda_smooth=0, lambda_body_length=0, max_iter=25),
+            'consts': dict(lambda_smooth=1e-3, lambda_body_length=1.0, max_iter=10),
+            'stop': dict(lambda_smooth=0, lambda_body_length=0, max_iter=200, patience=4, tolerance=0.05)}
+    for dt_name, dt in (('f64', torch.float64), ('f32', torch.float32)):
+        for name, kw in runs.items():
+            np.random.seed(3)
+            random.seed(3)
+            torch.manual_seed(3)
+            opt = ref_refine.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(),
+                                                          decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), N_sample_points=6, torch_dtype=dt)
+            with contextlib.redirect_stdout(io.StringIO()):
+                opt.sgd_optimize(extrinsic_optimization_IDs=[2], optimize_trajectory=False, GT_camera_IDs=[0, 1], lr=1e-3,
+                                 print_frequency=1000, time_interval=[0, 12], **kw)
+            key = f'{dt_name}_{name}'
+            store[f'{key}_samples'] = np.asarray(opt.samples)
+            store[f'{key}_samples3d'] = opt.samples_3d.numpy().astype(np.float64)
+            for cost, vals in opt.all_costs_total.items():
+                store[f'{key}_hist_{cost}'] = np.array([float(v) for v in vals])
+            store[f'{key}_R'] = opt.decomposed_cam_params[2][1].detach().numpy().astype(np.float64)
+            store[f'{key}_T'] = opt.decomposed_cam_params[2][2].detach().numpy().astype(np.float64)
+            store[f'{key}_best_R'] = opt.best_decomposed_cam_params[2][1].numpy().astype(np.float64)
+            store[f'{key}_best_T'] = opt.best_decomposed_cam_params[2][2].numpy().astype(np.float64)
+            store[f'{key}_kw'] = np.array([f'{k}={v}' for k, v in kw.items()])
+    np.savez_compressed(os.path.join(out, 'extrinsic_T12.npz'), **store)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reference', default='/root/reference')
@@ -199,7 +239,7 @@ def main():
     syn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(syn)
     ref_utils, ref_refine, ref_mm, ref_pe = import_reference(args.reference)
-    todo = args.only or ['dlt', 'pose3d', 'moments', 'refine', 'interp']
+    todo = args.only or ['dlt', 'pose3d', 'moments', 'refine', 'interp', 'extrinsic']
     if 'dlt' in todo:
         golden_dlt(ref_utils, syn, HERE)
     if 'pose3d' in todo:
@@ -210,6 +250,8 @@ def main():
         golden_refine(ref_refine, ref_utils, syn, HERE)
     if 'interp' in todo:
         golden_interp(ref_refine, syn, HERE)
+    if 'extrinsic' in todo:
+        golden_extrinsic(ref_refine, syn, HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)), 'bytes')
