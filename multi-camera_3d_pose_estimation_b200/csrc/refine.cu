@@ -28,7 +28,7 @@ constexpr int RF_THREADS = 256;
 #define MC3D_RF_GRID 8
 #endif
 #ifndef MC3D_RF_SMALL
-#define MC3D_RF_SMALL 17         // items per thread of a full persistent grid (2 CTAs/SM) up to which a shard counts as small (~76k frames x 17 joints)
+#define MC3D_RF_SMALL 34         // shards up to MC3D_RF_SMALL x SMs x 512 items (~150 000 frames x 17 joints) run the two-phase persistent kernel
 #endif
 // control block layout (doubles)
 constexpr int CT_ACC = 0;        // + 16 * parity : S_lik N_lik S_s N_s ab bb aa_ok gnorm2
@@ -970,8 +970,11 @@ refine_step2_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
 }
 
 // All iterations inside one persistent cooperative kernel: two grid barriers per step.
-template <typename T>
-__global__ void __launch_bounds__(RF_THREADS)
+// BLOCKS = CTAs per SM the register allocation is held to: 2 = up to 128 registers (fastest while
+// a step is latency-bound), 3 = 80 registers (fastest from ~25 000 frames x 17 joints per GPU up: 122 vs 144 us per
+// step at 100 000 frames).
+template <typename T, int BLOCKS>
+__global__ void __launch_bounds__(RF_THREADS, BLOCKS)
 refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_parity, long long n_iters) {
     __shared__ double red[8 * NS2];
     __shared__ RefineTables tb;
@@ -1143,7 +1146,8 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
     const bool small = n_items <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
     mc3d_refine_problem prob = *pb;
     if (fused_env == 1 || (fused_env != 0 && small)) {
-        auto kern = refine_fused2_kernel<T>;
+        const bool big = n_items > 425000;
+        auto kern = big ? refine_fused2_kernel<T, 3> : refine_fused2_kernel<T, 2>;
         int per_sm = 0;
         MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RF_THREADS, 0));
         if (per_sm < 1) { set_error("persistent refinement kernel does not fit on an SM"); return MC3D_ERR_UNSUPPORTED; }
@@ -1228,9 +1232,10 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
     long long done = 0;
     if (pb->gc && pb->xchg[0] && n_iters > 0 && pb->n_frames > 0) {
         // Measured on B200 (float state, us per step at 400 / 12 500 / 100 000 frames x 17 joints on one GPU):
-        //   two-phase persistent 14.6 / 28 / 144, three-phase persistent 18 / 32 / 144, graph of three kernels
+        //   two-phase persistent 14.5 / 28 / 122, three-phase persistent 18 / 32 / 144, graph of three kernels
         //   17 / 40 / 134, graph of two kernels 17 / 43 / 164.  The two-phase step moves 25 % more bytes (four gradient
-        //   components instead of one), so it wins while a step is latency-bound and loses once it is bandwidth-bound.
+        //   components instead of one) but evaluates the projections once and has one reduction fewer; beyond the
+        //   sizes measured (MC3D_RF_SMALL) the byte count is assumed to win and the three-kernel graph is used.
         const char *env2 = getenv("MC3D_REFINE_TWO_PHASE");          // 1 forces the two-phase step, 0 forbids it
         const int two_env = env2 ? atoi(env2) : -1;
         const long long n_items2 = (long long)pb->n_frames * pb->n_joints;
