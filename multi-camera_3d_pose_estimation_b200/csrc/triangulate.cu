@@ -506,6 +506,33 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
         if (state[j] == 2) state[j] = 1;                         // did not converge in 6 passes
 }
 
+// Shared-memory rows.  One thread reads one joint's row, so a row of r 16-byte units with r a multiple of 8 puts every
+// lane of a warp on the same banks (double storage, V = 16: r = 24 -> 32-way conflicts; `short_scoreboard` 5 warps per
+// issue, 39 % of the roofline).  Such rows are copied one by one (each thread issues the bulk copy of its own row;
+// all of them complete on the stage's mbarrier) into slots of r + 1 units, which is conflict-free: +45 % for that
+// kernel.  For r = 12 (double, V = 8: 8-way) and r = 6 (float, V = 8: 2-way) the grouped variant (G = 8 / gcd(r, 8)
+// rows per copy, one padding unit per group) removes the conflicts too, but the 64-128 small TMA copies per tile cost
+// as much as they save (double V = 8: +-0 %, float V = 8: -12 %), so those keep the single contiguous bulk copy.
+struct RowPlan {
+    int group;        // rows per bulk copy (0: one contiguous copy for the whole tile)
+    int slot_elems;   // elements per group slot (group * row_elems + padding)
+};
+__host__ __device__ __forceinline__ RowPlan tri_row_plan(int row_elems, int esize) {
+    const int bytes = row_elems * esize;
+    if (bytes % 16 != 0) return RowPlan{0, 0};
+    const int r = bytes / 16;
+    if (r % 8 != 0) return RowPlan{0, 0};
+    return RowPlan{1, row_elems + 16 / esize};
+}
+__host__ __device__ __forceinline__ size_t tri_stage_elems(int tile, int row_elems, int esize) {
+    const RowPlan p = tri_row_plan(row_elems, esize);
+    return p.group ? (size_t)(tile / p.group) * p.slot_elems : (size_t)tile * row_elems;
+}
+// element offset of row `slot` of a tile inside its stage
+__device__ __forceinline__ size_t tri_row_offset(const RowPlan &p, int slot, int row_elems) {
+    return p.group ? (size_t)(slot / p.group) * p.slot_elems + (size_t)(slot % p.group) * row_elems : (size_t)slot * row_elems;
+}
+
 #ifndef MC3D_TRI_NJ
 #define MC3D_TRI_NJ 2
 #endif
@@ -530,7 +557,9 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
                          const __grid_constant__ TriParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int row_elems = 3 * V;
-    constexpr uint32_t stage_bytes = (uint32_t)(TRI_MTILE * row_elems * sizeof(float));
+    const RowPlan plan = tri_row_plan(row_elems, (int)sizeof(float));
+    constexpr uint32_t row_bytes = (uint32_t)(row_elems * sizeof(float));
+    const uint32_t stage_bytes = (uint32_t)(tri_stage_elems(TRI_MTILE, row_elems, (int)sizeof(float)) * sizeof(float));
     float *ring = reinterpret_cast<float *>(smem_raw);
     float *otile = reinterpret_cast<float *>(smem_raw + (size_t)n_stages * stage_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + 2 * TRI_MTILE * 3 * sizeof(float));
@@ -559,32 +588,41 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     }
     __syncthreads();
     auto tile_is_full = [&](long long tile) { return (tile + 1) * TRI_MTILE <= n; };
-    auto issue_load = [&](long long k, int s) {
+    auto issue_load = [&](long long k, int s) {   // every thread
         const long long tile = first + k * stride;
         if (k < my_tiles && tile_is_full(tile)) {
-            mbar_arrive_expect_tx(&full[s], stage_bytes);
-            bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes,
-                     kpts + tile * TRI_MTILE * (long long)row_elems, stage_bytes, &full[s]);
+            unsigned char *dst = reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes;
+            const float *src = kpts + tile * TRI_MTILE * (long long)row_elems;
+            if (plan.group) {
+                if (tid == 0) mbar_arrive_expect_tx(&full[s], TRI_MTILE * row_bytes);
+#pragma unroll
+                for (int j = 0; j < TRI_NJ; ++j) {
+                    const int slot = tid + j * TRI_MTHREADS;
+                    if (slot % plan.group == 0)
+                        bulk_g2s(dst + tri_row_offset(plan, slot, row_elems) * sizeof(float), src + (size_t)slot * row_elems,
+                                 plan.group * row_bytes, &full[s]);
+                }
+            } else if (tid == 0) {
+                mbar_arrive_expect_tx(&full[s], stage_bytes);
+                bulk_g2s(dst, src, stage_bytes, &full[s]);
+            }
         }
     };
-    if (tid == 0)
-        for (int k = 0; k < n_stages - 1; ++k) issue_load(k, k);
+    for (int k = 0; k < n_stages - 1; ++k) issue_load(k, k);
     int s = 0, s_next = n_stages - 1;
     uint32_t parity = 0;
     for (long long k = 0; k < my_tiles; ++k) {
         const long long tile = first + k * stride;
         const bool full_tile = tile_is_full(tile);
         float *stage = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes);
-        if (tid == 0) {
-            issue_load(k + n_stages - 1, s_next);
-            bulk_wait_read<1>();
-        }
+        issue_load(k + n_stages - 1, s_next);
+        if (tid == 0) bulk_wait_read<1>();
         if (full_tile) {
             mbar_wait(&full[s], parity);
         } else {
             const long long base = tile * TRI_MTILE * (long long)row_elems;
             const long long cnt = (n - tile * TRI_MTILE) * row_elems;
-            for (long long i = tid; i < cnt; i += TRI_MTHREADS) stage[i] = kpts[base + i];
+            for (long long i = tid; i < cnt; i += TRI_MTHREADS) stage[tri_row_offset(plan, (int)(i / row_elems), row_elems) + (i % row_elems)] = kpts[base + i];
             __syncthreads();
         }
         const float *rows[TRI_NJ];
@@ -595,7 +633,7 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
         for (int j = 0; j < TRI_NJ; ++j) {
             const int slot = tid + j * TRI_MTHREADS;
             act[j] = tile * TRI_MTILE + slot < n;
-            rows[j] = stage + (size_t)(act[j] ? slot : tid) * row_elems;      // inactive slots read a valid row
+            rows[j] = stage + tri_row_offset(plan, act[j] ? slot : tid, row_elems);      // inactive slots read a valid row
         }
         solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state);
 #pragma unroll
@@ -649,11 +687,13 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int nv = (V > 0) ? V : prm.n_views;
     const int row_elems = 3 * nv;
-    const uint32_t stage_bytes = (uint32_t)(TRI_TILE * row_elems * sizeof(T));
-    // layout: [n_stages][TILE*row] input ring | [2][TILE*3] output tiles | mbarriers | (TOP2) camera tables
+    const RowPlan plan = tri_row_plan(row_elems, (int)sizeof(T));
+    const uint32_t row_bytes = (uint32_t)(row_elems * sizeof(T));
+    const uint32_t stage_bytes = (uint32_t)(tri_stage_elems(TRI_TILE, row_elems, (int)sizeof(T)) * sizeof(T));
+    // layout: [n_stages][TILE*row_stride] input ring | [TILE*3] output tile | mbarriers | (TOP2) camera tables
     T *ring = reinterpret_cast<T *>(smem_raw);
     T *otile = reinterpret_cast<T *>(smem_raw + (size_t)n_stages * stage_bytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + 2 * TRI_TILE * 3 * sizeof(T));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + TRI_TILE * 3 * sizeof(T));
     double *cam = reinterpret_cast<double *>(full + 8);       // TOP2 only: [V][12+9+5]
 
     const int tid = threadIdx.x;
@@ -675,16 +715,23 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
     __syncthreads();
 
     auto tile_is_full = [&](long long tile) { return (tile + 1) * TRI_TILE <= n; };
-    auto issue_load = [&](long long k, int s) {   // thread 0 only; s = k % n_stages
+    auto issue_load = [&](long long k, int s) {   // every thread; s = k % n_stages
         const long long tile = first + k * stride;
         if (k < my_tiles && tile_is_full(tile)) {
-            mbar_arrive_expect_tx(&full[s], stage_bytes);
-            bulk_g2s(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes,
-                     kpts + tile * TRI_TILE * (long long)row_elems, stage_bytes, &full[s]);
+            unsigned char *dst = reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes;
+            const T *src = kpts + tile * TRI_TILE * (long long)row_elems;
+            if (plan.group) {
+                if (tid == 0) mbar_arrive_expect_tx(&full[s], TRI_TILE * row_bytes);
+                if (tid % plan.group == 0)
+                    bulk_g2s(dst + tri_row_offset(plan, tid, row_elems) * sizeof(T), src + (size_t)tid * row_elems,
+                             plan.group * row_bytes, &full[s]);
+            } else if (tid == 0) {
+                mbar_arrive_expect_tx(&full[s], stage_bytes);
+                bulk_g2s(dst, src, stage_bytes, &full[s]);
+            }
         }
     };
-    if (tid == 0)
-        for (int k = 0; k < n_stages - 1; ++k) issue_load(k, k);
+    for (int k = 0; k < n_stages - 1; ++k) issue_load(k, k);
 
     int s = 0;                     // stage of iteration k
     int s_next = n_stages - 1;     // stage of iteration k + n_stages - 1
@@ -693,10 +740,8 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
         const long long tile = first + k * stride;
         const bool full_tile = tile_is_full(tile);
         T *stage = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes);
-        if (tid == 0) {
-            issue_load(k + n_stages - 1, s_next);   // refills the stage consumed in iteration k-1
-            bulk_wait_read<1>();              // output tile (k&1) of iteration k-2 has left shared memory
-        }
+        issue_load(k + n_stages - 1, s_next);       // refills the stage consumed in iteration k-1
+        if (tid == 0) bulk_wait_read<0>();          // the output tile of iteration k-1 has left shared memory
         const long long joint = tile * TRI_TILE + tid;
         const bool active = joint < n;
         if (full_tile) {
@@ -704,7 +749,7 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
         } else {                               // ragged last tile: plain cooperative copy
             const long long base = tile * TRI_TILE * (long long)row_elems;
             const long long cnt = (n - tile * TRI_TILE) * row_elems;
-            for (long long i = tid; i < cnt; i += TRI_TILE) stage[i] = kpts[base + i];
+            for (long long i = tid; i < cnt; i += TRI_TILE) stage[tri_row_offset(plan, (int)(i / row_elems), row_elems) + (i % row_elems)] = kpts[base + i];
             __syncthreads();
         }
 
@@ -715,7 +760,7 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
         for (int i = 0; i < 10; ++i) B[i] = 0.0;
         int n_used = 0;
         if (active && !solved) {
-            const T *row = stage + (size_t)tid * row_elems;
+            const T *row = stage + tri_row_offset(plan, tid, row_elems);
             const bool l3v = prm.layout == MC3D_LAYOUT_3V;
             if (MODE == MC3D_TRI_WEIGHTED) {
 #pragma unroll
@@ -766,7 +811,7 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
             }
         }
 
-        T *ot = otile + (size_t)(k & 1) * TRI_TILE * 3;
+        T *ot = otile;
         if (full_tile) {
             ot[tid * 3 + 0] = (T)X0;
             ot[tid * 3 + 1] = (T)X1;
@@ -853,7 +898,7 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
 template <typename T, int V, int MODE, bool UNDISTORT>
 static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_out, cudaStream_t stream) {
     const int nv = prm.n_views;
-    const size_t stage_bytes = (size_t)TRI_TILE * 3 * nv * sizeof(T);
+    const size_t stage_bytes = tri_stage_elems(TRI_TILE, 3 * nv, (int)sizeof(T)) * sizeof(T);
     auto kern = triangulate_kernel<T, V, MODE, UNDISTORT>;
     static bool attr_done = false;     // per instantiation
     if (!attr_done) {
@@ -862,7 +907,7 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
     }
     // The kernel is bound by fp64 latency, not by bytes in flight: prefer more resident CTAs (warps) over a
     // deeper ring; 2 stages already cover the HBM latency at this arithmetic intensity.
-    const size_t fixed = 2 * TRI_TILE * 3 * sizeof(T) + 8 * sizeof(uint64_t) +
+    const size_t fixed = TRI_TILE * 3 * sizeof(T) + 8 * sizeof(uint64_t) +
                          (MODE == MC3D_TRI_TOP2 ? (size_t)nv * 26 * sizeof(double) : 0);
     int n_stages = 2, per_sm = 0;
     size_t smem = 0;
@@ -885,7 +930,7 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
 
 template <int V, int LAYOUT>
 static int launch_mixed(const float *d_kpts, long long n, const TriParams &prm, float *d_out, cudaStream_t stream) {
-    const size_t stage_bytes = (size_t)TRI_MTILE * 3 * V * sizeof(float);
+    const size_t stage_bytes = tri_stage_elems(TRI_MTILE, 3 * V, (int)sizeof(float)) * sizeof(float);
     auto kern = triangulate_mixed_kernel<V, LAYOUT>;
     static bool attr_done = false;
     if (!attr_done) {
