@@ -191,7 +191,7 @@ typedef struct {
 } mc3d_refine_problem;
 
 /* Exchange block at the start of each rank's peer allocation (zero-filled by mc3d_peer_alloc). */
-#define MC3D_XCHG_X_OFFSET 16384
+#define MC3D_XCHG_X_OFFSET 32768
 #define MC3D_REFINE_SUMS2 17     /* sums of the two-phase step: 7 cost sums + 10 gradient-component dot products */
 typedef struct {
     double sums[2][MC3D_MAX_PEERS][8];      /* [step parity][source rank]: S_lik N_lik S_s N_s a.b b.b a.a | gnorm^2 */
@@ -205,6 +205,7 @@ typedef struct {
     double acc2[2][24];                     /* [parity]: this rank's sums (atomic targets of its blocks) */
     double sums2[2][MC3D_MAX_PEERS][24];    /* [parity][source rank] */
     int64_t seq2[2][MC3D_MAX_PEERS];
+    int64_t ll[2][MC3D_MAX_PEERS][40];      /* persistent kernel: LL words, (step number << 32) | 32 data bits; 2 per sum */
 } mc3d_refine_xchg;
 
 /* Pinhole + 5-coefficient Brown projection of n points (n,3) -> (n,2) for one camera given as

@@ -36,7 +36,7 @@ MAX_JOINTS = 133
 MAX_BONES = 64
 MAX_PEERS = 16
 IPC_HANDLE_BYTES = 64
-XCHG_X_OFFSET = 16384
+XCHG_X_OFFSET = 32768
 CT_ACC, CT_STATE, CT_HIST = 0, 32, 64          # control-block layout (include/mc3d.h)
 
 
@@ -68,7 +68,7 @@ class RefineXchg(ctypes.Structure):
                 ('halo_seq', ctypes.c_int64 * 2), ('ticket', ctypes.c_int64 * 4), ('gen', ctypes.c_int64 * 4),
                 ('error', ctypes.c_int64),
                 ('acc2', (ctypes.c_double * 24) * 2), ('sums2', ((ctypes.c_double * 24) * MAX_PEERS) * 2),
-                ('seq2', (ctypes.c_int64 * MAX_PEERS) * 2)]
+                ('seq2', (ctypes.c_int64 * MAX_PEERS) * 2), ('ll', ((ctypes.c_int64 * 40) * MAX_PEERS) * 2)]
 
 
 class ExtrinsicProblem(ctypes.Structure):

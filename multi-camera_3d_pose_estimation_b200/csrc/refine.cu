@@ -489,10 +489,19 @@ struct GradMix {
     double mu;                             // this step's a.b / b.b (next step's mu_prev)
 };
 
+// Flag the neighbours' halos (after the caller's system fence).
+__device__ __forceinline__ void halo_flags(const mc3d_refine_problem &pb, long long seq) {
+    if (pb.rank > 0) st_relaxed_sys(&xchg_of(pb, pb.rank - 1)->halo_seq[1], seq);      // after the caller's system fence
+    if (pb.rank < pb.world - 1) st_relaxed_sys(&xchg_of(pb, pb.rank + 1)->halo_seq[0], seq);
+}
+
+// boundary_first (persistent kernel, several ranks): block 0 updates the elements of the first / last two frames before
+// anything else, stores them into the neighbours' halos and flags them at once, so that the halo travels while the
+// rest of the grid is still in its Adam pass; every block skips those elements in its regular share.
 template <typename T>
 __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int parity, int end_of_iteration, double gnorm2,
                                           const double *st, const RefineDerived &dv, bool xchg, double *bias, bool both_parities,
-                                          const GradMix<T> mix) {
+                                          const GradMix<T> mix, bool boundary_first = false, long long halo_flag_seq = 0) {
     double *ctrl = pb.ctrl;
     const double gnorm = sqrt(gnorm2);
     const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
@@ -548,8 +557,46 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         if (left_halo && i < halo_n) { left_halo[i] = xi; pushed = true; }
         if (right_halo && i >= n - halo_n) { right_halo[i - (n - halo_n)] = xi; pushed = true; }
     };
+    auto grad_at = [&](long long i) -> T {
+        T gi = mix.on ? fma(mix.alpha, c1[i], fma(mix.sigma, cs[i], fma(mix.beta, c2[i], mix.gamma * c3[i]))) : g[i];
+        if (!(i >= lo && i < hi)) gi = (T)0;
+        return gi;
+    };
+    auto one_element = [&](long long i) {
+        T gi = grad_at(i), mi = m[i], vi = v[i], xi = x[i];
+        adam(gi, mi, vi, xi);
+        m[i] = mi; v[i] = vi; x[i] = xi;
+        if (improved) bestx[i] = xi;
+        if (xchg) push(i, xi);
+    };
+    const bool bf = boundary_first && (left_halo || right_halo);
+    auto is_boundary = [&](long long i) { return (left_halo && i < halo_n) || (right_halo && i >= n - halo_n); };
+    if (bf && blockIdx.x == 0) {
+        // at most 2 * halo_n elements: [0, halo_n) and [n - halo_n, n) (they may overlap on a tiny shard)
+        const long long second = (n - halo_n > halo_n) ? n - halo_n : halo_n;
+        const long long n_first = halo_n < n ? halo_n : n, n_b = n_first + (n > second ? n - second : 0);
+        for (long long q = threadIdx.x; q < n_b; q += blockDim.x) {
+            const long long i = q < n_first ? q : second + (q - n_first);
+            if (is_boundary(i)) one_element(i);
+        }
+        if (pushed) fence_sys();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_sys();
+            halo_flags(pb, halo_flag_seq);
+        }
+        pushed = false;
+    }
     for (long long i2 = tid0; i2 < n2; i2 += nthr) {
         const long long i = i2 << 1;
+        if (bf) {
+            const bool ba = is_boundary(i), bb = is_boundary(i + 1);
+            if (ba || bb) {                                        // a pair that touches the boundary: scalar, boundary part skipped
+                if (!ba) one_element(i);
+                if (!bb) one_element(i + 1);
+                continue;
+            }
+        }
         Vec2 gv;
         if (mix.on) {
             const Vec2 a1 = reinterpret_cast<const Vec2 *>(c1)[i2], as = reinterpret_cast<const Vec2 *>(cs)[i2];
@@ -570,16 +617,7 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         if (improved) reinterpret_cast<Vec2 *>(bestx)[i2] = xv;
         if (xchg) { push(i, xv.a); push(i + 1, xv.b); }
     }
-    if ((n & 1) && tid0 == 0) {                                    // odd tail
-        const long long i = n - 1;
-        T gi = mix.on ? fma(mix.alpha, c1[i], fma(mix.sigma, cs[i], fma(mix.beta, c2[i], mix.gamma * c3[i]))) : g[i];
-        if (!(i >= lo && i < hi)) gi = (T)0;
-        T mi = m[i], vi = v[i], xi = x[i];
-        adam(gi, mi, vi, xi);
-        m[i] = mi; v[i] = vi; x[i] = xi;
-        if (improved) bestx[i] = xi;
-        if (xchg) push(i, xi);
-    }
+    if ((n & 1) && tid0 == 0 && !(bf && is_boundary(n - 1))) one_element(n - 1);      // odd tail
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         double *nx = ctrl + CT_STATE + 16 * (parity ^ 1);
         nx[0] = step; nx[1] = run_sum; nx[2] = run_cnt; nx[3] = best; nx[4] = no_imp;
@@ -595,12 +633,6 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         }
     }
     return pushed;
-}
-
-// Flag the neighbours' halos once every block's stores are out (ticket 2); returns true in the last block.
-__device__ __forceinline__ void halo_flags(const mc3d_refine_problem &pb, long long seq) {
-    if (pb.rank > 0) st_relaxed_sys(&xchg_of(pb, pb.rank - 1)->halo_seq[1], seq);      // after the caller's system fence
-    if (pb.rank < pb.world - 1) st_relaxed_sys(&xchg_of(pb, pb.rank + 1)->halo_seq[0], seq);
 }
 
 template <typename T>
@@ -651,7 +683,7 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
 // neighbours' halos and releases the local generation the other blocks poll.
 template <int N, int OFF, int NTOT, bool HALO>
 __device__ __forceinline__ void grid_exchange(const mc3d_refine_problem &pb, int parity, const double *acc, int idx, bool grad_flag,
-                                              long long seq, double *tot, bool pushed) {
+                                              long long seq, double *tot, bool pushed, bool send_halo_flags = true) {
     __shared__ int is_last;
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
     if (HALO && pushed) fence_sys();
@@ -673,9 +705,9 @@ __device__ __forceinline__ void grid_exchange(const mc3d_refine_problem &pb, int
             __syncthreads();
         }
         if (threadIdx.x == 0) {
-            fence_xchg(pb);
+            if (HALO && !send_halo_flags) fence_gpu(); else fence_xchg(pb);
             if (HALO) {
-                halo_flags(pb, seq);
+                if (send_halo_flags) halo_flags(pb, seq);
                 st_relaxed_sys(&mine->gen[idx], seq);
             } else {
                 for (int r = 0; r < pb.world; ++r) {
@@ -905,6 +937,49 @@ __device__ __forceinline__ void gather2(const mc3d_refine_problem &pb, int parit
     __syncthreads();
 }
 
+// LL exchange of the NS2 sums (persistent kernel): every 8-byte word carries 32 data bits and the 32-bit sequence
+// number of the step, stored with one relaxed system-scope store per peer -- no fence between data and flag, no
+// separate flag -- and the receivers poll the words of their own block until the sequence matches (the scheme of NCCL's
+// LL protocol).  The local rank's words double as the grid barrier.
+__device__ __forceinline__ void publish2_ll(const mc3d_refine_problem &pb, int parity, long long seq) {   // last block only
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    if (threadIdx.x < 2 * NS2) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(&mine->acc2[parity][threadIdx.x >> 1]));
+        const unsigned long long half = (threadIdx.x & 1) ? (bits >> 32) : (bits & 0xffffffffULL);
+        const long long word = (long long)(((unsigned long long)(unsigned int)seq << 32) | half);
+        for (int r = 0; r < pb.world; ++r) st_relaxed_sys(&xchg_of(pb, r)->ll[parity][pb.rank][threadIdx.x], word);
+    }
+    __syncthreads();
+    if (threadIdx.x < NS2) mine->acc2[parity][threadIdx.x] = 0.0;  // ready for the step after next
+}
+
+__device__ __forceinline__ void gather2_ll(const mc3d_refine_problem &pb, int parity, long long seq, double *tot, unsigned int *halves) {
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    const unsigned int want = (unsigned int)seq;
+    const unsigned long long limit = pb.spin_timeout_ns > 0 ? (unsigned long long)pb.spin_timeout_ns : 10000000000ULL;
+    for (int q = threadIdx.x; q < 2 * NS2 * pb.world; q += blockDim.x) {
+        const int r = q / (2 * NS2), k = q - r * (2 * NS2);
+        const int64_t *w = &mine->ll[parity][r][k];
+        unsigned long long word = (unsigned long long)ld_relaxed_sys(w);
+        if ((unsigned int)(word >> 32) != want) {
+            const unsigned long long t0 = globaltimer_ns();
+            while ((unsigned int)((word = (unsigned long long)ld_relaxed_sys(w)) >> 32) != want)
+                if (globaltimer_ns() - t0 > limit) { mine->error = 3; break; }
+        }
+        halves[q] = (unsigned int)word;
+    }
+    __syncthreads();
+    if (threadIdx.x < NS2) {
+        double s = 0.0;
+        for (int r = 0; r < pb.world; ++r) {
+            const unsigned long long lo = halves[r * 2 * NS2 + 2 * threadIdx.x], hi = halves[r * 2 * NS2 + 2 * threadIdx.x + 1];
+            s += __longlong_as_double((long long)((hi << 32) | lo));
+        }
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ bool take_ticket(mc3d_refine_xchg *mine, int idx) {      // true in the last block
     __shared__ int is_last;
     __syncthreads();
@@ -981,6 +1056,7 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
     __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
     __shared__ double tot[24];
     __shared__ double bias[2];
+    __shared__ unsigned int halves[2 * NS2 * MC3D_MAX_PEERS];
     double *ctrl = pb.ctrl;
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
     load_cameras_and_tables(pb, tb, camf);
@@ -1005,13 +1081,13 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
             costgrad_loop<T>(pb, tb, camf, (T)st[8], acc);
             block_reduce_add<NS2>(acc, red, mine->acc2[parity]);
         }
-        if (take_ticket(mine, 0)) publish2(pb, parity, seq);
-        gather2(pb, parity, seq, tot);                             // grid barrier + cross-rank sums in one
+        if (take_ticket(mine, 0)) publish2_ll(pb, parity, seq);
+        gather2_ll(pb, parity, seq, tot, halves);                  // grid barrier + cross-rank sums in one
         const RefineDerived dv = derive(pb, tot, st);
         double gnorm2;
         const GradMix<T> mix = mix_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);   // mu_prev as pass 1 used it
-        const bool pushed = step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, true, mix);
-        grid_exchange<0, 0, 0, true>(pb, parity, nullptr, 2, false, seq, tot, pushed);
+        step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, true, mix, true, seq);      // halos leave first (block 0)
+        grid_exchange<0, 0, 0, true>(pb, parity, nullptr, 2, false, seq, tot, false, false);  // local barrier only
     }
 }
 
