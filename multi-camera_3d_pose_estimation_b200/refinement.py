@@ -185,18 +185,29 @@ class PeerExchange:
             self.ptrs = [None] * comm.world
             self.ptrs[comm.rank] = self.local_ptr
             self._opened = []
+            self.failed = None
             if comm.world > 1:
                 if comm.world > _lib.MAX_PEERS:
                     raise ValueError(f'at most {_lib.MAX_PEERS} ranks are supported by the in-kernel exchange')
                 handles = comm.all_gather_object(bytes(handle))
-                for r, h in enumerate(handles):
-                    if r == comm.rank:
-                        continue
-                    p = ctypes.c_void_p()
-                    hb = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(h)
-                    _lib.check(self.lib.mc3d_peer_open(hb, ctypes.byref(p)))
-                    self.ptrs[r] = p.value
-                    self._opened.append(p.value)
+                try:
+                    if os.environ.get('MC3D_PEER_FAIL') == '1':            # test hook: behave as if a peer could not be mapped
+                        raise _lib.Mc3dError('MC3D_PEER_FAIL=1')
+                    for r, h in enumerate(handles):
+                        if r == comm.rank:
+                            continue
+                        p = ctypes.c_void_p()
+                        hb = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(h)
+                        _lib.check(self.lib.mc3d_peer_open(hb, ctypes.byref(p)))
+                        self.ptrs[r] = p.value
+                        self._opened.append(p.value)
+                except _lib.Mc3dError as exc:                               # e.g. the peer's GPU is not visible to this process
+                    self.failed = str(exc)
+                # every rank must take the same path: one failure sends all of them to the host-driven exchange
+                reasons = [r for r in comm.all_gather_object(self.failed) if r]
+                if reasons:
+                    self.failed = reasons[0]
+                    self.close()
 
     def x_view(self, shape, dtype):
         """The trajectory tensor living at byte XCHG_X_OFFSET of the local allocation."""
@@ -278,6 +289,11 @@ class RefineEngine:
                                            for r in range(self.comm.world)) < 2:
                 raise ValueError('the frame-sharded refinement needs at least two frames per rank')
             self.peer = PeerExchange(self.comm, dev, (n + 4) * self.J * 3 * torch.empty((), dtype=dt).element_size())
+            if self.peer.failed:
+                import warnings
+                warnings.warn(f'in-kernel exchange unavailable ({self.peer.failed}); using the host-driven exchange')
+                self.peer = None
+        if self.peer is not None:
             self.x_ext = self.peer.x_view((n + 4, self.J, 3), dt)
         else:
             self.x_ext = torch.zeros((n + 4, self.J, 3), dtype=dt, device=dev)
