@@ -235,11 +235,9 @@ int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step
  * doubles and the halo stores (the three-phase step needs three passes and two exchanges).
  * ctrl[32 + 16p + 8] carries mu_prev.  Small shards run all iterations inside one persistent cooperative kernel
  * (two grid barriers per step), big ones replay a CUDA graph of the two kernels.
- * Without `gc`: phases 0,1,2 replayed from a CUDA graph of the three kernels.  With the
- * in-kernel exchange (xchg set, any world size) the iterations run instead inside ONE persistent cooperative kernel:
- * the three phases are separated by grid barriers (the last block to arrive does the cross-rank exchange), the
- * cameras and bone tables stay in shared memory, and there is no launch boundary per phase (MC3D_REFINE_FUSED=0 in
- * the environment selects the graph of three kernels).  Every rank must call it with the same arguments. */
+ * Without `gc`, or for shards beyond ~150 000 frames: phases 0,1,2 replayed from a CUDA graph of the three kernels
+ * (with the in-kernel exchange between them when world > 1).  MC3D_REFINE_TWO_PHASE / MC3D_REFINE_FUSED = 0 / 1 in the
+ * environment force a variant (tests, A/B timing).  Every rank must call it with the same arguments. */
 /* Text describing what mc3d_refine_run_* launches for this problem on the current device (static string). */
 const char *mc3d_refine_plan(const mc3d_refine_problem *pb);
 int mc3d_refine_run_f32(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);

@@ -673,115 +673,28 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
     }
 }
 
-// ---- persistent kernel: n iterations of A -> B -> C with grid barriers instead of launch boundaries -------------------
-// Grid barrier + cross-rank exchange in one: every block takes a ticket; the last one publishes this rank's partial
-// sums to all peers, waits for theirs, and releases the local generation flag the other blocks spin on.  After the
-// barrier every block adds the per-rank partial sums itself (in rank order -> identical on every block and rank).
-// N sums starting at acc (local, filled by the blocks' atomics) go to slot OFF; NTOT totals come back in tot[].
-// Sum barriers: the last block publishes, and EVERY block polls the per-rank flags in its own exchange block (the
-// local rank's flag doubles as the grid barrier).  HALO barrier (closes phase C): the last block flags the
-// neighbours' halos and releases the local generation the other blocks poll.
-template <int N, int OFF, int NTOT, bool HALO>
-__device__ __forceinline__ void grid_exchange(const mc3d_refine_problem &pb, int parity, const double *acc, int idx, bool grad_flag,
-                                              long long seq, double *tot, bool pushed, bool send_halo_flags = true) {
+// ---- grid barrier of the persistent kernel --------------------------------------------------------------------------
+// Every block takes a ticket; the last one resets the counter and releases the generation flag the others poll
+// (relaxed polls, one fence on each side).  A wait that never ends (the blocks were not co-resident) gives up after the
+// time-out like the cross-rank waits.
+__device__ __forceinline__ void grid_barrier(const mc3d_refine_problem &pb, int idx, long long seq) {
     __shared__ int is_last;
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
-    if (HALO && pushed) fence_sys();
     __syncthreads();
     if (threadIdx.x == 0) {
         fence_gpu();
         const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&mine->ticket[idx]), 1ULL);
         is_last = old == (unsigned long long)gridDim.x - 1ULL;
-    }
-    __syncthreads();
-    if (is_last) {
-        if (threadIdx.x == 0) { mine->ticket[idx] = 0; fence_gpu(); }
-        if (!HALO) {
-            __syncthreads();
-            if (threadIdx.x < N) {
-                const double v = __ldcg(acc + threadIdx.x);
-                for (int r = 0; r < pb.world; ++r) xchg_of(pb, r)->sums[parity][pb.rank][OFF + threadIdx.x] = v;
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            if (HALO && !send_halo_flags) fence_gpu(); else fence_xchg(pb);
-            if (HALO) {
-                if (send_halo_flags) halo_flags(pb, seq);
-                st_relaxed_sys(&mine->gen[idx], seq);
-            } else {
-                for (int r = 0; r < pb.world; ++r) {
-                    mc3d_refine_xchg *xr = xchg_of(pb, r);
-                    st_relaxed_sys(grad_flag ? &xr->seq_grad[parity][pb.rank] : &xr->seq_costs[parity][pb.rank], seq);
-                }
-            }
-        }
-    }
-    if (threadIdx.x == 0) {
-        if (HALO) {
-            xchg_wait(pb, &mine->gen[idx], seq);
+        if (is_last) {
+            mine->ticket[idx] = 0;
             fence_gpu();
+            st_relaxed_sys(&mine->gen[idx], seq);
         } else {
-            for (int r = 0; r < pb.world; ++r)
-                xchg_wait(pb, grad_flag ? &mine->seq_grad[parity][r] : &mine->seq_costs[parity][r], seq);
-            fence_xchg(pb);
+            xchg_wait(pb, &mine->gen[idx], seq);
         }
+        fence_gpu();
     }
     __syncthreads();
-    if (NTOT > 0) {
-        if (threadIdx.x < NTOT) {
-            double s = 0.0;
-            for (int r = 0; r < pb.world; ++r) s += __ldcg(&mine->sums[parity][r][threadIdx.x]);
-            tot[threadIdx.x] = s;
-        }
-        __syncthreads();
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(RF_THREADS)
-refine_fused_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_parity, long long n_iters) {
-    __shared__ double red[8 * 7];
-    __shared__ RefineTables tb;
-    __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
-    __shared__ double tot[8];
-    __shared__ double bias[2];
-    double *ctrl = pb.ctrl;
-    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
-    load_cameras_and_tables(pb, tb, camf);
-    __syncthreads();
-    int parity = first_parity & 1;
-    for (long long it = 0; it < n_iters; ++it, parity ^= 1) {
-        double st[8];                                              // state entering this step (written before the last barrier)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) st[i] = __ldcg(ctrl + CT_STATE + 16 * parity + i);
-        if (st[5] != 0.0) break;                                   // stopped: identical decision in every block and rank
-        const long long seq = (long long)st[0] + 1;
-        if (pb.world > 1) {
-            if (threadIdx.x == 0) {                                // the neighbours' boundary frames of this step are in my halo
-                if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], seq - 1);
-                if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], seq - 1);
-                fence_sys();
-            }
-            __syncthreads();
-        }
-        double *acc = ctrl + CT_ACC + 16 * parity;
-        {   // A: costs
-            double a7[7];
-            costs_loop<T>(pb, tb, camf, a7);
-            block_reduce_add<7>(a7, red, acc);
-        }
-        grid_exchange<7, 0, 7, false>(pb, parity, acc, 0, false, seq, tot, false);
-        const RefineDerived dv = derive(pb, tot, st);
-        {   // B: gradient
-            double gn[1] = {grad_loop<T>(pb, tb, camf, dv)};
-            block_reduce_add<1>(gn, red, acc + 7);
-        }
-        grid_exchange<1, 7, 8, false>(pb, parity, acc + 7, 1, true, seq, tot, false);
-        // C: clipped Adam, boundary frames into the neighbours' halos, bookkeeping
-        const bool pushed = step_loop<T>(pb, parity, 1, tot[7], st, dv, true, bias, true, GradMix<T>{false, 0, 0, 0, 0, 0.0});
-        grid_exchange<0, 0, 0, true>(pb, parity, nullptr, 2, false, seq, tot, pushed);
-    }
 }
 
 // ==== two-phase step ================================================================================================
@@ -905,9 +818,8 @@ __device__ __forceinline__ GradMix<T> mix_of(const mc3d_refine_problem &pb, cons
     return m;
 }
 
-// Grid barrier + exchange of the two-phase step (see grid_exchange): NS2 sums, flags seq2.  FUSED: called by every block
-// of the persistent kernel (the local flag doubles as the grid barrier); otherwise only the publish half runs, in the
-// last block of pass 1, and pass 2 gathers.
+// Exchange of the NS2 sums between the two kernels of the graph variant: the last block of pass 1 publishes (plain stores,
+// one system fence, a sequence flag per peer), pass 2 gathers.
 __device__ __forceinline__ void publish2(const mc3d_refine_problem &pb, int parity, long long seq) {   // last block only
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
     if (threadIdx.x < NS2) {
@@ -1087,7 +999,7 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
         double gnorm2;
         const GradMix<T> mix = mix_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);   // mu_prev as pass 1 used it
         step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, true, mix, true, seq);      // halos leave first (block 0)
-        grid_exchange<0, 0, 0, true>(pb, parity, nullptr, 2, false, seq, tot, false, false);  // local barrier only
+        grid_barrier(pb, 2, seq);                                   // closes the step; local only
     }
 }
 
@@ -1278,27 +1190,6 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
     return MC3D_OK;
 }
 
-// n whole-window iterations inside one persistent cooperative kernel (needs the exchange block for its barriers).
-template <typename T>
-int refine_run_fused(const mc3d_refine_problem *pb, long long first_step, long long n_iters, cudaStream_t stream) {
-    auto kern = refine_fused_kernel<T>;
-    int per_sm = 0;
-    MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RF_THREADS, 0));
-    if (per_sm < 1) { set_error("persistent refinement kernel does not fit on an SM"); return MC3D_ERR_UNSUPPORTED; }
-    if (per_sm > MC3D_RF_GRID) per_sm = MC3D_RF_GRID;
-    const long long n_items = (long long)pb->n_frames * pb->n_joints;
-    long long grid = (n_items + RF_THREADS - 1) / RF_THREADS;
-    if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;      // all blocks co-resident
-    if (grid < 1) grid = 1;
-    mc3d_refine_problem prob = *pb;
-    int parity = (int)(first_step & 1);
-    long long iters = n_iters;
-    void *args[] = {(void *)&prob, (void *)&parity, (void *)&iters};
-    MC3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(RF_THREADS), args, 0, stream));
-    count_launch();
-    return MC3D_OK;
-}
-
 // n whole-window iterations on one GPU.  Pairs of iterations (parity 0,1) are captured once into a CUDA graph and
 // replayed, so the per-iteration cost is three graph kernel nodes and no host work.
 template <typename T>
@@ -1317,16 +1208,6 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
         const long long n_items2 = (long long)pb->n_frames * pb->n_joints;
         const bool small2 = n_items2 <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
         if (two_env == 1 || (two_env != 0 && small2)) return refine_run_two_phase<T>(pb, first_step, n_iters, stream);
-    }
-    if (pb->xchg[0] && n_iters > 0 && pb->n_frames > 0) {
-        // The persistent kernel wins while a phase is latency-bound (few items per thread: no launch boundaries,
-        // cheaper barriers); for big shards the three separate kernels run at higher occupancy and win.  Measured
-        // crossover on B200 (float state): between 12 500 and 100 000 frames x 17 joints per GPU.
-        const char *env = getenv("MC3D_REFINE_FUSED");              // read per call: tests switch it; 1 forces, 0 forbids
-        const int fused_env = env ? atoi(env) : -1;
-        const long long n_items = (long long)pb->n_frames * pb->n_joints;
-        const bool small = n_items <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
-        if (fused_env == 1 || (fused_env != 0 && small)) return refine_run_fused<T>(pb, first_step, n_iters, stream);
     }
     // One rank, big shard: the exchange protocol (tickets, fences, flags) would only cost time -- run the plain kernels.
     mc3d_refine_problem plain = *pb;
@@ -1382,8 +1263,6 @@ static const char *refine_plan(const mc3d_refine_problem *pb) {
     if (pb->gc && pb->xchg[0] && (two_env == 1 || (two_env != 0 && small)))
         return fused ? "two-phase step, persistent cooperative kernel (2 grid barriers, 1 exchange of 17 sums + halo stores per step)"
                      : "two-phase step, CUDA graph of 2 kernels per step (1 exchange of 17 sums + halo stores per step)";
-    if (pb->xchg[0] && fused)
-        return "three-phase step, persistent cooperative kernel (3 grid barriers, 2 exchanges + halo stores per step)";
     if (pb->xchg[0] && pb->world > 1)
         return "three-phase step, CUDA graph of 3 kernels per step with the in-kernel exchange (2 exchanges + halo stores per step)";
     return "three-phase step, CUDA graph of 3 kernels per step (one rank, or host-driven exchange)";
