@@ -130,6 +130,35 @@ def test_exchange_and_persistent_kernel_paths_on_one_gpu(pr, syn, dt_name, monke
         assert other.iterations == plain.iterations == 61
 
 
+def test_large_shard_two_phase_persistent_agrees_with_three_kernel_graph(syn, monkeypatch):
+    """60 000 frames x 17 joints (the 80-register, 3-CTA/SM build of the persistent kernel; BASELINE config 4 is
+    100 000): cost history of the default path against the graph of three kernels, float state."""
+    import torch
+    from mc3d_b200 import refinement as rf
+    n = 60_000
+    gs, init, cams, _ = syn.refinement_inputs(n, n_cams=2, seed=31)
+    rows = rf.camera_rows(cams, list(cams))
+
+    def history(peer):
+        monkeypatch.setenv('MC3D_REFINE_PEER', peer)
+        eng = rf.RefineEngine(init, gs, rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=torch.float32, device='cuda:0', lr=0.01,
+                              betas=(0.9, 0.999), lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
+                              max_iter=10 ** 9, ignore_distortions=False, window=(0, n), n_window_frames=n, hist_capacity=64)
+        plan = eng.plan()
+        eng.run(24)
+        h = eng.history(24)[:, 0].copy()
+        x = eng.trajectory().cpu().numpy()
+        eng.close()
+        return plan, h, x
+
+    p1, h1, x1 = history('1')
+    p0, h0, x0 = history('0')
+    assert 'two-phase' in p1 and 'persistent' in p1 and 'three-phase' in p0
+    assert np.all(np.diff(h1) < 0)                                      # the loss goes down every step
+    assert np.allclose(h1, h0, rtol=1e-6)
+    assert np.abs(x1 - x0).max() < 1e-3
+
+
 def test_persistent_kernel_early_stop_matches_three_kernel_graph(pr, syn, monkeypatch):
     """Early stopping inside the persistent kernel (it leaves its loop; the state is stored at both parities)."""
     import torch
