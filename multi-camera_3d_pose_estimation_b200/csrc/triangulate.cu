@@ -762,7 +762,29 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
         if (active && !solved) {
             const T *row = stage + tri_row_offset(plan, tid, row_elems);
             const bool l3v = prm.layout == MC3D_LAYOUT_3V;
-            if (MODE == MC3D_TRI_WEIGHTED) {
+            if (MODE == MC3D_TRI_WEIGHTED && std::is_same<T, double>::value && V > 0 && V % 2 == 0 && !UNDISTORT) {
+                // double storage, even view count: two views per three 128-bit loads (half the shared-memory
+                // instructions, and a quarter of the bank-conflict wavefronts of 64-bit loads at these row strides)
+                const double *rowd = reinterpret_cast<const double *>(row);
+#pragma unroll
+                for (int v = 0; v < ((V > 0) ? V : 2); v += 2) {
+                    double x0, y0, w0, x1, y1, w1;
+                    if (l3v) {
+                        const double2 qx = *reinterpret_cast<const double2 *>(rowd + v);
+                        const double2 qy = *reinterpret_cast<const double2 *>(rowd + V + v);
+                        const double2 qw = *reinterpret_cast<const double2 *>(rowd + 2 * V + v);
+                        x0 = qx.x; x1 = qx.y; y0 = qy.x; y1 = qy.y; w0 = qw.x; w1 = qw.y;
+                    } else {
+                        const double2 q0 = *reinterpret_cast<const double2 *>(rowd + 3 * v);
+                        const double2 q1 = *reinterpret_cast<const double2 *>(rowd + 3 * v + 2);
+                        const double2 q2 = *reinterpret_cast<const double2 *>(rowd + 3 * v + 4);
+                        x0 = q0.x; y0 = q0.y; w0 = q1.x; x1 = q1.y; y1 = q2.x; w1 = q2.y;
+                    }
+                    n_used += (w0 != 0.0) + (w1 != 0.0);
+                    accumulate_view(B, x0, y0, w0, prm.P[v]);
+                    accumulate_view(B, x1, y1, w1, prm.P[v + 1]);
+                }
+            } else if (MODE == MC3D_TRI_WEIGHTED) {
 #pragma unroll
                 for (int v = 0; v < ((V > 0) ? V : MC3D_MAX_VIEWS); ++v) {
                     if (V == 0 && v >= nv) break;
