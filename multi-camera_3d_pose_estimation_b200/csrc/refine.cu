@@ -1125,13 +1125,21 @@ int refine_phase(const mc3d_refine_problem *pb, int phase, long long step_index,
     return MC3D_OK;
 }
 
+// Every rank must pick the same step variant (they meet inside the kernels), so the size that decides is the LARGEST
+// shard of the run (frame_shard sizes differ by at most one frame), not this rank's own.
+static bool shard_is_small(const mc3d_refine_problem *pb) {
+    const long long world = pb->world > 1 ? pb->world : 1;
+    const long long frames = pb->world > 1 ? (pb->total_frames + world - 1) / world : pb->n_frames;
+    return frames * pb->n_joints <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
+}
+
 // Two-phase step: persistent kernel for small shards, otherwise a CUDA graph of (costgrad, step2) pairs.
 template <typename T>
 int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, long long n_iters, cudaStream_t stream) {
     const long long n_items = (long long)pb->n_frames * pb->n_joints;
     const char *env = getenv("MC3D_REFINE_FUSED");                  // 1 forces the persistent kernel, 0 forbids it
     const int fused_env = env ? atoi(env) : -1;
-    const bool small = n_items <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
+    const bool small = shard_is_small(pb);
     mc3d_refine_problem prob = *pb;
     if (fused_env == 1 || (fused_env != 0 && small)) {
         const bool big = n_items > 425000;
@@ -1205,9 +1213,7 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
         //   sizes measured (MC3D_RF_SMALL) the byte count is assumed to win and the three-kernel graph is used.
         const char *env2 = getenv("MC3D_REFINE_TWO_PHASE");          // 1 forces the two-phase step, 0 forbids it
         const int two_env = env2 ? atoi(env2) : -1;
-        const long long n_items2 = (long long)pb->n_frames * pb->n_joints;
-        const bool small2 = n_items2 <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
-        if (two_env == 1 || (two_env != 0 && small2)) return refine_run_two_phase<T>(pb, first_step, n_iters, stream);
+        if (two_env == 1 || (two_env != 0 && shard_is_small(pb))) return refine_run_two_phase<T>(pb, first_step, n_iters, stream);
     }
     // One rank, big shard: the exchange protocol (tickets, fences, flags) would only cost time -- run the plain kernels.
     mc3d_refine_problem plain = *pb;
@@ -1256,7 +1262,7 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
 static const char *refine_plan(const mc3d_refine_problem *pb) {
     if (!pb) return "invalid";
     const long long n_items = (long long)pb->n_frames * pb->n_joints;
-    const bool small = n_items <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
+    const bool small = shard_is_small(pb);
     const char *e2 = getenv("MC3D_REFINE_TWO_PHASE"), *ef = getenv("MC3D_REFINE_FUSED");
     const int two_env = e2 ? atoi(e2) : -1, fused_env = ef ? atoi(ef) : -1;
     const bool fused = fused_env == 1 || (fused_env != 0 && small);
