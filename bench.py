@@ -228,7 +228,6 @@ def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     import mc3d_b200
-    from mc3d_b200 import _lib
     from mc3d_b200.triangulation import triangulate_multiview
 
     torch.cuda.set_device(local_rank)

@@ -1,12 +1,11 @@
 """GPU: the raw-ctypes binding shown in INTEGRATION.md section 2 (no mc3d_b200 package involved) reproduces the
 reference's utils.triangulate_points golden."""
 import ctypes
-import os
 
 import numpy as np
 import pytest
 
-from conftest import ROOT, cams_from_golden, load_golden, rel_err
+from conftest import cams_from_golden, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 

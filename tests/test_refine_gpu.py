@@ -5,8 +5,6 @@ Tolerance (BASELINE.json north_star): the loss history at equal iterations withi
 path is held to 1e-9; trajectories to 1e-6 mm (float64) / 5e-2 mm (float32 state, the reference's own float32
 autograd noise over tens of Adam steps).
 """
-import os
-
 import numpy as np
 import pytest
 
