@@ -276,6 +276,20 @@ typedef struct {
 int mc3d_extrinsic_problem_size(void);
 int mc3d_extrinsic_run_f32(const mc3d_extrinsic_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
 int mc3d_extrinsic_run_f64(const mc3d_extrinsic_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
+/* Cameras and trajectory learnt together (extrinsic_optimization_IDs with optimize_trajectory=True, pose_refinement.py:931-961):
+ * the trajectory steps through mc3d_refine_phase_* 0, 1, 2; between phases 1 and 2, per learnt camera,
+ * mc3d_extrinsic_costgrad_* accumulates the raw sums (cost, count, dR, dT) over the trajectory points (problem with
+ * n_samples = 1, samples3d = the trajectory, sums into ctrl[0..13], no step), and mc3d_extrinsic_joint_step_* turns them
+ * into gradients (divided by the N_lik of all cameras), adds their squared norms to refine_ctrl's |g|^2 so that phase 2
+ * clips with the norm over every learnable parameter (:1047), applies Adam to the cameras and zeroes cam_ctrl.
+ *   cam_ctrl 64 zero-filled doubles per camera (that camera's mc3d_extrinsic_problem.ctrl); cam_params 36 doubles per
+ *   camera: R[9] T[3] | m[12] | v[12] (that camera's mc3d_extrinsic_problem.params). */
+int mc3d_extrinsic_costgrad_f32(const mc3d_extrinsic_problem *pb, void *stream);
+int mc3d_extrinsic_costgrad_f64(const mc3d_extrinsic_problem *pb, void *stream);
+int mc3d_extrinsic_joint_step_f32(double *d_refine_ctrl, double *d_cam_ctrl, double *d_cam_params, int n_learn, int64_t step_index,
+                                  double lr, double beta1, double beta2, double eps, void *stream);
+int mc3d_extrinsic_joint_step_f64(double *d_refine_ctrl, double *d_cam_ctrl, double *d_cam_params, int n_learn, int64_t step_index,
+                                  double lr, double beta1, double beta2, double eps, void *stream);
 
 
 /* ---- 4. linear interpolation (pose_refinement.py:15-84) ---------------------------------------------------

@@ -120,6 +120,10 @@ SIGNATURES = {
     'mc3d_extrinsic_problem_size': (_c_int, []),
     'mc3d_extrinsic_run_f32': (_c_int, [ctypes.POINTER(ExtrinsicProblem), _c_i64, _c_i64, _c_vp]),
     'mc3d_extrinsic_run_f64': (_c_int, [ctypes.POINTER(ExtrinsicProblem), _c_i64, _c_i64, _c_vp]),
+    'mc3d_extrinsic_costgrad_f32': (_c_int, [ctypes.POINTER(ExtrinsicProblem), _c_vp]),
+    'mc3d_extrinsic_costgrad_f64': (_c_int, [ctypes.POINTER(ExtrinsicProblem), _c_vp]),
+    'mc3d_extrinsic_joint_step_f32': (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_i64, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_vp]),
+    'mc3d_extrinsic_joint_step_f64': (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_i64, _c_dbl, _c_dbl, _c_dbl, _c_dbl, _c_vp]),
     'mc3d_peer_alloc': (_c_int, [_c_i64, ctypes.POINTER(_c_vp), _c_vp]),
     'mc3d_peer_open': (_c_int, [_c_vp, ctypes.POINTER(_c_vp)]),
     'mc3d_peer_close': (_c_int, [_c_vp]),

@@ -200,9 +200,86 @@ int extrinsic_run(const mc3d_extrinsic_problem *pb, long long first_step, long l
     return MC3D_OK;
 }
 
+// ---- cameras and trajectory learnt together (extrinsic_optimization_IDs with optimize_trajectory=True) ----------------
+// The trajectory's step is csrc/refine.cu's three phases; between its gradient phase and its Adam phase this kernel
+// (one block, one warp per learnt camera) turns each camera's raw sums -- extrinsic_costgrad_kernel over the
+// trajectory points, one "sample" per (frame, joint) -- into its gradient of the likelihood cost (divide by the
+// N_lik of ALL cameras, pose_refinement.py:889), adds the cameras' squared norms to the trajectory's so that ONE
+// clip_grad_norm_ covers every learnable parameter (:1047), and applies Adam to the cameras with that clip factor.
+//   refine_ctrl : the trajectory's control block (sums of this step at [16 p ...]: N_lik at 1, |g_x|^2 at 7; Adam step at 32 + 16 p)
+//   cam_ctrl    : per learnt camera a 64-double control block as in mc3d_extrinsic_problem.ctrl; [0..13] = cost, count,
+//                 dR[9], dT[3] from extrinsic_costgrad_kernel, zeroed here (the rest stays zero)
+//   cam_params  : per learnt camera 36 doubles: R[9] T[3] | m[12] | v[12]
+template <typename T>
+__global__ void extrinsic_joint_step_kernel(double *refine_ctrl, double *cam_ctrl, double *cam_params, int n_learn, int parity,
+                                            double lr, double beta1, double beta2, double eps) {
+    __shared__ double sq[MC3D_MAX_VIEWS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *acc = refine_ctrl + 16 * parity;
+    const double *st = refine_ctrl + 32 + 16 * parity;
+    if (st[5] != 0.0) return;                                      // stopped
+    const double n_lik = acc[1];
+    double g = 0.0;
+    if (warp < n_learn && lane < 12) g = cam_ctrl[64 * warp + 2 + lane] / n_lik;
+    const double s = warp_sum(g * g);
+    if (warp < n_learn && lane == 0) sq[warp] = s;
+    __syncthreads();
+    double total = acc[7];
+    for (int c = 0; c < n_learn; ++c) total += sq[c];
+    __syncthreads();
+    if (threadIdx.x == 0) acc[7] = total;                          // the trajectory's Adam phase clips with the joint norm
+    const double clip = fmin(1.0, 1.0 / (sqrt(total) + 1e-6));
+    const double step = st[0] + 1.0;
+    if (warp < n_learn && lane < 12) {
+        double *p = cam_params + 36 * warp + lane, *m = p + 12, *v = p + 24;
+        const double gc = !(clip == clip) ? NAN : g * clip;
+        const double mi = *m + (gc - *m) * (1.0 - beta1);
+        const double vi = *v * beta2 + (1.0 - beta2) * gc * gc;
+        const double pn = *p - (lr / (1.0 - pow(beta1, step))) * (mi / (sqrt(vi) / sqrt(1.0 - pow(beta2, step)) + eps));
+        *p = (double)(T)pn;
+        *m = (double)(T)mi;
+        *v = (double)(T)vi;
+    }
+    if (warp < n_learn && lane < 16) cam_ctrl[64 * warp + lane] = 0.0;
+}
+
+template <typename T>
+int extrinsic_costgrad(const mc3d_extrinsic_problem *pb, cudaStream_t stream) {
+    if (!pb || !pb->samples3d || !pb->mean || !pb->S || !pb->params || !pb->ctrl) { set_error("NULL pointer in extrinsic problem"); return MC3D_ERR_INVALID_ARGUMENT; }
+    const long long n = pb->n_frames * pb->n_joints * (long long)pb->n_samples;
+    if (n <= 0) return MC3D_OK;
+    long long grid = (n + EX_THREADS - 1) / EX_THREADS;
+    if (grid > (long long)sm_count() * 4) grid = (long long)sm_count() * 4;
+    extrinsic_costgrad_kernel<T><<<(unsigned)grid, EX_THREADS, 0, stream>>>(*pb, 0);
+    count_launch();
+    MC3D_CUDA_TRY(cudaGetLastError());
+    return MC3D_OK;
+}
+
+template <typename T>
+int extrinsic_joint_step(double *refine_ctrl, double *cam_ctrl, double *cam_params, int n_learn, long long step_index, double lr,
+                         double beta1, double beta2, double eps, cudaStream_t stream) {
+    if (!refine_ctrl || !cam_ctrl || !cam_params || n_learn < 1 || n_learn > MC3D_MAX_VIEWS) { set_error("bad joint-step arguments"); return MC3D_ERR_INVALID_ARGUMENT; }
+    extrinsic_joint_step_kernel<T><<<1, 32 * n_learn, 0, stream>>>(refine_ctrl, cam_ctrl, cam_params, n_learn, (int)(step_index & 1), lr,
+                                                                beta1, beta2, eps);
+    count_launch();
+    MC3D_CUDA_TRY(cudaGetLastError());
+    return MC3D_OK;
+}
+
 }  // namespace mc3d
 
 extern "C" {
+int mc3d_extrinsic_costgrad_f32(const mc3d_extrinsic_problem *pb, void *stream) { return mc3d::extrinsic_costgrad<float>(pb, (cudaStream_t)stream); }
+int mc3d_extrinsic_costgrad_f64(const mc3d_extrinsic_problem *pb, void *stream) { return mc3d::extrinsic_costgrad<double>(pb, (cudaStream_t)stream); }
+int mc3d_extrinsic_joint_step_f32(double *refine_ctrl, double *cam_ctrl, double *cam_params, int n_learn, int64_t step_index, double lr,
+                                  double beta1, double beta2, double eps, void *stream) {
+    return mc3d::extrinsic_joint_step<float>(refine_ctrl, cam_ctrl, cam_params, n_learn, step_index, lr, beta1, beta2, eps, (cudaStream_t)stream);
+}
+int mc3d_extrinsic_joint_step_f64(double *refine_ctrl, double *cam_ctrl, double *cam_params, int n_learn, int64_t step_index, double lr,
+                                  double beta1, double beta2, double eps, void *stream) {
+    return mc3d::extrinsic_joint_step<double>(refine_ctrl, cam_ctrl, cam_params, n_learn, step_index, lr, beta1, beta2, eps, (cudaStream_t)stream);
+}
 int mc3d_extrinsic_problem_size(void) { return (int)sizeof(mc3d_extrinsic_problem); }
 int mc3d_extrinsic_run_f32(const mc3d_extrinsic_problem *pb, int64_t first_step, int64_t n_iters, void *stream) {
     return mc3d::extrinsic_run<float>(pb, first_step, n_iters, (cudaStream_t)stream);

@@ -15,9 +15,11 @@ the kernel keeps one Gaussian per (frame, joint) because that is what upstream e
 camera's extrinsics from points sampled from the two ground-truth cameras' Gaussians (pose_refinement.py:684-706,
 :800-831, :915-1091; csrc/extrinsic.cu) -- SURVEY.md section 8(f3).
 
-Out of scope (raise NotImplementedError): learning cameras and trajectory jointly (``extrinsic_optimization_IDs`` with
-``optimize_trajectory=True``), ``use_NN``, ``randomize_params``, and the superseded ``ExtrinsicParameterRefinement`` /
-``Trajectory_Optimization`` classes.
+With ``optimize_trajectory=True`` the listed cameras are learnt together with the trajectory (:931-961; one GPU,
+whole-window batches).
+
+Out of scope (raise NotImplementedError): ``use_NN``, ``randomize_params``, and the superseded
+``ExtrinsicParameterRefinement`` / ``Trajectory_Optimization`` classes.
 """
 import argparse
 import ctypes
@@ -173,8 +175,7 @@ class Optimized_3d_Pose_Estimation:
                                                        print_frequency=print_frequency, batch_size=batch_size,
                                                        ignore_distortions=ignore_distortions,
                                                        reset_camera_params=reset_camera_params, time_interval=time_interval)
-        if extrinsic_optimization_IDs is not None and len(extrinsic_optimization_IDs):
-            raise NotImplementedError('learning cameras and trajectory jointly is outside the accelerated path (SURVEY.md 8(f3))')
+        learn_ids = list(extrinsic_optimization_IDs) if extrinsic_optimization_IDs is not None else []
         if self.body_lengths is None:
             raise AttributeError("'NoneType' object has no attribute 'values'")   # create_body_length_vect, :770
 
@@ -201,6 +202,18 @@ class Optimized_3d_Pose_Estimation:
 
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size() > 1
+        if learn_ids:
+            if dist_on or len(windows) > 1:
+                raise NotImplementedError('cameras and trajectory are learnt together on one GPU, whole-window batches only')
+            for ID in learn_ids:                                 # pose_refinement.py:931-943
+                assert ID in self.decomposed_cam_params
+                self.decomposed_cam_params_initial[ID][1] = utils.rotation_conversion(self.decomposed_cam_params_initial[ID][1], to_vector=True)
+                if tuple(self.decomposed_cam_params[ID][1].shape) != (3, 3):
+                    self.decomposed_cam_params[ID][1] = utils.rotation_conversion(
+                        self.decomposed_cam_params[ID][1].reshape(3), to_vector=False).to(self.torch_dtype)
+                Rl, Tl = self.decomposed_cam_params[ID][1], self.decomposed_cam_params[ID][2]
+                Rl[Rl == 0] = random.random() / 10 ** 6
+                Tl[Tl == 0] = random.random() / 10 ** 6
         if dist_on and len(windows) > 1:
             raise NotImplementedError('batch_size windows are sequential Adam steps and do not shard; run them on one GPU')
         comm = _ref.DistComm() if dist_on else _ref.LocalComm()
@@ -215,8 +228,10 @@ class Optimized_3d_Pose_Estimation:
                                    lambda_smooth=lambda_smooth, lambda_body_length=lambda_body_length,
                                    patience=patience, tolerance=tolerance, max_iter=max_iter,
                                    ignore_distortions=ignore_distortions, window=windows[0],
-                                   n_window_frames=batch_size, hist_capacity=hist_cap, comm=comm)
+                                   n_window_frames=batch_size, hist_capacity=hist_cap, comm=comm,
+                                   use_exchange=False if learn_ids else None)
         self._engine = engine
+        joint = _JointCameras(self, engine, learn_ids, lr, betas) if learn_ids else None
         names = ['total_cost', 'likelihood_cost'] + (['smoothness_cost'] if lambda_smooth > 0 else []) + \
                 (['body_length_cost'] if lambda_body_length > 0 else [])
         col = {'total_cost': 0, 'likelihood_cost': 1, 'smoothness_cost': 2, 'body_length_cost': 3}
@@ -227,7 +242,9 @@ class Optimized_3d_Pose_Estimation:
         with torch.cuda.device(device):
             while iters_done < n_iters_max:
                 n = min(chunk, n_iters_max - iters_done)
-                if len(windows) == 1:
+                if joint is not None:
+                    joint.steps(n)
+                elif len(windows) == 1:
                     engine.run(n)
                 else:
                     for _ in range(n):
@@ -260,8 +277,13 @@ class Optimized_3d_Pose_Estimation:
         improved_once = math.isfinite(st['best'])
         self.best_trajectory = engine.best_trajectory().cpu() if improved_once else None
         engine.close()                       # sharded runs: unmap the peers' exchange blocks (collective)
+        if joint is not None:
+            joint.write_back()
         self.best_decomposed_cam_params = {k: [p.clone().detach() for p in self.decomposed_cam_params[k]]
                                            for k in self.decomposed_cam_params} if improved_once else None
+        if joint is not None and improved_once:
+            for ID, (Rb, Tb) in joint.best.items():
+                self.best_decomposed_cam_params[ID][1], self.best_decomposed_cam_params[ID][2] = Rb, Tb
         self.all_costs_total = {}
         for nm in names:
             self.all_costs_total[nm] = _interleave_history(hist[:, col[nm]], len(windows), self.torch_dtype)
@@ -454,6 +476,94 @@ class Optimized_3d_Pose_Estimation:
         self.all_costs_total = {nm: _interleave_history(cols[nm], 1, dt) for nm in names}
         self.iterations = st['iterations']
         return self
+
+
+class _JointCameras:
+    """Cameras learnt together with the trajectory (``extrinsic_optimization_IDs`` with ``optimize_trajectory=True``,
+    pose_refinement.py:931-961): the trajectory steps through the engine's three phases; between its gradient phase and
+    its Adam phase every learnt camera's gradient of the likelihood cost is accumulated over the trajectory points
+    (csrc/extrinsic.cu) and one clip_grad_norm_ + Adam step covers everything (:1047-1050).  The cameras are kernel
+    parameters of the trajectory's phases, so their new values come back to the host once per step."""
+
+    def __init__(self, opt, engine, learn_ids, lr, betas):
+        torch = _torch()
+        self.opt, self.engine, self.ids = opt, engine, list(learn_ids)
+        self.lr, self.betas = float(lr), (float(betas[0]), float(betas[1]))
+        self.tag = engine.tag
+        self.lib = _lib.lib()
+        dev, dt = engine.device, opt.torch_dtype
+        n = len(self.ids)
+        self.cam_params = torch.zeros(36 * n, dtype=torch.float64, device=dev)
+        self.cam_ctrl = torch.zeros(64 * n, dtype=torch.float64, device=dev)
+        self.slots = [opt.camera_IDs.index(ID) if ID in opt.camera_IDs else None for ID in self.ids]
+        self.problems = []
+        J = engine.J
+        x0 = engine.x_ext[2:]                                    # local frame 0 (no exchange block in this mode)
+        for q, ID in enumerate(self.ids):
+            K, Rm, Tv, dist = opt.decomposed_cam_params[ID]
+            self.cam_params[36 * q:36 * q + 9] = Rm.detach().to(torch.float64).reshape(9).to(dev)
+            self.cam_params[36 * q + 9:36 * q + 12] = Tv.detach().to(torch.float64).reshape(3).to(dev)
+            pb = _lib.ExtrinsicProblem()
+            pb.n_frames, pb.n_joints, pb.n_samples = engine.n_local, J, 1
+            pb.ignore_distortions = engine.problem.ignore_distortions
+            Kd = torch.as_tensor(K).to(dt).to(torch.float64).reshape(9)
+            dd = torch.as_tensor(dist).to(dt).to(torch.float64).reshape(-1)
+            for i in range(9):
+                pb.K[i] = float(Kd[i])
+            for i in range(min(5, dd.numel())):
+                pb.dist[i] = float(dd[i])
+            pb.samples3d = x0.data_ptr()
+            pb.mean, pb.S = engine.mu0.data_ptr(), engine.S.data_ptr()
+            pb.params = self.cam_params.data_ptr() + 8 * 36 * q
+            pb.ctrl = self.cam_ctrl.data_ptr() + 8 * 64 * q
+            self.problems.append(pb)
+        self.host = self.cam_params.cpu().numpy().copy()
+        self.best = {}
+
+    def _sync_engine_cameras(self):
+        """The learnt cameras' current R, T into the kernel parameters of the trajectory's phases."""
+        for q, slot in enumerate(self.slots):
+            if slot is None:                                      # learnt but not part of the likelihood: no gradient reaches it
+                continue
+            row = self.engine.problem.cams[slot]
+            for i in range(9):
+                row[9 + i] = float(self.host[36 * q + i])
+            for i in range(3):
+                row[18 + i] = float(self.host[36 * q + 9 + i])
+
+    def steps(self, n):
+        torch = _torch()
+        eng = self.engine
+        costgrad = getattr(self.lib, f'mc3d_extrinsic_costgrad_{self.tag}')
+        joint = getattr(self.lib, f'mc3d_extrinsic_joint_step_{self.tag}')
+        for _ in range(int(n)):
+            st = eng._stream()
+            self._sync_engine_cameras()
+            eng.phases.phase(eng.problem, 0, eng.step, True, st)
+            eng.phases.phase(eng.problem, 1, eng.step, True, st)
+            for q, pb in enumerate(self.problems):
+                if self.slots[q] is not None:
+                    _lib.check(costgrad(ctypes.byref(pb), st))
+            _lib.check(joint(eng.ctrl.data_ptr(), self.cam_ctrl.data_ptr(), self.cam_params.data_ptr(), len(self.ids), eng.step,
+                             self.lr, self.betas[0], self.betas[1], 1e-8, st))
+            eng.phases.phase(eng.problem, 2, eng.step, True, st)
+            eng.step += 1
+            self.host = self.cam_params.cpu().numpy().copy()       # one small read-back per step
+            state = eng.state()
+            if state['improved']:
+                self.best = {ID: self._tensors(q) for q, ID in enumerate(self.ids)}
+            if state['stopped']:
+                break
+
+    def _tensors(self, q):
+        torch = _torch()
+        dt = self.opt.torch_dtype
+        return (torch.tensor(self.host[36 * q:36 * q + 9].reshape(3, 3), dtype=dt),
+                torch.tensor(self.host[36 * q + 9:36 * q + 12].reshape(3, 1), dtype=dt))
+
+    def write_back(self):
+        for q, ID in enumerate(self.ids):
+            self.opt.decomposed_cam_params[ID][1], self.opt.decomposed_cam_params[ID][2] = self._tensors(q)
 
 
 def _running_means(costs, steps_per_iter):

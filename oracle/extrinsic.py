@@ -106,3 +106,69 @@ def optimize(samples3d, K, R0, T0, dist, mean, Sinv, lr=0.001, betas=(0.9, 0.999
         it += 1
     return {'R': p[:9].reshape(3, 3), 'T': p[9:].reshape(3, 1), 'best_R': None if best is None else best[:9].reshape(3, 3),
             'best_T': None if best is None else best[9:].reshape(3, 1), 'history': hist, 'iterations': it}
+
+
+def joint_optimize(gaussians, initial_trajectory, cams, learn_ids, body_lengths, lr=0.001, betas=(0.9, 0.999), lambda_smooth=1.0,
+                   lambda_body_length=1.0, patience=100, tolerance=1e-5, max_iter=1000, ignore_distortions=False,
+                   time_interval=(0, -1), dtype=np.float64, eps_adam=1e-8):
+    """Trajectory AND the extrinsics of the cameras in ``learn_ids`` optimised together: ``extrinsic_optimization_IDs``
+    non-empty with ``optimize_trajectory=True`` (pose_refinement.py:931-961 for the parameters, :863-889 for the loss
+    whose gradient now also reaches R, T, :1044-1050 one clip_grad_norm_ + Adam step over everything).  ``cams``: dict id ->
+    [K, R, T, dist] with exact zeros of the learnt R, T already nudged (:937-938).  Single whole-window batch.
+    Returns dict(final, best, cams, best_cams, history, iterations)."""
+    t0, t1 = time_interval
+    g_sub = np.asarray(gaussians, dtype=np.float64)[t0:t1]
+    Sinv = R_.cov_inverse(np.asarray(gaussians), dtype=dtype).astype(np.float64)[t0:t1]
+    mu0 = g_sub[:, 0, :, :2].astype(dtype).astype(np.float64)
+    x = np.asarray(initial_trajectory, dtype=dtype)[t0:t1].astype(np.float64)
+    bones = R_.bone_table(body_lengths)
+    cams = {k: [np.asarray(a, dtype=dtype).astype(np.float64) for a in v] for k, v in cams.items()}
+    ids = list(cams)
+    names = ['total_cost', 'likelihood_cost'] + (['smoothness_cost'] if lambda_smooth > 0 else []) + \
+            (['body_length_cost'] if lambda_body_length > 0 else [])
+    hist = {n: [] for n in names}
+    m_x, v_x = np.zeros_like(x), np.zeros_like(x)
+    m_c = {k: np.zeros(12) for k in learn_ids}
+    v_c = {k: np.zeros(12) for k in learn_ids}
+    best_cost, best, best_cams, no_improve, it, step = np.inf, None, None, 0, 0, 0
+    b1, b2 = betas
+    while no_improve < patience and it <= max_iter:
+        cam_list = [cams[k] for k in ids]
+        costs, g_x = R_.total_cost_and_grad(x, mu0, Sinv, cam_list, bones, lambda_smooth, lambda_body_length, ignore_distortions)
+        n_lik = R_.likelihood(x, mu0, Sinv, cam_list, ignore_distortions, grad=False)[2]
+        g_c = {}
+        for k in learn_ids:
+            K, Rm, Tv, dist = cams[k]
+            _, dR, dT, n_ok = sample_cost_and_grad(x[:, :, None, :], K, Rm, Tv, dist, mu0, Sinv, ignore_distortions)
+            g_c[k] = np.concatenate([dR.reshape(9), dT.reshape(3)]) * (n_ok / n_lik)
+        norm = np.sqrt((g_x * g_x).sum() + sum((g * g).sum() for g in g_c.values()))
+        clip = min(1.0, 1.0 / (norm + 1e-6))
+        step += 1
+        bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+
+        def adam(p, g, m, v):
+            g = g * clip
+            m = m + (g - m) * (1 - b1)
+            v = b2 * v + (1 - b2) * g * g
+            p = (p - (lr / bc1) * (m / (np.sqrt(v) / np.sqrt(bc2) + eps_adam))).astype(dtype).astype(np.float64)
+            return p, m.astype(dtype).astype(np.float64), v.astype(dtype).astype(np.float64)
+
+        x, m_x, v_x = adam(x, g_x, m_x, v_x)
+        for k in learn_ids:
+            p = np.concatenate([cams[k][1].reshape(9), cams[k][2].reshape(3)])
+            p, m_c[k], v_c[k] = adam(p, g_c[k], m_c[k], v_c[k])
+            cams[k] = [cams[k][0], p[:9].reshape(3, 3), p[9:].reshape(3, 1), cams[k][3]]
+        for n in names:
+            hist[n].append(float(costs[n]))
+        for n in names:
+            hist[n].append(float(np.mean(hist[n])))
+        cur = hist['total_cost'][-1]
+        if cur < best_cost - tolerance:
+            best_cost, best, no_improve = cur, x.copy(), 0
+            best_cams = {k: [a.copy() for a in v] for k, v in cams.items()}
+        else:
+            no_improve += 1
+        if no_improve >= patience:
+            break
+        it += 1
+    return {'final': x, 'best': best, 'cams': cams, 'best_cams': best_cams, 'history': hist, 'iterations': it}

@@ -225,6 +225,26 @@ def golden_extrinsic(ref_refine, syn, out):
             store[f'{key}_best_R'] = opt.best_decomposed_cam_params[2][1].numpy().astype(np.float64)
             store[f'{key}_best_T'] = opt.best_decomposed_cam_params[2][2].numpy().astype(np.float64)
             store[f'{key}_kw'] = np.array([f'{k}={v}' for k, v in kw.items()])
+    # cameras and trajectory learnt together (extrinsic_optimization_IDs with optimize_trajectory=True, :931-961)
+    for dt_name, dt in (('f64', torch.float64), ('f32', torch.float32)):
+        np.random.seed(3)
+        random.seed(3)
+        torch.manual_seed(3)
+        opt = ref_refine.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(),
+                                                      decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                                      body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+        with contextlib.redirect_stdout(io.StringIO()):
+            opt.sgd_optimize(extrinsic_optimization_IDs=[2], optimize_trajectory=True, lr=1e-3, lambda_smooth=1e-3,
+                             lambda_body_length=1.0, max_iter=14, print_frequency=1000, time_interval=[0, 12])
+        key = f'{dt_name}_joint'
+        for cost, vals in opt.all_costs_total.items():
+            store[f'{key}_hist_{cost}'] = np.array([float(v) for v in vals])
+        store[f'{key}_traj'] = opt.trajectory.detach().numpy().astype(np.float64)
+        store[f'{key}_best_traj'] = opt.best_trajectory.numpy().astype(np.float64)
+        store[f'{key}_R'] = opt.decomposed_cam_params[2][1].detach().numpy().astype(np.float64)
+        store[f'{key}_T'] = opt.decomposed_cam_params[2][2].detach().numpy().astype(np.float64)
+        store[f'{key}_best_R'] = opt.best_decomposed_cam_params[2][1].numpy().astype(np.float64)
+        store[f'{key}_best_T'] = opt.best_decomposed_cam_params[2][2].numpy().astype(np.float64)
     np.savez_compressed(os.path.join(out, 'extrinsic_T12.npz'), **store)
 
 

@@ -107,3 +107,35 @@ def test_extrinsic_gradient_matches_oracle_on_a_larger_sample_set():
     gref = np.concatenate([dR.reshape(9), dT.reshape(3)])
     gclip = gref * min(1.0, 1.0 / (np.sqrt((gref ** 2).sum()) + 1e-6))
     assert np.allclose(m, gclip * (1 - 0.9 ** 2), rtol=1e-10, atol=1e-18)
+
+
+@pytest.mark.parametrize('key', ['f64_joint', 'f32_joint'])
+def test_cameras_and_trajectory_learnt_together_match_reference_runs(key):
+    """extrinsic_optimization_IDs=[2] with optimize_trajectory=True (pose_refinement.py:931-961): the trajectory's three
+    phases plus the camera gradient / joint clip / camera Adam kernels of csrc/extrinsic.cu."""
+    import torch
+    import mc3d_b200.pose_refinement as pr
+    import mc3d_b200.synthetic as syn
+    g = np.load(GOLD)
+    cams = {c: [g[f'cam{c}_K'], g[f'cam{c}_R'], g[f'cam{c}_T'], g[f'cam{c}_dist']] for c in range(3)}
+    dt = torch.float64 if key.startswith('f64') else torch.float32
+    np.random.seed(3)
+    random.seed(3)
+    opt = pr.Optimized_3d_Pose_Estimation(g['gaussians'].copy(), g['initial'].copy(),
+                                          decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+    opt.sgd_optimize(extrinsic_optimization_IDs=[2], optimize_trajectory=True, lr=1e-3, lambda_smooth=1e-3, lambda_body_length=1.0,
+                     max_iter=14, print_frequency=np.inf, time_interval=[0, 12])
+    rtol = 1e-9 if dt == torch.float64 else 1e-4
+    for name, vals in opt.all_costs_total.items():
+        ref = g[f'{key}_hist_{name}']
+        got = np.array([float(v) for v in vals])
+        assert len(got) == len(ref) == 30, (name, len(got))
+        assert np.allclose(got, ref, rtol=rtol, atol=0), (name, np.max(np.abs(got - ref) / np.abs(ref)))
+    atol = 1e-9 if dt == torch.float64 else 2e-4
+    assert np.abs(opt.trajectory.numpy() - g[f'{key}_traj']).max() < atol * 10
+    assert np.abs(opt.best_trajectory.numpy() - g[f'{key}_best_traj']).max() < atol * 10
+    assert np.abs(opt.decomposed_cam_params[2][1].numpy() - g[f'{key}_R']).max() < atol
+    assert np.abs(opt.decomposed_cam_params[2][2].numpy() - g[f'{key}_T']).max() < atol * 1e3
+    assert np.abs(opt.best_decomposed_cam_params[2][1].numpy() - g[f'{key}_best_R']).max() < atol
+    assert np.abs(opt.best_decomposed_cam_params[2][2].numpy() - g[f'{key}_best_T']).max() < atol * 1e3

@@ -70,3 +70,25 @@ def _lengths():
     syn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(syn)
     return dict(syn.EXAMPLE_BODY_LENGTHS)
+
+
+@pytest.mark.parametrize('key', ['f64_joint', 'f32_joint'])
+def test_joint_camera_and_trajectory_optimisation_matches_reference_runs(key):
+    """extrinsic_optimization_IDs=[2] with optimize_trajectory=True (pose_refinement.py:931-961)."""
+    import random
+    g = np.load(GOLD)
+    dt = np.float64 if key.startswith('f64') else np.float32
+    cams = {k: [np.asarray(a, dtype=dt).astype(np.float64) for a in v] for k, v in _cams(g).items()}
+    random.seed(3)
+    cams[2][1][cams[2][1] == 0] = dt(random.random() / 10 ** 6)
+    cams[2][2][cams[2][2] == 0] = dt(random.random() / 10 ** 6)
+    res = E.joint_optimize(g['gaussians'], g['initial'], cams, [2], _lengths(), lr=1e-3, lambda_smooth=1e-3,
+                           lambda_body_length=1.0, max_iter=14, time_interval=(0, 12), dtype=dt)
+    rtol = 1e-9 if dt == np.float64 else 2e-5
+    for name, got in res['history'].items():
+        ref = g[f'{key}_hist_{name}']
+        assert len(got) == len(ref) == 30 and np.allclose(got, ref, rtol=rtol, atol=0), name
+    atol = 1e-9 if dt == np.float64 else 1e-4
+    assert np.abs(res['final'] - g[f'{key}_traj']).max() < atol * 10
+    assert np.abs(res['cams'][2][1] - g[f'{key}_R']).max() < atol and np.abs(res['cams'][2][2] - g[f'{key}_T']).max() < atol * 1e3
+    assert np.abs(res['best_cams'][2][1] - g[f'{key}_best_R']).max() < atol

@@ -255,9 +255,13 @@ def test_unsupported_modes_and_errors(pr, syn):
     gs, init, cams, _ = syn.refinement_inputs(8, seed=1)
     mk = lambda **k: pr.Optimized_3d_Pose_Estimation(gs, init, decomposed_cam_params_initial={i: list(cams[i]) for i in cams}, **k)
     with pytest.raises(NotImplementedError):
-        mk(body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS)).sgd_optimize(extrinsic_optimization_IDs=[1])
+        mk(body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS)).sgd_optimize(randomize_params=True)
     with pytest.raises(NotImplementedError):
         mk(body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS)).sgd_optimize(use_NN=True)
+    with pytest.raises(NotImplementedError):                          # learnt cameras need whole-window batches
+        mk(body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS)).sgd_optimize(extrinsic_optimization_IDs=[1], batch_size=4, time_interval=[0, 8])
+    with pytest.raises(TypeError):                                    # upstream's default GT_camera_IDs expression fails the same way
+        mk(body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS)).sgd_optimize(extrinsic_optimization_IDs=[1], optimize_trajectory=False)
     with pytest.raises(AttributeError):
         mk(body_lengths=None).sgd_optimize(max_iter=1)                   # upstream: create_body_length_vect on None
     with pytest.raises(KeyError):
