@@ -135,6 +135,9 @@ def golden_refine(ref_refine, ref_utils, syn, out):
                      time_interval=[0, 48]),
         'nodist': dict(lr=0.005, lambda_smooth=0.5, lambda_body_length=0, max_iter=20, ignore_distortions=True,
                        time_interval=[4, 44]),
+        # half-overlapping windows of 16 frames stepped one after the other (pose_refinement.py:786-796, :1006):
+        # 46 frames -> Time = 32 -> windows [0,16) [8,24) [16,32), three Adam steps per iteration
+        'batch': dict(lr=0.01, lambda_smooth=1e-3, lambda_body_length=1, max_iter=12, batch_size=16, time_interval=[1, 47]),
     }
     for tag, dt in [('f32', torch.float32), ('f64', torch.float64)]:
         for rname, kw in runs.items():

@@ -13,6 +13,7 @@ RUNS = {
                  time_interval=[0, 48]),
     'nodist': dict(lr=0.005, lambda_smooth=0.5, lambda_body_length=0, max_iter=20, ignore_distortions=True,
                    time_interval=[4, 44]),
+    'batch': dict(lr=0.01, lambda_smooth=1e-3, lambda_body_length=1, max_iter=12, batch_size=16, time_interval=[1, 47]),
 }
 
 
