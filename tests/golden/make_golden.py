@@ -248,6 +248,14 @@ def golden_extrinsic(ref_refine, syn, out):
         store[f'{key}_T'] = opt.decomposed_cam_params[2][2].detach().numpy().astype(np.float64)
         store[f'{key}_best_R'] = opt.best_decomposed_cam_params[2][1].numpy().astype(np.float64)
         store[f'{key}_best_T'] = opt.best_decomposed_cam_params[2][2].numpy().astype(np.float64)
+    # plain trajectory optimisation with a subset of the cameras in the likelihood (camera_IDs, pose_refinement.py:866)
+    opt = ref_refine.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(), decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                                  body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), camera_IDs=[0, 2], torch_dtype=torch.float64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt.sgd_optimize(lr=0.01, lambda_smooth=1e-3, lambda_body_length=1.0, max_iter=8, print_frequency=1000, time_interval=[0, 12])
+    for cost, vals in opt.all_costs_total.items():
+        store[f'f64_subset_hist_{cost}'] = np.array([float(v) for v in vals])
+    store['f64_subset_traj'] = opt.trajectory.detach().numpy().astype(np.float64)
     np.savez_compressed(os.path.join(out, 'extrinsic_T12.npz'), **store)
 
 

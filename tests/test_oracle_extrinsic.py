@@ -92,3 +92,16 @@ def test_joint_camera_and_trajectory_optimisation_matches_reference_runs(key):
     assert np.abs(res['final'] - g[f'{key}_traj']).max() < atol * 10
     assert np.abs(res['cams'][2][1] - g[f'{key}_R']).max() < atol and np.abs(res['cams'][2][2] - g[f'{key}_T']).max() < atol * 1e3
     assert np.abs(res['best_cams'][2][1] - g[f'{key}_best_R']).max() < atol
+
+
+def test_camera_subset_in_the_likelihood_matches_reference_run():
+    """camera_IDs=[0, 2] out of three cameras (pose_refinement.py:866): pins the oracle path the GPU test
+    test_sgd_optimize_matches_oracle[subset_of_cameras] compares against."""
+    g = np.load(GOLD)
+    cams = _cams(g)
+    out = R.sgd_optimize(g['gaussians'], g['initial'], [cams[0], cams[2]], _lengths(), lr=0.01, lambda_smooth=1e-3,
+                         lambda_body_length=1.0, max_iter=8, time_interval=(0, 12))
+    for name, hist in out['history'].items():
+        ref = g[f'f64_subset_hist_{name}']
+        assert len(hist) == len(ref) and np.allclose(hist, ref, rtol=1e-12, atol=0), name
+    assert np.abs(out['final'] - g['f64_subset_traj']).max() < 1e-9
