@@ -2,7 +2,9 @@
 // reference's Optimized_3d_Pose_Estimation.sgd_optimize iterates with torch autograd
 // (pose_refinement.py:836-889 costs, :1002-1091 loop).
 //
-// One optimiser step = three kernels over the frame-sharded state (no host round trip in between):
+// Two formulations of one optimiser step over the frame-sharded state (no host round trip inside either):
+//
+// three-phase step (mc3d_refine_phase_*: windows of a batch, host-driven multi-GPU exchange, very large shards)
 //   A  costs   : per (frame, joint) reprojection Mahalanobis terms for every camera (camera-0 Gaussians, upstream
 //                quirk Q1), second-difference smoothness terms, bone lengths -> 7 global sums (finite-masked,
 //                nan_mean semantics)
@@ -10,12 +12,18 @@
 //                -> g, and the global sum of g^2
 //   C  step    : clip_grad_norm_(1.0), Adam (torch.optim.Adam arithmetic), running-mean early-stopping
 //                bookkeeping, conditional best-trajectory snapshot, cost history
-// Global sums live in a small double control block (ping-pong by step parity) so that a multi-GPU driver can
-// all-reduce them between kernels; every thread re-derives the scalars it needs from that block, so there are no
-// single-thread "finalise" launches.  A and B are grid-stride loops with one (frame, joint) item per thread
-// iteration and no barriers: temporal neighbours and bone end points come from global memory through L1, the
-// cameras sit in shared memory (128-bit loads), sums are reduced thread -> warp -> block -> one double atomic per
-// block.  The arithmetic type is the state dtype (float state -> float maths, as upstream's float32 run).
+// two-phase step (mc3d_refine_run_*, the default; see "two-phase step" below)
+//   1  costs + the four gradient components the gradient is linear in + their 10 dot products -> 17 global sums
+//   2  every thread derives the mix coefficients and |g|^2 from the sums, then the same clip / Adam / bookkeeping
+//   as a persistent cooperative kernel (all iterations in one launch, grid barriers) or a graph of two kernels.
+//
+// Global sums live in a small double control block (ping-pong by step parity); every thread re-derives the scalars it
+// needs, so there are no single-thread "finalise" launches.  The passes are grid-stride loops with one (frame, joint)
+// item per thread iteration and no block barriers inside: temporal neighbours and bone end points come from global
+// memory through L1, the cameras sit in shared memory (128-bit loads), sums are reduced thread -> warp -> block ->
+// one double atomic per block.  The arithmetic type is the state dtype (float state -> float maths, as upstream's
+// float32 run).  Several ranks exchange their partial sums and boundary frames INSIDE these kernels over NVLink peer
+// memory ("in-kernel exchange" below); a host-driven driver may instead all-reduce the control block between phases.
 #include "mc3d_common.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -1207,7 +1215,7 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
     long long done = 0;
     if (pb->gc && pb->xchg[0] && n_iters > 0 && pb->n_frames > 0) {
         // Measured on B200 (float state, us per step at 400 / 12 500 / 100 000 frames x 17 joints on one GPU):
-        //   two-phase persistent 14.5 / 28 / 122, three-phase persistent 18 / 32 / 144, graph of three kernels
+        //   two-phase persistent 13 / 26 / 122, (a three-phase persistent kernel: 18 / 32 / 144, removed), graph of three kernels
         //   17 / 40 / 134, graph of two kernels 17 / 43 / 164.  The two-phase step moves 25 % more bytes (four gradient
         //   components instead of one) but evaluates the projections once and has one reduction fewer; beyond the
         //   sizes measured (MC3D_RF_SMALL) the byte count is assumed to win and the three-kernel graph is used.
