@@ -1269,7 +1269,6 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
 // What refine_run would launch for this problem (same decisions, no launch).
 static const char *refine_plan(const mc3d_refine_problem *pb) {
     if (!pb) return "invalid";
-    const long long n_items = (long long)pb->n_frames * pb->n_joints;
     const bool small = shard_is_small(pb);
     const char *e2 = getenv("MC3D_REFINE_TWO_PHASE"), *ef = getenv("MC3D_REFINE_FUSED");
     const int two_env = e2 ? atoi(e2) : -1, fused_env = ef ? atoi(ef) : -1;
