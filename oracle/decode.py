@@ -14,6 +14,9 @@ MSRA heatmap codec (``get_heatmap_maximum`` + the 0.25-pixel shift towards the l
 ``MSRAHeatmap.decode``): flat argmax (first maximum), score = the maximum, locations with score <= 0
 become (-1, -1), and for 1 < px < W-1, 1 < py < H-1 the keypoint moves 0.25 px along the sign of the
 central difference.  Coordinates are heatmap pixels; the caller applies the bbox affine.
+The argmax half (integer pixel, score, the (-1, -1) rule, first-of-ties) IS pinned by a third-party port of
+mmpose's ``_get_max_preds``: tests/golden/argmax_vitpose.npz (HF transformers' ViTPose
+``get_keypoint_predictions``); only the quarter-pixel shift rests on the restatement alone.
 """
 import numpy as np
 

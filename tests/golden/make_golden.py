@@ -108,6 +108,28 @@ def golden_moments(ref_mm, syn, out):
              means=np.array(means), stds=np.array(stds), versions=versions())
 
 
+def golden_argmax(syn, out):
+    """NOT the reference: an independent third-party restatement of the argmax half of mmpose's decode.
+
+    mmpose itself is neither vendored nor pinned upstream and is not installed here, so the quarter-pixel
+    decode stays "parity unpinned".  What can be pinned is its first half: HF transformers' ViTPose image
+    processor carries a port of mmpose's ``_get_max_preds`` (flat argmax -> (x, y), score = maximum,
+    (-1, -1) where the maximum is <= 0) as ``get_keypoint_predictions``; its outputs on fixed heatmaps are
+    stored here and both the oracle and the CUDA kernel are held to them (integer pixel + score)."""
+    import transformers
+    from transformers.models.vitpose.image_processing_vitpose import get_keypoint_predictions
+    hm, _ = syn.gaussian_blob_heatmaps(17, seed=21)
+    hm[2] = 0.0                          # maximum <= 0 -> (-1, -1), score 0
+    hm[3] = -0.5                         # all negative -> (-1, -1)
+    hm[4, 0, 0] = 3.0                    # maximum in a corner
+    hm[5, 63, 47] = 3.0                  # ... and in the last pixel
+    hm[6, 20, 11] = hm[6, 40, 30] = 2.5  # a tie: the first one in flat order wins
+    hm[7, 31, 0] = 2.0                   # on the left border
+    coords, scores = get_keypoint_predictions(hm[None].copy())
+    np.savez_compressed(os.path.join(out, 'argmax_vitpose.npz'), heatmaps=hm, coords=coords[0], scores=scores[0, :, 0],
+                        versions=np.array([f'numpy {np.__version__}', f'transformers {transformers.__version__}']))
+
+
 def golden_refine(ref_refine, ref_utils, syn, out):
     import torch
     torch.manual_seed(0)
@@ -270,13 +292,15 @@ def main():
     syn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(syn)
     ref_utils, ref_refine, ref_mm, ref_pe = import_reference(args.reference)
-    todo = args.only or ['dlt', 'pose3d', 'moments', 'refine', 'interp', 'extrinsic']
+    todo = args.only or ['dlt', 'pose3d', 'moments', 'argmax', 'refine', 'interp', 'extrinsic']
     if 'dlt' in todo:
         golden_dlt(ref_utils, syn, HERE)
     if 'pose3d' in todo:
         golden_pose3d(ref_pe, syn, HERE)
     if 'moments' in todo:
         golden_moments(ref_mm, syn, HERE)
+    if 'argmax' in todo:
+        golden_argmax(syn, HERE)
     if 'refine' in todo:
         golden_refine(ref_refine, ref_utils, syn, HERE)
     if 'interp' in todo:

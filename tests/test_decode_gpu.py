@@ -143,3 +143,15 @@ def test_nan_map_gives_nan_moments_only_there(dec, syn):
     assert np.isnan(got[9]).all()
     keep = np.arange(40) != 9
     assert np.array_equal(got[keep], ref[keep])
+
+
+def test_argmax_half_matches_transformers_port_of_mmpose(dec):
+    """The kernel against tests/golden/argmax_vitpose.npz (HF transformers' port of mmpose's ``_get_max_preds``):
+    integer pixel and score of every map, through all three kernel variants."""
+    g = load_golden('argmax_vitpose.npz')
+    for kw in ({}, {'force_tma': True}, {'generic': True}):
+        kp, _ = dec(_cuda(g['heatmaps'].copy()), **kw)
+        kp = kp.cpu().numpy()
+        assert np.array_equal(kp[:, 2], g['scores'])
+        assert np.array_equal(np.rint(kp[:, :2]), g['coords'])
+        assert np.all(np.isin(np.abs(kp[:, :2] - g['coords']), (0.0, 0.25)))
