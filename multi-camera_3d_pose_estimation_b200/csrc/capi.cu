@@ -47,42 +47,75 @@ int decode_device(const float *d_hm, long long n_maps, int H, int W, float thr, 
 // (PCIe is full duplex, the copy engines run beside the SMs).
 namespace {
 constexpr int NBUF = 3;
+constexpr int MAX_DEVICES = 64;
 struct HostPipe {
-    int device = -1;
+    bool ready = false;
     cudaStream_t stream[NBUF] = {nullptr, nullptr, nullptr};
     void *d_in[NBUF] = {nullptr, nullptr, nullptr};
     void *d_out[NBUF] = {nullptr, nullptr, nullptr};
     size_t in_bytes = 0, out_bytes = 0;
 };
 std::mutex g_pipe_mutex;
-HostPipe g_pipe;
+HostPipe g_pipes[MAX_DEVICES];          // one staging pipeline per device ordinal, grown on demand, kept for the process
 
-int ensure_pipe(int device, size_t in_bytes, size_t out_bytes) {
+int ensure_pipe(int device, size_t in_bytes, size_t out_bytes, HostPipe **out) {
+    if (device < 0 || device >= MAX_DEVICES) { set_error("device ordinal %d out of range", device); return MC3D_ERR_INVALID_ARGUMENT; }
     MC3D_CUDA_TRY(cudaSetDevice(device));
-    if (g_pipe.device != device) {
-        if (g_pipe.device >= 0) { set_error("host pipeline already bound to device %d", g_pipe.device); return MC3D_ERR_UNSUPPORTED; }
-        for (int b = 0; b < NBUF; ++b) MC3D_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.stream[b], cudaStreamNonBlocking));
-        g_pipe.device = device;
+    HostPipe &pipe = g_pipes[device];
+    if (!pipe.ready) {
+        for (int b = 0; b < NBUF; ++b)
+            if (!pipe.stream[b]) MC3D_CUDA_TRY(cudaStreamCreateWithFlags(&pipe.stream[b], cudaStreamNonBlocking));
+        pipe.ready = true;
     }
-    if (in_bytes > g_pipe.in_bytes) {
+    if (in_bytes > pipe.in_bytes) {
+        pipe.in_bytes = 0;
         for (int b = 0; b < NBUF; ++b) {
-            if (g_pipe.d_in[b]) MC3D_CUDA_TRY(cudaFree(g_pipe.d_in[b]));
-            g_pipe.d_in[b] = nullptr;
-            MC3D_CUDA_TRY(cudaMalloc(&g_pipe.d_in[b], in_bytes));
+            if (pipe.d_in[b]) MC3D_CUDA_TRY(cudaFree(pipe.d_in[b]));
+            pipe.d_in[b] = nullptr;
+            MC3D_CUDA_TRY(cudaMalloc(&pipe.d_in[b], in_bytes));
         }
-        g_pipe.in_bytes = in_bytes;
+        pipe.in_bytes = in_bytes;
     }
-    if (out_bytes > g_pipe.out_bytes) {
+    if (out_bytes > pipe.out_bytes) {
+        pipe.out_bytes = 0;
         for (int b = 0; b < NBUF; ++b) {
-            if (g_pipe.d_out[b]) MC3D_CUDA_TRY(cudaFree(g_pipe.d_out[b]));
-            g_pipe.d_out[b] = nullptr;
-            MC3D_CUDA_TRY(cudaMalloc(&g_pipe.d_out[b], out_bytes));
+            if (pipe.d_out[b]) MC3D_CUDA_TRY(cudaFree(pipe.d_out[b]));
+            pipe.d_out[b] = nullptr;
+            MC3D_CUDA_TRY(cudaMalloc(&pipe.d_out[b], out_bytes));
         }
-        g_pipe.out_bytes = out_bytes;
+        pipe.out_bytes = out_bytes;
+    }
+    *out = &pipe;
+    return MC3D_OK;
+}
+
+// Wait for everything queued on the pipeline.  Called on every exit path: the copies read and write the CALLER's host
+// buffers, so nothing may still be in flight when the entry point returns, error or not.
+int drain_pipe(HostPipe &pipe, int status) {
+    for (int i = 0; i < NBUF; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(pipe.stream[i]);
+        if (e != cudaSuccess && status == MC3D_OK) status = cuda_fail(e, "cudaStreamSynchronize (host pipeline)");
+    }
+    return status;
+}
+}  // namespace
+
+template <typename T>
+static int triangulate_host_chunks(HostPipe &pipe, const T *h_kpts, long long n, long long chunk, const mc3d_rig *rig,
+                                   int layout, int mode, int flags, T *h_out) {
+    const size_t row_bytes = (size_t)3 * rig->n_views * sizeof(T);
+    int b = 0;
+    for (long long off = 0; off < n; off += chunk, b = (b + 1) % NBUF) {
+        const long long m = (n - off < chunk) ? (n - off) : chunk;
+        cudaStream_t s = pipe.stream[b];           // chunk i + NBUF re-uses buffer b in stream order
+        MC3D_CUDA_TRY(cudaMemcpyAsync(pipe.d_in[b], h_kpts + off * 3 * rig->n_views, (size_t)m * row_bytes,
+                                      cudaMemcpyHostToDevice, s));
+        const int st = triangulate_device<T>((const T *)pipe.d_in[b], m, rig, layout, mode, flags, (T *)pipe.d_out[b], s);
+        if (st != MC3D_OK) return st;
+        MC3D_CUDA_TRY(cudaMemcpyAsync(h_out + off * 3, pipe.d_out[b], (size_t)m * 3 * sizeof(T), cudaMemcpyDeviceToHost, s));
     }
     return MC3D_OK;
 }
-}  // namespace
 
 template <typename T>
 int triangulate_host(const T *h_kpts, long long n, const mc3d_rig *rig, int layout, int mode, int flags, T *h_out,
@@ -95,20 +128,28 @@ int triangulate_host(const T *h_kpts, long long n, const mc3d_rig *rig, int layo
     const size_t row_bytes = (size_t)3 * rig->n_views * sizeof(T);
     long long chunk = (long long)((64u << 20) / row_bytes) / 256 * 256;     // ~64 MiB of keypoints per chunk
     if (chunk > n) chunk = (n + 255) / 256 * 256;
-    int st = ensure_pipe(device, (size_t)chunk * row_bytes, (size_t)chunk * 3 * sizeof(T));
+    HostPipe *pipe = nullptr;
+    const int st = ensure_pipe(device, (size_t)chunk * row_bytes, (size_t)chunk * 3 * sizeof(T), &pipe);
     if (st != MC3D_OK) return st;
+    return drain_pipe(*pipe, triangulate_host_chunks<T>(*pipe, h_kpts, n, chunk, rig, layout, mode, flags, h_out));
+}
+
+static int decode_host_chunks(HostPipe &pipe, const float *h_hm, long long n_maps, long long chunk, size_t kpt_bytes, int H,
+                              int W, float thr, float *h_kpt, double *h_moments) {
+    const size_t map_bytes = (size_t)H * W * sizeof(float);
     int b = 0;
-    for (long long off = 0; off < n; off += chunk, b = (b + 1) % NBUF) {
-        const long long m = (n - off < chunk) ? (n - off) : chunk;
-        cudaStream_t s = g_pipe.stream[b];
-        MC3D_CUDA_TRY(cudaMemcpyAsync(g_pipe.d_in[b], h_kpts + off * 3 * rig->n_views, (size_t)m * row_bytes,
-                                      cudaMemcpyHostToDevice, s));
-        st = triangulate_device<T>((const T *)g_pipe.d_in[b], m, rig, layout, mode, flags, (T *)g_pipe.d_out[b], s);
+    for (long long off = 0; off < n_maps; off += chunk, b = (b + 1) % NBUF) {
+        const long long m = (n_maps - off < chunk) ? (n_maps - off) : chunk;
+        cudaStream_t s = pipe.stream[b];
+        float *d_kpt = (float *)pipe.d_out[b];
+        double *d_mom = (double *)((char *)pipe.d_out[b] + kpt_bytes);
+        MC3D_CUDA_TRY(cudaMemcpyAsync(pipe.d_in[b], h_hm + off * H * W, (size_t)m * map_bytes, cudaMemcpyHostToDevice, s));
+        const int st = decode_device((const float *)pipe.d_in[b], m, H, W, thr, 0, MC3D_KPT_PLAIN, 0, 0, nullptr, 0,
+                                     h_kpt ? d_kpt : nullptr, h_moments ? d_mom : nullptr, s);
         if (st != MC3D_OK) return st;
-        MC3D_CUDA_TRY(cudaMemcpyAsync(h_out + off * 3, g_pipe.d_out[b], (size_t)m * 3 * sizeof(T),
-                                      cudaMemcpyDeviceToHost, s));
+        if (h_kpt) MC3D_CUDA_TRY(cudaMemcpyAsync(h_kpt + off * 3, d_kpt, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_moments) MC3D_CUDA_TRY(cudaMemcpyAsync(h_moments + off * 6, d_mom, (size_t)m * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < NBUF; ++i) MC3D_CUDA_TRY(cudaStreamSynchronize(g_pipe.stream[i]));
     return MC3D_OK;
 }
 
@@ -123,23 +164,10 @@ int decode_host(const float *h_hm, long long n_maps, int H, int W, float thr, fl
     if (chunk < 1) chunk = 1;
     if (chunk > n_maps) chunk = n_maps;
     const size_t kpt_bytes = ((size_t)chunk * 3 * sizeof(float) + 255) / 256 * 256;   // moments start 256-B aligned
-    int st = ensure_pipe(device, (size_t)chunk * map_bytes, kpt_bytes + (size_t)chunk * 6 * sizeof(double));
+    HostPipe *pipe = nullptr;
+    const int st = ensure_pipe(device, (size_t)chunk * map_bytes, kpt_bytes + (size_t)chunk * 6 * sizeof(double), &pipe);
     if (st != MC3D_OK) return st;
-    int b = 0;
-    for (long long off = 0; off < n_maps; off += chunk, b = (b + 1) % NBUF) {
-        const long long m = (n_maps - off < chunk) ? (n_maps - off) : chunk;
-        cudaStream_t s = g_pipe.stream[b];
-        float *d_kpt = (float *)g_pipe.d_out[b];
-        double *d_mom = (double *)((char *)g_pipe.d_out[b] + kpt_bytes);
-        MC3D_CUDA_TRY(cudaMemcpyAsync(g_pipe.d_in[b], h_hm + off * H * W, (size_t)m * map_bytes, cudaMemcpyHostToDevice, s));
-        st = decode_device((const float *)g_pipe.d_in[b], m, H, W, thr, 0, MC3D_KPT_PLAIN, 0, 0, nullptr, 0,
-                           h_kpt ? d_kpt : nullptr, h_moments ? d_mom : nullptr, s);
-        if (st != MC3D_OK) return st;
-        if (h_kpt) MC3D_CUDA_TRY(cudaMemcpyAsync(h_kpt + off * 3, d_kpt, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-        if (h_moments) MC3D_CUDA_TRY(cudaMemcpyAsync(h_moments + off * 6, d_mom, (size_t)m * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    }
-    for (int i = 0; i < NBUF; ++i) MC3D_CUDA_TRY(cudaStreamSynchronize(g_pipe.stream[i]));
-    return MC3D_OK;
+    return drain_pipe(*pipe, decode_host_chunks(*pipe, h_hm, n_maps, chunk, kpt_bytes, H, W, thr, h_kpt, h_moments));
 }
 
 }  // namespace mc3d
