@@ -35,6 +35,7 @@ import yaml
 from . import _lib
 from . import refinement as _ref
 from . import utils
+from .interpolation import linear_interpolation  # noqa: F401  (module-level name upstream: pose_refinement.py:15)
 
 
 def _torch():
@@ -196,9 +197,11 @@ class Optimized_3d_Pose_Estimation:
         self.batch_size = batch_size
         self.lambda_smooth, self.lambda_body_length = lambda_smooth, lambda_body_length
         trajectory0 = self.initial_trajectory[t0:t1].clone().detach()
-        windows = [(b[0], b[-1] + 1) for b in self.create_batch_indices()]
+        batches = self.create_batch_indices()
+        windows = [(b[0], b[-1] + 1) for b in batches]
         if not windows:
             raise ValueError('time_interval / batch_size leave no frames to optimise')
+        self.indicies = batches[-1]                  # upstream leaves the last batch here (:1006); the cost methods read it
 
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size() > 1
@@ -290,6 +293,69 @@ class Optimized_3d_Pose_Estimation:
         self.iterations = st['iterations']
         return self
 
+
+    # ---- the three cost terms as public methods (pose_refinement.py:836-889) --------------------------------------------
+    def _evaluate_costs(self):
+        """One launch of the cost kernel (phase 0 of csrc/refine.cu) on ``self.trajectory`` over the frames
+        ``self.indicies`` with the settings of the last ``sgd_optimize`` call; returns the accumulator sums."""
+        torch = _torch()
+        for name in ('trajectory', 'gaussians_subset', 'Time'):
+            if getattr(self, name, None) is None:
+                raise AttributeError(f"'Optimized_3d_Pose_Estimation' object has no attribute '{name}'")   # as upstream before sgd_optimize
+        idx = list(getattr(self, 'indicies', None) or range(self.Time))
+        if idx != list(range(idx[0], idx[-1] + 1)):
+            raise NotImplementedError('self.indicies must be a contiguous range of frames (create_batch_indices makes only those)')
+        device = self._pick_device()
+        cam_rows = _ref.camera_rows(self.decomposed_cam_params, self.camera_IDs)
+        cam_rows = torch.tensor(cam_rows, dtype=self.torch_dtype).to(torch.float64).numpy()
+        traj = torch.as_tensor(self.trajectory).detach()
+        eng = _ref.RefineEngine(traj, self.gaussians_subset, cam_rows, self.body_lengths or {}, torch_dtype=self.torch_dtype,
+                                device=device, lr=0.0, betas=(0.9, 0.999), lambda_smooth=1.0, lambda_body_length=1.0,
+                                patience=1, tolerance=0.0, max_iter=1, ignore_distortions=getattr(self, 'ignore_distortions', False),
+                                window=(idx[0], idx[-1] + 1), n_window_frames=len(idx), hist_capacity=4,
+                                comm=_ref.LocalComm(), use_exchange=False)
+        with torch.cuda.device(device):
+            eng.phases.phase(eng.problem, 0, 0, True, torch.cuda.current_stream().cuda_stream)
+            acc = eng.ctrl[:8].cpu().numpy()
+        return acc, eng.problem.aa
+
+    def _as_cost(self, value):
+        return _torch().tensor(value, dtype=self.torch_dtype)
+
+    def compute_likelihood_cost(self):
+        """Sets ``self.likelihood_cost``: mean over cameras, frames and joints of 0.5 d^T S d (pose_refinement.py:863-889;
+        camera-0 Gaussians for every camera, non-finite entries dropped by nan_mean)."""
+        acc, _ = self._evaluate_costs()
+        self.likelihood_cost = self._as_cost(acc[0] / acc[1] if acc[1] else float('nan'))
+
+    def compute_smoothness_cost(self):
+        """Sets ``self.smoothness_cost`` = lambda_smooth * mean_t |x_t - 2 x_{t-1} + x_{t-2}|^2 (pose_refinement.py:836-845)."""
+        acc, _ = self._evaluate_costs()
+        self.smoothness_cost = self._as_cost(self.lambda_smooth * acc[2] / acc[3] if acc[3] else float('nan'))
+
+    def compute_body_length_cost(self):
+        """Sets ``self.body_length_cost`` = lambda_body_length * |a - mu b|^2 / |a|^2 (pose_refinement.py:848-860)."""
+        if self.body_lengths is None:
+            raise AttributeError("'NoneType' object has no attribute 'keys'")
+        acc, aa = self._evaluate_costs()
+        mu = acc[4] / acc[5]
+        self.body_length_cost = self._as_cost(self.lambda_body_length * (acc[6] - 2.0 * mu * acc[4] + mu * mu * acc[5]) / aa)
+
+    def create_body_length_vect(self):
+        """Target bone lengths, each repeated ``batch_size`` times, in yaml key order (pose_refinement.py:768-781)."""
+        torch = _torch()
+        lengths = torch.tensor(list(self.body_lengths.values()), dtype=self.torch_dtype)
+        return lengths.repeat_interleave(self.batch_size)
+
+    def gaussian_likelihood(self, x, mean, cov_mat, eps=1e-6, cov_inv=None):
+        """-0.5 d^T Sigma^-1 d without the normalisation term (pose_refinement.py:708-761); plain torch ops on the
+        caller's tensors -- API helper, the optimiser evaluates this inside its kernels."""
+        torch = _torch()
+        if cov_inv is None:
+            cov = cov_mat + eps * torch.eye(cov_mat.size(-1), device=cov_mat.device).expand_as(cov_mat)
+            cov_inv = torch.linalg.inv(cov).to(self.torch_dtype)
+        diff = x - mean
+        return -0.5 * torch.einsum('...i,...ij,...j->...', diff, cov_inv, diff)
 
     # ---- one camera's extrinsics from sampled points (pose_refinement.py:684-706, :800-831, :915-1091) -----------------
     def sample_gaussians(self, N=None):
@@ -645,7 +711,6 @@ def main(argv=None):
 
     kpts_3d_interpolation = None
     if 'linear_interpolation' in refinement_types or args.interpolate_before_SGD:
-        from .interpolation import linear_interpolation
         kwargs = utils.prepare_kwargs(linear_interpolation, params.get('linear_interpolation'))
         kpts_3d_interpolation = linear_interpolation(kpts_3d, **kwargs)
     if 'linear_interpolation' in refinement_types:

@@ -2,12 +2,16 @@
 
 ``RefineEngine`` owns the frame-sharded state of one rank (trajectory with a two-frame halo, Adam moments,
 best snapshot, gradient scratch, camera-0 means / inverse covariances, the double control block) and drives
-the three phases of an optimiser step.  With ``world_size > 1`` (``torch.distributed`` initialised, one
-process per GPU) frames are sharded contiguously and the ONLY traffic per step is
+the optimiser steps: ``run`` hands whole iterations to the library (``mc3d_refine_run_*`` picks the two-phase
+persistent kernel or the graph of three kernels, see ``plan``), ``one_step`` drives the three phases one by one.
+With ``world_size > 1`` (``torch.distributed`` initialised, one process per GPU) frames are sharded contiguously
+and the ONLY traffic per step of the three-phase formulation is
 
     after phase 2 (previous step):  x halo   -- 2 frames to each neighbour (all_gather of the boundary frames)
     after phase 0:                  all-reduce of 7 doubles (cost sums and counts)
     after phase 1:                  all-reduce of 1 double (sum g^2)
+
+(the two-phase step exchanges one block of 17 sums instead of the two all-reduces)
 
 so every rank takes identical clip / Adam / early-stopping decisions with no further communication
 (SURVEY.md section 8e).  On GPUs that exchange happens INSIDE the kernels over NVLink peer memory (``PeerExchange``,
@@ -269,6 +273,9 @@ class RefineEngine:
         if torch_dtype not in (torch.float32, torch.float64):
             raise TypeError('torch_dtype must be float32 or float64')
         self.device = torch.device(device)
+        if self.device.type != 'cuda' and phases is None:
+            # CPU tensors are accepted only together with injected phases (the gloo tests of the sharding logic)
+            raise _lib.Mc3dError('RefineEngine needs a CUDA device: the refinement kernels have no CPU fallback')
         self.total_frames = int(trajectory.shape[0])
         self.J = int(trajectory.shape[1])
         if self.J > _lib.MAX_JOINTS:

@@ -77,6 +77,27 @@ def test_no_cpu_fallback():
     with pytest.raises(mc3d_b200.Mc3dError):
         from mc3d_b200.triangulation import triangulate_multiview
         triangulate_multiview(torch.zeros(4, 2, 3), np.zeros((2, 3, 4)))
+    # every other entry point of the path: heatmap decode, projection, interpolation, refinement (class and engine)
+    from mc3d_b200.mmpose_pose_estimation import PoseEstimator
+    with pytest.raises(mc3d_b200.Mc3dError):
+        PoseEstimator.get_heatmap_means_cov(None, np.zeros((2, 64, 48), dtype=np.float32))
+    import mc3d_b200.pose_refinement as pr
+    with pytest.raises(mc3d_b200.Mc3dError):
+        pr.project_points_torch(np.zeros((2, 17, 3)), np.eye(3), np.eye(3), np.zeros((3, 1)), np.zeros((1, 5)))
+    with pytest.raises(mc3d_b200.Mc3dError):
+        pr.linear_interpolation(np.zeros((12, 17, 3)))
+    import mc3d_b200.synthetic as syn
+    gs, init, cams, _ = syn.refinement_inputs(8, seed=1)
+    opt = pr.Optimized_3d_Pose_Estimation(gs, init, decomposed_cam_params_initial={i: list(cams[i]) for i in cams},
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS))
+    with pytest.raises(mc3d_b200.Mc3dError):
+        opt.sgd_optimize(max_iter=1, print_frequency=np.inf)
+    from mc3d_b200.refinement import RefineEngine, camera_rows
+    with pytest.raises(mc3d_b200.Mc3dError):
+        RefineEngine(init, gs, camera_rows(cams, [0, 1]), dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=torch.float64,
+                     device='cpu', lr=1e-3, betas=(0.9, 0.999), lambda_smooth=1.0, lambda_body_length=1.0, patience=10,
+                     tolerance=1e-5, max_iter=1, ignore_distortions=False, window=(0, 8), n_window_frames=8,
+                     hist_capacity=4)
 
 
 def test_product_never_imports_the_oracle():

@@ -122,6 +122,20 @@ def test_refinement_histories(ref, syn, seed):
         assert np.max(np.abs(np.array(hist) - want) / np.abs(want)) < 1e-11, (name, kw)
     assert np.abs(out['best'] - opt.best_trajectory.numpy()).max() < 1e-9
     assert np.abs(out['final'] - opt.trajectory.detach().numpy()).max() < 1e-9
+    # the three public cost methods on the final trajectory (they read the state sgd_optimize leaves behind)
+    opt.compute_likelihood_cost()
+    opt.compute_smoothness_cost()
+    opt.compute_body_length_cost()
+    t0, t1 = kw['time_interval']
+    x = opt.trajectory.detach().numpy()
+    Sinv = R.cov_inverse(g)[t0:t1]
+    cam_list = [[np.asarray(a, dtype=np.float64) for a in cams[i]] for i in cams]
+    lik, _, _ = R.likelihood(x, g[t0:t1, 0, :, :2], Sinv, cam_list, kw['ignore_distortions'], grad=False)
+    sm, _, _ = R.smoothness(x, kw['lambda_smooth'], grad=False)
+    bl, _, _ = R.body_length(x, R.bone_table(syn.EXAMPLE_BODY_LENGTHS), kw['lambda_body_length'], grad=False)
+    assert np.isclose(lik, float(opt.likelihood_cost), rtol=1e-11)
+    assert np.isclose(sm, float(opt.smoothness_cost), rtol=1e-11)
+    assert np.isclose(bl, float(opt.body_length_cost), rtol=1e-11, atol=1e-300)
 
 
 @pytest.mark.parametrize('seed', [141, 142])

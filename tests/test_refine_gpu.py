@@ -332,3 +332,38 @@ def test_long_run_at_scale_is_consistent_with_oracle_statistics(pr, syn):
     costs, _ = R.total_cost_and_grad(x, gs[:, 0, :, :2], R.cov_inverse(gs), list(cams.values()),
                                      R.bone_table(syn.EXAMPLE_BODY_LENGTHS), 1e-6, 1.0)
     assert np.isclose(hist['total_cost'][-2], costs['total_cost'], rtol=1e-9)
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+def test_public_cost_methods_on_the_final_trajectory(pr, syn, tag):
+    """compute_likelihood_cost / compute_smoothness_cost / compute_body_length_cost (pose_refinement.py:836-889) set the
+    cost attributes from the state sgd_optimize leaves behind; the oracle's costs of the same trajectory are the check
+    (tests/test_oracle_live_reference.py holds the oracle to upstream's own three methods)."""
+    import torch
+    g = load_golden('refine_T48.npz')
+    dt = torch.float64 if tag == 'f64' else torch.float32
+    cams = _cam_params(g, 2)
+    opt = pr.Optimized_3d_Pose_Estimation(g['gaussians'].copy(), g['init'].copy(), decomposed_cam_params_initial=cams,
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+    with pytest.raises(AttributeError):
+        opt.compute_smoothness_cost()                                  # no trajectory before sgd_optimize, as upstream
+    kw = dict(lr=0.01, lambda_smooth=1e-3, lambda_body_length=0.5, max_iter=6, time_interval=[2, 45], print_frequency=np.inf)
+    opt.sgd_optimize(**kw)
+    opt.compute_likelihood_cost()
+    opt.compute_smoothness_cost()
+    opt.compute_body_length_cost()
+    x = opt.trajectory.numpy().astype(np.float64)
+    gs = g['gaussians'].astype(np.float32 if tag == 'f32' else np.float64).astype(np.float64)
+    cam_list = [[np.asarray(a, dtype=np.float32 if tag == 'f32' else np.float64).astype(np.float64) for a in cams[i]] for i in cams]
+    Sinv = R.cov_inverse(gs)[2:45]
+    lik, _, _ = R.likelihood(x, gs[2:45, 0, :, :2], Sinv, cam_list, False, grad=False)
+    sm, _, _ = R.smoothness(x, kw['lambda_smooth'], grad=False)
+    bl, _, _ = R.body_length(x, R.bone_table(syn.EXAMPLE_BODY_LENGTHS), kw['lambda_body_length'], grad=False)
+    rtol = 1e-9 if tag == 'f64' else LOSS_RTOL
+    for got, want in ((opt.likelihood_cost, lik), (opt.smoothness_cost, sm), (opt.body_length_cost, bl)):
+        assert isinstance(got, torch.Tensor) and got.dtype == dt and got.dim() == 0
+        assert abs(float(got) - want) <= rtol * abs(want), (float(got), want)
+    assert tuple(opt.create_body_length_vect().shape) == (43 * len(syn.EXAMPLE_BODY_LENGTHS),)
+    d = torch.randn(5, 17, 2, dtype=dt)
+    Si = torch.eye(2, dtype=dt).expand(5, 17, 2, 2)
+    assert torch.allclose(opt.gaussian_likelihood(d, torch.zeros_like(d), None, cov_inv=Si), -0.5 * (d * d).sum(-1))
