@@ -10,11 +10,13 @@ from . import decode as _decode
 
 
 class PoseEstimator:
-    def __init__(self, *args, **kwargs):
+    def __init__(self, det_config, det_checkpoint, pose_config, pose_checkpoint, device='cpu', det_cat_id=0,
+                 bbox_thr=0.3, nms_thr=0.3, using_detector=True):
+        # upstream's signature (mmpose_pose_estimation.py:82); building the mmdet / mmpose networks is not on the path
         raise NotImplementedError('mc3d_b200 accelerates the decode only; construct the mmpose model with the '
                                   "reference's PoseEstimator and call PoseEstimator.get_heatmap_means_cov from here")
 
-    def predict(self, frame):
+    def predict(self, input_file, return_full_heatmaps=False):
         raise NotImplementedError('network inference is out of scope of mc3d_b200')
 
     @staticmethod

@@ -281,6 +281,45 @@ def golden_extrinsic(ref_refine, syn, out):
     np.savez_compressed(os.path.join(out, 'extrinsic_T12.npz'), **store)
 
 
+SURFACE = {
+    'utils': ['DLT', 'triangulate_points', 'get_projection_matrix', 'calculate_projection_matrix', 'get_params_from_name',
+              '_make_homogeneous_rep_matrix', 'project_points', 'compute_2d_coordinates', 'rotation_conversion',
+              'prepare_kwargs', 'load_config', 'get_function_defaults', 'get_body_part_lengths', 'get_body_part_vects',
+              'read_camera_parameters', 'read_rotation_translation', 'generate_connectivity_names'],
+    'pose_refinement': ['linear_interpolation', 'project_points_torch', 'gaussian_likelihood', 'nan_mean',
+                        'Optimized_3d_Pose_Estimation', 'Optimized_3d_Pose_Estimation.sgd_optimize',
+                        'Optimized_3d_Pose_Estimation.create_batch_indices', 'Optimized_3d_Pose_Estimation.sample_gaussians',
+                        'Optimized_3d_Pose_Estimation.compute_likelihood_cost',
+                        'Optimized_3d_Pose_Estimation.compute_smoothness_cost',
+                        'Optimized_3d_Pose_Estimation.compute_body_length_cost',
+                        'Optimized_3d_Pose_Estimation.gaussian_likelihood',
+                        'Optimized_3d_Pose_Estimation.create_body_length_vect'],
+    'pose_estimation': ['get_pose_3D'],
+    'mmpose_pose_estimation': ['PoseEstimator', 'PoseEstimator.predict', 'PoseEstimator.get_heatmap_means_cov',
+                               'PoseEstimator.get_heatmap_means_stds'],
+}
+
+
+def signature_of(module, dotted):
+    """[[parameter name, repr(default) or None], ...] of ``module.<dotted>`` (classes: their __init__ without self)."""
+    import inspect
+    obj = module
+    for part in dotted.split('.'):
+        obj = getattr(obj, part)
+    params = list(inspect.signature(obj).parameters.values())
+    return [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)] for p in params]
+
+
+def golden_surface(ref_utils, ref_refine, ref_mm, ref_pe, out):
+    """Names, parameter order and defaults of the reference's call surface for the path."""
+    import json
+    mods = {'utils': ref_utils, 'pose_refinement': ref_refine, 'pose_estimation': ref_pe, 'mmpose_pose_estimation': ref_mm}
+    surface = {m: {name: signature_of(mods[m], name) for name in names} for m, names in SURFACE.items()}
+    with open(os.path.join(out, 'surface.json'), 'w') as fh:
+        json.dump(surface, fh, indent=1, sort_keys=True)
+        fh.write('\n')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reference', default='/root/reference')
@@ -292,7 +331,7 @@ def main():
     syn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(syn)
     ref_utils, ref_refine, ref_mm, ref_pe = import_reference(args.reference)
-    todo = args.only or ['dlt', 'pose3d', 'moments', 'argmax', 'refine', 'interp', 'extrinsic']
+    todo = args.only or ['dlt', 'pose3d', 'moments', 'argmax', 'refine', 'interp', 'extrinsic', 'surface']
     if 'dlt' in todo:
         golden_dlt(ref_utils, syn, HERE)
     if 'pose3d' in todo:
@@ -307,8 +346,10 @@ def main():
         golden_interp(ref_refine, syn, HERE)
     if 'extrinsic' in todo:
         golden_extrinsic(ref_refine, syn, HERE)
+    if 'surface' in todo:
+        golden_surface(ref_utils, ref_refine, ref_mm, ref_pe, HERE)
     for f in sorted(os.listdir(HERE)):
-        if f.endswith('.npz'):
+        if f.endswith(('.npz', '.json')):
             print(f, os.path.getsize(os.path.join(HERE, f)), 'bytes')
 
 
