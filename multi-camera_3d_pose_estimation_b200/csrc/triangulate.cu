@@ -301,6 +301,51 @@ __device__ __forceinline__ void ldl3_apply_f(const Ldl3f &f, float r0, float r1,
     z0 = fmaf(r0, f.i0, -fmaf(f.l10, z1, f.l20 * z2));
 }
 
+// ---- the same 3x3 solve for TWO joints at once (MC3D_TRI_PACKED_SOLVE) -----------------------------------------------
+// Every float2 holds (joint 0, joint 1) of one thread.  Operation by operation the arithmetic is that of ldl3_factor_f /
+// ldl3_apply_f (one FFMA2 / FMUL2 / FADD2 = two independent IEEE operations), so results are bit-identical to the scalar
+// code; what changes is the issue-slot count of the two solve phases (scalar: ~130 float instructions per joint).
+#ifndef MC3D_TRI_PACKED_SOLVE
+#define MC3D_TRI_PACKED_SOLVE 0
+#endif
+struct Ldl3f2 {
+    float2 i0, l10, l20, i1, l21, i2;
+};
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 rcp_fast2(float2 a) { return make_float2(rcp_fast(a.x), rcp_fast(a.y)); }
+__device__ __forceinline__ float2 dot3_2(float2 a0, float2 a1, float2 a2, float2 b0, float2 b1, float2 b2) {
+    return __ffma2_rn(a0, b0, __ffma2_rn(a1, b1, __fmul2_rn(a2, b2)));       // fmaf(a0, b0, fmaf(a1, b1, a2 * b2))
+}
+
+__device__ __forceinline__ void ldl3_factor_f2(float2 m00, float2 m10, float2 m11, float2 m20, float2 m21, float2 m22,
+                                               Ldl3f2 &f, bool &ok0, bool &ok1) {
+    f.i0 = rcp_fast2(m00);
+    f.l10 = __fmul2_rn(m10, f.i0);
+    f.l20 = __fmul2_rn(m20, f.i0);
+    const float2 d1 = __ffma2_rn(neg2(f.l10), m10, m11);
+    f.i1 = rcp_fast2(d1);
+    const float2 t21 = __ffma2_rn(neg2(f.l20), m10, m21);
+    f.l21 = __fmul2_rn(t21, f.i1);
+    const float2 d2 = __ffma2_rn(neg2(f.l21), t21, __ffma2_rn(neg2(f.l20), m20, m22));
+    f.i2 = rcp_fast2(d2);
+    const float2 lim = make_float2(1e-6f, 1e-6f);
+    const float2 t1 = __fmul2_rn(lim, m11), t2 = __fmul2_rn(lim, m22);
+    ok0 = (m00.x > 0.f) & (d1.x > t1.x) & (d2.x > t2.x);
+    ok1 = (m00.y > 0.f) & (d1.y > t1.y) & (d2.y > t2.y);
+}
+
+__device__ __forceinline__ void ldl3_apply_f2(const Ldl3f2 &f, float2 r0, float2 r1, float2 r2, float2 &z0, float2 &z1,
+                                              float2 &z2) {
+    const float2 y1 = __ffma2_rn(neg2(f.l10), r0, r1);
+    const float2 y2 = __ffma2_rn(neg2(f.l21), y1, __ffma2_rn(neg2(f.l20), r0, r2));
+    z2 = __fmul2_rn(y2, f.i2);
+    z1 = __ffma2_rn(y1, f.i1, __fmul2_rn(neg2(f.l21), z2));
+    z0 = __ffma2_rn(r0, f.i0, neg2(__ffma2_rn(f.l10, z1, __fmul2_rn(f.l20, z2))));
+}
+
+// (a[0][i].x + a[0][i].y, a[1][i].x + a[1][i].y): the two halves of a row-packed accumulator, per joint
+#define MC3D_HSUM2(a, i) make_float2((a)[0][i].x + (a)[0][i].y, (a)[1][i].x + (a)[1][i].y)
+
 // views of the starting-point subset: (i * V) / NE for i < NE, NE = min(V, 3)
 __host__ __device__ constexpr int est_count(int V) { return V < 3 ? V : 3; }
 __host__ __device__ constexpr bool is_est_view(int V, int v) {
@@ -391,6 +436,30 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
                 }
             }
         }
+#if MC3D_TRI_PACKED_SOLVE
+        if constexpr (NJ == 2) {
+            Ldl3f2 f;
+            bool ok[2];
+            ldl3_factor_f2(MC3D_HSUM2(aM, 0), MC3D_HSUM2(aM, 1), MC3D_HSUM2(aM, 2), MC3D_HSUM2(aM, 3), MC3D_HSUM2(aM, 4),
+                           MC3D_HSUM2(aM, 5), f, ok[0], ok[1]);
+            float2 z0, z1, z2;
+            ldl3_apply_f2(f, neg2(MC3D_HSUM2(ab, 0)), neg2(MC3D_HSUM2(ab, 1)), neg2(MC3D_HSUM2(ab, 2)), z0, z1, z2);
+            const float2 nz2 = dot3_2(z0, z1, z2, z0, z1, z2);
+            const float2 tr2 = __fadd2_rn(__fadd2_rn(MC3D_HSUM2(aM, 0), MC3D_HSUM2(aM, 2)), MC3D_HSUM2(aM, 5));
+            const float nz[2] = {nz2.x, nz2.y}, tr[2] = {tr2.x, tr2.y};
+            const float zs[2][3] = {{z0.x, z1.x, z2.x}, {z0.y, z1.y, z2.y}};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                X[j][0] = X[j][1] = X[j][2] = NAN;
+                Xd[j][0] = Xd[j][1] = Xd[j][2] = 0.0;
+                state[j] = 0;
+                if (!act[j]) continue;
+                if (!(tr[j] <= 3.0e38f)) { state[j] = 1; continue; }
+                state[j] = 2;
+                if (ok[j] && nz[j] <= 3.0e38f) { Xd[j][0] = (double)zs[j][0]; Xd[j][1] = (double)zs[j][1]; Xd[j][2] = (double)zs[j][2]; }
+            }
+        } else
+#endif
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             X[j][0] = X[j][1] = X[j][2] = NAN;
@@ -477,6 +546,41 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
                 }
             }
         }
+#if MC3D_TRI_PACKED_SOLVE
+        if constexpr (NJ == 2) {
+            Ldl3f2 f;
+            bool ok[2];
+            ldl3_factor_f2(MC3D_HSUM2(aM, 0), MC3D_HSUM2(aM, 1), MC3D_HSUM2(aM, 2), MC3D_HSUM2(aM, 3), MC3D_HSUM2(aM, 4),
+                           MC3D_HSUM2(aM, 5), f, ok[0], ok[1]);
+            const float2 g0 = MC3D_HSUM2(ag, 0), g1 = MC3D_HSUM2(ag, 1), g2 = MC3D_HSUM2(ag, 2);
+            float2 e0, e1, e2;
+            ldl3_apply_f2(f, neg2(g0), neg2(g1), neg2(g2), e0, e1, e2);
+            const float2 rr = __fadd2_rn(make_float2(arr[0].x + arr[0].y, arr[1].x + arr[1].y), dot3_2(g0, g1, g2, e0, e1, e2));
+            const float2 x0 = __fadd2_rn(make_float2((float)Xd[0][0], (float)Xd[1][0]), e0);
+            const float2 x1 = __fadd2_rn(make_float2((float)Xd[0][1], (float)Xd[1][1]), e1);
+            const float2 x2 = __fadd2_rn(make_float2((float)Xd[0][2], (float)Xd[1][2]), e2);
+            const float2 nx2 = dot3_2(x0, x1, x2, x0, x1, x2);
+            const float2 lam2 = __fmul2_rn(rr, rcp_fast2(__fadd2_rn(make_float2(1.f, 1.f), nx2)));
+            float2 h0, h1, h2;
+            ldl3_apply_f2(f, __fmul2_rn(lam2, x0), __fmul2_rn(lam2, x1), __fmul2_rn(lam2, x2), h0, h1, h2);
+            e0 = __fadd2_rn(e0, h0); e1 = __fadd2_rn(e1, h1); e2 = __fadd2_rn(e2, h2);
+            const float2 ne2 = dot3_2(e0, e1, e2, e0, e1, e2);
+            const float2 lim2 = __fmul2_rn(make_float2(MC3D_TRI_ACCEPT, MC3D_TRI_ACCEPT), __fadd2_rn(nx2, make_float2(rig2, rig2)));
+            const float ne[2] = {ne2.x, ne2.y}, lam[2] = {lam2.x, lam2.y}, lim[2] = {lim2.x, lim2.y};
+            const float imax[2] = {fmaxf(f.i0.x, fmaxf(f.i1.x, f.i2.x)), fmaxf(f.i0.y, fmaxf(f.i1.y, f.i2.y))};
+            const float es[2][3] = {{e0.x, e1.x, e2.x}, {e0.y, e1.y, e2.y}};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (state[j] != 2) continue;
+                if (!ok[j] || !(ne[j] <= 3.0e38f) || !(fabsf(lam[j]) * imax[j] <= 3.0e-5f)) { state[j] = 1; continue; }
+                Xd[j][0] += (double)es[j][0]; Xd[j][1] += (double)es[j][1]; Xd[j][2] += (double)es[j][2];
+                if (ne[j] <= lim[j]) {
+                    X[j][0] = Xd[j][0]; X[j][1] = Xd[j][1]; X[j][2] = Xd[j][2];
+                    state[j] = 0;
+                }
+            }
+        } else
+#endif
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             if (state[j] != 2) continue;
@@ -679,6 +783,111 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     }
     if (tid == 0) bulk_wait_all<0>();
 }
+
+
+// ---- lean tile loop for the mixed kernel (MC3D_TRI_LEAN, tuning build) ----------------------------------------------------
+// Same ring, same solver, same results; what differs is the per-tile bookkeeping, which costs the kernel above ~75 of its
+// ~675 instructions per joint: this one processes FULL tiles only (the host launches the kernel above on the ragged tail),
+// so there is no activity mask and no ragged path in the loop; global addresses are running pointers instead of 64-bit
+// products; only thread 0 evaluates the refill; the output tile is written straight from the solver's registers with the
+// rare all-double fallback patching its slot afterwards (no register shuffling around an out-of-line call on the hot path);
+// and one block barrier per tile instead of two (thread 0 waits for the previous bulk store to have been read BEFORE the
+// barrier, which publishes that the other output buffer is free again).
+#ifndef MC3D_TRI_LEAN
+#define MC3D_TRI_LEAN 0
+#endif
+#if MC3D_TRI_LEAN
+template <int V>
+__device__ __noinline__ void mixed_cold_fix(const TriParams &prm, const float *row0, const float *row1, int st0, int st1,
+                                            bool l3v, float *ot0, float *ot1) {
+    if (st0 == 1) {
+        double f0, f1, f2;
+        solve_double_from_row(prm, row0, V, l3v, f0, f1, f2);
+        ot0[0] = (float)f0; ot0[1] = (float)f1; ot0[2] = (float)f2;
+    }
+    if (st1 == 1) {
+        double f0, f1, f2;
+        solve_double_from_row(prm, row1, V, l3v, f0, f1, f2);
+        ot1[0] = (float)f0; ot1[1] = (float)f1; ot1[2] = (float)f2;
+    }
+}
+
+template <int V, int LAYOUT>
+__global__ void __launch_bounds__(TRI_MTHREADS, (V >= 16) ? MC3D_TRI_MBLOCKS - 1 : MC3D_TRI_MBLOCKS)
+triangulate_mixed_lean_kernel(const float *__restrict__ kpts, float *__restrict__ out, unsigned n_tiles, int n_stages,
+                              const __grid_constant__ TriParams prm) {
+    static_assert(TRI_NJ == 2, "the lean loop is written for two joints per thread");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int row_elems = 3 * V;
+    constexpr uint32_t stage_bytes = (uint32_t)(TRI_MTILE * row_elems * sizeof(float));      // contiguous tiles only
+    constexpr uint32_t otile_bytes = (uint32_t)(TRI_MTILE * 3 * sizeof(float));
+    static_assert((row_elems * sizeof(float)) % 128 != 0, "padded row plans use the kernel above");
+    unsigned char *ring = smem_raw;
+    float *otile = reinterpret_cast<float *>(smem_raw + (size_t)n_stages * stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + 2 * otile_bytes);
+    CamC *cam = reinterpret_cast<CamC *>(full + 8);
+    const int tid = threadIdx.x;
+    const unsigned first = blockIdx.x, stride = gridDim.x;
+    const unsigned my_tiles = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    if (tid < V) {
+        CamC c;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) c.Pc[k] = prm.Pc[tid][k];
+        c.cxd = prm.cxyd[tid][0];
+        c.cyd = prm.cxyd[tid][1];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c.p10[k] = prm.p10[tid][k];
+        c.p2 = make_float4(prm.p2[tid][0].x, prm.p2[tid][1].x, prm.p2[tid][2].x, prm.p2[tid][3].x);
+        c.cx = prm.cxy[tid].x;
+        c.cy = prm.cxy[tid].y;
+        c.pad0 = c.pad1 = 0.f;
+        cam[tid] = c;
+    }
+    __syncthreads();
+    // thread 0 only: global addresses of the tiles this CTA loads and stores (computed inside its branches, so the other
+    // warps neither execute the 64-bit arithmetic nor hold the pointers in registers)
+    auto load_tile = [&](unsigned i, int st) {        // i-th tile of this CTA into stage st
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(kpts) + ((size_t)first + (size_t)i * stride) * stage_bytes;
+        mbar_arrive_expect_tx(&full[st], stage_bytes);
+        bulk_g2s(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st]);
+    };
+    if (tid == 0)
+        for (unsigned i = 0; i < (unsigned)(n_stages - 1) && i < my_tiles; ++i) load_tile(i, (int)i);
+    int s = 0, s_next = n_stages - 1;
+    uint32_t parity = 0;
+    for (unsigned k = 0; k < my_tiles; ++k) {
+        if (tid == 0 && k + (unsigned)(n_stages - 1) < my_tiles) load_tile(k + (unsigned)(n_stages - 1), s_next);   // refills the stage of iteration k - 1
+        const float *stage = reinterpret_cast<const float *>(ring + (size_t)s * stage_bytes);
+        mbar_wait(&full[s], parity);
+        const float *rows[TRI_NJ] = {stage + tid * row_elems, stage + (tid + TRI_MTHREADS) * row_elems};
+        const bool act[TRI_NJ] = {true, true};
+        double X[TRI_NJ][3];
+        int state[TRI_NJ];
+        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state);
+        float *ot = otile + (size_t)(k & 1) * TRI_MTILE * 3 + tid * 3;
+        ot[0] = (float)X[0][0]; ot[1] = (float)X[0][1]; ot[2] = (float)X[0][2];
+        ot[TRI_MTHREADS * 3 + 0] = (float)X[1][0]; ot[TRI_MTHREADS * 3 + 1] = (float)X[1][1]; ot[TRI_MTHREADS * 3 + 2] = (float)X[1][2];
+        if (state[0] == 1 || state[1] == 1)
+            mixed_cold_fix<V>(prm, stage + tid * row_elems, stage + (tid + TRI_MTHREADS) * row_elems, state[0], state[1],
+                              LAYOUT == MC3D_LAYOUT_3V, ot, ot + TRI_MTHREADS * 3);
+        fence_proxy_async_smem();
+        if (tid == 0) bulk_wait_read<0>();            // the store of iteration k - 1 has left the OTHER output buffer
+        __syncthreads();                              // stage s consumed by everyone; output tile complete
+        if (tid == 0) {
+            bulk_s2g(reinterpret_cast<unsigned char *>(out) + ((size_t)first + (size_t)k * stride) * otile_bytes,
+                     otile + (size_t)(k & 1) * TRI_MTILE * 3, otile_bytes);
+            bulk_commit();
+        }
+        if (++s == n_stages) { s = 0; parity ^= 1u; }
+        if (++s_next == n_stages) s_next = 0;
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+#endif  // MC3D_TRI_LEAN
 
 
 // ---- kernel -----------------------------------------------------------------------------------
@@ -973,6 +1182,30 @@ static int launch_mixed(const float *d_kpts, long long n, const TriParams &prm, 
         if (occ > per_sm) { per_sm = occ; n_stages = st; smem = sm_bytes; }
     }
     if (per_sm < 1) { set_error("mixed triangulate kernel does not fit in shared memory"); return MC3D_ERR_UNSUPPORTED; }
+#if MC3D_TRI_LEAN
+    // tuning build: full tiles through the lean loop, the ragged tail (< one tile) through the kernel above
+    if (tri_row_plan(3 * V, (int)sizeof(float)).group == 0 && n / TRI_MTILE > 0 && n / TRI_MTILE < 0x7fffffffLL) {
+        auto lean = triangulate_mixed_lean_kernel<V, LAYOUT>;
+        static bool lean_attr_done = false;
+        if (!lean_attr_done) {
+            MC3D_CUDA_TRY(cudaFuncSetAttribute(lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            lean_attr_done = true;
+        }
+        const long long n_full = n / TRI_MTILE, tail = n - n_full * TRI_MTILE;
+        long long lgrid = (long long)sm_count() * per_sm;
+        if (lgrid > n_full) lgrid = n_full;
+        lean<<<(unsigned)lgrid, TRI_MTHREADS, smem, stream>>>(d_kpts, d_out, (unsigned)n_full, n_stages, prm);
+        count_launch();
+        MC3D_CUDA_TRY(cudaGetLastError());
+        if (tail > 0) {
+            kern<<<1, TRI_MTHREADS, smem, stream>>>(d_kpts + n_full * TRI_MTILE * 3 * V, d_out + n_full * TRI_MTILE * 3, tail,
+                                                    n_stages, prm);
+            count_launch();
+            MC3D_CUDA_TRY(cudaGetLastError());
+        }
+        return MC3D_OK;
+    }
+#endif
     const long long n_tiles = (n + TRI_MTILE - 1) / TRI_MTILE;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > n_tiles) grid = n_tiles;
