@@ -20,6 +20,8 @@ VARIANTS = {
     'packed': ['-DMC3D_TRI_PACKED_SOLVE=1'],             # both solve phases of the float kernel on (joint 0, joint 1) pairs
     'lean': ['-DMC3D_TRI_LEAN=1'],                       # full-tile loop with running pointers, one barrier per tile
     'lean_packed': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1'],
+    # rows formed as w (yx P2 + p10): two instructions fewer per joint-view, rounding differs (NOT bit-identical)
+    'lean_packed_rows': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_ROWS_E=1'],
 }
 
 
