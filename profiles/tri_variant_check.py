@@ -62,8 +62,14 @@ def main():
             ref = out.clone()
             same = 'reference'
         else:
-            same = 'bit-identical' if torch.equal(out.view(torch.int32), ref.view(torch.int32)) else \
-                f'DIFFERENT in {(out.view(torch.int32) != ref.view(torch.int32)).any(dim=1).sum().item()} joints'
+            if torch.equal(out.view(torch.int32), ref.view(torch.int32)):
+                same = 'bit-identical'
+            else:
+                n_diff = (out.view(torch.int32) != ref.view(torch.int32)).any(dim=1).sum().item()
+                ok = torch.isfinite(out).all(dim=1) & torch.isfinite(ref).all(dim=1)
+                worst = (out[ok].double() - ref[ok].double()).abs().max().item() if ok.any() else float('nan')
+                nan_mismatch = (torch.isnan(out) != torch.isnan(ref)).any().item()
+                same = f'DIFFERENT in {n_diff} joints (max |diff| {worst:.3e} mm, NaN pattern {"differs" if nan_mismatch else "equal"})'
         print(f'{name:14s} {ms:8.4f} ms  {args.joints / ms * 1e3:.4e} joints/s  {same}', flush=True)
 
 
