@@ -95,6 +95,22 @@ def golden_pose3d(ref_pe, syn, out):
                     for k, n in enumerate(['K', 'R', 'T', 'dist'])})
 
 
+def golden_config1(ref_pe, syn, out):
+    """BASELINE.json configs[0] at its full size: 2-camera COCO-17 triangulation of 400 synthetic frames through the
+    reference's own ``get_pose_3D`` (the record_and_estimate_pose 3D step).  Keypoints are rounded to float32 first so
+    that the fixture stores them in half the bytes; the reference ran on exactly those values."""
+    rng = np.random.default_rng(0)
+    cams = syn.stereo_rig(distortion=True)
+    X = syn.smooth_trajectory(400, 17, rng, centre=(0, 0, 3000.0))
+    kp32 = syn.keypoints_from_trajectory(X, cams, rng).astype(np.float32)          # (400, 17, 3, 2)
+    kp = kp32.astype(np.float64)
+    cam_params = {i: [np.asarray(a) for a in cams[i]] for i in cams}
+    with contextlib.redirect_stdout(io.StringIO()):
+        p3d = ref_pe.get_pose_3D(cam_params, list(kp))
+    np.savez_compressed(os.path.join(out, 'pose3d_config1.npz'), kpts=kp32, p3d=p3d, versions=versions(),
+                        **{f'cam{i}_{n}': np.asarray(cams[i][k]) for i in cams for k, n in enumerate(['K', 'R', 'T', 'dist'])})
+
+
 def golden_moments(ref_mm, syn, out):
     import torch
     hm, _ = syn.gaussian_blob_heatmaps(17, seed=13)
@@ -331,11 +347,13 @@ def main():
     syn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(syn)
     ref_utils, ref_refine, ref_mm, ref_pe = import_reference(args.reference)
-    todo = args.only or ['dlt', 'pose3d', 'moments', 'argmax', 'refine', 'interp', 'extrinsic', 'surface']
+    todo = args.only or ['dlt', 'pose3d', 'config1', 'moments', 'argmax', 'refine', 'interp', 'extrinsic', 'surface']
     if 'dlt' in todo:
         golden_dlt(ref_utils, syn, HERE)
     if 'pose3d' in todo:
         golden_pose3d(ref_pe, syn, HERE)
+    if 'config1' in todo:
+        golden_config1(ref_pe, syn, HERE)
     if 'moments' in todo:
         golden_moments(ref_mm, syn, HERE)
     if 'argmax' in todo:

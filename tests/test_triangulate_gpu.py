@@ -78,6 +78,21 @@ def test_get_pose_3D_matches_reference_golden(tag, n):
     assert np.array_equal(np.array(kp), g['kpts'])
 
 
+def test_get_pose_3D_config1_full_size_matches_reference():
+    """BASELINE.json configs[0] at its full size -- 2-camera COCO-17 triangulation of 400 frames -- against the output of
+    the reference's own get_pose_3D on the same keypoints (tests/golden/pose3d_config1.npz); one kernel launch here."""
+    import mc3d_b200
+    import mc3d_b200.pose_estimation as pe
+    g = load_golden('pose3d_config1.npz')
+    cams = cams_from_golden(g, 2)
+    kp = list(g['kpts'].astype(np.float64))
+    before = mc3d_b200.launch_count()
+    got = pe.get_pose_3D(cams, kp)
+    assert mc3d_b200.launch_count() - before == 1
+    assert got.shape == (400, 17, 3) and got.dtype == np.float64
+    assert rel_err(got, g['p3d']).max() < FP64_RTOL
+
+
 def test_get_pose_3D_camera_subset_and_no_scores(syn):
     import mc3d_b200.pose_estimation as pe
     rng = np.random.default_rng(3)
