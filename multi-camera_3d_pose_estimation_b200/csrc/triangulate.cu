@@ -362,6 +362,12 @@ __host__ __device__ constexpr bool group_has_est_view(int V, int vg, int G) {
 #ifndef MC3D_TRI_ROWS_E
 #define MC3D_TRI_ROWS_E 0
 #endif
+// tuning build: the double residuals use the projection rows as given (P0, P1, P2) instead of the rows re-centred on
+// the principal point -- the same residuals in exact arithmetic (re-centring only matters for the FLOAT rows), two
+// DADD and one shared-memory load fewer per joint-view; equal to the shipped kernel up to float-rounding ties
+#ifndef MC3D_TRI_RAW_RESID
+#define MC3D_TRI_RAW_RESID 0
+#endif
 // weighted float rows of one view, packed (a_k, c_k), k < NK
 template <int NK>
 __device__ __forceinline__ void float_rows(float x, float y, float w, float cx, float cy, const float (&p2)[4],
@@ -389,9 +395,31 @@ __device__ __forceinline__ void float_rows(float x, float y, float w, float cx, 
 #define MC3D_TRI_ACCEPT 1.0e-3f      // accept a correction with |e|^2 <= this * (|X|^2 + rig scale^2): |e| <~ 3 % of the range
 #endif
 
+// tuning build (with MC3D_TRI_PACKED_SOLVE, two joints per thread): the accepted result leaves the solver as FLOATS.  In the
+// first pass the starting point is float-valued, so the result float(Xp + e) is one float addition; the conversions
+// float(Xp), double(e), float(X) and the double additions of the shipped tail (9 F2F + 3 DADD per joint) are then only
+// executed by joints that need another pass.  Same value as the shipped kernel up to double-rounding ties.
+#ifndef MC3D_TRI_FLOAT_TAIL
+#define MC3D_TRI_FLOAT_TAIL 0
+#endif
+#if MC3D_TRI_FLOAT_TAIL && !MC3D_TRI_PACKED_SOLVE
+#error "MC3D_TRI_FLOAT_TAIL needs MC3D_TRI_PACKED_SOLVE"
+#endif
+#if MC3D_TRI_FLOAT_TAIL
+#define MC3D_XO_PARAM , float (&Xo)[NJ][3]
+#define MC3D_XO_ARG , Xo
+#else
+#define MC3D_XO_PARAM
+#define MC3D_XO_ARG
+#endif
+
 template <int V, int LAYOUT, int NJ>
 __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float rig2, const float *const (&rows)[NJ],
-                                             const bool (&act)[NJ], double (&X)[NJ][3], int (&state)[NJ]) {
+                                             const bool (&act)[NJ], double (&X)[NJ][3], int (&state)[NJ] MC3D_XO_PARAM) {
+#if MC3D_TRI_FLOAT_TAIL
+    static_assert(NJ == 2, "MC3D_TRI_FLOAT_TAIL is written for two joints per thread");
+    float Xf[NJ][3];                                                // float(Xd): exact in the first pass
+#endif
     constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
     double Xd[NJ][3];
     // ---- E: starting point from the subset ---------------------------------------------------------------
@@ -470,6 +498,14 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
                 state[j] = 2;
                 if (ok[j] && nz[j] <= 3.0e38f) { Xd[j][0] = (double)zs[j][0]; Xd[j][1] = (double)zs[j][1]; Xd[j][2] = (double)zs[j][2]; }
             }
+#if MC3D_TRI_FLOAT_TAIL
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const bool started = act[j] && tr[j] <= 3.0e38f && ok[j] && nz[j] <= 3.0e38f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { Xf[j][k] = started ? zs[j][k] : 0.f; Xo[j][k] = NAN; }
+            }
+#endif
         } else
 #endif
 #pragma unroll
@@ -523,7 +559,9 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
                     const double2 t = *reinterpret_cast<const double2 *>(&c.Pc[2 * k]);
                     Pc[2 * k] = t.x; Pc[2 * k + 1] = t.y;
                 }
+#if !MC3D_TRI_RAW_RESID
                 const double2 cxyd = *reinterpret_cast<const double2 *>(&c.cxd);
+#endif
                 const float4 p2v = c.p2;
                 const float p2[4] = {p2v.x, p2v.y, p2v.z, p2v.w};
                 float2 p10[4];
@@ -548,7 +586,11 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
                     const double d0 = fma(Pc[0], Xd[j][0], fma(Pc[1], Xd[j][1], fma(Pc[2], Xd[j][2], Pc[3])));
                     const double d1 = fma(Pc[4], Xd[j][0], fma(Pc[5], Xd[j][1], fma(Pc[6], Xd[j][2], Pc[7])));
                     const double d2 = fma(Pc[8], Xd[j][0], fma(Pc[9], Xd[j][1], fma(Pc[10], Xd[j][2], Pc[11])));
+#if MC3D_TRI_RAW_RESID
+                    const double xcd = (double)x, ycd = (double)y;                      // Pc holds P0, P1, P2 themselves
+#else
                     const double xcd = (double)x - cxyd.x, ycd = (double)y - cxyd.y;
+#endif
                     const float r1 = (float)fma(ycd, d2, -d1);   // y (P2.X) - P1.X : the cancellation is in double
                     const float r2 = (float)fma(-xcd, d2, d0);   // P0.X - x (P2.X)
                     const float2 t = __fmul2_rn(make_float2(w, w), make_float2(r1, r2));
@@ -568,9 +610,15 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
             float2 e0, e1, e2;
             ldl3_apply_f2(f, neg2(g0), neg2(g1), neg2(g2), e0, e1, e2);
             const float2 rr = __fadd2_rn(make_float2(arr[0].x + arr[0].y, arr[1].x + arr[1].y), dot3_2(g0, g1, g2, e0, e1, e2));
+#if MC3D_TRI_FLOAT_TAIL
+            const float2 x0 = __fadd2_rn(make_float2(Xf[0][0], Xf[1][0]), e0);
+            const float2 x1 = __fadd2_rn(make_float2(Xf[0][1], Xf[1][1]), e1);
+            const float2 x2 = __fadd2_rn(make_float2(Xf[0][2], Xf[1][2]), e2);
+#else
             const float2 x0 = __fadd2_rn(make_float2((float)Xd[0][0], (float)Xd[1][0]), e0);
             const float2 x1 = __fadd2_rn(make_float2((float)Xd[0][1], (float)Xd[1][1]), e1);
             const float2 x2 = __fadd2_rn(make_float2((float)Xd[0][2], (float)Xd[1][2]), e2);
+#endif
             const float2 nx2 = dot3_2(x0, x1, x2, x0, x1, x2);
             const float2 lam2 = __fmul2_rn(rr, rcp_fast2(__fadd2_rn(make_float2(1.f, 1.f), nx2)));
             float2 h0, h1, h2;
@@ -585,11 +633,26 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
             for (int j = 0; j < 2; ++j) {
                 if (state[j] != 2) continue;
                 if (!ok[j] || !(ne[j] <= 3.0e38f) || !(fabsf(lam[j]) * imax[j] <= 3.0e-5f)) { state[j] = 1; continue; }
+#if MC3D_TRI_FLOAT_TAIL
+                if (ne[j] <= lim[j]) {
+                    if (it == 0) {                                   // Xd is float-valued: float(Xd + e) is one float addition
+                        Xo[j][0] = Xf[j][0] + es[j][0]; Xo[j][1] = Xf[j][1] + es[j][1]; Xo[j][2] = Xf[j][2] + es[j][2];
+                    } else {
+                        Xo[j][0] = (float)(Xd[j][0] + (double)es[j][0]); Xo[j][1] = (float)(Xd[j][1] + (double)es[j][1]);
+                        Xo[j][2] = (float)(Xd[j][2] + (double)es[j][2]);
+                    }
+                    state[j] = 0;
+                } else {                                             // another pass from the updated point
+                    Xd[j][0] += (double)es[j][0]; Xd[j][1] += (double)es[j][1]; Xd[j][2] += (double)es[j][2];
+                    Xf[j][0] = (float)Xd[j][0]; Xf[j][1] = (float)Xd[j][1]; Xf[j][2] = (float)Xd[j][2];
+                }
+#else
                 Xd[j][0] += (double)es[j][0]; Xd[j][1] += (double)es[j][1]; Xd[j][2] += (double)es[j][2];
                 if (ne[j] <= lim[j]) {
                     X[j][0] = Xd[j][0]; X[j][1] = Xd[j][1]; X[j][2] = Xd[j][2];
                     state[j] = 0;
                 }
+#endif
             }
         } else
 #endif
@@ -694,7 +757,7 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     if (tid < V) {
         CamC c;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) c.Pc[k] = prm.Pc[tid][k];
+        for (int k = 0; k < 12; ++k) c.Pc[k] = MC3D_TRI_RAW_RESID ? prm.P[tid][k] : prm.Pc[tid][k];
         c.cxd = prm.cxyd[tid][0];
         c.cyd = prm.cxyd[tid][1];
 #pragma unroll
@@ -754,7 +817,10 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
             act[j] = tile * TRI_MTILE + slot < n;
             rows[j] = stage + tri_row_offset(plan, act[j] ? slot : tid, row_elems);      // inactive slots read a valid row
         }
-        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state);
+#if MC3D_TRI_FLOAT_TAIL
+        float Xo[TRI_NJ][3];
+#endif
+        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state MC3D_XO_ARG);
 #pragma unroll
         for (int j = 0; j < TRI_NJ; ++j)
             if (act[j] && state[j] == 1) {
@@ -762,6 +828,11 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
                 solve_double_from_row(prm, rows[j], V, LAYOUT == MC3D_LAYOUT_3V, f0, f1, f2);
                 X[j][0] = f0; X[j][1] = f1; X[j][2] = f2;
             }
+#if MC3D_TRI_FLOAT_TAIL
+#pragma unroll
+        for (int j = 0; j < TRI_NJ; ++j)             // accepted joints left the solver as floats; widen for the common tail
+            if (!(act[j] && state[j] == 1)) { X[j][0] = (double)Xo[j][0]; X[j][1] = (double)Xo[j][1]; X[j][2] = (double)Xo[j][2]; }
+#endif
         __syncthreads();                       // [A] every thread has consumed stage s
         float *ot = otile + (size_t)(k & 1) * TRI_MTILE * 3;
         if (full_tile) {
@@ -848,7 +919,7 @@ triangulate_mixed_lean_kernel(const float *__restrict__ kpts, float *__restrict_
     if (tid < V) {
         CamC c;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) c.Pc[k] = prm.Pc[tid][k];
+        for (int k = 0; k < 12; ++k) c.Pc[k] = MC3D_TRI_RAW_RESID ? prm.P[tid][k] : prm.Pc[tid][k];
         c.cxd = prm.cxyd[tid][0];
         c.cyd = prm.cxyd[tid][1];
 #pragma unroll
@@ -879,10 +950,17 @@ triangulate_mixed_lean_kernel(const float *__restrict__ kpts, float *__restrict_
         const bool act[TRI_NJ] = {true, true};
         double X[TRI_NJ][3];
         int state[TRI_NJ];
-        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state);
         float *ot = otile + (size_t)(k & 1) * TRI_MTILE * 3 + tid * 3;
+#if MC3D_TRI_FLOAT_TAIL
+        float Xo[TRI_NJ][3];
+        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state, Xo);
+        ot[0] = Xo[0][0]; ot[1] = Xo[0][1]; ot[2] = Xo[0][2];
+        ot[TRI_MTHREADS * 3 + 0] = Xo[1][0]; ot[TRI_MTHREADS * 3 + 1] = Xo[1][1]; ot[TRI_MTHREADS * 3 + 2] = Xo[1][2];
+#else
+        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state);
         ot[0] = (float)X[0][0]; ot[1] = (float)X[0][1]; ot[2] = (float)X[0][2];
         ot[TRI_MTHREADS * 3 + 0] = (float)X[1][0]; ot[TRI_MTHREADS * 3 + 1] = (float)X[1][1]; ot[TRI_MTHREADS * 3 + 2] = (float)X[1][2];
+#endif
         if (state[0] == 1 || state[1] == 1)
             mixed_cold_fix<V>(prm, stage + tid * row_elems, stage + (tid + TRI_MTHREADS) * row_elems, state[0], state[1],
                               LAYOUT == MC3D_LAYOUT_3V, ot, ot + TRI_MTHREADS * 3);

@@ -22,6 +22,12 @@ VARIANTS = {
     'lean_packed': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1'],
     # rows formed as w (yx P2 + p10): two instructions fewer per joint-view, rounding differs (NOT bit-identical)
     'lean_packed_rows': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_ROWS_E=1'],
+    # + double residuals from the rows as given (no re-centring subtraction): equal up to float-rounding ties
+    'lean_packed_rows_raw': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_ROWS_E=1', '-DMC3D_TRI_RAW_RESID=1'],
+    'lean_packed_raw': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_RAW_RESID=1'],
+    # + accepted results leave the solver as floats (9 F2F + 3 DADD per joint only for joints that need another pass)
+    'lean_packed_raw_ftail': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_RAW_RESID=1', '-DMC3D_TRI_FLOAT_TAIL=1'],
+    'all': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_ROWS_E=1', '-DMC3D_TRI_RAW_RESID=1', '-DMC3D_TRI_FLOAT_TAIL=1'],
 }
 
 
