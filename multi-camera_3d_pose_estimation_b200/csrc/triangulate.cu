@@ -1219,6 +1219,103 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
     return MC3D_OK;
 }
 
+// ---- lean tile loop for double storage (MC3D_TRI_LEAN64, tuning build) -------------------------------------------------------
+// The generic kernel above spends ~170 of its ~1 030 instructions per joint on per-tile bookkeeping (one joint per thread,
+// so nothing amortises it).  This one is the weighted, undistortion-free, compile-time-V, contiguous-tile case only: full
+// tiles (the host launches the generic kernel on the ragged tail), layout as a template parameter, global addresses computed
+// in thread 0's branches.  Same accumulation order, same solver: bit-identical results.
+#ifndef MC3D_TRI_LEAN64
+#define MC3D_TRI_LEAN64 0
+#endif
+#if MC3D_TRI_LEAN64
+template <int V, int LAYOUT>
+__global__ void __launch_bounds__(TRI_TILE, (V <= 8) ? 3 : 2)
+triangulate_lean64_kernel(const double *__restrict__ kpts, double *__restrict__ out, unsigned n_tiles, int n_stages,
+                          const __grid_constant__ TriParams prm) {
+    static_assert(V > 0 && V % 2 == 0, "even compile-time view count");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int row_elems = 3 * V;
+    constexpr uint32_t stage_bytes = (uint32_t)(TRI_TILE * row_elems * sizeof(double));
+    constexpr uint32_t otile_bytes = (uint32_t)(TRI_TILE * 3 * sizeof(double));
+    static_assert((row_elems * sizeof(double)) % 128 != 0, "padded row plans use the generic kernel");
+    unsigned char *ring = smem_raw;
+    double *otile = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + otile_bytes);
+    const int tid = threadIdx.x;
+    const unsigned first = blockIdx.x, stride = gridDim.x;
+    const unsigned my_tiles = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto load_tile = [&](unsigned i, int st) {
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(kpts) + ((size_t)first + (size_t)i * stride) * stage_bytes;
+        mbar_arrive_expect_tx(&full[st], stage_bytes);
+        bulk_g2s(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st]);
+    };
+    if (tid == 0)
+        for (unsigned i = 0; i < (unsigned)(n_stages - 1) && i < my_tiles; ++i) load_tile(i, (int)i);
+    int s = 0, s_next = n_stages - 1;
+    uint32_t parity = 0;
+    for (unsigned k = 0; k < my_tiles; ++k) {
+        if (tid == 0) {
+            if (k + (unsigned)(n_stages - 1) < my_tiles) load_tile(k + (unsigned)(n_stages - 1), s_next);
+            bulk_wait_read<0>();                   // the output tile of iteration k - 1 has left shared memory
+        }
+        const double *rowd = reinterpret_cast<const double *>(ring + (size_t)s * stage_bytes) + tid * row_elems;
+        mbar_wait(&full[s], parity);
+        double B[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) B[i] = 0.0;
+        int n_used = 0;
+#pragma unroll
+        for (int v = 0; v < V; v += 2) {
+            double x0, y0, w0, x1, y1, w1;
+            if (LAYOUT == MC3D_LAYOUT_3V) {
+                const double2 qx = *reinterpret_cast<const double2 *>(rowd + v);
+                const double2 qy = *reinterpret_cast<const double2 *>(rowd + V + v);
+                const double2 qw = *reinterpret_cast<const double2 *>(rowd + 2 * V + v);
+                x0 = qx.x; x1 = qx.y; y0 = qy.x; y1 = qy.y; w0 = qw.x; w1 = qw.y;
+            } else {
+                const double2 q0 = *reinterpret_cast<const double2 *>(rowd + 3 * v);
+                const double2 q1 = *reinterpret_cast<const double2 *>(rowd + 3 * v + 2);
+                const double2 q2 = *reinterpret_cast<const double2 *>(rowd + 3 * v + 4);
+                x0 = q0.x; y0 = q0.y; w0 = q1.x; x1 = q1.y; y1 = q2.x; w1 = q2.y;
+            }
+            n_used += (w0 != 0.0) + (w1 != 0.0);
+            accumulate_view(B, x0, y0, w0, prm.P[v]);
+            accumulate_view(B, x1, y1, w1, prm.P[v + 1]);
+        }
+        __syncthreads();                           // [A] stage s consumed; thread 0's wait on the previous store is published
+        double X0 = NAN, X1 = NAN, X2 = NAN;
+        const bool finite_in = fabs((B[0] + B[2]) + (B[5] + B[9])) <= 1.0e300;
+        if (finite_in && n_used >= 2) {
+            bool ok = false;
+            if (!(prm.flags & MC3D_TRI_FLAG_JACOBI)) ok = secular_newton(B, X0, X1, X2);
+            if (!ok) {
+                double Bl[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) Bl[i] = B[i];
+                jacobi4_smallest(Bl, X0, X1, X2);
+            }
+        }
+        otile[tid * 3 + 0] = X0;
+        otile[tid * 3 + 1] = X1;
+        otile[tid * 3 + 2] = X2;
+        fence_proxy_async_smem();
+        __syncthreads();                           // [B] tile complete and visible to the async proxy
+        if (tid == 0) {
+            bulk_s2g(reinterpret_cast<unsigned char *>(out) + ((size_t)first + (size_t)k * stride) * otile_bytes, otile, otile_bytes);
+            bulk_commit();
+        }
+        if (++s == n_stages) { s = 0; parity ^= 1u; }
+        if (++s_next == n_stages) s_next = 0;
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+#endif  // MC3D_TRI_LEAN64
+
 template <typename T, int V, int MODE, bool UNDISTORT>
 static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_out, cudaStream_t stream) {
     const int nv = prm.n_views;
@@ -1243,6 +1340,37 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
         if (occ > per_sm) { per_sm = occ; n_stages = st; smem = sm_bytes; }
     }
     if (per_sm < 1) { set_error("triangulate kernel does not fit in shared memory (views=%d)", nv); return MC3D_ERR_UNSUPPORTED; }
+#if MC3D_TRI_LEAN64
+    // tuning build: weighted double storage with a compile-time even view count -- full tiles through the lean loop, the
+    // ragged tail through the generic kernel
+    if constexpr (std::is_same<T, double>::value && MODE == MC3D_TRI_WEIGHTED && !UNDISTORT && V > 0 && V % 2 == 0 &&
+                  (3 * V * sizeof(double)) % 128 != 0) {              // rows of a multiple of 128 bytes use padded slots
+        if (tri_row_plan(3 * V, (int)sizeof(double)).group == 0 && n / TRI_TILE > 0 && n / TRI_TILE < 0x7fffffffLL) {
+            const long long n_full = n / TRI_TILE, tail = n - n_full * TRI_TILE;
+            long long lgrid = (long long)sm_count() * per_sm;
+            if (lgrid > n_full) lgrid = n_full;
+            static bool lean_attr_done[2] = {false, false};
+            const int li = prm.layout == MC3D_LAYOUT_3V ? 1 : 0;
+            if (li) {
+                auto lean = triangulate_lean64_kernel<V, MC3D_LAYOUT_3V>;
+                if (!lean_attr_done[li]) { MC3D_CUDA_TRY(cudaFuncSetAttribute(lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); lean_attr_done[li] = true; }
+                lean<<<(unsigned)lgrid, TRI_TILE, smem, stream>>>(d_kpts, d_out, (unsigned)n_full, n_stages, prm);
+            } else {
+                auto lean = triangulate_lean64_kernel<V, MC3D_LAYOUT_V3>;
+                if (!lean_attr_done[li]) { MC3D_CUDA_TRY(cudaFuncSetAttribute(lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); lean_attr_done[li] = true; }
+                lean<<<(unsigned)lgrid, TRI_TILE, smem, stream>>>(d_kpts, d_out, (unsigned)n_full, n_stages, prm);
+            }
+            count_launch();
+            MC3D_CUDA_TRY(cudaGetLastError());
+            if (tail > 0) {
+                kern<<<1, TRI_TILE, smem, stream>>>(d_kpts + n_full * TRI_TILE * 3 * V, d_out + n_full * TRI_TILE * 3, tail, n_stages, prm);
+                count_launch();
+                MC3D_CUDA_TRY(cudaGetLastError());
+            }
+            return MC3D_OK;
+        }
+    }
+#endif
     const long long n_tiles = (n + TRI_TILE - 1) / TRI_TILE;
     long long grid = (long long)sm_count() * per_sm;      // persistent: a whole number of waves
     if (grid > n_tiles) grid = n_tiles;

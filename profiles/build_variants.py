@@ -27,7 +27,9 @@ VARIANTS = {
     'lean_packed_raw': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_RAW_RESID=1'],
     # + accepted results leave the solver as floats (9 F2F + 3 DADD per joint only for joints that need another pass)
     'lean_packed_raw_ftail': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_RAW_RESID=1', '-DMC3D_TRI_FLOAT_TAIL=1'],
-    'all': ['-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_ROWS_E=1', '-DMC3D_TRI_RAW_RESID=1', '-DMC3D_TRI_FLOAT_TAIL=1'],
+    # double storage: lean full-tile loop (bit-identical)
+    'lean64': ['-DMC3D_TRI_LEAN64=1'],
+    'all': ['-DMC3D_TRI_LEAN64=1', '-DMC3D_TRI_LEAN=1', '-DMC3D_TRI_PACKED_SOLVE=1', '-DMC3D_TRI_ROWS_E=1', '-DMC3D_TRI_RAW_RESID=1', '-DMC3D_TRI_FLOAT_TAIL=1'],
 }
 
 

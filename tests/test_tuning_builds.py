@@ -10,7 +10,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, 'multi-camera_3d_pose_estimation_b200', 'csrc', 'triangulate.cu')
-MACROS = ['MC3D_TRI_LEAN', 'MC3D_TRI_PACKED_SOLVE', 'MC3D_TRI_ROWS_E', 'MC3D_TRI_RAW_RESID', 'MC3D_TRI_FLOAT_TAIL']
+MACROS = ['MC3D_TRI_LEAN', 'MC3D_TRI_PACKED_SOLVE', 'MC3D_TRI_ROWS_E', 'MC3D_TRI_RAW_RESID', 'MC3D_TRI_FLOAT_TAIL', 'MC3D_TRI_LEAN64']
 
 
 def _module(path, name):
