@@ -99,7 +99,10 @@ int mc3d_triangulate_f64(const double *d_kpts, int64_t n, const mc3d_rig *rig, i
                          int flags, double *d_out, void *stream);
 
 /* Host-buffer variants: chunked H2D -> kernel -> D2H pipeline on the library's own streams;
- * returns after the last byte of h_out is written.  `device` = CUDA ordinal. */
+ * returns after the last byte of h_out is written.  `device` = CUDA ordinal.  One staging pipeline
+ * (three streams, three pairs of device buffers for chunks of <= 64 MiB) per device ordinal, created
+ * on first use and kept for the life of the process; calls are serialised by a mutex; on an error
+ * every stream is drained before the call returns, so nothing still touches the caller's buffers. */
 int mc3d_triangulate_host_f32(const float *h_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode,
                               int flags, float *h_out, int device);
 int mc3d_triangulate_host_f64(const double *h_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode,
