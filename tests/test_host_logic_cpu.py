@@ -90,3 +90,40 @@ def test_get_pose_3D_config1_full_size(shims):
     g = load_golden('pose3d_config1.npz')
     got = pe.get_pose_3D(cams_from_golden(g, 2), list(g['kpts'].astype(np.float64)))
     assert got.shape == (400, 17, 3) and rel_err(got, g['p3d']).max() < 1e-9
+
+
+# ---- PoseEstimator.get_heatmap_means_cov / _stds: recursion, in-place thresholding, containers --------------------------
+def _oracle_decode(heatmaps, threshold=0.01, want_kpts=True, want_moments=True, **kw):
+    from oracle import decode as D
+    hm = np.asarray(heatmaps, dtype=np.float32)
+    lead = hm.shape[:-2]
+    flat = hm.reshape((-1,) + hm.shape[-2:])
+    mom = D.heatmap_means_cov(flat.copy(), threshold=threshold, mutate=False).reshape(lead + (6,)) if want_moments else None
+    kp = None
+    if want_kpts:
+        xy, sc = D.argmax_decode(flat)
+        kp = np.concatenate([xy, sc[:, None]], axis=1).astype(np.float32).reshape(lead + (3,))
+    return kp, mom
+
+
+def test_heatmap_moment_shims(monkeypatch):
+    import torch
+    import mc3d_b200.decode as dec
+    from mc3d_b200.mmpose_pose_estimation import PoseEstimator
+    monkeypatch.setattr(dec, 'decode_heatmaps', _oracle_decode)
+    g = load_golden('heatmap_moments.npz')
+    expect = g['heatmaps'].copy()
+    expect[expect < 0.01] = 0
+    hm = g['heatmaps'].copy()
+    got = PoseEstimator.get_heatmap_means_cov(None, hm)
+    assert got.shape == (17, 6) and got.dtype == np.float64 and np.abs(got - g['moments']).max() < 2e-5
+    assert np.array_equal(hm, expect)                                 # the caller's array is thresholded in place (Q7)
+    t = torch.tensor(g['heatmaps'].copy())
+    got_t = PoseEstimator.get_heatmap_means_cov(None, t)
+    assert np.abs(got_t - g['moments_torch_in']).max() < 2e-5 and np.array_equal(t.numpy(), expect)
+    lst = PoseEstimator.get_heatmap_means_cov(None, [g['heatmaps'].copy(), g['heatmaps'].copy()])
+    assert lst.shape == (2, 17, 6) and np.array_equal(lst[0], lst[1])
+    means, stds = PoseEstimator.get_heatmap_means_stds(expect.copy())
+    assert np.abs(np.array(means) - g['means']).max() < 2e-5 and np.abs(np.array(stds) - g['stds']).max() < 2e-5
+    with pytest.raises(NotImplementedError):
+        PoseEstimator('det.py', 'det.pth', 'pose.py', 'pose.pth')
