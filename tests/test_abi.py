@@ -108,3 +108,18 @@ def test_product_never_imports_the_oracle():
                 with open(os.path.join(dirpath, f)) as fh:
                     src = fh.read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_header_is_valid_c_and_links_from_c(built_lib, tmp_path):
+    """tests/c/abi_check.c (C99, -pedantic): includes mc3d.h, takes the address of all 35 entry points, compares the struct
+    sizes a C compiler sees with the library's, and checks one argument-validation path -- no compute, no GPU."""
+    from mc3d_b200 import _lib
+    exe = str(tmp_path / 'abi_check')
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'),
+           os.path.join(ROOT, 'tests', 'c', 'abi_check.c'), '-o', exe, '-L', libdir, '-lmc3d', f'-Wl,-rpath,{libdir}']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith(f'ok {len(_header_symbols())} entry points')
