@@ -306,7 +306,7 @@ __device__ __forceinline__ void ldl3_apply_f(const Ldl3f &f, float r0, float r1,
 // ldl3_apply_f (one FFMA2 / FMUL2 / FADD2 = two independent IEEE operations), so results are bit-identical to the scalar
 // code; what changes is the issue-slot count of the two solve phases (scalar: ~130 float instructions per joint).
 #ifndef MC3D_TRI_PACKED_SOLVE
-#define MC3D_TRI_PACKED_SOLVE 0
+#define MC3D_TRI_PACKED_SOLVE 1
 #endif
 struct Ldl3f2 {
     float2 i0, l10, l20, i1, l21, i2;
@@ -360,13 +360,13 @@ __host__ __device__ constexpr bool group_has_est_view(int V, int vg, int G) {
 }
 
 #ifndef MC3D_TRI_ROWS_E
-#define MC3D_TRI_ROWS_E 0
+#define MC3D_TRI_ROWS_E 1
 #endif
 // tuning build: the double residuals use the projection rows as given (P0, P1, P2) instead of the rows re-centred on
 // the principal point -- the same residuals in exact arithmetic (re-centring only matters for the FLOAT rows), two
 // DADD and one shared-memory load fewer per joint-view; equal to the shipped kernel up to float-rounding ties
 #ifndef MC3D_TRI_RAW_RESID
-#define MC3D_TRI_RAW_RESID 0
+#define MC3D_TRI_RAW_RESID 1
 #endif
 // weighted float rows of one view, packed (a_k, c_k), k < NK
 template <int NK>
@@ -400,7 +400,7 @@ __device__ __forceinline__ void float_rows(float x, float y, float w, float cx, 
 // float(Xp), double(e), float(X) and the double additions of the shipped tail (9 F2F + 3 DADD per joint) are then only
 // executed by joints that need another pass.  Same value as the shipped kernel up to double-rounding ties.
 #ifndef MC3D_TRI_FLOAT_TAIL
-#define MC3D_TRI_FLOAT_TAIL 0
+#define MC3D_TRI_FLOAT_TAIL 1
 #endif
 #if MC3D_TRI_FLOAT_TAIL && !MC3D_TRI_PACKED_SOLVE
 #error "MC3D_TRI_FLOAT_TAIL needs MC3D_TRI_PACKED_SOLVE"
@@ -877,7 +877,7 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
 // and one block barrier per tile instead of two (thread 0 waits for the previous bulk store to have been read BEFORE the
 // barrier, which publishes that the other output buffer is free again).
 #ifndef MC3D_TRI_LEAN
-#define MC3D_TRI_LEAN 0
+#define MC3D_TRI_LEAN 1
 #endif
 #if MC3D_TRI_LEAN
 template <int V>
@@ -1225,7 +1225,7 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
 // tiles (the host launches the generic kernel on the ragged tail), layout as a template parameter, global addresses computed
 // in thread 0's branches.  Same accumulation order, same solver: bit-identical results.
 #ifndef MC3D_TRI_LEAN64
-#define MC3D_TRI_LEAN64 0
+#define MC3D_TRI_LEAN64 1
 #endif
 #if MC3D_TRI_LEAN64
 template <int V, int LAYOUT>
