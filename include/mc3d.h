@@ -90,13 +90,29 @@ int mc3d_device_info(char *name, int name_len, int *sm_count, int *cc_major, int
 /* ---- 1. triangulation ---------------------------------------------------------------------
  * d_kpts: n joints x 3V scalars in `layout`; d_out: n x 3 (X,Y,Z).
  * Replaces: the per-(frame,joint) loop of pose_estimation.py:27-54 and utils.py:19-34.
- * f32: float storage; A^T A is accumulated in float and the solution is polished with residuals evaluated in
- *      double, so the error is one output rounding (MC3D_TRI_FLAG_FP64 selects all-double arithmetic).
+ * f32: float storage; a closed-form two-view start, then the float normal matrix and the gradient of ONE pass over the
+ *      views with residuals evaluated in double, so the error is one output rounding (MC3D_TRI_FLAG_FP64 selects
+ *      all-double arithmetic).
  * Degenerate joints (fewer than two views with non-zero weight, non-finite input) give NaN. */
 int mc3d_triangulate_f32(const float *d_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode,
                          int flags, float *d_out, void *stream);
 int mc3d_triangulate_f64(const double *d_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode,
                          int flags, double *d_out, void *stream);
+
+/* Starting-point plan of the float-storage kernel (host-only, no device work): up to two pairs of views (A, B) whose
+ * closed-form two-view point X = C + s H (x_A, y_A, 1),  s = (z kb - ka) / (ua.q - z ub.q),  q = (x_A, y_A, 1),
+ * z = alpha x_B + beta y_B  starts the iteration (the ray of view A cut by the plane that view B's pixel spans along
+ * its epipolar direction).  Exposed so that the plan can be checked without a GPU; the kernel's result does not
+ * depend on it, only its speed.  24 four-byte fields, no padding. */
+typedef struct {
+    float H[9];            /* inverse of the left 3x3 block of P_A (row-major) */
+    float C[3];            /* centre of camera A */
+    float ua[3], ub[3];    /* H^T (alpha P0 + beta P1)_B[:3],  H^T P2_B[:3] */
+    float alpha, beta;     /* unit epipolar direction in view B */
+    float ka, kb;          /* (alpha P0 + beta P1)_B . (C,1),  P2_B . (C,1) */
+    int32_t view_a, view_b;
+} mc3d_tri_start_pair;
+int mc3d_triangulate_start_plan(const mc3d_rig *rig, mc3d_tri_start_pair *pairs /* [2] */, int32_t *n_pairs);
 
 /* Host-buffer variants: chunked H2D -> kernel -> D2H pipeline on the library's own streams;
  * returns after the last byte of h_out is written.  `device` = CUDA ordinal.  One staging pipeline

@@ -32,6 +32,13 @@ class Rig(ctypes.Structure):
                 ('dist', ctypes.POINTER(ctypes.c_double))]
 
 
+class TriStartPair(ctypes.Structure):
+    """mc3d_tri_start_pair (include/mc3d.h): constants of one closed-form two-view starting point."""
+    _fields_ = [('H', ctypes.c_float * 9), ('C', ctypes.c_float * 3), ('ua', ctypes.c_float * 3), ('ub', ctypes.c_float * 3),
+                ('alpha', ctypes.c_float), ('beta', ctypes.c_float), ('ka', ctypes.c_float), ('kb', ctypes.c_float),
+                ('view_a', ctypes.c_int32), ('view_b', ctypes.c_int32)]
+
+
 MAX_JOINTS = 133
 MAX_BONES = 64
 MAX_PEERS = 16
@@ -100,6 +107,7 @@ SIGNATURES = {
                                   ctypes.POINTER(_c_int)]),
     'mc3d_triangulate_f32': (_c_int, [_c_vp, _c_i64, ctypes.POINTER(Rig), _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     'mc3d_triangulate_f64': (_c_int, [_c_vp, _c_i64, ctypes.POINTER(Rig), _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    'mc3d_triangulate_start_plan': (_c_int, [ctypes.POINTER(Rig), ctypes.POINTER(TriStartPair), ctypes.POINTER(ctypes.c_int32)]),
     'mc3d_triangulate_host_f32': (_c_int, [_c_vp, _c_i64, ctypes.POINTER(Rig), _c_int, _c_int, _c_int, _c_vp, _c_int]),
     'mc3d_triangulate_host_f64': (_c_int, [_c_vp, _c_i64, ctypes.POINTER(Rig), _c_int, _c_int, _c_int, _c_vp, _c_int]),
     'mc3d_decode_heatmaps_f32': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, ctypes.c_float, _c_int, _c_int, _c_int, _c_int,

@@ -15,6 +15,7 @@
 // registers.  Results leave through a shared-memory tile and a TMA bulk store.
 #include "mc3d_common.cuh"
 #include <math.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include <type_traits>
@@ -31,13 +32,9 @@ struct TriParams {
     int undistort;
     int flags;
     int layout;
-    // mixed-precision path (float storage): rows re-centred on each view's principal point
-    //   a = (y - cy) P2 - P1',  c = P0' - (x - cx) P2,   P0' = P0 - cx P2,  P1' = P1 - cy P2   (same rows, smaller numbers)
-    float2 p2[MC3D_MAX_VIEWS][4];     // (P2_k, P2_k)
-    float2 p10[MC3D_MAX_VIEWS][4];    // (-P1'_k, P0'_k)
-    float2 cxy[MC3D_MAX_VIEWS];       // (cx, cy) as floats
-    double cxyd[MC3D_MAX_VIEWS][2];   // the same values as doubles
-    double Pc[MC3D_MAX_VIEWS][12];    // P0', P1', P2 in double
+    // mixed-precision path (float storage)
+    mc3d_tri_start_pair start[2];     // closed-form two-view starting points (fill_start_pairs)
+    int n_start;
     float rig2;                       // mean squared distance of the camera centres from the world origin
 };
 
@@ -194,9 +191,6 @@ __device__ __forceinline__ void accumulate_view(double *B, double x, double y, d
     B[9] = fma(a[3], a[3], fma(c[3], c[3], B[9]));
 }
 
-// ---- mixed-precision solver (float storage) ---------------------------------------------------------------------
-// float LDL^T of a 3x3 SPD system (ldl3_factor_f / ldl3_apply_f below); approximate reciprocals are fine: the solve
-// only preconditions an iteration whose fixed point is set by residuals evaluated in double.
 __device__ __forceinline__ float rcp_fast(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -252,71 +246,50 @@ __device__ __forceinline__ void load_group(const float *row, int vg, float (&gx)
     }
 }
 
-// ---- merged-pass mixed-precision solver (float storage) -----------------------------------------------------------
-// The two-pass solver above touches every view twice (float normal equations, then double residuals).  This one
-// touches the full view set once:
-//   E. a weighted float DLT over a fixed subset of (at most) three well-spread views gives a starting point Xp that
-//      is a few millimetres from the minimiser (the subset's own noise); a subset without two usable views starts
-//      from the world origin instead and takes a second pass;
-//   M. ONE pass over all V views accumulates, per view, the float normal matrix M~ = sum w^2 (a a^T + c c^T) and the
-//      gradient g = A_m^T A (Xp,1) with the residual A (Xp,1) evaluated in DOUBLE (the cancellation
-//      y (P2.X) - P1.X needs it) and rounded to float;
-//   S. the correction solves the eigen-equations to first order in lam/M:
-//         e1 = -M~^-1 g,   lam = (|r|^2 + g.e1) / (1 + |Xp + e1|^2),   e = e1 + lam M~^-1 (Xp + e1)
-//      (exact fixed point (M - lam) X = -b; the neglected term is (lam/mu_min)^2 |X|, checked per joint).
-// The float solve is accurate to ~3e-7 |e|, so a correction of up to a few centimetres lands within 1e-5 mm;
-// larger corrections take another pass from the updated point, and whatever cannot be handled (failed pivots,
-// non-finite input, lam not small, no convergence) goes to the all-double solver.
-struct __align__(16) CamC {
-    double Pc[12];       // P0', P1', P2 (rows re-centred on the principal point)
-    double cxd, cyd;
-    float2 p10[4];       // (-P1'_k, P0'_k)
-    float4 p2;           // P2_k
-    float cx, cy, pad0, pad1;
+// ---- mixed-precision kernel (float storage) -----------------------------------------------------------------------
+// Forming B in double costs >= 304 DFMA per joint at 8 views -- more than the FP64 pipe delivers at the HBM rate -- and
+// forming it in float loses the answer (up to 1e-3 mm).  The float kernel therefore touches the full view set ONCE:
+//   start  a closed-form two-view point Xp: the ray of view A cut by the plane that view B's pixel spans along its
+//          epipolar direction (18 float operations and one reciprocal, all constants prepared on the host in double).
+//          It lies a few millimetres from the minimiser (the pixel noise of two views); a second pair of views serves
+//          the joints whose first pair has a zero-weight view, and a joint without a usable pair starts from the world
+//          origin (first pass = float solve over all views, the second pass finishes);
+//   pass   ONE loop over all V views accumulates the float normal matrix M~ = sum w^2 (a a^T + c c^T) (packed FFMA2: the
+//          two rows of a view ride in one float2) and the gradient g = A_m^T A (Xp,1) with the residual A (Xp,1)
+//          evaluated in DOUBLE (only the cancellation y (P2.X) - P1.X needs it: 11 DFMA per joint-view) and rounded to float;
+//   solve  the correction solves the eigen-equations to first order in lam/M with one float LDL^T factorisation:
+//             e1 = -M~^-1 g,   lam = (|r|^2 + g.e1) / (1 + |Xp + e1|^2),   e = e1 + lam M~^-1 (Xp + e1)
+//          (exact fixed point (M - lam) X = -b; the neglected term is (lam/mu_min)^2 |X|, checked per joint).
+// The float solve is accurate to ~3e-7 |e|, so a correction of up to a few centimetres lands within 1e-5 mm; larger
+// corrections take another pass from the updated point, and whatever cannot be handled (failed pivots, non-finite
+// input, lam not small, no convergence) goes to the all-double solver.  M~ and the float rows only precondition the
+// iteration: its fixed point is set by the double residuals.
+struct __align__(16) CamF {
+    double P[12];        // projection rows as given (double residuals)
+    float2 p2pm[3];      // (-P2_k, P2_k), k < 3
+    float2 p01[3];       // (P0_k, -P1_k), k < 3:  (x, y) * p2pm + p01 = (P0_k - x P2_k, y P2_k - P1_k) = (c_k, a_k)
 };
-static_assert(sizeof(CamC) == 176, "CamC layout");
+static_assert(sizeof(CamF) == 144, "CamF layout");
+static_assert(sizeof(mc3d_tri_start_pair) == 96 && offsetof(mc3d_tri_start_pair, C) == 36 && offsetof(mc3d_tri_start_pair, ua) == 48 &&
+                  offsetof(mc3d_tri_start_pair, alpha) == 72 && offsetof(mc3d_tri_start_pair, ka) == 80 &&
+                  offsetof(mc3d_tri_start_pair, view_a) == 88,
+              "pair_start reads mc3d_tri_start_pair as 24 consecutive four-byte fields");
 
-struct Ldl3f {
-    float i0, l10, l20, i1, l21, i2;
-};
-
-__device__ __forceinline__ bool ldl3_factor_f(float m00, float m10, float m11, float m20, float m21, float m22, Ldl3f &f) {
-    f.i0 = rcp_fast(m00);
-    f.l10 = m10 * f.i0;
-    f.l20 = m20 * f.i0;
-    const float d1 = fmaf(-f.l10, m10, m11);
-    f.i1 = rcp_fast(d1);
-    const float t21 = fmaf(-f.l20, m10, m21);
-    f.l21 = t21 * f.i1;
-    const float d2 = fmaf(-f.l21, t21, fmaf(-f.l20, m20, m22));
-    f.i2 = rcp_fast(d2);
-    return (m00 > 0.f) & (d1 > 1e-6f * m11) & (d2 > 1e-6f * m22);
-}
-
-__device__ __forceinline__ void ldl3_apply_f(const Ldl3f &f, float r0, float r1, float r2, float &z0, float &z1, float &z2) {
-    const float y1 = fmaf(-f.l10, r0, r1);
-    const float y2 = fmaf(-f.l21, y1, fmaf(-f.l20, r0, r2));
-    z2 = y2 * f.i2;
-    z1 = fmaf(y1, f.i1, -f.l21 * z2);
-    z0 = fmaf(r0, f.i0, -fmaf(f.l10, z1, f.l20 * z2));
-}
-
-// ---- the same 3x3 solve for TWO joints at once (MC3D_TRI_PACKED_SOLVE) -----------------------------------------------
-// Every float2 holds (joint 0, joint 1) of one thread.  Operation by operation the arithmetic is that of ldl3_factor_f /
-// ldl3_apply_f (one FFMA2 / FMUL2 / FADD2 = two independent IEEE operations), so results are bit-identical to the scalar
-// code; what changes is the issue-slot count of the two solve phases (scalar: ~130 float instructions per joint).
-#ifndef MC3D_TRI_PACKED_SOLVE
-#define MC3D_TRI_PACKED_SOLVE 1
+#ifndef MC3D_TRI_PIVOT
+#define MC3D_TRI_PIVOT 1.0e-3f
 #endif
+// Two joints per thread; every float2 below holds (joint 0, joint 1) unless it is a row pair (c_k, a_k).
 struct Ldl3f2 {
     float2 i0, l10, l20, i1, l21, i2;
 };
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 rcp_fast2(float2 a) { return make_float2(rcp_fast(a.x), rcp_fast(a.y)); }
+__device__ __forceinline__ float2 bcast2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 dot3_2(float2 a0, float2 a1, float2 a2, float2 b0, float2 b1, float2 b2) {
-    return __ffma2_rn(a0, b0, __ffma2_rn(a1, b1, __fmul2_rn(a2, b2)));       // fmaf(a0, b0, fmaf(a1, b1, a2 * b2))
+    return __ffma2_rn(a0, b0, __ffma2_rn(a1, b1, __fmul2_rn(a2, b2)));
 }
-
+// LDL^T of the SPD 3x3 systems of both joints (lower triangles m00 m10 m11 m20 m21 m22).  Approximate reciprocals are
+// fine: the solve only preconditions an iteration whose fixed point is set by residuals evaluated in double.
 __device__ __forceinline__ void ldl3_factor_f2(float2 m00, float2 m10, float2 m11, float2 m20, float2 m21, float2 m22,
                                                Ldl3f2 &f, bool &ok0, bool &ok1) {
     f.i0 = rcp_fast2(m00);
@@ -328,12 +301,12 @@ __device__ __forceinline__ void ldl3_factor_f2(float2 m00, float2 m10, float2 m1
     f.l21 = __fmul2_rn(t21, f.i1);
     const float2 d2 = __ffma2_rn(neg2(f.l21), t21, __ffma2_rn(neg2(f.l20), m20, m22));
     f.i2 = rcp_fast2(d2);
-    const float2 lim = make_float2(1e-6f, 1e-6f);
-    const float2 t1 = __fmul2_rn(lim, m11), t2 = __fmul2_rn(lim, m22);
+    // a pivot below 1e-3 of its diagonal entry means cond(M~) >~ 1e3: two nearly collinear rays, or ONE usable view (rank 2,
+    // the pivot is rounding noise ~1e-7) -- the all-double solver takes those joints (and counts their usable views)
+    const float2 t1 = __fmul2_rn(bcast2(MC3D_TRI_PIVOT), m11), t2 = __fmul2_rn(bcast2(MC3D_TRI_PIVOT), m22);
     ok0 = (m00.x > 0.f) & (d1.x > t1.x) & (d2.x > t2.x);
     ok1 = (m00.y > 0.f) & (d1.y > t1.y) & (d2.y > t2.y);
 }
-
 __device__ __forceinline__ void ldl3_apply_f2(const Ldl3f2 &f, float2 r0, float2 r1, float2 r2, float2 &z0, float2 &z1,
                                               float2 &z2) {
     const float2 y1 = __ffma2_rn(neg2(f.l10), r0, r1);
@@ -342,199 +315,107 @@ __device__ __forceinline__ void ldl3_apply_f2(const Ldl3f2 &f, float2 r0, float2
     z1 = __ffma2_rn(y1, f.i1, __fmul2_rn(neg2(f.l21), z2));
     z0 = __ffma2_rn(r0, f.i0, neg2(__ffma2_rn(f.l10, z1, __fmul2_rn(f.l20, z2))));
 }
-
 // (a[0][i].x + a[0][i].y, a[1][i].x + a[1][i].y): the two halves of a row-packed accumulator, per joint
 #define MC3D_HSUM2(a, i) make_float2((a)[0][i].x + (a)[0][i].y, (a)[1][i].x + (a)[1][i].y)
 
-// views of the starting-point subset: (i * V) / NE for i < NE, NE = min(V, 3)
-__host__ __device__ constexpr int est_count(int V) { return V < 3 ? V : 3; }
-__host__ __device__ constexpr bool is_est_view(int V, int v) {
-    for (int i = 0; i < est_count(V); ++i)
-        if ((i * V) / est_count(V) == v) return true;
-    return false;
-}
-__host__ __device__ constexpr bool group_has_est_view(int V, int vg, int G) {
-    for (int i = 0; i < G; ++i)
-        if (is_est_view(V, vg + i)) return true;
-    return false;
+// x, y, w of one (runtime) view of a joint's shared-memory row
+template <int V, int LAYOUT>
+__device__ __forceinline__ void load_view(const float *row, int v, float &x, float &y, float &w) {
+    if constexpr (LAYOUT == MC3D_LAYOUT_3V) {
+        x = row[v]; y = row[V + v]; w = row[2 * V + v];
+    } else {
+        x = row[3 * v]; y = row[3 * v + 1]; w = row[3 * v + 2];
+    }
 }
 
-#ifndef MC3D_TRI_ROWS_E
-#define MC3D_TRI_ROWS_E 1
-#endif
-// tuning build: the double residuals use the projection rows as given (P0, P1, P2) instead of the rows re-centred on
-// the principal point -- the same residuals in exact arithmetic (re-centring only matters for the FLOAT rows), two
-// DADD and one shared-memory load fewer per joint-view; equal to the shipped kernel up to float-rounding ties
-#ifndef MC3D_TRI_RAW_RESID
-#define MC3D_TRI_RAW_RESID 1
-#endif
-// weighted float rows of one view, packed (a_k, c_k), k < NK
-template <int NK>
-__device__ __forceinline__ void float_rows(float x, float y, float w, float cx, float cy, const float (&p2)[4],
-                                           const float2 (&p10)[4], float2 (&ac)[NK]) {
-#if MC3D_TRI_ROWS_E
-    // tuning build: w (yx P2 + p10) as the starting-point phase forms its rows -- two instructions fewer per view than
-    // (w yx) P2 + w p10, different rounding (not bit-identical to the shipped kernel; the fixed point is unchanged)
-    const float2 yx = make_float2(y - cy, cx - x);
-    const float2 ww = make_float2(w, w);
-#pragma unroll
-    for (int k = 0; k < NK; ++k) ac[k] = __fmul2_rn(ww, __ffma2_rn(yx, make_float2(p2[k], p2[k]), p10[k]));
-#else
-    const float xc = x - cx, yc = y - cy;
-    const float2 sv = make_float2(w * yc, -(w * xc));
-    const float2 ww = make_float2(w, w);
-#pragma unroll
-    for (int k = 0; k < NK; ++k) ac[k] = __ffma2_rn(sv, make_float2(p2[k], p2[k]), __fmul2_rn(ww, p10[k]));
-#endif
+// Closed-form two-view start (constants: fill_start_pairs).  X(s) = C_A + s D_A with D_A = H_A (x_A, y_A, 1) is the ray of
+// view A; view B contributes the one linear constraint along its epipolar direction (alpha, beta):
+//     [(alpha P0 + beta P1) - z P2]_B . (X(s), 1) = 0,   z = alpha x_B + beta y_B
+// whose solution is s = (z kb - ka) / (ua.q - z ub.q), q = (x_A, y_A, 1).  wmin = min(w_A, w_B).
+template <int V, int LAYOUT>
+__device__ __forceinline__ void pair_start(const mc3d_tri_start_pair *pc, int va, int vb, const float *row, float &X0,
+                                           float &X1, float &X2, float &wmin) {
+    const float *pf = reinterpret_cast<const float *>(pc);              // 24 four-byte fields, 16-byte aligned
+    const float4 h0 = *reinterpret_cast<const float4 *>(pf);            // H00 H01 H02 H10
+    const float4 h1 = *reinterpret_cast<const float4 *>(pf + 4);        // H11 H12 H20 H21
+    const float4 h2 = *reinterpret_cast<const float4 *>(pf + 8);        // H22 C0 C1 C2
+    const float4 u0 = *reinterpret_cast<const float4 *>(pf + 12);       // ua0 ua1 ua2 ub0
+    const float4 u1 = *reinterpret_cast<const float4 *>(pf + 16);       // ub1 ub2 alpha beta
+    const float2 kk = *reinterpret_cast<const float2 *>(pf + 20);       // ka kb
+    float xa, ya, wa, xb, yb, wb;
+    load_view<V, LAYOUT>(row, va, xa, ya, wa);
+    load_view<V, LAYOUT>(row, vb, xb, yb, wb);
+    const float z = fmaf(u1.z, xb, u1.w * yb);
+    const float ta = fmaf(u0.x, xa, fmaf(u0.y, ya, u0.z));
+    const float tb = fmaf(u0.w, xa, fmaf(u1.x, ya, u1.y));
+    const float s = fmaf(z, kk.y, -kk.x) * rcp_fast(fmaf(-z, tb, ta));
+    X0 = fmaf(s, fmaf(h0.x, xa, fmaf(h0.y, ya, h0.z)), h2.y);
+    X1 = fmaf(s, fmaf(h0.w, xa, fmaf(h1.x, ya, h1.y)), h2.z);
+    X2 = fmaf(s, fmaf(h1.z, xa, fmaf(h1.w, ya, h2.x)), h2.w);
+    wmin = fminf(wa, wb);
 }
 
 #ifndef MC3D_TRI_UNR_LIMIT
-#define MC3D_TRI_UNR_LIMIT 4            // full unrolling of 8+ views hoists loads into spills
+#define MC3D_TRI_UNR_LIMIT 8            // view loop fully unrolled up to 8 views (no spills at 128 registers; +5 % at V = 8)
 #endif
+// The float solve leaves an error of ~cond(M~) 1e-7 |e|, so a correction is final when cond |e| is small against the range:
+//     |e|^2 (tr(M~) / smallest pivot)^2 <= MC3D_TRI_ACCEPT (|X|^2 + rig scale^2)
+// tr / pivot is ~6 for eight views on a ring (|e| <~ 3 % of the range, the limit of the first-order treatment of lam) and
+// up to ~3e3 for the worst pair of views the pivot test lets through (|e| <~ 1e-4 of the range); either way the error stays
+// below ~2e-8 of the range.  Larger corrections take another pass from the updated point.
 #ifndef MC3D_TRI_ACCEPT
-#define MC3D_TRI_ACCEPT 1.0e-3f      // accept a correction with |e|^2 <= this * (|X|^2 + rig scale^2): |e| <~ 3 % of the range
+#define MC3D_TRI_ACCEPT 4.0e-2f
 #endif
 
-// tuning build (with MC3D_TRI_PACKED_SOLVE, two joints per thread): the accepted result leaves the solver as FLOATS.  In the
-// first pass the starting point is float-valued, so the result float(Xp + e) is one float addition; the conversions
-// float(Xp), double(e), float(X) and the double additions of the shipped tail (9 F2F + 3 DADD per joint) are then only
-// executed by joints that need another pass.  Same value as the shipped kernel up to double-rounding ties.
-#ifndef MC3D_TRI_FLOAT_TAIL
-#define MC3D_TRI_FLOAT_TAIL 1
-#endif
-#if MC3D_TRI_FLOAT_TAIL && !MC3D_TRI_PACKED_SOLVE
-#error "MC3D_TRI_FLOAT_TAIL needs MC3D_TRI_PACKED_SOLVE"
-#endif
-#if MC3D_TRI_FLOAT_TAIL
-#define MC3D_XO_PARAM , float (&Xo)[NJ][3]
-#define MC3D_XO_ARG , Xo
-#else
-#define MC3D_XO_PARAM
-#define MC3D_XO_ARG
-#endif
-
-template <int V, int LAYOUT, int NJ>
-__device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float rig2, const float *const (&rows)[NJ],
-                                             const bool (&act)[NJ], double (&X)[NJ][3], int (&state)[NJ] MC3D_XO_PARAM) {
-#if MC3D_TRI_FLOAT_TAIL
-    static_assert(NJ == 2, "MC3D_TRI_FLOAT_TAIL is written for two joints per thread");
-    float Xf[NJ][3];                                                // float(Xd): exact in the first pass
-#endif
+// All NJ = 2 NP joints of a thread (the solve runs on NP packed pairs).  state: 0 = Xo holds the result, 1 = the all-double solver has to take the joint.
+template <int V, int LAYOUT, int NP>
+__device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const mc3d_tri_start_pair *__restrict__ pairs,
+                                            const int4 sv, int n_pairs, float rig2, const float *const (&rows)[2 * NP],
+                                            float (&Xo)[2 * NP][3], int (&state)[2 * NP]) {
+    constexpr int NJ = 2 * NP;
     constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
-    double Xd[NJ][3];
-    // ---- E: starting point from the subset ---------------------------------------------------------------
+    double Xd[NJ][3];                                           // float-valued in the first pass
+    // ---- start ---------------------------------------------------------------------------------------------------
     {
-        float2 aM[NJ][6], ab[NJ][3];
+        const float lim = 1.0e4f * (rig2 + 1.f);                // a start farther out than 100 rig radii is not one
+        bool have[NJ];
+        float Xf[NJ][3];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
+        for (int j = 0; j < NJ; ++j) { have[j] = false; Xf[j][0] = Xf[j][1] = Xf[j][2] = 0.f; }
+        if (n_pairs > 0) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) aM[j][i] = make_float2(0.f, 0.f);
+            for (int j = 0; j < NJ; ++j) {
+                float s0, s1, s2, wm;
+                pair_start<V, LAYOUT>(&pairs[0], sv.x, sv.y, rows[j], s0, s1, s2, wm);
+                if (wm > 0.f && fmaf(s0, s0, fmaf(s1, s1, s2 * s2)) <= lim) { Xf[j][0] = s0; Xf[j][1] = s1; Xf[j][2] = s2; have[j] = true; }
+            }
+            // warp-uniform: clean input never evaluates the second pair
+            bool all_have = true;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) ab[j][i] = make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int vg = 0; vg < V; vg += G) {
-            if (!group_has_est_view(V, vg, G)) continue;
-            float gx[NJ][G], gy[NJ][G], gw[NJ][G];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) load_group<V, LAYOUT, G>(rows[j], vg, gx[j], gy[j], gw[j]);
-#pragma unroll
-            for (int i = 0; i < G; ++i) {
-                const int v = vg + i;
-                if (!is_est_view(V, v)) continue;
-                const CamC &c = cam[v];
-                const float4 p2v = c.p2;
-                const float p2[4] = {p2v.x, p2v.y, p2v.z, p2v.w};
-                float2 p10[4];
-                {
-                    const float4 a = *reinterpret_cast<const float4 *>(&c.p10[0]);
-                    const float4 b = *reinterpret_cast<const float4 *>(&c.p10[2]);
-                    p10[0] = make_float2(a.x, a.y); p10[1] = make_float2(a.z, a.w);
-                    p10[2] = make_float2(b.x, b.y); p10[3] = make_float2(b.z, b.w);
-                }
-                const float2 cxy = *reinterpret_cast<const float2 *>(&c.cx);
+            for (int j = 0; j < NJ; ++j) all_have = all_have && have[j];
+            if (n_pairs > 1 && __any_sync(0xffffffffu, !all_have)) {
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
-                    // rows w (y P2 - P1'), w (P0' - x P2) of this view: a zero-weight view drops out of the start and a
-                    // low-confidence one barely moves it, so unusable detections among the starting views do not cost
-                    // the warp a second pass (measured at 1 % unusable views: 2.8e10 joints/s against 1.9e10 with
-                    // unweighted rows, which are 3 % faster on clean input)
-                    float2 ac[4];
-                    const float2 yx = make_float2(gy[j][i] - cxy.y, cxy.x - gx[j][i]);
-                    const float2 ww = make_float2(gw[j][i], gw[j][i]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) ac[k] = __fmul2_rn(ww, __ffma2_rn(yx, make_float2(p2[k], p2[k]), p10[k]));
-                    aM[j][0] = __ffma2_rn(ac[0], ac[0], aM[j][0]);
-                    aM[j][1] = __ffma2_rn(ac[1], ac[0], aM[j][1]);
-                    aM[j][2] = __ffma2_rn(ac[1], ac[1], aM[j][2]);
-                    aM[j][3] = __ffma2_rn(ac[2], ac[0], aM[j][3]);
-                    aM[j][4] = __ffma2_rn(ac[2], ac[1], aM[j][4]);
-                    aM[j][5] = __ffma2_rn(ac[2], ac[2], aM[j][5]);
-                    ab[j][0] = __ffma2_rn(ac[3], ac[0], ab[j][0]);
-                    ab[j][1] = __ffma2_rn(ac[3], ac[1], ab[j][1]);
-                    ab[j][2] = __ffma2_rn(ac[3], ac[2], ab[j][2]);
+                    float s0, s1, s2, wm;
+                    pair_start<V, LAYOUT>(&pairs[1], sv.z, sv.w, rows[j], s0, s1, s2, wm);
+                    if (!have[j] && wm > 0.f && fmaf(s0, s0, fmaf(s1, s1, s2 * s2)) <= lim) { Xf[j][0] = s0; Xf[j][1] = s1; Xf[j][2] = s2; }
                 }
             }
         }
-#if MC3D_TRI_PACKED_SOLVE
-        if constexpr (NJ == 2) {
-            Ldl3f2 f;
-            bool ok[2];
-            ldl3_factor_f2(MC3D_HSUM2(aM, 0), MC3D_HSUM2(aM, 1), MC3D_HSUM2(aM, 2), MC3D_HSUM2(aM, 3), MC3D_HSUM2(aM, 4),
-                           MC3D_HSUM2(aM, 5), f, ok[0], ok[1]);
-            float2 z0, z1, z2;
-            ldl3_apply_f2(f, neg2(MC3D_HSUM2(ab, 0)), neg2(MC3D_HSUM2(ab, 1)), neg2(MC3D_HSUM2(ab, 2)), z0, z1, z2);
-            const float2 nz2 = dot3_2(z0, z1, z2, z0, z1, z2);
-            const float2 tr2 = __fadd2_rn(__fadd2_rn(MC3D_HSUM2(aM, 0), MC3D_HSUM2(aM, 2)), MC3D_HSUM2(aM, 5));
-            const float nz[2] = {nz2.x, nz2.y}, tr[2] = {tr2.x, tr2.y};
-            const float zs[2][3] = {{z0.x, z1.x, z2.x}, {z0.y, z1.y, z2.y}};
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                X[j][0] = X[j][1] = X[j][2] = NAN;
-                Xd[j][0] = Xd[j][1] = Xd[j][2] = 0.0;
-                state[j] = 0;
-                if (!act[j]) continue;
-                if (!(tr[j] <= 3.0e38f)) { state[j] = 1; continue; }
-                state[j] = 2;
-                if (ok[j] && nz[j] <= 3.0e38f) { Xd[j][0] = (double)zs[j][0]; Xd[j][1] = (double)zs[j][1]; Xd[j][2] = (double)zs[j][2]; }
-            }
-#if MC3D_TRI_FLOAT_TAIL
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const bool started = act[j] && tr[j] <= 3.0e38f && ok[j] && nz[j] <= 3.0e38f;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { Xf[j][k] = started ? zs[j][k] : 0.f; Xo[j][k] = NAN; }
-            }
-#endif
-        } else
-#endif
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            X[j][0] = X[j][1] = X[j][2] = NAN;
-            Xd[j][0] = Xd[j][1] = Xd[j][2] = 0.0;
-            state[j] = 0;
-            if (!act[j]) continue;
-            Ldl3f f;
-            const bool ok = ldl3_factor_f(aM[j][0].x + aM[j][0].y, aM[j][1].x + aM[j][1].y, aM[j][2].x + aM[j][2].y,
-                                          aM[j][3].x + aM[j][3].y, aM[j][4].x + aM[j][4].y, aM[j][5].x + aM[j][5].y, f);
-            float z0, z1, z2;
-            ldl3_apply_f(f, -(ab[j][0].x + ab[j][0].y), -(ab[j][1].x + ab[j][1].y), -(ab[j][2].x + ab[j][2].y), z0, z1, z2);
-            const float nz = fmaf(z0, z0, fmaf(z1, z1, z2 * z2));
-            const float tr = (aM[j][0].x + aM[j][0].y) + (aM[j][2].x + aM[j][2].y) + (aM[j][5].x + aM[j][5].y);
-            if (!(tr <= 3.0e38f)) { state[j] = 1; continue; }         // non-finite input: the all-double path classifies it
             state[j] = 2;
-            // fewer than two usable views in the subset (zero weights): start from the world origin -- the first pass
-            // is then a float solve over all views, the second one finishes
-            if (ok && nz <= 3.0e38f) { Xd[j][0] = (double)z0; Xd[j][1] = (double)z1; Xd[j][2] = (double)z2; }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { Xd[j][k] = (double)Xf[j][k]; Xo[j][k] = NAN; }
         }
     }
-    // ---- M + S: merged pass from Xp, repeated only when the correction was large ---------------------------------
+    // ---- pass + solve from Xp, repeated only when the correction was large ----------------------------------------
     constexpr int UNR = (V > MC3D_TRI_UNR_LIMIT) ? 1 : (V / G);
 #pragma unroll 1
     for (int it = 0; it < 6; ++it) {
         bool any = false;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) any = any || (state[j] == 2);
+        for (int j = 0; j < NJ; ++j) any = any || state[j] == 2;
         if (!any) break;
         float2 aM[NJ][6], ag[NJ][3], arr[NJ];
 #pragma unroll
@@ -552,134 +433,98 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
             for (int j = 0; j < NJ; ++j) load_group<V, LAYOUT, G>(rows[j], vg, gx[j], gy[j], gw[j]);
 #pragma unroll
             for (int i = 0; i < G; ++i) {
-                const CamC &c = cam[vg + i];
-                double Pc[12];
+                const CamF &c = cam[vg + i];
+                double P[12];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
-                    const double2 t = *reinterpret_cast<const double2 *>(&c.Pc[2 * k]);
-                    Pc[2 * k] = t.x; Pc[2 * k + 1] = t.y;
+                    const double2 t = *reinterpret_cast<const double2 *>(&c.P[2 * k]);
+                    P[2 * k] = t.x; P[2 * k + 1] = t.y;
                 }
-#if !MC3D_TRI_RAW_RESID
-                const double2 cxyd = *reinterpret_cast<const double2 *>(&c.cxd);
-#endif
-                const float4 p2v = c.p2;
-                const float p2[4] = {p2v.x, p2v.y, p2v.z, p2v.w};
-                float2 p10[4];
+                float2 p2pm[3], p01[3];
                 {
-                    const float4 a = *reinterpret_cast<const float4 *>(&c.p10[0]);
-                    const float2 b = c.p10[2];
-                    p10[0] = make_float2(a.x, a.y); p10[1] = make_float2(a.z, a.w); p10[2] = b;
-                    p10[3] = make_float2(0.f, 0.f);
+                    const float4 q0 = *reinterpret_cast<const float4 *>(&c.p2pm[0]);
+                    const float4 q1 = *reinterpret_cast<const float4 *>(&c.p2pm[2]);
+                    const float4 q2 = *reinterpret_cast<const float4 *>(&c.p01[1]);
+                    p2pm[0] = make_float2(q0.x, q0.y); p2pm[1] = make_float2(q0.z, q0.w); p2pm[2] = make_float2(q1.x, q1.y);
+                    p01[0] = make_float2(q1.z, q1.w); p01[1] = make_float2(q2.x, q2.y); p01[2] = make_float2(q2.z, q2.w);
                 }
-                const float2 cxy = *reinterpret_cast<const float2 *>(&c.cx);
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const float x = gx[j][i], y = gy[j][i], w = gw[j][i];
-                    float2 ac[3];
-                    float_rows<3>(x, y, w, cxy.x, cxy.y, p2, p10, ac);
+                    const float2 xy = make_float2(x, y), ww = make_float2(w, w);
+                    float2 ac[3];                        // weighted rows (c_k, a_k) = w (P0_k - x P2_k, y P2_k - P1_k)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) ac[k] = __fmul2_rn(ww, __ffma2_rn(xy, p2pm[k], p01[k]));
                     aM[j][0] = __ffma2_rn(ac[0], ac[0], aM[j][0]);
                     aM[j][1] = __ffma2_rn(ac[1], ac[0], aM[j][1]);
                     aM[j][2] = __ffma2_rn(ac[1], ac[1], aM[j][2]);
                     aM[j][3] = __ffma2_rn(ac[2], ac[0], aM[j][3]);
                     aM[j][4] = __ffma2_rn(ac[2], ac[1], aM[j][4]);
                     aM[j][5] = __ffma2_rn(ac[2], ac[2], aM[j][5]);
-                    const double d0 = fma(Pc[0], Xd[j][0], fma(Pc[1], Xd[j][1], fma(Pc[2], Xd[j][2], Pc[3])));
-                    const double d1 = fma(Pc[4], Xd[j][0], fma(Pc[5], Xd[j][1], fma(Pc[6], Xd[j][2], Pc[7])));
-                    const double d2 = fma(Pc[8], Xd[j][0], fma(Pc[9], Xd[j][1], fma(Pc[10], Xd[j][2], Pc[11])));
-#if MC3D_TRI_RAW_RESID
-                    const double xcd = (double)x, ycd = (double)y;                      // Pc holds P0, P1, P2 themselves
-#else
-                    const double xcd = (double)x - cxyd.x, ycd = (double)y - cxyd.y;
-#endif
-                    const float r1 = (float)fma(ycd, d2, -d1);   // y (P2.X) - P1.X : the cancellation is in double
-                    const float r2 = (float)fma(-xcd, d2, d0);   // P0.X - x (P2.X)
-                    const float2 t = __fmul2_rn(make_float2(w, w), make_float2(r1, r2));
+                    const double d0 = fma(P[0], Xd[j][0], fma(P[1], Xd[j][1], fma(P[2], Xd[j][2], P[3])));
+                    const double d1 = fma(P[4], Xd[j][0], fma(P[5], Xd[j][1], fma(P[6], Xd[j][2], P[7])));
+                    const double d2 = fma(P[8], Xd[j][0], fma(P[9], Xd[j][1], fma(P[10], Xd[j][2], P[11])));
+                    const float rc = (float)fma(-(double)x, d2, d0);    // P0.X - x (P2.X)
+                    const float ra = (float)fma((double)y, d2, -d1);    // y (P2.X) - P1.X : the cancellation is in double
+                    const float2 t = __fmul2_rn(ww, make_float2(rc, ra));
 #pragma unroll
                     for (int k = 0; k < 3; ++k) ag[j][k] = __ffma2_rn(t, ac[k], ag[j][k]);
                     arr[j] = __ffma2_rn(t, t, arr[j]);
                 }
             }
         }
-#if MC3D_TRI_PACKED_SOLVE
-        if constexpr (NJ == 2) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
             Ldl3f2 f;
             bool ok[2];
-            ldl3_factor_f2(MC3D_HSUM2(aM, 0), MC3D_HSUM2(aM, 1), MC3D_HSUM2(aM, 2), MC3D_HSUM2(aM, 3), MC3D_HSUM2(aM, 4),
-                           MC3D_HSUM2(aM, 5), f, ok[0], ok[1]);
-            const float2 g0 = MC3D_HSUM2(ag, 0), g1 = MC3D_HSUM2(ag, 1), g2 = MC3D_HSUM2(ag, 2);
+            const float2 m00 = MC3D_HSUM2(aM + 2 * q, 0), m11 = MC3D_HSUM2(aM + 2 * q, 2), m22 = MC3D_HSUM2(aM + 2 * q, 5);
+            const float2 tr2 = __fadd2_rn(__fadd2_rn(m00, m11), m22);
+            ldl3_factor_f2(m00, MC3D_HSUM2(aM + 2 * q, 1), m11, MC3D_HSUM2(aM + 2 * q, 3), MC3D_HSUM2(aM + 2 * q, 4), m22, f, ok[0], ok[1]);
+            const float2 g0 = MC3D_HSUM2(ag + 2 * q, 0), g1 = MC3D_HSUM2(ag + 2 * q, 1), g2 = MC3D_HSUM2(ag + 2 * q, 2);
             float2 e0, e1, e2;
             ldl3_apply_f2(f, neg2(g0), neg2(g1), neg2(g2), e0, e1, e2);
-            const float2 rr = __fadd2_rn(make_float2(arr[0].x + arr[0].y, arr[1].x + arr[1].y), dot3_2(g0, g1, g2, e0, e1, e2));
-#if MC3D_TRI_FLOAT_TAIL
+            const float2 rs = make_float2(arr[2 * q].x + arr[2 * q].y, arr[2 * q + 1].x + arr[2 * q + 1].y);           // |A (Xp,1)|^2
+            const float2 rr = __fadd2_rn(rs, dot3_2(g0, g1, g2, e0, e1, e2));
+            float Xf[2][3];                                       // float(Xd): exact in the first pass
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) Xf[j][k] = (float)Xd[2 * q + j][k];
             const float2 x0 = __fadd2_rn(make_float2(Xf[0][0], Xf[1][0]), e0);
             const float2 x1 = __fadd2_rn(make_float2(Xf[0][1], Xf[1][1]), e1);
             const float2 x2 = __fadd2_rn(make_float2(Xf[0][2], Xf[1][2]), e2);
-#else
-            const float2 x0 = __fadd2_rn(make_float2((float)Xd[0][0], (float)Xd[1][0]), e0);
-            const float2 x1 = __fadd2_rn(make_float2((float)Xd[0][1], (float)Xd[1][1]), e1);
-            const float2 x2 = __fadd2_rn(make_float2((float)Xd[0][2], (float)Xd[1][2]), e2);
-#endif
             const float2 nx2 = dot3_2(x0, x1, x2, x0, x1, x2);
-            const float2 lam2 = __fmul2_rn(rr, rcp_fast2(__fadd2_rn(make_float2(1.f, 1.f), nx2)));
+            const float2 lam2 = __fmul2_rn(rr, rcp_fast2(__fadd2_rn(bcast2(1.f), nx2)));
             float2 h0, h1, h2;
             ldl3_apply_f2(f, __fmul2_rn(lam2, x0), __fmul2_rn(lam2, x1), __fmul2_rn(lam2, x2), h0, h1, h2);
             e0 = __fadd2_rn(e0, h0); e1 = __fadd2_rn(e1, h1); e2 = __fadd2_rn(e2, h2);
             const float2 ne2 = dot3_2(e0, e1, e2, e0, e1, e2);
-            const float2 lim2 = __fmul2_rn(make_float2(MC3D_TRI_ACCEPT, MC3D_TRI_ACCEPT), __fadd2_rn(nx2, make_float2(rig2, rig2)));
-            const float ne[2] = {ne2.x, ne2.y}, lam[2] = {lam2.x, lam2.y}, lim[2] = {lim2.x, lim2.y};
+            const float2 lim2 = __fmul2_rn(bcast2(MC3D_TRI_ACCEPT), __fadd2_rn(nx2, bcast2(rig2)));
+            // first-order treatment of lam needs lam << smallest pivot of M~
             const float imax[2] = {fmaxf(f.i0.x, fmaxf(f.i1.x, f.i2.x)), fmaxf(f.i0.y, fmaxf(f.i1.y, f.i2.y))};
+            const float2 kap = __fmul2_rn(tr2, make_float2(imax[0], imax[1]));          // ~cond(M~)
+            const float2 nk2 = __fmul2_rn(ne2, __fmul2_rn(kap, kap));
+            // g is a float sum of terms ~|r| |a| that cancel: its rounding error ~1e-7 sqrt(|r|^2 tr) moves the solution by that
+            // times 1 / (smallest pivot), whatever the size of e -- no further pass can repair it, the double solver has to
+            const float2 gn2 = __fmul2_rn(__fmul2_rn(rs, kap), make_float2(imax[0], imax[1]));   // |r|^2 tr / pivot^2
+            const float ne[2] = {ne2.x, ne2.y}, nk[2] = {nk2.x, nk2.y}, gn[2] = {gn2.x, gn2.y}, lam[2] = {lam2.x, lam2.y}, lim[2] = {lim2.x, lim2.y};
             const float es[2][3] = {{e0.x, e1.x, e2.x}, {e0.y, e1.y, e2.y}};
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = 2 * q + jj;
                 if (state[j] != 2) continue;
-                if (!ok[j] || !(ne[j] <= 3.0e38f) || !(fabsf(lam[j]) * imax[j] <= 3.0e-5f)) { state[j] = 1; continue; }
-#if MC3D_TRI_FLOAT_TAIL
-                if (ne[j] <= lim[j]) {
+                if (!ok[jj] || !(ne[jj] <= 3.0e38f) || !(fabsf(lam[jj]) * imax[jj] <= 3.0e-5f) || !(gn[jj] <= lim[jj])) { state[j] = 1; continue; }
+                if (nk[jj] <= lim[jj]) {
                     if (it == 0) {                                   // Xd is float-valued: float(Xd + e) is one float addition
-                        Xo[j][0] = Xf[j][0] + es[j][0]; Xo[j][1] = Xf[j][1] + es[j][1]; Xo[j][2] = Xf[j][2] + es[j][2];
+                        Xo[j][0] = Xf[jj][0] + es[jj][0]; Xo[j][1] = Xf[jj][1] + es[jj][1]; Xo[j][2] = Xf[jj][2] + es[jj][2];
                     } else {
-                        Xo[j][0] = (float)(Xd[j][0] + (double)es[j][0]); Xo[j][1] = (float)(Xd[j][1] + (double)es[j][1]);
-                        Xo[j][2] = (float)(Xd[j][2] + (double)es[j][2]);
+                        Xo[j][0] = (float)(Xd[j][0] + (double)es[jj][0]); Xo[j][1] = (float)(Xd[j][1] + (double)es[jj][1]);
+                        Xo[j][2] = (float)(Xd[j][2] + (double)es[jj][2]);
                     }
                     state[j] = 0;
                 } else {                                             // another pass from the updated point
-                    Xd[j][0] += (double)es[j][0]; Xd[j][1] += (double)es[j][1]; Xd[j][2] += (double)es[j][2];
-                    Xf[j][0] = (float)Xd[j][0]; Xf[j][1] = (float)Xd[j][1]; Xf[j][2] = (float)Xd[j][2];
+                    Xd[j][0] += (double)es[jj][0]; Xd[j][1] += (double)es[jj][1]; Xd[j][2] += (double)es[jj][2];
                 }
-#else
-                Xd[j][0] += (double)es[j][0]; Xd[j][1] += (double)es[j][1]; Xd[j][2] += (double)es[j][2];
-                if (ne[j] <= lim[j]) {
-                    X[j][0] = Xd[j][0]; X[j][1] = Xd[j][1]; X[j][2] = Xd[j][2];
-                    state[j] = 0;
-                }
-#endif
-            }
-        } else
-#endif
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            if (state[j] != 2) continue;
-            Ldl3f f;
-            const bool ok = ldl3_factor_f(aM[j][0].x + aM[j][0].y, aM[j][1].x + aM[j][1].y, aM[j][2].x + aM[j][2].y,
-                                          aM[j][3].x + aM[j][3].y, aM[j][4].x + aM[j][4].y, aM[j][5].x + aM[j][5].y, f);
-            const float g0 = ag[j][0].x + ag[j][0].y, g1 = ag[j][1].x + ag[j][1].y, g2 = ag[j][2].x + ag[j][2].y;
-            float e0, e1, e2;
-            ldl3_apply_f(f, -g0, -g1, -g2, e0, e1, e2);
-            const float rr = (arr[j].x + arr[j].y) + fmaf(g0, e0, fmaf(g1, e1, g2 * e2));
-            const float x0 = (float)Xd[j][0] + e0, x1 = (float)Xd[j][1] + e1, x2 = (float)Xd[j][2] + e2;
-            const float nx = fmaf(x0, x0, fmaf(x1, x1, x2 * x2));
-            const float lam = rr * rcp_fast(1.f + nx);
-            float h0, h1, h2;
-            ldl3_apply_f(f, lam * x0, lam * x1, lam * x2, h0, h1, h2);
-            e0 += h0; e1 += h1; e2 += h2;
-            const float ne = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
-            // first-order treatment of lam needs lam << smallest pivot of M~
-            const float imax = fmaxf(f.i0, fmaxf(f.i1, f.i2));
-            if (!ok || !(ne <= 3.0e38f) || !(fabsf(lam) * imax <= 3.0e-5f)) { state[j] = 1; continue; }
-            Xd[j][0] += (double)e0; Xd[j][1] += (double)e1; Xd[j][2] += (double)e2;
-            if (ne <= MC3D_TRI_ACCEPT * (nx + rig2)) {
-                X[j][0] = Xd[j][0]; X[j][1] = Xd[j][1]; X[j][2] = Xd[j][2];
-                state[j] = 0;
             }
         }
     }
@@ -688,13 +533,157 @@ __device__ __forceinline__ void solve_merged(const CamC *__restrict__ cam, float
         if (state[j] == 2) state[j] = 1;                         // did not converge in 6 passes
 }
 
-// Shared-memory rows.  One thread reads one joint's row, so a row of r 16-byte units with r a multiple of 8 puts every
-// lane of a warp on the same banks (double storage, V = 16: r = 24 -> 32-way conflicts; `short_scoreboard` 5 warps per
-// issue, 39 % of the roofline).  Such rows are copied one by one (each thread issues the bulk copy of its own row;
-// all of them complete on the stage's mbarrier) into slots of r + 1 units, which is conflict-free: +45 % for that
-// kernel.  For r = 12 (double, V = 8: 8-way) and r = 6 (float, V = 8: 2-way) the grouped variant (G = 8 / gcd(r, 8)
-// rows per copy, one padding unit per group) removes the conflicts too, but the 64-128 small TMA copies per tile cost
-// as much as they save (double V = 8: +-0 %, float V = 8: -12 %), so those keep the single contiguous bulk copy.
+#ifndef MC3D_TRI_MBLOCKS
+#define MC3D_TRI_MBLOCKS 4
+#endif
+constexpr int TRI_MWARPS = 4;                   // warps per CTA of the mixed kernel
+constexpr int TRI_MTHREADS = 32 * TRI_MWARPS;
+#ifndef MC3D_TRI_NP
+#define MC3D_TRI_NP 1
+#endif
+constexpr int TRI_NP = MC3D_TRI_NP;             // packed joint pairs per thread
+constexpr int TRI_NJ = 2 * TRI_NP;              // joints per thread: lane l owns joints l, l + 32, ... of its warp's tile
+constexpr int TRI_WTILE = 32 * TRI_NJ;          // joints per warp tile
+
+// Resident CTAs per SM the mixed kernel is compiled for.  Measured at V = 8: 4 CTAs x 128 registers and 3 CTAs x 162
+// registers run at the same speed (the extra registers buy the compiler what the fourth CTA's warps would hide), so the
+// instantiations that spill at 128 registers -- the (N, 3, V) layout, whose x / y pairs need moves, and V = 4 -- get 3.
+__host__ __device__ constexpr int tri_mixed_blocks(int V, int layout) {
+    return (V * TRI_NP >= 16) ? 2 : ((layout == MC3D_LAYOUT_3V && V >= 4) || V == 4) ? MC3D_TRI_MBLOCKS - 1 : MC3D_TRI_MBLOCKS;
+}
+
+__device__ __noinline__ void mixed_cold_fix(const TriParams &prm, int nv, const float *row, bool l3v, float *o) {
+    double f0, f1, f2;
+    solve_double_from_row(prm, row, nv, l3v, f0, f1, f2);
+    o[0] = (float)f0; o[1] = (float)f1; o[2] = (float)f2;
+}
+
+// Mixed-precision kernel (float storage, weighted mode, V in {2,3,4,8,16}, no undistortion).  Every WARP is its own
+// pipeline: 64-joint tiles of the keypoint array stream through the warp's private shared-memory ring, filled by 1-D TMA
+// bulk copies that lane 0 issues (cp.async.bulk + mbarrier complete_tx), and the 64 results leave through the warp's
+// private output tile and a TMA bulk store.  There is no block-wide barrier after the set-up (the tile loop of the
+// block-cooperative version spent 7 % of its issue slots' time in one, and a warp that needs a second pass -- an
+// unusable view -- now delays nobody else).  Lane l solves joints l, l + 32, ... of the tile together (packed float2
+// arithmetic, the camera constants of a view fetched once for all of them); the ragged tail (less than a tile) is one
+// more tile of the next warp in line, filled with plain loads.
+template <int V, int LAYOUT>
+__global__ void __launch_bounds__(TRI_MTHREADS, tri_mixed_blocks(V, LAYOUT))
+triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out, long long n,
+                         const __grid_constant__ TriParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int row_elems = 3 * V;
+    constexpr uint32_t stage_bytes = (uint32_t)(TRI_WTILE * row_elems * sizeof(float));
+    constexpr uint32_t otile_bytes = (uint32_t)(TRI_WTILE * 3 * sizeof(float));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // layout: [warp][2] input stages | [warp][2] output tiles | [warp][2] mbarriers | cameras | start pairs
+    unsigned char *ring = smem_raw + (size_t)warp * 2 * stage_bytes;
+    float *otile = reinterpret_cast<float *>(smem_raw + (size_t)TRI_MWARPS * 2 * stage_bytes + (size_t)warp * 2 * otile_bytes);
+    unsigned char *fixed = smem_raw + (size_t)TRI_MWARPS * 2 * (stage_bytes + otile_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(fixed) + warp * 2;
+    CamF *cam = reinterpret_cast<CamF *>(fixed + TRI_MWARPS * 2 * sizeof(uint64_t));
+    mc3d_tri_start_pair *pairs = reinterpret_cast<mc3d_tri_start_pair *>(cam + V);
+    if (lane == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    if (tid < V) {
+        CamF c;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) c.P[k] = prm.P[tid][k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            c.p2pm[k] = make_float2(-(float)prm.P[tid][8 + k], (float)prm.P[tid][8 + k]);
+            c.p01[k] = make_float2((float)prm.P[tid][k], -(float)prm.P[tid][4 + k]);
+        }
+        cam[tid] = c;
+    } else if (tid < V + 2) {
+        pairs[tid - V] = prm.start[tid - V];
+    }
+    __syncthreads();                                   // the only block-wide barrier
+
+    const unsigned n_tiles = (unsigned)(n / TRI_WTILE);           // full tiles (the host keeps n / 64 below 2^31)
+    const int tail = (int)(n - (long long)n_tiles * TRI_WTILE);
+    const unsigned gw = blockIdx.x * TRI_MWARPS + warp, gstride = gridDim.x * TRI_MWARPS;
+    const unsigned my_tiles = (gw < n_tiles) ? (n_tiles - gw + gstride - 1) / gstride : 0;
+    // shared-window addresses and running global pointers (lane 0 is the only one that uses them)
+    const uint32_t ring_sa = smem_u32(ring), full_sa = smem_u32(full), ot_sa = smem_u32(otile);
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(kpts) + (size_t)gw * stage_bytes;    // tile k + 1
+    unsigned char *dst = reinterpret_cast<unsigned char *>(out) + (size_t)gw * otile_bytes;                 // tile k
+    const uint32_t src_step = gstride * stage_bytes, dst_step = gstride * otile_bytes;                      // < 2^32
+    if (lane == 0 && my_tiles > 0) {
+        mbar_arrive_expect_tx_sa(full_sa, stage_bytes);
+        bulk_g2s_sa(ring_sa, src, stage_bytes, full_sa);
+    }
+    src += src_step;
+    const int n_pairs = prm.n_start;
+    // views of the starting pairs straight from the parameter bank (uniform): no shared-memory load in front of the row loads
+    const int4 sv = make_int4(prm.start[0].view_a, prm.start[0].view_b, prm.start[1].view_a, prm.start[1].view_b);
+    for (unsigned k = 0; k < my_tiles; ++k) {
+        const uint32_t b = k & 1u;
+        // refills the stage of iteration k - 1 (every lane left it before that iteration's last __syncwarp)
+        if (lane == 0 && k + 1 < my_tiles) {
+            mbar_arrive_expect_tx_sa(full_sa + 8u * (b ^ 1u), stage_bytes);
+            bulk_g2s_sa(ring_sa + (b ^ 1u) * stage_bytes, src, stage_bytes, full_sa + 8u * (b ^ 1u));
+        }
+        src += src_step;
+        const float *stage = reinterpret_cast<const float *>(ring + b * stage_bytes);
+        mbar_wait_sa(full_sa + 8u * b, (k >> 1) & 1u);
+        const float *rows[TRI_NJ];
+#pragma unroll
+        for (int j = 0; j < TRI_NJ; ++j) rows[j] = stage + (lane + 32 * j) * row_elems;
+        float Xo[TRI_NJ][3];
+        int state[TRI_NJ];
+        solve_mixed<V, LAYOUT, TRI_NP>(cam, pairs, sv, n_pairs, prm.rig2, rows, Xo, state);
+        float *ot = otile + b * (TRI_WTILE * 3);
+        if (lane == 0) bulk_wait_read<1>();           // the store of iteration k - 2 has left this output buffer
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < TRI_NJ; ++j) {
+            float *o = ot + (lane + 32 * j) * 3;
+            o[0] = Xo[j][0]; o[1] = Xo[j][1]; o[2] = Xo[j][2];
+            if (state[j] == 1) mixed_cold_fix(prm, V, rows[j], LAYOUT == MC3D_LAYOUT_3V, o);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();                                 // stage b consumed by every lane; output tile complete
+        if (lane == 0) {
+            bulk_s2g_sa(dst, ot_sa + b * otile_bytes, otile_bytes);
+            bulk_commit();
+        }
+        dst += dst_step;
+    }
+    if (tail > 0 && gw == n_tiles % gstride) {        // ragged tail: the next warp in line, plain loads and stores
+        float *stage = reinterpret_cast<float *>(ring);            // every bulk load of this warp has been consumed
+        const float *tsrc = kpts + (size_t)n_tiles * TRI_WTILE * row_elems;
+        for (int i = lane; i < tail * row_elems; i += 32) stage[i] = tsrc[i];
+        __syncwarp();
+        const float *rows[TRI_NJ];
+#pragma unroll
+        for (int j = 0; j < TRI_NJ; ++j) rows[j] = stage + (lane + 32 * j < tail ? lane + 32 * j : 0) * row_elems;   // idle slots repeat joint 0
+        float Xo[TRI_NJ][3];
+        int state[TRI_NJ];
+        solve_mixed<V, LAYOUT, TRI_NP>(cam, pairs, sv, n_pairs, prm.rig2, rows, Xo, state);
+        float *tdst = out + (size_t)n_tiles * TRI_WTILE * 3;
+#pragma unroll
+        for (int j = 0; j < TRI_NJ; ++j) {
+            const int slot = lane + 32 * j;
+            if (slot < tail) {
+                float fix[3] = {Xo[j][0], Xo[j][1], Xo[j][2]};
+                if (state[j] == 1) mixed_cold_fix(prm, V, rows[j], LAYOUT == MC3D_LAYOUT_3V, fix);
+                tdst[slot * 3 + 0] = fix[0]; tdst[slot * 3 + 1] = fix[1]; tdst[slot * 3 + 2] = fix[2];
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_all<0>();
+}
+
+// Shared-memory rows of the generic kernel.  One thread reads one joint's row, so a row of r 16-byte units with r a multiple
+// of 8 puts every lane of a warp on the same banks (double storage, V = 16: r = 24 -> 32-way conflicts; `short_scoreboard`
+// 5 warps per issue, 39 % of the roofline).  Such rows are copied one by one (each thread issues the bulk copy of its own
+// row; all of them complete on the stage's mbarrier) into slots of r + 1 units, which is conflict-free: +45 % for that
+// kernel.  For r = 12 (double, V = 8: 8-way) the grouped variant (two rows per copy, one padding unit per group) removes
+// the conflicts too, but the 128 small TMA copies per tile cost as much as they save, so it keeps the single contiguous
+// bulk copy.
 struct RowPlan {
     int group;        // rows per bulk copy (0: one contiguous copy for the whole tile)
     int slot_elems;   // elements per group slot (group * row_elems + padding)
@@ -715,272 +704,7 @@ __device__ __forceinline__ size_t tri_row_offset(const RowPlan &p, int slot, int
     return p.group ? (size_t)(slot / p.group) * p.slot_elems + (size_t)(slot % p.group) * row_elems : (size_t)slot * row_elems;
 }
 
-#ifndef MC3D_TRI_NJ
-#define MC3D_TRI_NJ 2
-#endif
-#ifndef MC3D_TRI_MTHREADS
-#define MC3D_TRI_MTHREADS 128
-#endif
-#ifndef MC3D_TRI_MBLOCKS
-#define MC3D_TRI_MBLOCKS 4
-#endif
-constexpr int TRI_NJ = MC3D_TRI_NJ;             // joints per thread in the mixed kernel
-constexpr int TRI_MTHREADS = MC3D_TRI_MTHREADS; // threads per CTA of the mixed kernel
-constexpr int TRI_MTILE = TRI_MTHREADS * TRI_NJ;    // joints per tile
-
-// Mixed-precision kernel (float storage, weighted mode, V in {2,3,4,8,16}, no undistortion).  Same TMA ring as the
-// generic kernel; 128 threads x 2 joints per thread (thread t owns joints t and t + 128 of a 256-joint tile), view
-// loops unrolled four views at a time, camera constants in shared memory (128-bit broadcast loads), 4 CTAs per SM
-// (3 for 16 views): the fastest on B200 of the (joints/thread, threads, CTAs/SM, unroll) variants timed
-// (profiles/README.md).
-template <int V, int LAYOUT>
-__global__ void __launch_bounds__(TRI_MTHREADS, (V >= 16) ? MC3D_TRI_MBLOCKS - 1 : MC3D_TRI_MBLOCKS)
-triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out, long long n, int n_stages,
-                         const __grid_constant__ TriParams prm) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int row_elems = 3 * V;
-    const RowPlan plan = tri_row_plan(row_elems, (int)sizeof(float));
-    constexpr uint32_t row_bytes = (uint32_t)(row_elems * sizeof(float));
-    const uint32_t stage_bytes = (uint32_t)(tri_stage_elems(TRI_MTILE, row_elems, (int)sizeof(float)) * sizeof(float));
-    float *ring = reinterpret_cast<float *>(smem_raw);
-    float *otile = reinterpret_cast<float *>(smem_raw + (size_t)n_stages * stage_bytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + 2 * TRI_MTILE * 3 * sizeof(float));
-    CamC *cam = reinterpret_cast<CamC *>(full + 8);          // per-view constants, read with 128-bit loads
-    const int tid = threadIdx.x;
-    const long long n_tiles = (n + TRI_MTILE - 1) / TRI_MTILE;
-    const long long first = blockIdx.x, stride = gridDim.x;
-    const long long my_tiles = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
-    if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
-        fence_mbar_init();
-    }
-    if (tid < V) {
-        CamC c;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) c.Pc[k] = MC3D_TRI_RAW_RESID ? prm.P[tid][k] : prm.Pc[tid][k];
-        c.cxd = prm.cxyd[tid][0];
-        c.cyd = prm.cxyd[tid][1];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) c.p10[k] = prm.p10[tid][k];
-        c.p2 = make_float4(prm.p2[tid][0].x, prm.p2[tid][1].x, prm.p2[tid][2].x, prm.p2[tid][3].x);
-        c.cx = prm.cxy[tid].x;
-        c.cy = prm.cxy[tid].y;
-        c.pad0 = c.pad1 = 0.f;
-        cam[tid] = c;
-    }
-    __syncthreads();
-    auto tile_is_full = [&](long long tile) { return (tile + 1) * TRI_MTILE <= n; };
-    auto issue_load = [&](long long k, int s) {   // every thread
-        const long long tile = first + k * stride;
-        if (k < my_tiles && tile_is_full(tile)) {
-            unsigned char *dst = reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes;
-            const float *src = kpts + tile * TRI_MTILE * (long long)row_elems;
-            if (plan.group) {
-                if (tid == 0) mbar_arrive_expect_tx(&full[s], TRI_MTILE * row_bytes);
-#pragma unroll
-                for (int j = 0; j < TRI_NJ; ++j) {
-                    const int slot = tid + j * TRI_MTHREADS;
-                    if (slot % plan.group == 0)
-                        bulk_g2s(dst + tri_row_offset(plan, slot, row_elems) * sizeof(float), src + (size_t)slot * row_elems,
-                                 plan.group * row_bytes, &full[s]);
-                }
-            } else if (tid == 0) {
-                mbar_arrive_expect_tx(&full[s], stage_bytes);
-                bulk_g2s(dst, src, stage_bytes, &full[s]);
-            }
-        }
-    };
-    for (int k = 0; k < n_stages - 1; ++k) issue_load(k, k);
-    int s = 0, s_next = n_stages - 1;
-    uint32_t parity = 0;
-    for (long long k = 0; k < my_tiles; ++k) {
-        const long long tile = first + k * stride;
-        const bool full_tile = tile_is_full(tile);
-        float *stage = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ring) + (size_t)s * stage_bytes);
-        issue_load(k + n_stages - 1, s_next);
-        if (tid == 0) bulk_wait_read<1>();
-        if (full_tile) {
-            mbar_wait(&full[s], parity);
-        } else {
-            const long long base = tile * TRI_MTILE * (long long)row_elems;
-            const long long cnt = (n - tile * TRI_MTILE) * row_elems;
-            for (long long i = tid; i < cnt; i += TRI_MTHREADS) stage[tri_row_offset(plan, (int)(i / row_elems), row_elems) + (i % row_elems)] = kpts[base + i];
-            __syncthreads();
-        }
-        const float *rows[TRI_NJ];
-        bool act[TRI_NJ];
-        double X[TRI_NJ][3];
-        int state[TRI_NJ];
-#pragma unroll
-        for (int j = 0; j < TRI_NJ; ++j) {
-            const int slot = tid + j * TRI_MTHREADS;
-            act[j] = tile * TRI_MTILE + slot < n;
-            rows[j] = stage + tri_row_offset(plan, act[j] ? slot : tid, row_elems);      // inactive slots read a valid row
-        }
-#if MC3D_TRI_FLOAT_TAIL
-        float Xo[TRI_NJ][3];
-#endif
-        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state MC3D_XO_ARG);
-#pragma unroll
-        for (int j = 0; j < TRI_NJ; ++j)
-            if (act[j] && state[j] == 1) {
-                double f0, f1, f2;                   // separate scalars: X[][] must not have its address taken
-                solve_double_from_row(prm, rows[j], V, LAYOUT == MC3D_LAYOUT_3V, f0, f1, f2);
-                X[j][0] = f0; X[j][1] = f1; X[j][2] = f2;
-            }
-#if MC3D_TRI_FLOAT_TAIL
-#pragma unroll
-        for (int j = 0; j < TRI_NJ; ++j)             // accepted joints left the solver as floats; widen for the common tail
-            if (!(act[j] && state[j] == 1)) { X[j][0] = (double)Xo[j][0]; X[j][1] = (double)Xo[j][1]; X[j][2] = (double)Xo[j][2]; }
-#endif
-        __syncthreads();                       // [A] every thread has consumed stage s
-        float *ot = otile + (size_t)(k & 1) * TRI_MTILE * 3;
-        if (full_tile) {
-#pragma unroll
-            for (int j = 0; j < TRI_NJ; ++j) {
-                const int slot = tid + j * TRI_MTHREADS;
-                ot[slot * 3 + 0] = (float)X[j][0];
-                ot[slot * 3 + 1] = (float)X[j][1];
-                ot[slot * 3 + 2] = (float)X[j][2];
-            }
-            fence_proxy_async_smem();
-            __syncthreads();                   // [B]
-            if (tid == 0) {
-                bulk_s2g(out + tile * TRI_MTILE * 3, ot, (uint32_t)(TRI_MTILE * 3 * sizeof(float)));
-                bulk_commit();
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < TRI_NJ; ++j) {
-                const long long joint = tile * TRI_MTILE + tid + j * TRI_MTHREADS;
-                if (act[j]) {
-                    out[joint * 3 + 0] = (float)X[j][0];
-                    out[joint * 3 + 1] = (float)X[j][1];
-                    out[joint * 3 + 2] = (float)X[j][2];
-                }
-            }
-            if (tid == 0) bulk_commit();
-        }
-        if (++s == n_stages) { s = 0; parity ^= 1u; }
-        if (++s_next == n_stages) s_next = 0;
-    }
-    if (tid == 0) bulk_wait_all<0>();
-}
-
-
-// ---- lean tile loop for the mixed kernel (MC3D_TRI_LEAN, tuning build) ----------------------------------------------------
-// Same ring, same solver, same results; what differs is the per-tile bookkeeping, which costs the kernel above ~75 of its
-// ~675 instructions per joint: this one processes FULL tiles only (the host launches the kernel above on the ragged tail),
-// so there is no activity mask and no ragged path in the loop; global addresses are running pointers instead of 64-bit
-// products; only thread 0 evaluates the refill; the output tile is written straight from the solver's registers with the
-// rare all-double fallback patching its slot afterwards (no register shuffling around an out-of-line call on the hot path);
-// and one block barrier per tile instead of two (thread 0 waits for the previous bulk store to have been read BEFORE the
-// barrier, which publishes that the other output buffer is free again).
-#ifndef MC3D_TRI_LEAN
-#define MC3D_TRI_LEAN 1
-#endif
-#if MC3D_TRI_LEAN
-template <int V>
-__device__ __noinline__ void mixed_cold_fix(const TriParams &prm, const float *row0, const float *row1, int st0, int st1,
-                                            bool l3v, float *ot0, float *ot1) {
-    if (st0 == 1) {
-        double f0, f1, f2;
-        solve_double_from_row(prm, row0, V, l3v, f0, f1, f2);
-        ot0[0] = (float)f0; ot0[1] = (float)f1; ot0[2] = (float)f2;
-    }
-    if (st1 == 1) {
-        double f0, f1, f2;
-        solve_double_from_row(prm, row1, V, l3v, f0, f1, f2);
-        ot1[0] = (float)f0; ot1[1] = (float)f1; ot1[2] = (float)f2;
-    }
-}
-
-template <int V, int LAYOUT>
-__global__ void __launch_bounds__(TRI_MTHREADS, (V >= 16) ? MC3D_TRI_MBLOCKS - 1 : MC3D_TRI_MBLOCKS)
-triangulate_mixed_lean_kernel(const float *__restrict__ kpts, float *__restrict__ out, unsigned n_tiles, int n_stages,
-                              const __grid_constant__ TriParams prm) {
-    static_assert(TRI_NJ == 2, "the lean loop is written for two joints per thread");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int row_elems = 3 * V;
-    constexpr uint32_t stage_bytes = (uint32_t)(TRI_MTILE * row_elems * sizeof(float));      // contiguous tiles only
-    constexpr uint32_t otile_bytes = (uint32_t)(TRI_MTILE * 3 * sizeof(float));
-    static_assert((row_elems * sizeof(float)) % 128 != 0, "padded row plans use the kernel above");
-    unsigned char *ring = smem_raw;
-    float *otile = reinterpret_cast<float *>(smem_raw + (size_t)n_stages * stage_bytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + 2 * otile_bytes);
-    CamC *cam = reinterpret_cast<CamC *>(full + 8);
-    const int tid = threadIdx.x;
-    const unsigned first = blockIdx.x, stride = gridDim.x;
-    const unsigned my_tiles = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
-    if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
-        fence_mbar_init();
-    }
-    if (tid < V) {
-        CamC c;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) c.Pc[k] = MC3D_TRI_RAW_RESID ? prm.P[tid][k] : prm.Pc[tid][k];
-        c.cxd = prm.cxyd[tid][0];
-        c.cyd = prm.cxyd[tid][1];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) c.p10[k] = prm.p10[tid][k];
-        c.p2 = make_float4(prm.p2[tid][0].x, prm.p2[tid][1].x, prm.p2[tid][2].x, prm.p2[tid][3].x);
-        c.cx = prm.cxy[tid].x;
-        c.cy = prm.cxy[tid].y;
-        c.pad0 = c.pad1 = 0.f;
-        cam[tid] = c;
-    }
-    __syncthreads();
-    // thread 0 only: global addresses of the tiles this CTA loads and stores (computed inside its branches, so the other
-    // warps neither execute the 64-bit arithmetic nor hold the pointers in registers)
-    auto load_tile = [&](unsigned i, int st) {        // i-th tile of this CTA into stage st
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(kpts) + ((size_t)first + (size_t)i * stride) * stage_bytes;
-        mbar_arrive_expect_tx(&full[st], stage_bytes);
-        bulk_g2s(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st]);
-    };
-    if (tid == 0)
-        for (unsigned i = 0; i < (unsigned)(n_stages - 1) && i < my_tiles; ++i) load_tile(i, (int)i);
-    int s = 0, s_next = n_stages - 1;
-    uint32_t parity = 0;
-    for (unsigned k = 0; k < my_tiles; ++k) {
-        if (tid == 0 && k + (unsigned)(n_stages - 1) < my_tiles) load_tile(k + (unsigned)(n_stages - 1), s_next);   // refills the stage of iteration k - 1
-        const float *stage = reinterpret_cast<const float *>(ring + (size_t)s * stage_bytes);
-        mbar_wait(&full[s], parity);
-        const float *rows[TRI_NJ] = {stage + tid * row_elems, stage + (tid + TRI_MTHREADS) * row_elems};
-        const bool act[TRI_NJ] = {true, true};
-        double X[TRI_NJ][3];
-        int state[TRI_NJ];
-        float *ot = otile + (size_t)(k & 1) * TRI_MTILE * 3 + tid * 3;
-#if MC3D_TRI_FLOAT_TAIL
-        float Xo[TRI_NJ][3];
-        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state, Xo);
-        ot[0] = Xo[0][0]; ot[1] = Xo[0][1]; ot[2] = Xo[0][2];
-        ot[TRI_MTHREADS * 3 + 0] = Xo[1][0]; ot[TRI_MTHREADS * 3 + 1] = Xo[1][1]; ot[TRI_MTHREADS * 3 + 2] = Xo[1][2];
-#else
-        solve_merged<V, LAYOUT, TRI_NJ>(cam, prm.rig2, rows, act, X, state);
-        ot[0] = (float)X[0][0]; ot[1] = (float)X[0][1]; ot[2] = (float)X[0][2];
-        ot[TRI_MTHREADS * 3 + 0] = (float)X[1][0]; ot[TRI_MTHREADS * 3 + 1] = (float)X[1][1]; ot[TRI_MTHREADS * 3 + 2] = (float)X[1][2];
-#endif
-        if (state[0] == 1 || state[1] == 1)
-            mixed_cold_fix<V>(prm, stage + tid * row_elems, stage + (tid + TRI_MTHREADS) * row_elems, state[0], state[1],
-                              LAYOUT == MC3D_LAYOUT_3V, ot, ot + TRI_MTHREADS * 3);
-        fence_proxy_async_smem();
-        if (tid == 0) bulk_wait_read<0>();            // the store of iteration k - 1 has left the OTHER output buffer
-        __syncthreads();                              // stage s consumed by everyone; output tile complete
-        if (tid == 0) {
-            bulk_s2g(reinterpret_cast<unsigned char *>(out) + ((size_t)first + (size_t)k * stride) * otile_bytes,
-                     otile + (size_t)(k & 1) * TRI_MTILE * 3, otile_bytes);
-            bulk_commit();
-        }
-        if (++s == n_stages) { s = 0; parity ^= 1u; }
-        if (++s_next == n_stages) s_next = 0;
-    }
-    if (tid == 0) bulk_wait_all<0>();
-}
-#endif  // MC3D_TRI_LEAN
-
-
-// ---- kernel -----------------------------------------------------------------------------------
+// ---- generic kernel -----------------------------------------------------------------------------------
 // V > 0: number of views known at compile time (fully unrolled); V == 0: runtime prm.n_views.
 template <typename T, int V, int MODE, bool UNDISTORT>
 __global__ void __launch_bounds__(TRI_TILE, (V > 0 && V <= 8) ? 3 : 2)
@@ -1161,6 +885,153 @@ triangulate_kernel(const T *__restrict__ kpts, T *__restrict__ out, long long n,
 }
 
 // ---- host side --------------------------------------------------------------------------------
+namespace {
+struct ViewGeom {
+    bool ok;             // finite camera: the left 3x3 block of P is invertible
+    double H[9];         // its inverse
+    double C[3];         // camera centre: P (C,1) = 0
+    double axis[3];      // unit viewing direction (third row of the block, towards positive depth)
+};
+
+bool invert3(const double *m, double *inv, double &det) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    const double scale = fabs(a) + fabs(b) + fabs(c) + fabs(d) + fabs(e) + fabs(f) + fabs(g) + fabs(h) + fabs(i);
+    if (!(fabs(det) > 1e-30 * scale * scale * scale) || !(fabs(det) <= 1.0e300)) return false;
+    const double r = 1.0 / det;
+    inv[0] = (e * i - f * h) * r; inv[1] = (c * h - b * i) * r; inv[2] = (b * f - c * e) * r;
+    inv[3] = (f * g - d * i) * r; inv[4] = (a * i - c * g) * r; inv[5] = (c * d - a * f) * r;
+    inv[6] = (d * h - e * g) * r; inv[7] = (b * g - a * h) * r; inv[8] = (a * e - b * d) * r;
+    return true;
+}
+
+ViewGeom view_geometry(const double *P) {
+    ViewGeom g;
+    const double M[9] = {P[0], P[1], P[2], P[4], P[5], P[6], P[8], P[9], P[10]};
+    double det = 0.0;
+    g.ok = invert3(M, g.H, det);
+    if (!g.ok) return g;
+    for (int r = 0; r < 3; ++r) g.C[r] = -(g.H[3 * r] * P[3] + g.H[3 * r + 1] * P[7] + g.H[3 * r + 2] * P[11]);
+    const double n = sqrt(P[8] * P[8] + P[9] * P[9] + P[10] * P[10]);
+    const double sgn = det < 0 ? -1.0 : 1.0;
+    for (int k = 0; k < 3; ++k) g.axis[k] = n > 0 ? sgn * P[8 + k] / n : 0.0;
+    for (int k = 0; k < 3; ++k) g.ok = g.ok && fabs(g.C[k]) <= 1.0e300;
+    return g;
+}
+}  // namespace
+
+// Starting-point plan of the mixed-precision kernel: up to two pairs of views (A, B), chosen for the widest angle
+// between their rays to a nominal scene point, with the constants of the closed-form two-view point (pair_start).
+// Returns the number of pairs (0 when no two finite cameras exist: every joint then starts from the world origin).
+// Only the speed of the kernel depends on the choice -- its fixed point does not.
+int fill_start_pairs(const double (*P)[12], int n_views, mc3d_tri_start_pair *out) {
+    ViewGeom geo[MC3D_MAX_VIEWS];
+    int idx[MC3D_MAX_VIEWS], m = 0;
+    for (int v = 0; v < n_views; ++v) {
+        geo[v] = view_geometry(P[v]);
+        if (geo[v].ok) idx[m++] = v;
+    }
+    if (m < 2) return 0;
+    // nominal scene point: closest to every optical axis, pulled (weakly) towards a point in front of the rig so that
+    // parallel axes do not leave it undetermined
+    double Cm[3] = {0, 0, 0}, am[3] = {0, 0, 0};
+    for (int i = 0; i < m; ++i)
+        for (int k = 0; k < 3; ++k) { Cm[k] += geo[idx[i]].C[k] / m; am[k] += geo[idx[i]].axis[k] / m; }
+    double L = 0.0;
+    for (int i = 0; i < m; ++i)
+        for (int k = 0; k < 3; ++k) L += (geo[idx[i]].C[k] - Cm[k]) * (geo[idx[i]].C[k] - Cm[k]) / m;
+    L = sqrt(L);
+    if (!(L > 0.0)) L = 1.0;
+    const double an = sqrt(am[0] * am[0] + am[1] * am[1] + am[2] * am[2]);
+    double Xreg[3];
+    for (int k = 0; k < 3; ++k) Xreg[k] = Cm[k] + (an > 1e-6 ? am[k] / an : 0.0) * L;
+    const double eps = 1e-3 * m;
+    double A[9] = {eps, 0, 0, 0, eps, 0, 0, 0, eps}, b[3] = {eps * Xreg[0], eps * Xreg[1], eps * Xreg[2]};
+    for (int i = 0; i < m; ++i) {
+        const ViewGeom &g = geo[idx[i]];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                const double q = (r == c ? 1.0 : 0.0) - g.axis[r] * g.axis[c];
+                A[3 * r + c] += q;
+                b[r] += q * g.C[c];
+            }
+    }
+    double Ai[9], det = 0.0, X0[3] = {Xreg[0], Xreg[1], Xreg[2]};
+    if (invert3(A, Ai, det)) {
+        double cand[3];
+        for (int r = 0; r < 3; ++r) cand[r] = Ai[3 * r] * b[0] + Ai[3 * r + 1] * b[1] + Ai[3 * r + 2] * b[2];
+        bool in_front = true;               // diverging axes meet BEHIND the cameras: keep the point in front of the rig
+        for (int i = 0; i < m; ++i) {
+            const ViewGeom &g = geo[idx[i]];
+            const double depth = g.axis[0] * (cand[0] - g.C[0]) + g.axis[1] * (cand[1] - g.C[1]) + g.axis[2] * (cand[2] - g.C[2]);
+            in_front = in_front && depth > 0.0;
+        }
+        if (in_front) for (int k = 0; k < 3; ++k) X0[k] = cand[k];
+    }
+    auto score = [&](int a, int c) {        // |sin| of the angle between the rays from the two centres to X0
+        double da[3], db[3];
+        for (int k = 0; k < 3; ++k) { da[k] = X0[k] - geo[a].C[k]; db[k] = X0[k] - geo[c].C[k]; }
+        const double cx = da[1] * db[2] - da[2] * db[1], cy = da[2] * db[0] - da[0] * db[2], cz = da[0] * db[1] - da[1] * db[0];
+        const double na = sqrt(da[0] * da[0] + da[1] * da[1] + da[2] * da[2]), nb = sqrt(db[0] * db[0] + db[1] * db[1] + db[2] * db[2]);
+        return (na > 0 && nb > 0) ? sqrt(cx * cx + cy * cy + cz * cz) / (na * nb) : 0.0;
+    };
+    int pa[2] = {-1, -1}, pb[2] = {-1, -1};
+    double best = -1.0;
+    for (int i = 0; i < m; ++i)
+        for (int j = i + 1; j < m; ++j) {
+            const double s = score(idx[i], idx[j]);
+            if (s > best) { best = s; pa[0] = idx[i]; pb[0] = idx[j]; }
+        }
+    best = -1.0;                            // second pair: no view in common with the first when the rig allows it
+    for (int pass = 0; pass < 2 && pa[1] < 0; ++pass)
+        for (int i = 0; i < m; ++i)
+            for (int j = i + 1; j < m; ++j) {
+                const int a = idx[i], c = idx[j];
+                const bool shares = a == pa[0] || a == pb[0] || c == pa[0] || c == pb[0];
+                if ((a == pa[0] && c == pb[0]) || (pass == 0 && shares)) continue;
+                const double s = score(a, c);
+                if (s > best) { best = s; pa[1] = a; pb[1] = c; }
+            }
+    if (pa[1] < 0) { pa[1] = pb[0]; pb[1] = pa[0]; }        // two cameras: the same pair with the roles exchanged
+    for (int p = 0; p < 2; ++p) {
+        const ViewGeom &ga = geo[pa[p]];
+        const double *Pb = P[pb[p]];
+        // epipolar direction in view B: the image of a step along the ray from C_A to X0
+        double dir[3], len = 0.0;
+        for (int k = 0; k < 3; ++k) { dir[k] = X0[k] - ga.C[k]; len += dir[k] * dir[k]; }
+        len = sqrt(len);
+        auto project_b = [&](const double *X, double &u, double &v) {
+            const double h0 = Pb[0] * X[0] + Pb[1] * X[1] + Pb[2] * X[2] + Pb[3];
+            const double h1 = Pb[4] * X[0] + Pb[5] * X[1] + Pb[6] * X[2] + Pb[7];
+            const double h2 = Pb[8] * X[0] + Pb[9] * X[1] + Pb[10] * X[2] + Pb[11];
+            u = h0 / h2; v = h1 / h2;
+        };
+        double X1[3], u0, v0, u1, v1;
+        for (int k = 0; k < 3; ++k) X1[k] = X0[k] + 0.01 * dir[k];
+        project_b(X0, u0, v0);
+        project_b(X1, u1, v1);
+        double alpha = u1 - u0, beta = v1 - v0;
+        const double nl = sqrt(alpha * alpha + beta * beta);
+        if (nl > 0.0 && nl <= 1.0e300 && len > 0.0) { alpha /= nl; beta /= nl; } else { alpha = 1.0; beta = 0.0; }
+        double Pa[4];
+        for (int k = 0; k < 4; ++k) Pa[k] = alpha * Pb[k] + beta * Pb[4 + k];
+        mc3d_tri_start_pair &o = out[p];
+        for (int k = 0; k < 9; ++k) o.H[k] = (float)ga.H[k];
+        for (int k = 0; k < 3; ++k) {
+            o.C[k] = (float)ga.C[k];
+            o.ua[k] = (float)(ga.H[k] * Pa[0] + ga.H[3 + k] * Pa[1] + ga.H[6 + k] * Pa[2]);        // H^T Pa
+            o.ub[k] = (float)(ga.H[k] * Pb[8] + ga.H[3 + k] * Pb[9] + ga.H[6 + k] * Pb[10]);       // H^T P2_B
+        }
+        o.alpha = (float)alpha;
+        o.beta = (float)beta;
+        o.ka = (float)(Pa[0] * ga.C[0] + Pa[1] * ga.C[1] + Pa[2] * ga.C[2] + Pa[3]);
+        o.kb = (float)(Pb[8] * ga.C[0] + Pb[9] * ga.C[1] + Pb[10] * ga.C[2] + Pb[11]);
+        o.view_a = pa[p];
+        o.view_b = pb[p];
+    }
+    return 2;
+}
+
 static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode, int flags) {
     if (!rig || !rig->P) { set_error("rig / rig->P is NULL"); return MC3D_ERR_INVALID_ARGUMENT; }
     if (rig->n_views < 2 || rig->n_views > MC3D_MAX_VIEWS) {
@@ -1185,49 +1056,24 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
             for (int k = 0; k < 5; ++k) prm.dist[v][k] = rig->dist[v * 5 + k];
         }
     }
-    for (int v = 0; v < rig->n_views; ++v) {
-        const double *P0 = prm.P[v], *P1 = prm.P[v] + 4, *P2 = prm.P[v] + 8;
-        const double n2 = P2[0] * P2[0] + P2[1] * P2[1] + P2[2] * P2[2];
-        // principal point of the view: any value keeps the rows identical, this one keeps their entries small
-        const float cx = n2 > 0 ? (float)((P0[0] * P2[0] + P0[1] * P2[1] + P0[2] * P2[2]) / n2) : 0.f;
-        const float cy = n2 > 0 ? (float)((P1[0] * P2[0] + P1[1] * P2[1] + P1[2] * P2[2]) / n2) : 0.f;
-        prm.cxy[v] = make_float2(cx, cy);
-        prm.cxyd[v][0] = (double)cx;
-        prm.cxyd[v][1] = (double)cy;
-        for (int k = 0; k < 4; ++k) {
-            const double p0c = P0[k] - (double)cx * P2[k], p1c = P1[k] - (double)cy * P2[k];
-            prm.Pc[v][k] = p0c; prm.Pc[v][4 + k] = p1c; prm.Pc[v][8 + k] = P2[k];
-            prm.p2[v][k] = make_float2((float)P2[k], (float)P2[k]);
-            prm.p10[v][k] = make_float2((float)-p1c, (float)p0c);
-        }
-    }
-    double acc = 0.0;
+    prm.n_start = fill_start_pairs(prm.P, rig->n_views, prm.start);
+    double acc = 0.0;                         // rig scale: mean squared distance of the camera centres from the world origin
     int cnt = 0;
-    for (int v = 0; v < rig->n_views; ++v) {                 // camera centre C: P (C,1) = 0
-        const double *p = prm.P[v];
-        const double a = p[0], b = p[1], c = p[2], d = p[4], e = p[5], f = p[6], g = p[8], h = p[9], i = p[10];
-        const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
-        if (!(fabs(det) > 0.0)) continue;
-        const double r0 = -p[3], r1 = -p[7], r2 = -p[11];
-        const double c0 = (r0 * (e * i - f * h) - b * (r1 * i - f * r2) + c * (r1 * h - e * r2)) / det;
-        const double c1 = (a * (r1 * i - f * r2) - r0 * (d * i - f * g) + c * (d * r2 - r1 * g)) / det;
-        const double c2 = (a * (e * r2 - r1 * h) - b * (d * r2 - r1 * g) + r0 * (d * h - e * g)) / det;
-        const double n2 = c0 * c0 + c1 * c1 + c2 * c2;
+    for (int v = 0; v < rig->n_views; ++v) {
+        const ViewGeom g = view_geometry(prm.P[v]);
+        if (!g.ok) continue;
+        const double n2 = g.C[0] * g.C[0] + g.C[1] * g.C[1] + g.C[2] * g.C[2];
         if (n2 <= 1.0e300) { acc += n2; ++cnt; }
     }
     prm.rig2 = cnt ? (float)fmin(acc / cnt, 1.0e30) : 0.f;
     return MC3D_OK;
 }
 
-// ---- lean tile loop for double storage (MC3D_TRI_LEAN64, tuning build) -------------------------------------------------------
+// ---- lean tile loop for double storage -------------------------------------------------------
 // The generic kernel above spends ~170 of its ~1 030 instructions per joint on per-tile bookkeeping (one joint per thread,
 // so nothing amortises it).  This one is the weighted, undistortion-free, compile-time-V, contiguous-tile case only: full
 // tiles (the host launches the generic kernel on the ragged tail), layout as a template parameter, global addresses computed
 // in thread 0's branches.  Same accumulation order, same solver: bit-identical results.
-#ifndef MC3D_TRI_LEAN64
-#define MC3D_TRI_LEAN64 1
-#endif
-#if MC3D_TRI_LEAN64
 template <int V, int LAYOUT>
 __global__ void __launch_bounds__(TRI_TILE, (V <= 8) ? 3 : 2)
 triangulate_lean64_kernel(const double *__restrict__ kpts, double *__restrict__ out, unsigned n_tiles, int n_stages,
@@ -1314,7 +1160,6 @@ triangulate_lean64_kernel(const double *__restrict__ kpts, double *__restrict__ 
     }
     if (tid == 0) bulk_wait_all<0>();
 }
-#endif  // MC3D_TRI_LEAN64
 
 template <typename T, int V, int MODE, bool UNDISTORT>
 static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_out, cudaStream_t stream) {
@@ -1340,9 +1185,8 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
         if (occ > per_sm) { per_sm = occ; n_stages = st; smem = sm_bytes; }
     }
     if (per_sm < 1) { set_error("triangulate kernel does not fit in shared memory (views=%d)", nv); return MC3D_ERR_UNSUPPORTED; }
-#if MC3D_TRI_LEAN64
-    // tuning build: weighted double storage with a compile-time even view count -- full tiles through the lean loop, the
-    // ragged tail through the generic kernel
+    // weighted double storage with a compile-time even view count: full tiles through the lean loop, the ragged tail
+    // through the generic kernel
     if constexpr (std::is_same<T, double>::value && MODE == MC3D_TRI_WEIGHTED && !UNDISTORT && V > 0 && V % 2 == 0 &&
                   (3 * V * sizeof(double)) % 128 != 0) {              // rows of a multiple of 128 bytes use padded slots
         if (tri_row_plan(3 * V, (int)sizeof(double)).group == 0 && n / TRI_TILE > 0 && n / TRI_TILE < 0x7fffffffLL) {
@@ -1370,7 +1214,6 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
             return MC3D_OK;
         }
     }
-#endif
     const long long n_tiles = (n + TRI_TILE - 1) / TRI_TILE;
     long long grid = (long long)sm_count() * per_sm;      // persistent: a whole number of waves
     if (grid > n_tiles) grid = n_tiles;
@@ -1382,52 +1225,27 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
 
 template <int V, int LAYOUT>
 static int launch_mixed(const float *d_kpts, long long n, const TriParams &prm, float *d_out, cudaStream_t stream) {
-    const size_t stage_bytes = tri_stage_elems(TRI_MTILE, 3 * V, (int)sizeof(float)) * sizeof(float);
+    constexpr size_t stage_bytes = (size_t)TRI_WTILE * 3 * V * sizeof(float);
+    constexpr size_t otile_bytes = (size_t)TRI_WTILE * 3 * sizeof(float);
+    // two stages per warp: a warp needs ~3 us per tile, which covers the HBM latency, and more resident warps beat a deeper ring
+    constexpr size_t smem = TRI_MWARPS * 2 * (stage_bytes + otile_bytes + sizeof(uint64_t)) + V * sizeof(CamF) +
+                            2 * sizeof(mc3d_tri_start_pair);
+    static_assert(smem <= 227 * 1024, "mixed kernel: shared memory");
     auto kern = triangulate_mixed_kernel<V, LAYOUT>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
         MC3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
-    const size_t fixed = 2 * TRI_MTILE * 3 * sizeof(float) + 8 * sizeof(uint64_t) + V * sizeof(CamC);
-    int n_stages = 2, per_sm = 0;
-    size_t smem = 0;
-    for (int st = 3; st >= 2; --st) {
-        const size_t sm_bytes = st * stage_bytes + fixed;
-        if (sm_bytes > 227 * 1024) continue;
         int occ = 0;
-        MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TRI_MTHREADS, sm_bytes));
-        if (occ > per_sm) { per_sm = occ; n_stages = st; smem = sm_bytes; }
+        MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TRI_MTHREADS, smem));
+        if (occ < 1) { set_error("mixed triangulate kernel does not fit on an SM"); return MC3D_ERR_UNSUPPORTED; }
+        per_sm = occ;
     }
-    if (per_sm < 1) { set_error("mixed triangulate kernel does not fit in shared memory"); return MC3D_ERR_UNSUPPORTED; }
-#if MC3D_TRI_LEAN
-    // tuning build: full tiles through the lean loop, the ragged tail (< one tile) through the kernel above
-    if (tri_row_plan(3 * V, (int)sizeof(float)).group == 0 && n / TRI_MTILE > 0 && n / TRI_MTILE < 0x7fffffffLL) {
-        auto lean = triangulate_mixed_lean_kernel<V, LAYOUT>;
-        static bool lean_attr_done = false;
-        if (!lean_attr_done) {
-            MC3D_CUDA_TRY(cudaFuncSetAttribute(lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            lean_attr_done = true;
-        }
-        const long long n_full = n / TRI_MTILE, tail = n - n_full * TRI_MTILE;
-        long long lgrid = (long long)sm_count() * per_sm;
-        if (lgrid > n_full) lgrid = n_full;
-        lean<<<(unsigned)lgrid, TRI_MTHREADS, smem, stream>>>(d_kpts, d_out, (unsigned)n_full, n_stages, prm);
-        count_launch();
-        MC3D_CUDA_TRY(cudaGetLastError());
-        if (tail > 0) {
-            kern<<<1, TRI_MTHREADS, smem, stream>>>(d_kpts + n_full * TRI_MTILE * 3 * V, d_out + n_full * TRI_MTILE * 3, tail,
-                                                    n_stages, prm);
-            count_launch();
-            MC3D_CUDA_TRY(cudaGetLastError());
-        }
-        return MC3D_OK;
-    }
-#endif
-    const long long n_tiles = (n + TRI_MTILE - 1) / TRI_MTILE;
-    long long grid = (long long)sm_count() * per_sm;
-    if (grid > n_tiles) grid = n_tiles;
-    kern<<<(unsigned)grid, TRI_MTHREADS, smem, stream>>>(d_kpts, d_out, n, n_stages, prm);
+    if (n / TRI_WTILE >= 0x7fffffffLL) { set_error("n=%lld: more than 2^31 tiles in one launch", n); return MC3D_ERR_UNSUPPORTED; }
+    const long long warp_tiles = (n + TRI_WTILE - 1) / TRI_WTILE;          // the ragged tail is one more warp tile
+    long long grid = (long long)sm_count() * per_sm;                       // persistent: a whole number of waves
+    const long long ctas = (warp_tiles + TRI_MWARPS - 1) / TRI_MWARPS;
+    if (grid > ctas) grid = ctas;
+    kern<<<(unsigned)grid, TRI_MTHREADS, smem, stream>>>(d_kpts, d_out, n, prm);
     count_launch();
     MC3D_CUDA_TRY(cudaGetLastError());
     return MC3D_OK;
@@ -1486,6 +1304,20 @@ template int triangulate_device<double>(const double *, long long, const mc3d_ri
 }  // namespace mc3d
 
 extern "C" {
+
+int mc3d_triangulate_start_plan(const mc3d_rig *rig, mc3d_tri_start_pair *pairs, int32_t *n_pairs) {
+    if (!rig || !rig->P || !pairs || !n_pairs) { mc3d::set_error("mc3d_triangulate_start_plan: NULL argument"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (rig->n_views < 2 || rig->n_views > MC3D_MAX_VIEWS) {
+        mc3d::set_error("n_views=%d outside [2, %d]", rig->n_views, MC3D_MAX_VIEWS);
+        return MC3D_ERR_INVALID_ARGUMENT;
+    }
+    double P[MC3D_MAX_VIEWS][12];
+    for (int v = 0; v < rig->n_views; ++v)
+        for (int k = 0; k < 12; ++k) P[v][k] = rig->P[v * 12 + k];
+    memset(pairs, 0, 2 * sizeof(mc3d_tri_start_pair));
+    *n_pairs = mc3d::fill_start_pairs(P, rig->n_views, pairs);
+    return MC3D_OK;
+}
 
 int mc3d_triangulate_f32(const float *d_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode, int flags,
                          float *d_out, void *stream) {

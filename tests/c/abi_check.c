@@ -12,7 +12,7 @@ int main(void) {
         (fn_t)mc3d_version, (fn_t)mc3d_last_error, (fn_t)mc3d_status_string,
         (fn_t)mc3d_launch_count, (fn_t)mc3d_device_info,
         (fn_t)mc3d_triangulate_f32, (fn_t)mc3d_triangulate_f64,
-        (fn_t)mc3d_triangulate_host_f32, (fn_t)mc3d_triangulate_host_f64,
+        (fn_t)mc3d_triangulate_host_f32, (fn_t)mc3d_triangulate_host_f64, (fn_t)mc3d_triangulate_start_plan,
         (fn_t)mc3d_decode_heatmaps_f32, (fn_t)mc3d_decode_heatmaps_host_f32,
         (fn_t)mc3d_project_points_f32, (fn_t)mc3d_project_points_f64,
         (fn_t)mc3d_refine_prepare_f32, (fn_t)mc3d_refine_prepare_f64,
