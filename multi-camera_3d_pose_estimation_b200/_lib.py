@@ -166,6 +166,23 @@ def check(status):
         raise Mc3dError(f'{l.mc3d_status_string(status).decode()}: {l.mc3d_last_error().decode()}')
 
 
+def default_device(device=None):
+    """CUDA ordinal for the host-buffer pipelines: an explicit ``device`` wins; otherwise the process's current CUDA
+    device when torch has one selected (under torchrun: the rank's own GPU), else LOCAL_RANK, else 0.  The library
+    itself restores the calling thread's current device before it returns."""
+    if device is not None:
+        if hasattr(device, 'index'):                      # torch.device
+            return int(device.index or 0)
+        return int(device)
+    try:
+        import torch
+        if torch.cuda.is_available() and torch.cuda.is_initialized():
+            return int(torch.cuda.current_device())
+    except Exception:
+        pass
+    return int(os.environ.get('LOCAL_RANK', '0') or 0)
+
+
 def launch_count():
     return int(lib().mc3d_launch_count())
 

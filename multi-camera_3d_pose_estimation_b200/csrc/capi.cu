@@ -58,9 +58,25 @@ struct HostPipe {
 std::mutex g_pipe_mutex;
 HostPipe g_pipes[MAX_DEVICES];          // one staging pipeline per device ordinal, grown on demand, kept for the process
 
+// The host-buffer entry points work on the device the CALLER names, and hand the calling thread back on the device it
+// was on: under torchrun every rank has its own current device, and a library call must not move it.
+struct DeviceGuard {
+    int prev = -1;
+    bool moved = false;
+    int enter(int device) {
+        MC3D_CUDA_TRY(cudaGetDevice(&prev));
+        if (prev != device) {
+            MC3D_CUDA_TRY(cudaSetDevice(device));
+            moved = true;
+        }
+        return MC3D_OK;
+    }
+    ~DeviceGuard() {
+        if (moved) cudaSetDevice(prev);
+    }
+};
+
 int ensure_pipe(int device, size_t in_bytes, size_t out_bytes, HostPipe **out) {
-    if (device < 0 || device >= MAX_DEVICES) { set_error("device ordinal %d out of range", device); return MC3D_ERR_INVALID_ARGUMENT; }
-    MC3D_CUDA_TRY(cudaSetDevice(device));
     HostPipe &pipe = g_pipes[device];
     if (!pipe.ready) {
         for (int b = 0; b < NBUF; ++b)
@@ -124,7 +140,10 @@ int triangulate_host(const T *h_kpts, long long n, const mc3d_rig *rig, int layo
     if (n == 0) return MC3D_OK;
     if (!h_kpts || !h_out) { set_error("NULL host pointer"); return MC3D_ERR_INVALID_ARGUMENT; }
     if (rig->n_views < 2 || rig->n_views > MC3D_MAX_VIEWS) { set_error("n_views=%d out of range", rig->n_views); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (device < 0 || device >= MAX_DEVICES) { set_error("device ordinal %d out of range", device); return MC3D_ERR_INVALID_ARGUMENT; }
     std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    DeviceGuard guard;                                                      // restores the caller's device on every exit path
+    { const int gs = guard.enter(device); if (gs != MC3D_OK) return gs; }
     const size_t row_bytes = (size_t)3 * rig->n_views * sizeof(T);
     long long chunk = (long long)((64u << 20) / row_bytes) / 256 * 256;     // ~64 MiB of keypoints per chunk
     if (chunk > n) chunk = (n + 255) / 256 * 256;
@@ -158,7 +177,10 @@ int decode_host(const float *h_hm, long long n_maps, int H, int W, float thr, fl
     if (n_maps < 0 || H <= 0 || W <= 0) { set_error("bad heatmap shape"); return MC3D_ERR_INVALID_ARGUMENT; }
     if (n_maps == 0) return MC3D_OK;
     if (!h_hm || (!h_kpt && !h_moments)) { set_error("NULL host pointer"); return MC3D_ERR_INVALID_ARGUMENT; }
+    if (device < 0 || device >= MAX_DEVICES) { set_error("device ordinal %d out of range", device); return MC3D_ERR_INVALID_ARGUMENT; }
     std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    DeviceGuard guard;                                                      // restores the caller's device on every exit path
+    { const int gs = guard.enter(device); if (gs != MC3D_OK) return gs; }
     const size_t map_bytes = (size_t)H * W * sizeof(float);
     long long chunk = (long long)((64u << 20) / map_bytes);
     if (chunk < 1) chunk = 1;

@@ -9,7 +9,7 @@ _KPT_LAYOUTS = {'plain': _lib.KPT_PLAIN, 'nv3': _lib.KPT_NV3, 'n3v': _lib.KPT_N3
 
 
 def decode_heatmaps(heatmaps, threshold=0.01, want_kpts=True, want_moments=True, write_back=False,
-                    kpt_layout='plain', affine=None, affine_group=None, generic=False, device=0, force_tma=False):
+                    kpt_layout='plain', affine=None, affine_group=None, generic=False, device=None, force_tma=False):
     """heatmaps (..., H, W) float32 -> (kpts (..., 3) float32 [x, y, score] | None,
                                          moments (..., 6) float64 | None).
 
@@ -42,7 +42,7 @@ def decode_heatmaps(heatmaps, threshold=0.01, want_kpts=True, want_moments=True,
         mom = np.empty(lead + (6,), dtype=np.float64) if want_moments else None
         _lib.check(lib.mc3d_decode_heatmaps_host_f32(hm.ctypes.data, n, H, W, float(threshold),
                                                      kpts.ctypes.data if want_kpts else None,
-                                                     mom.ctypes.data if want_moments else None, device))
+                                                     mom.ctypes.data if want_moments else None, _lib.default_device(device)))
         return kpts, mom
 
     import torch

@@ -28,7 +28,7 @@ def _views_of(shape, layout):
     return shape[-1]
 
 
-def triangulate_multiview(kpts, P, K=None, dist=None, layout='nv3', mode='weighted', out=None, flags=0, device=0):
+def triangulate_multiview(kpts, P, K=None, dist=None, layout='nv3', mode='weighted', out=None, flags=0, device=None):
     """Triangulate every joint of ``kpts`` from V views.
 
     kpts   (..., V, 3) [x, y, w] (layout 'nv3') or (..., 3, V) (layout 'n3v', the reference's
@@ -58,7 +58,7 @@ def triangulate_multiview(kpts, P, K=None, dist=None, layout='nv3', mode='weight
         res = np.empty(lead + (3,), dtype=kpts.dtype) if out is None else out
         fn = lib.mc3d_triangulate_host_f32 if kpts.dtype == np.float32 else lib.mc3d_triangulate_host_f64
         _lib.check(fn(kpts.ctypes.data, n, ctypes.byref(rig), _LAYOUTS[layout], _MODES[mode], flags,
-                      res.ctypes.data, device))
+                      res.ctypes.data, _lib.default_device(device)))
         return res
 
     import torch

@@ -127,3 +127,17 @@ def test_heatmap_moment_shims(monkeypatch):
     assert np.abs(np.array(means) - g['means']).max() < 2e-5 and np.abs(np.array(stds) - g['stds']).max() < 2e-5
     with pytest.raises(NotImplementedError):
         PoseEstimator('det.py', 'det.pth', 'pose.py', 'pose.pth')
+
+
+def test_default_device_resolution(monkeypatch):
+    """The host-buffer pipelines run on the process's own GPU (`device=0` sent every torchrun rank to GPU 0):
+    explicit argument > torch's current device (when CUDA is initialised) > LOCAL_RANK > 0."""
+    import torch
+    from mc3d_b200 import _lib
+    assert _lib.default_device(3) == 3
+    assert _lib.default_device(torch.device('cuda', 2)) == 2
+    if not (torch.cuda.is_available() and torch.cuda.is_initialized()):
+        monkeypatch.setenv('LOCAL_RANK', '5')
+        assert _lib.default_device() == 5
+        monkeypatch.delenv('LOCAL_RANK')
+        assert _lib.default_device() == 0

@@ -51,3 +51,27 @@ def test_sharded_triangulation_bench_line():
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('{')][-1])
     assert line['n_gpus'] == 2 and line['scaling'] == 'weak' and line['value'] > 1e10
     assert line['e2e']['matches_device_path']
+
+
+def test_host_pipeline_leaves_the_current_device_alone():
+    """mc3d_triangulate_host_* / mc3d_decode_heatmaps_host_f32 work on the device they are given and restore the calling
+    thread's current device; with device=None they follow torch's current device."""
+    if _n_gpus() < 2:
+        pytest.skip('needs two GPUs')
+    import numpy as np
+    import torch
+    from mc3d_b200 import synthetic as syn
+    from mc3d_b200.decode import decode_heatmaps
+    from mc3d_b200.triangulation import triangulate_multiview
+    kp, P, _, _ = syn.multiview_points(3000, 4, seed=2)
+    torch.cuda.set_device(1)
+    ref = triangulate_multiview(kp, P, device=0)
+    assert torch.cuda.current_device() == 1
+    got = triangulate_multiview(kp, P)                       # device=None -> cuda:1
+    assert torch.cuda.current_device() == 1 and np.array_equal(ref, got)
+    hm, _ = syn.gaussian_blob_heatmaps(34, seed=3)
+    k0, m0 = decode_heatmaps(hm, device=0)
+    assert torch.cuda.current_device() == 1
+    k1, m1 = decode_heatmaps(hm)
+    assert np.array_equal(k0, k1) and np.array_equal(m0, m1)
+    torch.cuda.set_device(0)
