@@ -17,6 +17,15 @@ whole batch.  Metric: 3D joints triangulated per second (whole job, all ranks).
 
 One JSON line on stdout (rank 0).  Multi-GPU: frames are sharded across ranks, no data-path collective
 (weak scaling: every rank triangulates its own 10 M frames).
+
+Beside the headline the line carries, at EVERY --gpus N (each rank works on its shard, times are the max over ranks):
+  other_configs  config 2 in float64 at its full 10 M frames, config 3 (decode 17x64x48 x 4 views + triangulation) and
+                 config 5 (16 views, point-count sweep 1e6..1e9 sharded over the ranks), each with its own roofline block
+  refine         config 4: iterations/s of the 100 000-frame refinement (sharded over the ranks when N > 1) with a roofline
+                 block, and -- N > 1 -- `vs_single_gpu`: the same problem run on ONE GPU by rank 0 and compared with the
+                 sharded run (cost history and trajectory); the process exits non-zero when they differ by more than 1e-6
+  e2e.host_link  H2D / D2H / both-ways pinned-copy bandwidth of this box measured beside the e2e number (its ceiling)
+and, at N = 1 only: `occlusion` (throughput at 0 / 1 / 5 / 20 % unusable views) and the CPU baselines of all three kernels.
 """
 import argparse
 import json
@@ -162,6 +171,63 @@ def cpu_loop_rate(n_views, n=4000):
     return n / (time.perf_counter() - t0)
 
 
+def _cpu_decode_worker(args):
+    n_maps, seed, reps = args
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    from mc3d_b200 import synthetic as syn
+    from oracle import decode as D
+    hm, _ = syn.gaussian_blob_heatmaps(n_maps, seed=seed)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        D.heatmap_means_cov(hm.copy())                   # upstream thresholds its input in place (Q7): a fresh copy per call
+        D.argmax_decode(hm)
+    return n_maps * reps, time.perf_counter() - t0
+
+
+def cpu_decode_baseline(per_worker=1700, reps=100, workers=None):
+    """Oracle port of get_heatmap_means_cov (mmpose_pose_estimation.py:163-215) + the argmax decode, all host cores."""
+    import multiprocessing as mp
+    workers = workers or (os.cpu_count() or 1)
+    with mp.get_context('spawn').Pool(workers) as pool:
+        pool.map(_cpu_decode_worker, [(17, 1, 1)] * workers)          # imports, untimed
+        res = pool.map(_cpu_decode_worker, [(per_worker, 50 + i, reps) for i in range(workers)])
+    wall = max(r[1] for r in res)
+    maps = sum(r[0] for r in res)
+    return {'value': maps / wall, 'unit': 'heatmaps/s', 'cores': workers, 'kind': 'port',
+            'sample': f'{maps} maps of 64x48 ({maps // workers} per worker x {workers} workers), {wall:.1f} s; numpy oracle of '
+                      'get_heatmap_means_cov + argmax decode', 'frames_per_s_4views_17joints': maps / wall / 68.0}
+
+
+def cpu_refine_baseline():
+    """Oracle port of sgd_optimize (closed-form numpy loss + gradient + Adam, pose_refinement.py:894-1096) on one host
+    core at the sizes BASELINE.md section 3.1 names; the reference itself (torch autograd + a Python loop over frames)
+    ran ~10 it/s at T = 400 in the survey's probe."""
+    from mc3d_b200 import synthetic as syn
+    from oracle import refine as R
+    out = {}
+    for T_, iters in ((400, 600), (4000, 120)):
+        gs, init, cams, _ = syn.refinement_inputs(T_, n_cams=2, seed=0)
+        kw = dict(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1.0, time_interval=[0, T_], patience=10 ** 9, dtype=np.float32)
+        R.sgd_optimize(gs, init, list(cams.values()), syn.EXAMPLE_BODY_LENGTHS, max_iter=1, **kw)      # warm-up
+        t0 = time.perf_counter()
+        R.sgd_optimize(gs, init, list(cams.values()), syn.EXAMPLE_BODY_LENGTHS, max_iter=iters - 1, **kw)
+        dt = time.perf_counter() - t0
+        out[f'T{T_}'] = {'value': iters / dt, 'unit': 'iterations/s', 'cores': 1, 'kind': 'port',
+                         'sample': f'{iters} iterations of {T_} frames x 17 joints x 2 cameras, {dt:.1f} s; numpy oracle of sgd_optimize'}
+    return out
+
+
+def workload_config(name):
+    """`config` of the JSON line: the same dict in both arms (the driver compares them)."""
+    frames, n_views, io = WORKLOADS[name]
+    esize = 4 if io == 'f32' else 8
+    n = frames * JOINTS
+    return {'workload': name, 'views': n_views, 'joints_per_frame': JOINTS, 'frames_per_gpu': frames,
+            'joints_per_gpu': n, 'io_dtype': io, 'layout': '(N, V, 3) [x, y, w]', 'mode': 'weighted',
+            'l2': f'inputs {n * 3 * n_views * esize / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)',
+            'sharding': 'frames across ranks, no collective'}
+
+
 def measured_peak():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -210,11 +276,11 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': 'joints_triangulated_per_sec', 'value': value, 'unit': 'joints/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(1, args.steps),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'views': n_views, 'joints_per_frame': JOINTS,
-                   'frames_per_gpu': frames, 'io_dtype': io,
-                   'note': 'CPU arm: numpy oracle port of the reference DLT (batched LAPACK SVD of A^T A, utils.py:19-34 '
-                           f'generalised to V weighted views) on a bounded sample of {per_worker} joints per worker per step; '
-                           'the reference itself is pure Python without a V-view path and is not pip-installable (no setup.py)'},
+        'config': workload_config(args.workload),
+        'note': 'CPU arm: numpy oracle port of the reference DLT (batched LAPACK SVD of A^T A, utils.py:19-34 generalised to V '
+                f'weighted views, float64 arithmetic on the float32-rounded input) on a bounded sample of {per_worker} joints per '
+                'worker per step of the same workload; the reference itself is pure Python without a V-view path and is not '
+                'pip-installable (no setup.py)',
         'cpu_baseline': {'value': value, 'unit': 'joints/s', 'cores': workers, 'kind': 'port',
                          'sample': f'{per_worker} joints x {workers} workers per step, {args.steps} steps'},
         'e2e': {'value': value, 'unit': 'joints/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -317,71 +383,223 @@ def run_ours(args, rank, local_rank, world):
     except Exception as exc:            # report, do not hide
         e2e = {'value': None, 'unit': 'joints/s', 'error': repr(exc)}
 
-    refine_mgpu = None
-    if world > 1 and not args.no_refine:
-        # config 4 sharded over the ranks: 100 000 frames in total, halos + 2 scalar all-reduces per step over NCCL
-        del kp, out
-        torch.cuda.empty_cache()
+    # ---- the box's host <-> device link, measured beside the e2e number (all ranks at once) ------------------------
+    if e2e is not None and e2e.get('value'):
         try:
-            refine_mgpu = refine_benchmark(100_000, 400, 'f32', device, world=world)
+            link = host_link_bandwidth(device, world)
+            ceiling = link['h2d_GBs'] * 1e9 / (3 * n_views * esize)
+            e2e['host_link'] = link
+            e2e['ceiling_joints_per_s'] = ceiling
+            e2e['frac_of_ceiling'] = e2e['value'] / ceiling
+            e2e['ceiling_note'] = ('every joint needs 3V scalars host -> device and 3 back; the ceiling is the measured aggregate pinned '
+                                   'H2D bandwidth of this box with all ranks copying at once, divided by the input bytes per joint')
         except Exception as exc:
-            refine_mgpu = {'error': repr(exc)}
+            e2e['host_link'] = {'error': repr(exc)}
+
+    del kp, out
+    torch.cuda.empty_cache()
+    peak, peak_src = measured_peak()
+    refine = None
+    mgpu_ok = True
+    if not args.no_refine:
+        try:
+            refine = {}
+            key = 'T100k_f32' if world == 1 else f'T100k_f32_sharded_over_{world}_gpus'
+            refine[key] = refine_benchmark(100_000, 400, 'f32', device, world=world, peak=peak)
+            if world == 1:
+                refine['T400_f32'] = refine_benchmark(400, 2000, 'f32', device, peak=peak)
+                for nf in (50_000, 25_000, 12_500):     # the per-GPU shard sizes of config 4 at 2 / 4 / 8 GPUs, alone on one GPU
+                    refine[f'T{nf}_f32'] = refine_benchmark(nf, 400, 'f32', device, peak=peak)
+            else:
+                refine['vs_single_gpu'] = refine_sharded_vs_single(device, rank, world)
+                mgpu_ok = bool(refine['vs_single_gpu'].get('ok', False))
+        except Exception as exc:
+            refine = {'error': repr(exc)}
+            mgpu_ok = world == 1
+    extras = None
+    if not args.no_extras:
+        try:
+            extras = extra_measurements(device, peak, rank, world)
+        except Exception as exc:
+            extras = {'error': repr(exc)}
 
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+        if not mgpu_ok:
+            sys.exit(3)
         return
 
-    peak, peak_src = measured_peak()
     line = {
         'metric': 'joints_triangulated_per_sec', 'value': value, 'unit': 'joints/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32+f64' if io == 'f32' else 'f64',     # f32 storage: float normal equations, double residuals
         'data': 'synthetic',
-        'config': {'workload': args.workload, 'views': n_views, 'joints_per_frame': JOINTS, 'frames_per_gpu': frames,
-                   'joints_per_gpu': n, 'io_dtype': io, 'layout': '(N, V, 3) [x, y, w]', 'mode': 'weighted',
-                   'l2': f'inputs {n * 3 * n_views * esize / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)',
-                   'sharding': 'frames across ranks, no collective'},
+        'config': workload_config(args.workload),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': recorded_traffic(args.workload), 'peak_source': peak_src,
                      'algorithmic_bytes_per_joint': algo_bytes_per_joint,
-                     'kernel': f'mc3d::triangulate_mixed_kernel<{n_views}, layout>' if io == 'f32' else f'mc3d::triangulate_kernel<double, {n_views}, weighted>',
+                     'kernel': f'mc3d::triangulate_mixed_kernel<{n_views}, layout>' if io == 'f32' else f'mc3d::triangulate_lean64_kernel<{n_views}, layout>',
                      'frac_of_nominal_8TBs': achieved / 8000.0},
         'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }
-    if refine_mgpu is not None:
-        line['refine'] = {f'T100k_f32_sharded_over_{world}_gpus': refine_mgpu}
-    if world == 1 and not args.no_refine:
-        try:
-            line['refine'] = {'T100k_f32': refine_benchmark(100_000, 400, 'f32', device),
-                              'T400_f32': refine_benchmark(400, 2000, 'f32', device)}
-            # the per-GPU shard sizes of config 4 at 2 / 4 / 8 GPUs, on one GPU (no exchange partner)
-            for nf in (50_000, 25_000, 12_500):
-                line['refine'][f'T{nf}_f32'] = refine_benchmark(nf, 400, 'f32', device)
-        except Exception as exc:
-            line['refine'] = {'error': repr(exc)}
+    if refine is not None:
+        line['refine'] = refine
+    if extras is not None:
+        line['other_configs'] = extras
     if world == 1 and not args.no_extras:
-        del kp, out
-        torch.cuda.empty_cache()
         try:
-            line['other_configs'] = extra_measurements(device, peak)
+            line['occlusion'] = occlusion_sweep(device, n_views, tdtype, peak, algo_bytes_per_joint)
         except Exception as exc:
-            line['other_configs'] = {'error': repr(exc)}
+            line['occlusion'] = {'error': repr(exc)}
     if world == 1 and not args.no_cpu:
         rate, workers, joints, wall = cpu_baseline_run(n_views)
         line['cpu_baseline'] = {'value': rate, 'unit': 'joints/s', 'cores': workers, 'kind': 'port',
                                 'sample': f'{joints} joints ({joints // workers} per worker x {workers} workers), '
                                           f'{wall:.1f} s; numpy oracle: batched LAPACK SVD of A^T A',
                                 'reference_style_loop_joints_per_s_1core': cpu_loop_rate(n_views)}
+        try:                                             # the other two kernels' CPU figures, same box
+            dec = cpu_decode_baseline()
+            ref = cpu_refine_baseline()
+            line['cpu_baseline']['decode'] = dec
+            line['cpu_baseline']['refine'] = ref
+            if extras and 'decode_tri4_coco17' in extras:
+                extras['decode_tri4_coco17']['cpu_baseline'] = dec
+            if refine and 'T400_f32' in refine:
+                refine['T400_f32']['cpu_baseline'] = ref['T400']
+                refine['T100k_f32']['cpu_baseline'] = dict(ref['T4000'], note='largest size the CPU port is timed at (T = 4 000); its time '
+                                                           'per iteration grows linearly with T')
+        except Exception as exc:
+            line['cpu_baseline']['others_error'] = repr(exc)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not mgpu_ok:
+        sys.exit(3)
 
 
-def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0):
+def _max_over_ranks(value, device, world):
+    if world <= 1:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sync_all(world):
+    import torch
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+
+def host_link_bandwidth(device, world, nbytes=256 << 20, reps=4):
+    """Aggregate pinned-memory copy bandwidth of this box, every rank copying at the same time: H2D alone, D2H alone, both."""
+    import torch
+    h_a = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_b = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+    def timed(fn):
+        fn()
+        _sync_all(world)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        dt = _max_over_ranks(time.perf_counter() - t0, device, world)
+        _sync_all(world)
+        return world * nbytes * reps / dt / 1e9
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+
+    def both():
+        h2d()
+        d2h()
+
+    out = {'h2d_GBs': timed(h2d), 'd2h_GBs': timed(d2h), 'bidirectional_GBs_each_way': timed(both), 'ranks': world,
+           'bytes_per_copy': nbytes, 'note': 'aggregate over the ranks, pinned host memory, cudaMemcpyAsync'}
+    return out
+
+
+def occlusion_sweep(device, n_views, tdtype, peak, bytes_per_joint, n=17_000_000):
+    """Throughput when a fraction of all views is unusable (weight 0, wild pixel): a joint whose first starting pair holds such
+    a view takes the second pair; a warp pays another pass only when both pairs of one of its joints fail."""
+    import torch
+    from mc3d_b200.triangulation import triangulate_multiview
+    kp, P = make_triangulation_workload(n, n_views, tdtype, device, seed=77)
+    res = torch.empty((n, 3), dtype=tdtype, device=device)
+    out = {}
+    for frac in (0.0, 0.01, 0.05, 0.2):
+        k2 = kp.clone()
+        if frac:
+            gen = torch.Generator(device=device).manual_seed(3)
+            bad = torch.rand((n, n_views), device=device, generator=gen) < frac
+            k2[..., 2][bad] = 0.0
+            k2[..., 0][bad] = 5000.0 * torch.rand((int(bad.sum()),), device=device, generator=gen).to(tdtype)
+            k2[..., 1][bad] = 5000.0 * torch.rand((int(bad.sum()),), device=device, generator=gen).to(tdtype)
+        ms = _time_launches(lambda: triangulate_multiview(k2, P, out=res), 10)
+        out[f'{frac:.2f}'] = {'joints_per_s': n / ms * 1e3, 'roofline_frac': n * bytes_per_joint / ms / 1e6 / peak,
+                              'finite_outputs': float(torch.isfinite(res).all(dim=1).float().mean())}
+        del k2
+    out['joints'] = n
+    return out
+
+
+def refine_sharded_vs_single(device, rank, world, n_frames=100_000, iters=60):
+    """Config 4 sharded over the ranks against the SAME problem on one GPU (rank 0): cost history and final trajectory.
+    Float state: the two runs add their 17 global sums in different orders, so they agree to rounding, not bit for bit."""
+    import torch
+    from mc3d_b200 import refinement as rf
+    from mc3d_b200 import synthetic as syn
+    gs, init, cams, _ = syn.refinement_inputs(n_frames, n_cams=2, seed=11)
+    rows = rf.camera_rows(cams, list(cams))
+
+    def run(comm):
+        eng = rf.RefineEngine(init, gs, rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=torch.float32, device=device, lr=0.01,
+                              betas=(0.9, 0.999), lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
+                              max_iter=10 ** 9, ignore_distortions=False, window=(0, n_frames), n_window_frames=n_frames,
+                              hist_capacity=iters + 8, comm=comm)
+        eng.run(iters)
+        torch.cuda.synchronize()
+        hist = eng.history(iters)[:, 0].copy()
+        traj = eng.trajectory()                       # gathers the shards (collective when sharded)
+        traj = traj.cpu().numpy() if hasattr(traj, 'cpu') else np.asarray(traj)
+        peer = eng.peer is not None
+        eng.close()
+        return hist, traj, peer
+
+    h_sh, x_sh, peer = run(rf.DistComm())
+    out = {'frames': n_frames, 'iters': iters, 'dtype': 'f32', 'world': world, 'in_kernel_exchange': peer}
+    if rank == 0:
+        h_1, x_1, _ = run(rf.LocalComm())
+        hist_rel = float(np.max(np.abs(h_sh - h_1) / np.abs(h_1)))
+        moved = float(np.max(np.abs(x_1 - np.asarray(init, dtype=np.float32))))
+        traj_abs = float(np.max(np.abs(x_sh - x_1)))
+        traj_rel = traj_abs / float(np.max(np.abs(x_1)))
+        worst = max(hist_rel, traj_rel)
+        out.update({'max_rel_diff_vs_single_gpu': worst, 'cost_history_rel_diff': hist_rel, 'trajectory_abs_diff_mm': traj_abs,
+                    'trajectory_rel_diff': traj_rel, 'largest_move_mm': moved, 'tolerance': 1e-6, 'ok': bool(worst <= 1e-6)})
+    flag = torch.tensor([1.0 if out.get('ok', True) else 0.0], device=device)
+    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+    out['ok'] = bool(flag.item() == 1.0)
+    return out
+
+
+def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0, peak=None):
     """Config 4 shape: refinement iterations per second on `n_frames` frames x 17 joints x 2 cameras
     (lambda_smooth=1e-6, lambda_body_length=1, lr=0.01).  Returns a dict for the JSON line."""
     import torch
@@ -417,14 +635,26 @@ def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0):
     plan = eng.plan()
     eng.close()
     esize = 4 if dtype_name == 'f32' else 8
-    # per joint-frame and iteration: A reads x, mu0, S (8 scalars); B reads the same and writes g (11); C reads g, x, m, v
-    # and writes x, m, v (+ best when improved) (21..24)
-    algo = n_frames * 17 * (8 + 11 + 21) * esize
-    return {'frames': n_frames, 'iters': iters, 'dtype': dtype_name, 'iters_per_s': iters / (ms * 1e-3), 'us_per_iter': 1e3 * ms / iters,
-            'algorithmic_bytes_per_iter': algo, 'achieved_GBs': algo / (ms * 1e-3 / iters) / 1e9,
-            'cost_first': float(hist[0, 0]), 'cost_last': float(hist[-1, 0]), 'step': plan, 'world': world,
-            'exchange': exchange, 'nccl_collectives_per_iter': 3 if exchange.startswith('NCCL') else 0,
-            'multi_rank_cuda_graph': graphed}
+    # per joint-frame and iteration read x, m, v, mu0, S (15 scalars) and write x, m, v (9), plus the gradient
+    # written and read once when the step is split in passes (6): 30 scalars = 120 B in float.  The shipped two-phase step
+    # stores FOUR gradient components and moves 50 scalars = 200 B.
+    us = 1e3 * ms / iters
+    algo = n_frames * 17 * 30 * esize
+    moved = n_frames * 17 * 50 * esize
+    per_gpu = algo / world
+    out = {'frames': n_frames, 'iters': iters, 'dtype': dtype_name, 'iters_per_s': iters / (ms * 1e-3), 'us_per_iter': us,
+           'algorithmic_bytes_per_iter': algo, 'moved_bytes_per_iter_two_phase': moved,
+           'cost_first': float(hist[0, 0]), 'cost_last': float(hist[-1, 0]), 'step': plan, 'world': world,
+           'exchange': exchange, 'nccl_collectives_per_iter': 3 if exchange.startswith('NCCL') else 0,
+           'multi_rank_cuda_graph': graphed}
+    if peak:
+        gbs = per_gpu / (us * 1e-6) / 1e9
+        out['roofline'] = {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
+                           'algorithmic_bytes_per_joint_frame': 30 * esize, 'moved_bytes_per_joint_frame': 50 * esize,
+                           'per': 'GPU', 'kernel': 'mc3d::refine_fused2_kernel (pass 1: costs + gradient components; pass 2: clip + Adam)',
+                           'note': 'a shard of 12 500 .. 25 000 frames (25 .. 50 MB of state) is L2-resident and the step is bound by '
+                                   'latency (two grid barriers, one cross-rank exchange), not by HBM'}
+    return out
 
 
 def _time_launches(fn, reps):
@@ -440,38 +670,63 @@ def _time_launches(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
-def extra_measurements(device, peak):
-    """The other BASELINE.json configs, measured briefly on one GPU (inputs resident, CUDA events):
-    config 2 in float64, config 5 (COCO-WholeBody 133 joints x 16 views, point-count sweep) and config 3
-    (heatmap decode 17x64x48 x 4 views feeding the triangulation)."""
+def _time_max(fn, reps, device, world):
+    """Average ms per call of fn over `reps` calls (CUDA events), max over the ranks."""
+    import torch
+    fn()
+    _sync_all(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return _max_over_ranks(e0.elapsed_time(e1) / reps, device, world)
+
+
+def _roof(bytes_per_gpu, ms, peak, **more):
+    gbs = bytes_per_gpu / ms / 1e6
+    return dict({'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak, 'per': 'GPU'}, **more)
+
+
+def extra_measurements(device, peak, rank=0, world=1):
+    """The other BASELINE.json configs (inputs resident, CUDA events, every rank on its shard, times = max over ranks):
+    config 2 in float64 at its full 10 M frames per GPU, config 5 (COCO-WholeBody 133 joints x 16 views: a total of 1e6 .. 1e9
+    points sharded over the ranks) and config 3 (heatmap decode 17x64x48 x 4 views feeding the triangulation)."""
     import torch
     from mc3d_b200.decode import decode_heatmaps
     from mc3d_b200.triangulation import triangulate_multiview
     out = {}
-    # config 2, float64 storage
-    n = 4_000_000 * JOINTS
-    kp, P = make_triangulation_workload(n, 8, torch.float64, device, seed=5)
+    # config 2, float64 storage, 10 M frames per GPU (weak scaling like the headline)
+    n = 10_000_000 * JOINTS
+    kp, P = make_triangulation_workload(n, 8, torch.float64, device, seed=5 + rank)
     res = torch.empty((n, 3), dtype=torch.float64, device=device)
-    ms = _time_launches(lambda: triangulate_multiview(kp, P, out=res), 5)
-    gbs = n * 216 / ms / 1e6
-    out['tri8_coco17_f64'] = {'joints': n, 'joints_per_s': n / ms * 1e3, 'GBs': gbs, 'roofline_frac': gbs / peak,
-                              'algorithmic_bytes_per_joint': 216}
+    ms = _time_max(lambda: triangulate_multiview(kp, P, out=res), 5, device, world)
+    out['tri8_coco17_10Mframes_f64'] = {'joints_per_gpu': n, 'joints_per_s': world * n / ms * 1e3, 'ms_per_launch': ms,
+                                        'roofline': _roof(n * 216, ms, peak, algorithmic_bytes_per_joint=216,
+                                                          kernel='mc3d::triangulate_lean64_kernel<8, layout>'), 'n_gpus': world}
     del kp, res
-    # config 5: 16 views, WholeBody; points = frames x 133
+    torch.cuda.empty_cache()
+    # config 5: 16 views, WholeBody; a TOTAL of `total` points, sharded over the ranks (strong scaling)
     sweep = {}
-    for npts in (1_000_000, 10_000_000, 100_000_000):
+    for total in (1_000_000, 10_000_000, 100_000_000, 1_000_000_000):
         for io, dt, es in (('f32', torch.float32, 4), ('f64', torch.float64, 8)):
-            if npts * 51 * es > 45e9:
+            shard = total // world
+            key = f'{total:.0e}_{io}'
+            if shard * 54 * es > 150e9:
+                sweep[key] = {'skipped': f'{shard * 54 * es / 1e9:.0f} GB per GPU does not fit in 180 GB of HBM beside the workspace: '
+                                         'needs more ranks'}
                 continue
-            kp, P = make_triangulation_workload(npts, 16, dt, device, seed=6)
-            res = torch.empty((npts, 3), dtype=dt, device=device)
-            ms = _time_launches(lambda: triangulate_multiview(kp, P, out=res), 3)
-            gbs = npts * 51 * es / ms / 1e6
-            sweep[f'{npts:.0e}_{io}'] = {'points_per_s': npts / ms * 1e3, 'GBs': gbs, 'roofline_frac': gbs / peak}
+            kp, P = make_triangulation_workload(shard, 16, dt, device, seed=6 + rank)
+            res = torch.empty((shard, 3), dtype=dt, device=device)
+            ms = _time_max(lambda: triangulate_multiview(kp, P, out=res), 3, device, world)
+            sweep[key] = {'points_per_s': world * shard / ms * 1e3, 'points_per_gpu': shard, 'ms_per_launch': ms,
+                          'roofline': _roof(shard * 51 * es, ms, peak, algorithmic_bytes_per_point=51 * es)}
             del kp, res
-    out['tri16_wholebody133'] = {'algorithmic_bytes_per_point': {'f32': 204, 'f64': 408}, 'sweep': sweep,
-                                 'note': '1e9 points = 204 GB in float32: sharded over >= 2 GPUs (frames across ranks)'}
-    # config 3: decode (17 x 64 x 48 per view, 4 views) + triangulation; 16 384 frames resident, re-used as a stream
+            torch.cuda.empty_cache()
+    out['tri16_wholebody133'] = {'scaling': 'strong (total points fixed, sharded over the ranks, no collective)', 'n_gpus': world, 'sweep': sweep,
+                                 'kernels': 'mc3d::triangulate_mixed_kernel<16, layout> (f32), mc3d::triangulate_kernel<double, 16, weighted> (f64)'}
+    # config 3: decode (17 x 64 x 48 per view, 4 views) + triangulation; 16 384 frames resident per GPU, re-used as a stream
     T_, C = 16_384, 4
     hm = torch.rand((T_, C, JOINTS, 64, 48), device=device) * 0.02
     cy = torch.randint(8, 56, (T_, C, JOINTS), device=device)
@@ -490,16 +745,22 @@ def extra_measurements(device, peak):
         kpts, _ = decode_heatmaps(hm, want_moments=False, kpt_layout='nv3', affine=aff, affine_group=JOINTS)
         triangulate_multiview(kpts, P4, out=res)
 
-    ms = _time_launches(step, 5)
+    ms = _time_max(step, 5, device, world)
     in_bytes = hm.numel() * 4
-    both = _time_launches(lambda: decode_heatmaps(hm, kpt_layout='nv3', affine=aff, affine_group=JOINTS), 5)
-    out['decode_tri4_coco17'] = {'frames_resident': T_, 'frames_per_s': T_ / ms * 1e3, 'joints_per_s': T_ * JOINTS / ms * 1e3,
-                                 'GBs': in_bytes / ms / 1e6, 'roofline_frac': in_bytes / ms / 1e6 / peak,
-                                 'algorithmic_bytes_per_frame': 835_584 + 204,
-                                 'decode_kpts_plus_moments_GBs': in_bytes / both / 1e6,
-                                 'time_for_1M_frames_s': 1e6 / (T_ / ms * 1e3),
-                                 'note': '1 M frames = 835.6 GB of heatmaps: streamed through HBM in 16 384-frame chunks; '
-                                         'the resident chunk (13.7 GB >> L2) is re-used for timing'}
+    both = _time_max(lambda: decode_heatmaps(hm, kpt_layout='nv3', affine=aff, affine_group=JOINTS), 5, device, world)
+    bytes_per_frame = 835_584 + 204
+    out['decode_tri4_coco17'] = {'frames_resident_per_gpu': T_, 'frames_per_s': world * T_ / ms * 1e3,
+                                 'joints_per_s': world * T_ * JOINTS / ms * 1e3, 'n_gpus': world,
+                                 'roofline': _roof(T_ * bytes_per_frame, ms, peak, algorithmic_bytes_per_frame=bytes_per_frame,
+                                                   kernel='mc3d::decode_reg6448_kernel<false> + mc3d::triangulate_mixed_kernel<4, layout>'),
+                                 'decode_kpts_plus_moments': {'frames_per_s': world * T_ / both * 1e3,
+                                                              'roofline': _roof(T_ * (835_584 + 4 * 17 * (12 + 48)), both, peak,
+                                                                                kernel='mc3d::decode_reg6448_kernel<true>')},
+                                 'time_for_1M_frames_s': 1e6 / (world * T_ / ms * 1e3),
+                                 'note': '1 M frames = 835.6 GB of heatmaps, sharded over the ranks and streamed through HBM in 16 384-frame '
+                                         'chunks; the resident chunk (13.7 GB >> L2) is re-used for timing'}
+    del hm, res
+    torch.cuda.empty_cache()
     return out
 
 
