@@ -2,6 +2,8 @@
 #include "mc3d_common.cuh"
 #include <atomic>
 #include <mutex>
+#include <set>
+#include <utility>
 #include <string.h>
 
 namespace mc3d {
@@ -33,6 +35,23 @@ int sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    return dev;
+}
+
+int func_max_smem_once(const void *func, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void *>> done;
+    const int dev = current_device_slot();
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({dev, func})) return MC3D_OK;
+    MC3D_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert({dev, func});
+    return MC3D_OK;
 }
 
 template <typename T>

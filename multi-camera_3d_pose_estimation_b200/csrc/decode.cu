@@ -409,11 +409,7 @@ int decode_device(const float *d_hm, long long n_maps, int H, int W, float thr, 
         while (warps > 1 && (size_t)warps * stages * map_bytes > budget) warps >>= 1;
         while ((size_t)warps * (stages + 1) * map_bytes <= budget && stages < 4) ++stages;
         const size_t smem = (size_t)warps * stages * map_bytes + (size_t)warps * 8 * sizeof(uint64_t);
-        static bool attr_done = false;
-        if (!attr_done) {
-            MC3D_CUDA_TRY(cudaFuncSetAttribute(decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_done = true;
-        }
+        { const int as = func_max_smem_once((const void *)decode_tma_kernel, 227 * 1024); if (as != MC3D_OK) return as; }
         long long grid = sm_count();
         const long long need = (n_maps + warps - 1) / warps;
         if (grid > need) grid = need;

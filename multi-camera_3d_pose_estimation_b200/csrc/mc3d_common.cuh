@@ -26,6 +26,10 @@ void count_launch(int n = 1);
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();   // cached SM count of the current device (148 on B200)
+int current_device_slot();   // ordinal of the current device clamped to [0, 64): index of per-device caches
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (device, kernel), not once per
+// process (a process that works on two devices would otherwise launch with the 48 KB default on the second one).
+int func_max_smem_once(const void *func, int bytes);
 
 // ---- PTX wrappers (device) ---------------------------------------------------------------
 #ifdef __CUDACC__

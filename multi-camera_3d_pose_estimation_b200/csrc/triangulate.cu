@@ -1166,11 +1166,7 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
     const int nv = prm.n_views;
     const size_t stage_bytes = tri_stage_elems(TRI_TILE, 3 * nv, (int)sizeof(T)) * sizeof(T);
     auto kern = triangulate_kernel<T, V, MODE, UNDISTORT>;
-    static bool attr_done = false;     // per instantiation
-    if (!attr_done) {
-        MC3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    { const int as = func_max_smem_once((const void *)kern, 227 * 1024); if (as != MC3D_OK) return as; }
     // The kernel is bound by fp64 latency, not by bytes in flight: prefer more resident CTAs (warps) over a
     // deeper ring; 2 stages already cover the HBM latency at this arithmetic intensity.
     const size_t fixed = TRI_TILE * 3 * sizeof(T) + 8 * sizeof(uint64_t) +
@@ -1193,15 +1189,14 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
             const long long n_full = n / TRI_TILE, tail = n - n_full * TRI_TILE;
             long long lgrid = (long long)sm_count() * per_sm;
             if (lgrid > n_full) lgrid = n_full;
-            static bool lean_attr_done[2] = {false, false};
             const int li = prm.layout == MC3D_LAYOUT_3V ? 1 : 0;
             if (li) {
                 auto lean = triangulate_lean64_kernel<V, MC3D_LAYOUT_3V>;
-                if (!lean_attr_done[li]) { MC3D_CUDA_TRY(cudaFuncSetAttribute(lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); lean_attr_done[li] = true; }
+                { const int as = func_max_smem_once((const void *)lean, 227 * 1024); if (as != MC3D_OK) return as; }
                 lean<<<(unsigned)lgrid, TRI_TILE, smem, stream>>>(d_kpts, d_out, (unsigned)n_full, n_stages, prm);
             } else {
                 auto lean = triangulate_lean64_kernel<V, MC3D_LAYOUT_V3>;
-                if (!lean_attr_done[li]) { MC3D_CUDA_TRY(cudaFuncSetAttribute(lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); lean_attr_done[li] = true; }
+                { const int as = func_max_smem_once((const void *)lean, 227 * 1024); if (as != MC3D_OK) return as; }
                 lean<<<(unsigned)lgrid, TRI_TILE, smem, stream>>>(d_kpts, d_out, (unsigned)n_full, n_stages, prm);
             }
             count_launch();
@@ -1232,9 +1227,10 @@ static int launch_mixed(const float *d_kpts, long long n, const TriParams &prm, 
                             2 * sizeof(mc3d_tri_start_pair);
     static_assert(smem <= 227 * 1024, "mixed kernel: shared memory");
     auto kern = triangulate_mixed_kernel<V, LAYOUT>;
-    static int per_sm = 0;
+    { const int as = func_max_smem_once((const void *)kern, 227 * 1024); if (as != MC3D_OK) return as; }
+    static int per_sm_cache[64] = {0};                                     // per device (this instantiation)
+    int &per_sm = per_sm_cache[current_device_slot()];
     if (per_sm == 0) {
-        MC3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int occ = 0;
         MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TRI_MTHREADS, smem));
         if (occ < 1) { set_error("mixed triangulate kernel does not fit on an SM"); return MC3D_ERR_UNSUPPORTED; }
