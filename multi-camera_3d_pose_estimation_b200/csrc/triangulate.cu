@@ -1069,48 +1069,49 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
     return MC3D_OK;
 }
 
-// ---- lean tile loop for double storage -------------------------------------------------------
-// The generic kernel above spends ~170 of its ~1 030 instructions per joint on per-tile bookkeeping (one joint per thread,
-// so nothing amortises it).  This one is the weighted, undistortion-free, compile-time-V, contiguous-tile case only: full
-// tiles (the host launches the generic kernel on the ragged tail), layout as a template parameter, global addresses computed
-// in thread 0's branches.  Same accumulation order, same solver: bit-identical results.
+// ---- warp-pipelined kernel for double storage -----------------------------------------------------------------------------
+// The weighted, undistortion-free, compile-time-even-V case of the generic kernel above with the data path of the mixed
+// kernel: every warp is its own pipeline (private two-stage ring of 32-joint tiles filled by 1-D TMA bulk copies, private
+// output tile, TMA bulk store), one joint per lane, no block-wide barrier after the set-up and none of the generic kernel's
+// per-tile bookkeeping (~170 of its ~1 030 instructions per joint).  Same accumulation order, same solver: results are
+// bit-identical to the generic kernel's.  The ragged tail (< 32 joints) is one more tile of the next warp in line.
+constexpr int TRI_W64_WARPS = 4;
+constexpr int TRI_W64_TILE = 32;
+
 template <int V, int LAYOUT>
-__global__ void __launch_bounds__(TRI_TILE, (V <= 8) ? 3 : 2)
-triangulate_lean64_kernel(const double *__restrict__ kpts, double *__restrict__ out, unsigned n_tiles, int n_stages,
+__global__ void __launch_bounds__(32 * TRI_W64_WARPS, 4)
+triangulate_warp64_kernel(const double *__restrict__ kpts, double *__restrict__ out, long long n,
                           const __grid_constant__ TriParams prm) {
     static_assert(V > 0 && V % 2 == 0, "even compile-time view count");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int row_elems = 3 * V;
-    constexpr uint32_t stage_bytes = (uint32_t)(TRI_TILE * row_elems * sizeof(double));
-    constexpr uint32_t otile_bytes = (uint32_t)(TRI_TILE * 3 * sizeof(double));
-    static_assert((row_elems * sizeof(double)) % 128 != 0, "padded row plans use the generic kernel");
-    unsigned char *ring = smem_raw;
-    double *otile = reinterpret_cast<double *>(smem_raw + (size_t)n_stages * stage_bytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)n_stages * stage_bytes + otile_bytes);
-    const int tid = threadIdx.x;
-    const unsigned first = blockIdx.x, stride = gridDim.x;
-    const unsigned my_tiles = (first < n_tiles) ? (n_tiles - first + stride - 1) / stride : 0;
-    if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
+    constexpr uint32_t stage_bytes = (uint32_t)(TRI_W64_TILE * row_elems * sizeof(double));
+    constexpr uint32_t otile_bytes = (uint32_t)(TRI_W64_TILE * 3 * sizeof(double));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // layout: [warp][2] input stages | [warp][2] output tiles | [warp][2] mbarriers
+    unsigned char *ring = smem_raw + (size_t)warp * 2 * stage_bytes;
+    double *otile = reinterpret_cast<double *>(smem_raw + (size_t)TRI_W64_WARPS * 2 * stage_bytes + (size_t)warp * 2 * otile_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)TRI_W64_WARPS * 2 * (stage_bytes + otile_bytes)) + warp * 2;
+    if (lane == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
         fence_mbar_init();
     }
-    __syncthreads();
-    auto load_tile = [&](unsigned i, int st) {
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(kpts) + ((size_t)first + (size_t)i * stride) * stage_bytes;
-        mbar_arrive_expect_tx(&full[st], stage_bytes);
-        bulk_g2s(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st]);
-    };
-    if (tid == 0)
-        for (unsigned i = 0; i < (unsigned)(n_stages - 1) && i < my_tiles; ++i) load_tile(i, (int)i);
-    int s = 0, s_next = n_stages - 1;
-    uint32_t parity = 0;
-    for (unsigned k = 0; k < my_tiles; ++k) {
-        if (tid == 0) {
-            if (k + (unsigned)(n_stages - 1) < my_tiles) load_tile(k + (unsigned)(n_stages - 1), s_next);
-            bulk_wait_read<0>();                   // the output tile of iteration k - 1 has left shared memory
-        }
-        const double *rowd = reinterpret_cast<const double *>(ring + (size_t)s * stage_bytes) + tid * row_elems;
-        mbar_wait(&full[s], parity);
+    __syncwarp();
+    const unsigned n_tiles = (unsigned)(n / TRI_W64_TILE);
+    const int tail = (int)(n - (long long)n_tiles * TRI_W64_TILE);
+    const unsigned gw = blockIdx.x * TRI_W64_WARPS + warp, gstride = gridDim.x * TRI_W64_WARPS;
+    const unsigned my_tiles = (gw < n_tiles) ? (n_tiles - gw + gstride - 1) / gstride : 0;
+    const uint32_t ring_sa = smem_u32(ring), full_sa = smem_u32(full), ot_sa = smem_u32(otile);
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(kpts) + (size_t)gw * stage_bytes;
+    unsigned char *dst = reinterpret_cast<unsigned char *>(out) + (size_t)gw * otile_bytes;
+    const uint32_t src_step = gstride * stage_bytes, dst_step = gstride * otile_bytes;
+    if (lane == 0 && my_tiles > 0) {
+        mbar_arrive_expect_tx_sa(full_sa, stage_bytes);
+        bulk_g2s_sa(ring_sa, src, stage_bytes, full_sa);
+    }
+    src += src_step;
+    auto solve_row = [&](const double *rowd, double &X0, double &X1, double &X2) {
         double B[10];
 #pragma unroll
         for (int i = 0; i < 10; ++i) B[i] = 0.0;
@@ -1133,8 +1134,7 @@ triangulate_lean64_kernel(const double *__restrict__ kpts, double *__restrict__ 
             accumulate_view(B, x0, y0, w0, prm.P[v]);
             accumulate_view(B, x1, y1, w1, prm.P[v + 1]);
         }
-        __syncthreads();                           // [A] stage s consumed; thread 0's wait on the previous store is published
-        double X0 = NAN, X1 = NAN, X2 = NAN;
+        X0 = X1 = X2 = NAN;
         const bool finite_in = fabs((B[0] + B[2]) + (B[5] + B[9])) <= 1.0e300;
         if (finite_in && n_used >= 2) {
             bool ok = false;
@@ -1146,19 +1146,43 @@ triangulate_lean64_kernel(const double *__restrict__ kpts, double *__restrict__ 
                 jacobi4_smallest(Bl, X0, X1, X2);
             }
         }
-        otile[tid * 3 + 0] = X0;
-        otile[tid * 3 + 1] = X1;
-        otile[tid * 3 + 2] = X2;
+    };
+    for (unsigned k = 0; k < my_tiles; ++k) {
+        const uint32_t b = k & 1u;
+        if (lane == 0 && k + 1 < my_tiles) {          // refills the stage of iteration k - 1
+            mbar_arrive_expect_tx_sa(full_sa + 8u * (b ^ 1u), stage_bytes);
+            bulk_g2s_sa(ring_sa + (b ^ 1u) * stage_bytes, src, stage_bytes, full_sa + 8u * (b ^ 1u));
+        }
+        src += src_step;
+        const double *rowd = reinterpret_cast<const double *>(ring + b * stage_bytes) + lane * row_elems;
+        mbar_wait_sa(full_sa + 8u * b, (k >> 1) & 1u);
+        double X0, X1, X2;
+        solve_row(rowd, X0, X1, X2);
+        double *ot = otile + b * (TRI_W64_TILE * 3);
+        if (lane == 0) bulk_wait_read<1>();           // the store of iteration k - 2 has left this output buffer
+        __syncwarp();
+        ot[lane * 3 + 0] = X0; ot[lane * 3 + 1] = X1; ot[lane * 3 + 2] = X2;
         fence_proxy_async_smem();
-        __syncthreads();                           // [B] tile complete and visible to the async proxy
-        if (tid == 0) {
-            bulk_s2g(reinterpret_cast<unsigned char *>(out) + ((size_t)first + (size_t)k * stride) * otile_bytes, otile, otile_bytes);
+        __syncwarp();                                 // stage b consumed by every lane; output tile complete
+        if (lane == 0) {
+            bulk_s2g_sa(dst, ot_sa + b * otile_bytes, otile_bytes);
             bulk_commit();
         }
-        if (++s == n_stages) { s = 0; parity ^= 1u; }
-        if (++s_next == n_stages) s_next = 0;
+        dst += dst_step;
     }
-    if (tid == 0) bulk_wait_all<0>();
+    if (tail > 0 && gw == n_tiles % gstride) {        // ragged tail: plain loads and stores
+        double *stage = reinterpret_cast<double *>(ring);
+        const double *tsrc = kpts + (size_t)n_tiles * TRI_W64_TILE * row_elems;
+        for (int i = lane; i < tail * row_elems; i += 32) stage[i] = tsrc[i];
+        __syncwarp();
+        double X0, X1, X2;
+        solve_row(stage + (lane < tail ? lane : 0) * row_elems, X0, X1, X2);
+        if (lane < tail) {
+            double *tdst = out + ((size_t)n_tiles * TRI_W64_TILE + lane) * 3;
+            tdst[0] = X0; tdst[1] = X1; tdst[2] = X2;
+        }
+    }
+    if (lane == 0) bulk_wait_all<0>();
 }
 
 template <typename T, int V, int MODE, bool UNDISTORT>
@@ -1181,32 +1205,28 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
         if (occ > per_sm) { per_sm = occ; n_stages = st; smem = sm_bytes; }
     }
     if (per_sm < 1) { set_error("triangulate kernel does not fit in shared memory (views=%d)", nv); return MC3D_ERR_UNSUPPORTED; }
-    // weighted double storage with a compile-time even view count: full tiles through the lean loop, the ragged tail
-    // through the generic kernel
+    // weighted double storage with a compile-time even view count whose rows need no padded slots: the warp-pipelined kernel
     if constexpr (std::is_same<T, double>::value && MODE == MC3D_TRI_WEIGHTED && !UNDISTORT && V > 0 && V % 2 == 0 &&
-                  (3 * V * sizeof(double)) % 128 != 0) {              // rows of a multiple of 128 bytes use padded slots
-        if (tri_row_plan(3 * V, (int)sizeof(double)).group == 0 && n / TRI_TILE > 0 && n / TRI_TILE < 0x7fffffffLL) {
-            const long long n_full = n / TRI_TILE, tail = n - n_full * TRI_TILE;
-            long long lgrid = (long long)sm_count() * per_sm;
-            if (lgrid > n_full) lgrid = n_full;
-            const int li = prm.layout == MC3D_LAYOUT_3V ? 1 : 0;
-            if (li) {
-                auto lean = triangulate_lean64_kernel<V, MC3D_LAYOUT_3V>;
-                { const int as = func_max_smem_once((const void *)lean, 227 * 1024); if (as != MC3D_OK) return as; }
-                lean<<<(unsigned)lgrid, TRI_TILE, smem, stream>>>(d_kpts, d_out, (unsigned)n_full, n_stages, prm);
-            } else {
-                auto lean = triangulate_lean64_kernel<V, MC3D_LAYOUT_V3>;
-                { const int as = func_max_smem_once((const void *)lean, 227 * 1024); if (as != MC3D_OK) return as; }
-                lean<<<(unsigned)lgrid, TRI_TILE, smem, stream>>>(d_kpts, d_out, (unsigned)n_full, n_stages, prm);
-            }
-            count_launch();
-            MC3D_CUDA_TRY(cudaGetLastError());
-            if (tail > 0) {
-                kern<<<1, TRI_TILE, smem, stream>>>(d_kpts + n_full * TRI_TILE * 3 * V, d_out + n_full * TRI_TILE * 3, tail, n_stages, prm);
+                  (3 * V * sizeof(double)) % 128 != 0) {
+        if (n / TRI_W64_TILE < 0x7fffffffLL) {
+            constexpr size_t smem64 = (size_t)TRI_W64_WARPS * 2 * (TRI_W64_TILE * 3 * V * sizeof(double) + TRI_W64_TILE * 3 * sizeof(double) + sizeof(uint64_t));
+            static_assert(smem64 <= 227 * 1024, "warp64 kernel: shared memory");
+            const long long warp_tiles = (n + TRI_W64_TILE - 1) / TRI_W64_TILE;
+            const long long ctas = (warp_tiles + TRI_W64_WARPS - 1) / TRI_W64_WARPS;
+            auto launch = [&](auto wk) -> int {
+                { const int as = func_max_smem_once((const void *)wk, 227 * 1024); if (as != MC3D_OK) return as; }
+                int occ = 0;
+                MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wk, 32 * TRI_W64_WARPS, smem64));
+                if (occ < 1) { set_error("warp64 triangulate kernel does not fit on an SM"); return MC3D_ERR_UNSUPPORTED; }
+                long long wgrid = (long long)sm_count() * occ;
+                if (wgrid > ctas) wgrid = ctas;
+                wk<<<(unsigned)wgrid, 32 * TRI_W64_WARPS, smem64, stream>>>(d_kpts, d_out, n, prm);
                 count_launch();
                 MC3D_CUDA_TRY(cudaGetLastError());
-            }
-            return MC3D_OK;
+                return MC3D_OK;
+            };
+            if (prm.layout == MC3D_LAYOUT_3V) return launch(triangulate_warp64_kernel<V, MC3D_LAYOUT_3V>);
+            return launch(triangulate_warp64_kernel<V, MC3D_LAYOUT_V3>);
         }
     }
     const long long n_tiles = (n + TRI_TILE - 1) / TRI_TILE;
