@@ -207,6 +207,11 @@ typedef struct {
     int64_t n_frames_left;   /* local frame count of rank - 1 (locates its right halo) */
     int64_t spin_timeout_ns; /* a wait on a peer gives up after this long and sets mc3d_refine_xchg.error */
     void *xchg[MC3D_MAX_PEERS];   /* exchange blocks of all ranks as mapped in this process; xchg[rank] is local */
+    /* 0: camera 0's means and inverse covariances are used for EVERY camera (what upstream computes: pose_refinement.py:663,
+     * :885, quirk Q1) and mu0 / S are (n_frames, J, 2 / 3).  n_frames * n_joints: per-camera Gaussians (the form of the
+     * superseded Trajectory_Optimization, :499) -- mu0 / S are (n_cams, n_frames, J, 2 / 3), one mc3d_refine_prepare_* call
+     * per camera. */
+    int64_t gauss_cam_stride;
 } mc3d_refine_problem;
 
 /* Exchange block at the start of each rank's peer allocation (zero-filled by mc3d_peer_alloc). */

@@ -65,7 +65,8 @@ class RefineProblem(ctypes.Structure):
                 ('g', ctypes.c_void_p), ('mu0', ctypes.c_void_p), ('S', ctypes.c_void_p),
                 ('term_ok', ctypes.c_void_p), ('ctrl', ctypes.c_void_p), ('gc', ctypes.c_void_p),
                 ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('n_frames_left', ctypes.c_int64),
-                ('spin_timeout_ns', ctypes.c_int64), ('xchg', ctypes.c_void_p * MAX_PEERS)]
+                ('spin_timeout_ns', ctypes.c_int64), ('xchg', ctypes.c_void_p * MAX_PEERS),
+                ('gauss_cam_stride', ctypes.c_int64)]
 
 
 class RefineXchg(ctypes.Structure):

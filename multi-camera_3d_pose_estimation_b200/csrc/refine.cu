@@ -312,6 +312,7 @@ __device__ __forceinline__ void costs_loop(const mc3d_refine_problem &pb, const 
     const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones, JS = J * 3;
     const T *x = (const T *)pb.x + 2LL * JS;                       // local frame 0 (halo frames sit before / after)
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
+    const long long gstride = pb.gauss_cam_stride;                 // 0: camera-0 Gaussians for every camera (upstream, Q1)
     const long long n_items = pb.n_frames * J;
     const bool ign = pb.ignore_distortions != 0;
     const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
@@ -323,11 +324,16 @@ __device__ __forceinline__ void costs_loop(const mc3d_refine_problem &pb, const 
         if (t < lo || t >= hi) continue;
         const T *xc = x + e * 3;
         const T X = xc[0], Y = xc[1], Z = xc[2];
-        const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
-        const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
+        T mx = mu0[e * 2], my = mu0[e * 2 + 1];
+        T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
         for (int c = 0; c < C; ++c) {
             T cam[CAM_STRIDE];
             load_camera(camf + c * CAM_STRIDE, cam);
+            if (gstride && c > 0) {                                 // per-camera Gaussians (opt-in; upstream uses camera 0's, Q1)
+                const long long ec = e + c * gstride;
+                mx = mu0[ec * 2]; my = mu0[ec * 2 + 1];
+                s00 = S[ec * 3]; s01 = S[ec * 3 + 1]; s11 = S[ec * 3 + 2];
+            }
             const T q = reproject_term<false, T>(cam, ign, X, Y, Z, mx, my, s00, s01, s11, (T)0, nullptr);
             const bool ok = finite_c(q);
             accf[0] += ok ? q : (T)0;
@@ -394,6 +400,7 @@ __device__ __forceinline__ double grad_loop(const mc3d_refine_problem &pb, const
     const int J = pb.n_joints, C = pb.n_cams, JS = J * 3;
     const T *x = (const T *)pb.x + 2LL * JS;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
+    const long long gstride = pb.gauss_cam_stride;                 // 0: camera-0 Gaussians for every camera (upstream, Q1)
     T *gout = (T *)pb.g;
     const long long n_items = pb.n_frames * J;
     const bool ign = pb.ignore_distortions != 0;
@@ -409,11 +416,16 @@ __device__ __forceinline__ double grad_loop(const mc3d_refine_problem &pb, const
         const T X = xc[0], Y = xc[1], Z = xc[2];
         const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
         if (t >= lo && t < hi && self_ok) {
-            const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
-            const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
+            T mx = mu0[e * 2], my = mu0[e * 2 + 1];
+            T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
             for (int c = 0; c < C; ++c) {
                 T cam[CAM_STRIDE];
                 load_camera(camf + c * CAM_STRIDE, cam);
+                if (gstride && c > 0) {
+                    const long long ec = e + c * gstride;
+                    mx = mu0[ec * 2]; my = mu0[ec * 2 + 1];
+                    s00 = S[ec * 3]; s01 = S[ec * 3 + 1]; s11 = S[ec * 3 + 2];
+                }
                 reproject_term<true, T>(cam, ign, X, Y, Z, mx, my, s00, s01, s11, inv_nlik, g);
             }
             if (do_smooth) {
@@ -719,6 +731,7 @@ __device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, con
     const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones, JS = J * 3;
     const T *x = (const T *)pb.x + 2LL * JS;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
+    const long long gstride = pb.gauss_cam_stride;                 // 0: camera-0 Gaussians for every camera (upstream, Q1)
     const long long n_items = pb.n_frames * J, n3 = gc_stride(pb);
     T *o1 = (T *)pb.gc, *os = o1 + n3, *o2 = os + n3, *o3 = o2 + n3;
     const bool ign = pb.ignore_distortions != 0;
@@ -735,11 +748,16 @@ __device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, con
             const T *xc = x + e * 3;
             const T X = xc[0], Y = xc[1], Z = xc[2];
             const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
-            const T mx = mu0[e * 2], my = mu0[e * 2 + 1];
-            const T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
+            T mx = mu0[e * 2], my = mu0[e * 2 + 1];
+            T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
             for (int c = 0; c < C; ++c) {
                 T cam[CAM_STRIDE];
                 load_camera(camf + c * CAM_STRIDE, cam);
+                if (gstride && c > 0) {
+                    const long long ec = e + c * gstride;
+                    mx = mu0[ec * 2]; my = mu0[ec * 2 + 1];
+                    s00 = S[ec * 3]; s01 = S[ec * 3 + 1]; s11 = S[ec * 3 + 2];
+                }
                 const T q = reproject_term<true, T>(cam, ign, X, Y, Z, mx, my, s00, s01, s11, (T)1, g1);   // adds only when finite
                 const bool ok = finite_c(q);
                 a[0] += ok ? q : (T)0;
@@ -1095,6 +1113,10 @@ static int validate(const mc3d_refine_problem *pb) {
             set_error("in-kernel exchange: every rank needs at least two frames");
             return MC3D_ERR_INVALID_ARGUMENT;
         }
+    }
+    if (pb->gauss_cam_stride != 0 && pb->gauss_cam_stride != pb->n_frames * pb->n_joints) {
+        set_error("gauss_cam_stride must be 0 (camera-0 Gaussians) or n_frames * n_joints (per-camera Gaussians)");
+        return MC3D_ERR_INVALID_ARGUMENT;
     }
     for (int k = 0; k < pb->n_bones; ++k)
         if (pb->bone_start[k] < 0 || pb->bone_start[k] >= pb->n_joints || pb->bone_end[k] < 0 || pb->bone_end[k] >= pb->n_joints) {

@@ -113,9 +113,15 @@ class Optimized_3d_Pose_Estimation:
     """
 
     def __init__(self, gaussians, initial_trajectory, decomposed_cam_params_initial=None, body_lengths=None,
-                 camera_IDs=None, R_initial=None, T_initial=None, N_sample_points=100, torch_dtype=None, device=None):
+                 camera_IDs=None, R_initial=None, T_initial=None, N_sample_points=100, torch_dtype=None, device=None,
+                 per_camera_gaussians=False):
+        """``per_camera_gaussians`` (not upstream; default off = upstream's behaviour): compare camera c's projection with
+        camera c's OWN heatmap Gaussian instead of camera 0's for every camera.  Upstream's vectorised class reads
+        ``gaussians[:, 0]`` for all cameras (pose_refinement.py:663, :885 -- SURVEY.md quirk Q1) where its superseded
+        ``Trajectory_Optimization`` indexes ``camera_index`` (:499); this switch gives the latter form."""
         torch = _torch()
         torch_dtype = torch_dtype or torch.float32
+        self.per_camera_gaussians = bool(per_camera_gaussians)
         if decomposed_cam_params_initial is None:
             raise TypeError("'NoneType' object is not iterable")                  # upstream iterates it unconditionally (:608)
         for cid in decomposed_cam_params_initial:
@@ -177,6 +183,9 @@ class Optimized_3d_Pose_Estimation:
                                                        ignore_distortions=ignore_distortions,
                                                        reset_camera_params=reset_camera_params, time_interval=time_interval)
         learn_ids = list(extrinsic_optimization_IDs) if extrinsic_optimization_IDs is not None else []
+        if self.per_camera_gaussians and (learn_ids or not optimize_trajectory):
+            raise NotImplementedError('per_camera_gaussians is offered for the trajectory optimisation only '
+                                      '(the camera-learning kernels read camera 0\'s Gaussians like upstream)')
         if self.body_lengths is None:
             raise AttributeError("'NoneType' object has no attribute 'values'")   # create_body_length_vect, :770
 
@@ -232,7 +241,8 @@ class Optimized_3d_Pose_Estimation:
                                    patience=patience, tolerance=tolerance, max_iter=max_iter,
                                    ignore_distortions=ignore_distortions, window=windows[0],
                                    n_window_frames=batch_size, hist_capacity=hist_cap, comm=comm,
-                                   use_exchange=False if learn_ids else None)
+                                   use_exchange=False if learn_ids else None,
+                                   gaussian_cameras=list(self.camera_indices) if self.per_camera_gaussians else None)
         self._engine = engine
         joint = _JointCameras(self, engine, learn_ids, lr, betas) if learn_ids else None
         names = ['total_cost', 'likelihood_cost'] + (['smoothness_cost'] if lambda_smooth > 0 else []) + \
@@ -313,7 +323,8 @@ class Optimized_3d_Pose_Estimation:
                                 device=device, lr=0.0, betas=(0.9, 0.999), lambda_smooth=1.0, lambda_body_length=1.0,
                                 patience=1, tolerance=0.0, max_iter=1, ignore_distortions=getattr(self, 'ignore_distortions', False),
                                 window=(idx[0], idx[-1] + 1), n_window_frames=len(idx), hist_capacity=4,
-                                comm=_ref.LocalComm(), use_exchange=False)
+                                comm=_ref.LocalComm(), use_exchange=False,
+                                gaussian_cameras=list(self.camera_indices) if self.per_camera_gaussians else None)
         with torch.cuda.device(device):
             eng.phases.phase(eng.problem, 0, 0, True, torch.cuda.current_stream().cuda_stream)
             acc = eng.ctrl[:8].cpu().numpy()

@@ -264,7 +264,10 @@ class RefineEngine:
     def __init__(self, trajectory, gaussians, cam_rows, body_lengths, *, torch_dtype, device, lr, betas,
                  lambda_smooth, lambda_body_length, patience, tolerance, max_iter, ignore_distortions,
                  window, n_window_frames, hist_capacity, comm=None, phases=None, gaussian_camera=0, adam_eps=1e-8,
-                 use_exchange=None):
+                 use_exchange=None, gaussian_cameras=None):
+        """``gaussian_cameras``: None = camera ``gaussian_camera``'s Gaussians for every camera (upstream's behaviour, quirk Q1);
+        a list with one entry per row of ``cam_rows`` = per-camera Gaussians (camera c is compared with
+        ``gaussians[:, gaussian_cameras[c]]``)."""
         import torch
         self.torch = torch
         self.comm = comm or LocalComm()
@@ -313,8 +316,12 @@ class RefineEngine:
         # (four components at a stride of n*J*3 rounded up to a multiple of 4 scalars)
         self.gc = torch.zeros((4 * ((n * self.J * 3 + 3) // 4 * 4),), dtype=dt, device=dev) if self.peer is not None else None
         self.term_ok = torch.zeros((n + 4,), dtype=torch.uint8, device=dev)
-        self.mu0 = torch.zeros((n, self.J, 2), dtype=dt, device=dev)
-        self.S = torch.zeros((n, self.J, 3), dtype=dt, device=dev)
+        self.gaussian_cameras = None if gaussian_cameras is None else [int(c) for c in gaussian_cameras]
+        if self.gaussian_cameras is not None and len(self.gaussian_cameras) != int(cam_rows.shape[0]):
+            raise ValueError('gaussian_cameras needs one entry per camera')
+        n_gc = 1 if self.gaussian_cameras is None else len(self.gaussian_cameras)
+        self.mu0 = torch.zeros((n_gc, n, self.J, 2), dtype=dt, device=dev)     # (cameras, frames, joints, .): one camera unless per-camera
+        self.S = torch.zeros((n_gc, n, self.J, 3), dtype=dt, device=dev)
         self.hist_capacity = int(hist_capacity)
         self.ctrl = torch.zeros((_lib.CT_HIST + 4 * self.hist_capacity,), dtype=torch.float64, device=dev)
         self.ctrl[_lib.CT_STATE + 3] = math.inf
@@ -326,14 +333,15 @@ class RefineEngine:
         self.n_cams_in_gaussians = int(g_all.shape[1])
         if n_g > 0:
             g_loc = g_all[self.begin:self.begin + n_g].to(dev).contiguous()
-            if dev.type == 'cuda':
-                fn = getattr(_lib.lib(), f'mc3d_refine_prepare_{self.tag}')
-                with torch.cuda.device(dev):
-                    _lib.check(fn(g_loc.data_ptr(), n_g, int(g_loc.shape[1]), self.J, int(gaussian_camera), 1e-6,
-                                  self.mu0.data_ptr(), self.S.data_ptr(), torch.cuda.current_stream().cuda_stream))
-                    torch.cuda.current_stream().synchronize()           # g_loc may be freed after this
-            else:
-                self._prepare_host(g_loc, n_g, gaussian_camera)
+            for slot, gcam in enumerate([gaussian_camera] if self.gaussian_cameras is None else self.gaussian_cameras):
+                if dev.type == 'cuda':
+                    fn = getattr(_lib.lib(), f'mc3d_refine_prepare_{self.tag}')
+                    with torch.cuda.device(dev):
+                        _lib.check(fn(g_loc.data_ptr(), n_g, int(g_loc.shape[1]), self.J, int(gcam), 1e-6,
+                                      self.mu0[slot].data_ptr(), self.S[slot].data_ptr(), torch.cuda.current_stream().cuda_stream))
+                        torch.cuda.current_stream().synchronize()           # g_loc may be freed after this
+                else:
+                    self._prepare_host(g_loc, n_g, gcam, slot)
 
         start, end_, length, adj_start, adj_bone, adj_sign = bone_tables(body_lengths, self.J)
         pb = self.problem = _lib.RefineProblem()
@@ -363,6 +371,7 @@ class RefineEngine:
         for name in ('m', 'v', 'best', 'g', 'mu0', 'S', 'term_ok', 'ctrl'):
             setattr(pb, name, getattr(self, name).data_ptr())
         pb.x = self.x_ext.data_ptr()
+        pb.gauss_cam_stride = 0 if self.gaussian_cameras is None else n * self.J
         if self.peer is not None:
             pb.gc = self.gc.data_ptr()
             pb.rank, pb.world = self.comm.rank, self.comm.world
@@ -382,14 +391,14 @@ class RefineEngine:
             self.phases.engine = self
         self.phases.flags(self.problem, self._stream())       # smoothness-term validity, once per run
 
-    def _prepare_host(self, g_loc, n_g, cam):
+    def _prepare_host(self, g_loc, n_g, cam, slot=0):
         # CPU tensors exist only for the gloo tests of the sharding logic (tests inject their own phases).
         torch = self.torch
         gp = g_loc[:, cam]
         c00, c01, c10, c11 = gp[..., 2] + 1e-6, gp[..., 3], gp[..., 4], gp[..., 5] + 1e-6
         det = c00.double() * c11.double() - c01.double() * c10.double()
-        self.mu0[:n_g] = gp[..., :2]
-        self.S[:n_g] = torch.stack([c11.double() / det, -0.5 * (c01.double() + c10.double()) / det,
+        self.mu0[slot, :n_g] = gp[..., :2]
+        self.S[slot, :n_g] = torch.stack([c11.double() / det, -0.5 * (c01.double() + c10.double()) / det,
                                     c00.double() / det], dim=-1).to(self.dtype)
 
     # ---- stepping ------------------------------------------------------------------------------------------------

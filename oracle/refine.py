@@ -83,11 +83,12 @@ def project(X, cam, ignore_distortions=False, jac=False):
     return pix, J
 
 
-def cov_inverse(gaussians, eps=1e-6, dtype=np.float64):
+def cov_inverse(gaussians, eps=1e-6, dtype=np.float64, camera=0):
     """(T, J, 2, 2) inverse of camera 0's covariances + eps I (pose_refinement.py:663-668; quirk Q1:
-    ``gaussians[:, 0]`` regardless of camera), computed in ``dtype`` like the reference."""
+    ``gaussians[:, 0]`` regardless of camera), computed in ``dtype`` like the reference.  ``camera`` selects another
+    camera's covariances for the per-camera form (``per_camera_gaussians`` of sgd_optimize below)."""
     g = np.asarray(gaussians, dtype=dtype)
-    cov = g[:, 0, :, 2:].reshape(g.shape[0], g.shape[2], 2, 2) + dtype(eps) * np.eye(2, dtype=dtype)
+    cov = g[:, camera, :, 2:].reshape(g.shape[0], g.shape[2], 2, 2) + dtype(eps) * np.eye(2, dtype=dtype)
     return np.linalg.inv(cov).astype(dtype)
 
 
@@ -101,19 +102,21 @@ def likelihood(x, mu0, Sinv, cams, ignore_distortions=False, grad=True):
     total, count = 0.0, 0
     g = np.zeros_like(x) if grad else None
     parts = []
-    for cam in cams:
+    per_camera = isinstance(mu0, (list, tuple))            # per-camera Gaussians: one (mu, Sinv) per camera
+    for ci, cam in enumerate(cams):
         pix, J = project(x, cam, ignore_distortions, jac=True)
-        d = pix - mu0
-        Sd = np.einsum('tjab,tjb->tja', Sinv, d)
+        mu_c, S_c = (mu0[ci], Sinv[ci]) if per_camera else (mu0, Sinv)
+        d = pix - mu_c
+        Sd = np.einsum('tjab,tjb->tja', S_c, d)
         q = 0.5 * np.einsum('tja,tja->tj', d, Sd)
         ok = _finite(q)
-        parts.append((ok, q, d, J))
+        parts.append((ok, q, d, J, S_c))
         total += q[ok].sum()
         count += int(ok.sum())
     cost = total / count if count else np.nan
     if grad:
-        for ok, q, d, J in parts:
-            Ssym_d = 0.5 * (np.einsum('tjab,tjb->tja', Sinv, d) + np.einsum('tjba,tjb->tja', Sinv, d))
+        for ok, q, d, J, S_c in parts:
+            Ssym_d = 0.5 * (np.einsum('tjab,tjb->tja', S_c, d) + np.einsum('tjba,tjb->tja', S_c, d))
             gi = np.einsum('tjak,tja->tjk', J, Ssym_d) / count
             gi[~ok] = 0.0                                   # masked entries carry no gradient (see module note)
             g += np.where(np.isfinite(gi), gi, 0.0)
@@ -188,13 +191,18 @@ def total_cost_and_grad(x, mu0, Sinv, cams, bones, lam_s, lam_b, ignore_distorti
 
 def sgd_optimize(gaussians, initial_trajectory, cams, body_lengths, lr=0.001, betas=(0.9, 0.999), lambda_smooth=1.0,
                  lambda_body_length=1.0, patience=100, tolerance=1e-5, max_iter=1000, batch_size=None,
-                 ignore_distortions=False, time_interval=(0, -1), dtype=np.float64, eps_adam=1e-8):
+                 ignore_distortions=False, time_interval=(0, -1), dtype=np.float64, eps_adam=1e-8,
+                 per_camera_gaussians=False, gaussian_cameras=None):
     """The reference's optimisation loop (pose_refinement.py:894-1096, default path).
 
     Returns dict(best, final, history) where history[name] is the reference's interleaved list
     [cost_batch..., running_mean, ...] (quirk Q5: the running mean is over the list that already contains the
     previous running means).  Quirks kept: time_interval slicing incl. the default [0,-1] dropping the last
     frame (Q3), max_iter + 1 iterations (Q4), half-overlapping batch windows stepped sequentially.
+
+    ``per_camera_gaussians=True`` is the opt-in the survey asks for: camera c's projection is
+    compared with camera c's OWN Gaussian -- ``gaussians[:, gaussian_cameras[c]]``, default c -- as the superseded
+    ``Trajectory_Optimization`` indexes them (pose_refinement.py:499), instead of camera 0's for every camera.
     """
     t0, t1 = time_interval
     g_sub = np.asarray(gaussians, dtype=np.float64)[t0:t1]
@@ -206,6 +214,10 @@ def sgd_optimize(gaussians, initial_trajectory, cams, body_lengths, lr=0.001, be
     bones = bone_table(body_lengths)
     windows = [(s, s + bs) for s in range(0, Time - bs + 1, bs // 2)]
     mu0_all = g_sub[:, 0, :, :2].astype(dtype).astype(np.float64)
+    if per_camera_gaussians:
+        gcs = list(range(len(cams))) if gaussian_cameras is None else list(gaussian_cameras)
+        mu_pc = [g_sub[:, c, :, :2].astype(dtype).astype(np.float64) for c in gcs]
+        S_pc = [cov_inverse(np.asarray(gaussians), dtype=dtype, camera=c).astype(np.float64)[t0:t1] for c in gcs]
     names = ['total_cost', 'likelihood_cost'] + (['smoothness_cost'] if lambda_smooth > 0 else []) + \
             (['body_length_cost'] if lambda_body_length > 0 else [])
     hist = {n: [] for n in names}
@@ -220,8 +232,12 @@ def sgd_optimize(gaussians, initial_trajectory, cams, body_lengths, lr=0.001, be
     while no_improve < patience and it <= max_iter:
         for (f0, f1) in windows:
             xs = x[f0:f1]
-            costs, gs = total_cost_and_grad(xs, mu0_all[f0:f1], Sinv_all[f0:f1], cams, bones, lambda_smooth,
-                                            lambda_body_length, ignore_distortions)
+            if per_camera_gaussians:
+                costs, gs = total_cost_and_grad(xs, [a[f0:f1] for a in mu_pc], [a[f0:f1] for a in S_pc], cams, bones,
+                                                lambda_smooth, lambda_body_length, ignore_distortions)
+            else:
+                costs, gs = total_cost_and_grad(xs, mu0_all[f0:f1], Sinv_all[f0:f1], cams, bones, lambda_smooth,
+                                                lambda_body_length, ignore_distortions)
             g = np.zeros_like(x)
             g[f0:f1] = gs
             norm = np.sqrt((g * g).sum())

@@ -17,7 +17,7 @@ class NumpyPhases:
 
     def _views(self):
         e = self.engine
-        return (e.x_ext.numpy(), e.m.numpy(), e.v.numpy(), e.best.numpy(), e.g.numpy(), e.mu0.numpy(), e.S.numpy(),
+        return (e.x_ext.numpy(), e.m.numpy(), e.v.numpy(), e.best.numpy(), e.g.numpy(), e.mu0[0].numpy(), e.S[0].numpy(),
                 e.term_ok.numpy(), e.ctrl.numpy())
 
     def flags(self, pb, stream):

@@ -336,6 +336,57 @@ def golden_surface(ref_utils, ref_refine, ref_mm, ref_pe, out):
         fh.write('\n')
 
 
+def golden_refine_percam(ref_refine, ref_utils, syn, out):
+    """Per-camera Gaussians (the opt-in of SURVEY.md section 8a, Q1).  The reference's vectorised class compares EVERY
+    camera's projection with camera 0's Gaussian (pose_refinement.py:663, :885); its superseded Trajectory_Optimization
+    indexes the Gaussian of the camera at hand (:499).  This golden is the reference's own optimisation loop
+    (sgd_optimize: costs, autograd, clip_grad_norm_, Adam, early stopping -- all unmodified) with ONE method replaced:
+    the likelihood cost below is assembled from the reference's project_points_torch, its gaussian_likelihood method and
+    nan_mean exactly like :866-889, but with `camera_index` where upstream has the literal 0."""
+    import torch
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+
+    class PerCameraGaussians(ref_refine.Optimized_3d_Pose_Estimation):
+        def compute_likelihood_cost(self):
+            if not hasattr(self, '_percam_inv'):
+                eye = 1e-6 * torch.eye(2, dtype=self.gaussians.dtype)
+                self._percam_inv = [torch.linalg.inv(self.gaussians[:, ci, :, 2:].reshape(self.gaussians.shape[0], self.n_joints, 2, 2)
+                                                     + eye).to(self.torch_dtype) for ci in self.camera_indices]
+                self._percam_t0 = self._percam_time_interval[0]
+            terms = []
+            for slot, (ci, cid) in enumerate(zip(self.camera_indices, self.camera_IDs)):
+                proj = ref_refine.project_points_torch(self.trajectory, *self.decomposed_cam_params[cid], indicies=self.indicies,
+                                                       torch_dtype=self.torch_dtype, ignore_distortions=self.ignore_distortions)
+                sub = self.gaussians_subset[self.indicies, ci]
+                inv = self._percam_inv[slot][self._percam_t0:][self.indicies]
+                terms.append(-self.gaussian_likelihood(proj, sub[..., :2], sub[..., 2:].reshape(len(self.indicies), self.n_joints, 2, 2),
+                                                       cov_inv=inv))
+            self.likelihood_costs = terms
+            self.likelihood_cost = ref_refine.nan_mean(terms)
+
+    g, init, cams, _ = syn.refinement_inputs(32, n_cams=3, seed=23)
+    lengths = dict(syn.EXAMPLE_BODY_LENGTHS)
+    store = dict(gaussians=g, init=init, versions=versions(),
+                 **{f'cam{i}_{n}': np.asarray(cams[i][k]) for i in cams for k, n in enumerate(['K', 'R', 'T', 'dist'])})
+    runs = {'a': dict(lr=0.01, lambda_smooth=1e-3, lambda_body_length=1, max_iter=30, time_interval=[0, 32]),
+            'b': dict(lr=0.005, lambda_smooth=0.5, lambda_body_length=0, max_iter=15, time_interval=[2, 30], ignore_distortions=True)}
+    for tag, dt in [('f32', torch.float32), ('f64', torch.float64)]:
+        for rname, kw in runs.items():
+            cam_params = {i: [np.asarray(a).copy() for a in cams[i]] for i in cams}
+            with contextlib.redirect_stdout(io.StringIO()):
+                opt = PerCameraGaussians(g.copy(), init.copy(), decomposed_cam_params_initial=cam_params, body_lengths=lengths,
+                                         torch_dtype=dt)
+                opt._percam_time_interval = kw['time_interval']
+                opt.sgd_optimize(**ref_utils.prepare_kwargs(opt.sgd_optimize, kw))
+            key = f'run_{rname}_{tag}'
+            for cname, hist in opt.all_costs_total.items():
+                store[f'{key}_{cname}'] = np.array([float(h) for h in hist], dtype=np.float64)
+            store[f'{key}_best'] = opt.best_trajectory.numpy()
+            store[f'{key}_final'] = opt.trajectory.detach().numpy()
+    np.savez(os.path.join(out, 'refine_percam_T32.npz'), **store)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reference', default='/root/reference')
@@ -347,7 +398,7 @@ def main():
     syn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(syn)
     ref_utils, ref_refine, ref_mm, ref_pe = import_reference(args.reference)
-    todo = args.only or ['dlt', 'pose3d', 'config1', 'moments', 'argmax', 'refine', 'interp', 'extrinsic', 'surface']
+    todo = args.only or ['dlt', 'pose3d', 'config1', 'moments', 'argmax', 'refine', 'refine_percam', 'interp', 'extrinsic', 'surface']
     if 'dlt' in todo:
         golden_dlt(ref_utils, syn, HERE)
     if 'pose3d' in todo:
@@ -360,6 +411,8 @@ def main():
         golden_argmax(syn, HERE)
     if 'refine' in todo:
         golden_refine(ref_refine, ref_utils, syn, HERE)
+    if 'refine_percam' in todo:
+        golden_refine_percam(ref_refine, ref_utils, syn, HERE)
     if 'interp' in todo:
         golden_interp(ref_refine, syn, HERE)
     if 'extrinsic' in todo:

@@ -99,3 +99,29 @@ def test_closed_form_gradient_matches_autograd(syn):
     total.backward()
     assert np.isclose(costs['total_cost'], float(total), rtol=1e-12)
     assert np.abs(grad - x.grad.numpy()).max() < 1e-12 * max(1.0, np.abs(grad).max())
+
+
+PERCAM_RUNS = {'a': dict(lr=0.01, lambda_smooth=1e-3, lambda_body_length=1, max_iter=30, time_interval=[0, 32]),
+               'b': dict(lr=0.005, lambda_smooth=0.5, lambda_body_length=0, max_iter=15, time_interval=[2, 30], ignore_distortions=True)}
+
+
+@pytest.mark.parametrize('run', sorted(PERCAM_RUNS))
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+def test_per_camera_gaussians_match_the_reference_loop(syn, run, tag):
+    """The opt-in form: tests/golden/refine_percam_T32.npz is the reference's own sgd_optimize with
+    its likelihood cost re-indexed by `camera_index` as Trajectory_Optimization does (pose_refinement.py:499); three cameras
+    so that camera 0's Gaussian differs from the others'."""
+    g = load_golden('refine_percam_T32.npz')
+    cams = list(cams_from_golden(g, 3).values())
+    out = R.sgd_optimize(g['gaussians'], g['init'], cams, syn.EXAMPLE_BODY_LENGTHS, per_camera_gaussians=True,
+                         dtype=np.float64 if tag == 'f64' else np.float32, **PERCAM_RUNS[run])
+    rtol, atol = (1e-12, 1e-9) if tag == 'f64' else (1e-5, 1e-3)
+    key = f'run_{run}_{tag}'
+    for name, hist in out['history'].items():
+        ref = g[f'{key}_{name}']
+        assert len(hist) == len(ref)
+        assert np.max(np.abs(np.array(hist) - ref) / np.abs(ref)) < rtol, name
+    assert np.abs(out['best'] - g[f'{key}_best']).max() < atol
+    # and it is NOT what upstream's default computes: camera-0 Gaussians for every camera give another loss
+    quirk = R.sgd_optimize(g['gaussians'], g['init'], cams, syn.EXAMPLE_BODY_LENGTHS, dtype=np.float64, **dict(PERCAM_RUNS[run], max_iter=0))
+    assert abs(quirk['history']['likelihood_cost'][0] - g[f'run_{run}_f64_likelihood_cost'][0]) > 1e-3 * abs(g[f'run_{run}_f64_likelihood_cost'][0])

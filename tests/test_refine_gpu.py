@@ -10,7 +10,7 @@ import pytest
 
 from conftest import cams_from_golden, load_golden
 from oracle import refine as R
-from test_oracle_refine import RUNS
+from test_oracle_refine import PERCAM_RUNS, RUNS
 
 pytestmark = pytest.mark.gpu
 
@@ -367,3 +367,34 @@ def test_public_cost_methods_on_the_final_trajectory(pr, syn, tag):
     d = torch.randn(5, 17, 2, dtype=dt)
     Si = torch.eye(2, dtype=dt).expand(5, 17, 2, 2)
     assert torch.allclose(opt.gaussian_likelihood(d, torch.zeros_like(d), None, cov_inv=Si), -0.5 * (d * d).sum(-1))
+
+
+@pytest.mark.parametrize('run', sorted(PERCAM_RUNS))
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+def test_per_camera_gaussians_opt_in_matches_the_reference_loop(pr, syn, run, tag):
+    """`per_camera_gaussians=True` (mc3d_refine_problem.gauss_cam_stride): the reference's own loop with the
+    likelihood indexed per camera (tests/golden/make_golden.py::golden_refine_percam), three cameras."""
+    import torch
+    import mc3d_b200.utils as u
+    g = load_golden('refine_percam_T32.npz')
+    dt = torch.float64 if tag == 'f64' else torch.float32
+    opt = pr.Optimized_3d_Pose_Estimation(g['gaussians'].copy(), g['init'].copy(), decomposed_cam_params_initial=_cam_params(g, 3),
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt, per_camera_gaussians=True)
+    opt.sgd_optimize(print_frequency=np.inf, **{k: v for k, v in u.prepare_kwargs(opt.sgd_optimize, PERCAM_RUNS[run]).items()
+                                               if k != 'print_frequency'})
+    key = f'run_{run}_{tag}'
+    hist = _history(opt)
+    rtol = 1e-9 if tag == 'f64' else LOSS_RTOL
+    for name, h in hist.items():
+        ref = g[f'{key}_{name}']
+        assert len(h) == len(ref), (name, len(h), len(ref))
+        assert np.max(np.abs(h - ref) / np.abs(ref)) < rtol, name
+    atol = 1e-6 if tag == 'f64' else 5e-2
+    assert np.abs(np.array(opt.best_trajectory) - g[f'{key}_best']).max() < atol
+    # the default (upstream's camera-0 Gaussians for every camera) is a different loss on this rig
+    ref0 = g[f'{key}_likelihood_cost'][0]
+    dflt = pr.Optimized_3d_Pose_Estimation(g['gaussians'].copy(), g['init'].copy(), decomposed_cam_params_initial=_cam_params(g, 3),
+                                           body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+    dflt.sgd_optimize(print_frequency=np.inf, **dict({k: v for k, v in u.prepare_kwargs(dflt.sgd_optimize, PERCAM_RUNS[run]).items()
+                                                      if k != 'print_frequency'}, max_iter=0))
+    assert abs(float(dflt.all_costs_total['likelihood_cost'][0]) - ref0) > 1e-3 * abs(ref0)
