@@ -18,8 +18,11 @@ camera's extrinsics from points sampled from the two ground-truth cameras' Gauss
 With ``optimize_trajectory=True`` the listed cameras are learnt together with the trajectory (:931-961; one GPU,
 whole-window batches).
 
-Out of scope (raise NotImplementedError): ``use_NN``, ``randomize_params``, and the superseded
-``ExtrinsicParameterRefinement`` / ``Trajectory_Optimization`` classes.
+``ExtrinsicParameterRefinement`` (:233-362, upstream's first, superseded extrinsic learner) is mirrored with its quirks; its
+loss / gradient evaluations are one kernel launch each.
+
+Out of scope (raise NotImplementedError): ``use_NN``, ``randomize_params``, and the superseded ``Trajectory_Optimization``
+class (``per_camera_gaussians=True`` gives its per-camera likelihood inside ``Optimized_3d_Pose_Estimation``).
 """
 import argparse
 import ctypes
@@ -553,6 +556,168 @@ class Optimized_3d_Pose_Estimation:
         self.all_costs_total = {nm: _interleave_history(cols[nm], 1, dt) for nm in names}
         self.iterations = st['iterations']
         return self
+
+
+class ExtrinsicParameterRefinement:
+    """Upstream's first, superseded extrinsic learner (pose_refinement.py:233-362): R, T of a third camera from points
+    sampled from two ground-truth cameras' heatmap Gaussians.  Kept call-compatible -- same constructor, ``sample_gaussians``,
+    ``construct_loss``, ``optimize`` and attributes (``R``, ``T``, ``samples``, ``samples_3d``, ``best_params``,
+    ``loss_function``) -- with its arithmetic on the GPU: the samples are triangulated by the batched 2-view kernel and every
+    evaluation of the loss and its gradient w.r.t. the 9 entries of R and T is one launch of ``mc3d_extrinsic_costgrad_*``.
+    The 12-parameter Adam step and the SVD re-orthogonalisation of R (:337-340) stay on the host, in float32 as upstream.
+
+    Upstream's behaviour, kept on purpose:
+      * the loss is the mean LOG-likelihood and it is *minimised* (:310-314, :325-333), i.e. the optimiser pushes the
+        projections away from the Gaussians; use ``Optimized_3d_Pose_Estimation.sgd_optimize(extrinsic_optimization_IDs=...)``
+        for the corrected form;
+      * the covariances are reshaped to (T, 1, J, 2, 2) (:298), which broadcasts against the (T, J) residuals to a (T, T, J)
+        table: every sample frame is scored with the inverse covariance of EVERY frame.  The mean over that table equals
+        scoring each residual with the time-average of the inverse covariances, which is what the kernel is given;
+      * R, T are float32 whatever ``torch_dtype`` is (:240-247), an explicit ``R_initial`` / ``T_initial`` is ignored
+        (:245-247), means and covariances are those of camera index 2 (:297-298), and exactly three cameras are required.
+    Non-finite samples are not supported (upstream's nan_mean would weight the normalisation term per joint)."""
+
+    def __init__(self, gaussians, R_initial=None, T_initial=None, decomposed_cam_params=None, N_sample_points=100,
+                 GT_camera_indicies=[0, 1], estimation_camera_index=2, torch_dtype=None, device=None):
+        torch = _torch()
+        torch_dtype = torch_dtype or torch.float32
+        assert len(GT_camera_indicies) == 2
+        assert min([idx in decomposed_cam_params.keys() for idx in GT_camera_indicies])
+        if R_initial is None and T_initial is None:
+            if estimation_camera_index in decomposed_cam_params:
+                self.R = torch.tensor(np.asarray(_ref._as_numpy(decomposed_cam_params[estimation_camera_index][1])), dtype=torch.float32)
+                self.T = torch.tensor(np.asarray(_ref._as_numpy(decomposed_cam_params[estimation_camera_index][2])), dtype=torch.float32)
+            else:
+                self.R = torch.eye(3)
+                self.T = torch.zeros(3, 1)
+        else:                                                     # upstream ignores the values it was given (:245-247)
+            self.R = torch.eye(3)
+            self.T = torch.zeros(3, 1)
+        self.gaussians = torch.tensor(np.asarray(_ref._as_numpy(gaussians)), dtype=torch_dtype)
+        self.decomposed_cam_params = {k: [torch.tensor(np.asarray(_ref._as_numpy(cp)), dtype=torch_dtype) for cp in decomposed_cam_params[k]]
+                                      for k in decomposed_cam_params}
+        self.Time = gaussians.shape[0]
+        self.n_cams = gaussians.shape[1]
+        assert self.n_cams == 3
+        self.n_joints = gaussians.shape[2]
+        self.N_sample_points = N_sample_points
+        self.GT_camera_indicies = GT_camera_indicies
+        self.estimation_camera_index = estimation_camera_index
+        self.torch_dtype = torch_dtype
+        self.device = device
+        self.best_params = None
+
+    def sample_gaussians(self, N=None):
+        """N draws per (frame, ground-truth camera, joint) in upstream's order (:277-286): the same numpy stream."""
+        if N is None:
+            N = self.N_sample_points
+        means = self.gaussians[:, self.GT_camera_indicies, :, :2].numpy()
+        covs = self.gaussians[:, self.GT_camera_indicies, :, 2:].reshape(self.Time, 2, self.n_joints, 2, 2).numpy()
+        samples = np.empty((self.Time, 2, self.n_joints, N, 2))
+        for t in range(self.Time):
+            for cam in range(2):
+                for point in range(self.n_joints):
+                    samples[t, cam, point] = np.random.multivariate_normal(means[t, cam, point], covs[t, cam, point], N)
+        self.samples = np.transpose(samples, (0, 2, 3, 1, 4))
+        return self.samples
+
+    def construct_loss(self):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.Mc3dError('ExtrinsicParameterRefinement needs a CUDA device (no CPU fallback)')
+        dev = torch.device(self.device) if self.device is not None else torch.device('cuda', torch.cuda.current_device())
+        dt = self.torch_dtype
+        tag = 'f32' if dt == torch.float32 else 'f64'
+        cm1, R1, T1, d1 = self.decomposed_cam_params[self.GT_camera_indicies[0]]
+        cm2, R2, T2, d2 = self.decomposed_cam_params[self.GT_camera_indicies[1]]
+        self.samples_3d = torch.from_numpy(utils.triangulate_points(self.samples, cm1, d1, R1, T1, cm2, d2, R2, T2)).to(dt)
+        if not bool(torch.isfinite(self.samples_3d).all()):
+            raise NotImplementedError('non-finite samples are not supported by this class')
+        g2 = self.gaussians[:, 2]                                             # camera index 2, hard-coded upstream (:297-298)
+        cov = g2[..., 2:].reshape(self.Time, self.n_joints, 2, 2) + 1e-6 * torch.eye(2, dtype=dt)
+        cov_inv = torch.linalg.inv(cov).to(torch.float32)                      # gaussian_likelihood(..., torch_dtype=torch.float32), :311
+        s_bar = cov_inv.to(dt).mean(dim=0)                                     # the (T, T, J) broadcast, averaged over the covariance frame
+        S = torch.stack([s_bar[:, 0, 0], 0.5 * (s_bar[:, 0, 1] + s_bar[:, 1, 0]), s_bar[:, 1, 1]], dim=-1)
+        norm = 0.5 * torch.log((2 * math.pi) ** 2 * torch.det(cov) + 1e-6)     # (T, J)
+        self._norm_const = float(norm.mean())
+        lib = _lib.lib()
+        with torch.cuda.device(dev):
+            self._dev = dev
+            self._s3 = self.samples_3d.to(dev).contiguous()
+            self._mean = g2[..., :2].to(dt).to(dev).contiguous()
+            self._S = S.to(dt).unsqueeze(0).repeat(self.Time, 1, 1).to(dev).contiguous()
+            self._params = torch.zeros(48, dtype=torch.float64, device=dev)
+            self._ctrl = torch.zeros(64, dtype=torch.float64, device=dev)
+            pb = self._pb = _lib.ExtrinsicProblem()
+            pb.n_frames, pb.n_joints, pb.n_samples = self.Time, self.n_joints, int(self.samples_3d.shape[2])
+            pb.ignore_distortions, pb.patience, pb.max_iter, pb.hist_capacity = 0, 1, 1, 0
+            K = self.decomposed_cam_params[self.estimation_camera_index][0].to(torch.float64).reshape(9)
+            dd = self.decomposed_cam_params[self.estimation_camera_index][-1].to(torch.float64).reshape(-1)
+            for i in range(9):
+                pb.K[i] = float(K[i])
+            for i in range(min(5, dd.numel())):
+                pb.dist[i] = float(dd[i])
+            pb.samples3d, pb.mean, pb.S = self._s3.data_ptr(), self._mean.data_ptr(), self._S.data_ptr()
+            pb.params, pb.ctrl = self._params.data_ptr(), self._ctrl.data_ptr()
+        self._costgrad = getattr(lib, f'mc3d_extrinsic_costgrad_{tag}')
+
+        def loss(R, T, with_grad=False):
+            """Mean log-likelihood of the projected samples (the quantity upstream minimises); with_grad: also d loss / d (R, T)."""
+            with torch.cuda.device(self._dev):
+                self._params[:9] = torch.as_tensor(R).detach().to(torch.float64).reshape(9).to(self._dev)
+                self._params[9:12] = torch.as_tensor(T).detach().to(torch.float64).reshape(3).to(self._dev)
+                self._ctrl.zero_()
+                _lib.check(self._costgrad(ctypes.byref(self._pb), torch.cuda.current_stream().cuda_stream))
+                acc = self._ctrl[:14].cpu().numpy()
+            if acc[1] != self.Time * self.n_joints * self._pb.n_samples:
+                raise NotImplementedError('non-finite projections are not supported by this class')
+            value = -acc[0] / acc[1] - self._norm_const
+            if not with_grad:
+                return torch.tensor(value, dtype=self.torch_dtype)
+            return value, (-acc[2:11] / acc[1]).reshape(3, 3), (-acc[11:14] / acc[1]).reshape(3, 1)
+
+        self.loss_function = loss
+        return loss
+
+    def optimize(self, learning_rate=0.001, print_frequency=10, max_iter=np.inf, patience=10):
+        torch = _torch()
+        self.sample_gaussians()
+        self.construct_loss()
+        f32 = np.float32
+        p = np.concatenate([self.R.detach().numpy().reshape(9), self.T.detach().numpy().reshape(3)]).astype(f32)
+        m, v = np.zeros(12, f32), np.zeros(12, f32)
+        b1, b2, eps = 0.9, 0.999, 1e-8
+        best_cost, iteration, no_improvement_count, step = float('inf'), 0, 0, 0
+        self.costs = []
+        while no_improvement_count < patience and iteration <= max_iter:
+            cost, gR, gT = self.loss_function(p[:9].reshape(3, 3), p[9:].reshape(3, 1), with_grad=True)
+            g = np.concatenate([gR.reshape(9), gT.reshape(3)]).astype(f32)
+            # torch.optim.Adam on two float32 tensors (no clipping here, :325-335)
+            step += 1
+            m = m + f32(1 - b1) * (g - m)
+            v = v * f32(b2) + (f32(1 - b2) * g) * g
+            step_size = learning_rate / (1 - b1 ** step)
+            denom = np.sqrt(v) / f32(math.sqrt(1 - b2 ** step)) + f32(eps)
+            p = (p + f32(-step_size) * (m / denom)).astype(f32)
+            U, _, Vt = np.linalg.svd(p[:9].reshape(3, 3))                        # re-orthogonalise R (:337-340)
+            p[:9] = (U @ Vt).astype(f32).reshape(9)
+            self.R = torch.tensor(p[:9].reshape(3, 3).copy())
+            self.T = torch.tensor(p[9:].reshape(3, 1).copy())
+            current_cost = f32(cost)
+            self.costs.append(float(current_cost))
+            if current_cost < best_cost:
+                best_cost = current_cost
+                self.best_params = [self.R.clone().detach(), self.T.clone().detach()]
+                no_improvement_count = 0
+            else:
+                no_improvement_count += 1
+            if no_improvement_count >= patience:
+                print(f'Early stopping at iteration {iteration}. Best cost = {best_cost:.2e}')
+                break
+            if iteration % print_frequency == 0:
+                print(f'Iteration {iteration}: Cost = {current_cost:.2e}')
+            iteration += 1
+        return self.best_params
 
 
 class _JointCameras:

@@ -309,7 +309,9 @@ SURFACE = {
                         'Optimized_3d_Pose_Estimation.compute_smoothness_cost',
                         'Optimized_3d_Pose_Estimation.compute_body_length_cost',
                         'Optimized_3d_Pose_Estimation.gaussian_likelihood',
-                        'Optimized_3d_Pose_Estimation.create_body_length_vect'],
+                        'Optimized_3d_Pose_Estimation.create_body_length_vect',
+                        'ExtrinsicParameterRefinement', 'ExtrinsicParameterRefinement.sample_gaussians',
+                        'ExtrinsicParameterRefinement.construct_loss', 'ExtrinsicParameterRefinement.optimize'],
     'pose_estimation': ['get_pose_3D'],
     'mmpose_pose_estimation': ['PoseEstimator', 'PoseEstimator.predict', 'PoseEstimator.get_heatmap_means_cov',
                                'PoseEstimator.get_heatmap_means_stds'],
@@ -387,6 +389,50 @@ def golden_refine_percam(ref_refine, ref_utils, syn, out):
     np.savez(os.path.join(out, 'refine_percam_T32.npz'), **store)
 
 
+def golden_epr(ref_refine, syn, out):
+    """The superseded ExtrinsicParameterRefinement class (pose_refinement.py:233-362), unmodified, with a recording wrapper
+    around the loss it builds: samples drawn, their triangulation, the cost of every iteration, final and best R, T."""
+    import torch
+    gs, init, cams, _ = syn.refinement_inputs(10, n_cams=3, seed=9)
+    cams = {k: [np.array(c, dtype=np.float64) for c in v] for k, v in cams.items()}
+    cams[2][2] = cams[2][2] + np.array([[12.0], [-8.0], [15.0]])
+    store = dict(gaussians=gs, versions=versions())
+    for cid, cam in cams.items():
+        for nm, arr in zip(('K', 'R', 'T', 'dist'), cam):
+            store[f'cam{cid}_{nm}'] = np.asarray(arr)
+
+    class Recording(ref_refine.ExtrinsicParameterRefinement):
+        def construct_loss(self):
+            inner = super().construct_loss()
+            self.costs = []
+
+            def wrapped(R, T):
+                c = inner(R, T)
+                self.costs.append(float(c))
+                return c
+            self.loss_function = wrapped
+            return wrapped
+
+    for dt_name, dt in (('f32', torch.float32), ('f64', torch.float64)):
+        np.random.seed(4)
+        torch.manual_seed(4)
+        try:
+            opt = Recording(gs.copy(), decomposed_cam_params={i: list(cams[i]) for i in cams}, N_sample_points=5, torch_dtype=dt)
+            with contextlib.redirect_stdout(io.StringIO()):
+                best = opt.optimize(learning_rate=1e-3, max_iter=24, patience=10)
+        except Exception as exc:                                  # recorded, not hidden
+            store[f'{dt_name}_raised'] = np.array(f'{type(exc).__name__}: {exc}'[:300])
+            continue
+        store[f'{dt_name}_samples'] = np.asarray(opt.samples)
+        store[f'{dt_name}_samples3d'] = opt.samples_3d.numpy().astype(np.float64)
+        store[f'{dt_name}_costs'] = np.array(opt.costs)
+        store[f'{dt_name}_R'] = opt.R.detach().numpy().astype(np.float64)
+        store[f'{dt_name}_T'] = opt.T.detach().numpy().astype(np.float64)
+        store[f'{dt_name}_best_R'] = best[0].numpy().astype(np.float64)
+        store[f'{dt_name}_best_T'] = best[1].numpy().astype(np.float64)
+    np.savez(os.path.join(out, 'epr_T10.npz'), **store)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reference', default='/root/reference')
@@ -398,7 +444,7 @@ def main():
     syn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(syn)
     ref_utils, ref_refine, ref_mm, ref_pe = import_reference(args.reference)
-    todo = args.only or ['dlt', 'pose3d', 'config1', 'moments', 'argmax', 'refine', 'refine_percam', 'interp', 'extrinsic', 'surface']
+    todo = args.only or ['dlt', 'pose3d', 'config1', 'moments', 'argmax', 'refine', 'refine_percam', 'interp', 'extrinsic', 'epr', 'surface']
     if 'dlt' in todo:
         golden_dlt(ref_utils, syn, HERE)
     if 'pose3d' in todo:
@@ -417,6 +463,8 @@ def main():
         golden_interp(ref_refine, syn, HERE)
     if 'extrinsic' in todo:
         golden_extrinsic(ref_refine, syn, HERE)
+    if 'epr' in todo:
+        golden_epr(ref_refine, syn, HERE)
     if 'surface' in todo:
         golden_surface(ref_utils, ref_refine, ref_mm, ref_pe, HERE)
     for f in sorted(os.listdir(HERE)):

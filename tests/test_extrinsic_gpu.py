@@ -7,7 +7,7 @@ import random
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, load_golden
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(ROOT, 'tests', 'golden', 'extrinsic_T12.npz')
@@ -139,3 +139,28 @@ def test_cameras_and_trajectory_learnt_together_match_reference_runs(key):
     assert np.abs(opt.decomposed_cam_params[2][2].numpy() - g[f'{key}_T']).max() < atol * 1e3
     assert np.abs(opt.best_decomposed_cam_params[2][1].numpy() - g[f'{key}_best_R']).max() < atol
     assert np.abs(opt.best_decomposed_cam_params[2][2].numpy() - g[f'{key}_best_T']).max() < atol * 1e3
+
+
+def test_superseded_extrinsic_parameter_refinement_class_matches_reference():
+    """pose_refinement.ExtrinsicParameterRefinement (reference :233-362) against a run of the unmodified
+    class (tests/golden/epr_T10.npz, float32 -- upstream raises in float64): same numpy draws, the triangulated samples, the
+    cost of every iteration (the mean log-likelihood it minimises, wrong sign and (T, T, J) broadcast included) and R, T."""
+    import torch
+    import mc3d_b200.pose_refinement as pr
+    g = load_golden('epr_T10.npz')
+    assert 'expected scalar type' in str(g['f64_raised'])                     # what upstream does with torch_dtype=float64
+    cams = {i: [g[f'cam{i}_{n}'] for n in ('K', 'R', 'T', 'dist')] for i in range(3)}
+    np.random.seed(4)
+    opt = pr.ExtrinsicParameterRefinement(g['gaussians'].copy(), decomposed_cam_params={i: list(cams[i]) for i in cams},
+                                          N_sample_points=5, torch_dtype=torch.float32)
+    best = opt.optimize(learning_rate=1e-3, max_iter=24, patience=10, print_frequency=1000)
+    assert np.array_equal(np.asarray(opt.samples), g['f32_samples'])           # identical random stream
+    assert np.abs(opt.samples_3d.numpy().astype(np.float64) - g['f32_samples3d']).max() < 1e-2   # float32 storage of ~3 m coordinates
+    costs = np.array(opt.costs)
+    assert len(costs) == len(g['f32_costs'])
+    assert np.max(np.abs(costs - g['f32_costs']) / np.abs(g['f32_costs'])) < 1e-3
+    assert np.abs(opt.R.numpy() - g['f32_R']).max() < 1e-4 and np.abs(opt.T.numpy() - g['f32_T']).max() < 1e-2
+    assert np.abs(best[0].numpy() - g['f32_best_R']).max() < 1e-4 and np.abs(best[1].numpy() - g['f32_best_T']).max() < 1e-2
+    # the loss it builds is callable like upstream's (R, T) -> scalar tensor
+    val = opt.loss_function(opt.R, opt.T)
+    assert isinstance(val, torch.Tensor) and val.ndim == 0
