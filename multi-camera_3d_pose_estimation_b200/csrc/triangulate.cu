@@ -356,7 +356,7 @@ __device__ __forceinline__ void pair_start(const mc3d_tri_start_pair *pc, int va
 }
 
 #ifndef MC3D_TRI_UNR_LIMIT
-#define MC3D_TRI_UNR_LIMIT 8            // view loop fully unrolled up to 8 views (no spills at 128 registers; +5 % at V = 8)
+#define MC3D_TRI_UNR_LIMIT 16           // view loop fully unrolled (no spills at 128 registers; +5 % at V = 8, +6 % at V = 16)
 #endif
 // The float solve leaves an error of ~cond(M~) 1e-7 |e|, so a correction is final when cond |e| is small against the range:
 //     |e|^2 (tr(M~) / smallest pivot)^2 <= MC3D_TRI_ACCEPT (|X|^2 + rig scale^2)
@@ -548,8 +548,15 @@ constexpr int TRI_WTILE = 32 * TRI_NJ;          // joints per warp tile
 // Resident CTAs per SM the mixed kernel is compiled for.  Measured at V = 8: 4 CTAs x 128 registers and 3 CTAs x 162
 // registers run at the same speed (the extra registers buy the compiler what the fourth CTA's warps would hide), so the
 // instantiations that spill at 128 registers -- the (N, 3, V) layout, whose x / y pairs need moves, and V = 4 -- get 3.
+#ifndef MC3D_TRI_V16_STAGES
+#define MC3D_TRI_V16_STAGES 1
+#endif
+// Input stages per warp: two, except for 16 views, where a 64-joint tile is 12 KB and two stages per warp would hold the SM
+// to 8 warps; with one stage 16 warps are resident.
+__host__ __device__ constexpr int tri_mixed_stages(int V) { return (V * TRI_NP >= 16) ? MC3D_TRI_V16_STAGES : 2; }
 __host__ __device__ constexpr int tri_mixed_blocks(int V, int layout) {
-    return (V * TRI_NP >= 16) ? 2 : ((layout == MC3D_LAYOUT_3V && V >= 4) || V == 4) ? MC3D_TRI_MBLOCKS - 1 : MC3D_TRI_MBLOCKS;
+    return (V * TRI_NP >= 16) ? (tri_mixed_stages(V) == 1 ? (layout == MC3D_LAYOUT_3V ? MC3D_TRI_MBLOCKS - 1 : MC3D_TRI_MBLOCKS) : 2)
+                              : ((layout == MC3D_LAYOUT_3V && V >= 4) || V == 4) ? MC3D_TRI_MBLOCKS - 1 : MC3D_TRI_MBLOCKS;
 }
 
 __device__ __noinline__ void mixed_cold_fix(const TriParams &prm, int nv, const float *row, bool l3v, float *o) {
@@ -574,11 +581,12 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     constexpr int row_elems = 3 * V;
     constexpr uint32_t stage_bytes = (uint32_t)(TRI_WTILE * row_elems * sizeof(float));
     constexpr uint32_t otile_bytes = (uint32_t)(TRI_WTILE * 3 * sizeof(float));
+    constexpr int NST = tri_mixed_stages(V);           // input stages per warp
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // layout: [warp][2] input stages | [warp][2] output tiles | [warp][2] mbarriers | cameras | start pairs
-    unsigned char *ring = smem_raw + (size_t)warp * 2 * stage_bytes;
-    float *otile = reinterpret_cast<float *>(smem_raw + (size_t)TRI_MWARPS * 2 * stage_bytes + (size_t)warp * 2 * otile_bytes);
-    unsigned char *fixed = smem_raw + (size_t)TRI_MWARPS * 2 * (stage_bytes + otile_bytes);
+    // layout: [warp][NST] input stages | [warp][2] output tiles | [warp][2] mbarriers | cameras | start pairs
+    unsigned char *ring = smem_raw + (size_t)warp * NST * stage_bytes;
+    float *otile = reinterpret_cast<float *>(smem_raw + (size_t)TRI_MWARPS * NST * stage_bytes + (size_t)warp * 2 * otile_bytes);
+    unsigned char *fixed = smem_raw + (size_t)TRI_MWARPS * (NST * stage_bytes + 2 * otile_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(fixed) + warp * 2;
     CamF *cam = reinterpret_cast<CamF *>(fixed + TRI_MWARPS * 2 * sizeof(uint64_t));
     mc3d_tri_start_pair *pairs = reinterpret_cast<mc3d_tri_start_pair *>(cam + V);
@@ -620,15 +628,16 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     // views of the starting pairs straight from the parameter bank (uniform): no shared-memory load in front of the row loads
     const int4 sv = make_int4(prm.start[0].view_a, prm.start[0].view_b, prm.start[1].view_a, prm.start[1].view_b);
     for (unsigned k = 0; k < my_tiles; ++k) {
-        const uint32_t b = k & 1u;
-        // refills the stage of iteration k - 1 (every lane left it before that iteration's last __syncwarp)
-        if (lane == 0 && k + 1 < my_tiles) {
+        const uint32_t b = k & 1u;                    // output buffer; input stage when there are two
+        const uint32_t sb = NST == 2 ? b : 0u;
+        // two stages: refill the stage of iteration k - 1 (every lane left it before that iteration's last __syncwarp)
+        if (NST == 2 && lane == 0 && k + 1 < my_tiles) {
             mbar_arrive_expect_tx_sa(full_sa + 8u * (b ^ 1u), stage_bytes);
             bulk_g2s_sa(ring_sa + (b ^ 1u) * stage_bytes, src, stage_bytes, full_sa + 8u * (b ^ 1u));
         }
-        src += src_step;
-        const float *stage = reinterpret_cast<const float *>(ring + b * stage_bytes);
-        mbar_wait_sa(full_sa + 8u * b, (k >> 1) & 1u);
+        if (NST == 2) src += src_step;
+        const float *stage = reinterpret_cast<const float *>(ring + sb * stage_bytes);
+        mbar_wait_sa(full_sa + 8u * sb, NST == 2 ? ((k >> 1) & 1u) : (k & 1u));
         const float *rows[TRI_NJ];
 #pragma unroll
         for (int j = 0; j < TRI_NJ; ++j) rows[j] = stage + (lane + 32 * j) * row_elems;
@@ -645,11 +654,16 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
             if (state[j] == 1) mixed_cold_fix(prm, V, rows[j], LAYOUT == MC3D_LAYOUT_3V, o);
         }
         fence_proxy_async_smem();
-        __syncwarp();                                 // stage b consumed by every lane; output tile complete
+        __syncwarp();                                 // the stage is consumed by every lane; output tile complete
         if (lane == 0) {
+            if (NST == 1 && k + 1 < my_tiles) {       // one stage (16 views: twice the resident warps instead of a second stage):
+                mbar_arrive_expect_tx_sa(full_sa, stage_bytes);                       // the refill overlaps the output epilogue only,
+                bulk_g2s_sa(ring_sa, src, stage_bytes, full_sa);                      // the other warps of the SM cover its latency
+            }
             bulk_s2g_sa(dst, ot_sa + b * otile_bytes, otile_bytes);
             bulk_commit();
         }
+        if (NST == 1) src += src_step;
         dst += dst_step;
     }
     if (tail > 0 && gw == n_tiles % gstride) {        // ragged tail: the next warp in line, plain loads and stores
@@ -1242,8 +1256,9 @@ template <int V, int LAYOUT>
 static int launch_mixed(const float *d_kpts, long long n, const TriParams &prm, float *d_out, cudaStream_t stream) {
     constexpr size_t stage_bytes = (size_t)TRI_WTILE * 3 * V * sizeof(float);
     constexpr size_t otile_bytes = (size_t)TRI_WTILE * 3 * sizeof(float);
-    // two stages per warp: a warp needs ~3 us per tile, which covers the HBM latency, and more resident warps beat a deeper ring
-    constexpr size_t smem = TRI_MWARPS * 2 * (stage_bytes + otile_bytes + sizeof(uint64_t)) + V * sizeof(CamF) +
+    // two stages per warp (one for 16 views): a warp needs ~3 us per tile, which covers the HBM latency, and more resident
+    // warps beat a deeper ring
+    constexpr size_t smem = TRI_MWARPS * (tri_mixed_stages(V) * stage_bytes + 2 * otile_bytes + 2 * sizeof(uint64_t)) + V * sizeof(CamF) +
                             2 * sizeof(mc3d_tri_start_pair);
     static_assert(smem <= 227 * 1024, "mixed kernel: shared memory");
     auto kern = triangulate_mixed_kernel<V, LAYOUT>;
