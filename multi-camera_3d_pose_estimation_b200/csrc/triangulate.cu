@@ -1092,6 +1092,18 @@ static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode
 constexpr int TRI_W64_WARPS = 4;
 constexpr int TRI_W64_TILE = 32;
 
+// Rows whose size is a multiple of 128 bytes (16 views: 384 B) would put every lane of a warp on the same shared-memory
+// banks: each lane then bulk-copies its OWN row into a slot padded by 16 bytes (conflict-free), all 32 copies completing on
+// the warp's mbarrier, and -- the slots being 12.8 KB per tile -- the warp keeps ONE input stage and one output tile so that
+// 16 warps stay resident.
+__host__ __device__ constexpr bool tri_w64_padded(int V) { return (3 * V * sizeof(double)) % 128 == 0; }
+__host__ __device__ constexpr int tri_w64_slot_elems(int V) { return 3 * V + (tri_w64_padded(V) ? 2 : 0); }
+__host__ __device__ constexpr int tri_w64_stages(int V) { return tri_w64_padded(V) ? 1 : 2; }
+__host__ __device__ constexpr size_t tri_w64_smem(int V) {
+    return (size_t)TRI_W64_WARPS * (tri_w64_stages(V) * (size_t)TRI_W64_TILE * tri_w64_slot_elems(V) * sizeof(double) +
+                                    tri_w64_stages(V) * (size_t)TRI_W64_TILE * 3 * sizeof(double) + 2 * sizeof(uint64_t));
+}
+
 template <int V, int LAYOUT>
 __global__ void __launch_bounds__(32 * TRI_W64_WARPS, 4)
 triangulate_warp64_kernel(const double *__restrict__ kpts, double *__restrict__ out, long long n,
@@ -1099,13 +1111,18 @@ triangulate_warp64_kernel(const double *__restrict__ kpts, double *__restrict__ 
     static_assert(V > 0 && V % 2 == 0, "even compile-time view count");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int row_elems = 3 * V;
-    constexpr uint32_t stage_bytes = (uint32_t)(TRI_W64_TILE * row_elems * sizeof(double));
+    constexpr bool PADDED = tri_w64_padded(V);
+    constexpr int NST = tri_w64_stages(V);             // input stages and output tiles per warp
+    constexpr int slot_elems = tri_w64_slot_elems(V);
+    constexpr uint32_t row_bytes = (uint32_t)(row_elems * sizeof(double));
+    constexpr uint32_t tile_bytes = (uint32_t)(TRI_W64_TILE * row_elems * sizeof(double));      // bytes a tile has in global memory
+    constexpr uint32_t stage_bytes = (uint32_t)(TRI_W64_TILE * slot_elems * sizeof(double));     // ... and in shared memory
     constexpr uint32_t otile_bytes = (uint32_t)(TRI_W64_TILE * 3 * sizeof(double));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // layout: [warp][2] input stages | [warp][2] output tiles | [warp][2] mbarriers
-    unsigned char *ring = smem_raw + (size_t)warp * 2 * stage_bytes;
-    double *otile = reinterpret_cast<double *>(smem_raw + (size_t)TRI_W64_WARPS * 2 * stage_bytes + (size_t)warp * 2 * otile_bytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)TRI_W64_WARPS * 2 * (stage_bytes + otile_bytes)) + warp * 2;
+    // layout: [warp][NST] input stages | [warp][NST] output tiles | [warp][2] mbarriers
+    unsigned char *ring = smem_raw + (size_t)warp * NST * stage_bytes;
+    double *otile = reinterpret_cast<double *>(smem_raw + (size_t)TRI_W64_WARPS * NST * stage_bytes + (size_t)warp * NST * otile_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)TRI_W64_WARPS * NST * (stage_bytes + otile_bytes)) + warp * 2;
     if (lane == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -1117,13 +1134,21 @@ triangulate_warp64_kernel(const double *__restrict__ kpts, double *__restrict__ 
     const unsigned gw = blockIdx.x * TRI_W64_WARPS + warp, gstride = gridDim.x * TRI_W64_WARPS;
     const unsigned my_tiles = (gw < n_tiles) ? (n_tiles - gw + gstride - 1) / gstride : 0;
     const uint32_t ring_sa = smem_u32(ring), full_sa = smem_u32(full), ot_sa = smem_u32(otile);
-    const unsigned char *src = reinterpret_cast<const unsigned char *>(kpts) + (size_t)gw * stage_bytes;
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(kpts) + (size_t)gw * tile_bytes;
     unsigned char *dst = reinterpret_cast<unsigned char *>(out) + (size_t)gw * otile_bytes;
-    const uint32_t src_step = gstride * stage_bytes, dst_step = gstride * otile_bytes;
-    if (lane == 0 && my_tiles > 0) {
-        mbar_arrive_expect_tx_sa(full_sa, stage_bytes);
-        bulk_g2s_sa(ring_sa, src, stage_bytes, full_sa);
-    }
+    const uint32_t src_step = gstride * tile_bytes, dst_step = gstride * otile_bytes;
+    // one tile from global memory into stage `st`: one contiguous bulk copy, or one copy per lane into its padded slot
+    auto load_tile = [&](const unsigned char *from, uint32_t st) {
+        if (lane == 0) mbar_arrive_expect_tx_sa(full_sa + 8u * st, tile_bytes);
+        if (PADDED) {
+            __syncwarp();                             // the expected byte count is registered before any copy can complete
+            bulk_g2s_sa(ring_sa + st * stage_bytes + lane * (uint32_t)(slot_elems * sizeof(double)), from + (size_t)lane * row_bytes,
+                        row_bytes, full_sa + 8u * st);
+        } else if (lane == 0) {
+            bulk_g2s_sa(ring_sa + st * stage_bytes, from, tile_bytes, full_sa + 8u * st);
+        }
+    };
+    if (my_tiles > 0) load_tile(src, 0);
     src += src_step;
     auto solve_row = [&](const double *rowd, double &X0, double &X1, double &X2) {
         double B[10];
@@ -1162,22 +1187,27 @@ triangulate_warp64_kernel(const double *__restrict__ kpts, double *__restrict__ 
         }
     };
     for (unsigned k = 0; k < my_tiles; ++k) {
-        const uint32_t b = k & 1u;
-        if (lane == 0 && k + 1 < my_tiles) {          // refills the stage of iteration k - 1
-            mbar_arrive_expect_tx_sa(full_sa + 8u * (b ^ 1u), stage_bytes);
-            bulk_g2s_sa(ring_sa + (b ^ 1u) * stage_bytes, src, stage_bytes, full_sa + 8u * (b ^ 1u));
+        const uint32_t b = NST == 2 ? (k & 1u) : 0u;
+        if (NST == 2) {                               // refills the stage of iteration k - 1
+            if (k + 1 < my_tiles) load_tile(src, b ^ 1u);
+            src += src_step;
         }
-        src += src_step;
-        const double *rowd = reinterpret_cast<const double *>(ring + b * stage_bytes) + lane * row_elems;
-        mbar_wait_sa(full_sa + 8u * b, (k >> 1) & 1u);
+        const double *rowd = reinterpret_cast<const double *>(ring + b * stage_bytes) + lane * slot_elems;
+        mbar_wait_sa(full_sa + 8u * b, NST == 2 ? ((k >> 1) & 1u) : (k & 1u));
         double X0, X1, X2;
         solve_row(rowd, X0, X1, X2);
         double *ot = otile + b * (TRI_W64_TILE * 3);
-        if (lane == 0) bulk_wait_read<1>();           // the store of iteration k - 2 has left this output buffer
-        __syncwarp();
+        if (lane == 0) {                              // the store that last used this output buffer has left it
+            if (NST == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
+        __syncwarp();                                 // ... and every lane has consumed the stage
+        if (NST == 1) {                               // one stage: the refill overlaps the epilogue, the other warps cover its latency
+            if (k + 1 < my_tiles) load_tile(src, 0);
+            src += src_step;
+        }
         ot[lane * 3 + 0] = X0; ot[lane * 3 + 1] = X1; ot[lane * 3 + 2] = X2;
         fence_proxy_async_smem();
-        __syncwarp();                                 // stage b consumed by every lane; output tile complete
+        __syncwarp();                                 // output tile complete
         if (lane == 0) {
             bulk_s2g_sa(dst, ot_sa + b * otile_bytes, otile_bytes);
             bulk_commit();
@@ -1187,10 +1217,10 @@ triangulate_warp64_kernel(const double *__restrict__ kpts, double *__restrict__ 
     if (tail > 0 && gw == n_tiles % gstride) {        // ragged tail: plain loads and stores
         double *stage = reinterpret_cast<double *>(ring);
         const double *tsrc = kpts + (size_t)n_tiles * TRI_W64_TILE * row_elems;
-        for (int i = lane; i < tail * row_elems; i += 32) stage[i] = tsrc[i];
+        for (int i = lane; i < tail * row_elems; i += 32) stage[(i / row_elems) * slot_elems + i % row_elems] = tsrc[i];
         __syncwarp();
         double X0, X1, X2;
-        solve_row(stage + (lane < tail ? lane : 0) * row_elems, X0, X1, X2);
+        solve_row(stage + (lane < tail ? lane : 0) * slot_elems, X0, X1, X2);
         if (lane < tail) {
             double *tdst = out + ((size_t)n_tiles * TRI_W64_TILE + lane) * 3;
             tdst[0] = X0; tdst[1] = X1; tdst[2] = X2;
@@ -1219,11 +1249,10 @@ static int launch_one(const T *d_kpts, long long n, const TriParams &prm, T *d_o
         if (occ > per_sm) { per_sm = occ; n_stages = st; smem = sm_bytes; }
     }
     if (per_sm < 1) { set_error("triangulate kernel does not fit in shared memory (views=%d)", nv); return MC3D_ERR_UNSUPPORTED; }
-    // weighted double storage with a compile-time even view count whose rows need no padded slots: the warp-pipelined kernel
-    if constexpr (std::is_same<T, double>::value && MODE == MC3D_TRI_WEIGHTED && !UNDISTORT && V > 0 && V % 2 == 0 &&
-                  (3 * V * sizeof(double)) % 128 != 0) {
+    // weighted double storage with a compile-time even view count: the warp-pipelined kernel
+    if constexpr (std::is_same<T, double>::value && MODE == MC3D_TRI_WEIGHTED && !UNDISTORT && V > 0 && V % 2 == 0) {
         if (n / TRI_W64_TILE < 0x7fffffffLL) {
-            constexpr size_t smem64 = (size_t)TRI_W64_WARPS * 2 * (TRI_W64_TILE * 3 * V * sizeof(double) + TRI_W64_TILE * 3 * sizeof(double) + sizeof(uint64_t));
+            constexpr size_t smem64 = tri_w64_smem(V);
             static_assert(smem64 <= 227 * 1024, "warp64 kernel: shared memory");
             const long long warp_tiles = (n + TRI_W64_TILE - 1) / TRI_W64_TILE;
             const long long ctas = (warp_tiles + TRI_W64_WARPS - 1) / TRI_W64_WARPS;
