@@ -1095,7 +1095,8 @@ constexpr int TRI_W64_TILE = 32;
 // Rows whose size is a multiple of 128 bytes (16 views: 384 B) would put every lane of a warp on the same shared-memory
 // banks: each lane then bulk-copies its OWN row into a slot padded by 16 bytes (conflict-free), all 32 copies completing on
 // the warp's mbarrier, and -- the slots being 12.8 KB per tile -- the warp keeps ONE input stage and one output tile so that
-// 16 warps stay resident.
+// 16 warps stay resident.  Measured: V = 16 8.8e9 -> 1.26e10 points/s (80 % of the HBM roofline).  Padding the 192-byte rows of
+// V = 8 the same way (4-way conflicts) costs more in small TMA copies than it saves: 2.18e10 -> 1.75e10, not done.
 __host__ __device__ constexpr bool tri_w64_padded(int V) { return (3 * V * sizeof(double)) % 128 == 0; }
 __host__ __device__ constexpr int tri_w64_slot_elems(int V) { return 3 * V + (tri_w64_padded(V) ? 2 : 0); }
 __host__ __device__ constexpr int tri_w64_stages(int V) { return tri_w64_padded(V) ? 1 : 2; }

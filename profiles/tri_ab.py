@@ -52,22 +52,25 @@ def run(argv):
     ap.add_argument('--joints', type=int, default=17_000_000)
     ap.add_argument('--views', type=int, default=8)
     ap.add_argument('--reps', type=int, default=20)
+    ap.add_argument('--dtype', choices=['f32', 'f64'], default='f32')
     args = ap.parse_args(argv)
     import torch
     import bench
     from mc3d_b200 import _lib
     dev = torch.device('cuda:0')
-    kp, P = bench.make_triangulation_workload(args.joints, args.views, torch.float32, dev, seed=0)
+    tdt = torch.float32 if args.dtype == 'f32' else torch.float64
+    idt = torch.int32 if args.dtype == 'f32' else torch.int64
+    kp, P = bench.make_triangulation_workload(args.joints, args.views, tdt, dev, seed=0)
     rig, keep = _lib.make_rig(P)
     libs = [('default', _lib.LIB_PATH)] + [(os.path.basename(p)[8:-3], p) for p in sorted(glob.glob(os.path.join(OUT, 'libmc3d_*.so')))]
     ref = None
     stream = torch.cuda.current_stream().cuda_stream
     for name, path in libs:
         h = ctypes.CDLL(path)
-        fn = h.mc3d_triangulate_f32
+        fn = getattr(h, f'mc3d_triangulate_{args.dtype}')
         fn.restype = ctypes.c_int
-        fn.argtypes = _lib.SIGNATURES['mc3d_triangulate_f32'][1]
-        out = torch.empty((args.joints, 3), dtype=torch.float32, device=dev)
+        fn.argtypes = _lib.SIGNATURES[f'mc3d_triangulate_{args.dtype}'][1]
+        out = torch.empty((args.joints, 3), dtype=tdt, device=dev)
 
         def go():
             st = fn(kp.data_ptr(), args.joints, ctypes.byref(rig), _lib.LAYOUT_V3, _lib.TRI_WEIGHTED, 0, out.data_ptr(), stream)
@@ -87,7 +90,7 @@ def run(argv):
         else:
             ok = torch.isfinite(out).all(dim=1) & torch.isfinite(ref).all(dim=1)
             worst = (out[ok].double() - ref[ok].double()).abs().max().item()
-            same = 'bit-identical' if torch.equal(out.view(torch.int32), ref.view(torch.int32)) else f'max |diff| {worst:.2e} mm'
+            same = 'bit-identical' if torch.equal(out.view(idt), ref.view(idt)) else f'max |diff| {worst:.2e} mm'
         print(f'{name:24s} {ms:8.4f} ms  {args.joints / ms * 1e3:.4e} joints/s  {same}', flush=True)
 
 
