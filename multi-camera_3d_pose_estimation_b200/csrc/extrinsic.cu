@@ -178,7 +178,7 @@ int extrinsic_run(const mc3d_extrinsic_problem *pb, long long first_step, long l
     int st = MC3D_OK;
     if ((first_step & 1) && n_iters > 0) { st = one(first_step, stream); if (st != MC3D_OK) return st; count_launch(2); done = 1; }
     const long long pairs = (n_iters - done) / 2;
-    if (pairs >= 4) {
+    if (pairs >= 4 && !stream_is_capturing(stream)) {          // a capturing caller gets plain launches (they join its capture)
         static thread_local cudaStream_t cap_stream = nullptr;
         if (!cap_stream) MC3D_CUDA_TRY(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
@@ -187,14 +187,14 @@ int extrinsic_run(const mc3d_extrinsic_problem *pb, long long first_step, long l
         for (int u = 0; u < 2 && st == MC3D_OK; ++u) st = one(first_step + done + u, cap_stream);
         cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
         if (st != MC3D_OK) { if (graph) cudaGraphDestroy(graph); return st; }
-        MC3D_CUDA_TRY(ce);
+        if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(ce, "cudaStreamEndCapture"); }
+        GraphGuard guard{graph, nullptr};                          // destroys the graph and its exec on every exit path
         MC3D_CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+        guard.exec = exec;
         for (long long i = 0; i < pairs; ++i) MC3D_CUDA_TRY(cudaGraphLaunch(exec, stream));
         count_launch((int)(pairs * 4));
         done += pairs * 2;
         MC3D_CUDA_TRY(cudaStreamSynchronize(stream));
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(graph);
     }
     for (; done < n_iters; ++done) { st = one(first_step + done, stream); if (st != MC3D_OK) return st; count_launch(2); }
     return MC3D_OK;

@@ -23,6 +23,24 @@ void count_launch(int n = 1);
         if (_e != cudaSuccess) return ::mc3d::cuda_fail(_e, #expr); \
     } while (0)
 
+// A captured graph and its executable, destroyed on every exit path of the function that replays them (the replay loops
+// return through MC3D_CUDA_TRY on the first failing launch).
+struct GraphGuard {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    ~GraphGuard() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+    }
+};
+
+// The replay paths capture on a private stream and synchronise the caller's stream afterwards: not possible while the caller
+// is itself capturing that stream.
+inline bool stream_is_capturing(cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();   // cached SM count of the current device (148 on B200)

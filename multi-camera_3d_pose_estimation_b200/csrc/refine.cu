@@ -1204,7 +1204,7 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
     int st = MC3D_OK;
     if ((first_step & 1) && n_iters > 0) { st = one(first_step, stream); if (st != MC3D_OK) return st; count_launch(2); done = 1; }
     const long long pairs = (n_iters - done) / 2;
-    if (pairs >= 4) {
+    if (pairs >= 4 && !stream_is_capturing(stream)) {          // a capturing caller gets plain launches (they join its capture)
         static thread_local cudaStream_t cap_stream = nullptr;
         if (!cap_stream) MC3D_CUDA_TRY(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
@@ -1214,15 +1214,15 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
         for (int u = 0; u < 2 * unroll && st == MC3D_OK; ++u) st = one(first_step + done + u, cap_stream);
         cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
         if (st != MC3D_OK) { if (graph) cudaGraphDestroy(graph); return st; }
-        MC3D_CUDA_TRY(ce);
+        if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(ce, "cudaStreamEndCapture"); }
+        GraphGuard guard{graph, nullptr};                          // destroys the graph and its exec on every exit path
         MC3D_CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+        guard.exec = exec;
         const long long launches = pairs / unroll;
         for (long long i = 0; i < launches; ++i) MC3D_CUDA_TRY(cudaGraphLaunch(exec, stream));
         count_launch((int)(launches * 2 * unroll * 2));
         done += launches * 2 * unroll;
         MC3D_CUDA_TRY(cudaStreamSynchronize(stream));
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(graph);
     }
     for (; done < n_iters; ++done) { st = one(first_step + done, stream); if (st != MC3D_OK) return st; count_launch(2); }
     return MC3D_OK;
@@ -1261,7 +1261,7 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
     };
     if ((first_step & 1) && n_iters > 0) { st = one(first_step, stream); if (st != MC3D_OK) return st; done = 1; }
     const long long pairs = (n_iters - done) / 2;
-    if (pairs >= 4) {
+    if (pairs >= 4 && !stream_is_capturing(stream)) {          // a capturing caller gets plain launches (they join its capture)
         // The legacy default stream cannot be captured: record on a private stream, replay on the caller's.
         static thread_local cudaStream_t cap_stream = nullptr;
         if (!cap_stream) MC3D_CUDA_TRY(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
@@ -1274,15 +1274,15 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
         cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
         count_launch((int)(before - mc3d_launch_count()));          // recording is not launching
         if (st != MC3D_OK) { if (graph) cudaGraphDestroy(graph); return st; }
-        MC3D_CUDA_TRY(ce);
+        if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(ce, "cudaStreamEndCapture"); }
+        GraphGuard guard{graph, nullptr};                          // destroys the graph and its exec on every exit path
         MC3D_CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+        guard.exec = exec;
         const long long launches = pairs / unroll;
         for (long long i = 0; i < launches; ++i) MC3D_CUDA_TRY(cudaGraphLaunch(exec, stream));
         count_launch((int)(launches * 2 * unroll * 3));
         done += launches * 2 * unroll;
         MC3D_CUDA_TRY(cudaStreamSynchronize(stream));               // the exec must outlive its launches
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(graph);
     }
     for (; done < n_iters; ++done) { st = one(first_step + done, stream); if (st != MC3D_OK) return st; }
     return MC3D_OK;

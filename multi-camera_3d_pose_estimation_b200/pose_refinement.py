@@ -284,6 +284,10 @@ class Optimized_3d_Pose_Estimation:
         engine.release_graph()
         st = engine.state()
         hist = engine.history(st['adam_step'])
+        if st['adam_step'] > hist_cap:
+            import warnings
+            warnings.warn(f'{st["adam_step"]} optimiser steps were taken but only the first {hist_cap} are recorded: all_costs_total and the '
+                          'printed running means stop there (the early-stopping statistic on the device is unaffected)')
         if stopped_early:
             cur = {nm: _running_means(hist[:, col[nm]], len(windows))[-1] for nm in names}
             print(f"Early stopping at iteration {st['iterations'] - 1}. " + ', '.join(f'{k}: {v:.2e}' for k, v in cur.items()))
