@@ -234,13 +234,24 @@ struct RefineTables {
     int bone_start[MC3D_MAX_BONES], bone_end[MC3D_MAX_BONES];
     int adj_start[MC3D_MAX_JOINTS + 3];
     int adj_bone[2 * MC3D_MAX_BONES], adj_sign[2 * MC3D_MAX_BONES];
+    // the same adjacency, resolved for the two-phase pass 1: per (joint, incident bone) the OTHER end point's offset inside a
+    // frame (scalars), the target length, and whether this joint owns the bone's three cost sums (it is the bone's end)
+    int2 adj_other_owner[2 * MC3D_MAX_BONES];
+    double adj_len[2 * MC3D_MAX_BONES];
 };
 
 __device__ __forceinline__ void load_tables(RefineTables &tb, const mc3d_refine_problem &pb) {
     for (int i = threadIdx.x; i < MC3D_MAX_BONES; i += blockDim.x) {
         tb.bone_len[i] = pb.bone_len[i]; tb.bone_start[i] = pb.bone_start[i]; tb.bone_end[i] = pb.bone_end[i];
     }
-    for (int i = threadIdx.x; i < 2 * MC3D_MAX_BONES; i += blockDim.x) { tb.adj_bone[i] = pb.adj_bone[i]; tb.adj_sign[i] = pb.adj_sign[i]; }
+    for (int i = threadIdx.x; i < 2 * MC3D_MAX_BONES; i += blockDim.x) {
+        const int k = pb.adj_bone[i], sg = pb.adj_sign[i];
+        tb.adj_bone[i] = k; tb.adj_sign[i] = sg;
+        const bool valid = k >= 0 && k < MC3D_MAX_BONES;
+        const int other = valid ? (sg > 0 ? pb.bone_start[k] : pb.bone_end[k]) : 0;
+        tb.adj_other_owner[i] = make_int2(other * 3, sg > 0 ? 1 : 0);
+        tb.adj_len[i] = valid ? pb.bone_len[k] : 0.0;
+    }
     for (int i = threadIdx.x; i <= pb.n_joints; i += blockDim.x) tb.adj_start[i] = pb.adj_start[i];
 }
 
@@ -607,6 +618,32 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         }
         pushed = false;
     }
+    // Interior fast path (the common case: whole-window batch, two-phase step): every element lies inside the window and the
+    // boundary elements -- if there are neighbours at all -- are block 0's, so the loop carries no per-element tests; pairs of
+    // elements [e0, e1) with e0 even.  Everything else (windows of a batch, the graph variant's per-element halo pushes, the
+    // three-phase step) takes the general loop below.
+    const bool fast = mix.on && lo <= 0 && hi >= n && (bf || !(left_halo || right_halo));
+    if (fast) {
+        const long long e0 = (bf && left_halo) ? (halo_n < n ? halo_n : n) : 0;
+        long long e1 = (bf && right_halo) ? n - halo_n : n;
+        if (e1 < e0) e1 = e0;
+        const Vec2 *q1 = reinterpret_cast<const Vec2 *>(c1), *qs = reinterpret_cast<const Vec2 *>(cs);
+        const Vec2 *q2 = reinterpret_cast<const Vec2 *>(c2), *q3 = reinterpret_cast<const Vec2 *>(c3);
+        Vec2 *pm = reinterpret_cast<Vec2 *>(m), *pv = reinterpret_cast<Vec2 *>(v), *px = reinterpret_cast<Vec2 *>(x);
+        Vec2 *pbest = reinterpret_cast<Vec2 *>(bestx);
+        const T al = mix.alpha, si = mix.sigma, be = mix.beta, ga = mix.gamma;
+        for (long long i2 = (e0 >> 1) + tid0; i2 < (e1 >> 1); i2 += nthr) {
+            const Vec2 a1 = q1[i2], as = qs[i2], a2 = q2[i2], a3 = q3[i2];
+            Vec2 mv = pm[i2], vv = pv[i2], xv = px[i2];
+            const T ga_ = fma(al, a1.a, fma(si, as.a, fma(be, a2.a, ga * a3.a)));
+            const T gb_ = fma(al, a1.b, fma(si, as.b, fma(be, a2.b, ga * a3.b)));
+            adam(ga_, mv.a, vv.a, xv.a);
+            adam(gb_, mv.b, vv.b, xv.b);
+            pm[i2] = mv; pv[i2] = vv; px[i2] = xv;
+            if (improved) pbest[i2] = xv;
+        }
+        if ((e1 & 1) && e1 > e0 && tid0 == 0) one_element(e1 - 1);             // unpaired last interior element
+    } else {
     for (long long i2 = tid0; i2 < n2; i2 += nthr) {
         const long long i = i2 << 1;
         if (bf) {
@@ -638,6 +675,7 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         if (xchg) { push(i, xv.a); push(i + 1, xv.b); }
     }
     if ((n & 1) && tid0 == 0 && !(bf && is_boundary(n - 1))) one_element(n - 1);      // odd tail
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         double *nx = ctrl + CT_STATE + 16 * (parity ^ 1);
         nx[0] = step; nx[1] = run_sum; nx[2] = run_cnt; nx[3] = best; nx[4] = no_imp;
@@ -728,28 +766,40 @@ constexpr int NS2 = MC3D_REFINE_SUMS2;
 template <typename T>
 __device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, T mu_prev,
                                               double (&acc)[NS2]) {
-    const int J = pb.n_joints, C = pb.n_cams, NB = pb.n_bones, JS = J * 3;
+    // Lean form (round 2): 32-bit item indices (a shard holds < 2^31 joint-frames), every bone evaluated once per END POINT
+    // with the sign folded away -- with u = x_joint - x_other both sign v = u and sign c2 v = c2' u hold exactly -- and its
+    // three cost sums taken by the end point that owns it (the separate per-frame cost loop with its own square roots is
+    // gone), the smoothness terms selected instead of branched over.  Same values as before in g1, gs, G2', G3.
+    const int J = pb.n_joints, C = pb.n_cams, JS = J * 3;
     const T *x = (const T *)pb.x + 2LL * JS;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
     const long long gstride = pb.gauss_cam_stride;                 // 0: camera-0 Gaussians for every camera (upstream, Q1)
-    const long long n_items = pb.n_frames * J, n3 = gc_stride(pb);
+    const int n_items = (int)(pb.n_frames * J);
+    const long long n3 = gc_stride(pb);
     T *o1 = (T *)pb.gc, *os = o1 + n3, *o2 = os + n3, *o3 = o2 + n3;
     const bool ign = pb.ignore_distortions != 0;
     const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
-    const long long lo = pb.win_begin - pb.frame_offset, hi = pb.win_end - pb.frame_offset;
+    const long long lo_ = pb.win_begin - pb.frame_offset, hi_ = pb.win_end - pb.frame_offset;
+    const int lo = (int)(lo_ < -4 ? -4 : (lo_ > pb.n_frames + 4 ? pb.n_frames + 4 : lo_));     // clamped: only comparisons with
+    const int hi = (int)(hi_ < -4 ? -4 : (hi_ > pb.n_frames + 4 ? pb.n_frames + 4 : hi_));     // t - 2 .. t + 2 matter
+    const unsigned char *tok = pb.term_ok + 2;                     // tok[t] = term ending at local frame t
     T a[NS2];
 #pragma unroll
     for (int i = 0; i < NS2; ++i) a[i] = (T)0;
-    for (ItemCursor it(J); it.e < n_items; it.next(J)) {
-        const long long t = it.t, e = it.e;
-        const int j = it.j;
+    const int nthr = (int)(gridDim.x * blockDim.x);
+    int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    int t = e / J, j = e - t * J;
+    const int dt = nthr / J, dj = nthr - dt * J;
+    for (; e < n_items; e += nthr, t += dt, j += dj) {
+        if (j >= J) { j -= J; ++t; }
         T g1[3] = {(T)0, (T)0, (T)0}, gs[3] = {(T)0, (T)0, (T)0}, g2[3] = {(T)0, (T)0, (T)0}, g3[3] = {(T)0, (T)0, (T)0};
         if (t >= lo && t < hi) {
-            const T *xc = x + e * 3;
+            const T *xc = x + (long long)e * 3;
             const T X = xc[0], Y = xc[1], Z = xc[2];
             const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
-            T mx = mu0[e * 2], my = mu0[e * 2 + 1];
-            T s00 = S[e * 3], s01 = S[e * 3 + 1], s11 = S[e * 3 + 2];
+            const long long e2 = (long long)e * 2, e3 = (long long)e * 3;
+            T mx = mu0[e2], my = mu0[e2 + 1];
+            T s00 = S[e3], s01 = S[e3 + 1], s11 = S[e3 + 2];
             for (int c = 0; c < C; ++c) {
                 T cam[CAM_STRIDE];
                 load_camera(camf + c * CAM_STRIDE, cam);
@@ -765,59 +815,49 @@ __device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, con
             }
             if (do_smooth) {
                 const T two = (T)2;
-                const bool k0 = t - 2 >= lo && pb.term_ok[t + 2];
-                if (k0) {                                           // the cost term ending at this frame
-                    const T d0 = X - two * xc[-JS] + xc[-2 * JS], d1 = Y - two * xc[1 - JS] + xc[1 - 2 * JS],
-                            d2 = Z - two * xc[2 - JS] + xc[2 - 2 * JS];
-                    a[2] += d0 * d0 + d1 * d1 + d2 * d2;
-                    a[3] += j == 0 ? (T)1 : (T)0;
-                    gs[0] += d0; gs[1] += d1; gs[2] += d2;
+                const bool k0 = t - 2 >= lo && tok[t];
+                const bool k1 = self_ok && t - 1 >= lo && t + 1 < hi && tok[t + 1];
+                const bool k2 = self_ok && t + 2 < hi && tok[t + 2];
+                // x has two halo frames on either side: all five frames are addressable whatever the flags say
+                const T *xm2 = xc - 2 * JS, *xm1 = xc - JS, *xp1 = xc + JS, *xp2 = xc + 2 * JS;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const T c0 = xc[k];
+                    const T d0 = c0 - two * xm1[k] + xm2[k];              // the cost term ending at this frame
+                    const T d1 = xp1[k] - two * c0 + xm1[k];
+                    const T d2 = xp2[k] - two * xp1[k] + c0;
+                    a[2] += k0 ? d0 * d0 : (T)0;
+                    T acc_s = k0 ? d0 : (T)0;
+                    acc_s = k1 ? acc_s - two * d1 : acc_s;
+                    acc_s = k2 ? acc_s + d2 : acc_s;
+                    gs[k] = self_ok ? acc_s : (T)0;                       // a non-finite joint is frozen
                 }
-                if (self_ok) {
-                    const bool k1 = t - 1 >= lo && t + 1 < hi && pb.term_ok[t + 3];
-                    const bool k2 = t + 2 < hi && pb.term_ok[t + 4];
-                    if (k1) {
-                        gs[0] -= two * (xc[JS] - two * xc[0] + xc[-JS]); gs[1] -= two * (xc[1 + JS] - two * xc[1] + xc[1 - JS]);
-                        gs[2] -= two * (xc[2 + JS] - two * xc[2] + xc[2 - JS]);
-                    }
-                    if (k2) {
-                        gs[0] += xc[2 * JS] - two * xc[JS] + xc[0]; gs[1] += xc[1 + 2 * JS] - two * xc[1 + JS] + xc[1];
-                        gs[2] += xc[2 + 2 * JS] - two * xc[2 + JS] + xc[2];
-                    }
-                } else {
-                    gs[0] = gs[1] = gs[2] = (T)0;                   // a non-finite joint is frozen
-                }
+                a[3] += (k0 && j == 0) ? (T)1 : (T)0;
             }
-            if (do_body) {
-                const T *xf = x + t * JS;
-                for (int k = j; k < NB; k += J) {                   // cost: every bone of the frame once
-                    const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
-                    const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
-                    const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-                    if (finite_c(b)) {
-                        const T al = (T)tb.bone_len[k];
-                        a[4] += al * b; a[5] += b * b; a[6] += al * al;
-                    }
-                }
-                if (self_ok)
-                    for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {   // gradient: the bones at this joint
-                        const int k = tb.adj_bone[q];
-                        const T sign = (T)tb.adj_sign[q];
-                        const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
-                        const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
-                        const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-                        if (finite_c(b) && b > (T)0) {
-                            const T c2 = sign * ((T)tb.bone_len[k] - mu_prev * b) / b;     // G2 - mu_prev G3
-                            g2[0] = fma(c2, v0, g2[0]); g2[1] = fma(c2, v1, g2[1]); g2[2] = fma(c2, v2, g2[2]);
-                            g3[0] = fma(sign, v0, g3[0]); g3[1] = fma(sign, v1, g3[1]); g3[2] = fma(sign, v2, g3[2]);
+            if (do_body && self_ok) {
+                const T *xf = xc - j * 3;
+                for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {   // the bones at this joint
+                    const int2 oo = tb.adj_other_owner[q];
+                    const T *po = xf + oo.x;
+                    const T u0 = X - po[0], u1 = Y - po[1], u2 = Z - po[2];      // = sign (end - start)
+                    const T len = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+                    if (finite_c(len)) {
+                        const T al = (T)tb.adj_len[q];
+                        if (oo.y) { a[4] += al * len; a[5] += len * len; a[6] += al * al; }    // the bone's cost sums, once
+                        if (len > (T)0) {
+                            const T c2 = (al - mu_prev * len) / len;                             // G2 - mu_prev G3
+                            g2[0] = fma(c2, u0, g2[0]); g2[1] = fma(c2, u1, g2[1]); g2[2] = fma(c2, u2, g2[2]);
+                            g3[0] += u0; g3[1] += u1; g3[2] += u2;
                         }
                     }
+                }
             }
             if (!self_ok) g1[0] = g1[1] = g1[2] = (T)0;
         }
+        const long long o = (long long)e * 3;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            o1[e * 3 + k] = g1[k]; os[e * 3 + k] = gs[k]; o2[e * 3 + k] = g2[k]; o3[e * 3 + k] = g3[k];
+            o1[o + k] = g1[k]; os[o + k] = gs[k]; o2[o + k] = g2[k]; o3[o + k] = g3[k];
             a[7] = fma(g1[k], g1[k], a[7]);   a[8] = fma(g1[k], gs[k], a[8]);   a[9] = fma(g1[k], g2[k], a[9]);
             a[10] = fma(g1[k], g3[k], a[10]); a[11] = fma(gs[k], gs[k], a[11]); a[12] = fma(gs[k], g2[k], a[12]);
             a[13] = fma(gs[k], g3[k], a[13]); a[14] = fma(g2[k], g2[k], a[14]); a[15] = fma(g2[k], g3[k], a[15]);
