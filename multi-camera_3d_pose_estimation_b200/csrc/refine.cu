@@ -159,8 +159,24 @@ template <typename C> struct Lim;
 template <> struct Lim<float> { static __device__ __forceinline__ float big() { return 3.0e38f; } };
 template <> struct Lim<double> { static __device__ __forceinline__ double big() { return 1.0e300; } };
 template <typename C> __device__ __forceinline__ bool finite_c(C v) { return fabs(v) <= Lim<C>::big(); }
-__device__ __forceinline__ float rcp_c(float v) { return 1.0f / v; }
+// Float state: the special-function unit's reciprocal / square root (one MUFU, <= 1-2 ulp) with one Newton step for the
+// reciprocals of the projection -- no IEEE slow path (a subroutine call per division that also pins the schedule).  The
+// float run is compared with upstream's float32 history at 1e-4; these differ from correctly rounded results in the last
+// bit.  Double state: IEEE.
+__device__ __forceinline__ float rcp_c(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return fmaf(r, fmaf(-v, r, 1.0f), r);
+}
 __device__ __forceinline__ double rcp_c(double v) { return 1.0 / v; }
+__device__ __forceinline__ float sqrt_c(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ double sqrt_c(double v) { return sqrt(v); }
+__device__ __forceinline__ float div_c(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double div_c(double a, double b) { return a / b; }
 
 // Reprojection term of one camera: returns 0.5 d^T S d, and (when GRAD) adds J^T S d * scale to g[3].
 constexpr int CAM_STRIDE = 28;      // K[9] R[9] T[3] dist[5] + 2 pad: a whole number of 16-byte shared-memory loads
@@ -361,7 +377,7 @@ __device__ __forceinline__ void costs_loop(const mc3d_refine_problem &pb, const 
             for (int k = j; k < NB; k += J) {
                 const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
                 const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
-                const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                const T b = sqrt_c(v0 * v0 + v1 * v1 + v2 * v2);
                 if (finite_c(b)) {
                     const T a = (T)tb.bone_len[k];
                     accf[4] += a * b; accf[5] += b * b; accf[6] += a * a;
@@ -467,9 +483,9 @@ __device__ __forceinline__ double grad_loop(const mc3d_refine_problem &pb, const
                     const T sign = (T)tb.adj_sign[q];
                     const T *ps = xf + tb.bone_start[k] * 3, *pe = xf + tb.bone_end[k] * 3;
                     const T v0 = pe[0] - ps[0], v1 = pe[1] - ps[1], v2 = pe[2] - ps[2];
-                    const T b = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+                    const T b = sqrt_c(v0 * v0 + v1 * v1 + v2 * v2);
                     if (finite_c(b) && b > (T)0) {
-                        const T coef = sign * body_c * ((T)tb.bone_len[k] - mu * b) / b;
+                        const T coef = div_c(sign * body_c * ((T)tb.bone_len[k] - mu * b), b);
                         g[0] = fma(coef, v0, g[0]); g[1] = fma(coef, v1, g[1]); g[2] = fma(coef, v2, g[2]);
                     }
                 }
@@ -532,7 +548,8 @@ __device__ __forceinline__ void halo_flags(const mc3d_refine_problem &pb, long l
 template <typename T>
 __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int parity, int end_of_iteration, double gnorm2,
                                           const double *st, const RefineDerived &dv, bool xchg, double *bias, bool both_parities,
-                                          const GradMix<T> mix, bool boundary_first = false, long long halo_flag_seq = 0) {
+                                          const GradMix<T> mix, bool boundary_first = false, long long halo_flag_seq = 0,
+                                          bool *best_pending = nullptr, bool last_of_launch = true) {
     double *ctrl = pb.ctrl;
     const double gnorm = sqrt(gnorm2);
     const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
@@ -547,6 +564,16 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         if (improved) { best = mean; no_imp = 0.0; } else { no_imp += 1.0; }
         iters += 1.0;
         stop = (no_imp >= (double)pb.patience) || (iters > (double)pb.max_iter);
+    }
+    // The best-trajectory snapshot (x after the update of a step whose running mean improved).  The persistent kernel defers it
+    // (best_pending): while consecutive steps improve, the snapshot would be overwritten again at once, so nothing is written
+    // until a step does NOT improve -- then the value of x from before this step's update is the snapshot -- or the launch
+    // ends.  Saves 3 of the 12 scalars a step writes per item while the cost is falling.
+    bool wr_new = improved, wr_old = false;
+    if (best_pending) {
+        wr_new = improved && (last_of_launch || stop);
+        wr_old = !improved && *best_pending;
+        *best_pending = improved && !wr_new;
     }
     if (threadIdx.x == 0) {                                        // two double pow() per block, not per thread
         bias[0] = 1.0 - pow(pb.beta1, step);
@@ -569,8 +596,8 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         gi = clip_nan ? (T)NAN : gi * clipT;
         mi = mi + (gi - mi) * w1;                                  // exp_avg.lerp_(grad, 1 - beta1)
         vi = vi * b2 + w2 * gi * gi;                               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-        const T denom = sqrt(vi) * inv_bc2_sqrt + eps;
-        xi = xi - step_size * (mi / denom);                        // param.addcdiv_(exp_avg, denom, value=-step_size)
+        const T denom = sqrt_c(vi) * inv_bc2_sqrt + eps;
+        xi = xi - step_size * div_c(mi, denom);                    // param.addcdiv_(exp_avg, denom, value=-step_size)
     };
     // two scalars per access: the halo offset of x (2 J 3 scalars) is always 8-byte (float) / 16-byte (double) aligned
     struct alignas(2 * sizeof(T)) Vec2 { T a, b; };
@@ -595,9 +622,10 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
     };
     auto one_element = [&](long long i) {
         T gi = grad_at(i), mi = m[i], vi = v[i], xi = x[i];
+        if (wr_old) bestx[i] = xi;
         adam(gi, mi, vi, xi);
         m[i] = mi; v[i] = vi; x[i] = xi;
-        if (improved) bestx[i] = xi;
+        if (wr_new) bestx[i] = xi;
         if (xchg) push(i, xi);
     };
     const bool bf = boundary_first && (left_halo || right_halo);
@@ -637,10 +665,11 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
             Vec2 mv = pm[i2], vv = pv[i2], xv = px[i2];
             const T ga_ = fma(al, a1.a, fma(si, as.a, fma(be, a2.a, ga * a3.a)));
             const T gb_ = fma(al, a1.b, fma(si, as.b, fma(be, a2.b, ga * a3.b)));
+            if (wr_old) pbest[i2] = xv;
             adam(ga_, mv.a, vv.a, xv.a);
             adam(gb_, mv.b, vv.b, xv.b);
             pm[i2] = mv; pv[i2] = vv; px[i2] = xv;
-            if (improved) pbest[i2] = xv;
+            if (wr_new) pbest[i2] = xv;
         }
         if ((e1 & 1) && e1 > e0 && tid0 == 0) one_element(e1 - 1);             // unpaired last interior element
     } else {
@@ -666,12 +695,13 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         Vec2 mv = reinterpret_cast<Vec2 *>(m)[i2], vv = reinterpret_cast<Vec2 *>(v)[i2], xv = reinterpret_cast<Vec2 *>(x)[i2];
         if (!(i >= lo && i < hi)) gv.a = (T)0;
         if (!(i + 1 >= lo && i + 1 < hi)) gv.b = (T)0;
+        if (wr_old) reinterpret_cast<Vec2 *>(bestx)[i2] = xv;
         adam(gv.a, mv.a, vv.a, xv.a);
         adam(gv.b, mv.b, vv.b, xv.b);
         reinterpret_cast<Vec2 *>(m)[i2] = mv;
         reinterpret_cast<Vec2 *>(v)[i2] = vv;
         reinterpret_cast<Vec2 *>(x)[i2] = xv;
-        if (improved) reinterpret_cast<Vec2 *>(bestx)[i2] = xv;
+        if (wr_new) reinterpret_cast<Vec2 *>(bestx)[i2] = xv;
         if (xchg) { push(i, xv.a); push(i + 1, xv.b); }
     }
     if ((n & 1) && tid0 == 0 && !(bf && is_boundary(n - 1))) one_element(n - 1);      // odd tail
@@ -763,26 +793,124 @@ __device__ __forceinline__ void grid_barrier(const mc3d_refine_problem &pb, int 
 // products that give |g|^2 as a quadratic form.  sums: [0..7) as in pass A, [7..17) = 11 1s 12 13 ss s2 s3 22 23 33.
 constexpr int NS2 = MC3D_REFINE_SUMS2;
 
+// Everything pass 1 needs to know that does not depend on the item.
+template <typename T>
+struct P1Const {
+    int J, C, JS, lo, hi;
+    bool ign, do_smooth, do_body;
+    long long gstride;
+    T mu_prev;
+    const unsigned char *tok;                                      // tok[t] = smoothness term ending at local frame t
+};
+
+template <typename T>
+__device__ __forceinline__ P1Const<T> p1_const(const mc3d_refine_problem &pb, T mu_prev) {
+    P1Const<T> k;
+    k.J = pb.n_joints; k.C = pb.n_cams; k.JS = k.J * 3;
+    const long long lo_ = pb.win_begin - pb.frame_offset, hi_ = pb.win_end - pb.frame_offset;
+    k.lo = (int)(lo_ < -4 ? -4 : (lo_ > pb.n_frames + 4 ? pb.n_frames + 4 : lo_));     // clamped: only comparisons with
+    k.hi = (int)(hi_ < -4 ? -4 : (hi_ > pb.n_frames + 4 ? pb.n_frames + 4 : hi_));     // t - 2 .. t + 2 matter
+    k.ign = pb.ignore_distortions != 0;
+    k.do_smooth = pb.lambda_smooth > 0.0; k.do_body = pb.lambda_body > 0.0;
+    k.gstride = pb.gauss_cam_stride;                               // 0: camera-0 Gaussians for every camera (upstream, Q1)
+    k.mu_prev = mu_prev;
+    k.tok = pb.term_ok + 2;
+    return k;
+}
+
+// One (frame t, joint j) item of pass 1.  Lean form (round 2): every bone is evaluated once per END POINT with the sign folded
+// away -- with u = x_joint - x_other both sign v = u and sign c2 v = c2' u hold exactly -- and its three cost sums are taken by
+// the end point that owns it; the smoothness terms are selected, not branched over.  xc points at the item's own position with
+// its frame neighbours JS scalars apart (global memory, or a warp's shared-memory window), mup / Sp at its Gaussian (camera
+// c's at + c * gstride items, global memory only), tk = the three smoothness flags tok[t], tok[t+1], tok[t+2].  The four
+// gradient components go to out[q * ostride + k]; a[] collects the NS2 partial sums.
+template <typename T>
+__device__ __forceinline__ void costgrad_item(const P1Const<T> &pc, const RefineTables &tb, const T *camf, int t, int j,
+                                              const T *xc, const T *mup, const T *Sp, unsigned tk0, unsigned tk1, unsigned tk2,
+                                              T *out, long long ostride, T (&a)[NS2]) {
+    const int J = pc.J, JS = pc.JS, lo = pc.lo, hi = pc.hi;
+    T g1[3] = {(T)0, (T)0, (T)0}, gs[3] = {(T)0, (T)0, (T)0}, g2[3] = {(T)0, (T)0, (T)0}, g3[3] = {(T)0, (T)0, (T)0};
+    if (t >= lo && t < hi) {
+        const T X = xc[0], Y = xc[1], Z = xc[2];
+        const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
+        T mx = mup[0], my = mup[1];
+        T s00 = Sp[0], s01 = Sp[1], s11 = Sp[2];
+        for (int c = 0; c < pc.C; ++c) {
+            T cam[CAM_STRIDE];
+            load_camera(camf + c * CAM_STRIDE, cam);
+            if (pc.gstride && c > 0) {
+                const long long ec = c * pc.gstride;
+                mx = mup[ec * 2]; my = mup[ec * 2 + 1];
+                s00 = Sp[ec * 3]; s01 = Sp[ec * 3 + 1]; s11 = Sp[ec * 3 + 2];
+            }
+            const T q = reproject_term<true, T>(cam, pc.ign, X, Y, Z, mx, my, s00, s01, s11, (T)1, g1);   // adds only when finite
+            const bool ok = finite_c(q);
+            a[0] += ok ? q : (T)0;
+            a[1] += ok ? (T)1 : (T)0;
+        }
+        if (pc.do_smooth) {
+            const T two = (T)2;
+            const bool k0 = t - 2 >= lo && tk0;
+            const bool k1 = self_ok && t - 1 >= lo && t + 1 < hi && tk1;
+            const bool k2 = self_ok && t + 2 < hi && tk2;
+            // x has two halo frames on either side: all five frames are addressable whatever the flags say
+            const T *xm2 = xc - 2 * JS, *xm1 = xc - JS, *xp1 = xc + JS, *xp2 = xc + 2 * JS;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const T c0 = xc[k];
+                const T d0 = c0 - two * xm1[k] + xm2[k];              // the cost term ending at this frame
+                const T d1 = xp1[k] - two * c0 + xm1[k];
+                const T d2 = xp2[k] - two * xp1[k] + c0;
+                a[2] += k0 ? d0 * d0 : (T)0;
+                T acc_s = k0 ? d0 : (T)0;
+                acc_s = k1 ? acc_s - two * d1 : acc_s;
+                acc_s = k2 ? acc_s + d2 : acc_s;
+                gs[k] = self_ok ? acc_s : (T)0;                       // a non-finite joint is frozen
+            }
+            a[3] += (k0 && j == 0) ? (T)1 : (T)0;
+        }
+        if (pc.do_body && self_ok) {
+            const T *xf = xc - j * 3;
+            for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {   // the bones at this joint
+                const int2 oo = tb.adj_other_owner[q];
+                const T *po = xf + oo.x;
+                const T u0 = X - po[0], u1 = Y - po[1], u2 = Z - po[2];      // = sign (end - start)
+                const T len = sqrt_c(u0 * u0 + u1 * u1 + u2 * u2);
+                if (finite_c(len)) {
+                    const T al = (T)tb.adj_len[q];
+                    if (oo.y) { a[4] += al * len; a[5] += len * len; a[6] += al * al; }    // the bone's cost sums, once
+                    if (len > (T)0) {
+                        const T c2 = div_c(al - pc.mu_prev * len, len);                      // G2 - mu_prev G3
+                        g2[0] = fma(c2, u0, g2[0]); g2[1] = fma(c2, u1, g2[1]); g2[2] = fma(c2, u2, g2[2]);
+                        g3[0] += u0; g3[1] += u1; g3[2] += u2;
+                    }
+                }
+            }
+        }
+        if (!self_ok) g1[0] = g1[1] = g1[2] = (T)0;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        out[k] = g1[k]; out[ostride + k] = gs[k]; out[2 * ostride + k] = g2[k]; out[3 * ostride + k] = g3[k];
+        a[7] = fma(g1[k], g1[k], a[7]);   a[8] = fma(g1[k], gs[k], a[8]);   a[9] = fma(g1[k], g2[k], a[9]);
+        a[10] = fma(g1[k], g3[k], a[10]); a[11] = fma(gs[k], gs[k], a[11]); a[12] = fma(gs[k], g2[k], a[12]);
+        a[13] = fma(gs[k], g3[k], a[13]); a[14] = fma(g2[k], g2[k], a[14]); a[15] = fma(g2[k], g3[k], a[15]);
+        a[16] = fma(g3[k], g3[k], a[16]);
+    }
+}
+
+// Grid-stride form: one item per thread and trip, neighbours from global memory through L1 (32-bit item indices: a shard
+// holds < 2^31 joint-frames).
 template <typename T>
 __device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, T mu_prev,
                                               double (&acc)[NS2]) {
-    // Lean form (round 2): 32-bit item indices (a shard holds < 2^31 joint-frames), every bone evaluated once per END POINT
-    // with the sign folded away -- with u = x_joint - x_other both sign v = u and sign c2 v = c2' u hold exactly -- and its
-    // three cost sums taken by the end point that owns it (the separate per-frame cost loop with its own square roots is
-    // gone), the smoothness terms selected instead of branched over.  Same values as before in g1, gs, G2', G3.
-    const int J = pb.n_joints, C = pb.n_cams, JS = J * 3;
-    const T *x = (const T *)pb.x + 2LL * JS;
+    const P1Const<T> pc = p1_const<T>(pb, mu_prev);
+    const int J = pc.J;
+    const T *x = (const T *)pb.x + 2LL * pc.JS;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
-    const long long gstride = pb.gauss_cam_stride;                 // 0: camera-0 Gaussians for every camera (upstream, Q1)
     const int n_items = (int)(pb.n_frames * J);
     const long long n3 = gc_stride(pb);
-    T *o1 = (T *)pb.gc, *os = o1 + n3, *o2 = os + n3, *o3 = o2 + n3;
-    const bool ign = pb.ignore_distortions != 0;
-    const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
-    const long long lo_ = pb.win_begin - pb.frame_offset, hi_ = pb.win_end - pb.frame_offset;
-    const int lo = (int)(lo_ < -4 ? -4 : (lo_ > pb.n_frames + 4 ? pb.n_frames + 4 : lo_));     // clamped: only comparisons with
-    const int hi = (int)(hi_ < -4 ? -4 : (hi_ > pb.n_frames + 4 ? pb.n_frames + 4 : hi_));     // t - 2 .. t + 2 matter
-    const unsigned char *tok = pb.term_ok + 2;                     // tok[t] = term ending at local frame t
+    T *o1 = (T *)pb.gc;
     T a[NS2];
 #pragma unroll
     for (int i = 0; i < NS2; ++i) a[i] = (T)0;
@@ -792,78 +920,121 @@ __device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, con
     const int dt = nthr / J, dj = nthr - dt * J;
     for (; e < n_items; e += nthr, t += dt, j += dj) {
         if (j >= J) { j -= J; ++t; }
-        T g1[3] = {(T)0, (T)0, (T)0}, gs[3] = {(T)0, (T)0, (T)0}, g2[3] = {(T)0, (T)0, (T)0}, g3[3] = {(T)0, (T)0, (T)0};
-        if (t >= lo && t < hi) {
-            const T *xc = x + (long long)e * 3;
-            const T X = xc[0], Y = xc[1], Z = xc[2];
-            const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
-            const long long e2 = (long long)e * 2, e3 = (long long)e * 3;
-            T mx = mu0[e2], my = mu0[e2 + 1];
-            T s00 = S[e3], s01 = S[e3 + 1], s11 = S[e3 + 2];
-            for (int c = 0; c < C; ++c) {
-                T cam[CAM_STRIDE];
-                load_camera(camf + c * CAM_STRIDE, cam);
-                if (gstride && c > 0) {
-                    const long long ec = e + c * gstride;
-                    mx = mu0[ec * 2]; my = mu0[ec * 2 + 1];
-                    s00 = S[ec * 3]; s01 = S[ec * 3 + 1]; s11 = S[ec * 3 + 2];
-                }
-                const T q = reproject_term<true, T>(cam, ign, X, Y, Z, mx, my, s00, s01, s11, (T)1, g1);   // adds only when finite
-                const bool ok = finite_c(q);
-                a[0] += ok ? q : (T)0;
-                a[1] += ok ? (T)1 : (T)0;
-            }
-            if (do_smooth) {
-                const T two = (T)2;
-                const bool k0 = t - 2 >= lo && tok[t];
-                const bool k1 = self_ok && t - 1 >= lo && t + 1 < hi && tok[t + 1];
-                const bool k2 = self_ok && t + 2 < hi && tok[t + 2];
-                // x has two halo frames on either side: all five frames are addressable whatever the flags say
-                const T *xm2 = xc - 2 * JS, *xm1 = xc - JS, *xp1 = xc + JS, *xp2 = xc + 2 * JS;
+        const long long e2 = (long long)e * 2, e3 = (long long)e * 3;
+        costgrad_item<T>(pc, tb, camf, t, j, x + e3, mu0 + e2, S + e3, pc.tok[t], pc.tok[t + 1], pc.tok[t + 2], o1 + e3, n3, a);
+    }
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const T c0 = xc[k];
-                    const T d0 = c0 - two * xm1[k] + xm2[k];              // the cost term ending at this frame
-                    const T d1 = xp1[k] - two * c0 + xm1[k];
-                    const T d2 = xp2[k] - two * xp1[k] + c0;
-                    a[2] += k0 ? d0 * d0 : (T)0;
-                    T acc_s = k0 ? d0 : (T)0;
-                    acc_s = k1 ? acc_s - two * d1 : acc_s;
-                    acc_s = k2 ? acc_s + d2 : acc_s;
-                    gs[k] = self_ok ? acc_s : (T)0;                       // a non-finite joint is frozen
-                }
-                a[3] += (k0 && j == 0) ? (T)1 : (T)0;
-            }
-            if (do_body && self_ok) {
-                const T *xf = xc - j * 3;
-                for (int q = tb.adj_start[j]; q < tb.adj_start[j + 1]; ++q) {   // the bones at this joint
-                    const int2 oo = tb.adj_other_owner[q];
-                    const T *po = xf + oo.x;
-                    const T u0 = X - po[0], u1 = Y - po[1], u2 = Z - po[2];      // = sign (end - start)
-                    const T len = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
-                    if (finite_c(len)) {
-                        const T al = (T)tb.adj_len[q];
-                        if (oo.y) { a[4] += al * len; a[5] += len * len; a[6] += al * al; }    // the bone's cost sums, once
-                        if (len > (T)0) {
-                            const T c2 = (al - mu_prev * len) / len;                             // G2 - mu_prev G3
-                            g2[0] = fma(c2, u0, g2[0]); g2[1] = fma(c2, u1, g2[1]); g2[2] = fma(c2, u2, g2[2]);
-                            g3[0] += u0; g3[1] += u1; g3[2] += u2;
-                        }
-                    }
-                }
-            }
-            if (!self_ok) g1[0] = g1[1] = g1[2] = (T)0;
+    for (int i = 0; i < NS2; ++i) acc[i] = (double)a[i];
+}
+
+// ---- pass 1, every warp its own pipeline -----------------------------------------------------------------------------
+// The persistent kernel's pass 1 for camera-0 Gaussians: a warp takes tiles of P1_TILE consecutive items (one per lane).
+// Its lane 0 fetches, one tile ahead, everything the tile reads with three 1-D TMA bulk copies into the warp's private
+// two-stage ring -- the x window (the tile's items with two frames on either side: stencil neighbours and bone end points come
+// from shared memory, stride-3 accesses are conflict-free), the tile's mu0 and Sigma^-1 -- completing on the stage's mbarrier;
+// the four gradient components leave through a private output tile and four bulk stores.  No block barrier, no global load
+// in the item's dependency chain.  In ext items (x with its two halo frames) a tile's window starts at the tile's own index,
+// so every copy is 16-byte aligned whatever J is; the ragged last tile is filled and written with plain accesses.
+constexpr int P1_TILE = 32, P1_STAGES = 2;
+__host__ __device__ __forceinline__ int p1_win_scalars(int J) { return (P1_TILE + 4 * J) * 3; }
+__host__ __device__ __forceinline__ int p1_stage_scalars(int J) { return p1_win_scalars(J) + P1_TILE * 5; }
+__host__ __device__ __forceinline__ int p1_warp_scalars(int J) { return P1_STAGES * p1_stage_scalars(J) + 4 * P1_TILE * 3; }
+
+struct P1Ring {
+    uint32_t issued, consumed;                                     // full tiles this warp has fetched / used since launch
+};
+
+template <typename T>
+__device__ __forceinline__ void costgrad_tiles(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, T mu_prev,
+                                               double (&acc)[NS2], T *wsm, uint64_t *bars, P1Ring &ring) {
+    const P1Const<T> pc = p1_const<T>(pb, mu_prev);
+    const int J = pc.J, lane = threadIdx.x & 31;
+    const int n_items = (int)(pb.n_frames * J), n_tiles = (n_items + P1_TILE - 1) / P1_TILE;
+    const int n_warps = (int)(gridDim.x * (blockDim.x >> 5)), gw = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    const T *x_ext = (const T *)pb.x, *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
+    const long long n3 = gc_stride(pb);
+    T *gc = (T *)pb.gc;
+    const int win = p1_win_scalars(J), stage = p1_stage_scalars(J);
+    T *outt = wsm + P1_STAGES * stage;                             // [4][P1_TILE * 3]
+    const uint32_t win_bytes = (uint32_t)(win * sizeof(T)), mu_bytes = (uint32_t)(P1_TILE * 2 * sizeof(T)),
+                   s_bytes = (uint32_t)(P1_TILE * 3 * sizeof(T));
+    auto issue = [&](int tile) {                                   // lane 0; full tiles only
+        if ((tile + 1) * P1_TILE > n_items) return;
+        const uint32_t s = ring.issued % P1_STAGES;
+        T *dst = wsm + s * stage;
+        const long long e0 = (long long)tile * P1_TILE;
+        mbar_arrive_expect_tx(bars + s, win_bytes + mu_bytes + s_bytes);
+        bulk_g2s(dst, x_ext + e0 * 3, win_bytes, bars + s);
+        bulk_g2s(dst + win, mu0 + e0 * 2, mu_bytes, bars + s);
+        bulk_g2s(dst + win + P1_TILE * 2, S + e0 * 3, s_bytes, bars + s);
+    };
+    T a[NS2];
+#pragma unroll
+    for (int i = 0; i < NS2; ++i) a[i] = (T)0;
+    int tile = gw;
+    if (lane == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");           // x was written with plain stores (pass 2, the neighbours' halos)
+        if (tile < n_tiles) issue(tile);
+    }
+    if (tile < n_tiles && (tile + 1) * P1_TILE <= n_items) ++ring.issued;
+    int e = tile * P1_TILE + lane;
+    int t = e / J, j = e - t * J;
+    const int de = n_warps * P1_TILE, dt = de / J, dj = de - dt * J;
+    bool stored = false;
+    for (; tile < n_tiles; tile += n_warps, e += de, t += dt, j += dj) {
+        if (j >= J) { j -= J; ++t; }
+        const int next = tile + n_warps;
+        if (next < n_tiles) {
+            if (lane == 0) issue(next);
+            if ((next + 1) * P1_TILE <= n_items) ++ring.issued;
         }
-        const long long o = (long long)e * 3;
+        const bool valid = e < n_items, full = (tile + 1) * P1_TILE <= n_items;
+        unsigned tk0 = 0, tk1 = 0, tk2 = 0;
+        if (valid) { tk0 = pc.tok[t]; tk1 = pc.tok[t + 1]; tk2 = pc.tok[t + 2]; }
+        const uint32_t s = ring.consumed % P1_STAGES;
+        T *buf = wsm + s * stage;
+        if (full) {
+            mbar_wait(bars + s, (ring.consumed / P1_STAGES) & 1);
+            ++ring.consumed;
+        } else {                                                   // the ragged last tile: nothing of this warp's is in flight
+            const long long e0 = (long long)tile * P1_TILE;
+            const long long ext_n = (pb.n_frames + 4) * (long long)pc.JS;
+            for (int i = lane; i < win; i += 32) buf[i] = e0 * 3 + i < ext_n ? x_ext[e0 * 3 + i] : (T)0;
+            for (int i = lane; i < P1_TILE * 2; i += 32) buf[win + i] = e0 * 2 + i < (long long)n_items * 2 ? mu0[e0 * 2 + i] : (T)0;
+            for (int i = lane; i < P1_TILE * 3; i += 32) buf[win + P1_TILE * 2 + i] = e0 * 3 + i < (long long)n_items * 3 ? S[e0 * 3 + i] : (T)0;
+            __syncwarp();
+        }
+        if (stored) {                                              // the previous tile's bulk stores have read the output tile
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+        }
+        if (valid)
+            costgrad_item<T>(pc, tb, camf, t, j, buf + (lane + 2 * J) * 3, buf + win + lane * 2, buf + win + P1_TILE * 2 + lane * 3,
+                             tk0, tk1, tk2, outt + lane * 3, P1_TILE * 3, a);
+        if (full) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                const long long e0 = (long long)tile * P1_TILE;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            o1[o + k] = g1[k]; os[o + k] = gs[k]; o2[o + k] = g2[k]; o3[o + k] = g3[k];
-            a[7] = fma(g1[k], g1[k], a[7]);   a[8] = fma(g1[k], gs[k], a[8]);   a[9] = fma(g1[k], g2[k], a[9]);
-            a[10] = fma(g1[k], g3[k], a[10]); a[11] = fma(gs[k], gs[k], a[11]); a[12] = fma(gs[k], g2[k], a[12]);
-            a[13] = fma(gs[k], g3[k], a[13]); a[14] = fma(g2[k], g2[k], a[14]); a[15] = fma(g2[k], g3[k], a[15]);
-            a[16] = fma(g3[k], g3[k], a[16]);
+                for (int q = 0; q < 4; ++q) bulk_s2g(gc + q * n3 + e0 * 3, outt + q * P1_TILE * 3, s_bytes);
+                bulk_commit();
+            }
+            stored = true;
+        } else {
+            __syncwarp();
+            const long long e0 = (long long)tile * P1_TILE;
+            const int left = (n_items - (int)e0) * 3;
+            for (int q = 0; q < 4; ++q)
+                for (int i = lane; i < left; i += 32) gc[q * n3 + e0 * 3 + i] = outt[q * P1_TILE * 3 + i];
+            stored = false;
         }
     }
+    if (lane == 0) {
+        bulk_wait_all<0>();                                         // the components are in global memory ...
+        asm volatile("fence.proxy.async;" ::: "memory");           // ... before the barrier that lets pass 2 read them
+    }
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < NS2; ++i) acc[i] = (double)a[i];
 }
@@ -1028,7 +1199,9 @@ refine_step2_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
 // step at 100 000 frames).
 template <typename T, int BLOCKS>
 __global__ void __launch_bounds__(RF_THREADS, BLOCKS)
-refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_parity, long long n_iters) {
+refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_parity, long long n_iters, int tiled) {
+    extern __shared__ __align__(16) unsigned char p1_smem[];      // tiled pass 1: per warp a two-stage ring + the output tile
+    __shared__ __align__(8) uint64_t p1_bars[(RF_THREADS / 32) * P1_STAGES];
     __shared__ double red[8 * NS2];
     __shared__ RefineTables tb;
     __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
@@ -1038,6 +1211,14 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
     double *ctrl = pb.ctrl;
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
     load_cameras_and_tables(pb, tb, camf);
+    T *wsm = reinterpret_cast<T *>(p1_smem) + (size_t)(threadIdx.x >> 5) * p1_warp_scalars(pb.n_joints);
+    uint64_t *bars = p1_bars + (threadIdx.x >> 5) * P1_STAGES;
+    P1Ring ring{0u, 0u};
+    bool best_pending = false;                                     // the best snapshot is owed (see step_loop)
+    if (tiled && (threadIdx.x & 31) == 0) {
+        for (int s = 0; s < P1_STAGES; ++s) mbar_init(bars + s, 1);
+        fence_mbar_init();
+    }
     __syncthreads();
     int parity = first_parity & 1;
     for (long long it = 0; it < n_iters; ++it, parity ^= 1) {
@@ -1056,7 +1237,8 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
         }
         {   // pass 1
             double acc[NS2];
-            costgrad_loop<T>(pb, tb, camf, (T)st[8], acc);
+            if (tiled) costgrad_tiles<T>(pb, tb, camf, (T)st[8], acc, wsm, bars, ring);
+            else costgrad_loop<T>(pb, tb, camf, (T)st[8], acc);
             block_reduce_add<NS2>(acc, red, mine->acc2[parity]);
         }
         if (take_ticket(mine, 0)) publish2_ll(pb, parity, seq);
@@ -1064,7 +1246,8 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
         const RefineDerived dv = derive(pb, tot, st);
         double gnorm2;
         const GradMix<T> mix = mix_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);   // mu_prev as pass 1 used it
-        step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, true, mix, true, seq);      // halos leave first (block 0)
+        step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, true, mix, true, seq,      // halos leave first (block 0)
+                     &best_pending, it + 1 == n_iters);
         grid_barrier(pb, 2, seq);                                   // closes the step; local only
     }
 }
@@ -1212,10 +1395,20 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
     const bool small = shard_is_small(pb);
     mc3d_refine_problem prob = *pb;
     if (fused_env == 1 || (fused_env != 0 && small)) {
-        const bool big = n_items > 425000;
+        const char *envb = getenv("MC3D_REFINE_BLOCKS");            // 2 / 3 force a register build (measurement)
+        const bool big = envb ? atoi(envb) >= 3 : n_items > 425000;
         auto kern = big ? refine_fused2_kernel<T, 3> : refine_fused2_kernel<T, 2>;
+        // Tiled pass 1 (every warp its own TMA pipeline): camera-0 Gaussians, 16-byte aligned arrays, and a ring that leaves
+        // room for the build's CTAs per SM; otherwise the grid-stride pass 1.
+        const char *envt = getenv("MC3D_REFINE_TILED");             // 1 selects it (measured slower than the grid-stride pass)
+        size_t dyn = (size_t)(RF_THREADS / 32) * p1_warp_scalars(pb->n_joints) * sizeof(T);
+        int tiled = (envt && atoi(envt) != 0) && pb->gauss_cam_stride == 0 && aligned16(pb->x) && aligned16(pb->mu0) &&
+                    aligned16(pb->S) && aligned16(pb->gc) && dyn <= (size_t)(big ? 60 : 90) * 1024 && n_items < (1LL << 30);
+        if (!tiled) dyn = 0;
+        // static + dynamic shared memory beyond 48 KB needs the opt-in (the kernel's static part is ~12 KB)
+        if (dyn > 0) { const int as = func_max_smem_once((const void *)kern, 200 * 1024); if (as != MC3D_OK) return as; }
         int per_sm = 0;
-        MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RF_THREADS, 0));
+        MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RF_THREADS, dyn));
         if (per_sm < 1) { set_error("persistent refinement kernel does not fit on an SM"); return MC3D_ERR_UNSUPPORTED; }
         if (per_sm > MC3D_RF_GRID) per_sm = MC3D_RF_GRID;
         long long grid = (n_items + RF_THREADS - 1) / RF_THREADS;
@@ -1223,8 +1416,8 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
         if (grid < 1) grid = 1;
         int parity = (int)(first_step & 1);
         long long iters = n_iters;
-        void *args[] = {(void *)&prob, (void *)&parity, (void *)&iters};
-        MC3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(RF_THREADS), args, 0, stream));
+        void *args[] = {(void *)&prob, (void *)&parity, (void *)&iters, (void *)&tiled};
+        MC3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(RF_THREADS), args, dyn, stream));
         count_launch();
         return MC3D_OK;
     }
