@@ -230,6 +230,7 @@ typedef struct {
     double sums2[2][MC3D_MAX_PEERS][24];    /* [parity][source rank] */
     int64_t seq2[2][MC3D_MAX_PEERS];
     int64_t ll[2][MC3D_MAX_PEERS][40];      /* persistent kernel: LL words, (step number << 32) | 32 data bits; 2 per sum */
+    int64_t ll_retry[MC3D_MAX_PEERS][40];   /* the same for a repeated pass 1 of a step (counts of finite terms changed) */
 } mc3d_refine_xchg;
 
 /* Pinhole + 5-coefficient Brown projection of n points (n,3) -> (n,2) for one camera given as

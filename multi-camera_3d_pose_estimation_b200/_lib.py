@@ -76,7 +76,8 @@ class RefineXchg(ctypes.Structure):
                 ('halo_seq', ctypes.c_int64 * 2), ('ticket', ctypes.c_int64 * 4), ('gen', ctypes.c_int64 * 4),
                 ('error', ctypes.c_int64),
                 ('acc2', (ctypes.c_double * 24) * 2), ('sums2', ((ctypes.c_double * 24) * MAX_PEERS) * 2),
-                ('seq2', (ctypes.c_int64 * MAX_PEERS) * 2), ('ll', ((ctypes.c_int64 * 40) * MAX_PEERS) * 2)]
+                ('seq2', (ctypes.c_int64 * MAX_PEERS) * 2), ('ll', ((ctypes.c_int64 * 40) * MAX_PEERS) * 2),
+                ('ll_retry', (ctypes.c_int64 * 40) * MAX_PEERS)]
 
 
 class ExtrinsicProblem(ctypes.Structure):

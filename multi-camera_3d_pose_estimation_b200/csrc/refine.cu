@@ -534,6 +534,7 @@ struct GradMix {
     bool on;
     T alpha, sigma, beta, gamma;           // g = alpha g1 + sigma gs + beta G2' + gamma G3
     double mu;                             // this step's a.b / b.b (next step's mu_prev)
+    bool three;                            // three stored components: g = gA + beta G2' + gamma G3, gA = alpha g1 + sigma gs
 };
 
 // Flag the neighbours' halos (after the caller's system fence).
@@ -549,7 +550,7 @@ template <typename T>
 __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int parity, int end_of_iteration, double gnorm2,
                                           const double *st, const RefineDerived &dv, bool xchg, double *bias, bool both_parities,
                                           const GradMix<T> mix, bool boundary_first = false, long long halo_flag_seq = 0,
-                                          bool *best_pending = nullptr, bool last_of_launch = true) {
+                                          bool *best_pending = nullptr, bool last_of_launch = true, const double *counts = nullptr) {
     double *ctrl = pb.ctrl;
     const double gnorm = sqrt(gnorm2);
     const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
@@ -616,7 +617,9 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         if (right_halo && i >= n - halo_n) { right_halo[i - (n - halo_n)] = xi; pushed = true; }
     };
     auto grad_at = [&](long long i) -> T {
-        T gi = mix.on ? fma(mix.alpha, c1[i], fma(mix.sigma, cs[i], fma(mix.beta, c2[i], mix.gamma * c3[i]))) : g[i];
+        T gi = !mix.on ? g[i]
+             : mix.three ? fma(mix.beta, cs[i], fma(mix.gamma, c2[i], c1[i]))      // components stored as gA, G2', G3
+                         : fma(mix.alpha, c1[i], fma(mix.sigma, cs[i], fma(mix.beta, c2[i], mix.gamma * c3[i])));
         if (!(i >= lo && i < hi)) gi = (T)0;
         return gi;
     };
@@ -660,16 +663,30 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         Vec2 *pm = reinterpret_cast<Vec2 *>(m), *pv = reinterpret_cast<Vec2 *>(v), *px = reinterpret_cast<Vec2 *>(x);
         Vec2 *pbest = reinterpret_cast<Vec2 *>(bestx);
         const T al = mix.alpha, si = mix.sigma, be = mix.beta, ga = mix.gamma;
-        for (long long i2 = (e0 >> 1) + tid0; i2 < (e1 >> 1); i2 += nthr) {
-            const Vec2 a1 = q1[i2], as = qs[i2], a2 = q2[i2], a3 = q3[i2];
-            Vec2 mv = pm[i2], vv = pv[i2], xv = px[i2];
-            const T ga_ = fma(al, a1.a, fma(si, as.a, fma(be, a2.a, ga * a3.a)));
-            const T gb_ = fma(al, a1.b, fma(si, as.b, fma(be, a2.b, ga * a3.b)));
-            if (wr_old) pbest[i2] = xv;
-            adam(ga_, mv.a, vv.a, xv.a);
-            adam(gb_, mv.b, vv.b, xv.b);
-            pm[i2] = mv; pv[i2] = vv; px[i2] = xv;
-            if (wr_new) pbest[i2] = xv;
+        if (mix.three) {
+            for (long long i2 = (e0 >> 1) + tid0; i2 < (e1 >> 1); i2 += nthr) {
+                const Vec2 a1 = q1[i2], a2 = qs[i2], a3 = q2[i2];              // gA, G2', G3
+                Vec2 mv = pm[i2], vv = pv[i2], xv = px[i2];
+                const T ga_ = fma(be, a2.a, fma(ga, a3.a, a1.a));
+                const T gb_ = fma(be, a2.b, fma(ga, a3.b, a1.b));
+                if (wr_old) pbest[i2] = xv;
+                adam(ga_, mv.a, vv.a, xv.a);
+                adam(gb_, mv.b, vv.b, xv.b);
+                pm[i2] = mv; pv[i2] = vv; px[i2] = xv;
+                if (wr_new) pbest[i2] = xv;
+            }
+        } else {
+            for (long long i2 = (e0 >> 1) + tid0; i2 < (e1 >> 1); i2 += nthr) {
+                const Vec2 a1 = q1[i2], as = qs[i2], a2 = q2[i2], a3 = q3[i2];
+                Vec2 mv = pm[i2], vv = pv[i2], xv = px[i2];
+                const T ga_ = fma(al, a1.a, fma(si, as.a, fma(be, a2.a, ga * a3.a)));
+                const T gb_ = fma(al, a1.b, fma(si, as.b, fma(be, a2.b, ga * a3.b)));
+                if (wr_old) pbest[i2] = xv;
+                adam(ga_, mv.a, vv.a, xv.a);
+                adam(gb_, mv.b, vv.b, xv.b);
+                pm[i2] = mv; pv[i2] = vv; px[i2] = xv;
+                if (wr_new) pbest[i2] = xv;
+            }
         }
         if ((e1 & 1) && e1 > e0 && tid0 == 0) one_element(e1 - 1);             // unpaired last interior element
     } else {
@@ -684,7 +701,9 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
             }
         }
         Vec2 gv;
-        if (mix.on) {
+        if (mix.on && mix.three) {
+            gv.a = grad_at(i); gv.b = grad_at(i + 1);
+        } else if (mix.on) {
             const Vec2 a1 = reinterpret_cast<const Vec2 *>(c1)[i2], as = reinterpret_cast<const Vec2 *>(cs)[i2];
             const Vec2 a2 = reinterpret_cast<const Vec2 *>(c2)[i2], a3 = reinterpret_cast<const Vec2 *>(c3)[i2];
             gv.a = fma(mix.alpha, a1.a, fma(mix.sigma, as.a, fma(mix.beta, a2.a, mix.gamma * a3.a)));
@@ -711,8 +730,9 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
         nx[0] = step; nx[1] = run_sum; nx[2] = run_cnt; nx[3] = best; nx[4] = no_imp;
         nx[5] = stop ? 1.0 : 0.0; nx[6] = iters; nx[7] = improved ? 1.0 : 0.0;
         nx[8] = mix.on ? mix.mu : 0.0;
+        nx[9] = counts ? counts[0] : 0.0; nx[10] = counts ? counts[1] : 0.0;   // N_lik, N_s of this step (the next one assumes them)
         if (both_parities && stop)                                 // a persistent kernel leaves its loop here: the stopped
-            for (int i = 0; i < 9; ++i) ctrl[CT_STATE + 16 * parity + i] = nx[i];      // state must be found at either parity
+            for (int i = 0; i < 11; ++i) ctrl[CT_STATE + 16 * parity + i] = nx[i];     // state must be found at either parity
         for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
         const long long hs = (long long)(step - 1.0);
         if (hs < pb.hist_capacity) {
@@ -742,7 +762,7 @@ refine_step_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity, i
     if (xchg) xchg_gather<8>(pb, parity, true, adam_step + 1, tot);     // every rank has finished its gradient pass
     const double *acc = xchg ? tot : ctrl + CT_ACC + 16 * parity;
     const RefineDerived dv = derive(pb, acc, st);
-    const bool pushed = step_loop<T>(pb, parity, end_of_iteration, acc[7], st, dv, xchg, bias, false, GradMix<T>{false, 0, 0, 0, 0, 0.0});
+    const bool pushed = step_loop<T>(pb, parity, end_of_iteration, acc[7], st, dv, xchg, bias, false, GradMix<T>{false, 0, 0, 0, 0, 0.0, false});
     if (xchg && pb.world > 1) {                                    // flag the halos once every block's stores are out
         __shared__ int is_last;
         if (pushed) __threadfence_system();
@@ -800,6 +820,7 @@ struct P1Const {
     bool ign, do_smooth, do_body;
     long long gstride;
     T mu_prev;
+    T alpha_a, sigma_a;                                            // three-component form: the 1/N_lik and 2 lambda_s/N_s assumed
     const unsigned char *tok;                                      // tok[t] = smoothness term ending at local frame t
 };
 
@@ -814,6 +835,7 @@ __device__ __forceinline__ P1Const<T> p1_const(const mc3d_refine_problem &pb, T 
     k.do_smooth = pb.lambda_smooth > 0.0; k.do_body = pb.lambda_body > 0.0;
     k.gstride = pb.gauss_cam_stride;                               // 0: camera-0 Gaussians for every camera (upstream, Q1)
     k.mu_prev = mu_prev;
+    k.alpha_a = k.sigma_a = (T)0;
     k.tok = pb.term_ok + 2;
     return k;
 }
@@ -824,7 +846,7 @@ __device__ __forceinline__ P1Const<T> p1_const(const mc3d_refine_problem &pb, T 
 // its frame neighbours JS scalars apart (global memory, or a warp's shared-memory window), mup / Sp at its Gaussian (camera
 // c's at + c * gstride items, global memory only), tk = the three smoothness flags tok[t], tok[t+1], tok[t+2].  The four
 // gradient components go to out[q * ostride + k]; a[] collects the NS2 partial sums.
-template <typename T>
+template <typename T, bool THREE = false>
 __device__ __forceinline__ void costgrad_item(const P1Const<T> &pc, const RefineTables &tb, const T *camf, int t, int j,
                                               const T *xc, const T *mup, const T *Sp, unsigned tk0, unsigned tk1, unsigned tk2,
                                               T *out, long long ostride, T (&a)[NS2]) {
@@ -889,6 +911,18 @@ __device__ __forceinline__ void costgrad_item(const P1Const<T> &pc, const Refine
         }
         if (!self_ok) g1[0] = g1[1] = g1[2] = (T)0;
     }
+    if (THREE) {
+        // gA = alpha g1 + sigma gs with the counts of the previous step (they change only when a value turns non-finite; the
+        // caller checks them against this step's totals and repeats the pass in that case); sums [7..13) = AA A2 A3 22 23 33
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const T gA = fma(pc.alpha_a, g1[k], pc.sigma_a * gs[k]);
+            out[k] = gA; out[ostride + k] = g2[k]; out[2 * ostride + k] = g3[k];
+            a[7] = fma(gA, gA, a[7]);        a[8] = fma(gA, g2[k], a[8]);     a[9] = fma(gA, g3[k], a[9]);
+            a[10] = fma(g2[k], g2[k], a[10]); a[11] = fma(g2[k], g3[k], a[11]); a[12] = fma(g3[k], g3[k], a[12]);
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         out[k] = g1[k]; out[ostride + k] = gs[k]; out[2 * ostride + k] = g2[k]; out[3 * ostride + k] = g3[k];
@@ -901,10 +935,11 @@ __device__ __forceinline__ void costgrad_item(const P1Const<T> &pc, const Refine
 
 // Grid-stride form: one item per thread and trip, neighbours from global memory through L1 (32-bit item indices: a shard
 // holds < 2^31 joint-frames).
-template <typename T>
+template <typename T, bool THREE = false>
 __device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, T mu_prev,
-                                              double (&acc)[NS2]) {
-    const P1Const<T> pc = p1_const<T>(pb, mu_prev);
+                                              double (&acc)[NS2], T alpha_a = (T)0, T sigma_a = (T)0) {
+    P1Const<T> pc = p1_const<T>(pb, mu_prev);
+    pc.alpha_a = alpha_a; pc.sigma_a = sigma_a;
     const int J = pc.J;
     const T *x = (const T *)pb.x + 2LL * pc.JS;
     const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
@@ -921,7 +956,7 @@ __device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, con
     for (; e < n_items; e += nthr, t += dt, j += dj) {
         if (j >= J) { j -= J; ++t; }
         const long long e2 = (long long)e * 2, e3 = (long long)e * 3;
-        costgrad_item<T>(pc, tb, camf, t, j, x + e3, mu0 + e2, S + e3, pc.tok[t], pc.tok[t + 1], pc.tok[t + 2], o1 + e3, n3, a);
+        costgrad_item<T, THREE>(pc, tb, camf, t, j, x + e3, mu0 + e2, S + e3, pc.tok[t], pc.tok[t + 1], pc.tok[t + 2], o1 + e3, n3, a);
     }
 #pragma unroll
     for (int i = 0; i < NS2; ++i) acc[i] = (double)a[i];
@@ -946,8 +981,9 @@ struct P1Ring {
 
 template <typename T>
 __device__ __forceinline__ void costgrad_tiles(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, T mu_prev,
-                                               double (&acc)[NS2], T *wsm, uint64_t *bars, P1Ring &ring) {
-    const P1Const<T> pc = p1_const<T>(pb, mu_prev);
+                                               double (&acc)[NS2], T *wsm, uint64_t *bars, P1Ring &ring, T alpha_a, T sigma_a) {
+    P1Const<T> pc = p1_const<T>(pb, mu_prev);
+    pc.alpha_a = alpha_a; pc.sigma_a = sigma_a;
     const int J = pc.J, lane = threadIdx.x & 31;
     const int n_items = (int)(pb.n_frames * J), n_tiles = (n_items + P1_TILE - 1) / P1_TILE;
     const int n_warps = (int)(gridDim.x * (blockDim.x >> 5)), gw = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
@@ -1009,15 +1045,15 @@ __device__ __forceinline__ void costgrad_tiles(const mc3d_refine_problem &pb, co
             __syncwarp();
         }
         if (valid)
-            costgrad_item<T>(pc, tb, camf, t, j, buf + (lane + 2 * J) * 3, buf + win + lane * 2, buf + win + P1_TILE * 2 + lane * 3,
-                             tk0, tk1, tk2, outt + lane * 3, P1_TILE * 3, a);
+            costgrad_item<T, true>(pc, tb, camf, t, j, buf + (lane + 2 * J) * 3, buf + win + lane * 2, buf + win + P1_TILE * 2 + lane * 3,
+                                   tk0, tk1, tk2, outt + lane * 3, P1_TILE * 3, a);
         if (full) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
                 const long long e0 = (long long)tile * P1_TILE;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) bulk_s2g(gc + q * n3 + e0 * 3, outt + q * P1_TILE * 3, s_bytes);
+                for (int q = 0; q < 3; ++q) bulk_s2g(gc + q * n3 + e0 * 3, outt + q * P1_TILE * 3, s_bytes);
                 bulk_commit();
             }
             stored = true;
@@ -1025,7 +1061,7 @@ __device__ __forceinline__ void costgrad_tiles(const mc3d_refine_problem &pb, co
             __syncwarp();
             const long long e0 = (long long)tile * P1_TILE;
             const int left = (n_items - (int)e0) * 3;
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 3; ++q)
                 for (int i = lane; i < left; i += 32) gc[q * n3 + e0 * 3 + i] = outt[q * P1_TILE * 3 + i];
             stored = false;
         }
@@ -1047,10 +1083,23 @@ __device__ __forceinline__ GradMix<T> mix_of(const mc3d_refine_problem &pb, cons
     const double al = dv.inv_nlik, si = do_smooth ? dv.smooth_scale : 0.0;
     const double be = do_body ? dv.body_c : 0.0, ga = do_body ? dv.body_c * (mu_prev - dv.mu) : 0.0;
     // rounded to the state type first: |g|^2 is the norm of the gradient that is actually applied
-    GradMix<T> m{true, (T)al, (T)si, (T)be, (T)ga, do_body ? dv.mu : 0.0};
+    GradMix<T> m{true, (T)al, (T)si, (T)be, (T)ga, do_body ? dv.mu : 0.0, false};
     const double A = (double)m.alpha, S = (double)m.sigma, B = (double)m.beta, G = (double)m.gamma;
     gnorm2 = A * A * tot[7] + S * S * tot[11] + B * B * tot[14] + G * G * tot[16] +
              2.0 * (A * S * tot[8] + A * B * tot[9] + A * G * tot[10] + S * B * tot[12] + S * G * tot[13] + B * G * tot[15]);
+    if (gnorm2 < 0.0) gnorm2 = 0.0;
+    return m;
+}
+
+// The same for the three-component form (persistent kernel): gA already carries alpha and sigma.
+template <typename T>
+__device__ __forceinline__ GradMix<T> mix3_of(const mc3d_refine_problem &pb, const double *tot, const RefineDerived &dv, double mu_prev,
+                                              double &gnorm2) {
+    const bool do_smooth = pb.lambda_smooth > 0.0, do_body = pb.lambda_body > 0.0;
+    const double be = do_body ? dv.body_c : 0.0, ga = do_body ? dv.body_c * (mu_prev - dv.mu) : 0.0;
+    GradMix<T> m{true, (T)dv.inv_nlik, (T)(do_smooth ? dv.smooth_scale : 0.0), (T)be, (T)ga, do_body ? dv.mu : 0.0, true};
+    const double B = (double)m.beta, G = (double)m.gamma;
+    gnorm2 = tot[7] + B * B * tot[10] + G * G * tot[12] + 2.0 * (B * tot[8] + G * tot[9] + B * G * tot[11]);
     if (gnorm2 < 0.0) gnorm2 = 0.0;
     return m;
 }
@@ -1090,25 +1139,35 @@ __device__ __forceinline__ void gather2(const mc3d_refine_problem &pb, int parit
 // number of the step, stored with one relaxed system-scope store per peer -- no fence between data and flag, no
 // separate flag -- and the receivers poll the words of their own block until the sequence matches (the scheme of NCCL's
 // LL protocol).  The local rank's words double as the grid barrier.
-__device__ __forceinline__ void publish2_ll(const mc3d_refine_problem &pb, int parity, long long seq) {   // last block only
+// `retry`: the repeated pass 1 of a step (its counts of finite terms differed from the assumed ones) goes through its own
+// slot, so that the first attempt's words stay in place for blocks and ranks that have not read them yet.
+__device__ __forceinline__ void publish2_ll(const mc3d_refine_problem &pb, int parity, long long seq, bool retry) {   // last block only
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    unsigned long long bits = 0;
+    if (threadIdx.x < 2 * NS2) bits = (unsigned long long)__double_as_longlong(__ldcg(&mine->acc2[parity][threadIdx.x >> 1]));
+    __syncthreads();
+    if (threadIdx.x < NS2) mine->acc2[parity][threadIdx.x] = 0.0;  // ready for a repeated pass / the step after next ...
+    __syncthreads();
+    if (threadIdx.x == 0) fence_gpu();                             // ... before anybody can see the words
+    __syncthreads();
     if (threadIdx.x < 2 * NS2) {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(&mine->acc2[parity][threadIdx.x >> 1]));
         const unsigned long long half = (threadIdx.x & 1) ? (bits >> 32) : (bits & 0xffffffffULL);
         const long long word = (long long)(((unsigned long long)(unsigned int)seq << 32) | half);
-        for (int r = 0; r < pb.world; ++r) st_relaxed_sys(&xchg_of(pb, r)->ll[parity][pb.rank][threadIdx.x], word);
+        for (int r = 0; r < pb.world; ++r) {
+            mc3d_refine_xchg *xr = xchg_of(pb, r);
+            st_relaxed_sys(retry ? &xr->ll_retry[pb.rank][threadIdx.x] : &xr->ll[parity][pb.rank][threadIdx.x], word);
+        }
     }
-    __syncthreads();
-    if (threadIdx.x < NS2) mine->acc2[parity][threadIdx.x] = 0.0;  // ready for the step after next
 }
 
-__device__ __forceinline__ void gather2_ll(const mc3d_refine_problem &pb, int parity, long long seq, double *tot, unsigned int *halves) {
+__device__ __forceinline__ void gather2_ll(const mc3d_refine_problem &pb, int parity, long long seq, double *tot, unsigned int *halves,
+                                           bool retry) {
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
     const unsigned int want = (unsigned int)seq;
     const unsigned long long limit = pb.spin_timeout_ns > 0 ? (unsigned long long)pb.spin_timeout_ns : 10000000000ULL;
     for (int q = threadIdx.x; q < 2 * NS2 * pb.world; q += blockDim.x) {
         const int r = q / (2 * NS2), k = q - r * (2 * NS2);
-        const int64_t *w = &mine->ll[parity][r][k];
+        const int64_t *w = retry ? &mine->ll_retry[r][k] : &mine->ll[parity][r][k];
         unsigned long long word = (unsigned long long)ld_relaxed_sys(w);
         if ((unsigned int)(word >> 32) != want) {
             const unsigned long long t0 = globaltimer_ns();
@@ -1222,9 +1281,9 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
     __syncthreads();
     int parity = first_parity & 1;
     for (long long it = 0; it < n_iters; ++it, parity ^= 1) {
-        double st[9];                                              // state entering this step (written before the last barrier)
+        double st[11];                                             // state entering this step (written before the last barrier)
 #pragma unroll
-        for (int i = 0; i < 9; ++i) st[i] = __ldcg(ctrl + CT_STATE + 16 * parity + i);
+        for (int i = 0; i < 11; ++i) st[i] = __ldcg(ctrl + CT_STATE + 16 * parity + i);
         if (st[5] != 0.0) break;                                   // stopped: identical decision in every block and rank
         const long long seq = (long long)st[0] + 1;
         if (pb.world > 1) {
@@ -1235,19 +1294,31 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
             }
             __syncthreads();
         }
-        {   // pass 1
-            double acc[NS2];
-            if (tiled) costgrad_tiles<T>(pb, tb, camf, (T)st[8], acc, wsm, bars, ring);
-            else costgrad_loop<T>(pb, tb, camf, (T)st[8], acc);
-            block_reduce_add<NS2>(acc, red, mine->acc2[parity]);
+        // pass 1, three stored components: gA = alpha g1 + sigma gs with the counts N_lik, N_s the previous step found (they
+        // change only when a value turns non-finite).  If this step's totals say otherwise -- or nothing is known yet: the
+        // first step after the state was initialised -- the pass is repeated once with the right counts.
+        double counts[2] = {st[9], st[10]};
+        const bool do_smooth = pb.lambda_smooth > 0.0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const T alpha_a = counts[0] > 0.0 ? (T)(1.0 / counts[0]) : (T)0;
+            const T sigma_a = (do_smooth && counts[1] > 0.0) ? (T)(2.0 * pb.lambda_smooth / counts[1]) : (T)0;
+            {
+                double acc[NS2];
+                if (tiled) costgrad_tiles<T>(pb, tb, camf, (T)st[8], acc, wsm, bars, ring, alpha_a, sigma_a);
+                else costgrad_loop<T, true>(pb, tb, camf, (T)st[8], acc, alpha_a, sigma_a);
+                block_reduce_add<NS2>(acc, red, mine->acc2[parity]);
+            }
+            if (take_ticket(mine, 0)) publish2_ll(pb, parity, seq, attempt != 0);
+            gather2_ll(pb, parity, seq, tot, halves, attempt != 0);    // grid barrier + cross-rank sums in one
+            const bool same = tot[1] == counts[0] && (!do_smooth || tot[3] == counts[1]);
+            counts[0] = tot[1]; counts[1] = tot[3];
+            if (same) break;                                       // identical decision in every block and rank
         }
-        if (take_ticket(mine, 0)) publish2_ll(pb, parity, seq);
-        gather2_ll(pb, parity, seq, tot, halves);                  // grid barrier + cross-rank sums in one
         const RefineDerived dv = derive(pb, tot, st);
         double gnorm2;
-        const GradMix<T> mix = mix_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);   // mu_prev as pass 1 used it
+        const GradMix<T> mix = mix3_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);  // mu_prev as pass 1 used it
         step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, true, mix, true, seq,      // halos leave first (block 0)
-                     &best_pending, it + 1 == n_iters);
+                     &best_pending, it + 1 == n_iters, counts);
         grid_barrier(pb, 2, seq);                                   // closes the step; local only
     }
 }
