@@ -216,6 +216,7 @@ typedef struct {
 
 /* Exchange block at the start of each rank's peer allocation (zero-filled by mc3d_peer_alloc). */
 #define MC3D_XCHG_X_OFFSET 32768
+#define MC3D_XCHG_BLOCK_FLAGS 960 /* blocks of the persistent kernel that can announce their range edges */
 #define MC3D_REFINE_SUMS2 17     /* sums of the two-phase step: 7 cost sums + 10 gradient-component dot products */
 typedef struct {
     double sums[2][MC3D_MAX_PEERS][8];      /* [step parity][source rank]: S_lik N_lik S_s N_s a.b b.b a.a | gnorm^2 */
@@ -231,6 +232,7 @@ typedef struct {
     int64_t seq2[2][MC3D_MAX_PEERS];
     int64_t ll[2][MC3D_MAX_PEERS][40];      /* persistent kernel: LL words, (step number << 32) | 32 data bits; 2 per sum */
     int64_t ll_retry[MC3D_MAX_PEERS][40];   /* the same for a repeated pass 1 of a step (counts of finite terms changed) */
+    int64_t blk_seq[MC3D_XCHG_BLOCK_FLAGS]; /* fused sweep: Adam step count the two edges of block b's item range hold (local) */
 } mc3d_refine_xchg;
 
 /* Pinhole + 5-coefficient Brown projection of n points (n,3) -> (n,2) for one camera given as

@@ -77,7 +77,7 @@ class RefineXchg(ctypes.Structure):
                 ('error', ctypes.c_int64),
                 ('acc2', (ctypes.c_double * 24) * 2), ('sums2', ((ctypes.c_double * 24) * MAX_PEERS) * 2),
                 ('seq2', (ctypes.c_int64 * MAX_PEERS) * 2), ('ll', ((ctypes.c_int64 * 40) * MAX_PEERS) * 2),
-                ('ll_retry', (ctypes.c_int64 * 40) * MAX_PEERS)]
+                ('ll_retry', (ctypes.c_int64 * 40) * MAX_PEERS), ('blk_seq', ctypes.c_int64 * 960)]
 
 
 class ExtrinsicProblem(ctypes.Structure):

@@ -537,6 +537,86 @@ struct GradMix {
     bool three;                            // three stored components: g = gA + beta G2' + gamma G3, gA = alpha g1 + sigma gs
 };
 
+// Scalars of one optimiser step that every thread derives from the step's sums and the state entering it: the clip factor,
+// Adam's bias corrections, the running-mean early-stopping bookkeeping (pose_refinement.py:1069-1089, quirk Q5) and what
+// happens to the best-trajectory snapshot.
+template <typename T>
+struct StepScalars {
+    double step, run_sum, run_cnt, best, no_imp, iters;
+    bool improved, stop, clip_nan, wr_new, wr_old;
+    T step_size, inv_bc2_sqrt, w1, b2, w2, eps, clipT;
+    __device__ __forceinline__ void adam(T gi, T &mi, T &vi, T &xi) const {
+        gi = clip_nan ? (T)NAN : gi * clipT;
+        mi = mi + (gi - mi) * w1;                                  // exp_avg.lerp_(grad, 1 - beta1)
+        vi = vi * b2 + w2 * gi * gi;                               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const T denom = sqrt_c(vi) * inv_bc2_sqrt + eps;
+        xi = xi - step_size * div_c(mi, denom);                    // param.addcdiv_(exp_avg, denom, value=-step_size)
+    }
+};
+
+// Contains one block barrier (the two pow() are evaluated by one thread per block).
+template <typename T>
+__device__ __forceinline__ StepScalars<T> step_scalars(const mc3d_refine_problem &pb, int end_of_iteration, double gnorm2,
+                                                       const double *st, const RefineDerived &dv, double *bias, bool *best_pending,
+                                                       bool last_of_launch) {
+    StepScalars<T> ss;
+    const double gnorm = sqrt(gnorm2);
+    const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
+    ss.step = st[0] + 1.0;
+    ss.run_sum = st[1] + dv.total; ss.run_cnt = st[2] + 1.0;
+    ss.best = st[3]; ss.no_imp = st[4]; ss.iters = st[6];
+    ss.improved = false; ss.stop = false;
+    if (end_of_iteration) {
+        const double mean = ss.run_sum / ss.run_cnt;               // running mean over costs AND earlier means (Q5)
+        ss.run_sum += mean; ss.run_cnt += 1.0;
+        ss.improved = mean < ss.best - pb.tolerance;
+        if (ss.improved) { ss.best = mean; ss.no_imp = 0.0; } else { ss.no_imp += 1.0; }
+        ss.iters += 1.0;
+        ss.stop = (ss.no_imp >= (double)pb.patience) || (ss.iters > (double)pb.max_iter);
+    }
+    // The best-trajectory snapshot (x after the update of a step whose running mean improved).  The persistent kernel defers it
+    // (best_pending): while consecutive steps improve, the snapshot would be overwritten again at once, so nothing is written
+    // until a step does NOT improve -- then the value of x from before this step's update is the snapshot -- or the launch
+    // ends.  Saves 3 of the 12 scalars a step writes per item while the cost is falling.
+    ss.wr_new = ss.improved; ss.wr_old = false;
+    if (best_pending) {
+        ss.wr_new = ss.improved && (last_of_launch || ss.stop);
+        ss.wr_old = !ss.improved && *best_pending;
+        *best_pending = ss.improved && !ss.wr_new;
+    }
+    __syncthreads();                                               // bias[] may still be read from the previous step
+    if (threadIdx.x == 0) {                                        // two double pow() per block, not per thread
+        bias[0] = 1.0 - pow(pb.beta1, ss.step);
+        bias[1] = 1.0 - pow(pb.beta2, ss.step);
+    }
+    __syncthreads();
+    ss.step_size = (T)(pb.lr / bias[0]);
+    ss.inv_bc2_sqrt = (T)(1.0 / sqrt(bias[1]));
+    ss.w1 = (T)(1.0 - pb.beta1); ss.b2 = (T)pb.beta2; ss.w2 = (T)(1.0 - pb.beta2); ss.eps = (T)pb.eps; ss.clipT = (T)clip;
+    ss.clip_nan = !(clip == clip);
+    return ss;
+}
+
+// Block 0, thread 0: the state entering the next step, the cost history of this one.
+template <typename T>
+__device__ __forceinline__ void write_next_state(const mc3d_refine_problem &pb, int parity, const StepScalars<T> &ss,
+                                                 const RefineDerived &dv, double mu, bool both_parities, const double *counts) {
+    double *ctrl = pb.ctrl;
+    double *nx = ctrl + CT_STATE + 16 * (parity ^ 1);
+    nx[0] = ss.step; nx[1] = ss.run_sum; nx[2] = ss.run_cnt; nx[3] = ss.best; nx[4] = ss.no_imp;
+    nx[5] = ss.stop ? 1.0 : 0.0; nx[6] = ss.iters; nx[7] = ss.improved ? 1.0 : 0.0;
+    nx[8] = mu;
+    nx[9] = counts ? counts[0] : 0.0; nx[10] = counts ? counts[1] : 0.0;   // N_lik, N_s of this step (the next one assumes them)
+    if (both_parities && ss.stop)                                  // a persistent kernel leaves its loop here: the stopped
+        for (int i = 0; i < 11; ++i) ctrl[CT_STATE + 16 * parity + i] = nx[i];     // state must be found at either parity
+    for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
+    const long long hs = (long long)(ss.step - 1.0);
+    if (hs < pb.hist_capacity) {
+        double *h = ctrl + CT_HIST + 4 * hs;
+        h[0] = dv.total; h[1] = dv.cost_lik; h[2] = dv.cost_s; h[3] = dv.cost_b;
+    }
+}
+
 // Flag the neighbours' halos (after the caller's system fence).
 __device__ __forceinline__ void halo_flags(const mc3d_refine_problem &pb, long long seq) {
     if (pb.rank > 0) st_relaxed_sys(&xchg_of(pb, pb.rank - 1)->halo_seq[1], seq);      // after the caller's system fence
@@ -550,41 +630,10 @@ template <typename T>
 __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int parity, int end_of_iteration, double gnorm2,
                                           const double *st, const RefineDerived &dv, bool xchg, double *bias, bool both_parities,
                                           const GradMix<T> mix, bool boundary_first = false, long long halo_flag_seq = 0,
-                                          bool *best_pending = nullptr, bool last_of_launch = true, const double *counts = nullptr) {
-    double *ctrl = pb.ctrl;
-    const double gnorm = sqrt(gnorm2);
-    const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
-    const double step = st[0] + 1.0;
-    double run_sum = st[1] + dv.total, run_cnt = st[2] + 1.0;
-    double best = st[3], no_imp = st[4], iters = st[6];
-    bool improved = false, stop = false;
-    if (end_of_iteration) {
-        const double mean = run_sum / run_cnt;                     // running mean over costs AND earlier means (Q5)
-        run_sum += mean; run_cnt += 1.0;
-        improved = mean < best - pb.tolerance;
-        if (improved) { best = mean; no_imp = 0.0; } else { no_imp += 1.0; }
-        iters += 1.0;
-        stop = (no_imp >= (double)pb.patience) || (iters > (double)pb.max_iter);
-    }
-    // The best-trajectory snapshot (x after the update of a step whose running mean improved).  The persistent kernel defers it
-    // (best_pending): while consecutive steps improve, the snapshot would be overwritten again at once, so nothing is written
-    // until a step does NOT improve -- then the value of x from before this step's update is the snapshot -- or the launch
-    // ends.  Saves 3 of the 12 scalars a step writes per item while the cost is falling.
-    bool wr_new = improved, wr_old = false;
-    if (best_pending) {
-        wr_new = improved && (last_of_launch || stop);
-        wr_old = !improved && *best_pending;
-        *best_pending = improved && !wr_new;
-    }
-    if (threadIdx.x == 0) {                                        // two double pow() per block, not per thread
-        bias[0] = 1.0 - pow(pb.beta1, step);
-        bias[1] = 1.0 - pow(pb.beta2, step);
-    }
-    __syncthreads();
-    const T step_size = (T)(pb.lr / bias[0]);
-    const T inv_bc2_sqrt = (T)(1.0 / sqrt(bias[1]));
-    const T w1 = (T)(1.0 - pb.beta1), b2 = (T)pb.beta2, w2 = (T)(1.0 - pb.beta2), eps = (T)pb.eps, clipT = (T)clip;
-    const bool clip_nan = !(clip == clip);
+                                          bool *best_pending = nullptr, bool last_of_launch = true, const double *counts = nullptr,
+                                          const StepScalars<T> *pre = nullptr) {
+    const StepScalars<T> ss = pre ? *pre : step_scalars<T>(pb, end_of_iteration, gnorm2, st, dv, bias, best_pending, last_of_launch);
+    const bool improved = ss.improved, wr_new = ss.wr_new, wr_old = ss.wr_old;
     T *x = (T *)pb.x + 2LL * pb.n_joints * 3;                       // skip the two halo frames
     T *m = (T *)pb.m, *v = (T *)pb.v, *bestx = (T *)pb.best;
     const T *g = (const T *)pb.g;
@@ -593,13 +642,7 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
     const long long per_frame = (long long)pb.n_joints * 3;
     const long long n = pb.n_frames * per_frame;
     const long long lo = (pb.win_begin - pb.frame_offset) * per_frame, hi = (pb.win_end - pb.frame_offset) * per_frame;
-    auto adam = [&](T gi, T &mi, T &vi, T &xi) {
-        gi = clip_nan ? (T)NAN : gi * clipT;
-        mi = mi + (gi - mi) * w1;                                  // exp_avg.lerp_(grad, 1 - beta1)
-        vi = vi * b2 + w2 * gi * gi;                               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-        const T denom = sqrt_c(vi) * inv_bc2_sqrt + eps;
-        xi = xi - step_size * div_c(mi, denom);                    // param.addcdiv_(exp_avg, denom, value=-step_size)
-    };
+    auto adam = [&](T gi, T &mi, T &vi, T &xi) { ss.adam(gi, mi, vi, xi); };
     // two scalars per access: the halo offset of x (2 J 3 scalars) is always 8-byte (float) / 16-byte (double) aligned
     struct alignas(2 * sizeof(T)) Vec2 { T a, b; };
     const long long n2 = n >> 1;
@@ -725,21 +768,7 @@ __device__ __forceinline__ bool step_loop(const mc3d_refine_problem &pb, int par
     }
     if ((n & 1) && tid0 == 0 && !(bf && is_boundary(n - 1))) one_element(n - 1);      // odd tail
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double *nx = ctrl + CT_STATE + 16 * (parity ^ 1);
-        nx[0] = step; nx[1] = run_sum; nx[2] = run_cnt; nx[3] = best; nx[4] = no_imp;
-        nx[5] = stop ? 1.0 : 0.0; nx[6] = iters; nx[7] = improved ? 1.0 : 0.0;
-        nx[8] = mix.on ? mix.mu : 0.0;
-        nx[9] = counts ? counts[0] : 0.0; nx[10] = counts ? counts[1] : 0.0;   // N_lik, N_s of this step (the next one assumes them)
-        if (both_parities && stop)                                 // a persistent kernel leaves its loop here: the stopped
-            for (int i = 0; i < 11; ++i) ctrl[CT_STATE + 16 * parity + i] = nx[i];     // state must be found at either parity
-        for (int i = 0; i < 8; ++i) ctrl[CT_ACC + 16 * (parity ^ 1) + i] = 0.0;
-        const long long hs = (long long)(step - 1.0);
-        if (hs < pb.hist_capacity) {
-            double *h = ctrl + CT_HIST + 4 * hs;
-            h[0] = dv.total; h[1] = dv.cost_lik; h[2] = dv.cost_s; h[3] = dv.cost_b;
-        }
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) write_next_state<T>(pb, parity, ss, dv, mix.on ? mix.mu : 0.0, both_parities, counts);
     return pushed;
 }
 
@@ -846,17 +875,22 @@ __device__ __forceinline__ P1Const<T> p1_const(const mc3d_refine_problem &pb, T 
 // its frame neighbours JS scalars apart (global memory, or a warp's shared-memory window), mup / Sp at its Gaussian (camera
 // c's at + c * gstride items, global memory only), tk = the three smoothness flags tok[t], tok[t+1], tok[t+2].  The four
 // gradient components go to out[q * ostride + k]; a[] collects the NS2 partial sums.
+template <typename T>
+struct P1Own {                      // what an item loads for itself: its position and its (camera-0) Gaussian
+    T X, Y, Z, mx, my, s00, s01, s11;
+};
+
 template <typename T, bool THREE = false>
 __device__ __forceinline__ void costgrad_item(const P1Const<T> &pc, const RefineTables &tb, const T *camf, int t, int j,
-                                              const T *xc, const T *mup, const T *Sp, unsigned tk0, unsigned tk1, unsigned tk2,
-                                              T *out, long long ostride, T (&a)[NS2]) {
+                                              const T *xc, const P1Own<T> &own, const T *mup, const T *Sp, unsigned tk0,
+                                              unsigned tk1, unsigned tk2, T *out, long long ostride, T (&a)[NS2]) {
     const int J = pc.J, JS = pc.JS, lo = pc.lo, hi = pc.hi;
     T g1[3] = {(T)0, (T)0, (T)0}, gs[3] = {(T)0, (T)0, (T)0}, g2[3] = {(T)0, (T)0, (T)0}, g3[3] = {(T)0, (T)0, (T)0};
     if (t >= lo && t < hi) {
-        const T X = xc[0], Y = xc[1], Z = xc[2];
+        const T X = own.X, Y = own.Y, Z = own.Z;
         const bool self_ok = finite_c(X) && finite_c(Y) && finite_c(Z);
-        T mx = mup[0], my = mup[1];
-        T s00 = Sp[0], s01 = Sp[1], s11 = Sp[2];
+        T mx = own.mx, my = own.my;
+        T s00 = own.s00, s01 = own.s01, s11 = own.s11;
         for (int c = 0; c < pc.C; ++c) {
             T cam[CAM_STRIDE];
             load_camera(camf + c * CAM_STRIDE, cam);
@@ -879,7 +913,7 @@ __device__ __forceinline__ void costgrad_item(const P1Const<T> &pc, const Refine
             const T *xm2 = xc - 2 * JS, *xm1 = xc - JS, *xp1 = xc + JS, *xp2 = xc + 2 * JS;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const T c0 = xc[k];
+                const T c0 = k == 0 ? X : (k == 1 ? Y : Z);
                 const T d0 = c0 - two * xm1[k] + xm2[k];              // the cost term ending at this frame
                 const T d1 = xp1[k] - two * c0 + xm1[k];
                 const T d2 = xp2[k] - two * xp1[k] + c0;
@@ -956,121 +990,13 @@ __device__ __forceinline__ void costgrad_loop(const mc3d_refine_problem &pb, con
     for (; e < n_items; e += nthr, t += dt, j += dj) {
         if (j >= J) { j -= J; ++t; }
         const long long e2 = (long long)e * 2, e3 = (long long)e * 3;
-        costgrad_item<T, THREE>(pc, tb, camf, t, j, x + e3, mu0 + e2, S + e3, pc.tok[t], pc.tok[t + 1], pc.tok[t + 2], o1 + e3, n3, a);
-    }
-#pragma unroll
-    for (int i = 0; i < NS2; ++i) acc[i] = (double)a[i];
-}
-
-// ---- pass 1, every warp its own pipeline -----------------------------------------------------------------------------
-// The persistent kernel's pass 1 for camera-0 Gaussians: a warp takes tiles of P1_TILE consecutive items (one per lane).
-// Its lane 0 fetches, one tile ahead, everything the tile reads with three 1-D TMA bulk copies into the warp's private
-// two-stage ring -- the x window (the tile's items with two frames on either side: stencil neighbours and bone end points come
-// from shared memory, stride-3 accesses are conflict-free), the tile's mu0 and Sigma^-1 -- completing on the stage's mbarrier;
-// the four gradient components leave through a private output tile and four bulk stores.  No block barrier, no global load
-// in the item's dependency chain.  In ext items (x with its two halo frames) a tile's window starts at the tile's own index,
-// so every copy is 16-byte aligned whatever J is; the ragged last tile is filled and written with plain accesses.
-constexpr int P1_TILE = 32, P1_STAGES = 2;
-__host__ __device__ __forceinline__ int p1_win_scalars(int J) { return (P1_TILE + 4 * J) * 3; }
-__host__ __device__ __forceinline__ int p1_stage_scalars(int J) { return p1_win_scalars(J) + P1_TILE * 5; }
-__host__ __device__ __forceinline__ int p1_warp_scalars(int J) { return P1_STAGES * p1_stage_scalars(J) + 4 * P1_TILE * 3; }
-
-struct P1Ring {
-    uint32_t issued, consumed;                                     // full tiles this warp has fetched / used since launch
-};
-
-template <typename T>
-__device__ __forceinline__ void costgrad_tiles(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, T mu_prev,
-                                               double (&acc)[NS2], T *wsm, uint64_t *bars, P1Ring &ring, T alpha_a, T sigma_a) {
-    P1Const<T> pc = p1_const<T>(pb, mu_prev);
-    pc.alpha_a = alpha_a; pc.sigma_a = sigma_a;
-    const int J = pc.J, lane = threadIdx.x & 31;
-    const int n_items = (int)(pb.n_frames * J), n_tiles = (n_items + P1_TILE - 1) / P1_TILE;
-    const int n_warps = (int)(gridDim.x * (blockDim.x >> 5)), gw = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
-    const T *x_ext = (const T *)pb.x, *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
-    const long long n3 = gc_stride(pb);
-    T *gc = (T *)pb.gc;
-    const int win = p1_win_scalars(J), stage = p1_stage_scalars(J);
-    T *outt = wsm + P1_STAGES * stage;                             // [4][P1_TILE * 3]
-    const uint32_t win_bytes = (uint32_t)(win * sizeof(T)), mu_bytes = (uint32_t)(P1_TILE * 2 * sizeof(T)),
-                   s_bytes = (uint32_t)(P1_TILE * 3 * sizeof(T));
-    auto issue = [&](int tile) {                                   // lane 0; full tiles only
-        if ((tile + 1) * P1_TILE > n_items) return;
-        const uint32_t s = ring.issued % P1_STAGES;
-        T *dst = wsm + s * stage;
-        const long long e0 = (long long)tile * P1_TILE;
-        mbar_arrive_expect_tx(bars + s, win_bytes + mu_bytes + s_bytes);
-        bulk_g2s(dst, x_ext + e0 * 3, win_bytes, bars + s);
-        bulk_g2s(dst + win, mu0 + e0 * 2, mu_bytes, bars + s);
-        bulk_g2s(dst + win + P1_TILE * 2, S + e0 * 3, s_bytes, bars + s);
-    };
-    T a[NS2];
-#pragma unroll
-    for (int i = 0; i < NS2; ++i) a[i] = (T)0;
-    int tile = gw;
-    if (lane == 0) {
-        asm volatile("fence.proxy.async;" ::: "memory");           // x was written with plain stores (pass 2, the neighbours' halos)
-        if (tile < n_tiles) issue(tile);
-    }
-    if (tile < n_tiles && (tile + 1) * P1_TILE <= n_items) ++ring.issued;
-    int e = tile * P1_TILE + lane;
-    int t = e / J, j = e - t * J;
-    const int de = n_warps * P1_TILE, dt = de / J, dj = de - dt * J;
-    bool stored = false;
-    for (; tile < n_tiles; tile += n_warps, e += de, t += dt, j += dj) {
-        if (j >= J) { j -= J; ++t; }
-        const int next = tile + n_warps;
-        if (next < n_tiles) {
-            if (lane == 0) issue(next);
-            if ((next + 1) * P1_TILE <= n_items) ++ring.issued;
+        P1Own<T> own;
+        if (t >= pc.lo && t < pc.hi) {
+            own.X = x[e3]; own.Y = x[e3 + 1]; own.Z = x[e3 + 2];
+            own.mx = mu0[e2]; own.my = mu0[e2 + 1]; own.s00 = S[e3]; own.s01 = S[e3 + 1]; own.s11 = S[e3 + 2];
         }
-        const bool valid = e < n_items, full = (tile + 1) * P1_TILE <= n_items;
-        unsigned tk0 = 0, tk1 = 0, tk2 = 0;
-        if (valid) { tk0 = pc.tok[t]; tk1 = pc.tok[t + 1]; tk2 = pc.tok[t + 2]; }
-        const uint32_t s = ring.consumed % P1_STAGES;
-        T *buf = wsm + s * stage;
-        if (full) {
-            mbar_wait(bars + s, (ring.consumed / P1_STAGES) & 1);
-            ++ring.consumed;
-        } else {                                                   // the ragged last tile: nothing of this warp's is in flight
-            const long long e0 = (long long)tile * P1_TILE;
-            const long long ext_n = (pb.n_frames + 4) * (long long)pc.JS;
-            for (int i = lane; i < win; i += 32) buf[i] = e0 * 3 + i < ext_n ? x_ext[e0 * 3 + i] : (T)0;
-            for (int i = lane; i < P1_TILE * 2; i += 32) buf[win + i] = e0 * 2 + i < (long long)n_items * 2 ? mu0[e0 * 2 + i] : (T)0;
-            for (int i = lane; i < P1_TILE * 3; i += 32) buf[win + P1_TILE * 2 + i] = e0 * 3 + i < (long long)n_items * 3 ? S[e0 * 3 + i] : (T)0;
-            __syncwarp();
-        }
-        if (stored) {                                              // the previous tile's bulk stores have read the output tile
-            if (lane == 0) bulk_wait_read<0>();
-            __syncwarp();
-        }
-        if (valid)
-            costgrad_item<T, true>(pc, tb, camf, t, j, buf + (lane + 2 * J) * 3, buf + win + lane * 2, buf + win + P1_TILE * 2 + lane * 3,
-                                   tk0, tk1, tk2, outt + lane * 3, P1_TILE * 3, a);
-        if (full) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                const long long e0 = (long long)tile * P1_TILE;
-#pragma unroll
-                for (int q = 0; q < 3; ++q) bulk_s2g(gc + q * n3 + e0 * 3, outt + q * P1_TILE * 3, s_bytes);
-                bulk_commit();
-            }
-            stored = true;
-        } else {
-            __syncwarp();
-            const long long e0 = (long long)tile * P1_TILE;
-            const int left = (n_items - (int)e0) * 3;
-            for (int q = 0; q < 3; ++q)
-                for (int i = lane; i < left; i += 32) gc[q * n3 + e0 * 3 + i] = outt[q * P1_TILE * 3 + i];
-            stored = false;
-        }
+        costgrad_item<T, THREE>(pc, tb, camf, t, j, x + e3, own, mu0 + e2, S + e3, pc.tok[t], pc.tok[t + 1], pc.tok[t + 2], o1 + e3, n3, a);
     }
-    if (lane == 0) {
-        bulk_wait_all<0>();                                         // the components are in global memory ...
-        asm volatile("fence.proxy.async;" ::: "memory");           // ... before the barrier that lets pass 2 read them
-    }
-    __syncwarp();
 #pragma unroll
     for (int i = 0; i < NS2; ++i) acc[i] = (double)a[i];
 }
@@ -1177,6 +1103,7 @@ __device__ __forceinline__ void gather2_ll(const mc3d_refine_problem &pb, int pa
         halves[q] = (unsigned int)word;
     }
     __syncthreads();
+    if (threadIdx.x == 0) fence_xchg(pb);                          // acquire: what the other blocks / ranks wrote before their words
     if (threadIdx.x < NS2) {
         double s = 0.0;
         for (int r = 0; r < pb.world; ++r) {
@@ -1252,15 +1179,284 @@ refine_step2_kernel(const __grid_constant__ mc3d_refine_problem pb, int parity) 
     }
 }
 
+// Pass 1 as a grid-stride loop with its totals exchanged (grid barrier + cross-rank sums in one), repeated once when the counts
+// of finite terms it assumed (`counts`, updated) are not the ones it found.  first_attempt = 1: only the repetition (the caller
+// has made the first attempt in another form).
+template <typename T>
+__device__ __forceinline__ void pass1_checked(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, int parity,
+                                              long long seq, T mu_prev, double (&counts)[2], int first_attempt, double *red,
+                                              double *tot, unsigned int *halves) {
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    const bool do_smooth = pb.lambda_smooth > 0.0;
+    for (int attempt = first_attempt; attempt < 2; ++attempt) {
+        const T alpha_a = counts[0] > 0.0 ? (T)(1.0 / counts[0]) : (T)0;
+        const T sigma_a = (do_smooth && counts[1] > 0.0) ? (T)(2.0 * pb.lambda_smooth / counts[1]) : (T)0;
+        {
+            double acc[NS2];
+            costgrad_loop<T, true>(pb, tb, camf, mu_prev, acc, alpha_a, sigma_a);
+            block_reduce_add<NS2>(acc, red, mine->acc2[parity]);
+        }
+        if (take_ticket(mine, 0)) publish2_ll(pb, parity, seq, attempt != 0);
+        gather2_ll(pb, parity, seq, tot, halves, attempt != 0);
+        const bool same = tot[1] == counts[0] && (!do_smooth || tot[3] == counts[1]);
+        counts[0] = tot[1]; counts[1] = tot[3];
+        if (same) break;                                           // identical decision in every block and rank
+    }
+}
+
+// ==== fused sweep =======================================================================================================
+// Adam of step s and pass 1 of step s + 1 in ONE sweep over the shard, and one grid-wide meeting per step (the exchange of the
+// sums) instead of two.  Pass 2 is bound by memory (it streams 18 scalars per item and does ~60 operations on them), pass 1 by
+// instruction issue (~700 per item on 8 loaded scalars); run one after the other, each leaves the other resource idle.  Here
+// every block owns a contiguous range of items and walks it in chunks of one item per thread; in one trip a thread
+//   1. starts the asynchronous copies (cp.async, 4 / 8 bytes each, coalesced) of the 18 scalars of three elements of Adam chunk
+//      i + 1 -- gA, G2', G3, m, v, x -- into its own shared-memory slots,
+//   2. evaluates pass 1 of step s + 1 for one item of chunk i (the copies are in flight meanwhile),
+//   3. waits for its copies, applies Adam of step s to the three elements and stores m, v, x,
+// then the block meets (the next chunk's pass 1 reads the x just written).  Adam chunks start one 2-frame edge (2 J items) into
+// the range, so that chunk i of pass 1 finds x_{s+1} on all items it touches -- itself, two frames either side, its frame's
+// bones -- once Adam chunk i is done; a trip's Adam writes begin exactly where its pass 1 reads end.  The two edges of the range
+// are updated first and announced with a per-block flag (blk_seq, the Adam step count): the neighbouring blocks read them,
+// the rank's first / last block also stores them into the neighbour ranks' halo frames.  In-place: every element of x, m, v
+// and the components is read and written once per step, as in the two-pass form.
+constexpr int SWEEP_ITEMS = 2;       // items of pass 1 per thread and trip
+// staged scalars per thread: 3 pairs x (gA, G2', G3, m, v, x) of the next Adam chunk + two buffers of (mu0, Sigma^-1) for the
+// items of the next / the current trip
+constexpr int SWEEP_STAGE = 36 + 2 * 5 * SWEEP_ITEMS;
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_bytes(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, int parity,
+                                                long long n_iters, double *red, double *tot, double *bias, unsigned int *halves,
+                                                T *stage) {
+    struct alignas(2 * sizeof(T)) Vec2 { T a, b; };
+    __shared__ T adamc[8];                                         // Adam's constants of the step in the state type
+    double *ctrl = pb.ctrl;
+    mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
+    const int J = pb.n_joints, JS = J * 3, tid = threadIdx.x, NT = RF_THREADS;
+    const int n_items = (int)(pb.n_frames * J);
+    const int b = blockIdx.x, G = gridDim.x;
+    // my items: boundaries at multiples of 4 items, so that pairs of elements are 8-byte aligned in every array
+    const int r_lo = b == 0 ? 0 : (int)(((long long)n_items * b / G) & ~3LL);
+    const int r_hi = b == G - 1 ? n_items : (int)(((long long)n_items * (b + 1) / G) & ~3LL);
+    const int E = 2 * J;                                           // items of a 2-frame edge
+    const bool do_smooth = pb.lambda_smooth > 0.0;
+    double st[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) st[i] = __ldcg(ctrl + CT_STATE + 16 * parity + i);
+    if (st[5] != 0.0) return;                                      // stopped
+    long long seq = (long long)st[0] + 1;
+    if (pb.world > 1) {                                            // the neighbours' boundary frames of this step are in my halo
+        if (tid == 0) {
+            if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], seq - 1);
+            if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], seq - 1);
+            fence_sys();
+        }
+        __syncthreads();
+    }
+    double counts[2] = {st[9], st[10]};
+    pass1_checked<T>(pb, tb, camf, parity, seq, (T)st[8], counts, 0, red, tot, halves);      // pass 1 of the launch's first step
+    bool best_pending = false;
+    T *x = (T *)pb.x + 2LL * JS;                                    // local frame 0
+    T *m = (T *)pb.m, *v = (T *)pb.v, *bestx = (T *)pb.best;
+    const T *mu0 = (const T *)pb.mu0, *S = (const T *)pb.S;
+    const long long n3 = gc_stride(pb);
+    T *gc = (T *)pb.gc;
+    const T *c1 = gc, *c2 = gc + n3, *c3 = gc + 2 * n3;             // gA, G2', G3
+    const int n = n_items * 3, halo_n = 2 * JS;
+    const long long lo_ = (pb.win_begin - pb.frame_offset) * (long long)JS, hi_ = (pb.win_end - pb.frame_offset) * (long long)JS;
+    const int lo_el = (int)(lo_ < 0 ? 0 : (lo_ > n ? n : lo_)), hi_el = (int)(hi_ < 0 ? 0 : (hi_ > n ? n : hi_));
+    const bool whole = lo_el <= 0 && hi_el >= n;
+    T *left_halo = nullptr, *right_halo = nullptr;                  // my first / last two frames are the neighbours' halo frames
+    if (pb.rank > 0 && b == 0)
+        left_halo = reinterpret_cast<T *>(reinterpret_cast<char *>(pb.xchg[pb.rank - 1]) + MC3D_XCHG_X_OFFSET) + (pb.n_frames_left + 2) * (long long)JS;
+    if (pb.rank < pb.world - 1 && b == G - 1)
+        right_halo = reinterpret_cast<T *>(reinterpret_cast<char *>(pb.xchg[pb.rank + 1]) + MC3D_XCHG_X_OFFSET);
+    // elements: left edge [eL0, A0), interior pairs [A0, A1) (A0 even, A1 - A0 even), right edge and an odd leftover [A1, eR1)
+    const int eL0 = r_lo * 3, A0 = eL0 + 3 * E, eR1 = r_hi * 3;
+    const int A1 = A0 + ((eR1 - 3 * E - A0) & ~1);
+    const int n_edge = (A0 - eL0) + (eR1 - A1);
+    constexpr int CI = SWEEP_ITEMS * RF_THREADS, CE = 3 * CI;       // items / elements per trip
+    const int n_c = (r_hi - r_lo + CI - 1) / CI, n_a = (A1 - A0 + CE - 1) / CE;
+    Vec2 *stage2 = reinterpret_cast<Vec2 *>(stage);                 // [18][NT] pairs
+    T *stage_ms = stage + 36 * NT;                                  // [2][SWEEP_ITEMS][5][NT]
+    for (long long it = 0; it < n_iters; ++it) {
+        const RefineDerived dv = derive(pb, tot, st);
+        double gnorm2;
+        const GradMix<T> mix = mix3_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);   // mu_prev as pass 1 used it
+        const bool last_iter = it + 1 == n_iters;
+        const StepScalars<T> ss = step_scalars<T>(pb, 1, gnorm2, st, dv, bias, &best_pending, last_iter);
+        if (last_iter || ss.stop) {                                // Adam alone (the launch ends here); halos leave first (block 0)
+            step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, true, mix, true, seq, nullptr, true, counts, &ss);
+            grid_barrier(pb, 2, seq);
+            return;
+        }
+        if (tid == 0) {
+            if (b == 0) write_next_state<T>(pb, parity, ss, dv, mix.mu, true, counts);
+            adamc[0] = ss.clip_nan ? (T)NAN : ss.clipT; adamc[1] = ss.w1; adamc[2] = ss.b2; adamc[3] = ss.w2;
+            adamc[4] = ss.inv_bc2_sqrt; adamc[5] = ss.eps; adamc[6] = ss.step_size;
+        }
+        __syncthreads();
+        const bool wr_old = ss.wr_old, wr_new = ss.wr_new;
+        const T beta = mix.beta, gamma = mix.gamma;
+        // Adam of one element with the constants from shared memory (registers are pass 1's)
+        auto adam_el = [&](int i, T ga, T g2, T g3, T &mi, T &vi, T &xi) {
+            T gi = fma(beta, g2, fma(gamma, g3, ga));
+            if (!whole && !(i >= lo_el && i < hi_el)) gi = (T)0;
+            gi *= adamc[0];                                        // clip (NaN when the norm is)
+            mi = mi + (gi - mi) * adamc[1];                        // exp_avg.lerp_(grad, 1 - beta1)
+            vi = vi * adamc[2] + adamc[3] * gi * gi;               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+            const T denom = sqrt_c(vi) * adamc[4] + adamc[5];
+            xi = xi - adamc[6] * div_c(mi, denom);                 // param.addcdiv_(exp_avg, denom, value=-step_size)
+        };
+        // 1. the two edges of my range, announced at once
+        bool pushed = false;
+        for (int q = tid; q < n_edge; q += NT) {
+            const int i = q < A0 - eL0 ? eL0 + q : A1 + (q - (A0 - eL0));
+            T mi = m[i], vi = v[i], xi = x[i];
+            if (wr_old) bestx[i] = xi;
+            adam_el(i, c1[i], c2[i], c3[i], mi, vi, xi);
+            m[i] = mi; v[i] = vi; x[i] = xi;
+            if (wr_new) bestx[i] = xi;
+            if (left_halo && i < halo_n) { left_halo[i] = xi; pushed = true; }
+            if (right_halo && i >= n - halo_n) { right_halo[i - (n - halo_n)] = xi; pushed = true; }
+        }
+        if (pushed) fence_sys();
+        __syncthreads();
+        // 2. Adam chunk 0 while the neighbours announce theirs
+        auto issue = [&](int k) {                                   // Adam chunk k + the Gaussians of pass-1 chunk k
+            const int p0 = (A0 >> 1) + k * (CE / 2) + tid;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int pi = p0 + r * NT;
+                if (2 * pi < A1) {
+                    cp_async_bytes<sizeof(Vec2)>(stage2 + (0 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(c1) + pi);
+                    cp_async_bytes<sizeof(Vec2)>(stage2 + (1 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(c2) + pi);
+                    cp_async_bytes<sizeof(Vec2)>(stage2 + (2 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(c3) + pi);
+                    cp_async_bytes<sizeof(Vec2)>(stage2 + (3 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(m) + pi);
+                    cp_async_bytes<sizeof(Vec2)>(stage2 + (4 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(v) + pi);
+                    cp_async_bytes<sizeof(Vec2)>(stage2 + (5 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(x) + pi);
+                }
+            }
+            if (k < n_c) {
+                T *ms = stage_ms + (k & 1) * (SWEEP_ITEMS * 5 * NT);
+#pragma unroll
+                for (int u = 0; u < SWEEP_ITEMS; ++u) {
+                    const int e = r_lo + k * CI + u * NT + tid;
+                    if (e < r_hi) {
+                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 0) * NT + tid, mu0 + 2LL * e);
+                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 1) * NT + tid, mu0 + 2LL * e + 1);
+                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 2) * NT + tid, S + 3LL * e);
+                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 3) * NT + tid, S + 3LL * e + 1);
+                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 4) * NT + tid, S + 3LL * e + 2);
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        auto finish = [&](int k) {
+            cp_async_wait_all();
+            const int p0 = (A0 >> 1) + k * (CE / 2) + tid;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int pi = p0 + r * NT;
+                if (2 * pi < A1) {
+                    const Vec2 ga = stage2[(0 * 3 + r) * NT + tid], g2 = stage2[(1 * 3 + r) * NT + tid], g3 = stage2[(2 * 3 + r) * NT + tid];
+                    Vec2 mv = stage2[(3 * 3 + r) * NT + tid], vv = stage2[(4 * 3 + r) * NT + tid], xv = stage2[(5 * 3 + r) * NT + tid];
+                    if (wr_old) reinterpret_cast<Vec2 *>(bestx)[pi] = xv;
+                    adam_el(2 * pi, ga.a, g2.a, g3.a, mv.a, vv.a, xv.a);
+                    adam_el(2 * pi + 1, ga.b, g2.b, g3.b, mv.b, vv.b, xv.b);
+                    reinterpret_cast<Vec2 *>(m)[pi] = mv; reinterpret_cast<Vec2 *>(v)[pi] = vv; reinterpret_cast<Vec2 *>(x)[pi] = xv;
+                    if (wr_new) reinterpret_cast<Vec2 *>(bestx)[pi] = xv;
+                }
+            }
+        };
+        issue(0);
+        if (tid == 0) {
+            if (left_halo) { fence_sys(); st_relaxed_sys(&xchg_of(pb, pb.rank - 1)->halo_seq[1], seq); }
+            if (right_halo) { fence_sys(); st_relaxed_sys(&xchg_of(pb, pb.rank + 1)->halo_seq[0], seq); }
+            fence_gpu();
+            st_relaxed_sys(&mine->blk_seq[b], seq);                // my edges hold x of step `seq`
+            if (b > 0) xchg_wait(pb, &mine->blk_seq[b - 1], seq);
+            else if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], seq);
+            if (b < G - 1) xchg_wait(pb, &mine->blk_seq[b + 1], seq);
+            else if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], seq);
+            fence_xchg(pb);
+        }
+        finish(0);
+        __syncthreads();
+        // 3. the sweep
+        P1Const<T> pc = p1_const<T>(pb, (T)mix.mu);
+        pc.alpha_a = counts[0] > 0.0 ? (T)(1.0 / counts[0]) : (T)0;
+        pc.sigma_a = (do_smooth && counts[1] > 0.0) ? (T)(2.0 * pb.lambda_smooth / counts[1]) : (T)0;
+        T a[NS2];
+#pragma unroll
+        for (int i = 0; i < NS2; ++i) a[i] = (T)0;
+        const int dt = NT / J, dj = NT - dt * J;
+        int e = r_lo + tid;
+        int t = e / J, j = e - t * J;
+        for (int i = 0; i < n_c; ++i) {
+            // the items' own positions first: they were written a moment ago (L2), the copies below are issued while they travel
+            T px[SWEEP_ITEMS][3];
+            unsigned ptk[SWEEP_ITEMS][3];
+#pragma unroll
+            for (int u = 0; u < SWEEP_ITEMS; ++u) {
+                const int eu = e + u * NT;
+                int tu = t + u * dt, ju = j + u * dj;
+                if (ju >= J) { ju -= J; ++tu; }
+                if (ju >= J) { ju -= J; ++tu; }
+                if (eu < r_hi) {
+                    px[u][0] = x[3LL * eu]; px[u][1] = x[3LL * eu + 1]; px[u][2] = x[3LL * eu + 2];
+                    ptk[u][0] = pc.tok[tu]; ptk[u][1] = pc.tok[tu + 1]; ptk[u][2] = pc.tok[tu + 2];
+                }
+            }
+            issue(i + 1);                                           // Adam chunk i + 1 (if any), the Gaussians of the next trip
+            const T *ms = stage_ms + (i & 1) * (SWEEP_ITEMS * 5 * NT);
+#pragma unroll
+            for (int u = 0; u < SWEEP_ITEMS; ++u, e += NT, t += dt, j += dj) {
+                if (j >= J) { j -= J; ++t; }
+                if (e < r_hi) {
+                    const P1Own<T> own{px[u][0], px[u][1], px[u][2], ms[(u * 5 + 0) * NT + tid], ms[(u * 5 + 1) * NT + tid],
+                                       ms[(u * 5 + 2) * NT + tid], ms[(u * 5 + 3) * NT + tid], ms[(u * 5 + 4) * NT + tid]};
+                    costgrad_item<T, true>(pc, tb, camf, t, j, x + 3LL * e, own, nullptr, nullptr, ptk[u][0], ptk[u][1], ptk[u][2],
+                                           gc + 3LL * e, n3, a);
+                }
+            }
+            finish(i + 1);
+            __syncthreads();
+        }
+        {
+            double acc[NS2];
+#pragma unroll
+            for (int i = 0; i < NS2; ++i) acc[i] = (double)a[i];
+            block_reduce_add<NS2>(acc, red, mine->acc2[parity ^ 1]);
+        }
+        if (take_ticket(mine, 0)) publish2_ll(pb, parity ^ 1, seq + 1, false);
+        gather2_ll(pb, parity ^ 1, seq + 1, tot, halves, false);    // the step's one grid-wide meeting (+ cross-rank sums)
+        const bool same = tot[1] == counts[0] && (!do_smooth || tot[3] == counts[1]);
+        counts[0] = tot[1]; counts[1] = tot[3];
+        if (!same) pass1_checked<T>(pb, tb, camf, parity ^ 1, seq + 1, (T)mix.mu, counts, 1, red, tot, halves);
+        st[0] = ss.step; st[1] = ss.run_sum; st[2] = ss.run_cnt; st[3] = ss.best; st[4] = ss.no_imp; st[5] = 0.0;
+        st[6] = ss.iters; st[7] = ss.improved ? 1.0 : 0.0; st[8] = mix.mu; st[9] = counts[0]; st[10] = counts[1];
+        parity ^= 1;
+        seq += 1;
+    }
+}
+
 // All iterations inside one persistent cooperative kernel: two grid barriers per step.
 // BLOCKS = CTAs per SM the register allocation is held to: 2 = up to 128 registers (fastest while
 // a step is latency-bound), 3 = 80 registers (fastest from ~25 000 frames x 17 joints per GPU up: 122 vs 144 us per
 // step at 100 000 frames).
 template <typename T, int BLOCKS>
 __global__ void __launch_bounds__(RF_THREADS, BLOCKS)
-refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_parity, long long n_iters, int tiled) {
-    extern __shared__ __align__(16) unsigned char p1_smem[];      // tiled pass 1: per warp a two-stage ring + the output tile
-    __shared__ __align__(8) uint64_t p1_bars[(RF_THREADS / 32) * P1_STAGES];
+refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_parity, long long n_iters, int sweep) {
+    extern __shared__ __align__(16) unsigned char sweep_smem[];   // fused sweep: 18 staged scalars per thread
     __shared__ double red[8 * NS2];
     __shared__ RefineTables tb;
     __shared__ __align__(16) T camf[MC3D_MAX_VIEWS * CAM_STRIDE];
@@ -1270,15 +1466,12 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
     double *ctrl = pb.ctrl;
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
     load_cameras_and_tables(pb, tb, camf);
-    T *wsm = reinterpret_cast<T *>(p1_smem) + (size_t)(threadIdx.x >> 5) * p1_warp_scalars(pb.n_joints);
-    uint64_t *bars = p1_bars + (threadIdx.x >> 5) * P1_STAGES;
-    P1Ring ring{0u, 0u};
-    bool best_pending = false;                                     // the best snapshot is owed (see step_loop)
-    if (tiled && (threadIdx.x & 31) == 0) {
-        for (int s = 0; s < P1_STAGES; ++s) mbar_init(bars + s, 1);
-        fence_mbar_init();
-    }
+    bool best_pending = false;                                     // the best snapshot is owed (see step_flags)
     __syncthreads();
+    if (sweep) {
+        fused_sweep_run<T>(pb, tb, camf, first_parity & 1, n_iters, red, tot, bias, halves, reinterpret_cast<T *>(sweep_smem));
+        return;
+    }
     int parity = first_parity & 1;
     for (long long it = 0; it < n_iters; ++it, parity ^= 1) {
         double st[11];                                             // state entering this step (written before the last barrier)
@@ -1298,22 +1491,7 @@ refine_fused2_kernel(const __grid_constant__ mc3d_refine_problem pb, int first_p
         // change only when a value turns non-finite).  If this step's totals say otherwise -- or nothing is known yet: the
         // first step after the state was initialised -- the pass is repeated once with the right counts.
         double counts[2] = {st[9], st[10]};
-        const bool do_smooth = pb.lambda_smooth > 0.0;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            const T alpha_a = counts[0] > 0.0 ? (T)(1.0 / counts[0]) : (T)0;
-            const T sigma_a = (do_smooth && counts[1] > 0.0) ? (T)(2.0 * pb.lambda_smooth / counts[1]) : (T)0;
-            {
-                double acc[NS2];
-                if (tiled) costgrad_tiles<T>(pb, tb, camf, (T)st[8], acc, wsm, bars, ring, alpha_a, sigma_a);
-                else costgrad_loop<T, true>(pb, tb, camf, (T)st[8], acc, alpha_a, sigma_a);
-                block_reduce_add<NS2>(acc, red, mine->acc2[parity]);
-            }
-            if (take_ticket(mine, 0)) publish2_ll(pb, parity, seq, attempt != 0);
-            gather2_ll(pb, parity, seq, tot, halves, attempt != 0);    // grid barrier + cross-rank sums in one
-            const bool same = tot[1] == counts[0] && (!do_smooth || tot[3] == counts[1]);
-            counts[0] = tot[1]; counts[1] = tot[3];
-            if (same) break;                                       // identical decision in every block and rank
-        }
+        pass1_checked<T>(pb, tb, camf, parity, seq, (T)st[8], counts, 0, red, tot, halves);
         const RefineDerived dv = derive(pb, tot, st);
         double gnorm2;
         const GradMix<T> mix = mix3_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);  // mu_prev as pass 1 used it
@@ -1467,16 +1645,16 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
     mc3d_refine_problem prob = *pb;
     if (fused_env == 1 || (fused_env != 0 && small)) {
         const char *envb = getenv("MC3D_REFINE_BLOCKS");            // 2 / 3 force a register build (measurement)
-        const bool big = envb ? atoi(envb) >= 3 : n_items > 425000;
+        const char *envs = getenv("MC3D_REFINE_SWEEP");
+        int sweep = !(envs && atoi(envs) == 0) && pb->gauss_cam_stride == 0;
+        // the fused sweep is fastest spill-free (2 CTAs x 128 registers: 94 vs 109 us per step at 100 000 frames); the two-pass
+        // form of large shards with 3 CTAs x 80 registers
+        const bool big = envb ? atoi(envb) >= 3 : (!sweep && n_items > 425000);
         auto kern = big ? refine_fused2_kernel<T, 3> : refine_fused2_kernel<T, 2>;
-        // Tiled pass 1 (every warp its own TMA pipeline): camera-0 Gaussians, 16-byte aligned arrays, and a ring that leaves
-        // room for the build's CTAs per SM; otherwise the grid-stride pass 1.
-        const char *envt = getenv("MC3D_REFINE_TILED");             // 1 selects it (measured slower than the grid-stride pass)
-        size_t dyn = (size_t)(RF_THREADS / 32) * p1_warp_scalars(pb->n_joints) * sizeof(T);
-        int tiled = (envt && atoi(envt) != 0) && pb->gauss_cam_stride == 0 && aligned16(pb->x) && aligned16(pb->mu0) &&
-                    aligned16(pb->S) && aligned16(pb->gc) && dyn <= (size_t)(big ? 60 : 90) * 1024 && n_items < (1LL << 30);
-        if (!tiled) dyn = 0;
-        // static + dynamic shared memory beyond 48 KB needs the opt-in (the kernel's static part is ~12 KB)
+        // Fused sweep (Adam of step s beside pass 1 of step s + 1, one grid-wide meeting per step): every block needs a range
+        // that holds its two 2-frame edges and some interior; MC3D_REFINE_SWEEP=0 forbids it (measurement).
+        size_t dyn = (size_t)RF_THREADS * SWEEP_STAGE * sizeof(T);
+        if (!sweep) dyn = 0;
         if (dyn > 0) { const int as = func_max_smem_once((const void *)kern, 200 * 1024); if (as != MC3D_OK) return as; }
         int per_sm = 0;
         MC3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RF_THREADS, dyn));
@@ -1485,9 +1663,10 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
         long long grid = (n_items + RF_THREADS - 1) / RF_THREADS;
         if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;      // all blocks co-resident
         if (grid < 1) grid = 1;
+        if (grid > MC3D_XCHG_BLOCK_FLAGS || n_items / grid < 4LL * pb->n_joints + 32 || n_items >= (1LL << 30)) sweep = 0;
         int parity = (int)(first_step & 1);
         long long iters = n_iters;
-        void *args[] = {(void *)&prob, (void *)&parity, (void *)&iters, (void *)&tiled};
+        void *args[] = {(void *)&prob, (void *)&parity, (void *)&iters, (void *)&sweep};
         MC3D_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(RF_THREADS), args, dyn, stream));
         count_launch();
         return MC3D_OK;
