@@ -637,10 +637,11 @@ def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0, peak=
     esize = 4 if dtype_name == 'f32' else 8
     # per joint-frame and iteration read x, m, v, mu0, S (15 scalars) and write x, m, v (9), plus the gradient
     # written and read once when the step is split in passes (6): 30 scalars = 120 B in float.  The shipped two-phase step
-    # stores FOUR gradient components and moves 50 scalars = 200 B.
+    # stores THREE gradient components: pass 1 reads x, mu0, S (8) and writes 9, Adam reads 9 + m, v, x (9)
+    # and writes m, v, x (9) = 44 scalars = 176 B (the best-trajectory snapshot is written when an improving streak ends).
     us = 1e3 * ms / iters
     algo = n_frames * 17 * 30 * esize
-    moved = n_frames * 17 * 50 * esize
+    moved = n_frames * 17 * 44 * esize
     per_gpu = algo / world
     out = {'frames': n_frames, 'iters': iters, 'dtype': dtype_name, 'iters_per_s': iters / (ms * 1e-3), 'us_per_iter': us,
            'algorithmic_bytes_per_iter': algo, 'moved_bytes_per_iter_two_phase': moved,
@@ -650,10 +651,12 @@ def refine_benchmark(n_frames, iters, dtype_name, device, world=1, seed=0, peak=
     if peak:
         gbs = per_gpu / (us * 1e-6) / 1e9
         out['roofline'] = {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
-                           'algorithmic_bytes_per_joint_frame': 30 * esize, 'moved_bytes_per_joint_frame': 50 * esize,
-                           'per': 'GPU', 'kernel': 'mc3d::refine_fused2_kernel (pass 1: costs + gradient components; pass 2: clip + Adam)',
+                           'algorithmic_bytes_per_joint_frame': 30 * esize, 'moved_bytes_per_joint_frame': 44 * esize,
+                           'achieved_moved': gbs * 44 / 30, 'frac_moved': gbs * 44 / 30 / peak,
+                           'per': 'GPU', 'kernel': 'mc3d::refine_fused2_kernel (float state: fused sweep, Adam of step s beside pass 1 of '
+                                                   'step s + 1; double state: pass 1, then clip + Adam)',
                            'note': 'a shard of 12 500 .. 25 000 frames (25 .. 50 MB of state) is L2-resident and the step is bound by '
-                                   'latency (two grid barriers, one cross-rank exchange), not by HBM'}
+                                   'latency (one grid-wide meeting with the cross-rank exchange, the per-thread chain of pass 1), not by HBM'}
     return out
 
 

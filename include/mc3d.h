@@ -141,7 +141,8 @@ typedef enum { MC3D_KPT_PLAIN = 0, MC3D_KPT_NV3 = 1, MC3D_KPT_N3V = 2 } mc3d_kpt
 enum {
     MC3D_DECODE_FLAG_WRITE_BACK = 1,  /* also store the thresholded maps in place (upstream mutates its input) */
     MC3D_DECODE_FLAG_GENERIC = 2,     /* force the plain-load kernel (test hook) */
-    MC3D_DECODE_FLAG_TMA = 4          /* force the TMA / shared-memory kernel even for 64x48 maps (test hook) */
+    MC3D_DECODE_FLAG_TMA = 4,         /* force the TMA / shared-memory kernel even for 64x48 maps (test hook) */
+    MC3D_DECODE_FLAG_NO_STAGE = 8     /* 64x48 maps with moments: plain streaming loads instead of the per-warp TMA stage (A/B) */
 };
 int mc3d_decode_heatmaps_f32(const float *d_heatmaps, int64_t n_maps, int H, int W, float threshold, int flags,
                              int kpt_layout, int views, int joints, const float *d_affine, int affine_group,

@@ -19,6 +19,7 @@ KPT_PLAIN, KPT_NV3, KPT_N3V = 0, 1, 2
 DECODE_FLAG_WRITE_BACK = 1
 DECODE_FLAG_GENERIC = 2
 DECODE_FLAG_TMA = 4
+DECODE_FLAG_NO_STAGE = 8
 
 
 class Mc3dError(RuntimeError):

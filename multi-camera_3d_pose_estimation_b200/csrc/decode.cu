@@ -194,17 +194,33 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
 }
 
 #ifndef MC3D_DEC_BLOCKS
-#define MC3D_DEC_BLOCKS 4
+#define MC3D_DEC_BLOCKS 4        // CTAs per SM of the unstaged moments kernel (128 registers, 240 B spilled: occupancy beats spills)
+#endif
+#ifndef MC3D_DEC_STAGED_BLOCKS
+#define MC3D_DEC_STAGED_BLOCKS 3 // CTAs per SM of the staged one: 168 registers hold the map (measured 0.83 of the HBM peak; 4 CTAs x
+#endif                           // 128 registers with their spills 0.46, 2 CTAs x 255 0.75, two stages per warp 0.71)
+#ifndef MC3D_DEC_STAGES
+#define MC3D_DEC_STAGES 1
 #endif
 // MOMENTS = false (keypoints only, e.g. decode -> triangulate): the thresholding, both moment passes and six of the
 // eight warp reductions disappear and the kernel is a pure streaming max.
-template <bool MOMENTS>
-__global__ void __launch_bounds__(128, MOMENTS ? MC3D_DEC_BLOCKS : 4)
+// STAGED (the moments variant): the two passes cost ~1 850 issue slots per map and 16 resident warps cannot hide the ~3 000
+// cycles a map takes to arrive behind them, so each warp also owns ONE 12 KB shared-memory stage: its lane 0 starts the 1-D TMA
+// bulk copy of the warp's NEXT map as soon as the current one has been lifted from the stage into registers (24 conflict-free
+// LDS.128 per lane), and the copy travels while the current map is reduced.  16 warps x 12 KB = 192 KB per SM in flight.
+template <bool MOMENTS, bool STAGED = false>
+__global__ void __launch_bounds__(128, STAGED ? MC3D_DEC_STAGED_BLOCKS : (MOMENTS ? MC3D_DEC_BLOCKS : 4))
 decode_reg6448_kernel(const float *__restrict__ hm, float *__restrict__ hm_wb, long long n_maps,
                       const float *__restrict__ affine, float *__restrict__ kpt, double *__restrict__ moments,
                       const __grid_constant__ DecodeParams p) {
     constexpr int W = 48, HW = 64 * 48, NK = HW / 128;          // 24 float4 per lane
+    constexpr int NST = MC3D_DEC_STAGES;
+    extern __shared__ __align__(128) unsigned char dec_stage_raw[];
+    __shared__ __align__(8) uint64_t dec_bars[4 * NST];
     const int lane = threadIdx.x & 31;
+    const float4 *stage = reinterpret_cast<const float4 *>(dec_stage_raw) + (threadIdx.x >> 5) * (NST * HW / 4);
+    uint64_t *bar = &dec_bars[(threadIdx.x >> 5) * NST];
+    uint32_t uses = 0;
     const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long stride = ((long long)gridDim.x * blockDim.x) >> 5;
     // lane constants: k = 3 j + r  ->  x0 = X[r], y = 8 j + Y[r]
@@ -216,11 +232,37 @@ decode_reg6448_kernel(const float *__restrict__ hm, float *__restrict__ hm_wb, l
         Yr[r] = (float)(2 * r + u / W);
     }
     const float thr = p.thr;
+    if (STAGED) {
+        if (lane == 0) {
+            for (int q = 0; q < NST; ++q) mbar_init(bar + q, 1);
+            fence_mbar_init();
+            for (int q = 0; q < NST; ++q)
+                if (gwarp + q * stride < n_maps) {
+                    mbar_arrive_expect_tx(bar + q, HW * 4);
+                    bulk_g2s(const_cast<float4 *>(stage) + q * (HW / 4), hm + (gwarp + q * stride) * HW, HW * 4, bar + q);
+                }
+        }
+        __syncwarp();
+    }
     for (long long map = gwarp; map < n_maps; map += stride) {
         const float4 *src = reinterpret_cast<const float4 *>(hm + map * HW) + lane;
         float4 v[NK];
+        if (STAGED) {
+            const uint32_t q = uses % NST;
+            mbar_wait(bar + q, (uses / NST) & 1u);
+            ++uses;
+            const float4 *st = stage + q * (HW / 4);
 #pragma unroll
-        for (int k = 0; k < NK; ++k) v[k] = ldg_stream(src + 32 * k);
+            for (int k = 0; k < NK; ++k) v[k] = st[lane + 32 * k];
+            __syncwarp();                                        // every lane has lifted its share: the stage is free
+            if (lane == 0 && map + NST * stride < n_maps) {
+                mbar_arrive_expect_tx(bar + q, HW * 4);
+                bulk_g2s(const_cast<float4 *>(st), hm + (map + NST * stride) * HW, HW * 4, bar + q);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NK; ++k) v[k] = ldg_stream(src + 32 * k);
+        }
         // pass 1: argmax on the raw values, threshold in place, zeroth and first moments
         float best = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
         int bk = 0;
@@ -393,10 +435,16 @@ int decode_device(const float *d_hm, long long n_maps, int H, int W, float thr, 
     const bool tma_ok = (W % 4 == 0) && aligned16(d_hm) && map_bytes <= 96 * 1024 && !(flags & MC3D_DECODE_FLAG_GENERIC);
     const bool reg_ok = H == 64 && W == 48 && aligned16(d_hm) && !(flags & (MC3D_DECODE_FLAG_GENERIC | MC3D_DECODE_FLAG_TMA));
     if (reg_ok) {
-        long long grid = (long long)sm_count() * 4;
+        const bool staged = (d_moments || p.write_back) && !(flags & MC3D_DECODE_FLAG_NO_STAGE);
+        long long grid = (long long)sm_count() * (staged ? MC3D_DEC_STAGED_BLOCKS : 4);   // persistent: one wave of resident CTAs
         const long long need = (n_maps + 3) / 4;
         if (grid > need) grid = need;
-        if (d_moments || p.write_back)
+        if ((d_moments || p.write_back) && !(flags & MC3D_DECODE_FLAG_NO_STAGE)) {
+            auto kern = decode_reg6448_kernel<true, true>;
+            const size_t smem = 4 * MC3D_DEC_STAGES * map_bytes;    // the warps' stages
+            { const int as = func_max_smem_once((const void *)kern, 112 * 1024); if (as != MC3D_OK) return as; }
+            kern<<<(unsigned)grid, 128, smem, stream>>>(d_hm, wb, n_maps, d_affine, d_kpt, d_moments, p);
+        } else if (d_moments || p.write_back)
             decode_reg6448_kernel<true><<<(unsigned)grid, 128, 0, stream>>>(d_hm, wb, n_maps, d_affine, d_kpt, d_moments, p);
         else
             decode_reg6448_kernel<false><<<(unsigned)grid, 128, 0, stream>>>(d_hm, wb, n_maps, d_affine, d_kpt, nullptr, p);

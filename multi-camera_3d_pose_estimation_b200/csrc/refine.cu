@@ -1103,7 +1103,9 @@ __device__ __forceinline__ void gather2_ll(const mc3d_refine_problem &pb, int pa
         halves[q] = (unsigned int)word;
     }
     __syncthreads();
-    if (threadIdx.x == 0) fence_xchg(pb);                          // acquire: what the other blocks / ranks wrote before their words
+    // acquire what the other blocks of this GPU wrote before their tickets (device scope: the peers' halo stores are acquired
+    // where their own flags are waited for)
+    if (threadIdx.x == 0) fence_gpu();
     if (threadIdx.x < NS2) {
         double s = 0.0;
         for (int r = 0; r < pb.world; ++r) {
@@ -1383,11 +1385,12 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             if (right_halo) { fence_sys(); st_relaxed_sys(&xchg_of(pb, pb.rank + 1)->halo_seq[0], seq); }
             fence_gpu();
             st_relaxed_sys(&mine->blk_seq[b], seq);                // my edges hold x of step `seq`
+            bool remote = false;
             if (b > 0) xchg_wait(pb, &mine->blk_seq[b - 1], seq);
-            else if (pb.rank > 0) xchg_wait(pb, &mine->halo_seq[0], seq);
+            else if (pb.rank > 0) { xchg_wait(pb, &mine->halo_seq[0], seq); remote = true; }
             if (b < G - 1) xchg_wait(pb, &mine->blk_seq[b + 1], seq);
-            else if (pb.rank < pb.world - 1) xchg_wait(pb, &mine->halo_seq[1], seq);
-            fence_xchg(pb);
+            else if (pb.rank < pb.world - 1) { xchg_wait(pb, &mine->halo_seq[1], seq); remote = true; }
+            if (remote) fence_sys(); else fence_gpu();             // a system-scope acquire only where a peer stored
         }
         finish(0);
         __syncthreads();
@@ -1629,9 +1632,18 @@ int refine_phase(const mc3d_refine_problem *pb, int phase, long long step_index,
 
 // Every rank must pick the same step variant (they meet inside the kernels), so the size that decides is the LARGEST
 // shard of the run (frame_shard sizes differ by at most one frame), not this rank's own.
-static bool shard_is_small(const mc3d_refine_problem *pb) {
+static bool sweep_wanted(const mc3d_refine_problem *pb, size_t elem_size) {
+    // float state only: in double the step is bound by the FP64 pipe and the sweep's bookkeeping costs more than the
+    // overlap returns (measured 261 vs 247 us per step at 100 000 frames, 42 vs 34 at 12 500)
+    const char *envs = getenv("MC3D_REFINE_SWEEP");                 // 0 forbids the fused sweep (measurement)
+    return !(envs && atoi(envs) == 0) && pb->gauss_cam_stride == 0 && elem_size == 4;
+}
+static bool shard_is_small(const mc3d_refine_problem *pb, size_t elem_size) {
     const long long world = pb->world > 1 ? pb->world : 1;
     const long long frames = pb->world > 1 ? (pb->total_frames + world - 1) / world : pb->n_frames;
+    // the fused sweep walks block-owned ranges of any length (measured to 200 000 frames); the two-pass persistent kernel was
+    // measured up to ~150 000 frames x 17 joints
+    if (sweep_wanted(pb, elem_size)) return frames * pb->n_joints < (1LL << 30);
     return frames * pb->n_joints <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
 }
 
@@ -1641,12 +1653,11 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
     const long long n_items = (long long)pb->n_frames * pb->n_joints;
     const char *env = getenv("MC3D_REFINE_FUSED");                  // 1 forces the persistent kernel, 0 forbids it
     const int fused_env = env ? atoi(env) : -1;
-    const bool small = shard_is_small(pb);
+    const bool small = shard_is_small(pb, sizeof(T));
     mc3d_refine_problem prob = *pb;
     if (fused_env == 1 || (fused_env != 0 && small)) {
         const char *envb = getenv("MC3D_REFINE_BLOCKS");            // 2 / 3 force a register build (measurement)
-        const char *envs = getenv("MC3D_REFINE_SWEEP");
-        int sweep = !(envs && atoi(envs) == 0) && pb->gauss_cam_stride == 0;
+        int sweep = sweep_wanted(pb, sizeof(T)) ? 1 : 0;
         // the fused sweep is fastest spill-free (2 CTAs x 128 registers: 94 vs 109 us per step at 100 000 frames); the two-pass
         // form of large shards with 3 CTAs x 80 registers
         const bool big = envb ? atoi(envb) >= 3 : (!sweep && n_items > 425000);
@@ -1726,7 +1737,7 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
         //   sizes measured (MC3D_RF_SMALL) the byte count is assumed to win and the three-kernel graph is used.
         const char *env2 = getenv("MC3D_REFINE_TWO_PHASE");          // 1 forces the two-phase step, 0 forbids it
         const int two_env = env2 ? atoi(env2) : -1;
-        if (two_env == 1 || (two_env != 0 && shard_is_small(pb))) return refine_run_two_phase<T>(pb, first_step, n_iters, stream);
+        if (two_env == 1 || (two_env != 0 && shard_is_small(pb, sizeof(T)))) return refine_run_two_phase<T>(pb, first_step, n_iters, stream);
     }
     // One rank, big shard: the exchange protocol (tickets, fences, flags) would only cost time -- run the plain kernels.
     mc3d_refine_problem plain = *pb;
@@ -1774,12 +1785,14 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
 // What refine_run would launch for this problem (same decisions, no launch).
 static const char *refine_plan(const mc3d_refine_problem *pb) {
     if (!pb) return "invalid";
-    const bool small = shard_is_small(pb);
+    const bool small = shard_is_small(pb, 8);                      // the dtype is not known here: the stricter answer
     const char *e2 = getenv("MC3D_REFINE_TWO_PHASE"), *ef = getenv("MC3D_REFINE_FUSED");
     const int two_env = e2 ? atoi(e2) : -1, fused_env = ef ? atoi(ef) : -1;
     const bool fused = fused_env == 1 || (fused_env != 0 && small);
     if (pb->gc && pb->xchg[0] && (two_env == 1 || (two_env != 0 && small)))
-        return fused ? "two-phase step, persistent cooperative kernel (2 grid barriers, 1 exchange of 17 sums + halo stores per step)"
+        return fused ? "two-phase step, persistent cooperative kernel (float state: fused sweep -- Adam of step s beside pass 1 of step "
+                       "s + 1, one grid-wide meeting per step; double state: two passes, 2 grid barriers; 1 exchange of 13 sums + halo "
+                       "stores per step)"
                      : "two-phase step, CUDA graph of 2 kernels per step (1 exchange of 17 sums + halo stores per step)";
     if (pb->xchg[0] && pb->world > 1)
         return "three-phase step, CUDA graph of 3 kernels per step with the in-kernel exchange (2 exchanges + halo stores per step)";

@@ -9,7 +9,8 @@ _KPT_LAYOUTS = {'plain': _lib.KPT_PLAIN, 'nv3': _lib.KPT_NV3, 'n3v': _lib.KPT_N3
 
 
 def decode_heatmaps(heatmaps, threshold=0.01, want_kpts=True, want_moments=True, write_back=False,
-                    kpt_layout='plain', affine=None, affine_group=None, generic=False, device=None, force_tma=False):
+                    kpt_layout='plain', affine=None, affine_group=None, generic=False, device=None, force_tma=False,
+                    no_stage=False):
     """heatmaps (..., H, W) float32 -> (kpts (..., 3) float32 [x, y, score] | None,
                                          moments (..., 6) float64 | None).
 
@@ -17,6 +18,8 @@ def decode_heatmaps(heatmaps, threshold=0.01, want_kpts=True, want_moments=True,
     and return keypoints as (T, J, C, 3) / (T, J, 3, C), ready for ``triangulate_multiview``.
     write_back=True also zeroes values < threshold in the input, as upstream does (mmpose_pose_estimation.py:166).
     affine (G, 4) float32 [sx, sy, ox, oy] per ``affine_group`` consecutive maps maps heatmap pixels to image pixels.
+    generic / force_tma / no_stage select a kernel variant (test hooks: plain loads; the shared-memory kernel for 64x48
+    maps; the 64x48 moments kernel without its per-warp TMA stage).
     """
     lib = _lib.lib()
     if heatmaps.ndim < 2:
@@ -67,7 +70,7 @@ def decode_heatmaps(heatmaps, threshold=0.01, want_kpts=True, want_moments=True,
             raise ValueError('affine table too short for the number of heatmaps')
         aff_ptr = affine.data_ptr()
     flags = (_lib.DECODE_FLAG_WRITE_BACK if write_back else 0) | (_lib.DECODE_FLAG_GENERIC if generic else 0) | \
-        (_lib.DECODE_FLAG_TMA if force_tma else 0)
+        (_lib.DECODE_FLAG_TMA if force_tma else 0) | (_lib.DECODE_FLAG_NO_STAGE if no_stage else 0)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.mc3d_decode_heatmaps_f32(heatmaps.data_ptr(), n, H, W, float(threshold), flags,

@@ -67,7 +67,7 @@ def test_means_stds_match_reference_golden():
 
 
 @pytest.mark.parametrize('shape', [(64, 48), (96, 72), (32, 32), (17, 23), (128, 96), (5, 4)])
-@pytest.mark.parametrize('generic', [False, True, 'tma'])
+@pytest.mark.parametrize('generic', [False, True, 'tma', 'no_stage'])
 def test_decode_vs_oracle(dec, syn, shape, generic):
     H, W = shape
     hm, _ = syn.gaussian_blob_heatmaps(300, H=H, W=W, seed=H * W) if min(H, W) > 16 else \
@@ -75,7 +75,7 @@ def test_decode_vs_oracle(dec, syn, shape, generic):
     hm[3] = 0.0
     hm[4] = -1.0                                                   # maximum <= 0 -> (-1, -1)
     hm[7, 0, 0] = 5.0                                              # maximum on the border: no sub-pixel shift
-    kp, mom = dec(_cuda(hm), generic=(generic is True), force_tma=(generic == 'tma'))
+    kp, mom = dec(_cuda(hm), generic=(generic is True), force_tma=(generic == 'tma'), no_stage=(generic == 'no_stage'))
     kp, mom = kp.cpu().numpy(), mom.cpu().numpy()
     ref_kp, ref_sc = D.argmax_decode(hm)
     assert np.array_equal(kp[:, :2], ref_kp)
@@ -123,7 +123,7 @@ def test_transposed_layouts_feed_triangulation(dec, syn):
 def test_write_back_on_device_keeps_subpixel_decode(dec, syn):
     """In-place thresholding (upstream quirk Q7) must not disturb the raw-neighbour read of the quarter-pixel shift."""
     hm, _ = syn.gaussian_blob_heatmaps(500, seed=8, noise=0.02)
-    for kw in ({}, {'force_tma': True}, {'generic': True}):
+    for kw in ({}, {'force_tma': True}, {'generic': True}, {'no_stage': True}):
         t = _cuda(hm.copy())
         kp, mom = dec(t, write_back=True, **kw)
         ref_kp, ref_sc = D.argmax_decode(hm)
@@ -149,7 +149,7 @@ def test_argmax_half_matches_transformers_port_of_mmpose(dec):
     """The kernel against tests/golden/argmax_vitpose.npz (HF transformers' port of mmpose's ``_get_max_preds``):
     integer pixel and score of every map, through all three kernel variants."""
     g = load_golden('argmax_vitpose.npz')
-    for kw in ({}, {'force_tma': True}, {'generic': True}):
+    for kw in ({}, {'force_tma': True}, {'generic': True}, {'no_stage': True}):
         kp, _ = dec(_cuda(g['heatmaps'].copy()), **kw)
         kp = kp.cpu().numpy()
         assert np.array_equal(kp[:, 2], g['scores'])
