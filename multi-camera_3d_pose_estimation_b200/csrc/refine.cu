@@ -1224,7 +1224,7 @@ __device__ __forceinline__ void pass1_checked(const mc3d_refine_problem &pb, con
 constexpr int SWEEP_ITEMS = 2;       // items of pass 1 per thread and trip
 // staged scalars per thread: 3 pairs x (gA, G2', G3, m, v, x) of the next Adam chunk + two buffers of (mu0, Sigma^-1) for the
 // items of the next / the current trip
-constexpr int SWEEP_STAGE = 36 + 2 * 5 * SWEEP_ITEMS;
+constexpr int SWEEP_STAGE = 36 + 2 * 5 * SWEEP_ITEMS + 3 * 3 * SWEEP_ITEMS;   // + three tiles of updated x (own positions of pass 1)
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async_bytes(void *smem_dst, const void *gmem_src) {
@@ -1288,6 +1288,9 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
     const int n_c = (r_hi - r_lo + CI - 1) / CI, n_a = (A1 - A0 + CE - 1) / CE;
     Vec2 *stage2 = reinterpret_cast<Vec2 *>(stage);                 // [18][NT] pairs
     T *stage_ms = stage + 36 * NT;                                  // [2][SWEEP_ITEMS][5][NT]
+    // x as Adam left it, chunk k in tile k % 3: the own position of a pass-1 item comes from here (its chunk's tile or the one
+    // before) instead of from L2, where it would be the first thing every warp of the block waits for after the trip's barrier
+    T *xtile = stage_ms + 2 * SWEEP_ITEMS * 5 * NT;                 // [3][CE]
     for (long long it = 0; it < n_iters; ++it) {
         const RefineDerived dv = derive(pb, tot, st);
         double gnorm2;
@@ -1317,21 +1320,6 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             const T denom = sqrt_c(vi) * adamc[4] + adamc[5];
             xi = xi - adamc[6] * div_c(mi, denom);                 // param.addcdiv_(exp_avg, denom, value=-step_size)
         };
-        // 1. the two edges of my range, announced at once
-        bool pushed = false;
-        for (int q = tid; q < n_edge; q += NT) {
-            const int i = q < A0 - eL0 ? eL0 + q : A1 + (q - (A0 - eL0));
-            T mi = m[i], vi = v[i], xi = x[i];
-            if (wr_old) bestx[i] = xi;
-            adam_el(i, c1[i], c2[i], c3[i], mi, vi, xi);
-            m[i] = mi; v[i] = vi; x[i] = xi;
-            if (wr_new) bestx[i] = xi;
-            if (left_halo && i < halo_n) { left_halo[i] = xi; pushed = true; }
-            if (right_halo && i >= n - halo_n) { right_halo[i - (n - halo_n)] = xi; pushed = true; }
-        }
-        if (pushed) fence_sys();
-        __syncthreads();
-        // 2. Adam chunk 0 while the neighbours announce theirs
         auto issue = [&](int k) {                                   // Adam chunk k + the Gaussians of pass-1 chunk k
             const int p0 = (A0 >> 1) + k * (CE / 2) + tid;
 #pragma unroll
@@ -1375,11 +1363,27 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
                     adam_el(2 * pi, ga.a, g2.a, g3.a, mv.a, vv.a, xv.a);
                     adam_el(2 * pi + 1, ga.b, g2.b, g3.b, mv.b, vv.b, xv.b);
                     reinterpret_cast<Vec2 *>(m)[pi] = mv; reinterpret_cast<Vec2 *>(v)[pi] = vv; reinterpret_cast<Vec2 *>(x)[pi] = xv;
+                    reinterpret_cast<Vec2 *>(xtile + (k % 3) * CE)[r * NT + tid] = xv;
                     if (wr_new) reinterpret_cast<Vec2 *>(bestx)[pi] = xv;
                 }
             }
         };
-        issue(0);
+        issue(0);                                                   // Adam chunk 0 travels while the edges are updated
+        // 1. the two edges of my range, announced at once
+        bool pushed = false;
+        for (int q = tid; q < n_edge; q += NT) {
+            const int i = q < A0 - eL0 ? eL0 + q : A1 + (q - (A0 - eL0));
+            T mi = m[i], vi = v[i], xi = x[i];
+            if (wr_old) bestx[i] = xi;
+            adam_el(i, c1[i], c2[i], c3[i], mi, vi, xi);
+            m[i] = mi; v[i] = vi; x[i] = xi;
+            if (wr_new) bestx[i] = xi;
+            if (left_halo && i < halo_n) { left_halo[i] = xi; pushed = true; }
+            if (right_halo && i >= n - halo_n) { right_halo[i - (n - halo_n)] = xi; pushed = true; }
+        }
+        if (pushed) fence_sys();
+        __syncthreads();
+        // 2. Adam chunk 0 while the neighbours announce theirs
         if (tid == 0) {
             if (left_halo) { fence_sys(); st_relaxed_sys(&xchg_of(pb, pb.rank - 1)->halo_seq[1], seq); }
             if (right_halo) { fence_sys(); st_relaxed_sys(&xchg_of(pb, pb.rank + 1)->halo_seq[0], seq); }
@@ -1415,7 +1419,14 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
                 if (ju >= J) { ju -= J; ++tu; }
                 if (ju >= J) { ju -= J; ++tu; }
                 if (eu < r_hi) {
-                    px[u][0] = x[3LL * eu]; px[u][1] = x[3LL * eu + 1]; px[u][2] = x[3LL * eu + 2];
+                    const int el = 3 * eu, off = el - A0;
+                    if (off >= 0 && el + 2 < A1 && off >= (i - 1) * CE) {      // Adam chunk i or i - 1: in the tiles
+                        const int ck = off >= i * CE ? i : i - 1;
+                        const T *tp = xtile + (ck % 3) * CE + (off - ck * CE);
+                        px[u][0] = tp[0]; px[u][1] = tp[1]; px[u][2] = tp[2];
+                    } else {
+                        px[u][0] = x[3LL * eu]; px[u][1] = x[3LL * eu + 1]; px[u][2] = x[3LL * eu + 2];
+                    }
                     ptk[u][0] = pc.tok[tu]; ptk[u][1] = pc.tok[tu + 1]; ptk[u][2] = pc.tok[tu + 2];
                 }
             }
