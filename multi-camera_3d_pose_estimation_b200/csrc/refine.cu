@@ -1224,7 +1224,7 @@ __device__ __forceinline__ void pass1_checked(const mc3d_refine_problem &pb, con
 constexpr int SWEEP_ITEMS = 2;       // items of pass 1 per thread and trip
 // staged scalars per thread: 3 pairs x (gA, G2', G3, m, v, x) of the next Adam chunk + two buffers of (mu0, Sigma^-1) for the
 // items of the next / the current trip
-constexpr int SWEEP_STAGE = 36 + 2 * 5 * SWEEP_ITEMS + 3 * 3 * SWEEP_ITEMS;   // + three tiles of updated x (own positions of pass 1)
+constexpr int SWEEP_STAGE = 36 + 2 * 5 * SWEEP_ITEMS + 4 * 3 * SWEEP_ITEMS;   // + four tile slots of updated x (pass 1 reads x there)
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async_bytes(void *smem_dst, const void *gmem_src) {
@@ -1288,9 +1288,12 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
     const int n_c = (r_hi - r_lo + CI - 1) / CI, n_a = (A1 - A0 + CE - 1) / CE;
     Vec2 *stage2 = reinterpret_cast<Vec2 *>(stage);                 // [18][NT] pairs
     T *stage_ms = stage + 36 * NT;                                  // [2][SWEEP_ITEMS][5][NT]
-    // x as Adam left it, chunk k in tile k % 3: the own position of a pass-1 item comes from here (its chunk's tile or the one
-    // before) instead of from L2, where it would be the first thing every warp of the block waits for after the trip's barrier
-    T *xtile = stage_ms + 2 * SWEEP_ITEMS * 5 * NT;                 // [3][CE]
+    // x as Adam left it, chunk k in tile slot k % 3 (and, when k % 3 == 0, also in slot 3, so that chunks k - 1 and k always lie
+    // side by side somewhere): everything pass 1 reads of x -- the item itself, two frames either side, its frame's bones -- lies
+    // in Adam chunks i - 1 and i, so trip i reads shared memory through ONE base pointer instead of L2, where the item's own
+    // position would be the first thing every warp of the block waits for after the trip's barrier.  Items whose window
+    // leaves the block's interior (its first / last ~4 J items) read global memory.
+    T *xtile = stage_ms + 2 * SWEEP_ITEMS * 5 * NT;                 // [4][CE]
     for (long long it = 0; it < n_iters; ++it) {
         const RefineDerived dv = derive(pb, tot, st);
         double gnorm2;
@@ -1364,6 +1367,7 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
                     adam_el(2 * pi + 1, ga.b, g2.b, g3.b, mv.b, vv.b, xv.b);
                     reinterpret_cast<Vec2 *>(m)[pi] = mv; reinterpret_cast<Vec2 *>(v)[pi] = vv; reinterpret_cast<Vec2 *>(x)[pi] = xv;
                     reinterpret_cast<Vec2 *>(xtile + (k % 3) * CE)[r * NT + tid] = xv;
+                    if (k % 3 == 0) reinterpret_cast<Vec2 *>(xtile + 3 * CE)[r * NT + tid] = xv;
                     if (wr_new) reinterpret_cast<Vec2 *>(bestx)[pi] = xv;
                 }
             }
@@ -1409,36 +1413,21 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
         int e = r_lo + tid;
         int t = e / J, j = e - t * J;
         for (int i = 0; i < n_c; ++i) {
-            // the items' own positions first: they were written a moment ago (L2), the copies below are issued while they travel
-            T px[SWEEP_ITEMS][3];
-            unsigned ptk[SWEEP_ITEMS][3];
-#pragma unroll
-            for (int u = 0; u < SWEEP_ITEMS; ++u) {
-                const int eu = e + u * NT;
-                int tu = t + u * dt, ju = j + u * dj;
-                if (ju >= J) { ju -= J; ++tu; }
-                if (ju >= J) { ju -= J; ++tu; }
-                if (eu < r_hi) {
-                    const int el = 3 * eu, off = el - A0;
-                    if (off >= 0 && el + 2 < A1 && off >= (i - 1) * CE) {      // Adam chunk i or i - 1: in the tiles
-                        const int ck = off >= i * CE ? i : i - 1;
-                        const T *tp = xtile + (ck % 3) * CE + (off - ck * CE);
-                        px[u][0] = tp[0]; px[u][1] = tp[1]; px[u][2] = tp[2];
-                    } else {
-                        px[u][0] = x[3LL * eu]; px[u][1] = x[3LL * eu + 1]; px[u][2] = x[3LL * eu + 2];
-                    }
-                    ptk[u][0] = pc.tok[tu]; ptk[u][1] = pc.tok[tu + 1]; ptk[u][2] = pc.tok[tu + 2];
-                }
-            }
             issue(i + 1);                                           // Adam chunk i + 1 (if any), the Gaussians of the next trip
             const T *ms = stage_ms + (i & 1) * (SWEEP_ITEMS * 5 * NT);
+            // chunks i - 1 and i side by side in the tile slots: element el of x at xwin[el] for lower <= el < A1
+            const int lower = A0 + (i > 0 ? i - 1 : 0) * CE;
+            const T *xwin = xtile + (i > 0 ? (i - 1) % 3 : 0) * CE - lower;
 #pragma unroll
             for (int u = 0; u < SWEEP_ITEMS; ++u, e += NT, t += dt, j += dj) {
                 if (j >= J) { j -= J; ++t; }
                 if (e < r_hi) {
-                    const P1Own<T> own{px[u][0], px[u][1], px[u][2], ms[(u * 5 + 0) * NT + tid], ms[(u * 5 + 1) * NT + tid],
+                    const int el = 3 * e;
+                    const bool in_tiles = el - 2 * JS >= lower && el + 2 * JS + 2 < A1;
+                    const T *xc = in_tiles ? xwin + el : x + el;
+                    const P1Own<T> own{xc[0], xc[1], xc[2], ms[(u * 5 + 0) * NT + tid], ms[(u * 5 + 1) * NT + tid],
                                        ms[(u * 5 + 2) * NT + tid], ms[(u * 5 + 3) * NT + tid], ms[(u * 5 + 4) * NT + tid]};
-                    costgrad_item<T, true>(pc, tb, camf, t, j, x + 3LL * e, own, nullptr, nullptr, ptk[u][0], ptk[u][1], ptk[u][2],
+                    costgrad_item<T, true>(pc, tb, camf, t, j, xc, own, nullptr, nullptr, pc.tok[t], pc.tok[t + 1], pc.tok[t + 2],
                                            gc + 3LL * e, n3, a);
                 }
             }
