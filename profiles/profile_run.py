@@ -62,13 +62,13 @@ def main():
                               max_iter=10 ** 9, ignore_distortions=False, window=(0, 100_000), n_window_frames=100_000,
                               hist_capacity=64)
         ms = timed(lambda: eng.run(16), reps=4) / 16
-        out['refine_step_f32_T100k'] = (ms, 1e3 / ms, 100_000 * 17 * 160 / ms / 1e6)
+        out['refine_step_f32_T100k'] = (ms, 1e3 / ms, 100_000 * 17 * 120 / ms / 1e6)        # 120 B per joint-frame
         eng.close()
         eng = rf.RefineEngine(init[:12500], gs[:12500], rows, syn.EXAMPLE_BODY_LENGTHS, torch_dtype=torch.float32, device=dev, lr=0.01,
                               betas=(0.9, 0.999), lambda_smooth=1e-6, lambda_body_length=1.0, patience=10 ** 9, tolerance=1e-5,
                               max_iter=10 ** 9, ignore_distortions=False, window=(0, 12_500), n_window_frames=12_500, hist_capacity=64)
         ms = timed(lambda: eng.run(16), reps=4) / 16           # one persistent launch = 16 steps
-        out['refine_step_f32_T12500'] = (ms, 1e3 / ms, 12_500 * 17 * 200 / ms / 1e6)
+        out['refine_step_f32_T12500'] = (ms, 1e3 / ms, 12_500 * 17 * 120 / ms / 1e6)
         eng.close()
     if only:
         for k, (ms, rate, gbs) in out.items():
