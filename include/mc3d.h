@@ -213,6 +213,10 @@ typedef struct {
      * superseded Trajectory_Optimization, :499) -- mu0 / S are (n_cams, n_frames, J, 2 / 3), one mc3d_refine_prepare_* call
      * per camera. */
     int64_t gauss_cam_stride;
+    /* NULL: the cameras are the `cams` above (kernel parameters).  Otherwise device memory holding n_cams x 26 doubles in
+     * the same order, read by every launch: cameras that are learnt together with the trajectory (pose_refinement.py:931-961)
+     * are updated on the device between the phases of a step, with no host round trip. */
+    const double *cams_dev;
 } mc3d_refine_problem;
 
 /* Exchange block at the start of each rank's peer allocation (zero-filled by mc3d_peer_alloc). */

@@ -393,7 +393,9 @@ template <typename T>
 __device__ __forceinline__ void load_cameras_and_tables(const mc3d_refine_problem &pb, RefineTables &tb, T *camf) {
     load_tables(tb, pb);
     for (int i = threadIdx.x; i < pb.n_cams * CAM_STRIDE; i += blockDim.x)
-        camf[i] = (i % CAM_STRIDE) < 26 ? (T)pb.cams[i / CAM_STRIDE][i % CAM_STRIDE] : (T)0;
+        camf[i] = (i % CAM_STRIDE) >= 26 ? (T)0
+                : pb.cams_dev ? (T)__ldcg(pb.cams_dev + (i / CAM_STRIDE) * 26 + i % CAM_STRIDE)      // learnt on the device
+                              : (T)pb.cams[i / CAM_STRIDE][i % CAM_STRIDE];
 }
 
 template <typename T>

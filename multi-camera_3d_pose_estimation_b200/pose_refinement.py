@@ -299,6 +299,7 @@ class Optimized_3d_Pose_Estimation:
         engine.close()                       # sharded runs: unmap the peers' exchange blocks (collective)
         if joint is not None:
             joint.write_back()
+            self.joint_graph_replays = joint.graph_replays        # two optimiser steps per replay (0: eager launches only)
         self.best_decomposed_cam_params = {k: [p.clone().detach() for p in self.decomposed_cam_params[k]]
                                            for k in self.decomposed_cam_params} if improved_once else None
         if joint is not None and improved_once:
@@ -728,8 +729,12 @@ class _JointCameras:
     """Cameras learnt together with the trajectory (``extrinsic_optimization_IDs`` with ``optimize_trajectory=True``,
     pose_refinement.py:931-961): the trajectory steps through the engine's three phases; between its gradient phase and
     its Adam phase every learnt camera's gradient of the likelihood cost is accumulated over the trajectory points
-    (csrc/extrinsic.cu) and one clip_grad_norm_ + Adam step covers everything (:1047-1050).  The cameras are kernel
-    parameters of the trajectory's phases, so their new values come back to the host once per step."""
+    (csrc/extrinsic.cu) and one clip_grad_norm_ + Adam step covers everything (:1047-1050).
+
+    Everything stays on the device: the cameras the trajectory's kernels project with live in device memory
+    (``mc3d_refine_problem.cams_dev``), the joint step's new R, T are copied into them on the stream, the best cameras are
+    kept by a masked copy driven by the ``improved`` flag of the control block, and two consecutive steps are captured once
+    into a CUDA graph and replayed; the host reads the state back once per chunk of iterations."""
 
     def __init__(self, opt, engine, learn_ids, lr, betas):
         torch = _torch()
@@ -763,43 +768,81 @@ class _JointCameras:
             pb.params = self.cam_params.data_ptr() + 8 * 36 * q
             pb.ctrl = self.cam_ctrl.data_ptr() + 8 * 64 * q
             self.problems.append(pb)
+        # the cameras of the trajectory's phases, in device memory from here on
+        n_cams = int(engine.problem.n_cams)
+        rows = np.array([[engine.problem.cams[c][i] for i in range(26)] for c in range(n_cams)], dtype=np.float64)
+        self.cams_dev = torch.tensor(rows, dtype=torch.float64, device=dev)
+        engine.problem.cams_dev = self.cams_dev.data_ptr()
+        self.cam_best = torch.zeros(12 * n, dtype=torch.float64, device=dev)
+        self.any_improved = torch.zeros((), dtype=torch.float64, device=dev)
         self.host = self.cam_params.cpu().numpy().copy()
         self.best = {}
+        self._graph = None
+        self.graph_replays = 0
+        self.use_graph = os.environ.get('MC3D_JOINT_GRAPH', '1') != '0'
 
-    def _sync_engine_cameras(self):
-        """The learnt cameras' current R, T into the kernel parameters of the trajectory's phases."""
-        for q, slot in enumerate(self.slots):
-            if slot is None:                                      # learnt but not part of the likelihood: no gradient reaches it
-                continue
-            row = self.engine.problem.cams[slot]
-            for i in range(9):
-                row[9 + i] = float(self.host[36 * q + i])
-            for i in range(3):
-                row[18 + i] = float(self.host[36 * q + 9 + i])
+    def _one_step(self):
+        """One optimiser step, entirely on the current stream (no host synchronisation: capturable)."""
+        torch = _torch()
+        eng = self.engine
+        st = eng._stream()
+        costgrad = getattr(self.lib, f'mc3d_extrinsic_costgrad_{self.tag}')
+        joint = getattr(self.lib, f'mc3d_extrinsic_joint_step_{self.tag}')
+        eng.phases.phase(eng.problem, 0, eng.step, True, st)
+        eng.phases.phase(eng.problem, 1, eng.step, True, st)
+        for q, pb in enumerate(self.problems):
+            if self.slots[q] is not None:                          # learnt but not part of the likelihood: no gradient reaches it
+                _lib.check(costgrad(ctypes.byref(pb), st))
+        _lib.check(joint(eng.ctrl.data_ptr(), self.cam_ctrl.data_ptr(), self.cam_params.data_ptr(), len(self.ids), eng.step,
+                         self.lr, self.betas[0], self.betas[1], 1e-8, st))
+        eng.phases.phase(eng.problem, 2, eng.step, True, st)      # the trajectory moves with the cameras of this step's gradient
+        for q, slot in enumerate(self.slots):                      # the next step projects with the new R, T
+            if slot is not None:
+                self.cams_dev[slot, 9:21].copy_(self.cam_params[36 * q:36 * q + 12])
+        eng.step += 1
+        # best cameras: kept when the step just taken improved the running mean (the flag of the state entering the next step)
+        improved = eng.ctrl[_lib.CT_STATE + 16 * (eng.step & 1) + 7] != 0
+        rt = self.cam_params.view(-1, 36)[:, :12].reshape(-1)
+        self.cam_best.copy_(torch.where(improved, rt, self.cam_best))
+        self.any_improved.copy_(torch.maximum(self.any_improved, improved.to(torch.float64)))
 
     def steps(self, n):
         torch = _torch()
         eng = self.engine
-        costgrad = getattr(self.lib, f'mc3d_extrinsic_costgrad_{self.tag}')
-        joint = getattr(self.lib, f'mc3d_extrinsic_joint_step_{self.tag}')
-        for _ in range(int(n)):
-            st = eng._stream()
-            self._sync_engine_cameras()
-            eng.phases.phase(eng.problem, 0, eng.step, True, st)
-            eng.phases.phase(eng.problem, 1, eng.step, True, st)
-            for q, pb in enumerate(self.problems):
-                if self.slots[q] is not None:
-                    _lib.check(costgrad(ctypes.byref(pb), st))
-            _lib.check(joint(eng.ctrl.data_ptr(), self.cam_ctrl.data_ptr(), self.cam_params.data_ptr(), len(self.ids), eng.step,
-                             self.lr, self.betas[0], self.betas[1], 1e-8, st))
-            eng.phases.phase(eng.problem, 2, eng.step, True, st)
-            eng.step += 1
-            self.host = self.cam_params.cpu().numpy().copy()       # one small read-back per step
-            state = eng.state()
-            if state['improved']:
-                self.best = {ID: self._tensors(q) for q, ID in enumerate(self.ids)}
-            if state['stopped']:
-                break
+        n = int(n)
+        done = 0
+        if self.use_graph and n >= 8:
+            while done < 2 or (eng.step & 1):                      # eager warm-up, even parity for the captured pair
+                self._one_step()
+                done += 1
+            if self._graph is None:
+                first = eng.step
+                try:
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                        self._one_step()
+                        self._one_step()
+                    self._graph = graph
+                except Exception:                                  # capture unsupported here: stay eager
+                    self.use_graph = False
+                eng.step = first                                   # capturing did not execute anything
+                torch.cuda.synchronize()
+            if self._graph is not None:
+                for _ in range((n - done) // 2):
+                    self._graph.replay()
+                    self.graph_replays += 1
+                    eng.step += 2
+                    done += 2
+        for _ in range(n - done):
+            self._one_step()
+        # one read-back per chunk of iterations (a stopped run makes every further step a no-op on the device)
+        self.host = self.cam_params.cpu().numpy().copy()
+        if float(self.any_improved.item()) != 0.0:
+            best = self.cam_best.cpu().numpy()
+            dt = self.opt.torch_dtype
+            self.best = {ID: (torch.tensor(best[12 * q:12 * q + 9].reshape(3, 3), dtype=dt),
+                              torch.tensor(best[12 * q + 9:12 * q + 12].reshape(3, 1), dtype=dt)) for q, ID in enumerate(self.ids)}
 
     def _tensors(self, q):
         torch = _torch()
@@ -808,6 +851,7 @@ class _JointCameras:
                 torch.tensor(self.host[36 * q + 9:36 * q + 12].reshape(3, 1), dtype=dt))
 
     def write_back(self):
+        self._graph = None
         for q, ID in enumerate(self.ids):
             self.opt.decomposed_cam_params[ID][1], self.opt.decomposed_cam_params[ID][2] = self._tensors(q)
 

@@ -109,11 +109,14 @@ def test_extrinsic_gradient_matches_oracle_on_a_larger_sample_set():
     assert np.allclose(m, gclip * (1 - 0.9 ** 2), rtol=1e-10, atol=1e-18)
 
 
+@pytest.mark.parametrize('graph', ['1', '0'])
 @pytest.mark.parametrize('key', ['f64_joint', 'f32_joint'])
-def test_cameras_and_trajectory_learnt_together_match_reference_runs(key):
+def test_cameras_and_trajectory_learnt_together_match_reference_runs(key, graph, monkeypatch):
     """extrinsic_optimization_IDs=[2] with optimize_trajectory=True (pose_refinement.py:931-961): the trajectory's three
-    phases plus the camera gradient / joint clip / camera Adam kernels of csrc/extrinsic.cu."""
+    phases plus the camera gradient / joint clip / camera Adam kernels of csrc/extrinsic.cu, the learnt cameras resident in
+    device memory (mc3d_refine_problem.cams_dev), two steps per CUDA-graph replay (graph = '1') or eager launches."""
     import torch
+    monkeypatch.setenv('MC3D_JOINT_GRAPH', graph)
     import mc3d_b200.pose_refinement as pr
     import mc3d_b200.synthetic as syn
     g = np.load(GOLD)
@@ -126,6 +129,7 @@ def test_cameras_and_trajectory_learnt_together_match_reference_runs(key):
                                           body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
     opt.sgd_optimize(extrinsic_optimization_IDs=[2], optimize_trajectory=True, lr=1e-3, lambda_smooth=1e-3, lambda_body_length=1.0,
                      max_iter=14, print_frequency=np.inf, time_interval=[0, 12])
+    assert (opt.joint_graph_replays > 0) == (graph == '1')           # 15 steps: 2 eager, 6 replays of 2, 1 eager
     rtol = 1e-9 if dt == torch.float64 else 1e-4
     for name, vals in opt.all_costs_total.items():
         ref = g[f'{key}_hist_{name}']
