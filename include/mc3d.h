@@ -260,16 +260,23 @@ int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step
  * Two-phase step (needs `gc` and the exchange block `xchg`; any world size): the gradient does not wait for the
  * global sums.  It is linear in three scalars that depend on them,
  *     g = alpha g1 + sigma gs + beta (G2 - mu G3),   alpha = 1/N_lik, sigma = 2 lambda_s/N_s, beta = -2 lambda_b mu/(a.a),
- * so ONE pass computes the costs, the four component vectors (g1 likelihood, gs smoothness, G2' = G2 - mu_prev G3 and
- * G3 bone length; mu_prev = last step's mu keeps the cancelling pair small) and their 10 mutual dot products.  After
- * ONE reduction of 17 sums every thread knows alpha, sigma, beta, mu and |g|^2 (a quadratic form in them), and the
- * second pass combines the components, clips and applies Adam.  Per step: two passes, one cross-rank exchange of 17
- * doubles and the halo stores (the three-phase step needs three passes and two exchanges).
- * ctrl[32 + 16p + 8] carries mu_prev.  Small shards run all iterations inside one persistent cooperative kernel
- * (two grid barriers per step), big ones replay a CUDA graph of the two kernels.
- * Without `gc`, or for shards beyond ~150 000 frames: phases 0,1,2 replayed from a CUDA graph of the three kernels
- * (with the in-kernel exchange between them when world > 1).  MC3D_REFINE_TWO_PHASE / MC3D_REFINE_FUSED = 0 / 1 in the
- * environment force a variant (tests, A/B timing).  Every rank must call it with the same arguments. */
+ * so ONE pass computes the costs, the component vectors (g1 likelihood, gs smoothness, G2' = G2 - mu_prev G3 and
+ * G3 bone length; mu_prev = last step's mu keeps the cancelling pair small) and their mutual dot products.  After
+ * ONE reduction every thread knows alpha, sigma, beta, mu and |g|^2 (a quadratic form in them), and the Adam pass
+ * combines the components, clips and applies Adam.  Per step: one cross-rank exchange of the sums and the halo stores
+ * (the three-phase step needs three passes and two exchanges).
+ * ctrl[32 + 16p + 8] carries mu_prev, [.. + 9], [.. + 10] the counts N_lik, N_s the step found.
+ * All iterations run inside one persistent cooperative kernel, which stores THREE components: gA = alpha g1 + sigma gs is
+ * folded with the previous step's counts (they change only when a value turns non-finite; the step's totals are checked
+ * and pass 1 is repeated once if they differ), 13 sums.  Float state: the FUSED SWEEP -- Adam of step s and pass 1 of step
+ * s + 1 in one sweep over block-owned item ranges (cp.async-staged Adam operands in flight during pass 1, range edges
+ * announced through blk_seq), ONE grid-wide meeting per step, any shard size below 2^30 joint-frames.  Double state:
+ * the two passes one after the other (two grid barriers per step) up to ~150 000 frames x 17 joints, beyond that a CUDA
+ * graph of the two kernels / the three phases.  MC3D_REFINE_FUSED=0 selects the graph of two kernels (four components, 17 sums).
+ * Without `gc`: phases 0,1,2 replayed from a CUDA graph of the three kernels (with the in-kernel exchange between them
+ * when world > 1).  MC3D_REFINE_TWO_PHASE / MC3D_REFINE_FUSED / MC3D_REFINE_SWEEP = 0 / 1 in the environment force a
+ * variant (tests, A/B timing).  Every rank must call it with the same arguments.  The best-trajectory snapshot is complete
+ * when the call returns (inside the persistent kernel it is deferred while consecutive steps improve). */
 /* Text describing what mc3d_refine_run_* launches for this problem on the current device (static string). */
 const char *mc3d_refine_plan(const mc3d_refine_problem *pb);
 int mc3d_refine_run_f32(const mc3d_refine_problem *pb, int64_t first_step, int64_t n_iters, void *stream);
