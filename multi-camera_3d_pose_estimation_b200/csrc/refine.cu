@@ -572,7 +572,7 @@ struct StepScalars {
 template <typename T>
 __device__ __forceinline__ StepScalars<T> step_scalars(const mc3d_refine_problem &pb, int end_of_iteration, double gnorm2,
                                                        const double *st, const RefineDerived &dv, double *bias, bool *best_pending,
-                                                       bool last_of_launch) {
+                                                       bool last_of_launch, bool bias_ready = false) {
     StepScalars<T> ss;
     const double gnorm = sqrt(gnorm2);
     const double clip = fmin(1.0, 1.0 / (gnorm + 1e-6));           // torch clip_grad_norm_(max_norm=1.0)
@@ -598,12 +598,14 @@ __device__ __forceinline__ StepScalars<T> step_scalars(const mc3d_refine_problem
         ss.wr_old = !ss.improved && *best_pending;
         *best_pending = ss.improved && !ss.wr_new;
     }
-    __syncthreads();                                               // bias[] may still be read from the previous step
-    if (threadIdx.x == 0) {                                        // two double pow() per block, not per thread
-        bias[0] = 1.0 - pow(pb.beta1, ss.step);
-        bias[1] = 1.0 - pow(pb.beta2, ss.step);
+    if (!bias_ready) {                                             // (the fused sweep evaluates them ahead, off the step's critical path)
+        __syncthreads();                                           // bias[] may still be read from the previous step
+        if (threadIdx.x == 0) {                                    // two double pow() per block, not per thread
+            bias[0] = 1.0 - pow(pb.beta1, ss.step);
+            bias[1] = 1.0 - pow(pb.beta2, ss.step);
+        }
+        __syncthreads();
     }
-    __syncthreads();
     ss.step_size = (T)(pb.lr / bias[0]);
     ss.inv_bc2_sqrt = (T)(1.0 / sqrt(bias[1]));
     ss.w1 = (T)(1.0 - pb.beta1); ss.b2 = (T)pb.beta2; ss.w2 = (T)(1.0 - pb.beta2); ss.eps = (T)pb.eps; ss.clipT = (T)clip;
@@ -1107,7 +1109,7 @@ __device__ __forceinline__ void publish2_ll(const mc3d_refine_problem &pb, int p
 }
 
 __device__ __forceinline__ void gather2_ll(const mc3d_refine_problem &pb, int parity, long long seq, double *tot, unsigned int *halves,
-                                           bool retry) {
+                                           bool retry, bool acquire = true) {
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
     const unsigned int want = (unsigned int)seq;
     const unsigned long long limit = pb.spin_timeout_ns > 0 ? (unsigned long long)pb.spin_timeout_ns : 10000000000ULL;
@@ -1124,8 +1126,9 @@ __device__ __forceinline__ void gather2_ll(const mc3d_refine_problem &pb, int pa
     }
     __syncthreads();
     // acquire what the other blocks of this GPU wrote before their tickets (device scope: the peers' halo stores are acquired
-    // where their own flags are waited for)
-    if (threadIdx.x == 0) fence_gpu();
+    // where their own flags are waited for).  The fused sweep passes acquire = false: a block reads only what it wrote itself
+    // (its range) and its neighbours' edges, which have their own flags and fences.
+    if (acquire && threadIdx.x == 0) fence_gpu();
     if (threadIdx.x < NS2) {
         double s = 0.0;
         for (int r = 0; r < pb.world; ++r) {
@@ -1319,8 +1322,11 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
         double gnorm2;
         const GradMix<T> mix = mix3_of<T>(pb, tot, dv, (double)(T)st[8], gnorm2);   // mu_prev as pass 1 used it
         const bool last_iter = it + 1 == n_iters;
-        const StepScalars<T> ss = step_scalars<T>(pb, 1, gnorm2, st, dv, bias, &best_pending, last_iter);
+        const StepScalars<T> ss = step_scalars<T>(pb, 1, gnorm2, st, dv, bias, &best_pending, last_iter, it > 0);
         if (last_iter || ss.stop) {                                // Adam alone (the launch ends here); halos leave first (block 0)
+            __syncthreads();
+            if (tid == 0) fence_gpu();                             // this pass reads what other blocks wrote (grid-stride order)
+            __syncthreads();
             step_loop<T>(pb, parity, 1, gnorm2, st, dv, true, bias, true, mix, true, seq, nullptr, true, counts, &ss);
             grid_barrier(pb, 2, seq);
             return;
@@ -1413,12 +1419,12 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             if (right_halo) { fence_sys(); st_relaxed_sys(&xchg_of(pb, pb.rank + 1)->halo_seq[0], seq); }
             fence_gpu();
             st_relaxed_sys(&mine->blk_seq[b], seq);                // my edges hold x of step `seq`
-            bool remote = false;
-            if (b > 0) xchg_wait(pb, &mine->blk_seq[b - 1], seq);
-            else if (pb.rank > 0) { xchg_wait(pb, &mine->halo_seq[0], seq); remote = true; }
-            if (b < G - 1) xchg_wait(pb, &mine->blk_seq[b + 1], seq);
-            else if (pb.rank < pb.world - 1) { xchg_wait(pb, &mine->halo_seq[1], seq); remote = true; }
-            if (remote) fence_sys(); else fence_gpu();             // a system-scope acquire only where a peer stored
+            // the left neighbour's edge (thread 32 waits for the right one meanwhile); a system-scope acquire only where a peer stored
+            if (b > 0) { xchg_wait(pb, &mine->blk_seq[b - 1], seq); fence_gpu(); }
+            else if (pb.rank > 0) { xchg_wait(pb, &mine->halo_seq[0], seq); fence_sys(); }
+        } else if (tid == 32) {
+            if (b < G - 1) { xchg_wait(pb, &mine->blk_seq[b + 1], seq); fence_gpu(); }
+            else if (pb.rank < pb.world - 1) { xchg_wait(pb, &mine->halo_seq[1], seq); fence_sys(); }
         }
         finish(0);
         __syncthreads();
@@ -1461,10 +1467,18 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             block_reduce_add<NS2>(acc, red, mine->acc2[parity ^ 1]);
         }
         if (take_ticket(mine, 0)) publish2_ll(pb, parity ^ 1, seq + 1, false);
-        gather2_ll(pb, parity ^ 1, seq + 1, tot, halves, false);    // the step's one grid-wide meeting (+ cross-rank sums)
+        if (tid == NT - 1) {                                        // Adam's bias corrections of the next step, while the words travel
+            bias[0] = 1.0 - pow(pb.beta1, ss.step + 1.0);
+            bias[1] = 1.0 - pow(pb.beta2, ss.step + 1.0);
+        }
+        gather2_ll(pb, parity ^ 1, seq + 1, tot, halves, false, false);   // the step's one grid-wide meeting (+ cross-rank sums)
         const bool same = tot[1] == counts[0] && (!do_smooth || tot[3] == counts[1]);
         counts[0] = tot[1]; counts[1] = tot[3];
-        if (!same) pass1_checked<T>(pb, tb, camf, parity ^ 1, seq + 1, (T)mix.mu, counts, 1, red, tot, halves);
+        if (!same) {
+            if (tid == 0) fence_gpu();                             // the repeated pass reads x in grid-stride order
+            __syncthreads();
+            pass1_checked<T>(pb, tb, camf, parity ^ 1, seq + 1, (T)mix.mu, counts, 1, red, tot, halves);
+        }
         st[0] = ss.step; st[1] = ss.run_sum; st[2] = ss.run_cnt; st[3] = ss.best; st[4] = ss.no_imp; st[5] = 0.0;
         st[6] = ss.iters; st[7] = ss.improved ? 1.0 : 0.0; st[8] = mix.mu; st[9] = counts[0]; st[10] = counts[1];
         parity ^= 1;
