@@ -213,6 +213,31 @@ def golden_refine(ref_refine, ref_utils, syn, out):
     np.savez(os.path.join(out, 'refine_T48.npz'), **store)
 
 
+def golden_refine_large(ref_refine, ref_utils, syn, out):
+    """The unmodified reference at 4 000 frames (68 000 joint-frames: hundreds of thread blocks, each with neighbours, in the
+    GPU kernels' block-owned ranges).  Inputs come from the seeded generator, so only results are stored: the cost histories
+    and every 97th frame of the final / best trajectories."""
+    import torch
+    torch.manual_seed(0)
+    n = 4000
+    g, init, cams, _ = syn.refinement_inputs(n, n_cams=2, seed=77)
+    lengths = dict(syn.EXAMPLE_BODY_LENGTHS)
+    kw = dict(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, patience=100, max_iter=11, time_interval=[0, n])
+    store = dict(versions=versions(), n_frames=np.array(n), seed=np.array(77), stride=np.array(97))
+    for tag, dt in [('f32', torch.float32), ('f64', torch.float64)]:
+        cam_params = {i: [np.asarray(a).copy() for a in cams[i]] for i in cams}
+        with contextlib.redirect_stdout(io.StringIO()):
+            opt = ref_refine.Optimized_3d_Pose_Estimation(g.copy(), init.copy(), decomposed_cam_params_initial=cam_params,
+                                                          body_lengths=lengths, torch_dtype=dt)
+            opt.sgd_optimize(**ref_utils.prepare_kwargs(opt.sgd_optimize, kw))
+        for cname, hist in opt.all_costs_total.items():
+            store[f'{tag}_{cname}'] = np.array([float(h) for h in hist], dtype=np.float64)
+        store[f'{tag}_final'] = opt.trajectory.detach().numpy()[::97]
+        store[f'{tag}_best'] = opt.best_trajectory.numpy()[::97]
+        store[f'{tag}_final_abs_sum'] = np.array(np.abs(opt.trajectory.detach().numpy().astype(np.float64)).sum())
+    np.savez_compressed(os.path.join(out, 'refine_T4000.npz'), **store)
+
+
 def golden_interp(ref_refine, syn, out):
     rng = np.random.default_rng(15)
     X = syn.smooth_trajectory(60, 17, rng, centre=(0, 0, 3000.0))
@@ -444,7 +469,7 @@ def main():
     syn = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(syn)
     ref_utils, ref_refine, ref_mm, ref_pe = import_reference(args.reference)
-    todo = args.only or ['dlt', 'pose3d', 'config1', 'moments', 'argmax', 'refine', 'refine_percam', 'interp', 'extrinsic', 'epr', 'surface']
+    todo = args.only or ['dlt', 'pose3d', 'config1', 'moments', 'argmax', 'refine', 'refine_large', 'refine_percam', 'interp', 'extrinsic', 'epr', 'surface']
     if 'dlt' in todo:
         golden_dlt(ref_utils, syn, HERE)
     if 'pose3d' in todo:
@@ -457,6 +482,8 @@ def main():
         golden_argmax(syn, HERE)
     if 'refine' in todo:
         golden_refine(ref_refine, ref_utils, syn, HERE)
+    if 'refine_large' in todo:
+        golden_refine_large(ref_refine, ref_utils, syn, HERE)
     if 'refine_percam' in todo:
         golden_refine_percam(ref_refine, ref_utils, syn, HERE)
     if 'interp' in todo:

@@ -43,6 +43,22 @@ def test_optimisation_history_matches_reference(syn, run, tag):
     assert np.abs(out['final'] - g[f'{key}_final']).max() < atol
 
 
+def test_optimisation_history_matches_reference_at_4000_frames(syn):
+    """tests/golden/refine_T4000.npz (the unmodified reference on 4 000 frames; inputs from the seeded generator)."""
+    g = load_golden('refine_T4000.npz')
+    n, stride = int(g['n_frames']), int(g['stride'])
+    gs, init, cams, _ = syn.refinement_inputs(n, n_cams=2, seed=int(g['seed']))
+    out = R.sgd_optimize(gs, init, list(cams.values()), syn.EXAMPLE_BODY_LENGTHS, dtype=np.float64, lr=0.01, lambda_smooth=1e-6,
+                         lambda_body_length=1, patience=100, max_iter=11, time_interval=[0, n])
+    for name, hist in out['history'].items():
+        ref = g[f'f64_{name}']
+        assert len(hist) == len(ref) == 24             # 12 iterations, each followed by the running mean (Q5)
+        assert np.max(np.abs(np.array(hist) - ref) / np.abs(ref)) < 1e-12
+    assert np.abs(out['final'][::stride] - g['f64_final']).max() < 1e-9
+    assert np.abs(out['best'][::stride] - g['f64_best']).max() < 1e-9
+    assert abs(np.abs(out['final']).sum() - float(g['f64_final_abs_sum'])) / float(g['f64_final_abs_sum']) < 1e-12
+
+
 def test_quirks_are_reproduced(syn):
     g = load_golden('refine_T48.npz')
     # Q3: the default time_interval [0, -1] drops the last frame; Q4: max_iter + 1 iterations; Q5: interleaved means

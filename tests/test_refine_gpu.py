@@ -50,6 +50,34 @@ def test_project_points_torch_matches_reference(pr):
         assert np.abs(sub.numpy() - g[f'proj_f64_cam{i}'][[3, 4, 9]]).max() < 1e-9
 
 
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
+def test_sgd_optimize_matches_reference_at_4000_frames(pr, syn, tag):
+    """tests/golden/refine_T4000.npz: the unmodified reference on 4 000 frames x 17 joints (inputs from the seeded generator,
+    only results stored).  68 000 joint-frames put hundreds of thread blocks -- each with neighbours on both sides -- into the
+    persistent kernel's block-owned ranges (float state: the fused sweep)."""
+    import torch
+    import mc3d_b200.utils as u
+    g = load_golden('refine_T4000.npz')
+    n, stride = int(g['n_frames']), int(g['stride'])
+    gs, init, cams, _ = syn.refinement_inputs(n, n_cams=2, seed=int(g['seed']))
+    dt = torch.float64 if tag == 'f64' else torch.float32
+    opt = pr.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(), decomposed_cam_params_initial={i: [np.asarray(a).copy() for a in cams[i]] for i in cams},
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+    kw = dict(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, patience=100, max_iter=11, time_interval=[0, n])
+    opt.sgd_optimize(**u.prepare_kwargs(opt.sgd_optimize, kw))
+    hist = _history(opt)
+    rtol = 1e-9 if tag == 'f64' else LOSS_RTOL
+    for name, h in hist.items():
+        ref = g[f'{tag}_{name}']
+        assert len(h) == len(ref) == 24, (name, len(h), len(ref))      # 12 iterations, each followed by the running mean (Q5)
+        assert np.max(np.abs(h - ref) / np.abs(ref)) < rtol, (name, np.max(np.abs(h - ref) / np.abs(ref)))
+    atol = 1e-6 if tag == 'f64' else 5e-2
+    assert np.abs(opt.trajectory.numpy()[::stride] - g[f'{tag}_final']).max() < atol
+    assert np.abs(np.array(opt.best_trajectory)[::stride] - g[f'{tag}_best']).max() < atol
+    total = np.abs(opt.trajectory.numpy().astype(np.float64)).sum()
+    assert abs(total - float(g[f'{tag}_final_abs_sum'])) / total < (1e-12 if tag == 'f64' else 1e-6)
+
+
 @pytest.mark.parametrize('run', sorted(RUNS))
 @pytest.mark.parametrize('tag', ['f64', 'f32'])
 def test_sgd_optimize_matches_reference_runs(pr, syn, run, tag, capsys):
