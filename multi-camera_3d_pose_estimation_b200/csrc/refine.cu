@@ -1692,9 +1692,10 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
     if (fused_env == 1 || (fused_env != 0 && small)) {
         const char *envb = getenv("MC3D_REFINE_BLOCKS");            // 2 / 3 force a register build (measurement)
         int sweep = sweep_wanted(pb, sizeof(T)) ? 1 : 0;
-        // the fused sweep is fastest spill-free (2 CTAs x 128 registers: 94 vs 109 us per step at 100 000 frames); the two-pass
-        // form of large shards with 3 CTAs x 80 registers
-        const bool big = envb ? atoi(envb) >= 3 : (!sweep && n_items > 425000);
+        // the fused sweep is fastest spill-free (2 CTAs x 128 registers: 94 vs 109 us per step at 100 000 frames), and so is the
+        // double-state kernel (165 vs 229 us: at 80 registers it spills 1.1 KB); only the float two-pass form of large shards
+        // gains from 3 CTAs x 80 registers
+        const bool big = envb ? atoi(envb) >= 3 : (!sweep && sizeof(T) == 4 && n_items > 425000);
         auto kern = big ? refine_fused2_kernel<T, 3> : refine_fused2_kernel<T, 2>;
         // Fused sweep (Adam of step s beside pass 1 of step s + 1, one grid-wide meeting per step): every block needs a range
         // that holds its two 2-frame edges and some interior; MC3D_REFINE_SWEEP=0 forbids it (measurement).
