@@ -1675,9 +1675,10 @@ static bool sweep_wanted(const mc3d_refine_problem *pb, size_t elem_size) {
 static bool shard_is_small(const mc3d_refine_problem *pb, size_t elem_size) {
     const long long world = pb->world > 1 ? pb->world : 1;
     const long long frames = pb->world > 1 ? (pb->total_frames + world - 1) / world : pb->n_frames;
-    // the fused sweep walks block-owned ranges of any length (measured to 200 000 frames); the two-pass persistent kernel was
-    // measured up to ~150 000 frames x 17 joints
-    if (sweep_wanted(pb, elem_size)) return frames * pb->n_joints < (1LL << 30);
+    // the fused sweep walks block-owned ranges of any length (measured to 200 000 frames); the double-state two-pass persistent
+    // kernel beats the graphs of kernels at every size measured (400 000 frames: 597 vs 803 us per step); the float two-pass
+    // form (MC3D_REFINE_SWEEP=0, per-camera Gaussians) was measured up to ~150 000 frames x 17 joints
+    if (sweep_wanted(pb, elem_size) || elem_size == 8) return frames * pb->n_joints < (1LL << 30);
     return frames * pb->n_joints <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
 }
 
@@ -1820,7 +1821,7 @@ int refine_run(const mc3d_refine_problem *pb, long long first_step, long long n_
 // What refine_run would launch for this problem (same decisions, no launch).
 static const char *refine_plan(const mc3d_refine_problem *pb) {
     if (!pb) return "invalid";
-    const bool small = shard_is_small(pb, 8);                      // the dtype is not known here: the stricter answer
+    const bool small = shard_is_small(pb, 4) && shard_is_small(pb, 8);      // the dtype is not known here: the stricter answer
     const char *e2 = getenv("MC3D_REFINE_TWO_PHASE"), *ef = getenv("MC3D_REFINE_FUSED");
     const int two_env = e2 ? atoi(e2) : -1, fused_env = ef ? atoi(ef) : -1;
     const bool fused = fused_env == 1 || (fused_env != 0 && small);
