@@ -1710,7 +1710,8 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
         long long grid = (n_items + RF_THREADS - 1) / RF_THREADS;
         if (grid > (long long)sm_count() * per_sm) grid = (long long)sm_count() * per_sm;      // all blocks co-resident
         if (grid < 1) grid = 1;
-        if (grid > MC3D_XCHG_BLOCK_FLAGS || n_items / grid < 4LL * pb->n_joints + 32 || n_items >= (1LL << 30)) sweep = 0;
+        // (the sweep indexes elements with 32-bit integers: 3 n_items must stay below 2^31)
+        if (grid > MC3D_XCHG_BLOCK_FLAGS || n_items / grid < 4LL * pb->n_joints + 32 || n_items >= 700000000LL) sweep = 0;
         int parity = (int)(first_step & 1);
         long long iters = n_iters;
         void *args[] = {(void *)&prob, (void *)&parity, (void *)&iters, (void *)&sweep};
