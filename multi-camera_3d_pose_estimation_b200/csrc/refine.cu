@@ -1244,10 +1244,12 @@ __device__ __forceinline__ void pass1_checked(const mc3d_refine_problem &pb, con
 // are updated first and announced with a per-block flag (blk_seq, the Adam step count): the neighbouring blocks read them,
 // the rank's first / last block also stores them into the neighbour ranks' halo frames.  In-place: every element of x, m, v
 // and the components is read and written once per step, as in the two-pass form.
-constexpr int SWEEP_ITEMS = 2;       // items of pass 1 per thread and trip
-// staged scalars per thread: 3 pairs x (gA, G2', G3, m, v, x) of the next Adam chunk + two buffers of (mu0, Sigma^-1) for the
-// items of the next / the current trip
-constexpr int SWEEP_STAGE = 36 + 2 * 5 * SWEEP_ITEMS + 4 * 3 * SWEEP_ITEMS;   // + four tile slots of updated x (pass 1 reads x there)
+// Everything is staged in 8-byte units -- two floats or one double: three units of (gA, G2', G3, m, v, x) of the next Adam
+// chunk per thread, and per trip as many pass-1 items per thread as a unit holds elements (2 in float, 1 in double).
+template <typename T> constexpr int sweep_items() { return (int)(8 / sizeof(T)); }
+// staged scalars per thread: the 18 units + two buffers of (mu0, Sigma^-1) for the items of the next / the current trip + four
+// tile slots of updated x (pass 1 reads x there): 320 bytes per thread in either type
+template <typename T> constexpr int sweep_stage() { return 18 * sweep_items<T>() + 2 * 5 * sweep_items<T>() + 4 * 3 * sweep_items<T>(); }
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async_bytes(void *smem_dst, const void *gmem_src) {
@@ -1260,7 +1262,8 @@ template <typename T>
 __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, int parity,
                                                 long long n_iters, double *red, double *tot, double *bias, unsigned int *halves,
                                                 T *stage) {
-    struct alignas(2 * sizeof(T)) Vec2 { T a, b; };
+    constexpr int SWEEP_ITEMS = sweep_items<T>();
+    struct alignas(8) Unit { T e[SWEEP_ITEMS]; };
     __shared__ T adamc[8];                                         // Adam's constants of the step in the state type
     double *ctrl = pb.ctrl;
     mc3d_refine_xchg *mine = xchg_of(pb, pb.rank);
@@ -1303,14 +1306,14 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
         left_halo = reinterpret_cast<T *>(reinterpret_cast<char *>(pb.xchg[pb.rank - 1]) + MC3D_XCHG_X_OFFSET) + (pb.n_frames_left + 2) * (long long)JS;
     if (pb.rank < pb.world - 1 && b == G - 1)
         right_halo = reinterpret_cast<T *>(reinterpret_cast<char *>(pb.xchg[pb.rank + 1]) + MC3D_XCHG_X_OFFSET);
-    // elements: left edge [eL0, A0), interior pairs [A0, A1) (A0 even, A1 - A0 even), right edge and an odd leftover [A1, eR1)
+    // elements: left edge [eL0, A0), interior units [A0, A1) (A0 and A1 - A0 whole units), right edge and an odd leftover [A1, eR1)
     const int eL0 = r_lo * 3, A0 = eL0 + 3 * E, eR1 = r_hi * 3;
-    const int A1 = A0 + ((eR1 - 3 * E - A0) & ~1);
+    const int A1 = A0 + ((eR1 - 3 * E - A0) / SWEEP_ITEMS) * SWEEP_ITEMS;
     const int n_edge = (A0 - eL0) + (eR1 - A1);
     constexpr int CI = SWEEP_ITEMS * RF_THREADS, CE = 3 * CI;       // items / elements per trip
     const int n_c = (r_hi - r_lo + CI - 1) / CI, n_a = (A1 - A0 + CE - 1) / CE;
-    Vec2 *stage2 = reinterpret_cast<Vec2 *>(stage);                 // [18][NT] pairs
-    T *stage_ms = stage + 36 * NT;                                  // [2][SWEEP_ITEMS][5][NT]
+    Unit *stage2 = reinterpret_cast<Unit *>(stage);                 // [18][NT] units
+    T *stage_ms = stage + 18 * SWEEP_ITEMS * NT;                    // [2][SWEEP_ITEMS][5][NT]
     // x as Adam left it, chunk k in tile slot k % 3 (and, when k % 3 == 0, also in slot 3, so that chunks k - 1 and k always lie
     // side by side somewhere): everything pass 1 reads of x -- the item itself, two frames either side, its frame's bones -- lies
     // in Adam chunks i - 1 and i, so trip i reads shared memory through ONE base pointer instead of L2, where the item's own
@@ -1350,17 +1353,17 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             xi = xi - adamc[6] * div_c(mi, denom);                 // param.addcdiv_(exp_avg, denom, value=-step_size)
         };
         auto issue = [&](int k) {                                   // Adam chunk k + the Gaussians of pass-1 chunk k
-            const int p0 = (A0 >> 1) + k * (CE / 2) + tid;
+            const int p0 = A0 / SWEEP_ITEMS + k * (CE / SWEEP_ITEMS) + tid;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const int pi = p0 + r * NT;
-                if (2 * pi < A1) {
-                    cp_async_bytes<sizeof(Vec2)>(stage2 + (0 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(c1) + pi);
-                    cp_async_bytes<sizeof(Vec2)>(stage2 + (1 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(c2) + pi);
-                    cp_async_bytes<sizeof(Vec2)>(stage2 + (2 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(c3) + pi);
-                    cp_async_bytes<sizeof(Vec2)>(stage2 + (3 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(m) + pi);
-                    cp_async_bytes<sizeof(Vec2)>(stage2 + (4 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(v) + pi);
-                    cp_async_bytes<sizeof(Vec2)>(stage2 + (5 * 3 + r) * NT + tid, reinterpret_cast<const Vec2 *>(x) + pi);
+                if (SWEEP_ITEMS * pi < A1) {
+                    cp_async_bytes<8>(stage2 + (0 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(c1) + pi);
+                    cp_async_bytes<8>(stage2 + (1 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(c2) + pi);
+                    cp_async_bytes<8>(stage2 + (2 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(c3) + pi);
+                    cp_async_bytes<8>(stage2 + (3 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(m) + pi);
+                    cp_async_bytes<8>(stage2 + (4 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(v) + pi);
+                    cp_async_bytes<8>(stage2 + (5 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(x) + pi);
                 }
             }
             if (k < n_c) {
@@ -1381,20 +1384,20 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
         };
         auto finish = [&](int k) {
             cp_async_wait_all();
-            const int p0 = (A0 >> 1) + k * (CE / 2) + tid;
+            const int p0 = A0 / SWEEP_ITEMS + k * (CE / SWEEP_ITEMS) + tid;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const int pi = p0 + r * NT;
-                if (2 * pi < A1) {
-                    const Vec2 ga = stage2[(0 * 3 + r) * NT + tid], g2 = stage2[(1 * 3 + r) * NT + tid], g3 = stage2[(2 * 3 + r) * NT + tid];
-                    Vec2 mv = stage2[(3 * 3 + r) * NT + tid], vv = stage2[(4 * 3 + r) * NT + tid], xv = stage2[(5 * 3 + r) * NT + tid];
-                    if (wr_old) reinterpret_cast<Vec2 *>(bestx)[pi] = xv;
-                    adam_el(2 * pi, ga.a, g2.a, g3.a, mv.a, vv.a, xv.a);
-                    adam_el(2 * pi + 1, ga.b, g2.b, g3.b, mv.b, vv.b, xv.b);
-                    reinterpret_cast<Vec2 *>(m)[pi] = mv; reinterpret_cast<Vec2 *>(v)[pi] = vv; reinterpret_cast<Vec2 *>(x)[pi] = xv;
-                    reinterpret_cast<Vec2 *>(xtile + (k % 3) * CE)[r * NT + tid] = xv;
-                    if (k % 3 == 0) reinterpret_cast<Vec2 *>(xtile + 3 * CE)[r * NT + tid] = xv;
-                    if (wr_new) reinterpret_cast<Vec2 *>(bestx)[pi] = xv;
+                if (SWEEP_ITEMS * pi < A1) {
+                    const Unit ga = stage2[(0 * 3 + r) * NT + tid], g2 = stage2[(1 * 3 + r) * NT + tid], g3 = stage2[(2 * 3 + r) * NT + tid];
+                    Unit mv = stage2[(3 * 3 + r) * NT + tid], vv = stage2[(4 * 3 + r) * NT + tid], xv = stage2[(5 * 3 + r) * NT + tid];
+                    if (wr_old) reinterpret_cast<Unit *>(bestx)[pi] = xv;
+#pragma unroll
+                    for (int q = 0; q < SWEEP_ITEMS; ++q) adam_el(SWEEP_ITEMS * pi + q, ga.e[q], g2.e[q], g3.e[q], mv.e[q], vv.e[q], xv.e[q]);
+                    reinterpret_cast<Unit *>(m)[pi] = mv; reinterpret_cast<Unit *>(v)[pi] = vv; reinterpret_cast<Unit *>(x)[pi] = xv;
+                    reinterpret_cast<Unit *>(xtile + (k % 3) * CE)[r * NT + tid] = xv;
+                    if (k % 3 == 0) reinterpret_cast<Unit *>(xtile + 3 * CE)[r * NT + tid] = xv;
+                    if (wr_new) reinterpret_cast<Unit *>(bestx)[pi] = xv;
                 }
             }
         };
@@ -1667,10 +1670,11 @@ int refine_phase(const mc3d_refine_problem *pb, int phase, long long step_index,
 // Every rank must pick the same step variant (they meet inside the kernels), so the size that decides is the LARGEST
 // shard of the run (frame_shard sizes differ by at most one frame), not this rank's own.
 static bool sweep_wanted(const mc3d_refine_problem *pb, size_t elem_size) {
-    // float state only: in double the step is bound by the FP64 pipe and the sweep's bookkeeping costs more than the
-    // overlap returns (measured 261 vs 247 us per step at 100 000 frames, 42 vs 34 at 12 500)
-    const char *envs = getenv("MC3D_REFINE_SWEEP");                 // 0 forbids the fused sweep (measurement)
-    return !(envs && atoi(envs) == 0) && pb->gauss_cam_stride == 0 && elem_size == 4;
+    // float state only: in double the step is bound by the FP64 pipe and its 128 registers already spill, so the sweep's
+    // bookkeeping costs more than the overlap returns (measured with one item per thread and trip, 2 CTAs per SM: 223 vs 165 us
+    // per step at 100 000 frames, 39 vs 33 at 12 500; parity suite green in both forms)
+    const char *envs = getenv("MC3D_REFINE_SWEEP");                 // 0 forbids the fused sweep, 2 allows it for double state (measurement)
+    return !(envs && atoi(envs) == 0) && pb->gauss_cam_stride == 0 && (elem_size == 4 || (envs && atoi(envs) == 2));
 }
 static bool shard_is_small(const mc3d_refine_problem *pb, size_t elem_size) {
     const long long world = pb->world > 1 ? pb->world : 1;
@@ -1700,7 +1704,7 @@ int refine_run_two_phase(const mc3d_refine_problem *pb, long long first_step, lo
         auto kern = big ? refine_fused2_kernel<T, 3> : refine_fused2_kernel<T, 2>;
         // Fused sweep (Adam of step s beside pass 1 of step s + 1, one grid-wide meeting per step): every block needs a range
         // that holds its two 2-frame edges and some interior; MC3D_REFINE_SWEEP=0 forbids it (measurement).
-        size_t dyn = (size_t)RF_THREADS * SWEEP_STAGE * sizeof(T);
+        size_t dyn = (size_t)RF_THREADS * sweep_stage<T>() * sizeof(T);
         if (!sweep) dyn = 0;
         if (dyn > 0) { const int as = func_max_smem_once((const void *)kern, 200 * 1024); if (as != MC3D_OK) return as; }
         int per_sm = 0;
