@@ -50,6 +50,26 @@ def test_project_points_torch_matches_reference(pr):
         assert np.abs(sub.numpy() - g[f'proj_f64_cam{i}'][[3, 4, 9]]).max() < 1e-9
 
 
+@pytest.mark.parametrize('tag,sweep', [('f32', '0'), ('f64', '2')])
+def test_persistent_kernel_forms_not_taken_by_default(pr, syn, tag, sweep, monkeypatch):
+    """The float two-pass form (MC3D_REFINE_SWEEP=0) and the double-state sweep (=2) of the persistent kernel against the
+    reference's 'readme' run: both are A/B paths that must stay correct."""
+    import torch
+    import mc3d_b200.utils as u
+    monkeypatch.setenv('MC3D_REFINE_SWEEP', sweep)
+    g = load_golden('refine_T48.npz')
+    dt = torch.float64 if tag == 'f64' else torch.float32
+    opt = pr.Optimized_3d_Pose_Estimation(g['gaussians'].copy(), g['init'].copy(), decomposed_cam_params_initial=_cam_params(g, 2),
+                                          body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+    opt.sgd_optimize(**u.prepare_kwargs(opt.sgd_optimize, RUNS['readme']))
+    key = f'run_readme_{tag}'
+    for name, h in _history(opt).items():
+        ref = g[f'{key}_{name}']
+        assert len(h) == len(ref)
+        assert np.max(np.abs(h - ref) / np.abs(ref)) < (1e-9 if tag == 'f64' else LOSS_RTOL), name
+    assert np.abs(opt.trajectory.numpy() - g[f'{key}_final']).max() < (1e-6 if tag == 'f64' else 5e-2)
+
+
 @pytest.mark.parametrize('tag', ['f64', 'f32'])
 def test_sgd_optimize_matches_reference_at_4000_frames(pr, syn, tag):
     """tests/golden/refine_T4000.npz: the unmodified reference on 4 000 frames x 17 joints (inputs from the seeded generator,
