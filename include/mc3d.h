@@ -272,7 +272,7 @@ int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step
  * s + 1 in one sweep over block-owned item ranges (cp.async-staged Adam operands in flight during pass 1, range edges
  * announced through blk_seq), ONE grid-wide meeting per step, any shard size below 2^30 joint-frames.  Double state:
  * the two passes one after the other (two grid barriers per step), any shard size as well (the float two-pass form --
- * per-camera Gaussians, MC3D_REFINE_SWEEP=0 -- up to ~150 000 frames x 17 joints, beyond that a CUDA graph of the three
+ * MC3D_REFINE_SWEEP=0 -- up to ~150 000 frames x 17 joints, beyond that a CUDA graph of the three
  * phases).  MC3D_REFINE_FUSED=0 selects the graph of two kernels (four components, 17 sums).
  * Without `gc`: phases 0,1,2 replayed from a CUDA graph of the three kernels (with the in-kernel exchange between them
  * when world > 1).  MC3D_REFINE_TWO_PHASE / MC3D_REFINE_FUSED / MC3D_REFINE_SWEEP = 0 / 1 in the environment force a

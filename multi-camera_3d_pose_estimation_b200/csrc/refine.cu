@@ -1456,8 +1456,8 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
                     const T *xc = in_tiles ? xwin + el : x + el;
                     const P1Own<T> own{xc[0], xc[1], xc[2], ms[(u * 5 + 0) * NT + tid], ms[(u * 5 + 1) * NT + tid],
                                        ms[(u * 5 + 2) * NT + tid], ms[(u * 5 + 3) * NT + tid], ms[(u * 5 + 4) * NT + tid]};
-                    costgrad_item<T, true>(pc, tb, camf, t, j, xc, own, nullptr, nullptr, pc.tok[t], pc.tok[t + 1], pc.tok[t + 2],
-                                           gc + 3LL * e, n3, a);
+                    costgrad_item<T, true>(pc, tb, camf, t, j, xc, own, mu0 + 2LL * e, S + 3LL * e, pc.tok[t], pc.tok[t + 1], pc.tok[t + 2],
+                                           gc + 3LL * e, n3, a);          // (the pointers serve cameras > 0 of per-camera Gaussians)
                 }
             }
             finish(i + 1);
@@ -1674,14 +1674,14 @@ static bool sweep_wanted(const mc3d_refine_problem *pb, size_t elem_size) {
     // bookkeeping costs more than the overlap returns (measured with one item per thread and trip, 2 CTAs per SM: 223 vs 165 us
     // per step at 100 000 frames, 39 vs 33 at 12 500; parity suite green in both forms)
     const char *envs = getenv("MC3D_REFINE_SWEEP");                 // 0 forbids the fused sweep, 2 allows it for double state (measurement)
-    return !(envs && atoi(envs) == 0) && pb->gauss_cam_stride == 0 && (elem_size == 4 || (envs && atoi(envs) == 2));
+    return !(envs && atoi(envs) == 0) && (elem_size == 4 || (envs && atoi(envs) == 2));
 }
 static bool shard_is_small(const mc3d_refine_problem *pb, size_t elem_size) {
     const long long world = pb->world > 1 ? pb->world : 1;
     const long long frames = pb->world > 1 ? (pb->total_frames + world - 1) / world : pb->n_frames;
     // the fused sweep walks block-owned ranges of any length (measured to 200 000 frames); the double-state two-pass persistent
     // kernel beats the graphs of kernels at every size measured (400 000 frames: 597 vs 803 us per step); the float two-pass
-    // form (MC3D_REFINE_SWEEP=0, per-camera Gaussians) was measured up to ~150 000 frames x 17 joints
+    // form (MC3D_REFINE_SWEEP=0) was measured up to ~150 000 frames x 17 joints
     if (sweep_wanted(pb, elem_size) || elem_size == 8) return frames * pb->n_joints < (1LL << 30);
     return frames * pb->n_joints <= (long long)MC3D_RF_SMALL * sm_count() * 2 * RF_THREADS;
 }
