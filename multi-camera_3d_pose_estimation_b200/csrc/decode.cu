@@ -135,6 +135,15 @@ __device__ __forceinline__ MapStats map_stats(const float *src, float *wb, int H
     return r;
 }
 
+__device__ __forceinline__ long long div_small(long long a, int b);
+__device__ __forceinline__ void store_keypoint(float kx, float ky, float score, long long map, const DecodeParams &p, float *__restrict__ kpt);
+
+// map index / small divisor: 32-bit when the index allows (a 64-bit division is ~100 instructions, and the transposing layouts
+// with an affine need two per map -- 10 % of the moments kernel)
+__device__ __forceinline__ long long div_small(long long a, int b) {
+    return (a >> 31) == 0 ? (long long)((unsigned)a / (unsigned)b) : a / b;
+}
+
 __device__ __forceinline__ void write_outputs(const MapStats &r, const float *src, long long map, const DecodeParams &p,
                                               const float *__restrict__ affine, float *__restrict__ kpt,
                                               double *__restrict__ moments, int lane) {
@@ -156,30 +165,34 @@ __device__ __forceinline__ void write_outputs(const MapStats &r, const float *sr
                 ky += dy > 0.f ? 0.25f : (dy < 0.f ? -0.25f : 0.f);
             }
             if (p.has_affine) {
-                const float *a = affine + (map / p.affine_group) * 4;
+                const float *a = affine + div_small(map, p.affine_group) * 4;
                 kx = fmaf(kx, a[0], a[2]);
                 ky = fmaf(ky, a[1], a[3]);
             }
         }
-        if (p.kpt_layout == MC3D_KPT_PLAIN) {
-            kpt[map * 3 + 0] = kx; kpt[map * 3 + 1] = ky; kpt[map * 3 + 2] = score;
-        } else {
-            const long long cj = (long long)p.views * p.joints;
-            const long long t = map / cj;
-            const int rem = (int)(map - t * cj);
-            const int c = rem / p.joints, j = rem - c * p.joints;
-            const long long tj = t * p.joints + j;
-            if (p.kpt_layout == MC3D_KPT_NV3) {
-                float *o = kpt + (tj * p.views + c) * 3;
-                o[0] = kx; o[1] = ky; o[2] = score;
-            } else {
-                float *o = kpt + tj * 3 * p.views + c;
-                o[0] = kx; o[p.views] = ky; o[2 * p.views] = score;
-            }
-        }
+        store_keypoint(kx, ky, score, map, p, kpt);
     }
 }
 
+
+__device__ __forceinline__ void store_keypoint(float kx, float ky, float score, long long map, const DecodeParams &p, float *__restrict__ kpt) {
+    if (p.kpt_layout == MC3D_KPT_PLAIN) {
+        kpt[map * 3 + 0] = kx; kpt[map * 3 + 1] = ky; kpt[map * 3 + 2] = score;
+    } else {
+        const int cj = p.views * p.joints;
+        const long long t = div_small(map, cj);
+        const int rem = (int)(map - t * cj);
+        const int c = rem / p.joints, j = rem - c * p.joints;
+        const long long tj = t * p.joints + j;
+        if (p.kpt_layout == MC3D_KPT_NV3) {
+            float *o = kpt + (tj * p.views + c) * 3;
+            o[0] = kx; o[1] = ky; o[2] = score;
+        } else {
+            float *o = kpt + tj * 3 * p.views + c;
+            o[0] = kx; o[p.views] = ky; o[2 * p.views] = score;
+        }
+    }
+}
 
 // ---- register-resident kernel for 64 x 48 maps (the reference's heatmap size, BASELINE config 3) ----------------
 // One warp per map; every lane pulls its 24 float4 (element e = 4 lane + 128 k, k = 0..23) with streaming 128-bit
@@ -290,6 +303,19 @@ decode_reg6448_kernel(const float *__restrict__ hm, float *__restrict__ hm_wb, l
             const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
             argmax_merge(best, best_idx, ov, oi);
         }
+        // The keypoint needs raw values around the maximum -- the winning float4 (which of its four elements is the first
+        // maximum), the elements left and right of it and the float4s one row above and below (the quarter-pixel shift) -- and the
+        // map's affine.  Fourteen lanes fetch one scalar each NOW (the map has just come through L2), four more the affine, so
+        // that the loads travel behind the moment reductions instead of forming a chain of L2 round trips in lane 0 at the end
+        // of every map (measured with moments: plain layout 0.88 -> 0.90 of the HBM peak, transposed layout with affine 0.80 -> 0.82; 1.01 without keypoints).
+        float nbv = 0.f, affv = 0.f;
+        if (kpt) {
+            const float *raw = hm + map * HW;
+            const int a = lane < 4 ? best_idx + lane : lane < 8 ? best_idx - W + (lane - 4) : lane < 12 ? best_idx + W + (lane - 8)
+                        : lane == 12 ? best_idx - 1 : lane == 13 ? best_idx + 4 : -1;
+            if (a >= 0 && a < HW) nbv = raw[a];
+            if (p.has_affine && lane >= 16 && lane < 20) affv = affine[div_small(map, p.affine_group) * 4 + (lane - 16)];
+        }
         MapStats r;
         r.best = best;
         r.best_idx = best_idx;
@@ -340,14 +366,38 @@ decode_reg6448_kernel(const float *__restrict__ hm, float *__restrict__ hm_wb, l
             r.vy = warp_sum((double)syy) * inv - ey * ey;
             r.cxy = warp_sum((double)sxy) * inv - ex * ey;
         }
-        // resolve the element inside the winning float4 (first maximum); raw values are still in memory
-        if (kpt && lane == 0 && best > -INFINITY) {
-            const float *raw = hm + map * HW;
-            int e = r.best_idx;
-            while (e < r.best_idx + 3 && !(raw[e] == best)) ++e;
-            r.best_idx = e;
+        if (moments && lane < 6) {
+            const double val = lane == 0 ? r.mx : lane == 1 ? r.my : lane == 2 ? r.vx : lane == 5 ? r.vy : r.cxy;
+            moments[map * 6 + lane] = val;
         }
-        write_outputs(r, hm + map * HW, map, p, affine, kpt, moments, lane);    // reads the raw neighbours of the maximum
+        if (kpt) {
+            // the element inside the winning float4 (first maximum) and its four neighbours, from the lanes that fetched them
+            const float q0 = __shfl_sync(0xffffffffu, nbv, 0), q1 = __shfl_sync(0xffffffffu, nbv, 1);
+            const float q2 = __shfl_sync(0xffffffffu, nbv, 2), q3 = __shfl_sync(0xffffffffu, nbv, 3);
+            const int i = q0 == best ? 0 : q1 == best ? 1 : q2 == best ? 2 : 3;
+            const float up = __shfl_sync(0xffffffffu, nbv, 4 + i), down = __shfl_sync(0xffffffffu, nbv, 8 + i);
+            const float l12 = __shfl_sync(0xffffffffu, nbv, 12), r13 = __shfl_sync(0xffffffffu, nbv, 13);
+            const float left = i == 0 ? l12 : i == 1 ? q0 : i == 2 ? q1 : q2;
+            const float right = i == 0 ? q1 : i == 1 ? q2 : i == 2 ? q3 : r13;
+            const float a0 = __shfl_sync(0xffffffffu, affv, 16), a1 = __shfl_sync(0xffffffffu, affv, 17);
+            const float a2 = __shfl_sync(0xffffffffu, affv, 18), a3 = __shfl_sync(0xffffffffu, affv, 19);
+            if (lane == 0) {
+                float kx = -1.f, ky = -1.f;
+                if (best > 0.f) {                               // mmpose: maxima <= 0 are "not found" (-1, -1)
+                    const int e = r.best_idx + i;
+                    const int py = e / W, px = e - py * W;
+                    kx = (float)px;
+                    ky = (float)py;
+                    if (px > 1 && px < W - 1 && py > 1 && py < 64 - 1) {
+                        const float dx = right - left, dy = down - up;
+                        kx += dx > 0.f ? 0.25f : (dx < 0.f ? -0.25f : 0.f);
+                        ky += dy > 0.f ? 0.25f : (dy < 0.f ? -0.25f : 0.f);
+                    }
+                    if (p.has_affine) { kx = fmaf(kx, a0, a2); ky = fmaf(ky, a1, a3); }
+                }
+                store_keypoint(kx, ky, best, map, p, kpt);
+            }
+        }
         if (MOMENTS && p.write_back) {                       // upstream's in-place thresholding, after the raw reads
             __syncwarp();
             float4 *dst = reinterpret_cast<float4 *>(hm_wb + map * HW) + lane;
@@ -430,7 +480,8 @@ int decode_device(const float *d_hm, long long n_maps, int H, int W, float thr, 
         set_error("bad kpt_layout %d", kpt_layout);
         return MC3D_ERR_INVALID_ARGUMENT;
     }
-    if (kpt_layout != MC3D_KPT_PLAIN && (views <= 0 || joints <= 0 || n_maps % ((long long)views * joints) != 0)) {
+    if (kpt_layout != MC3D_KPT_PLAIN && (views <= 0 || joints <= 0 || (long long)views * joints > (1LL << 30) ||
+                                         n_maps % ((long long)views * joints) != 0)) {
         set_error("transposing layouts need views, joints > 0 and n_maps %% (views*joints) == 0");
         return MC3D_ERR_INVALID_ARGUMENT;
     }
