@@ -217,6 +217,9 @@ typedef struct {
      * the same order, read by every launch: cameras that are learnt together with the trajectory (pose_refinement.py:931-961)
      * are updated on the device between the phases of a step, with no host round trip. */
     const double *cams_dev;
+    /* Test hook (0 in production).  Bit 0: the persistent kernel treats the counts of finite terms as changed at every fourth
+     * optimiser step, which sends it through the repetition of pass 1 that a value turning non-finite would cause. */
+    int64_t test_flags;
 } mc3d_refine_problem;
 
 /* Exchange block at the start of each rank's peer allocation (zero-filled by mc3d_peer_alloc). */

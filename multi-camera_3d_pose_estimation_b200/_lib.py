@@ -67,7 +67,7 @@ class RefineProblem(ctypes.Structure):
                 ('term_ok', ctypes.c_void_p), ('ctrl', ctypes.c_void_p), ('gc', ctypes.c_void_p),
                 ('rank', ctypes.c_int32), ('world', ctypes.c_int32), ('n_frames_left', ctypes.c_int64),
                 ('spin_timeout_ns', ctypes.c_int64), ('xchg', ctypes.c_void_p * MAX_PEERS),
-                ('gauss_cam_stride', ctypes.c_int64), ('cams_dev', ctypes.c_void_p)]
+                ('gauss_cam_stride', ctypes.c_int64), ('cams_dev', ctypes.c_void_p), ('test_flags', ctypes.c_int64)]
 
 
 class RefineXchg(ctypes.Structure):

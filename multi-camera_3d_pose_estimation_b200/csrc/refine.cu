@@ -1223,7 +1223,8 @@ __device__ __forceinline__ void pass1_checked(const mc3d_refine_problem &pb, con
         }
         if (take_ticket(mine, 0)) publish2_ll(pb, parity, seq, attempt != 0);
         gather2_ll(pb, parity, seq, tot, halves, attempt != 0);
-        const bool same = tot[1] == counts[0] && (!do_smooth || tot[3] == counts[1]);
+        const bool same = tot[1] == counts[0] && (!do_smooth || tot[3] == counts[1]) &&
+                          !(attempt == 0 && (pb.test_flags & 1) && (seq & 3) == 0);             // (test hook: see mc3d.h)
         counts[0] = tot[1]; counts[1] = tot[3];
         if (same) break;                                           // identical decision in every block and rank
     }
@@ -1475,7 +1476,7 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             bias[1] = 1.0 - pow(pb.beta2, ss.step + 1.0);
         }
         gather2_ll(pb, parity ^ 1, seq + 1, tot, halves, false, false);   // the step's one grid-wide meeting (+ cross-rank sums)
-        const bool same = tot[1] == counts[0] && (!do_smooth || tot[3] == counts[1]);
+        const bool same = tot[1] == counts[0] && (!do_smooth || tot[3] == counts[1]) && !((pb.test_flags & 1) && ((seq + 1) & 3) == 0);
         counts[0] = tot[1]; counts[1] = tot[3];
         if (!same) {
             if (tid == 0) fence_gpu();                             // the repeated pass reads x in grid-stride order

@@ -372,6 +372,7 @@ class RefineEngine:
             setattr(pb, name, getattr(self, name).data_ptr())
         pb.x = self.x_ext.data_ptr()
         pb.gauss_cam_stride = 0 if self.gaussian_cameras is None else n * self.J
+        pb.test_flags = int(os.environ.get('MC3D_REFINE_TEST_FLAGS', '0'))      # test hook (include/mc3d.h)
         if self.peer is not None:
             pb.gc = self.gc.data_ptr()
             pb.rank, pb.world = self.comm.rank, self.comm.world

@@ -71,6 +71,36 @@ def test_persistent_kernel_forms_not_taken_by_default(pr, syn, tag, sweep, monke
 
 
 @pytest.mark.parametrize('tag', ['f64', 'f32'])
+def test_repeated_pass1_gives_the_same_run(pr, syn, tag, monkeypatch):
+    """The persistent kernel folds 1/N_lik and 2 lambda_s/N_s into a stored gradient component with the counts of the previous
+    step and repeats pass 1 when a step's own counts differ (a value turned non-finite).  mc3d_refine_problem.test_flags bit 0
+    declares the counts changed at every fourth step: the run must equal the undisturbed one (the repeated pass adds its sums
+    in another order, hence the float tolerance).  4 000 frames: many blocks, in the fused sweep (float) and the two passes (double)."""
+    import torch
+    import mc3d_b200.utils as u
+    n = 4000
+    gs, init, cams, _ = syn.refinement_inputs(n, n_cams=2, seed=78)
+    dt = torch.float64 if tag == 'f64' else torch.float32
+    kw = dict(lr=0.01, lambda_smooth=1e-6, lambda_body_length=1, patience=100, max_iter=13, time_interval=[0, n])
+
+    def run(flags):
+        monkeypatch.setenv('MC3D_REFINE_TEST_FLAGS', flags)
+        opt = pr.Optimized_3d_Pose_Estimation(gs.copy(), init.copy(), decomposed_cam_params_initial={i: [np.asarray(a).copy() for a in cams[i]] for i in cams},
+                                              body_lengths=dict(syn.EXAMPLE_BODY_LENGTHS), torch_dtype=dt)
+        opt.sgd_optimize(**u.prepare_kwargs(opt.sgd_optimize, kw))
+        return _history(opt), opt.trajectory.numpy(), np.array(opt.best_trajectory)
+
+    h0, x0, b0 = run('0')
+    h1, x1, b1 = run('1')
+    rtol = 1e-10 if tag == 'f64' else 1e-6          # (the body-length cost is a small difference of large sums)
+    for name in h0:
+        assert len(h0[name]) == len(h1[name]) == 28
+        assert np.max(np.abs(h0[name] - h1[name]) / np.abs(h0[name])) < rtol, name
+    atol = 1e-9 if tag == 'f64' else 1e-3
+    assert np.abs(x0 - x1).max() < atol and np.abs(b0 - b1).max() < atol
+
+
+@pytest.mark.parametrize('tag', ['f64', 'f32'])
 def test_sgd_optimize_matches_reference_at_4000_frames(pr, syn, tag):
     """tests/golden/refine_T4000.npz: the unmodified reference on 4 000 frames x 17 joints (inputs from the seeded generator,
     only results stored).  68 000 joint-frames put hundreds of thread blocks -- each with neighbours on both sides -- into the
