@@ -27,6 +27,19 @@ def test_sharded_refinement_equals_single_gpu():
 
 
 @pytest.mark.timeout(900)
+def test_sharded_refinement_with_repeated_pass1_equals_single_gpu():
+    """The repetition of pass 1 (counts of finite terms declared changed at every fourth step: mc3d_refine_problem.test_flags)
+    exchanges its sums through the ranks' retry slots: sharded run == single-GPU run with the same hook."""
+    if _n_gpus() < 2:
+        pytest.skip('needs two GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29545', os.path.join(ROOT, 'tests', 'mgpu_refine_check.py')]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=800, env=dict(os.environ, MC3D_REFINE_TEST_FLAGS='1'))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'ok=True' in r.stdout and 'peer_exchange=True' in r.stdout
+
+
+@pytest.mark.timeout(900)
 def test_sharded_refinement_falls_back_to_host_driven_exchange():
     """When a peer's exchange block cannot be mapped (MC3D_PEER_FAIL=1 simulates it) every rank switches to the NCCL path."""
     if _n_gpus() < 2:
