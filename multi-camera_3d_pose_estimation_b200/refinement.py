@@ -11,7 +11,7 @@ and the ONLY traffic per step of the three-phase formulation is
     after phase 0:                  all-reduce of 7 doubles (cost sums and counts)
     after phase 1:                  all-reduce of 1 double (sum g^2)
 
-(the two-phase step exchanges one block of 17 sums instead of the two all-reduces)
+(the two-phase step exchanges one block of 13 sums instead of the two all-reduces)
 
 so every rank takes identical clip / Adam / early-stopping decisions with no further communication
 (SURVEY.md section 8e).  On GPUs that exchange happens INSIDE the kernels over NVLink peer memory (``PeerExchange``,
