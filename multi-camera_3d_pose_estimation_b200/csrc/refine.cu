@@ -1321,6 +1321,17 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
     // position would be the first thing every warp of the block waits for after the trip's barrier.  Items whose window
     // leaves the block's interior (its first / last ~4 J items) read global memory.
     T *xtile = stage_ms + 2 * SWEEP_ITEMS * 5 * NT;                 // [4][CE]
+    // the operands of a thread's first edge element, fetched before the step's meeting so that the edge update -- the first
+    // thing on the next step's critical path -- does not start with an L2 round trip
+    T epre[6] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
+    bool edge_pre = false;
+    auto fetch_edge = [&]() {
+        if (tid < n_edge) {
+            const int i = tid < A0 - eL0 ? eL0 + tid : A1 + (tid - (A0 - eL0));
+            epre[0] = c1[i]; epre[1] = c2[i]; epre[2] = c3[i]; epre[3] = m[i]; epre[4] = v[i]; epre[5] = x[i];
+        }
+        edge_pre = true;
+    };
     for (long long it = 0; it < n_iters; ++it) {
         const RefineDerived dv = derive(pb, tot, st);
         double gnorm2;
@@ -1403,13 +1414,14 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             }
         };
         issue(0);                                                   // Adam chunk 0 travels while the edges are updated
-        // 1. the two edges of my range, announced at once
+        // 1. the two edges of my range, announced at once (a thread's first edge element was fetched before the meeting)
         bool pushed = false;
         for (int q = tid; q < n_edge; q += NT) {
             const int i = q < A0 - eL0 ? eL0 + q : A1 + (q - (A0 - eL0));
-            T mi = m[i], vi = v[i], xi = x[i];
+            const bool pre = edge_pre && q == tid;
+            T mi = pre ? epre[3] : m[i], vi = pre ? epre[4] : v[i], xi = pre ? epre[5] : x[i];
             if (wr_old) bestx[i] = xi;
-            adam_el(i, c1[i], c2[i], c3[i], mi, vi, xi);
+            adam_el(i, pre ? epre[0] : c1[i], pre ? epre[1] : c2[i], pre ? epre[2] : c3[i], mi, vi, xi);
             m[i] = mi; v[i] = vi; x[i] = xi;
             if (wr_new) bestx[i] = xi;
             if (left_halo && i < halo_n) { left_halo[i] = xi; pushed = true; }
@@ -1471,6 +1483,7 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             block_reduce_add<NS2>(acc, red, mine->acc2[parity ^ 1]);
         }
         if (take_ticket(mine, 0)) publish2_ll(pb, parity ^ 1, seq + 1, false);
+        fetch_edge();                                               // (my own edges: written by this block, final since its last trip)
         if (tid == NT - 1) {                                        // Adam's bias corrections of the next step, while the words travel
             bias[0] = 1.0 - pow(pb.beta1, ss.step + 1.0);
             bias[1] = 1.0 - pow(pb.beta2, ss.step + 1.0);
@@ -1482,6 +1495,7 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             if (tid == 0) fence_gpu();                             // the repeated pass reads x in grid-stride order
             __syncthreads();
             pass1_checked<T>(pb, tb, camf, parity ^ 1, seq + 1, (T)mix.mu, counts, 1, red, tot, halves);
+            edge_pre = false;                                      // the components were written again (by other blocks)
         }
         st[0] = ss.step; st[1] = ss.run_sum; st[2] = ss.run_cnt; st[3] = ss.best; st[4] = ss.no_imp; st[5] = 0.0;
         st[6] = ss.iters; st[7] = ss.improved ? 1.0 : 0.0; st[8] = mix.mu; st[9] = counts[0]; st[10] = counts[1];
