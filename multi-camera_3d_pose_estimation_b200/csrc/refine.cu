@@ -1321,6 +1321,36 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
     // position would be the first thing every warp of the block waits for after the trip's barrier.  Items whose window
     // leaves the block's interior (its first / last ~4 J items) read global memory.
     T *xtile = stage_ms + 2 * SWEEP_ITEMS * 5 * NT;                 // [4][CE]
+    auto issue = [&](int k) {                                   // Adam chunk k + the Gaussians of pass-1 chunk k
+        const int p0 = A0 / SWEEP_ITEMS + k * (CE / SWEEP_ITEMS) + tid;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int pi = p0 + r * NT;
+            if (SWEEP_ITEMS * pi < A1) {
+                cp_async_bytes<8>(stage2 + (0 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(c1) + pi);
+                cp_async_bytes<8>(stage2 + (1 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(c2) + pi);
+                cp_async_bytes<8>(stage2 + (2 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(c3) + pi);
+                cp_async_bytes<8>(stage2 + (3 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(m) + pi);
+                cp_async_bytes<8>(stage2 + (4 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(v) + pi);
+                cp_async_bytes<8>(stage2 + (5 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(x) + pi);
+            }
+        }
+        if (k < n_c) {
+            T *ms = stage_ms + (k & 1) * (SWEEP_ITEMS * 5 * NT);
+#pragma unroll
+            for (int u = 0; u < SWEEP_ITEMS; ++u) {
+                const int e = r_lo + k * CI + u * NT + tid;
+                if (e < r_hi) {
+                    cp_async_bytes<sizeof(T)>(ms + (u * 5 + 0) * NT + tid, mu0 + 2LL * e);
+                    cp_async_bytes<sizeof(T)>(ms + (u * 5 + 1) * NT + tid, mu0 + 2LL * e + 1);
+                    cp_async_bytes<sizeof(T)>(ms + (u * 5 + 2) * NT + tid, S + 3LL * e);
+                    cp_async_bytes<sizeof(T)>(ms + (u * 5 + 3) * NT + tid, S + 3LL * e + 1);
+                    cp_async_bytes<sizeof(T)>(ms + (u * 5 + 4) * NT + tid, S + 3LL * e + 2);
+                }
+            }
+        }
+        cp_async_commit();
+    };
     // the operands of a thread's first edge element, fetched before the step's meeting so that the edge update -- the first
     // thing on the next step's critical path -- does not start with an L2 round trip
     T epre[6] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
@@ -1332,6 +1362,7 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
         }
         edge_pre = true;
     };
+    issue(0);                                                       // Adam chunk 0 and the first trip's Gaussians: always a step ahead
     for (long long it = 0; it < n_iters; ++it) {
         const RefineDerived dv = derive(pb, tot, st);
         double gnorm2;
@@ -1339,6 +1370,7 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
         const bool last_iter = it + 1 == n_iters;
         const StepScalars<T> ss = step_scalars<T>(pb, 1, gnorm2, st, dv, bias, &best_pending, last_iter, it > 0);
         if (last_iter || ss.stop) {                                // Adam alone (the launch ends here); halos leave first (block 0)
+            cp_async_wait_all();                                   // (the staged chunk is not used)
             __syncthreads();
             if (tid == 0) fence_gpu();                             // this pass reads what other blocks wrote (grid-stride order)
             __syncthreads();
@@ -1364,36 +1396,6 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             const T denom = sqrt_c(vi) * adamc[4] + adamc[5];
             xi = xi - adamc[6] * div_c(mi, denom);                 // param.addcdiv_(exp_avg, denom, value=-step_size)
         };
-        auto issue = [&](int k) {                                   // Adam chunk k + the Gaussians of pass-1 chunk k
-            const int p0 = A0 / SWEEP_ITEMS + k * (CE / SWEEP_ITEMS) + tid;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int pi = p0 + r * NT;
-                if (SWEEP_ITEMS * pi < A1) {
-                    cp_async_bytes<8>(stage2 + (0 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(c1) + pi);
-                    cp_async_bytes<8>(stage2 + (1 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(c2) + pi);
-                    cp_async_bytes<8>(stage2 + (2 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(c3) + pi);
-                    cp_async_bytes<8>(stage2 + (3 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(m) + pi);
-                    cp_async_bytes<8>(stage2 + (4 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(v) + pi);
-                    cp_async_bytes<8>(stage2 + (5 * 3 + r) * NT + tid, reinterpret_cast<const Unit *>(x) + pi);
-                }
-            }
-            if (k < n_c) {
-                T *ms = stage_ms + (k & 1) * (SWEEP_ITEMS * 5 * NT);
-#pragma unroll
-                for (int u = 0; u < SWEEP_ITEMS; ++u) {
-                    const int e = r_lo + k * CI + u * NT + tid;
-                    if (e < r_hi) {
-                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 0) * NT + tid, mu0 + 2LL * e);
-                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 1) * NT + tid, mu0 + 2LL * e + 1);
-                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 2) * NT + tid, S + 3LL * e);
-                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 3) * NT + tid, S + 3LL * e + 1);
-                        cp_async_bytes<sizeof(T)>(ms + (u * 5 + 4) * NT + tid, S + 3LL * e + 2);
-                    }
-                }
-            }
-            cp_async_commit();
-        };
         auto finish = [&](int k) {
             cp_async_wait_all();
             const int p0 = A0 / SWEEP_ITEMS + k * (CE / SWEEP_ITEMS) + tid;
@@ -1413,7 +1415,6 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
                 }
             }
         };
-        issue(0);                                                   // Adam chunk 0 travels while the edges are updated
         // 1. the two edges of my range, announced at once (a thread's first edge element was fetched before the meeting)
         bool pushed = false;
         for (int q = tid; q < n_edge; q += NT) {
@@ -1484,6 +1485,7 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
         }
         if (take_ticket(mine, 0)) publish2_ll(pb, parity ^ 1, seq + 1, false);
         fetch_edge();                                               // (my own edges: written by this block, final since its last trip)
+        issue(0);                                                   // the next step's Adam chunk 0 travels during the meeting
         if (tid == NT - 1) {                                        // Adam's bias corrections of the next step, while the words travel
             bias[0] = 1.0 - pow(pb.beta1, ss.step + 1.0);
             bias[1] = 1.0 - pow(pb.beta2, ss.step + 1.0);
@@ -1495,7 +1497,10 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
             if (tid == 0) fence_gpu();                             // the repeated pass reads x in grid-stride order
             __syncthreads();
             pass1_checked<T>(pb, tb, camf, parity ^ 1, seq + 1, (T)mix.mu, counts, 1, red, tot, halves);
-            edge_pre = false;                                      // the components were written again (by other blocks)
+            edge_pre = false;                                      // the components were written again (by other blocks):
+            cp_async_wait_all();                                   // stage chunk 0 anew
+            __syncthreads();
+            issue(0);
         }
         st[0] = ss.step; st[1] = ss.run_sum; st[2] = ss.run_cnt; st[3] = ss.best; st[4] = ss.no_imp; st[5] = 0.0;
         st[6] = ss.iters; st[7] = ss.improved ? 1.0 : 0.0; st[8] = mix.mu; st[9] = counts[0]; st[10] = counts[1];
