@@ -1271,9 +1271,22 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
     const int J = pb.n_joints, JS = J * 3, tid = threadIdx.x, NT = RF_THREADS;
     const int n_items = (int)(pb.n_frames * J);
     const int b = blockIdx.x, G = gridDim.x;
-    // my items: boundaries at multiples of 4 items, so that pairs of elements are 8-byte aligned in every array
-    const int r_lo = b == 0 ? 0 : (int)(((long long)n_items * b / G) & ~3LL);
-    const int r_hi = b == G - 1 ? n_items : (int)(((long long)n_items * (b + 1) / G) & ~3LL);
+    // my items: boundaries at multiples of 4 items, so that pairs of elements are 8-byte aligned in every array.  The block
+    // next to a neighbour RANK starts its sweep later than the others -- it waits for the halo that crosses NVLink -- and
+    // everybody meets again at the end of the step, so it gets one trip less than the rest.
+    constexpr int TRIP = sweep_items<T>() * RF_THREADS;
+    const int per = n_items / G;
+    int short_len = per - TRIP > (per < 480 ? per : 480) ? per - TRIP : (per < 480 ? per : 480);
+    short_len &= ~3;
+    const bool short_l = pb.rank > 0 && G >= 4 && short_len >= 4 * J + 32, short_r = pb.rank < pb.world - 1 && G >= 4 && short_len >= 4 * J + 32;
+    const int len_l = short_l ? short_len : 0, len_r = short_r ? short_len : 0;
+    const int mid_blocks = G - (short_l ? 1 : 0) - (short_r ? 1 : 0), mid_items = n_items - len_l - len_r;
+    auto range_start = [&](int q) -> int {                         // first item of block q, q in [0, G]
+        if (q <= 0) return 0;
+        if (q >= G) return n_items;
+        return len_l + (int)(((long long)mid_items * (q - (short_l ? 1 : 0)) / mid_blocks) & ~3LL);
+    };
+    const int r_lo = range_start(b), r_hi = range_start(b + 1);
     const int E = 2 * J;                                           // items of a 2-frame edge
     const bool do_smooth = pb.lambda_smooth > 0.0;
     double st[11];
