@@ -257,6 +257,10 @@ int mc3d_refine_flags_f32(const mc3d_refine_problem *pb, void *stream);
 int mc3d_refine_flags_f64(const mc3d_refine_problem *pb, void *stream);
 /* sizeof(mc3d_refine_problem), so that a binding can check its struct layout. */
 int mc3d_refine_problem_size(void);
+/* Host mirror of the fused sweep's work split (the function the kernel calls): the items [lo, hi) of the (frame, joint) order
+ * that thread block `block` of `grid` owns on rank `rank` of `world`.  Boundaries are multiples of 4 items; a block next to a
+ * neighbour rank gets one trip (256 threads x 8 / elem_size items) less than the others.  For tests and capacity planning. */
+int mc3d_refine_sweep_range(int64_t n_items, int grid, int n_joints, int rank, int world, int elem_size, int block, int64_t *lo, int64_t *hi);
 int mc3d_refine_phase_f32(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream);
 int mc3d_refine_phase_f64(const mc3d_refine_problem *pb, int phase, int64_t step_index, int end_of_iteration, void *stream);
 /* n_iters whole-window iterations.

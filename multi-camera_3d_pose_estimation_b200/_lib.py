@@ -122,6 +122,7 @@ SIGNATURES = {
     'mc3d_refine_prepare_f64': (_c_int, [_c_vp, _c_i64, _c_int, _c_int, _c_int, _c_dbl, _c_vp, _c_vp, _c_vp]),
     'mc3d_refine_problem_size': (_c_int, []),
     'mc3d_refine_plan': (ctypes.c_char_p, [ctypes.POINTER(RefineProblem)]),
+    'mc3d_refine_sweep_range': (_c_int, [_c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)]),
     'mc3d_refine_flags_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_vp]),
     'mc3d_refine_flags_f64': (_c_int, [ctypes.POINTER(RefineProblem), _c_vp]),
     'mc3d_refine_phase_f32': (_c_int, [ctypes.POINTER(RefineProblem), _c_int, _c_i64, _c_int, _c_vp]),

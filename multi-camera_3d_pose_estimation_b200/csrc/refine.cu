@@ -1259,6 +1259,27 @@ __device__ __forceinline__ void cp_async_bytes(void *smem_dst, const void *gmem_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Item range [lo, hi) of block `q` of `G` in the fused sweep (include/mc3d.h: mc3d_refine_sweep_range).  Boundaries at multiples
+// of 4 items, so that pairs of elements are 8-byte aligned in every array.  The block next to a neighbour RANK starts its sweep
+// later than the others -- it waits for the halo that crosses NVLink -- and everybody meets again at the end of the step, so
+// it gets one trip less than the rest.
+__host__ __device__ inline void sweep_range(int n_items, int G, int J, int rank, int world, int trip, int q, int &lo, int &hi) {
+    const int per = n_items / G;
+    const int cap = per < 480 ? per : 480;
+    int short_len = (per - trip > cap ? per - trip : cap) & ~3;
+    const bool ok = G >= 4 && short_len >= 4 * J + 32;
+    const bool short_l = rank > 0 && ok, short_r = rank < world - 1 && ok;
+    const int len_l = short_l ? short_len : 0, len_r = short_r ? short_len : 0;
+    const int mid_blocks = G - (short_l ? 1 : 0) - (short_r ? 1 : 0), mid_items = n_items - len_l - len_r;
+    auto start = [&](int b) -> int {
+        if (b <= 0) return 0;
+        if (b >= G) return n_items;
+        return len_l + (int)(((long long)mid_items * (b - (short_l ? 1 : 0)) / mid_blocks) & ~3LL);
+    };
+    lo = start(q);
+    hi = start(q + 1);
+}
+
 template <typename T>
 __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, const RefineTables &tb, const T *camf, int parity,
                                                 long long n_iters, double *red, double *tot, double *bias, unsigned int *halves,
@@ -1271,22 +1292,8 @@ __device__ __forceinline__ void fused_sweep_run(const mc3d_refine_problem &pb, c
     const int J = pb.n_joints, JS = J * 3, tid = threadIdx.x, NT = RF_THREADS;
     const int n_items = (int)(pb.n_frames * J);
     const int b = blockIdx.x, G = gridDim.x;
-    // my items: boundaries at multiples of 4 items, so that pairs of elements are 8-byte aligned in every array.  The block
-    // next to a neighbour RANK starts its sweep later than the others -- it waits for the halo that crosses NVLink -- and
-    // everybody meets again at the end of the step, so it gets one trip less than the rest.
-    constexpr int TRIP = sweep_items<T>() * RF_THREADS;
-    const int per = n_items / G;
-    int short_len = per - TRIP > (per < 480 ? per : 480) ? per - TRIP : (per < 480 ? per : 480);
-    short_len &= ~3;
-    const bool short_l = pb.rank > 0 && G >= 4 && short_len >= 4 * J + 32, short_r = pb.rank < pb.world - 1 && G >= 4 && short_len >= 4 * J + 32;
-    const int len_l = short_l ? short_len : 0, len_r = short_r ? short_len : 0;
-    const int mid_blocks = G - (short_l ? 1 : 0) - (short_r ? 1 : 0), mid_items = n_items - len_l - len_r;
-    auto range_start = [&](int q) -> int {                         // first item of block q, q in [0, G]
-        if (q <= 0) return 0;
-        if (q >= G) return n_items;
-        return len_l + (int)(((long long)mid_items * (q - (short_l ? 1 : 0)) / mid_blocks) & ~3LL);
-    };
-    const int r_lo = range_start(b), r_hi = range_start(b + 1);
+    int r_lo, r_hi;                                                // my items
+    sweep_range(n_items, G, J, pb.rank, pb.world > 1 ? pb.world : 1, sweep_items<T>() * RF_THREADS, b, r_lo, r_hi);
     const int E = 2 * J;                                           // items of a 2-frame edge
     const bool do_smooth = pb.lambda_smooth > 0.0;
     double st[11];
@@ -1904,6 +1911,17 @@ int refine_prepare(const T *d_gauss, long long n_frames, int n_cams, int n_joint
 
 extern "C" {
 int mc3d_refine_problem_size(void) { return (int)sizeof(mc3d_refine_problem); }
+int mc3d_refine_sweep_range(int64_t n_items, int grid, int n_joints, int rank, int world, int elem_size, int block, int64_t *lo, int64_t *hi) {
+    if (n_items < 0 || n_items >= 700000000LL || grid < 1 || n_joints < 1 || rank < 0 || world < 1 || rank >= world ||
+        (elem_size != 4 && elem_size != 8) || block < 0 || block >= grid || !lo || !hi) {
+        mc3d::set_error("mc3d_refine_sweep_range: bad arguments");
+        return MC3D_ERR_INVALID_ARGUMENT;
+    }
+    int a = 0, b = 0;
+    mc3d::sweep_range((int)n_items, grid, n_joints, rank, world, (8 / elem_size) * mc3d::RF_THREADS, block, a, b);
+    *lo = a; *hi = b;
+    return MC3D_OK;
+}
 const char *mc3d_refine_plan(const mc3d_refine_problem *pb) { return mc3d::refine_plan(pb); }
 int mc3d_project_points_f32(const float *d_points, int64_t n, const double *cam26, int ignore_distortions, float *d_out, void *stream) {
     return mc3d::project_points<float>(d_points, n, cam26, ignore_distortions, d_out, (cudaStream_t)stream);

@@ -16,7 +16,7 @@ int main(void) {
         (fn_t)mc3d_decode_heatmaps_f32, (fn_t)mc3d_decode_heatmaps_host_f32,
         (fn_t)mc3d_project_points_f32, (fn_t)mc3d_project_points_f64,
         (fn_t)mc3d_refine_prepare_f32, (fn_t)mc3d_refine_prepare_f64,
-        (fn_t)mc3d_refine_problem_size, (fn_t)mc3d_refine_plan,
+        (fn_t)mc3d_refine_problem_size, (fn_t)mc3d_refine_plan, (fn_t)mc3d_refine_sweep_range,
         (fn_t)mc3d_refine_flags_f32, (fn_t)mc3d_refine_flags_f64,
         (fn_t)mc3d_refine_phase_f32, (fn_t)mc3d_refine_phase_f64,
         (fn_t)mc3d_refine_run_f32, (fn_t)mc3d_refine_run_f64,
