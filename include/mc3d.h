@@ -99,7 +99,10 @@ int mc3d_triangulate_f32(const float *d_kpts, int64_t n, const mc3d_rig *rig, in
 int mc3d_triangulate_f64(const double *d_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode,
                          int flags, double *d_out, void *stream);
 
-/* Starting-point plan of the float-storage kernel (host-only, no device work): up to two pairs of views (A, B) whose
+#define MC3D_TRI_MAX_START 4
+/* Starting-point plan of the float-storage kernel (host-only, no device work): up to MC3D_TRI_MAX_START pairs of views (A, B)
+ * -- widest angle first, sharing no view with the earlier pairs while the rig allows it; a joint starts from the first pair
+ * whose two views it sees -- whose
  * closed-form two-view point X = C + s H (x_A, y_A, 1),  s = (z kb - ka) / (ua.q - z ub.q),  q = (x_A, y_A, 1),
  * z = alpha x_B + beta y_B  starts the iteration (the ray of view A cut by the plane that view B's pixel spans along
  * its epipolar direction).  Exposed so that the plan can be checked without a GPU; the kernel's result does not
@@ -112,7 +115,7 @@ typedef struct {
     float ka, kb;          /* (alpha P0 + beta P1)_B . (C,1),  P2_B . (C,1) */
     int32_t view_a, view_b;
 } mc3d_tri_start_pair;
-int mc3d_triangulate_start_plan(const mc3d_rig *rig, mc3d_tri_start_pair *pairs /* [2] */, int32_t *n_pairs);
+int mc3d_triangulate_start_plan(const mc3d_rig *rig, mc3d_tri_start_pair *pairs /* [MC3D_TRI_MAX_START] */, int32_t *n_pairs);
 
 /* Host-buffer variants: chunked H2D -> kernel -> D2H pipeline on the library's own streams;
  * returns after the last byte of h_out is written.  `device` = CUDA ordinal.  One staging pipeline

@@ -33,7 +33,7 @@ struct TriParams {
     int flags;
     int layout;
     // mixed-precision path (float storage)
-    mc3d_tri_start_pair start[2];     // closed-form two-view starting points (fill_start_pairs)
+    mc3d_tri_start_pair start[MC3D_TRI_MAX_START];     // closed-form two-view starting points (fill_start_pairs)
     int n_start;
     float rig2;                       // mean squared distance of the camera centres from the world origin
 };
@@ -370,7 +370,7 @@ __device__ __forceinline__ void pair_start(const mc3d_tri_start_pair *pc, int va
 // All NJ = 2 NP joints of a thread (the solve runs on NP packed pairs).  state: 0 = Xo holds the result, 1 = the all-double solver has to take the joint.
 template <int V, int LAYOUT, int NP>
 __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const mc3d_tri_start_pair *__restrict__ pairs,
-                                            const int4 sv, int n_pairs, float rig2, const float *const (&rows)[2 * NP],
+                                            const int (&sv)[2 * MC3D_TRI_MAX_START], int n_pairs, float rig2, const float *const (&rows)[2 * NP],
                                             float (&Xo)[2 * NP][3], int (&state)[2 * NP]) {
     constexpr int NJ = 2 * NP;
     constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
@@ -386,19 +386,21 @@ __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const 
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 float s0, s1, s2, wm;
-                pair_start<V, LAYOUT>(&pairs[0], sv.x, sv.y, rows[j], s0, s1, s2, wm);
+                pair_start<V, LAYOUT>(&pairs[0], sv[0], sv[1], rows[j], s0, s1, s2, wm);
                 if (wm > 0.f && fmaf(s0, s0, fmaf(s1, s1, s2 * s2)) <= lim) { Xf[j][0] = s0; Xf[j][1] = s1; Xf[j][2] = s2; have[j] = true; }
             }
-            // warp-uniform: clean input never evaluates the second pair
-            bool all_have = true;
+            // warp-uniform: clean input never evaluates the later pairs; a joint takes the first pair it sees with both views
+#pragma unroll 1
+            for (int p = 1; p < n_pairs; ++p) {
+                bool all_have = true;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) all_have = all_have && have[j];
-            if (n_pairs > 1 && __any_sync(0xffffffffu, !all_have)) {
+                for (int j = 0; j < NJ; ++j) all_have = all_have && have[j];
+                if (!__any_sync(0xffffffffu, !all_have)) break;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     float s0, s1, s2, wm;
-                    pair_start<V, LAYOUT>(&pairs[1], sv.z, sv.w, rows[j], s0, s1, s2, wm);
-                    if (!have[j] && wm > 0.f && fmaf(s0, s0, fmaf(s1, s1, s2 * s2)) <= lim) { Xf[j][0] = s0; Xf[j][1] = s1; Xf[j][2] = s2; }
+                    pair_start<V, LAYOUT>(&pairs[p], sv[2 * p], sv[2 * p + 1], rows[j], s0, s1, s2, wm);
+                    if (!have[j] && wm > 0.f && fmaf(s0, s0, fmaf(s1, s1, s2 * s2)) <= lim) { Xf[j][0] = s0; Xf[j][1] = s1; Xf[j][2] = s2; have[j] = true; }
                 }
             }
         }
@@ -605,7 +607,7 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
             c.p01[k] = make_float2((float)prm.P[tid][k], -(float)prm.P[tid][4 + k]);
         }
         cam[tid] = c;
-    } else if (tid < V + 2) {
+    } else if (tid < V + MC3D_TRI_MAX_START) {
         pairs[tid - V] = prm.start[tid - V];
     }
     __syncthreads();                                   // the only block-wide barrier
@@ -626,7 +628,9 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     src += src_step;
     const int n_pairs = prm.n_start;
     // views of the starting pairs straight from the parameter bank (uniform): no shared-memory load in front of the row loads
-    const int4 sv = make_int4(prm.start[0].view_a, prm.start[0].view_b, prm.start[1].view_a, prm.start[1].view_b);
+    int sv[2 * MC3D_TRI_MAX_START];
+#pragma unroll
+    for (int q = 0; q < MC3D_TRI_MAX_START; ++q) { sv[2 * q] = prm.start[q].view_a; sv[2 * q + 1] = prm.start[q].view_b; }
     for (unsigned k = 0; k < my_tiles; ++k) {
         const uint32_t b = k & 1u;                    // output buffer; input stage when there are two
         const uint32_t sb = NST == 2 ? b : 0u;
@@ -989,25 +993,31 @@ int fill_start_pairs(const double (*P)[12], int n_views, mc3d_tri_start_pair *ou
         const double na = sqrt(da[0] * da[0] + da[1] * da[1] + da[2] * da[2]), nb = sqrt(db[0] * db[0] + db[1] * db[1] + db[2] * db[2]);
         return (na > 0 && nb > 0) ? sqrt(cx * cx + cy * cy + cz * cz) / (na * nb) : 0.0;
     };
-    int pa[2] = {-1, -1}, pb[2] = {-1, -1};
-    double best = -1.0;
-    for (int i = 0; i < m; ++i)
-        for (int j = i + 1; j < m; ++j) {
-            const double s = score(idx[i], idx[j]);
-            if (s > best) { best = s; pa[0] = idx[i]; pb[0] = idx[j]; }
-        }
-    best = -1.0;                            // second pair: no view in common with the first when the rig allows it
-    for (int pass = 0; pass < 2 && pa[1] < 0; ++pass)
-        for (int i = 0; i < m; ++i)
-            for (int j = i + 1; j < m; ++j) {
-                const int a = idx[i], c = idx[j];
-                const bool shares = a == pa[0] || a == pb[0] || c == pa[0] || c == pb[0];
-                if ((a == pa[0] && c == pb[0]) || (pass == 0 && shares)) continue;
-                const double s = score(a, c);
-                if (s > best) { best = s; pa[1] = a; pb[1] = c; }
-            }
-    if (pa[1] < 0) { pa[1] = pb[0]; pb[1] = pa[0]; }        // two cameras: the same pair with the roles exchanged
-    for (int p = 0; p < 2; ++p) {
+    // Up to MC3D_TRI_MAX_START pairs, widest angle first; a pair shares no view with the earlier ones while the rig allows it
+    // (a joint takes the first pair whose two views it sees: with disjoint pairs one unusable view costs one pair, and only
+    // joints that lose every pair need the second pass from the origin), then pairs that differ from the earlier ones.
+    int pa[MC3D_TRI_MAX_START], pb[MC3D_TRI_MAX_START], np_ = 0;
+    bool used[MC3D_MAX_VIEWS] = {false};
+    for (int want = 0; want < MC3D_TRI_MAX_START; ++want) {
+        int ba = -1, bb = -1;
+        double best = -1.0;
+        for (int pass = 0; pass < 2 && ba < 0; ++pass)
+            for (int i = 0; i < m; ++i)
+                for (int j = i + 1; j < m; ++j) {
+                    const int a = idx[i], c = idx[j];
+                    if (pass == 0 && (used[a] || used[c])) continue;
+                    bool dup = false;
+                    for (int q = 0; q < np_; ++q) dup = dup || (pa[q] == a && pb[q] == c) || (pa[q] == c && pb[q] == a);
+                    if (dup) continue;
+                    const double s = score(a, c);
+                    if (s > best) { best = s; ba = a; bb = c; }
+                }
+        if (ba < 0) break;
+        pa[np_] = ba; pb[np_] = bb; ++np_;
+        used[ba] = used[bb] = true;
+    }
+    if (np_ == 1) { pa[1] = pb[0]; pb[1] = pa[0]; np_ = 2; }   // two cameras: the same pair with the roles exchanged
+    for (int p = 0; p < np_; ++p) {
         const ViewGeom &ga = geo[pa[p]];
         const double *Pb = P[pb[p]];
         // epipolar direction in view B: the image of a step along the ray from C_A to X0
@@ -1043,7 +1053,7 @@ int fill_start_pairs(const double (*P)[12], int n_views, mc3d_tri_start_pair *ou
         o.view_a = pa[p];
         o.view_b = pb[p];
     }
-    return 2;
+    return np_;
 }
 
 static int fill_params(TriParams &prm, const mc3d_rig *rig, int layout, int mode, int flags) {
@@ -1289,7 +1299,7 @@ static int launch_mixed(const float *d_kpts, long long n, const TriParams &prm, 
     // two stages per warp (one for 16 views): a warp needs ~3 us per tile, which covers the HBM latency, and more resident
     // warps beat a deeper ring
     constexpr size_t smem = TRI_MWARPS * (tri_mixed_stages(V) * stage_bytes + 2 * otile_bytes + 2 * sizeof(uint64_t)) + V * sizeof(CamF) +
-                            2 * sizeof(mc3d_tri_start_pair);
+                            MC3D_TRI_MAX_START * sizeof(mc3d_tri_start_pair);
     static_assert(smem <= 227 * 1024, "mixed kernel: shared memory");
     auto kern = triangulate_mixed_kernel<V, LAYOUT>;
     { const int as = func_max_smem_once((const void *)kern, 227 * 1024); if (as != MC3D_OK) return as; }
@@ -1375,7 +1385,7 @@ int mc3d_triangulate_start_plan(const mc3d_rig *rig, mc3d_tri_start_pair *pairs,
     double P[MC3D_MAX_VIEWS][12];
     for (int v = 0; v < rig->n_views; ++v)
         for (int k = 0; k < 12; ++k) P[v][k] = rig->P[v * 12 + k];
-    memset(pairs, 0, 2 * sizeof(mc3d_tri_start_pair));
+    memset(pairs, 0, MC3D_TRI_MAX_START * sizeof(mc3d_tri_start_pair));
     *n_pairs = mc3d::fill_start_pairs(P, rig->n_views, pairs);
     return MC3D_OK;
 }

@@ -1,6 +1,6 @@
 """CPU: the starting-point plan of the float triangulation kernel (host code of libmc3d.so, no device work).
 
-`mc3d_triangulate_start_plan` picks up to two pairs of views and the constants of the closed-form two-view point the
+`mc3d_triangulate_start_plan` picks up to four pairs of views and the constants of the closed-form two-view point the
 kernel starts from (csrc/triangulate.cu: fill_start_pairs / pair_start).  The kernel's RESULT does not depend on the
 plan (its fixed point is set by double residuals over all views); what has to hold is that the start lands within the
 kernel's acceptance radius (|e|^2 <= 1e-3 (|X|^2 + rig^2), a few per cent of the range) for ordinary input, otherwise
@@ -26,7 +26,7 @@ def lib():
 def start_plan(lib, P):
     from mc3d_b200 import _lib
     rig, keep = _lib.make_rig(P)
-    pairs = (_lib.TriStartPair * 2)()
+    pairs = (_lib.TriStartPair * 4)()
     n = ctypes.c_int32(-1)
     assert lib.mc3d_triangulate_start_plan(ctypes.byref(rig), pairs, ctypes.byref(n)) == 0
     return [pairs[i] for i in range(n.value)]
@@ -53,18 +53,20 @@ def test_ring_rig_pairs_are_disjoint_and_start_near_the_dlt_point(lib, syn, n_vi
     kp, P, X, _ = syn.multiview_points(20000, n_views, seed=3)
     kp = kp.astype(np.float32)
     pairs = start_plan(lib, P)
-    assert len(pairs) == 2
+    assert len(pairs) == min(4, n_views * (n_views - 1) // 2)
     views = [(p.view_a, p.view_b) for p in pairs]
     assert all(0 <= v < n_views for pr in views for v in pr) and all(a != b for a, b in views)
-    if n_views >= 4:
-        assert len({v for pr in views for v in pr}) == 4, views          # a zero-weight view spoils one pair only
+    assert len({frozenset(pr) for pr in views}) == len(views)            # no pair twice
+    n_disjoint = min(len(pairs), n_views // 2)                           # a zero-weight view spoils one pair only, while views last
+    assert len({v for pr in views[:n_disjoint] for v in pr}) == 2 * n_disjoint, views
     ref = O.dlt_weighted(kp.astype(np.float64), P)
-    for pc in pairs:
+    for k, pc in enumerate(pairs):
         assert abs(pc.alpha ** 2 + pc.beta ** 2 - 1.0) < 1e-5
         d = np.linalg.norm(eval_start(pc, kp) - ref, axis=1)
-        # 1 px of noise at 3 m is a few millimetres; the acceptance radius is ~3 % of the range (~130 mm)
-        assert np.median(d) < 10.0
-        assert np.mean(d < 100.0) > 0.999
+        # 1 px of noise at 3 m is a few millimetres; the acceptance radius is ~3 % of the range (~130 mm).  The later pairs
+        # have narrower angles: farther starts (another pass at worst), still inside the radius for nearly every joint
+        assert np.median(d) < (10.0 if k < 2 else 40.0), (k, np.median(d))
+        assert np.mean(d < 100.0) > (0.999 if k < 2 else 0.9), (k, np.mean(d < 100.0))
 
 
 def test_stereo_rig_with_diverging_axes(lib, syn):
@@ -99,7 +101,7 @@ def test_degenerate_rigs_give_no_plan_instead_of_garbage(lib):
 def test_bad_arguments(lib):
     from mc3d_b200 import _lib
     rig, keep = _lib.make_rig(np.zeros((1, 3, 4)))
-    pairs = (_lib.TriStartPair * 2)()
+    pairs = (_lib.TriStartPair * 4)()
     n = ctypes.c_int32(0)
     assert lib.mc3d_triangulate_start_plan(ctypes.byref(rig), pairs, ctypes.byref(n)) == 1
     assert lib.mc3d_triangulate_start_plan(None, pairs, ctypes.byref(n)) == 1
