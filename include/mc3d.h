@@ -99,7 +99,9 @@ int mc3d_triangulate_f32(const float *d_kpts, int64_t n, const mc3d_rig *rig, in
 int mc3d_triangulate_f64(const double *d_kpts, int64_t n, const mc3d_rig *rig, int layout, int mode,
                          int flags, double *d_out, void *stream);
 
+#ifndef MC3D_TRI_MAX_START
 #define MC3D_TRI_MAX_START 4
+#endif
 /* Starting-point plan of the float-storage kernel (host-only, no device work): up to MC3D_TRI_MAX_START pairs of views (A, B)
  * -- widest angle first, sharing no view with the earlier pairs while the rig allows it; a joint starts from the first pair
  * whose two views it sees -- whose
