@@ -370,7 +370,7 @@ __device__ __forceinline__ void pair_start(const mc3d_tri_start_pair *pc, int va
 // All NJ = 2 NP joints of a thread (the solve runs on NP packed pairs).  state: 0 = Xo holds the result, 1 = the all-double solver has to take the joint.
 template <int V, int LAYOUT, int NP>
 __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const mc3d_tri_start_pair *__restrict__ pairs,
-                                            const int (&sv)[2 * MC3D_TRI_MAX_START], int n_pairs, float rig2, const float *const (&rows)[2 * NP],
+                                            const int2 sv, int n_pairs, float rig2, const float *const (&rows)[2 * NP],
                                             float (&Xo)[2 * NP][3], int (&state)[2 * NP]) {
     constexpr int NJ = 2 * NP;
     constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
@@ -386,20 +386,23 @@ __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const 
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 float s0, s1, s2, wm;
-                pair_start<V, LAYOUT>(&pairs[0], sv[0], sv[1], rows[j], s0, s1, s2, wm);
+                pair_start<V, LAYOUT>(&pairs[0], sv.x, sv.y, rows[j], s0, s1, s2, wm);
                 if (wm > 0.f && fmaf(s0, s0, fmaf(s1, s1, s2 * s2)) <= lim) { Xf[j][0] = s0; Xf[j][1] = s1; Xf[j][2] = s2; have[j] = true; }
             }
             // warp-uniform: clean input never evaluates the later pairs; a joint takes the first pair it sees with both views
+            // (the later pairs' views come from their shared-memory records: as a register array indexed in this loop they
+            // went to local memory, and the cascade -- which most warps run as soon as 1 % of the views are unusable -- waited on it)
 #pragma unroll 1
             for (int p = 1; p < n_pairs; ++p) {
                 bool all_have = true;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) all_have = all_have && have[j];
                 if (!__any_sync(0xffffffffu, !all_have)) break;
+                const int va = pairs[p].view_a, vb = pairs[p].view_b;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     float s0, s1, s2, wm;
-                    pair_start<V, LAYOUT>(&pairs[p], sv[2 * p], sv[2 * p + 1], rows[j], s0, s1, s2, wm);
+                    pair_start<V, LAYOUT>(&pairs[p], va, vb, rows[j], s0, s1, s2, wm);
                     if (!have[j] && wm > 0.f && fmaf(s0, s0, fmaf(s1, s1, s2 * s2)) <= lim) { Xf[j][0] = s0; Xf[j][1] = s1; Xf[j][2] = s2; have[j] = true; }
                 }
             }
@@ -628,9 +631,7 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     src += src_step;
     const int n_pairs = prm.n_start;
     // views of the starting pairs straight from the parameter bank (uniform): no shared-memory load in front of the row loads
-    int sv[2 * MC3D_TRI_MAX_START];
-#pragma unroll
-    for (int q = 0; q < MC3D_TRI_MAX_START; ++q) { sv[2 * q] = prm.start[q].view_a; sv[2 * q + 1] = prm.start[q].view_b; }
+    const int2 sv = make_int2(prm.start[0].view_a, prm.start[0].view_b);
     for (unsigned k = 0; k < my_tiles; ++k) {
         const uint32_t b = k & 1u;                    // output buffer; input stage when there are two
         const uint32_t sb = NST == 2 ? b : 0u;
