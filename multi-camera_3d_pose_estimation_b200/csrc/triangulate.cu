@@ -370,7 +370,7 @@ __device__ __forceinline__ void pair_start(const mc3d_tri_start_pair *pc, int va
 // All NJ = 2 NP joints of a thread (the solve runs on NP packed pairs).  state: 0 = Xo holds the result, 1 = the all-double solver has to take the joint.
 template <int V, int LAYOUT, int NP>
 __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const mc3d_tri_start_pair *__restrict__ pairs,
-                                            const int2 sv, int n_pairs, float rig2, const float *const (&rows)[2 * NP],
+                                            const int4 sv, int n_pairs, float rig2, const float *const (&rows)[2 * NP],
                                             float (&Xo)[2 * NP][3], int (&state)[2 * NP]) {
     constexpr int NJ = 2 * NP;
     constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
@@ -398,7 +398,8 @@ __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const 
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) all_have = all_have && have[j];
                 if (!__any_sync(0xffffffffu, !all_have)) break;
-                const int va = pairs[p].view_a, vb = pairs[p].view_b;
+                // (pair 1 -- the one most warps reach -- has its views in registers like pair 0)
+                const int va = p == 1 ? sv.z : pairs[p].view_a, vb = p == 1 ? sv.w : pairs[p].view_b;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     float s0, s1, s2, wm;
@@ -631,7 +632,7 @@ triangulate_mixed_kernel(const float *__restrict__ kpts, float *__restrict__ out
     src += src_step;
     const int n_pairs = prm.n_start;
     // views of the starting pairs straight from the parameter bank (uniform): no shared-memory load in front of the row loads
-    const int2 sv = make_int2(prm.start[0].view_a, prm.start[0].view_b);
+    const int4 sv = make_int4(prm.start[0].view_a, prm.start[0].view_b, prm.start[1].view_a, prm.start[1].view_b);
     for (unsigned k = 0; k < my_tiles; ++k) {
         const uint32_t b = k & 1u;                    // output buffer; input stage when there are two
         const uint32_t sb = NST == 2 ? b : 0u;
