@@ -402,6 +402,7 @@ __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const 
                 const int va = p == 1 ? sv.z : pairs[p].view_a, vb = p == 1 ? sv.w : pairs[p].view_b;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
+                    if (!__any_sync(0xffffffffu, !have[j])) continue;   // this half of the tile has all its starts
                     float s0, s1, s2, wm;
                     pair_start<V, LAYOUT>(&pairs[p], va, vb, rows[j], s0, s1, s2, wm);
                     if (!have[j] && wm > 0.f && fmaf(s0, s0, fmaf(s1, s1, s2 * s2)) <= lim) { Xf[j][0] = s0; Xf[j][1] = s1; Xf[j][2] = s2; have[j] = true; }
