@@ -375,6 +375,9 @@ __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const 
     constexpr int NJ = 2 * NP;
     constexpr int G = (V % 4 == 0) ? 4 : V;                     // views per load group
     double Xd[NJ][3];                                           // float-valued in the first pass
+    bool own[NJ];                                               // started from its own first two usable views (below)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) own[j] = false;
     // ---- start ---------------------------------------------------------------------------------------------------
     {
         const float lim = 1.0e4f * (rig2 + 1.f);                // a start farther out than 100 rig radii is not one
@@ -406,6 +409,51 @@ __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const 
                     float s0, s1, s2, wm;
                     pair_start<V, LAYOUT>(&pairs[p], va, vb, rows[j], s0, s1, s2, wm);
                     if (!have[j] && wm > 0.f && fmaf(s0, s0, fmaf(s1, s1, s2 * s2)) <= lim) { Xf[j][0] = s0; Xf[j][1] = s1; Xf[j][2] = s2; have[j] = true; }
+                }
+            }
+        }
+        // A joint that sees none of the planned pairs with both views (typically one left with two or three usable views)
+        // would start from the origin, and the residual there trips the rounding guard: ~1 000 warp-instructions in the all-
+        // double solver for what is an ordinary two-view point.  It gets a two-view start from its OWN first two usable views
+        // instead: the weighted normal equations of their four rows in double (3 x 3, LDL^T) -- for a joint with exactly two
+        // usable views that is the answer up to the eigenvalue term.  Such a joint keeps its float result only when those
+        // views are well apart (tr / pivot <= 100 below, at least as strict as a pivot above 1 % of its diagonal): with two
+        // nearly opposite views the float correction is off by up to 3e-3 mm, and those go to the double solver as before.
+        if constexpr (V <= 8) {                                    // (sixteen views: the instantiation would spill at 128 registers)
+            bool all_have = true;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) all_have = all_have && have[j];
+            if (__any_sync(0xffffffffu, !all_have)) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    if (have[j]) continue;
+                    double m00 = 0.0, m10 = 0.0, m11 = 0.0, m20 = 0.0, m21 = 0.0, m22 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+                    int cnt = 0;
+#pragma unroll 1
+                    for (int v = 0; v < V && cnt < 2; ++v) {
+                        float x, y, w;
+                        load_view<V, LAYOUT>(rows[j], v, x, y, w);
+                        if (!(w > 0.f)) continue;
+                        const double *Pv = cam[v].P;
+                        const double xd = (double)x, yd = (double)y, wd = (double)w;
+                        double rc[4], ra[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            rc[k] = wd * fma(-xd, Pv[8 + k], Pv[k]);         // w (P0 - x P2)
+                            ra[k] = wd * fma(yd, Pv[8 + k], -Pv[4 + k]);     // w (y P2 - P1)
+                        }
+                        m00 = fma(rc[0], rc[0], fma(ra[0], ra[0], m00)); m10 = fma(rc[1], rc[0], fma(ra[1], ra[0], m10));
+                        m11 = fma(rc[1], rc[1], fma(ra[1], ra[1], m11)); m20 = fma(rc[2], rc[0], fma(ra[2], ra[0], m20));
+                        m21 = fma(rc[2], rc[1], fma(ra[2], ra[1], m21)); m22 = fma(rc[2], rc[2], fma(ra[2], ra[2], m22));
+                        b0 = fma(rc[0], rc[3], fma(ra[0], ra[3], b0)); b1 = fma(rc[1], rc[3], fma(ra[1], ra[3], b1));
+                        b2 = fma(rc[2], rc[3], fma(ra[2], ra[3], b2));
+                        ++cnt;
+                    }
+                    double z0, z1, z2, dmin;
+                    if (cnt == 2 && ldl3_solve(m00, m10, m11, m20, m21, m22, -b0, -b1, -b2, z0, z1, z2, dmin)) {
+                        const float f0 = (float)z0, f1 = (float)z1, f2 = (float)z2;
+                        if (fmaf(f0, f0, fmaf(f1, f1, f2 * f2)) <= lim) { Xf[j][0] = f0; Xf[j][1] = f1; Xf[j][2] = f2; own[j] = true; }
+                    }
                 }
             }
         }
@@ -515,12 +563,14 @@ __device__ __forceinline__ void solve_mixed(const CamF *__restrict__ cam, const 
             // times 1 / (smallest pivot), whatever the size of e -- no further pass can repair it, the double solver has to
             const float2 gn2 = __fmul2_rn(__fmul2_rn(rs, kap), make_float2(imax[0], imax[1]));   // |r|^2 tr / pivot^2
             const float ne[2] = {ne2.x, ne2.y}, nk[2] = {nk2.x, nk2.y}, gn[2] = {gn2.x, gn2.y}, lam[2] = {lam2.x, lam2.y}, lim[2] = {lim2.x, lim2.y};
+            const float kp[2] = {kap.x, kap.y};
             const float es[2][3] = {{e0.x, e1.x, e2.x}, {e0.y, e1.y, e2.y}};
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int j = 2 * q + jj;
                 if (state[j] != 2) continue;
-                if (!ok[jj] || !(ne[jj] <= 3.0e38f) || !(fabsf(lam[jj]) * imax[jj] <= 3.0e-5f) || !(gn[jj] <= lim[jj])) { state[j] = 1; continue; }
+                if (!ok[jj] || !(ne[jj] <= 3.0e38f) || !(fabsf(lam[jj]) * imax[jj] <= 3.0e-5f) || !(gn[jj] <= lim[jj]) ||
+                    (own[j] && !(kp[jj] <= 100.f))) { state[j] = 1; continue; }
                 if (nk[jj] <= lim[jj]) {
                     if (it == 0) {                                   // Xd is float-valued: float(Xd + e) is one float addition
                         Xo[j][0] = Xf[jj][0] + es[jj][0]; Xo[j][1] = Xf[jj][1] + es[jj][1]; Xo[j][2] = Xf[jj][2] + es[jj][2];
