@@ -198,6 +198,31 @@ def test_fp32_starting_subset_views_missing_or_wild(tri, syn):
     assert err.max() < FP32_ATOL_MM, (err.max(), int(err.argmax()))
 
 
+@pytest.mark.parametrize('frac', [0.05, 0.2, 0.5])
+def test_fp32_random_unusable_views_agree_with_all_double_solver(tri, syn, frac):
+    """A fraction of ALL views unusable (weight 0, wild pixel), at random: joints go through the cascade of planned start pairs,
+    the start from their own first two usable views (two or three views left) and, with nearly collinear rays, the double
+    fallback.  Same NaN pattern as the all-double solver (fewer than two usable views -> NaN) and within the float32 bar."""
+    import torch
+    from mc3d_b200 import _lib
+    n = 1_500_000
+    kp, P, _, _ = syn.multiview_points(n, 8, seed=91)
+    kp32 = torch.tensor(kp.astype(np.float32), device='cuda:0')
+    gen = torch.Generator(device='cuda:0').manual_seed(int(frac * 100))
+    bad = torch.rand((n, 8), device='cuda:0', generator=gen) < frac
+    kp32[..., 2][bad] = 0.0
+    kp32[..., 0][bad] = 5000.0 * torch.rand((int(bad.sum()),), device='cuda:0', generator=gen)
+    kp32[..., 1][bad] = 5000.0 * torch.rand((int(bad.sum()),), device='cuda:0', generator=gen)
+    got = tri(kp32, P)
+    ref = tri(kp32, P, flags=_lib.TRI_FLAG_FP64)
+    assert bool((torch.isnan(got) == torch.isnan(ref)).all())
+    ok = torch.isfinite(ref).all(dim=1)
+    n_views = (kp32[..., 2] > 0).sum(dim=1)
+    assert bool((ok == (n_views >= 2))[n_views != 2].all())          # (two views can still be refused as collinear)
+    err = (got[ok].double() - ref[ok].double()).norm(dim=1)
+    assert float(err.max()) < FP32_ATOL_MM, float(err.max())
+
+
 def test_fp32_points_near_world_origin(tri, syn):
     rng = np.random.default_rng(34)
     cams = syn.ring_rig(8, centre=(0.0, 0.0, 0.0))
